@@ -1,0 +1,94 @@
+"""ctypes binding of include/wealy_b200.h.  No torch types cross this boundary: only raw device
+pointers (tensor.data_ptr()), sizes and the current CUDA stream handle."""
+import ctypes
+import os
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libwealy_b200.so")
+
+if not os.path.isfile(_LIB_PATH):
+    raise ImportError(
+        f"{_LIB_PATH} is missing: the CUDA extension has not been built. Run "
+        "`python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback).")
+
+lib = ctypes.CDLL(_LIB_PATH)
+
+OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_ID_RANGE = range(6)
+F32, F16, BF16 = 0, 1, 2
+MODE_COSSIM, MODE_COS, MODE_DOTSIM, MODE_DOT, MODE_SQEUC, MODE_EUC = range(6)
+LOSS_NTXENT, LOSS_CLEWS = 0, 1
+OUT_COUNT = 16
+
+c_i64, c_int, c_f32, c_vp, c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+
+class LossCfg(ctypes.Structure):
+    _fields_ = [("kind", c_int), ("passes", c_int), ("temperature", c_f32), ("gamma", c_f32), ("b", c_f32),
+                ("eps", c_f32), ("epsilon", c_f32), ("uw", c_f32), ("numerically_friendly", c_int)]
+
+
+# every symbol include/wealy_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "wealy_last_error": (ctypes.c_char_p, []),
+    "wealy_version": (c_int, []),
+    "wealy_sim_matrix_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
+    "wealy_sim_matrix": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_f32, c_f32, c_int,
+                                 c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
+    "wealy_eval_plan_create": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, ctypes.POINTER(c_vp)]),
+    "wealy_eval_plan_info": (c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
+    "wealy_eval_run": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_vp,
+                               c_vp, c_vp, c_vp]),
+    "wealy_eval_plan_destroy": (None, [c_vp]),
+    "wealy_loss_workspace_bytes": (c_sz, [c_i64, c_i64, c_int]),
+    "wealy_loss_forward": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp,
+                                   c_sz, c_vp]),
+    "wealy_loss_backward": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_i64,
+                                    c_vp, c_sz, c_vp]),
+}
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here == a declared symbol is not exported
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class WealyError(RuntimeError):
+    pass
+
+
+def last_error():
+    msg = lib.wealy_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(status):
+    """Map C status codes onto the exception types the reference raises."""
+    if status == OK:
+        return
+    msg = last_error()
+    if status == ERR_BAD_ARG:
+        raise AssertionError(msg)
+    if status == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if status == ERR_ID_RANGE:
+        raise ValueError(msg)
+    raise WealyError(f"wealy_b200 native call failed (status {status}): {msg}")
+
+
+def dtype_code(t):
+    import torch
+    try:
+        return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}[t]
+    except KeyError:
+        raise NotImplementedError(f"wealy_b200: dtype {t} is not supported by the CUDA path "
+                                  "(float32 / float16 / bfloat16 only)") from None
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("wealy_b200 computes on CUDA only (no CPU fallback): got a tensor on "
+                               f"{t.device}; move it with .cuda() first")
+
+
+def stream_ptr(device):
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,498 @@
+// C-ABI entry points (include/wealy_b200.h) and host-side launch logic.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "../../include/wealy_b200.h"
+#include "epilogues.cuh"
+#include "eval_kernels.cuh"
+#include "loss_kernels.cuh"
+#include "prep.cuh"
+
+using namespace wealy;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                     \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) return fail(WEALY_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                              \
+  } while (0)
+
+#define W_TRY(expr)            \
+  do {                         \
+    int _s = (expr);           \
+    if (_s != WEALY_OK) return _s; \
+  } while (0)
+
+extern "C" const char* wealy_last_error(void) { return g_err; }
+extern "C" int wealy_version(void) { return 100; }
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+static int num_sms() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    if (cached <= 0) cached = 148;
+  }
+  return cached;
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA descriptors (driver entry point fetched through the runtime: no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 plane [rows][d_pad] row-major; box = [box_rows][block_k] with (2 * block_k)-byte swizzle
+static int make_plane_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t d_pad, int box_rows, int block_k) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(WEALY_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(WEALY_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return WEALY_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// operand planes
+// ------------------------------------------------------------------------------------------
+struct Planes {
+  __half* hi = nullptr;
+  __half* lo = nullptr;    // null in single-pass mode
+  float* norm = nullptr;   // raw L2 norm per row
+  float* scale = nullptr;  // epilogue row factor (power of two in RAW mode, 1 otherwise)
+  float* sq = nullptr;     // squared L2 norm per row
+  int64_t rows = 0;
+  int64_t d_pad = 0;
+};
+
+static int64_t pad_k(int64_t d) { return ceil_div(d, 64) * 64; }
+
+static size_t planes_bytes(int64_t rows, int64_t d, int passes) {
+  const size_t plane = align_up((size_t)rows * pad_k(d) * 2, 1024);
+  return plane * (passes == 3 ? 2 : 1) + 3 * align_up((size_t)rows * 4, 256);
+}
+
+// carve planes out of a workspace cursor
+static void carve_planes(Planes& p, uint8_t*& cur, int64_t rows, int64_t d, int passes) {
+  const size_t plane = align_up((size_t)rows * pad_k(d) * 2, 1024);
+  p.rows = rows;
+  p.d_pad = pad_k(d);
+  p.hi = reinterpret_cast<__half*>(cur); cur += plane;
+  p.lo = nullptr;
+  if (passes == 3) { p.lo = reinterpret_cast<__half*>(cur); cur += plane; }
+  const size_t vec = align_up((size_t)rows * 4, 256);
+  p.norm = reinterpret_cast<float*>(cur); cur += vec;
+  p.scale = reinterpret_cast<float*>(cur); cur += vec;
+  p.sq = reinterpret_cast<float*>(cur); cur += vec;
+}
+
+static int launch_prep(const void* x, int64_t ld, int64_t n, int64_t d, int dtype, int mode, float eps,
+                       const Planes& p, __half* hi_t, __half* lo_t, int64_t ld_t, ZStats* stats, int stats_on_scaled,
+                       cudaStream_t s) {
+  if (n == 0) return WEALY_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)ceil_div(n * 32, threads);
+#define PREP_ARGS (long long)ld, (int)n, (int)d, (int)p.d_pad, mode, eps, stats_on_scaled, p.hi, p.lo, hi_t, lo_t, \
+                  (long long)ld_t, p.norm, p.scale, p.sq, stats
+  switch (dtype) {
+    case WEALY_F32: prep_rows_kernel<float><<<blocks, threads, 0, s>>>((const float*)x, PREP_ARGS); break;
+    case WEALY_F16: prep_rows_kernel<__half><<<blocks, threads, 0, s>>>((const __half*)x, PREP_ARGS); break;
+    case WEALY_BF16: prep_rows_kernel<__nv_bfloat16><<<blocks, threads, 0, s>>>((const __nv_bfloat16*)x, PREP_ARGS); break;
+    default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
+  }
+#undef PREP_ARGS
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// contraction launcher
+// ------------------------------------------------------------------------------------------
+static void fill_shape(GemmShape& sh, int64_t m, int64_t n, int64_t d_pad, int block_k, int max_chunks) {
+  sh.m_rows = (int)m;
+  sh.n_cols = (int)n;
+  sh.k_blocks = (int)(d_pad / block_k);
+  sh.n_row_blocks = (int)ceil_div(m, kTileM);
+  sh.n_col_tiles = (int)ceil_div(n, kTileN);
+  // enough units for ~16 rounds of the persistent grid (tail quantisation < 4 %), but never more
+  // chunks than column tiles; CTAs resident together sweep the same chunk (L2 reuse of candidates)
+  const int64_t target_units = (int64_t)num_sms() * env_int("WEALY_ROUNDS", 16);
+  int64_t chunks = ceil_div(target_units, sh.n_row_blocks > 0 ? sh.n_row_blocks : 1);
+  if (chunks > sh.n_col_tiles) chunks = sh.n_col_tiles;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  sh.tiles_per_chunk = (int)ceil_div(sh.n_col_tiles, chunks);
+  if (sh.tiles_per_chunk < 1) sh.tiles_per_chunk = 1;
+  sh.n_col_chunks = (int)ceil_div(sh.n_col_tiles, sh.tiles_per_chunk);
+  if (sh.n_col_chunks < 1) sh.n_col_chunks = 1;
+}
+
+template <class Epi, int kPasses, int kBlockK, int kEpiWarps>
+static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, const typename Epi::Params& ep,
+                         cudaStream_t s) {
+  using SM = GemmSmem<kPasses, kBlockK>;
+  GemmTmaps maps;
+  memset(&maps, 0, sizeof(maps));
+  W_TRY(make_plane_tmap(&maps.a_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK));
+  W_TRY(make_plane_tmap(&maps.b_hi, b.hi, b.rows, b.d_pad, kTileN, kBlockK));
+  if (kPasses == 3) {
+    W_TRY(make_plane_tmap(&maps.a_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK));
+    W_TRY(make_plane_tmap(&maps.b_lo, b.lo, b.rows, b.d_pad, kTileN, kBlockK));
+  } else {
+    maps.a_lo = maps.a_hi;
+    maps.b_lo = maps.b_hi;
+  }
+  auto kern = gemm_kernel<Epi, kPasses, kBlockK, kEpiWarps>;
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+  const int n_units = sh.n_row_blocks * sh.n_col_chunks;
+  if (n_units == 0) return WEALY_OK;
+  const int grid = n_units < num_sms() ? n_units : num_sms();
+  kern<<<grid, 64 + kEpiWarps * 32, SM::kTotal, s>>>(maps, sh, ep);
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+template <class Epi>
+static int launch_gemm(int passes, const Planes& a, const Planes& b, GemmShape& sh, const typename Epi::Params& ep,
+                       cudaStream_t s) {
+  const int bk = env_int("WEALY_BLOCK_K", 64);
+  if (passes == 3) {
+    if (a.lo == nullptr || b.lo == nullptr) return fail(WEALY_ERR_BAD_ARG, "3-pass contraction needs lo planes");
+    if (bk == 32) {
+      sh.k_blocks = (int)(a.d_pad / 32);
+      return launch_gemm_t<Epi, 3, 32, 4>(a, b, sh, ep, s);
+    }
+    return launch_gemm_t<Epi, 3, 64, 4>(a, b, sh, ep, s);
+  }
+  if (passes == 1) return launch_gemm_t<Epi, 1, 64, 8>(a, b, sh, ep, s);
+  return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3, got %d", passes);
+}
+
+// ------------------------------------------------------------------------------------------
+// a1 / a2: materialised matrix
+// ------------------------------------------------------------------------------------------
+extern "C" size_t wealy_sim_matrix_workspace_bytes(int64_t n, int64_t m, int64_t d, int passes) {
+  if (n < 0 || m < 0 || d <= 0) return 0;
+  return planes_bytes(n, d, passes) + planes_bytes(m, d, passes) + 4096;
+}
+
+extern "C" int wealy_sim_matrix(const void* x, int64_t n, int64_t ldx, const void* y, int64_t m, int64_t ldy,
+                                int64_t d, int in_dtype, int mode, float eps, float post, int passes, void* out,
+                                int64_t ld_out, int out_dtype, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n < 0 || m < 0 || d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad shape n=%lld m=%lld d=%lld", (long long)n, (long long)m, (long long)d);
+  if (n == 0 || m == 0) return WEALY_OK;
+  if (!x || !y || !out || !workspace) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (mode < WEALY_MODE_COSSIM || mode > WEALY_MODE_EUC) return fail(WEALY_ERR_BAD_ARG, "unknown mode %d", mode);
+  if (passes != 1 && passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
+  if (n >= (1ll << 31) - 256 || m >= (1ll << 31) - 256) return fail(WEALY_ERR_UNSUPPORTED, "more than 2^31 rows");
+  if (workspace_bytes < wealy_sim_matrix_workspace_bytes(n, m, d, passes))
+    return fail(WEALY_ERR_WORKSPACE, "workspace too small: %zu < %zu", workspace_bytes,
+                wealy_sim_matrix_workspace_bytes(n, m, d, passes));
+  uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024));
+  Planes px, py;
+  carve_planes(px, cur, n, d, passes);
+  const bool same = (x == y && n == m && ldx == ldy);
+  if (same) py = px; else carve_planes(py, cur, m, d, passes);
+  const bool cosine = (mode == WEALY_MODE_COSSIM || mode == WEALY_MODE_COS);
+  const int pmode = cosine ? kPrepL2AddEps : kPrepRawPow2;
+  W_TRY(launch_prep(x, ldx, n, d, in_dtype, pmode, eps, px, nullptr, nullptr, 0, nullptr, 0, s));
+  if (!same) W_TRY(launch_prep(y, ldy, m, d, in_dtype, pmode, eps, py, nullptr, nullptr, 0, nullptr, 0, s));
+
+  StoreParams sp;
+  sp.out = out;
+  sp.ld = ld_out;
+  sp.mode = mode;
+  sp.out_dtype = out_dtype;
+  sp.post = post;
+  sp.rscale = cosine ? nullptr : px.scale;
+  sp.cscale = cosine ? nullptr : py.scale;
+  sp.rsq = px.sq;
+  sp.csq = py.sq;
+  GemmShape sh;
+  fill_shape(sh, n, m, px.d_pad, 64, 1 << 20);
+  return launch_gemm<StoreEpi>(passes, px, py, sh, sp, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// a7: evaluation plan + run
+// ------------------------------------------------------------------------------------------
+struct wealy_eval_plan {
+  int64_t nq = 0, nc = 0;
+  bool same_ids = false;
+  int *q_c = nullptr, *q_i = nullptr, *c_c = nullptr, *c_i = nullptr;
+  int *sorted_c = nullptr, *sorted_idx = nullptr;
+  int *seg_lo = nullptr, *seg_len = nullptr, *npos = nullptr;
+  long long* off = nullptr;  // [nq + 1]
+  int64_t total_pairs = 0, no_relevant = 0, max_relevant = 0;
+  // scratch that depends on ids only
+  float *raw = nullptr, *thr = nullptr, *lim = nullptr;
+  int* cnt = nullptr;
+  unsigned int* hist = nullptr;
+  // embedding-dependent scratch, (re)allocated when the shape grows
+  void* planes_buf = nullptr;
+  size_t planes_cap = 0;
+  void* topk_buf = nullptr;
+  size_t topk_cap = 0;
+};
+
+extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
+  if (!p) return;
+  void* ptrs[] = {p->q_c, p->q_i, p->sorted_c, p->sorted_idx, p->seg_lo, p->seg_len, p->npos, p->off,
+                  p->raw, p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  if (!p->same_ids) {
+    if (p->c_c) cudaFree(p->c_c);
+    if (p->c_i) cudaFree(p->c_i);
+  }
+  delete p;
+}
+
+static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_t* queries_i,
+                      const int64_t* candidates_c, const int64_t* candidates_i, cudaStream_t s) {
+  const int nq = (int)p->nq, nc = (int)p->nc;
+  const int T = 256;
+  int* bad = nullptr;
+  unsigned long long* totals = nullptr;
+  CU_TRY(cudaMalloc(&bad, 256));
+  totals = reinterpret_cast<unsigned long long*>(bad + 16);
+  CU_TRY(cudaMemsetAsync(bad, 0, 256, s));
+  CU_TRY(cudaMalloc(&p->q_c, (size_t)nq * 4 + 4));
+  CU_TRY(cudaMalloc(&p->q_i, (size_t)nq * 4 + 4));
+  ids_to_i32_kernel<<<(unsigned)ceil_div(nq, T), T, 0, s>>>((const long long*)queries_c, p->q_c, nq, bad);
+  ids_to_i32_kernel<<<(unsigned)ceil_div(nq, T), T, 0, s>>>((const long long*)queries_i, p->q_i, nq, bad);
+  p->same_ids = (queries_c == candidates_c && queries_i == candidates_i && p->nq == p->nc);
+  if (p->same_ids) {
+    p->c_c = p->q_c;
+    p->c_i = p->q_i;
+  } else {
+    CU_TRY(cudaMalloc(&p->c_c, (size_t)nc * 4 + 4));
+    CU_TRY(cudaMalloc(&p->c_i, (size_t)nc * 4 + 4));
+    ids_to_i32_kernel<<<(unsigned)ceil_div(nc, T), T, 0, s>>>((const long long*)candidates_c, p->c_c, nc, bad);
+    ids_to_i32_kernel<<<(unsigned)ceil_div(nc, T), T, 0, s>>>((const long long*)candidates_i, p->c_i, nc, bad);
+  }
+  CU_TRY(cudaGetLastError());
+
+  // candidates sorted by clique id (CUB radix sort: id-only preprocessing, not on the per-eval path)
+  int* iota = nullptr;
+  CU_TRY(cudaMalloc(&iota, (size_t)nc * 4 + 4));
+  CU_TRY(cudaMalloc(&p->sorted_c, (size_t)nc * 4 + 4));
+  CU_TRY(cudaMalloc(&p->sorted_idx, (size_t)nc * 4 + 4));
+  iota_kernel<<<(unsigned)ceil_div(nc, T), T, 0, s>>>(iota, nc);
+  size_t tmp_bytes = 0;
+  CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, p->c_c, p->sorted_c, iota, p->sorted_idx, nc, 0, 32, s));
+  void* tmp = nullptr;
+  CU_TRY(cudaMalloc(&tmp, tmp_bytes + 16));
+  CU_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p->c_c, p->sorted_c, iota, p->sorted_idx, nc, 0, 32, s));
+
+  CU_TRY(cudaMalloc(&p->seg_lo, (size_t)nq * 4 + 4));
+  CU_TRY(cudaMalloc(&p->seg_len, (size_t)nq * 4 + 4));
+  CU_TRY(cudaMalloc(&p->npos, (size_t)nq * 4 + 4));
+  CU_TRY(cudaMalloc(&p->off, ((size_t)nq + 1) * 8));
+  segment_lookup_kernel<<<(unsigned)ceil_div(nq, T), T, 0, s>>>(p->q_c, p->q_i, nq, p->sorted_c, p->sorted_idx, p->c_i,
+                                                               nc, p->seg_lo, p->seg_len, p->npos, totals);
+  CU_TRY(cudaGetLastError());
+  // CSR offsets over the per-query number of relevant candidates
+  size_t scan_bytes = 0;
+  CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, p->npos, p->off, nq + 1, s));
+  void* tmp2 = nullptr;
+  CU_TRY(cudaMalloc(&tmp2, scan_bytes + 16));
+  // npos has nq valid entries; entry nq is read by the scan of nq+1 items -> zero it first
+  CU_TRY(cudaMemsetAsync(p->npos + nq, 0, 4, s));
+  CU_TRY(cub::DeviceScan::ExclusiveSum(tmp2, scan_bytes, p->npos, p->off, nq + 1, s));
+
+  int bad_h[16];
+  unsigned long long totals_h[2];
+  long long total = 0;
+  CU_TRY(cudaMemcpyAsync(bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(totals_h, totals, sizeof(totals_h), cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaMemcpyAsync(&total, p->off + nq, 8, cudaMemcpyDeviceToHost, s));
+  CU_TRY(cudaStreamSynchronize(s));
+  cudaFree(tmp);
+  cudaFree(tmp2);
+  cudaFree(iota);
+  cudaFree(bad);
+  if (bad_h[0] != 0) return fail(WEALY_ERR_ID_RANGE, "%d clique/version ids do not fit in 32 bits", bad_h[0]);
+  p->total_pairs = total;
+  p->no_relevant = (int64_t)totals_h[0];
+  p->max_relevant = (int64_t)totals_h[1];
+  const size_t pairs = (size_t)(total > 0 ? total : 1);
+  CU_TRY(cudaMalloc(&p->raw, pairs * 4));
+  CU_TRY(cudaMalloc(&p->thr, pairs * 4));
+  CU_TRY(cudaMalloc(&p->hist, pairs * 4));
+  CU_TRY(cudaMalloc(&p->lim, (size_t)nq * 4 + 4));
+  CU_TRY(cudaMalloc(&p->cnt, (size_t)nq * 4 + 4));
+  return WEALY_OK;
+}
+
+extern "C" int wealy_eval_plan_create(const int64_t* queries_c, const int64_t* queries_i, int64_t nq,
+                                      const int64_t* candidates_c, const int64_t* candidates_i, int64_t nc,
+                                      void* stream, wealy_eval_plan** plan) {
+  if (!plan) return fail(WEALY_ERR_BAD_ARG, "plan output pointer is null");
+  *plan = nullptr;
+  if (nq <= 0 || nc <= 0) return fail(WEALY_ERR_BAD_ARG, "empty query or candidate set (nq=%lld nc=%lld)", (long long)nq, (long long)nc);
+  if (!queries_c || !queries_i || !candidates_c || !candidates_i) return fail(WEALY_ERR_BAD_ARG, "null id pointer");
+  if (nq >= (1ll << 31) - 256 || nc >= (1ll << 31) - 256) return fail(WEALY_ERR_UNSUPPORTED, "more than 2^31 rows");
+  wealy_eval_plan* p = new wealy_eval_plan();
+  p->nq = nq;
+  p->nc = nc;
+  int st = plan_build(p, queries_c, queries_i, candidates_c, candidates_i, (cudaStream_t)stream);
+  if (st != WEALY_OK) {
+    wealy_eval_plan_destroy(p);
+    return st;
+  }
+  *plan = p;
+  return WEALY_OK;
+}
+
+extern "C" int wealy_eval_plan_info(const wealy_eval_plan* p, int64_t* total_pairs, int64_t* queries_without_relevant,
+                                    int64_t* max_relevant) {
+  if (!p) return fail(WEALY_ERR_BAD_ARG, "null plan");
+  if (total_pairs) *total_pairs = p->total_pairs;
+  if (queries_without_relevant) *queries_without_relevant = p->no_relevant;
+  if (max_relevant) *max_relevant = p->max_relevant;
+  return WEALY_OK;
+}
+
+static int topk_capacity(int k) { return (int)align_up((size_t)k + 96, 32); }
+
+extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
+                              int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,
+                              float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!p) return fail(WEALY_ERR_BAD_ARG, "null plan");
+  if (!queries_z || !candidates_z || !aps || !r1s || !sums) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad embedding size %lld", (long long)d);
+  if (passes != 1 && passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
+  if (topk < 0 || topk > 900) return fail(WEALY_ERR_UNSUPPORTED, "topk must be in [0, 900], got %d", topk);
+  if (topk > 0 && (!topk_idx || !topk_sim)) return fail(WEALY_ERR_BAD_ARG, "topk outputs are null");
+  const int64_t nq = p->nq, nc = p->nc;
+  const bool same = (queries_z == candidates_z && nq == nc && ld_q == ld_c);
+
+  // operand planes (cached allocation)
+  const size_t need = planes_bytes(nq, d, passes) + (same ? 0 : planes_bytes(nc, d, passes)) + 2048;
+  if (need > p->planes_cap) {
+    if (p->planes_buf) CU_TRY(cudaFree(p->planes_buf));
+    p->planes_buf = nullptr;
+    p->planes_cap = 0;
+    CU_TRY(cudaMalloc(&p->planes_buf, need));
+    p->planes_cap = need;
+  }
+  uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)p->planes_buf, 1024));
+  Planes pq, pc;
+  carve_planes(pq, cur, nq, d, passes);
+  if (same) pc = pq; else carve_planes(pc, cur, nc, d, passes);
+  W_TRY(launch_prep(queries_z, ld_q, nq, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s));
+  if (!same) W_TRY(launch_prep(candidates_z, ld_c, nc, d, dtype, kPrepL2AddEps, eps, pc, nullptr, nullptr, 0, nullptr, 0, s));
+
+  // K_pos: relevant similarities, sorted per query
+  {
+    const int threads = 256;
+    const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
+    pos_thresholds_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, p->q_i, (int)nq,
+                                                     p->sorted_idx, p->c_i, p->seg_lo, p->seg_len, p->off, p->raw,
+                                                     p->thr, p->lim, p->cnt);
+    CU_TRY(cudaGetLastError());
+  }
+  CU_TRY(cudaMemsetAsync(p->hist, 0, (size_t)(p->total_pairs > 0 ? p->total_pairs : 1) * 4, s));
+  CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
+
+  GemmShape sh;
+  fill_shape(sh, nq, nc, pq.d_pad, 64, topk > 0 ? 8 : (1 << 20));
+  const int halves = passes == 1 ? 2 : 1;
+  const int parts = sh.n_col_chunks * halves;
+  const int cap = topk > 0 ? topk_capacity(topk) : 0;
+
+  EvalParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.lim = p->lim;
+  ep.q_c = p->q_c;
+  ep.q_i = p->q_i;
+  ep.c_c = p->c_c;
+  ep.c_i = p->c_i;
+  ep.thr = p->thr;
+  ep.off = p->off;
+  ep.cnt = p->cnt;
+  ep.hist = p->hist;
+  ep.topk = topk;
+  ep.cap = cap;
+  ep.nq_total = (int)nq;
+  if (topk > 0) {
+    const size_t slots = (size_t)parts * nq * cap;
+    const size_t tneed = slots * 8 + (size_t)parts * nq * 4 + 1024;
+    if (tneed > p->topk_cap) {
+      if (p->topk_buf) CU_TRY(cudaFree(p->topk_buf));
+      p->topk_buf = nullptr;
+      p->topk_cap = 0;
+      CU_TRY(cudaMalloc(&p->topk_buf, tneed));
+      p->topk_cap = tneed;
+    }
+    ep.cand_val = reinterpret_cast<float*>(p->topk_buf);
+    ep.cand_idx = reinterpret_cast<int*>(ep.cand_val + slots);
+    ep.cand_cnt = ep.cand_idx + slots;
+    CU_TRY(cudaMemsetAsync(ep.cand_cnt, 0, (size_t)parts * nq * 4, s));
+  }
+  W_TRY(launch_gemm<EvalEpi>(passes, pq, pc, sh, ep, s));
+
+  {
+    const int threads = 256;
+    const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
+    ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)nq, aps, r1s, sums);
+    CU_TRY(cudaGetLastError());
+    if (topk > 0) {
+      topk_finalize_kernel<<<blocks, threads, 0, s>>>(ep.cand_val, ep.cand_idx, ep.cand_cnt, parts, (int)nq, cap, topk,
+                                                      (long long*)topk_idx, topk_sim);
+      CU_TRY(cudaGetLastError());
+    }
+  }
+  return WEALY_OK;
+}
+
+#include "loss_api.inl"

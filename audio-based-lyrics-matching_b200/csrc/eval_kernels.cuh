@@ -1,0 +1,215 @@
+// Small kernels around the fused evaluation sweep (all HBM / latency bound, KB-MB of data):
+//   ids_to_i32       int64 ids -> int32 with range check
+//   segment_lookup   per query: its clique's segment in the clique-sorted candidate order
+//   pos_thresholds   K_pos: relevant similarities of every query, sorted ascending (CSR)
+//   ap_reduce        K2: rank counts -> AP, R1 per query (+ running sums for MAP / MR1)
+//   topk_finalize    K3: merge the per-part candidate buffers into the final top-k
+#pragma once
+#include <cuda_fp16.h>
+
+#include "prep.cuh"
+
+namespace wealy {
+
+__global__ void ids_to_i32_kernel(const long long* __restrict__ in, int* __restrict__ out, int n, int* bad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long v = in[t];
+  if (v > 2147483647ll || v < -2147483648ll) atomicAdd(bad, 1);
+  out[t] = (int)v;
+}
+
+__global__ void iota_kernel(int* out, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = t;
+}
+
+// sorted_c: candidate clique ids ascending; sorted_idx: candidate index at each sorted position.
+// For every query: [seg_lo, seg_lo + seg_len) = candidates of its clique, npos = those whose version id
+// differs from the query's (lib/losses.py:40-42: positives = same label & different idx).
+__global__ void segment_lookup_kernel(const int* __restrict__ q_c, const int* __restrict__ q_i, int nq,
+                                      const int* __restrict__ sorted_c, const int* __restrict__ sorted_idx,
+                                      const int* __restrict__ c_i, int nc, int* __restrict__ seg_lo,
+                                      int* __restrict__ seg_len, int* __restrict__ npos,
+                                      unsigned long long* __restrict__ totals /*[0]=queries w/o positives,[1]=max P*/) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  const int key = q_c[q];
+  int lo = 0, hi = nc;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sorted_c[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  const int first = lo;
+  hi = nc;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sorted_c[mid] <= key) lo = mid + 1; else hi = mid;
+  }
+  const int len = lo - first;
+  const int qi = q_i[q];
+  int np = 0;
+  for (int m = 0; m < len; ++m) np += (c_i[sorted_idx[first + m]] != qi);
+  seg_lo[q] = first;
+  seg_len[q] = len;
+  npos[q] = np;
+  if (np == 0) atomicAdd(&totals[0], 1ull);
+  atomicMax(&totals[1], (unsigned long long)np);
+}
+
+// K_pos.  One warp per query.  Similarities are computed from the SAME fp16 planes the tensor-core
+// sweep consumes (hi*hi [+ hi*lo + lo*hi]) so thresholds and swept similarities agree to fp32
+// accumulation noise; then rank-sorted ascending inside the warp (P_q is small: median 4, max ~360).
+__global__ void __launch_bounds__(256) pos_thresholds_kernel(
+    const __half* __restrict__ q_hi, const __half* __restrict__ q_lo, const __half* __restrict__ c_hi,
+    const __half* __restrict__ c_lo, int d_pad, const int* __restrict__ q_i, int nq,
+    const int* __restrict__ sorted_idx, const int* __restrict__ c_i, const int* __restrict__ seg_lo,
+    const int* __restrict__ seg_len, const long long* __restrict__ off, float* __restrict__ raw,
+    float* __restrict__ thr, float* __restrict__ lim, int* __restrict__ cnt) {
+  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (q >= nq) return;
+  const int first = seg_lo[q], len = seg_len[q], qi = q_i[q];
+  const long long o = off[q];
+  const uint4* qh = reinterpret_cast<const uint4*>(q_hi + (long long)q * d_pad);
+  const uint4* ql = q_lo ? reinterpret_cast<const uint4*>(q_lo + (long long)q * d_pad) : nullptr;
+  const int nvec = d_pad >> 3;  // 8 halves per 16-byte vector; d_pad is a multiple of 64
+  int n = 0;
+  for (int m = 0; m < len; ++m) {
+    const int j = sorted_idx[first + m];
+    if (c_i[j] == qi) continue;  // self / id collision
+    const uint4* ch = reinterpret_cast<const uint4*>(c_hi + (long long)j * d_pad);
+    const uint4* cl = c_lo ? reinterpret_cast<const uint4*>(c_lo + (long long)j * d_pad) : nullptr;
+    float acc = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 a = qh[v], b = ch[v];
+      const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+      const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+      uint4 al = make_uint4(0, 0, 0, 0), bl = make_uint4(0, 0, 0, 0);
+      if (ql) { al = ql[v]; bl = cl[v]; }
+      const __half2* al2 = reinterpret_cast<const __half2*>(&al);
+      const __half2* bl2 = reinterpret_cast<const __half2*>(&bl);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __half22float2(a2[e]), fb = __half22float2(b2[e]);
+        acc = fmaf(fa.x, fb.x, acc);
+        acc = fmaf(fa.y, fb.y, acc);
+        if (ql) {
+          const float2 fal = __half22float2(al2[e]), fbl = __half22float2(bl2[e]);
+          acc = fmaf(fa.x, fbl.x, acc);
+          acc = fmaf(fa.y, fbl.y, acc);
+          acc = fmaf(fal.x, fb.x, acc);
+          acc = fmaf(fal.y, fb.y, acc);
+        }
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) raw[o + n] = acc;
+    ++n;
+  }
+  __syncwarp();
+  // rank sort ascending: position = #{f : v_f < v_e or (v_f == v_e and f < e)}
+  for (int e = lane; e < n; e += 32) {
+    const float ve = raw[o + e];
+    int r = 0;
+    for (int f = 0; f < n; ++f) {
+      const float vf = raw[o + f];
+      r += (vf < ve) || (vf == ve && f < e);
+    }
+    thr[o + r] = ve;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    cnt[q] = n;
+    lim[q] = n > 0 ? thr[o] : __int_as_float(0x7f800000);
+  }
+}
+
+// K2.  One warp per query; warp-shuffle suffix scan over the rank histogram.
+//   above[r]    = sum_{m >= r} hist[m]            negatives ranked above the r-th lowest relevant item
+//   rank_all[r] = 1 + above[r] + (P - 1 - r)      relevant items above it are the ones sorted after it
+//   rank_rel[r] = P - r
+//   AP = 1/P sum_r rank_rel[r] / rank_all[r],  R1 = rank_all[P-1]
+__global__ void __launch_bounds__(256) ap_reduce_kernel(const unsigned int* __restrict__ hist,
+                                                        const long long* __restrict__ off,
+                                                        const int* __restrict__ cnt, int nq, float* __restrict__ ap,
+                                                        float* __restrict__ r1, double* __restrict__ sums) {
+  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (q >= nq) return;
+  const int P = cnt[q];
+  const unsigned int* h = hist + off[q];
+  float acc = 0.f;
+  unsigned int carry = 0;  // negatives above everything processed so far (higher r)
+  float first_rank = 0.f;
+  for (int base = P - 1; base >= 0; base -= 32) {
+    const int r = base - lane;  // lane 0 takes the highest remaining r
+    unsigned int v = r >= 0 ? h[r] : 0u;
+    // inclusive scan over lanes (lane l gets sum of lanes 0..l) == suffix sum over r
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    const unsigned int above = carry + v;
+    if (r >= 0) {
+      const float rank_all = 1.f + (float)above + (float)(P - 1 - r);
+      acc += (float)(P - r) / rank_all;
+      if (r == P - 1) first_rank = rank_all;
+    }
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+  acc = warp_sum(acc);
+  first_rank = warp_max(first_rank);
+  if (lane == 0) {
+    const float a = P > 0 ? acc / (float)P : __int_as_float(0x7fc00000);
+    const float f = P > 0 ? first_rank : __int_as_float(0x7fc00000);
+    ap[q] = a;
+    r1[q] = f;
+    if (P > 0) {
+      atomicAdd(&sums[0], (double)a);
+      atomicAdd(&sums[1], (double)f);
+      atomicAdd(&sums[2], 1.0);
+    }
+  }
+}
+
+// K3.  One warp per query: gather the candidates of every part, keep the k best (descending
+// similarity, ties -> lower candidate index, like a stable ascending-distance argsort).
+__global__ void __launch_bounds__(256) topk_finalize_kernel(const float* __restrict__ cand_val,
+                                                            const int* __restrict__ cand_idx,
+                                                            const int* __restrict__ cand_cnt, int parts, int nq,
+                                                            int cap, int k, long long* __restrict__ out_idx,
+                                                            float* __restrict__ out_sim) {
+  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (q >= nq) return;
+  for (int e = lane; e < k; e += 32) {
+    out_idx[(long long)q * k + e] = -1;
+    out_sim[(long long)q * k + e] = __int_as_float(0xff800000);
+  }
+  __syncwarp();
+  for (int p = 0; p < parts; ++p) {
+    const long long b = ((long long)p * nq + q) * cap;
+    const int n = cand_cnt[(long long)p * nq + q];
+    for (int e = lane; e < n; e += 32) {
+      const float ve = cand_val[b + e];
+      const int ie = cand_idx[b + e];
+      int r = 0;
+      for (int p2 = 0; p2 < parts && r < k; ++p2) {
+        const long long b2 = ((long long)p2 * nq + q) * cap;
+        const int n2 = cand_cnt[(long long)p2 * nq + q];
+        for (int f = 0; f < n2; ++f) {
+          const float vf = cand_val[b2 + f];
+          r += (vf > ve) || (vf == ve && cand_idx[b2 + f] < ie);
+        }
+      }
+      if (r < k) {
+        out_idx[(long long)q * k + r] = ie;
+        out_sim[(long long)q * k + r] = ve;
+      }
+    }
+  }
+}
+
+}  // namespace wealy

@@ -1,0 +1,229 @@
+// Warp-specialised sm_100a contraction core shared by every hot kernel of the path.
+//
+//   S[r, c] = sum_k A[r, k] * B[c, k]        A = query rows, B = candidate rows, both K-major fp16
+//
+// * operands are the fp16 "planes" written by the prep kernel: a `hi` plane and (3-pass parity
+//   mode) a `lo` residual plane; one pipeline stage holds {A_hi, A_lo, B_hi, B_lo} for one
+//   k-block and feeds three tcgen05.mma groups: hi*hi + hi*lo + lo*hi (fp32-grade accuracy from
+//   fp16 tensor cores, loading 4 tiles instead of the 6 a K'=3D GEMM would);
+// * TMA (128B/64B swizzle) -> shared-memory ring -> tcgen05.mma (M=128, N=256, K=16) issued by
+//   one thread -> two 256-column TMEM accumulators so the epilogue of tile t overlaps the MMAs
+//   of tile t+1;
+// * the N x N matrix is never written by this core: the accumulator is handed to an Epilogue
+//   policy 32 columns at a time, one accumulator row (= one query) per thread.
+//
+// Work decomposition: a *unit* is (row block of 128 queries) x (chunk of consecutive column
+// tiles).  Units are dealt round-robin to a persistent grid so that concurrently resident CTAs
+// sweep the same column chunk (candidate tiles are then shared through the 126 MB L2).
+#pragma once
+#include "ptx.cuh"
+
+namespace wealy {
+
+constexpr int kTileM = 128;   // queries per tile (TMEM lanes)
+constexpr int kTileN = 256;   // candidates per tile (TMEM columns per accumulator)
+constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit inputs
+constexpr int kChunkCols = 32;  // columns handed to the epilogue per tcgen05.ld
+
+struct GemmTmaps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
+
+struct GemmShape {
+  int m_rows;           // valid query rows
+  int n_cols;           // valid candidate columns
+  int k_blocks;         // number of kBlockK-wide k-blocks (planes are zero padded)
+  int n_row_blocks;     // ceil(m_rows / 128)
+  int n_col_tiles;      // ceil(n_cols / 256)
+  int tiles_per_chunk;  // column tiles per unit
+  int n_col_chunks;     // ceil(n_col_tiles / tiles_per_chunk)
+};
+
+template <int kPasses, int kBlockK>
+struct GemmSmem {
+  static constexpr int kSwizzle = kBlockK * 2;  // bytes per smem row == swizzle span
+  static constexpr int kABytes = kTileM * kBlockK * 2;
+  static constexpr int kBBytes = kTileN * kBlockK * 2;
+  static constexpr int kPlanes = kPasses == 3 ? 2 : 1;
+  static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+  static constexpr int kBudget = 227 * 1024 - 2048;  // alignment slack + barriers
+  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;
+  static_assert(kStages >= 2, "need at least a double-buffered ring");
+};
+
+// Epilogue policy contract (all __device__, called by the epilogue warps only):
+//   struct Params;                      POD passed by value to the kernel
+//   struct RowState;                    per-thread state that lives across one unit
+//   static void row_begin(const Params&, RowState&, int row, int part, const GemmShape&);
+//   static void chunk32(const Params&, RowState&, int row, int col0, const uint32_t (&acc)[32], const GemmShape&);
+//   static void row_end(const Params&, RowState&, int row, int part, const GemmShape&);
+// `row` is the global query row owned by the thread, `part` identifies the partial result slot
+// (column chunk x epilogue half) when a row is split over several units / warps.
+
+template <class Epi, int kPasses, int kBlockK, int kEpiWarps>
+__global__ void __launch_bounds__(64 + kEpiWarps * 32, 1)
+gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, const typename Epi::Params ep) {
+  using SM = GemmSmem<kPasses, kBlockK>;
+  constexpr int kStages = SM::kStages;
+  constexpr int kHalves = kEpiWarps / 4;  // epilogue warps per TMEM lane quadrant
+  static_assert(kEpiWarps == 4 || kEpiWarps == 8, "4 or 8 epilogue warps");
+  static_assert(kPasses == 1 || kPasses == 3, "1 (fp16) or 3 (fp16 hi/lo) passes");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* bar_base = smem + kStages * SM::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = (int)ptx::lane_id();
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmaps.a_hi);
+    ptx::prefetch_tensormap(&tmaps.b_hi);
+    if (kPasses == 3) {
+      ptx::prefetch_tensormap(&tmaps.a_lo);
+      ptx::prefetch_tensormap(&tmaps.b_lo);
+    }
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp_idx == 1) ptx::tmem_alloc<512>(tmem_slot);
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_units = shape.n_row_blocks * shape.n_col_chunks;
+
+  if (warp_idx == 0) {
+    // ===================================================== TMA producer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int chunk = u / shape.n_row_blocks;
+        const int rb = u - chunk * shape.n_row_blocks;
+        const int t0 = chunk * shape.tiles_per_chunk;
+        const int t1 = min(t0 + shape.tiles_per_chunk, shape.n_col_tiles);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < shape.k_blocks; ++kb) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* st = smem + stage * SM::kStageBytes;
+            ptx::mbar_expect_tx(&full_bar[stage], SM::kStageBytes);
+            // query tiles are re-read once per column tile (L2 hits); candidate tiles are shared
+            // by every resident CTA of the wave -> keep them in L2 preferentially
+            ptx::tma_load_2d(st, &tmaps.a_hi, &full_bar[stage], kb * kBlockK, rb * kTileM, ptx::kEvictNormal);
+            ptx::tma_load_2d(st + SM::kPlanes * SM::kABytes, &tmaps.b_hi, &full_bar[stage], kb * kBlockK,
+                             t * kTileN, ptx::kEvictLast);
+            if (kPasses == 3) {
+              ptx::tma_load_2d(st + SM::kABytes, &tmaps.a_lo, &full_bar[stage], kb * kBlockK, rb * kTileM,
+                               ptx::kEvictNormal);
+              ptx::tma_load_2d(st + 2 * SM::kABytes + SM::kBBytes, &tmaps.b_lo, &full_bar[stage], kb * kBlockK,
+                               t * kTileN, ptx::kEvictLast);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, kTileN, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int chunk = u / shape.n_row_blocks;
+        const int t0 = chunk * shape.tiles_per_chunk;
+        const int t1 = min(t0 + shape.tiles_per_chunk, shape.n_col_tiles);
+        for (int t = t0; t < t1; ++t) {
+          ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTileN);
+          for (int kb = 0; kb < shape.k_blocks; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t st = ptx::smem_u32(smem + stage * SM::kStageBytes);
+            const uint64_t a_hi = ptx::make_smem_desc<SM::kSwizzle>(st);
+            const uint64_t b_hi = ptx::make_smem_desc<SM::kSwizzle>(st + SM::kPlanes * SM::kABytes);
+            const uint64_t a_lo = ptx::make_smem_desc<SM::kSwizzle>(st + SM::kABytes);
+            const uint64_t b_lo = ptx::make_smem_desc<SM::kSwizzle>(st + 2 * SM::kABytes + SM::kBBytes);
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+              const uint64_t adv = (uint64_t)((kk * kUmmaK * 2) >> 4);  // +32 B inside the swizzle span
+              ptx::umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, (uint32_t)((kb | kk) != 0));
+              if (kPasses == 3) {
+                ptx::umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                ptx::umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+            ptx::umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+            if (kb == shape.k_blocks - 1) ptx::umma_commit(&tmem_full[acc]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps
+    const int ew = warp_idx - 2;
+    const int quad = warp_idx & 3;          // TMEM lane quadrant this warp may read
+    const int half = kHalves == 1 ? 0 : (ew >> 2);
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int chunk = u / shape.n_row_blocks;
+      const int rb = u - chunk * shape.n_row_blocks;
+      const int t0 = chunk * shape.tiles_per_chunk;
+      const int t1 = min(t0 + shape.tiles_per_chunk, shape.n_col_tiles);
+      const int row = rb * kTileM + row_in_tile;
+      const int part = chunk * kHalves + half;
+      typename Epi::RowState rs;
+      Epi::row_begin(ep, rs, row, part, shape);
+      for (int t = t0; t < t1; ++t) {
+        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN);
+#pragma unroll 1
+        for (int c = half; c < kTileN / kChunkCols; c += kHalves) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * kChunkCols), v);
+          ptx::tmem_ld_wait();
+          Epi::chunk32(ep, rs, row, t * kTileN + c * kChunkCols, v, shape);
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+      Epi::row_end(ep, rs, row, part, shape);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp_idx == 1) {
+    __syncwarp();
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace wealy

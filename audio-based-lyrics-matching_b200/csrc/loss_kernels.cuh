@@ -1,0 +1,344 @@
+// Epilogues and small kernels of the batch similarity-matrix contrastive losses:
+//   NT-Xent  (lib/losses.py:19-73)   and   CLEWS  (lib/losses.py:210-285).
+//
+// forward : prep (normalise + fp16 split) -> B x B sweep with a *statistics* epilogue (online
+//           log-sum-exp / masked sums per anchor row, never storing S) -> finalize (loss + logdict
+//           + per-row coefficients for the backward)
+// backward: B x B sweep again (recompute S on the tensor cores) with a *W* epilogue that forms
+//           W = dL/dS + (dL/dS)^T from the row and column coefficients and stores it as fp16
+//           hi/lo planes (L2-resident at training batch sizes) -> dU = W * U on the same
+//           contraction core -> row-wise normalisation Jacobian.
+// Closed forms: SURVEY.md section 8(a5),(a6); checked against the reference's autograd.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "gemm_core.cuh"
+#include "prep.cuh"
+
+namespace wealy {
+
+constexpr int kLossNtxent = 0;
+constexpr int kLossClews = 1;
+constexpr int kStatWidth = 8;  // floats per (part, row) partial record
+
+struct LossParams {
+  int kind;
+  int b;                // batch size
+  const int* label;     // [b]
+  const int* idx;       // [b]
+  float c2;             // NT-Xent: log2(e) / tau
+  float g2, b2;         // CLEWS: gamma * log2(e), b * log2(e)
+  // statistics sweep
+  float* partial;       // [parts][b][kStatWidth]
+  // W sweep
+  const float* rowstat; // [b][4]
+  __half* w_hi;         // [b][ldw] (ldw = b padded to the k-block)
+  __half* w_lo;         // nullable
+  long long ldw;
+};
+
+__device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+
+// ---------------------------------------------------------------------------------------------
+// statistics epilogue
+//   NT-Xent partial: {m2 (running max of logits in log2 units), A = sum exp, P = sum_pos exp}
+//   CLEWS   partial: {npos, nneg, sum_pos d, sum_neg X, sum_all d, sum_neg d}
+// ---------------------------------------------------------------------------------------------
+struct LossStatsEpi {
+  using Params = LossParams;
+  struct RowState {
+    int lab, id;
+    bool valid;
+    float a0, a1, a2, a3, a4, a5;
+  };
+
+  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&) {
+    st.valid = row < p.b;
+    st.lab = st.valid ? p.label[row] : 0;
+    st.id = st.valid ? p.idx[row] : 0;
+    st.a0 = p.kind == kLossNtxent ? neg_inf() : 0.f;
+    st.a1 = st.a2 = st.a3 = st.a4 = st.a5 = 0.f;
+  }
+
+  __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
+                                                 const uint32_t (&acc)[32], const GemmShape&) {
+    if (!st.valid || col0 >= p.b) return;
+    if (p.kind == kLossNtxent) {
+      float l[32];
+      float cm = neg_inf();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int j = col0 + e;
+        const bool ok = (j < p.b) && (j != row);  // diagonal masked by POSITION (losses.py:52-53)
+        l[e] = ok ? __uint_as_float(acc[e]) * p.c2 : neg_inf();
+        cm = fmaxf(cm, l[e]);
+      }
+      if (cm > st.a0) {  // online max: rescale the running sums
+        const float sc = exp2f(st.a0 - cm);  // a0 = -inf on first use -> 0
+        st.a1 *= sc;
+        st.a2 *= sc;
+        st.a0 = cm;
+      }
+      if (st.a0 == neg_inf()) return;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int j = min(col0 + e, p.b - 1);
+        const float ex = exp2f(l[e] - st.a0);  // masked entries: exp2(-inf) = 0
+        const bool pos = (__ldg(p.label + j) == st.lab) && (__ldg(p.idx + j) != st.id);
+        st.a1 += ex;
+        st.a2 += pos ? ex : 0.f;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const int j = col0 + e;
+        if (j < p.b) {
+          const float s = __uint_as_float(acc[e]);
+          const float d = 1.f - s;
+          const bool same = __ldg(p.label + j) == st.lab;
+          const bool pos = same && (__ldg(p.idx + j) != st.id);
+          const float x = exp2f(fmaf(-p.g2, d, p.b2));  // exp(b - gamma d)
+          st.a0 += pos ? 1.f : 0.f;
+          st.a1 += same ? 0.f : 1.f;
+          st.a2 += pos ? d : 0.f;
+          st.a3 += same ? 0.f : x;
+          st.a4 += d;
+          st.a5 += same ? 0.f : d;
+        }
+      }
+    }
+  }
+
+  __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part, const GemmShape&) {
+    if (!st.valid) return;
+    float* o = p.partial + ((long long)part * p.b + row) * kStatWidth;
+    reinterpret_cast<float4*>(o)[0] = make_float4(st.a0, st.a1, st.a2, st.a3);
+    reinterpret_cast<float4*>(o)[1] = make_float4(st.a4, st.a5, 0.f, 0.f);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// W epilogue: W'_ij = scale * (dS_ij + dS_ji), stored as fp16 hi (+ lo) planes.
+//   NT-Xent rowstat = {M2, a', b', -}:  dS_ij = E_ij (b'_i - pos a'_i),  E_ij = exp2(l2_ij - M2_i)   (scale = B)
+//   CLEWS   rowstat = {ca', cu', -, -}: dS_ij = -pos ca'_i + X_ij neg cu'_i                          (scale = H)
+// ---------------------------------------------------------------------------------------------
+struct LossWEpi {
+  using Params = LossParams;
+  struct RowState {
+    int lab, id;
+    bool valid;
+    float r0, r1, r2;
+  };
+
+  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&) {
+    st.valid = row < p.b;
+    st.lab = st.valid ? p.label[row] : 0;
+    st.id = st.valid ? p.idx[row] : 0;
+    const float4 r = st.valid ? reinterpret_cast<const float4*>(p.rowstat)[row] : make_float4(0.f, 0.f, 0.f, 0.f);
+    st.r0 = r.x;
+    st.r1 = r.y;
+    st.r2 = r.z;
+  }
+
+  __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
+                                                 const uint32_t (&acc)[32], const GemmShape&) {
+    if (!st.valid || col0 >= p.ldw) return;
+    __align__(16) __half hi[32];
+    __align__(16) __half lo[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int j = col0 + e;
+      float w = 0.f;
+      if (j < p.b && j != row) {
+        const float s = __uint_as_float(acc[e]);
+        const float4 cj = __ldg(reinterpret_cast<const float4*>(p.rowstat) + j);
+        const bool same = __ldg(p.label + j) == st.lab;
+        const bool pos = same && (__ldg(p.idx + j) != st.id);
+        if (p.kind == kLossNtxent) {
+          const float l2 = s * p.c2;
+          const float eij = exp2f(l2 - st.r0);
+          const float eji = exp2f(l2 - cj.x);
+          w = eij * (st.r2 - (pos ? st.r1 : 0.f)) + eji * (cj.z - (pos ? cj.y : 0.f));
+        } else {
+          const float x = exp2f(fmaf(-p.g2, 1.f - s, p.b2));
+          w = (pos ? -(st.r0 + cj.x) : 0.f) + (same ? 0.f : x * (st.r1 + cj.y));
+        }
+      }
+      hi[e] = __float2half_rn(w);
+      lo[e] = __float2half_rn(w - __half2float(hi[e]));
+    }
+    // ldw is a multiple of 64 and col0 of 32 -> whole 64-byte segments, 16-byte aligned
+    uint4* dh = reinterpret_cast<uint4*>(p.w_hi + (long long)row * p.ldw + col0);
+    const uint4* sh = reinterpret_cast<const uint4*>(hi);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) dh[v] = sh[v];
+    if (p.w_lo) {
+      uint4* dl = reinterpret_cast<uint4*>(p.w_lo + (long long)row * p.ldw + col0);
+      const uint4* sl = reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) dl[v] = sl[v];
+    }
+  }
+
+  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&) {}
+};
+
+// ---------------------------------------------------------------------------------------------
+// finalize (single block): merge the partial records, reduce the loss and the logdict numbers,
+// write the per-row coefficients the W sweep needs.
+// out (double[WEALY_OUT_COUNT]) indices follow include/wealy_b200.h.
+// scal[0] = factor the Jacobian kernel applies to dU (1/(B tau) for NT-Xent, 1/H for CLEWS).
+// ---------------------------------------------------------------------------------------------
+struct LossCfgDev {
+  int kind;
+  float temperature, gamma, b, eps, epsilon, uw;
+  int numerically_friendly;
+};
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum_d(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = l < (int)(blockDim.x >> 5) ? sh[l] : 0.0;
+    t = warp_sum_d(t);
+    if (l == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+__global__ void __launch_bounds__(1024) loss_finalize_kernel(LossCfgDev cfg, int b, int d, int parts,
+                                                             const float* __restrict__ partial,
+                                                             const ZStats* __restrict__ zs, float* __restrict__ rowstat,
+                                                             float* __restrict__ scal, double* __restrict__ out) {
+  __shared__ double sh[33];
+  const double B = (double)b;
+  if (cfg.kind == kLossNtxent) {
+    double lsum = 0.0;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+      float M = neg_inf();
+      for (int p = 0; p < parts; ++p) M = fmaxf(M, partial[((long long)p * b + i) * kStatWidth]);
+      float A = 0.f, P = 0.f;
+      for (int p = 0; p < parts; ++p) {
+        const float* r = partial + ((long long)p * b + i) * kStatWidth;
+        if (r[0] > neg_inf()) {
+          const float sc = exp2f(r[0] - M);
+          A = fmaf(r[1], sc, A);
+          P = fmaf(r[2], sc, P);
+        }
+      }
+      const float Ae = A + 1e-8f;               // losses.py:65-66
+      const float rho = P / Ae + 1e-8f;
+      lsum += -(double)logf(rho);
+      reinterpret_cast<float4*>(rowstat)[i] = make_float4(M, 1.f / (rho * Ae), P / (rho * Ae * Ae), 0.f);
+    }
+    lsum = block_sum(lsum, sh);
+    if (threadIdx.x == 0) {
+      out[0] = lsum / B;
+      scal[0] = 1.f / ((float)b * cfg.temperature);
+    }
+  } else {
+    double s_align = 0.0, s_uni = 0.0, s_np = 0.0, s_nn = 0.0, s_h = 0.0, s_pd = 0.0, s_ad = 0.0, s_nd = 0.0;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+      float np = 0.f, nn = 0.f, pd = 0.f, nx = 0.f, ad = 0.f, nd = 0.f;
+      for (int p = 0; p < parts; ++p) {
+        const float* r = partial + ((long long)p * b + i) * kStatWidth;
+        np += r[0]; nn += r[1]; pd += r[2]; nx += r[3]; ad += r[4]; nd += r[5];
+      }
+      const float align = pd / fmaxf(np, cfg.eps);          // _per_anchor_mean, losses.py:202-208
+      const float uni = nx / fmaxf(nn, cfg.eps);
+      const float lu = cfg.numerically_friendly ? log1pf(uni) : logf(uni + cfg.epsilon);
+      if (np > 0.f) { s_align += align; s_h += 1.0; }
+      s_uni += lu;
+      s_np += np; s_nn += nn; s_pd += pd; s_ad += ad; s_nd += nd;
+      // stash what phase 2 needs
+      reinterpret_cast<float4*>(rowstat)[i] = make_float4(np, nn, uni, 0.f);
+    }
+    s_align = block_sum(s_align, sh);
+    s_uni = block_sum(s_uni, sh);
+    s_np = block_sum(s_np, sh);
+    s_nn = block_sum(s_nn, sh);
+    s_h = block_sum(s_h, sh);
+    s_pd = block_sum(s_pd, sh);
+    s_ad = block_sum(s_ad, sh);
+    s_nd = block_sum(s_nd, sh);
+    const double H = s_h > 0.0 ? s_h : 1.0;
+    const double l_align = s_h > 0.0 ? s_align / s_h : 0.0;  // losses.py:239
+    const double l_uni = s_uni / B;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+      const float4 r = reinterpret_cast<const float4*>(rowstat)[i];
+      const float np = r.x, nn = r.y, uni = r.z;
+      const float ca = np > 0.f ? 1.f / np : 0.f;  // x H (the W scale) / (npos H)
+      const float outer = cfg.numerically_friendly ? 1.f / (1.f + uni) : 1.f / (uni + cfg.epsilon);
+      const float cu = nn > 0.f ? (float)(H * (double)cfg.uw * (double)cfg.gamma / (B * (double)nn)) * outer : 0.f;
+      reinterpret_cast<float4*>(rowstat)[i] = make_float4(ca, cu, 0.f, 0.f);
+    }
+    if (threadIdx.x == 0) {
+      const double n2 = B * B;
+      out[0] = l_align + (double)cfg.uw * l_uni;
+      out[4] = l_align;
+      out[5] = l_uni;
+      out[6] = s_np;
+      out[7] = s_nn;
+      out[8] = s_h / B;
+      // tops.mmean(d, mask=pos_mask) averages over the COMPLEMENT of the mask (losses.py:267-268)
+      out[9] = s_np > 0.0 ? (s_ad - s_pd) / fmax(n2 - s_np, 1e-7) : 0.0;
+      out[10] = s_nn > 0.0 ? (s_ad - s_nd) / fmax(n2 - s_nn, 1e-7) : 0.0;
+      scal[0] = (float)(1.0 / H);
+    }
+  }
+  if (threadIdx.x == 0) {
+    const double n = B * (double)d;
+    out[1] = (double)__uint_as_float(zs->maxabs_bits);
+    out[2] = zs->sum / n;
+    const double var = n > 1.0 ? (zs->sumsq - zs->sum * zs->sum / n) / (n - 1.0) : 0.0;
+    out[3] = sqrt(var > 0.0 ? var : 0.0);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// normalisation Jacobian (one warp per row):  u = z / div,  proj = u . dU
+//   NT-Xent: dz = g * scal * (dU - u proj (r + 1e-6) / r) / (r + 1e-6)      (x/(|x|+eps), tensor_ops.py:169)
+//   CLEWS  : dz = g * scal * (dU - u proj) / max(r, 1e-12)                  (F.normalize, losses.py:231)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) loss_jacobian_kernel(int kind, const T* __restrict__ z, long long ldz, int b, int d,
+                                                            const float* __restrict__ norm,
+                                                            const float* __restrict__ du, const float* __restrict__ scal,
+                                                            const float* __restrict__ grad_out, T* __restrict__ dz,
+                                                            long long ld_dz) {
+  const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (row >= b) return;
+  const float r = norm[row];
+  const float div = kind == kLossNtxent ? r + 1e-6f : fmaxf(r, 1e-12f);
+  const T* zr = z + (long long)row * ldz;
+  const float* g = du + (long long)row * d;
+  float proj = 0.f;
+  for (int k = lane; k < d; k += 32) proj = fmaf(to_f32<T>(zr[k]) / div, g[k], proj);
+  proj = warp_sum(proj);
+  // d(z/(r+eps))/dz has the extra (r+eps)/r on the radial term; r == 0 -> torch's norm subgradient is 0
+  const float radial = kind == kLossNtxent ? (r > 0.f ? proj * div / r : 0.f) : proj;
+  const float f = scal[0] * (grad_out ? grad_out[0] : 1.f) / div;
+  T* o = dz + (long long)row * ld_dz;
+  for (int k = lane; k < d; k += 32) {
+    const float u = to_f32<T>(zr[k]) / div;
+    o[k] = from_f32<T>(f * (g[k] - u * radial));
+  }
+}
+
+}  // namespace wealy

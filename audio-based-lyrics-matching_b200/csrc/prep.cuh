@@ -1,0 +1,138 @@
+// K0 `prep_rows`: one HBM pass over the embeddings that
+//   * computes the row L2 norm (and squared norm, max |x|),
+//   * applies the reference's normalisation  x / (|x| + eps)   [lib/tensor_ops.py:169-170]
+//     or F.normalize's  x / max(|x|, eps)                       [lib/losses.py:231]
+//     or, for dot / euclidean modes, an exact power-of-two row scaling (folded back in the epilogue),
+//   * splits the result into the fp16 `hi` plane and the fp16 residual `lo` plane the
+//     tensor-core contraction consumes (x ~= hi + lo to ~2^-22), zero-padding K to the k-block,
+//   * optionally accumulates the logdict statistics (max |z|, sum z, sum z^2; lib/losses.py:69-71,281-283).
+// HBM-bound: reads n*d*sizeof(T), writes n*d_pad*2*planes bytes.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "ptx.cuh"
+
+namespace wealy {
+
+enum PrepMode : int {
+  kPrepL2AddEps = 0,  // x / (|x| + eps)
+  kPrepL2Clamp = 1,   // x / max(|x|, eps)
+  kPrepRawPow2 = 2,   // x * 2^-e, e = exponent of max|x|; epilogue multiplies by 2^e
+};
+
+struct ZStats {
+  double sum;
+  double sumsq;
+  unsigned int maxabs_bits;  // float bits of max |z| (non-negative floats order like uints)
+  unsigned int pad;
+};
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per row.  `hi_t` / `lo_t` (optional) receive the transposed planes [d_pad_t rows = d][n_pad_t]
+// used as the K-major "B" operand of the  dU = W * U  product of the loss backward.
+template <typename T>
+__global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ x, long long ld, int n, int d, int d_pad,
+                                                        int mode, float eps, int stats_on_scaled,
+                                                        __half* __restrict__ hi, __half* __restrict__ lo,
+                                                        __half* __restrict__ hi_t, __half* __restrict__ lo_t,
+                                                        long long ld_t, float* __restrict__ norm_out,
+                                                        float* __restrict__ scale_out, float* __restrict__ sq_out,
+                                                        ZStats* __restrict__ stats) {
+  const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (warp >= n) return;
+  const T* row = x + (long long)warp * ld;
+
+  float ss = 0.f, mx = 0.f, sm = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float v = to_f32<T>(row[k]);
+    ss = fmaf(v, v, ss);
+    mx = fmaxf(mx, fabsf(v));
+    sm += v;
+  }
+  ss = warp_sum(ss);
+  mx = warp_max(mx);
+  const float nrm = sqrtf(ss);
+
+  float div = 1.f;   // x_hat = x / div
+  float escale = 1.f;  // epilogue row factor
+  if (mode == kPrepL2AddEps) {
+    div = nrm + eps;
+  } else if (mode == kPrepL2Clamp) {
+    div = fmaxf(nrm, eps);
+  } else {
+    int e = 0;
+    if (mx > 0.f) frexpf(mx, &e);  // mx = f * 2^e, f in [0.5, 1)  ->  |x * 2^-e| < 1
+    div = ldexpf(1.f, e);
+    escale = div;
+  }
+
+  double s1 = 0.0, s2 = 0.0;
+  float smx = 0.f;
+  __half* hrow = hi + (long long)warp * d_pad;
+  __half* lrow = lo ? lo + (long long)warp * d_pad : nullptr;
+  for (int k = lane; k < d_pad; k += 32) {
+    float v = 0.f;
+    if (k < d) v = to_f32<T>(row[k]) / div;  // IEEE division, as torch does
+    const __half h = __float2half_rn(v);
+    hrow[k] = h;
+    __half l = __float2half_rn(0.f);
+    if (lrow) {
+      l = __float2half_rn(v - __half2float(h));
+      lrow[k] = l;
+    }
+    if (hi_t && k < d) {
+      hi_t[(long long)k * ld_t + warp] = h;
+      if (lo_t) lo_t[(long long)k * ld_t + warp] = l;
+    }
+    if (stats && k < d) {
+      const float sv = stats_on_scaled ? v : to_f32<T>(row[k]);
+      s1 += (double)sv;
+      s2 += (double)sv * (double)sv;
+      smx = fmaxf(smx, fabsf(sv));
+    }
+  }
+  if (lane == 0) {
+    if (norm_out) norm_out[warp] = nrm;
+    if (scale_out) scale_out[warp] = escale;
+    if (sq_out) sq_out[warp] = ss;
+  }
+  if (stats) {
+    s1 = warp_sum_d(s1);
+    s2 = warp_sum_d(s2);
+    smx = warp_max(smx);
+    if (lane == 0) {
+      atomicAdd(&stats->sum, s1);
+      atomicAdd(&stats->sumsq, s2);
+      atomicMax(&stats->maxabs_bits, __float_as_uint(smx));
+    }
+  }
+  (void)sm;
+}
+
+}  // namespace wealy

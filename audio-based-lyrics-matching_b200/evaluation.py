@@ -1,0 +1,131 @@
+"""Retrieval evaluation on sm_100a: self / same-clique masking by id, per-query ranking,
+AP / MAP / MR1 and optional top-k, fused into the similarity sweep (wealy_eval_run).
+
+The reference has not released its evaluator; the interface is inferred from the
+evaluation tensors it prepares (`candidates_c`, `candidates_i`: lib/audio_dataset/dataset.py:82-86,
+448-449), positives / self follow lib/losses.py:40-42 and the distance is
+`pairwise_distance_matrix(q, cands, mode="cos")` (lib/tensor_ops.py:167-173):
+
+    aps, r1s = evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z)
+    aps, r1s, topk_idx, topk_sim = evaluate(..., topk=100)
+
+Host tensors are accepted and copied to the current CUDA device (that copy is part of the
+end-to-end measurement in bench.py); the computation itself has no CPU path.
+"""
+import ctypes
+
+import torch
+
+from . import _native as N
+from .tensor_ops import passes_of
+
+
+def _to_device(t, device, dtype=None):
+    t = torch.as_tensor(t)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_cuda:
+        t = t.to(device, non_blocking=True)
+    return t
+
+
+class EvalPlan:
+    """Everything that depends on ids only (clique-sorted candidate order, per-query relevant
+    segments, CSR offsets) -- build once per (queries, candidates) id set, run for any embeddings."""
+
+    def __init__(self, queries_c, queries_i, candidates_c, candidates_i, device=None):
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        same = (queries_c is candidates_c) and (queries_i is candidates_i)
+        self.q_c = _to_device(queries_c, self.device, torch.long).contiguous().view(-1)
+        self.q_i = _to_device(queries_i, self.device, torch.long).contiguous().view(-1)
+        if same:
+            self.c_c, self.c_i = self.q_c, self.q_i
+        else:
+            self.c_c = _to_device(candidates_c, self.device, torch.long).contiguous().view(-1)
+            self.c_i = _to_device(candidates_i, self.device, torch.long).contiguous().view(-1)
+        assert self.q_c.numel() == self.q_i.numel() and self.c_c.numel() == self.c_i.numel()
+        self.nq, self.nc = self.q_c.numel(), self.c_c.numel()
+        self._handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(N.lib.wealy_eval_plan_create(
+                self.q_c.data_ptr(), self.q_i.data_ptr(), self.nq, self.c_c.data_ptr(), self.c_i.data_ptr(), self.nc,
+                N.stream_ptr(self.device), ctypes.byref(self._handle)))
+        tp, nr, mr = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        N.check(N.lib.wealy_eval_plan_info(self._handle, ctypes.byref(tp), ctypes.byref(nr), ctypes.byref(mr)))
+        self.total_pairs, self.queries_without_relevant, self.max_relevant = tp.value, nr.value, mr.value
+
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            N.lib.wealy_eval_plan_destroy(self._handle)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, queries_z, candidates_z, *, topk=None, eps=1e-6, precision=None, allow_empty=False):
+        """-> dict(aps, r1s, sums[, topk_idx, topk_sim]); `sums` = device doubles {sum AP, sum R1, #scored}."""
+        if self.queries_without_relevant and not allow_empty:
+            raise ValueError(f"{self.queries_without_relevant} queries have no relevant candidate "
+                             "(every clique needs >= 2 versions; pass allow_empty=True to score the rest)")
+        same = queries_z is candidates_z
+        qz = _to_device(queries_z, self.device)
+        cz = qz if same else _to_device(candidates_z, self.device)
+        assert qz.ndim == 2 and cz.ndim == 2 and qz.shape[1] == cz.shape[1]
+        assert qz.shape[0] == self.nq and cz.shape[0] == self.nc
+        if qz.dtype != cz.dtype:
+            raise RuntimeError("queries_z and candidates_z must have the same dtype")
+        if qz.stride(1) != 1:
+            qz = qz.contiguous()
+            cz = qz if same else cz
+        if cz.stride(1) != 1:
+            cz = cz.contiguous()
+        k = 0 if topk is None else min(int(topk), self.nc)
+        aps = torch.empty(self.nq, dtype=torch.float32, device=self.device)
+        r1s = torch.empty(self.nq, dtype=torch.float32, device=self.device)
+        sums = torch.empty(3, dtype=torch.float64, device=self.device)
+        tk_idx = torch.empty((self.nq, k), dtype=torch.long, device=self.device) if k else None
+        tk_sim = torch.empty((self.nq, k), dtype=torch.float32, device=self.device) if k else None
+        with torch.cuda.device(self.device):
+            N.check(N.lib.wealy_eval_run(
+                self._handle, qz.data_ptr(), qz.stride(0), cz.data_ptr(), cz.stride(0), qz.shape[1],
+                N.dtype_code(qz.dtype), float(eps), passes_of(precision), k, aps.data_ptr(), r1s.data_ptr(),
+                sums.data_ptr(), tk_idx.data_ptr() if k else None, tk_sim.data_ptr() if k else None,
+                N.stream_ptr(self.device)))
+        out = {"aps": aps, "r1s": r1s, "sums": sums}
+        if k:
+            out["topk_idx"], out["topk_sim"] = tk_idx, tk_sim
+        return out
+
+
+def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z, *, topk=None, mode="cos",
+             eps=1e-6, precision=None, allow_empty=False, plan=None):
+    """-> (aps[Nq], r1s[Nq]) or (aps, r1s, topk_idx[Nq,k], topk_sim[Nq,k]) on the CUDA device.
+
+    AP_q = 1/P sum_{p relevant} rank_rel(p) / rank_all(p); R1_q = rank of the best relevant item;
+    self (candidates_i == queries_i) is excluded, relevant = same clique and not self."""
+    if mode not in ("cos", "cossim"):
+        raise NotImplementedError("wealy_b200.evaluate ranks by cosine distance (mode='cos')")
+    own = plan is None
+    if own:
+        plan = EvalPlan(queries_c, queries_i, candidates_c, candidates_i)
+    try:
+        res = plan.run(queries_z, candidates_z, topk=topk, eps=eps, precision=precision, allow_empty=allow_empty)
+    finally:
+        if own:
+            torch.cuda.current_stream(plan.device).synchronize()
+            plan.close()
+    if topk is None:
+        return res["aps"], res["r1s"]
+    return res["aps"], res["r1s"], res["topk_idx"], res["topk_sim"]
+
+
+def mean_metrics(sums):
+    """(MAP, MR1) from the device `sums` vector -- one 24-byte device->host read."""
+    s = sums.detach().to("cpu")
+    n = max(float(s[2]), 1.0)
+    return float(s[0]) / n, float(s[1]) / n

@@ -1,0 +1,140 @@
+/* wealy_b200.h -- C ABI of the B200-native (sm_100a) WEALY retrieval-and-scoring hot path.
+ *
+ * The reference (helemanc/audio-based-lyrics-matching) is pure Python / PyTorch: the path has
+ * no FFI of its own, only Python call signatures.  This header is the
+ * drop-in boundary a binding for that path talks to: plain pointers and sizes, no torch types,
+ * every entry point returns an int status (0 = ok) and never throws; wealy_last_error() returns
+ * the message of the last failure on the calling thread.  The Python mirror of the reference
+ * interface (package `wealy_b200`: tensor_ops / losses / evaluation) binds these symbols with
+ * ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * All data pointers are DEVICE pointers on the current CUDA device unless stated otherwise.
+ * `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are
+ * asynchronous with respect to the host unless documented otherwise.
+ */
+#ifndef WEALY_B200_H_
+#define WEALY_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---------------------------------------------------------------------- */
+#define WEALY_OK 0
+#define WEALY_ERR_BAD_ARG 1      /* null pointer, negative size, unknown enum (AssertionError / NotImplementedError upstream) */
+#define WEALY_ERR_UNSUPPORTED 2  /* valid in the reference but not built here (e.g. cdist with p != 2) */
+#define WEALY_ERR_CUDA 3         /* a CUDA runtime / driver call failed; see wealy_last_error() */
+#define WEALY_ERR_WORKSPACE 4    /* workspace too small */
+#define WEALY_ERR_ID_RANGE 5     /* a clique / version id does not fit in 32 bits */
+
+/* ---- enums ----------------------------------------------------------------------------- */
+/* element type of embedding / output buffers */
+#define WEALY_F32 0
+#define WEALY_F16 1
+#define WEALY_BF16 2
+
+/* pairwise_distance_matrix modes -- lib/tensor_ops.py:157-173 */
+#define WEALY_MODE_COSSIM 0
+#define WEALY_MODE_COS 1
+#define WEALY_MODE_DOTSIM 2
+#define WEALY_MODE_DOT 3
+#define WEALY_MODE_SQEUC 4  /* also nsqeuc via `post` = 1/D */
+#define WEALY_MODE_EUC 5    /* fro/euc with p = 2; nfro/neuc via `post` = D^-1/2 */
+
+/* tensor-core precision of the contraction */
+#define WEALY_PASSES_FP16 1   /* one fp16 pass: |err| ~ 1e-4 on unit vectors (fast mode) */
+#define WEALY_PASSES_FP16X3 3 /* hi*hi + hi*lo + lo*hi: |err| ~ 1e-6, fp32-grade (parity mode, default) */
+
+const char* wealy_last_error(void);
+int wealy_version(void);
+
+/* ---- a1/a2: materialised similarity / distance matrix ------------------------------------
+ * Replaces lib/tensor_ops.py:152-176 `pairwise_distance_matrix(x, y, mode, p, eps)` (modes
+ * cos/cossim/dot/dotsim/sqeuc/nsqeuc and the p = 2 cdist modes) and lib/tensor_ops.py:131-149
+ * `pairwise_euclidean_distance_matrix`.
+ *   x [n, d] (row stride ldx elements), y [m, d] (ldy); out [n, m] (row stride ld_out), out_dtype.
+ *   eps: the reference's `eps` added to the L2 norm (cos modes).  post: output scale for the
+ *   n* modes.  workspace: wealy_sim_matrix_workspace_bytes(n, m, d, passes) bytes.            */
+size_t wealy_sim_matrix_workspace_bytes(int64_t n, int64_t m, int64_t d, int passes);
+int wealy_sim_matrix(const void* x, int64_t n, int64_t ldx, const void* y, int64_t m, int64_t ldy, int64_t d,
+                     int in_dtype, int mode, float eps, float post, int passes, void* out, int64_t ld_out,
+                     int out_dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a7: fused retrieval evaluation -------------------------------------------------------
+ * Self / same-clique masking by id, per-query ranking, AP / R1 (and optional top-k) without
+ * materialising the Nq x Nc matrix.  The evaluator is not in the reference; argument vocabulary
+ * follows lib/audio_dataset/dataset.py:82-86,448-449 (candidates_c / candidates_i), positives
+ * and self follow lib/losses.py:40-42, distance follows lib/tensor_ops.py:167-173 mode "cos".
+ *
+ * A plan holds everything that depends on ids only (clique-sorted candidate order, per-query
+ * relevant segments, CSR offsets) plus cached device scratch; create it once per (queries,
+ * candidates) id set and run it for any embeddings.  plan_create synchronises the stream
+ * (it returns counts to the host); run / destroy do not allocate after the first run.        */
+typedef struct wealy_eval_plan wealy_eval_plan;
+
+int wealy_eval_plan_create(const int64_t* queries_c, const int64_t* queries_i, int64_t nq,
+                           const int64_t* candidates_c, const int64_t* candidates_i, int64_t nc, void* stream,
+                           wealy_eval_plan** plan);
+/* host-side facts computed at creation: total (query, same-clique candidate) pairs, number of
+ * queries without any relevant candidate, largest number of relevant candidates of a query.  */
+int wealy_eval_plan_info(const wealy_eval_plan* plan, int64_t* total_pairs, int64_t* queries_without_relevant,
+                         int64_t* max_relevant);
+/* queries_z [nq, d] (row stride ld_q), candidates_z [nc, d] (ld_c), same dtype.
+ * aps, r1s: [nq] float (NaN for a query without relevant candidates).
+ * sums: 3 doubles on the device = {sum AP, sum R1, number of scored queries}  (MAP = sums[0]/sums[2]).
+ * topk > 0: topk_idx [nq, topk] int64 (-1 padded), topk_sim [nq, topk] float (-inf padded),
+ *           best first, self excluded; pass NULL / 0 to skip.                                 */
+int wealy_eval_run(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, const void* candidates_z, int64_t ld_c,
+                   int64_t d, int dtype, float eps, int passes, int topk, float* aps, float* r1s, double* sums,
+                   int64_t* topk_idx, float* topk_sim, void* stream);
+void wealy_eval_plan_destroy(wealy_eval_plan* plan);
+
+/* ---- a5/a6: batch similarity-matrix contrastive losses -------------------------------------
+ * NT-Xent: lib/losses.py:19-73.  CLEWS: lib/losses.py:210-285.  Forward writes the loss terms
+ * and logdict statistics into `out` (doubles, device) and keeps the per-row statistics the
+ * backward needs inside `workspace`; backward writes d loss / d z (dtype of z) scaled by
+ * *grad_out (a device float, the upstream gradient of the scalar loss).
+ *   z [b, d] (row stride ldz), z_label / z_idx [b] int64 (already label-noised by the caller,
+ *   lib/losses.py:34-35).                                                                      */
+#define WEALY_LOSS_NTXENT 0
+#define WEALY_LOSS_CLEWS 1
+
+/* indices into `out` */
+#define WEALY_OUT_LOSS 0
+#define WEALY_OUT_ZMAX 1
+#define WEALY_OUT_ZMEAN 2
+#define WEALY_OUT_ZSTD 3
+#define WEALY_OUT_ALIGN 4     /* CLEWS l_cent */
+#define WEALY_OUT_UNIFORM 5   /* CLEWS l_cont */
+#define WEALY_OUT_NPOS 6      /* cnt_pos_pairs */
+#define WEALY_OUT_NNEG 7      /* cnt_neg_pairs */
+#define WEALY_OUT_ANCHORS 8   /* anchors_with_pos */
+#define WEALY_OUT_DPOS 9      /* v_dpos */
+#define WEALY_OUT_DNEG 10     /* v_dneg */
+#define WEALY_OUT_COUNT 16
+
+typedef struct wealy_loss_cfg {
+  int kind;          /* WEALY_LOSS_* */
+  int passes;        /* WEALY_PASSES_* */
+  float temperature; /* NT-Xent tau */
+  float gamma, b;    /* CLEWS */
+  float eps, epsilon;
+  float uw;          /* CLEWS resolved uniformity weight */
+  int numerically_friendly;
+} wealy_loss_cfg;
+
+size_t wealy_loss_workspace_bytes(int64_t b, int64_t d, int passes);
+int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
+                       const int64_t* z_label, const int64_t* z_idx, double* out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
+                        const float* grad_out, void* dz, int64_t ld_dz, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEALY_B200_H_ */

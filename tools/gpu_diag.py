@@ -1,0 +1,78 @@
+"""GPU bring-up diagnostics (developer tool, run under gpurun): each stage in its own process so a
+trap in one kernel does not poison the rest.  Usage: python tools/gpu_diag.py <stage> [args]"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import wealy_b200  # noqa: E402
+from wealy_b200 import tensor_ops as wt, evaluation as we  # noqa: E402
+from wealy_b200.data import synth  # noqa: E402
+from oracle import similarity as osim, evaluator as oev  # noqa: E402
+
+
+def stage_sim(precision, n, m, d, mode="cossim"):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(n, d, generator=g) * 3
+    y = torch.randn(m, d, generator=g)
+    ref = osim.distance_matrix(x.double(), y.double(), mode=mode)
+    out = wt.pairwise_distance_matrix(x.cuda(), y.cuda(), mode=mode, precision=precision)
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - ref).abs()
+    print(f"sim {mode} {precision} n={n} m={m} d={d}: max_err={err.max().item():.3e} mean_err={err.mean().item():.3e} "
+          f"ref_absmax={ref.abs().max().item():.3f}", flush=True)
+    if err.max().item() > 1e-2:
+        bad = (err > 1e-2).nonzero()
+        print("  first bad entries:", bad[:8].tolist(), "count", bad.shape[0], flush=True)
+        print("  out[0,:8]", out[0, :8].tolist(), "\n  ref[0,:8]", ref[0, :8].tolist(), flush=True)
+
+
+def stage_eval(precision, n, d, topk=0):
+    s = synth.make_eval_set(n, d, seed=0)
+    t = time.time()
+    aps_o, r1_o = oev.evaluate_rankcount(s["c"], s["i"], s["z"], s["c"], s["i"], s["z"]) if n <= 4000 else \
+        oev.evaluate_argsort(s["c"], s["i"], s["z"], s["c"], s["i"], s["z"])
+    t_or = time.time() - t
+    zc, cc, ic = s["z"].cuda(), s["c"].cuda(), s["i"].cuda()
+    res = we.evaluate(cc, ic, zc, cc, ic, zc, precision=precision, topk=(topk or None))
+    torch.cuda.synchronize()
+    aps, r1s = res[0].cpu().double(), res[1].cpu().double()
+    print(f"eval {precision} n={n} d={d}: MAP gpu={aps.mean():.6f} oracle={aps_o.mean():.6f} "
+          f"MR1 gpu={r1s.mean():.4f} oracle={r1_o.mean():.4f} max|dAP|={(aps - aps_o).abs().max():.2e} "
+          f"n(R1 differ)={(r1s != r1_o).sum().item()} oracle_s={t_or:.1f}", flush=True)
+    if topk:
+        _, _, tk_idx_o, tk_sim_o = oev.evaluate_argsort(s["c"][:512], s["i"][:512], s["z"][:512], s["c"], s["i"], s["z"], topk=topk)
+        idx, sim = res[2][:512].cpu(), res[3][:512].cpu()
+        print(f"  topk={topk}: idx mismatch={(idx != tk_idx_o).sum().item()} of {idx.numel()} "
+              f"max|dsim|={(sim - tk_sim_o).abs().max():.2e}", flush=True)
+
+
+def stage_time(precision, n, d, reps=3, topk=0):
+    s = synth.make_eval_set(n, d, seed=0, device="cuda", md5_ids=False)
+    plan = we.EvalPlan(s["c"], s["i"], s["c"], s["i"])
+    for _ in range(2):
+        out = plan.run(s["z"], s["z"], precision=precision, topk=(topk or None))
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for r in range(reps):
+        out = plan.run(s["z"], s["z"], precision=precision, topk=(topk or None))
+        ev[r + 1].record()
+    torch.cuda.synchronize()
+    ms = min(ev[r].elapsed_time(ev[r + 1]) for r in range(reps))
+    m, r1 = we.mean_metrics(out["sums"])
+    print(f"time {precision} n={n} d={d} topk={topk}: {ms:.2f} ms  {n * n / ms / 1e6:.1f} Gpairs/s  MAP={m:.4f} MR1={r1:.2f} "
+          f"pairs={plan.total_pairs}", flush=True)
+
+
+if __name__ == "__main__":
+    st = sys.argv[1]
+    a = sys.argv[2:]
+    if st == "sim":
+        stage_sim(a[0], int(a[1]), int(a[2]), int(a[3]), *(a[4:5]))
+    elif st == "eval":
+        stage_eval(a[0], int(a[1]), int(a[2]), int(a[3]) if len(a) > 3 else 0)
+    elif st == "time":
+        stage_time(a[0], int(a[1]), int(a[2]), 3, int(a[3]) if len(a) > 3 else 0)
