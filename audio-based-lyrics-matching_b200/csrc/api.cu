@@ -189,11 +189,13 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
     maps.b_lo = maps.b_hi;
   }
   auto kern = gemm_kernel<Epi, kPasses, kBlockK, kEpiWarps>;
-  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+  constexpr int kSmemBytes = SM::total(kEpiWarps, Epi::kWarpScratchBytes);
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int n_units = sh.n_row_blocks * sh.n_col_chunks;
   if (n_units == 0) return WEALY_OK;
   const int grid = n_units < num_sms() ? n_units : num_sms();
-  kern<<<grid, 64 + kEpiWarps * 32, SM::kTotal, s>>>(maps, sh, ep);
+  kern<<<grid, 64 + kEpiWarps * 32, kSmemBytes, s>>>(maps, sh, ep);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
 }

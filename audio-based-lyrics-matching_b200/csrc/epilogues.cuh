@@ -38,12 +38,13 @@ struct StoreParams {
 
 struct StoreEpi {
   using Params = StoreParams;
+  static constexpr int kWarpScratchBytes = 0;
   struct RowState {
     float rs, rq;
     bool valid;
   };
 
-  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape& sh) {
+  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape& sh, uint8_t*) {
     st.valid = row < sh.m_rows;
     st.rs = (st.valid && p.rscale) ? p.rscale[row] : 1.f;
     st.rq = (st.valid && p.rsq) ? p.rsq[row] : 0.f;
@@ -65,7 +66,7 @@ struct StoreEpi {
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape& sh) {
+                                                 const uint32_t (&acc)[32], const GemmShape& sh, uint8_t*) {
     if (!st.valid || col0 >= sh.n_cols) return;
     const int ncol = min(32, sh.n_cols - col0);
     float o[32];
@@ -95,7 +96,7 @@ struct StoreEpi {
     }
   }
 
-  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&) {}
+  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, uint8_t*) {}
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -133,37 +134,52 @@ struct EvalParams {
 
 struct EvalEpi {
   using Params = EvalParams;
+  // Per-warp work queue: the elements that pass the per-row limit are scattered unevenly over the
+  // 32 rows of a warp (a query with a poorly ranked relevant item passes almost everything, most
+  // queries pass nothing).  Handling them in place would serialise the warp on its hottest lane,
+  // so they are first compacted into a shared-memory queue and then processed 32 at a time with
+  // every lane busy, whatever row they came from.
+  static constexpr int kQueueCap = 256;
+  static constexpr int kWarpScratchBytes = kQueueCap * 4 + kQueueCap * 2 + 32 * 4;  // values, (lane,col) tags, top-k counts
   struct RowState {
-    float lim;      // min(lowest threshold, top-k filter)
+    float lim;      // min(lowest threshold, top-k filter): the only compare on the fast path
     float tlim;     // lowest threshold
     float tau;      // top-k filter (k-th best so far, -inf until k candidates are buffered)
-    int qc, qi, cnt, ncand;
+    int qc, qi, cnt;
     long long off;
     long long cbase;
   };
 
+  __device__ static __forceinline__ float* q_val(uint8_t* scratch) { return reinterpret_cast<float*>(scratch); }
+  __device__ static __forceinline__ uint16_t* q_tag(uint8_t* scratch) {
+    return reinterpret_cast<uint16_t*>(scratch + kQueueCap * 4);
+  }
+  __device__ static __forceinline__ int* n_cand(uint8_t* scratch) {
+    return reinterpret_cast<int*>(scratch + kQueueCap * 6);
+  }
+
   __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int part,
-                                                   const GemmShape& sh) {
+                                                   const GemmShape& sh, uint8_t* scratch) {
     st.tlim = __int_as_float(0x7f800000);
     st.tau = __int_as_float(0x7f800000);
-    st.qc = st.qi = st.cnt = st.ncand = 0;
+    st.qc = st.qi = st.cnt = 0;
     st.off = 0;
-    st.cbase = 0;
+    st.cbase = ((long long)part * p.nq_total + row) * p.cap;
     if (row < sh.m_rows) {
       st.tlim = p.lim[row];
       st.qc = p.q_c[row];
       st.qi = p.q_i[row];
       st.cnt = p.cnt[row];
       st.off = p.off[row];
-      if (p.topk > 0) {
-        st.tau = __int_as_float(0xff800000);
-        st.cbase = ((long long)part * p.nq_total + row) * p.cap;
-      }
+      if (p.topk > 0) st.tau = __int_as_float(0xff800000);
     }
     st.lim = fminf(st.tlim, st.tau);
+    __syncwarp();
+    n_cand(scratch)[ptx::lane_id()] = 0;
+    __syncwarp();
   }
 
-  // number of thresholds strictly below s (lower bound); thr[off .. off+cnt) ascending
+  // number of thresholds strictly below s (lower bound); thr[0 .. cnt) ascending
   __device__ static __forceinline__ int count_below(const float* __restrict__ thr, int cnt, float s) {
     int lo = 0, hi = cnt;
     while (lo < hi) {
@@ -180,7 +196,7 @@ struct EvalEpi {
     // rank(e) = #{f : val_f > val_e or (val_f == val_e and f < e)} < k ; survivors are scattered
     // to position rank (unique), staged in registers so reads complete before any write.
     constexpr int kMaxPerLane = 32;  // supports cap <= 1024
-    __syncwarp();  // the owning lane's appends must be visible to the whole warp
+    __syncwarp();  // appends of the other lanes must be visible to the whole warp
     float mv[kMaxPerLane];
     int mi[kMaxPerLane], mr[kMaxPerLane];
     int cntl = 0;
@@ -211,58 +227,110 @@ struct EvalEpi {
     return kth;
   }
 
-  __device__ static __forceinline__ void slow_path(const Params& p, RowState& st, float s, int col,
-                                                   const GemmShape& sh) {
-    if (col >= sh.n_cols) return;
-    const int ci = __ldg(p.c_i + col);
-    if (ci == st.qi) return;  // self (or a version-id collision): never a candidate
-    if (p.topk > 0 && s > st.tau) {
-      p.cand_val[st.cbase + st.ncand] = s;
-      p.cand_idx[st.cbase + st.ncand] = col;
-      ++st.ncand;
+  __device__ static __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
     }
-    if (s > st.tlim && __ldg(p.c_c + col) != st.qc) {
-      const int k = count_below(p.thr + st.off, st.cnt, s);
-      if (k > 0) atomicAdd(p.hist + st.off + (k - 1), 1u);
-    }
+    return v;
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape& sh) {
-    float mx = __uint_as_float(acc[0]);
+                                                 const uint32_t (&acc)[32], const GemmShape& sh, uint8_t* scratch) {
+    constexpr unsigned kFull = 0xffffffffu;
+    // ---- fast path: one compare per element, nothing else when no lane of the warp passes
+    unsigned m = 0;
 #pragma unroll
-    for (int e = 1; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(acc[e]));
-    if (mx > st.lim) {
+    for (int e = 0; e < 32; ++e) m |= (__uint_as_float(acc[e]) > st.lim) ? (1u << e) : 0u;
+    if (!__any_sync(kFull, m != 0)) return;
+
+    const int lane = (int)ptx::lane_id();
+    float* qv = q_val(scratch);
+    uint16_t* qt = q_tag(scratch);
+    int* ncand = n_cand(scratch);
+    // ids of the 32 candidates of this chunk, one per lane (coalesced), shared by every queued element
+    const int mycol = col0 + lane;
+    const int colok = mycol < sh.n_cols;
+    const int cc = colok ? __ldg(p.c_c + mycol) : 0;
+    const int ci = colok ? __ldg(p.c_i + mycol) : 0;
+
+    const int total = __shfl_sync(kFull, warp_incl_scan(__popc(m), lane), 31);
+    const int nb = total <= kQueueCap ? 1 : 4;  // 8 columns x 32 rows always fit
+    for (int bi = 0; bi < nb; ++bi) {
+      const unsigned mb = nb == 1 ? m : (m & (0xffu << (8 * bi)));
+      const int mine = __popc(mb);
+      const int incl = warp_incl_scan(mine, lane);
+      const int btotal = __shfl_sync(kFull, incl, 31);
+      if (btotal == 0) continue;
+      int pos = incl - mine;
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const float s = __uint_as_float(acc[e]);
-        if (s > st.lim) slow_path(p, st, s, col0 + e, sh);
+        if (mb & (1u << e)) {
+          qv[pos] = __uint_as_float(acc[e]);
+          qt[pos] = (uint16_t)((lane << 5) | e);
+          ++pos;
+        }
       }
+      __syncwarp();
+      for (int r0 = 0; r0 < btotal; r0 += 32) {
+        const int r = r0 + lane;
+        const bool active = r < btotal;
+        const float s = active ? qv[r] : 0.f;
+        const int tag = active ? (int)qt[r] : 0;
+        const int L = tag >> 5, e = tag & 31;  // owner lane (row) and column of the element
+        const int qc = __shfl_sync(kFull, st.qc, L);
+        const int qi = __shfl_sync(kFull, st.qi, L);
+        const int pc = __shfl_sync(kFull, st.cnt, L);
+        const float tl = __shfl_sync(kFull, st.tlim, L);
+        const float tau = __shfl_sync(kFull, st.tau, L);
+        const long long off = __shfl_sync(kFull, st.off, L);
+        const int ccol = __shfl_sync(kFull, cc, e);
+        const int cicol = __shfl_sync(kFull, ci, e);
+        const int ok = __shfl_sync(kFull, colok, e);
+        if (active && ok && cicol != qi) {  // i_j == i_q: self (or a version-id collision), never a candidate
+          if (p.topk > 0 && s > tau) {
+            const int slot = atomicAdd(&ncand[L], 1);
+            const long long cb = st.cbase + (long long)(L - lane) * p.cap + slot;  // rows of a warp are consecutive
+            p.cand_val[cb] = s;
+            p.cand_idx[cb] = col0 + e;
+          }
+          if (s > tl && ccol != qc) {  // a negative above at least the lowest relevant item
+            const int k = count_below(p.thr + off, pc, s);
+            if (k > 0) atomicAdd(p.hist + off + (k - 1), 1u);
+          }
+        }
+      }
+      __syncwarp();
     }
+
     if (p.topk > 0) {
-      // a row may gain up to 32 candidates per chunk: compact (warp-cooperatively, one row at a
-      // time) as soon as fewer than 32 free slots remain
-      unsigned need = __ballot_sync(0xffffffffu, st.ncand > p.cap - 32);
-      const int lane = (int)ptx::lane_id();
+      // a row gains at most 32 candidates per chunk: compact (warp-cooperatively, one row at a time)
+      // as soon as fewer than 32 free slots remain
+      unsigned need = __ballot_sync(kFull, ncand[lane] > p.cap - 32);
       while (need) {
         const int src = __ffs(need) - 1;
         need &= need - 1;
-        const long long cb = __shfl_sync(0xffffffffu, st.cbase, src);
-        const int n = __shfl_sync(0xffffffffu, st.ncand, src);
+        const long long cb = st.cbase + (long long)(src - lane) * p.cap;
+        const int n = ncand[src];
         const float kth = compact_row(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane);
         if (lane == src) {
-          st.ncand = p.topk;
+          ncand[lane] = p.topk;
           st.tau = kth;
           st.lim = fminf(st.tlim, st.tau);
         }
+        __syncwarp();
       }
     }
     (void)row;
   }
 
   __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part,
-                                                 const GemmShape& sh) {
-    if (p.topk > 0 && row < sh.m_rows) p.cand_cnt[(long long)part * p.nq_total + row] = st.ncand;
+                                                 const GemmShape& sh, uint8_t* scratch) {
+    __syncwarp();
+    if (p.topk > 0 && row < sh.m_rows) p.cand_cnt[(long long)part * p.nq_total + row] = n_cand(scratch)[ptx::lane_id()];
+    __syncwarp();
+    (void)st;
   }
 };
 

@@ -46,19 +46,22 @@ struct GemmSmem {
   static constexpr int kBBytes = kTileN * kBlockK * 2;
   static constexpr int kPlanes = kPasses == 3 ? 2 : 1;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kBudget = 227 * 1024 - 2048;  // alignment slack + barriers
+  static constexpr int kBudget = 227 * 1024 - 2048 - 16 * 1024;  // alignment slack + barriers + epilogue scratch
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;
+  static constexpr int kCore = kStages * kStageBytes + kBarBytes;  // + per-warp epilogue scratch + 1024 align slack
   static_assert(kStages >= 2, "need at least a double-buffered ring");
+  static constexpr int total(int epi_warps, int scratch_per_warp) { return kCore + epi_warps * scratch_per_warp + 1024; }
 };
 
 // Epilogue policy contract (all __device__, called by the epilogue warps only):
 //   struct Params;                      POD passed by value to the kernel
 //   struct RowState;                    per-thread state that lives across one unit
-//   static void row_begin(const Params&, RowState&, int row, int part, const GemmShape&);
-//   static void chunk32(const Params&, RowState&, int row, int col0, const uint32_t (&acc)[32], const GemmShape&);
-//   static void row_end(const Params&, RowState&, int row, int part, const GemmShape&);
+//   static constexpr int kWarpScratchBytes;   shared-memory scratch per epilogue warp (may be 0)
+//   static void row_begin(const Params&, RowState&, int row, int part, const GemmShape&, uint8_t* scratch);
+//   static void chunk32(const Params&, RowState&, int row, int col0, const uint32_t (&acc)[32], const GemmShape&,
+//                       uint8_t* scratch);
+//   static void row_end(const Params&, RowState&, int row, int part, const GemmShape&, uint8_t* scratch);
 // `row` is the global query row owned by the thread, `part` identifies the partial result slot
 // (column chunk x epilogue half) when a row is split over several units / warps.
 
@@ -79,6 +82,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* scratch_base = bar_base + SM::kBarBytes;
 
   const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = (int)ptx::lane_id();
@@ -196,7 +200,8 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       const int row = rb * kTileM + row_in_tile;
       const int part = chunk * kHalves + half;
       typename Epi::RowState rs;
-      Epi::row_begin(ep, rs, row, part, shape);
+      uint8_t* scratch = scratch_base + ew * Epi::kWarpScratchBytes;
+      Epi::row_begin(ep, rs, row, part, shape, scratch);
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&tmem_full[acc], acc_phase);
         ptx::tc_fence_after_sync();
@@ -206,14 +211,14 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
           uint32_t v[32];
           ptx::tmem_ld_32x32(taddr + (uint32_t)(c * kChunkCols), v);
           ptx::tmem_ld_wait();
-          Epi::chunk32(ep, rs, row, t * kTileN + c * kChunkCols, v, shape);
+          Epi::chunk32(ep, rs, row, t * kTileN + c * kChunkCols, v, shape, scratch);
         }
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      Epi::row_end(ep, rs, row, part, shape);
+      Epi::row_end(ep, rs, row, part, shape, scratch);
     }
   }
 

@@ -1,9 +1,173 @@
-extern "C" size_t wealy_loss_workspace_bytes(int64_t, int64_t, int) { return 0; }
-extern "C" int wealy_loss_forward(const wealy_loss_cfg*, const void*, int64_t, int64_t, int64_t, int, const int64_t*,
-                                  const int64_t*, double*, void*, size_t, void*) {
-  return fail(WEALY_ERR_UNSUPPORTED, "loss kernels not built yet");
+// a5 / a6: NT-Xent and CLEWS forward / backward (included by api.cu).
+//
+// Workspace layout (fixed by (b, d, passes) so that backward finds what forward left):
+//   U planes (hi[,lo] [b][d_pad], norm, scale, sq) | U^T planes (hi[,lo] [d][b_pad]) | W planes (hi[,lo] [b][b_pad])
+//   | dU [b][d] f32 | label, idx [b] i32 | partial [parts_max][b][8] f32 | rowstat [b][4] f32 | ZStats | scal | flags
+
+struct LossWs {
+  Planes u;
+  __half *ut_hi, *ut_lo;
+  __half *w_hi, *w_lo;
+  float* du;
+  int *label, *idx;
+  float* partial;
+  float* rowstat;
+  ZStats* zs;
+  float* scal;
+  int* bad;
+  int64_t b_pad;
+  int parts_max;
+  size_t bytes;
+};
+
+static void loss_ws_layout(LossWs& w, uint8_t* base, int64_t b, int64_t d, int passes) {
+  uint8_t* cur = base;
+  w.b_pad = pad_k(b);
+  carve_planes(w.u, cur, b, d, passes);
+  const size_t tplane = align_up((size_t)d * w.b_pad * 2, 1024);
+  w.ut_hi = reinterpret_cast<__half*>(cur); cur += tplane;
+  w.ut_lo = nullptr;
+  if (passes == 3) { w.ut_lo = reinterpret_cast<__half*>(cur); cur += tplane; }
+  const size_t wplane = align_up((size_t)b * w.b_pad * 2, 1024);
+  w.w_hi = reinterpret_cast<__half*>(cur); cur += wplane;
+  w.w_lo = nullptr;
+  if (passes == 3) { w.w_lo = reinterpret_cast<__half*>(cur); cur += wplane; }
+  w.du = reinterpret_cast<float*>(cur); cur += align_up((size_t)b * d * 4, 1024);
+  w.label = reinterpret_cast<int*>(cur); cur += align_up((size_t)b * 4, 256);
+  w.idx = reinterpret_cast<int*>(cur); cur += align_up((size_t)b * 4, 256);
+  w.parts_max = (int)ceil_div(b, kTileN) * 2;
+  w.partial = reinterpret_cast<float*>(cur); cur += align_up((size_t)w.parts_max * b * kStatWidth * 4, 1024);
+  w.rowstat = reinterpret_cast<float*>(cur); cur += align_up((size_t)b * 16, 256);
+  w.zs = reinterpret_cast<ZStats*>(cur); cur += 256;
+  w.scal = reinterpret_cast<float*>(cur); cur += 256;
+  w.bad = reinterpret_cast<int*>(cur); cur += 256;
+  w.bytes = (size_t)(cur - base);
 }
-extern "C" int wealy_loss_backward(const wealy_loss_cfg*, const void*, int64_t, int64_t, int64_t, int, const float*,
-                                   void*, int64_t, void*, size_t, void*) {
-  return fail(WEALY_ERR_UNSUPPORTED, "loss kernels not built yet");
+
+extern "C" size_t wealy_loss_workspace_bytes(int64_t b, int64_t d, int passes) {
+  if (b <= 0 || d <= 0) return 0;
+  LossWs w;
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(uintptr_t(1024)), b, d, passes);
+  return w.bytes + 1024;
+}
+
+static int loss_check(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t d, void* ws, size_t ws_bytes) {
+  if (!cfg || !z || !ws) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (cfg->kind != WEALY_LOSS_NTXENT && cfg->kind != WEALY_LOSS_CLEWS) return fail(WEALY_ERR_BAD_ARG, "unknown loss kind %d", cfg->kind);
+  if (cfg->passes != 1 && cfg->passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
+  if (b <= 0 || d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad shape b=%lld d=%lld", (long long)b, (long long)d);
+  if (b >= (1 << 24)) return fail(WEALY_ERR_UNSUPPORTED, "batch too large");
+  if (ws_bytes < wealy_loss_workspace_bytes(b, d, cfg->passes))
+    return fail(WEALY_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, wealy_loss_workspace_bytes(b, d, cfg->passes));
+  return WEALY_OK;
+}
+
+static void loss_params(LossParams& lp, const wealy_loss_cfg* cfg, const LossWs& w, int64_t b) {
+  memset(&lp, 0, sizeof(lp));
+  const float log2e = 1.4426950408889634f;
+  lp.kind = cfg->kind;
+  lp.b = (int)b;
+  lp.label = w.label;
+  lp.idx = w.idx;
+  lp.c2 = log2e / cfg->temperature;
+  lp.g2 = cfg->gamma * log2e;
+  lp.b2 = cfg->b * log2e;
+  lp.partial = w.partial;
+  lp.rowstat = w.rowstat;
+  lp.w_hi = w.w_hi;
+  lp.w_lo = w.w_lo;
+  lp.ldw = w.b_pad;
+}
+
+extern "C" int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
+                                  const int64_t* z_label, const int64_t* z_idx, double* out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  W_TRY(loss_check(cfg, z, b, d, workspace, workspace_bytes));
+  if (!z_label || !z_idx || !out) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  LossWs w;
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes);
+  const int T = 256;
+  CU_TRY(cudaMemsetAsync(w.zs, 0, 768, s));  // ZStats, scal, flags
+  CU_TRY(cudaMemsetAsync(out, 0, WEALY_OUT_COUNT * sizeof(double), s));
+  // the padded k-columns (j >= b) of the transposed planes must be zero
+  CU_TRY(cudaMemsetAsync(w.ut_hi, 0, (size_t)d * w.b_pad * 2, s));
+  if (w.ut_lo) CU_TRY(cudaMemsetAsync(w.ut_lo, 0, (size_t)d * w.b_pad * 2, s));
+  ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, w.label, (int)b, w.bad);
+  ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_idx, w.idx, (int)b, w.bad);
+  CU_TRY(cudaGetLastError());
+  const bool ntx = cfg->kind == WEALY_LOSS_NTXENT;
+  // NT-Xent: x/(|x|+1e-6) and statistics of the raw z; CLEWS: F.normalize (eps 1e-12), statistics of the normalised z
+  W_TRY(launch_prep(z, ldz, b, d, dtype, ntx ? kPrepL2AddEps : kPrepL2Clamp, ntx ? 1e-6f : 1e-12f, w.u, w.ut_hi,
+                    w.ut_lo, w.b_pad, w.zs, ntx ? 0 : 1, s));
+  LossParams lp;
+  loss_params(lp, cfg, w, b);
+  GemmShape sh;
+  fill_shape(sh, b, b, w.u.d_pad, 64, w.parts_max / 2);
+  const int halves = cfg->passes == 1 ? 2 : 1;
+  const int parts = sh.n_col_chunks * halves;
+  W_TRY(launch_gemm<LossStatsEpi>(cfg->passes, w.u, w.u, sh, lp, s));
+  LossCfgDev dc;
+  dc.kind = cfg->kind;
+  dc.temperature = cfg->temperature;
+  dc.gamma = cfg->gamma;
+  dc.b = cfg->b;
+  dc.eps = cfg->eps;
+  dc.epsilon = cfg->epsilon;
+  dc.uw = cfg->uw;
+  dc.numerically_friendly = cfg->numerically_friendly;
+  loss_finalize_kernel<<<1, 1024, 0, s>>>(dc, (int)b, (int)d, parts, w.partial, w.zs, w.rowstat, w.scal, out);
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+extern "C" int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
+                                   const float* grad_out, void* dz, int64_t ld_dz, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  W_TRY(loss_check(cfg, z, b, d, workspace, workspace_bytes));
+  if (!dz) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  LossWs w;
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes);
+  LossParams lp;
+  loss_params(lp, cfg, w, b);
+  // 1) W' = scale * (dL/dS + (dL/dS)^T): recompute S tile by tile, store fp16 hi/lo planes
+  GemmShape sh;
+  fill_shape(sh, b, b, w.u.d_pad, 64, 1 << 20);
+  W_TRY(launch_gemm<LossWEpi>(cfg->passes, w.u, w.u, sh, lp, s));
+  // 2) dU = W' * U   (A = W' [b][b_pad], B = U^T [d][b_pad], K = b_pad)
+  Planes pw, put;
+  pw.hi = w.w_hi; pw.lo = w.w_lo; pw.rows = b; pw.d_pad = w.b_pad;
+  put.hi = w.ut_hi; put.lo = w.ut_lo; put.rows = d; put.d_pad = w.b_pad;
+  StoreParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.out = w.du;
+  sp.ld = d;
+  sp.mode = kSimCossim;
+  sp.out_dtype = kOutF32;
+  sp.post = 1.f;
+  GemmShape sh2;
+  fill_shape(sh2, b, d, w.b_pad, 64, 1 << 20);
+  W_TRY(launch_gemm<StoreEpi>(cfg->passes, pw, put, sh2, sp, s));
+  // 3) normalisation Jacobian, upstream gradient, 1/(B tau) or 1/H
+  const int T = 256;
+  const unsigned blocks = (unsigned)ceil_div(b * 32, T);
+  switch (dtype) {
+    case WEALY_F32:
+      loss_jacobian_kernel<float><<<blocks, T, 0, s>>>(cfg->kind, (const float*)z, (long long)ldz, (int)b, (int)d, w.u.norm,
+                                                       w.du, w.scal, grad_out, (float*)dz, (long long)ld_dz);
+      break;
+    case WEALY_F16:
+      loss_jacobian_kernel<__half><<<blocks, T, 0, s>>>(cfg->kind, (const __half*)z, (long long)ldz, (int)b, (int)d,
+                                                        w.u.norm, w.du, w.scal, grad_out, (__half*)dz, (long long)ld_dz);
+      break;
+    case WEALY_BF16:
+      loss_jacobian_kernel<__nv_bfloat16><<<blocks, T, 0, s>>>(cfg->kind, (const __nv_bfloat16*)z, (long long)ldz, (int)b,
+                                                               (int)d, w.u.norm, w.du, w.scal, grad_out,
+                                                               (__nv_bfloat16*)dz, (long long)ld_dz);
+      break;
+    default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
+  }
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
 }

@@ -47,13 +47,14 @@ __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); 
 // ---------------------------------------------------------------------------------------------
 struct LossStatsEpi {
   using Params = LossParams;
+  static constexpr int kWarpScratchBytes = 0;
   struct RowState {
     int lab, id;
     bool valid;
     float a0, a1, a2, a3, a4, a5;
   };
 
-  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&) {
+  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, uint8_t*) {
     st.valid = row < p.b;
     st.lab = st.valid ? p.label[row] : 0;
     st.id = st.valid ? p.idx[row] : 0;
@@ -62,7 +63,7 @@ struct LossStatsEpi {
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape&) {
+                                                 const uint32_t (&acc)[32], const GemmShape&, uint8_t*) {
     if (!st.valid || col0 >= p.b) return;
     if (p.kind == kLossNtxent) {
       float l[32];
@@ -110,7 +111,7 @@ struct LossStatsEpi {
     }
   }
 
-  __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part, const GemmShape&) {
+  __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part, const GemmShape&, uint8_t*) {
     if (!st.valid) return;
     float* o = p.partial + ((long long)part * p.b + row) * kStatWidth;
     reinterpret_cast<float4*>(o)[0] = make_float4(st.a0, st.a1, st.a2, st.a3);
@@ -125,13 +126,14 @@ struct LossStatsEpi {
 // ---------------------------------------------------------------------------------------------
 struct LossWEpi {
   using Params = LossParams;
+  static constexpr int kWarpScratchBytes = 0;
   struct RowState {
     int lab, id;
     bool valid;
     float r0, r1, r2;
   };
 
-  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&) {
+  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, uint8_t*) {
     st.valid = row < p.b;
     st.lab = st.valid ? p.label[row] : 0;
     st.id = st.valid ? p.idx[row] : 0;
@@ -142,7 +144,7 @@ struct LossWEpi {
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape&) {
+                                                 const uint32_t (&acc)[32], const GemmShape&, uint8_t*) {
     if (!st.valid || col0 >= p.ldw) return;
     __align__(16) __half hi[32];
     __align__(16) __half lo[32];
@@ -181,7 +183,7 @@ struct LossWEpi {
     }
   }
 
-  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&) {}
+  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, uint8_t*) {}
 };
 
 // ---------------------------------------------------------------------------------------------

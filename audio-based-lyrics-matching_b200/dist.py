@@ -1,0 +1,66 @@
+"""Multi-GPU evaluation: queries partitioned over ranks, corpus replicated.
+
+Queries are independent units, so the data path needs no collective: rank r scores the
+contiguous query slice shard_range(Nq, r, world) against the whole corpus with the single-GPU
+fused kernel.  The only exchange is the result merge -- one all-reduce of {sum AP, sum R1,
+count} (24 bytes) for MAP / MR1 and, when per-query values are wanted, one all-gather of
+[Nq/world] x {ap, r1} (and of the top-k lists).  One process per GPU, torch.distributed (NCCL
+over NVLink / NVSwitch on the GPU box; gloo in the CPU tests of the merge logic).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n, rank, world):
+    """Contiguous, balanced partition of range(n): the first n % world ranks get one extra item."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def merge_sums(local_sums, group=None):
+    """All-reduce {sum AP, sum R1, count} -> (MAP, MR1, count) identical on every rank."""
+    s = local_sums.detach().clone().double()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
+    s = s.cpu()
+    n = max(float(s[2]), 1.0)
+    return float(s[0]) / n, float(s[1]) / n, int(s[2])
+
+
+def gather_rows(local, n_total, group=None):
+    """All-gather row-sharded results (shard_range layout) into the full [n_total, ...] tensor."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    longest = max(hi - lo for lo, hi in sizes)
+    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad, group=group)
+    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+def evaluate_sharded(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z, *, topk=None,
+                     precision=None, eps=1e-6, gather=True, group=None, plan=None):
+    """Every rank passes the FULL query / candidate tensors (or its own copy of them); rank r
+    scores its slice.  Returns dict(map, mr1, count[, aps, r1s, topk_idx, topk_sim]) on every rank."""
+    from .evaluation import EvalPlan
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    nq = len(queries_c)
+    lo, hi = shard_range(nq, rank, world)
+    own = plan is None
+    if own:
+        plan = EvalPlan(queries_c[lo:hi], queries_i[lo:hi], candidates_c, candidates_i)
+    res = plan.run(queries_z[lo:hi], candidates_z, topk=topk, eps=eps, precision=precision)
+    m, r1, cnt = merge_sums(res["sums"], group)
+    out = {"map": m, "mr1": r1, "count": cnt, "plan": plan}
+    if gather:
+        out["aps"] = gather_rows(res["aps"], nq, group)
+        out["r1s"] = gather_rows(res["r1s"], nq, group)
+        if topk:
+            out["topk_idx"] = gather_rows(res["topk_idx"], nq, group)
+            out["topk_sim"] = gather_rows(res["topk_sim"], nq, group)
+    return out

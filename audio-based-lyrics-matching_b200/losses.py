@@ -1,1 +1,150 @@
-"""placeholder -- filled in with the fused NT-Xent / CLEWS modules (build order: eval path first)."""
+"""Drop-in for the batch similarity-matrix contrastive losses of /root/reference/lib/losses.py,
+computed on sm_100a:
+
+  NTXentLoss(temperature=0.1).forward(z_label, z_idx, z, extra=None) -> (loss, logdict)   lib/losses.py:10-73
+  CLEWSLoss(gamma, b, eps, epsilon, uniformity_weight, warmup_steps)
+      .forward(z_label, z_idx, z, extra=None, numerically_friendly=True) -> (loss, logdict) lib/losses.py:176-285
+
+Same constructor arguments, forward signature, logdict keys and side effects (a single-label batch
+mutates the caller's z_label in place, lib/losses.py:34-35 / 221-222).  Forward and backward run in
+the fused tcgen05 kernels behind wealy_loss_forward / wealy_loss_backward (include/wealy_b200.h):
+the B x B similarity matrix is never stored; the backward recomputes it on the tensor cores.
+`loss` is differentiable w.r.t. z through a torch.autograd.Function; the logdict entries are
+detached diagnostics.  For fp16 / bf16 inputs the loss is returned in fp32 (the kernels accumulate
+in fp32; the reference would round it to the input dtype).  Inputs must be CUDA tensors.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from .tensor_ops import passes_of
+
+
+def _label_noise_(z_label):
+    """lib/losses.py:34-35: if the batch holds a single label, overwrite the first max(2, 1%) labels
+    with -1 IN PLACE.  Done without a host sync (the reference's .unique() forces one)."""
+    n = len(z_label)
+    k = max(2, int(n * 0.01))
+    single = (z_label == z_label[0]).all()
+    head = z_label[:k]
+    head.copy_(torch.where(single, torch.full_like(head, -1), head))
+
+
+class _FusedLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, z_label, z_idx, cfg_items):
+        cfg = N.LossCfg(**dict(cfg_items))
+        N.require_cuda(z, z_label, z_idx)
+        code = N.dtype_code(z.dtype)
+        zz = z if z.stride(1) == 1 else z.contiguous()
+        lab = z_label.to(torch.long).contiguous()
+        idx = z_idx.to(torch.long).contiguous()
+        b, d = zz.shape
+        with torch.cuda.device(zz.device):
+            ws_bytes = N.lib.wealy_loss_workspace_bytes(b, d, cfg.passes)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=zz.device)
+            out = torch.empty(N.OUT_COUNT, dtype=torch.float64, device=zz.device)
+            N.check(N.lib.wealy_loss_forward(ctypes.byref(cfg), zz.data_ptr(), b, zz.stride(0), d, code, lab.data_ptr(),
+                                             idx.data_ptr(), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                             N.stream_ptr(zz.device)))
+        ctx.save_for_backward(zz, ws)
+        ctx.cfg_items = cfg_items
+        loss_dtype = torch.float32 if z.dtype in (torch.float16, torch.bfloat16) else z.dtype
+        loss = out[0].to(loss_dtype)
+        ctx.mark_non_differentiable(out)
+        return loss, out
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_stats):
+        zz, ws = ctx.saved_tensors
+        cfg = N.LossCfg(**dict(ctx.cfg_items))
+        b, d = zz.shape
+        dz = torch.empty_like(zz)
+        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        with torch.cuda.device(zz.device):
+            N.check(N.lib.wealy_loss_backward(ctypes.byref(cfg), zz.data_ptr(), b, zz.stride(0), d,
+                                              N.dtype_code(zz.dtype), g.data_ptr(), dz.data_ptr(), dz.stride(0),
+                                              ws.data_ptr(), ws.numel(), N.stream_ptr(zz.device)))
+        return dz, None, None, None
+
+
+def _run(z, z_label, z_idx, **cfg):
+    base = dict(kind=0, passes=3, temperature=1.0, gamma=0.0, b=0.0, eps=1e-8, epsilon=1e-6, uw=0.0,
+                numerically_friendly=1)
+    base.update(cfg)
+    return _FusedLoss.apply(z, z_label, z_idx, tuple(sorted(base.items())))
+
+
+class NTXentLoss(nn.Module):
+    """lib/losses.py:10-73."""
+
+    def __init__(self, temperature=0.1, precision=None):
+        super().__init__()
+        self.tau = temperature
+        self.precision = precision
+
+    def forward(self, z_label, z_idx, z, extra=None):
+        assert len(z_label) == len(z_idx) and len(z_label) == len(z)
+        N.require_cuda(z, z_label, z_idx)
+        _label_noise_(z_label)
+        loss, st = _run(z, z_label, z_idx, kind=N.LOSS_NTXENT, passes=passes_of(self.precision),
+                        temperature=float(self.tau))
+        stats = st.to(loss.dtype)
+        logdict = {"l_main": loss, "v_zmax": stats[1], "v_zmean": stats[2], "v_zstd": stats[3]}
+        return loss, logdict
+
+
+class CLEWSLoss(nn.Module):
+    """lib/losses.py:176-285 (CLEWS-style alignment + uniformity on cosine distances)."""
+
+    def __init__(self, gamma: float = 8.0, b: float = 1.0, eps: float = 1e-8, epsilon: float = 1e-6,
+                 uniformity_weight: float = 0.5, warmup_steps: int = 1000, precision=None):
+        super().__init__()
+        self.gamma = float(gamma)
+        self.b = float(b)
+        self.eps = float(eps)
+        self.epsilon = float(epsilon)
+        self.uniformity_weight = float(uniformity_weight)
+        self.warmup_steps = int(warmup_steps)
+        self.precision = precision
+
+    def forward(self, z_label, z_idx, z, extra=None, numerically_friendly=True):
+        if z.dim() == 3:
+            assert z.size(1) == 1, f"CLEWS (vector) expects S=1, got S={z.size(1)}"
+            z = z.squeeze(1)
+        assert z.dim() == 2
+        B = z.size(0)
+        assert len(z_label) == len(z_idx) == B and B >= 4
+        N.require_cuda(z, z_label, z_idx)
+        _label_noise_(z_label)
+        # warm-up of the uniformity weight (lib/losses.py:248-258)
+        uw = self.uniformity_weight
+        if self.warmup_steps > 0:
+            step = None
+            if isinstance(extra, dict) and "global_step" in extra:
+                step = int(extra["global_step"])
+            elif hasattr(self, "global_step"):
+                step = int(self.global_step)
+            if step is not None:
+                uw = float(min(self.uniformity_weight, self.uniformity_weight * (step + 1) / self.warmup_steps))
+        loss, st = _run(z, z_label, z_idx, kind=N.LOSS_CLEWS, passes=passes_of(self.precision), gamma=self.gamma,
+                        b=self.b, eps=self.eps, epsilon=self.epsilon, uw=uw,
+                        numerically_friendly=1 if numerically_friendly else 0)
+        stats = st.to(loss.dtype)
+        logdict = {
+            "l_main": loss,
+            "l_cent": stats[4],
+            "l_cont": stats[5],
+            "cnt_pos_pairs": stats[6],
+            "cnt_neg_pairs": stats[7],
+            "anchors_with_pos": stats[8],
+            "v_dpos": stats[9],
+            "v_dneg": stats[10],
+            "uniformity_weight": torch.tensor(uw, device=z.device),
+            "z_max": stats[1],
+            "z_mean": stats[2],
+            "z_std": stats[3],
+        }
+        return loss, logdict

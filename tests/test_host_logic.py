@@ -1,0 +1,88 @@
+"""Host-side logic that needs no GPU: synthetic generator, query sharding and the result merge
+over a world_size-2 gloo group."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from wealy_b200 import dist as wd
+from wealy_b200.data import synth
+
+
+def test_clique_multisets_match_the_shipped_splits():
+    s = synth.clique_size_multiset("shs100k_test")
+    assert s.sum() == 10547 and s.size == 1692 and s.min() == 2 and s.max() == 162
+    s = synth.clique_size_multiset("lyric_covers_test")
+    assert s.sum() == 15584 and s.size == 4913 and s.max() == 66
+    assert synth.clique_size_multiset("shs100k_train").max() == 359
+
+
+@pytest.mark.parametrize("n", [64, 1000, 10547, 20001])
+def test_sampled_sizes_sum_and_have_no_singletons(n):
+    sizes = synth.sample_clique_sizes(n, "shs100k_test", seed=3)
+    assert sizes.sum() == n and sizes.min() >= 2
+
+
+def test_song_id_is_the_reference_hash():
+    # md5("12-3")[:4] big-endian & 0x7fffffff  (lib/embedding_dataset/utils.py:7-13)
+    import hashlib
+    ref = int.from_bytes(hashlib.md5(b"12-3").digest()[:4], "big") & 0x7FFFFFFF
+    assert synth.deterministic_song_id(12, 3) == ref and 0 <= ref < 2 ** 31
+
+
+def test_eval_set_shapes_and_determinism():
+    a = synth.make_eval_set(500, 32, seed=1)
+    b = synth.make_eval_set(500, 32, seed=1)
+    assert a["z"].shape == (500, 32) and a["z"].dtype == torch.float32 and a["c"].dtype == torch.long
+    assert torch.equal(a["z"], b["z"]) and torch.equal(a["i"], b["i"])
+    counts = torch.bincount(a["c"])
+    assert counts[counts > 0].min() >= 2
+
+
+def test_loss_batch():
+    s = synth.make_loss_batch(64, 16, seed=0, per_clique=4)
+    assert s["z"].shape == (64, 16) and torch.bincount(s["label"]).max() == 4
+    assert len(torch.unique(s["idx"])) == 62      # two duplicated sample ids
+
+
+@pytest.mark.parametrize("n,world", [(10, 1), (10, 3), (7, 8), (500000, 8), (0, 2)])
+def test_shard_range_partitions(n, world):
+    spans = [wd.shard_range(n, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == n
+    assert all(spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+    lens = [hi - lo for lo, hi in spans]
+    assert max(lens) - min(lens) <= 1
+
+
+def _worker(rank, world, port, n, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full_ap = torch.arange(n, dtype=torch.float32) / n
+        full_r1 = torch.arange(n, dtype=torch.float32) + 1
+        lo, hi = wd.shard_range(n, rank, world)
+        sums = torch.tensor([full_ap[lo:hi].double().sum(), full_r1[lo:hi].double().sum(), float(hi - lo)],
+                            dtype=torch.float64)
+        m, r1, cnt = wd.merge_sums(sums)
+        aps = wd.gather_rows(full_ap[lo:hi].clone(), n)
+        tk = wd.gather_rows(torch.arange(lo, hi)[:, None].repeat(1, 3), n)
+        ok = (cnt == n and abs(m - float(full_ap.double().mean())) < 1e-12
+              and abs(r1 - float(full_r1.double().mean())) < 1e-9
+              and torch.equal(aps, full_ap) and torch.equal(tk[:, 0], torch.arange(n)))
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [11, 64])
+def test_merge_over_gloo_world2(n):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, n, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

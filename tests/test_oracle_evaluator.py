@@ -1,0 +1,109 @@
+"""Known-answer and metamorphic tests of the evaluator oracle.  The reference has no evaluator
+(parity unpinned): these hand-computed cases ARE the specification the CUDA
+path is held to."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import evaluator as oev
+
+
+def _unit(vs):
+    z = torch.tensor(vs, dtype=torch.float32)
+    return z
+
+
+def test_kat_all_relevant_first():
+    # clique 0 = {0,1,2} tightly clustered, clique 1 = {3,4} far away -> every query ranks its clique first
+    z = _unit([[1, 0.01, 0], [1, 0.02, 0], [1, 0.03, 0], [0, 1, 0.01], [0, 1, 0.02]])
+    c = torch.tensor([0, 0, 0, 1, 1]); i = torch.arange(5)
+    aps, r1s = oev.evaluate_argsort(c, i, z, c, i, z)
+    assert torch.allclose(aps, torch.ones(5, dtype=torch.float64)) and torch.all(r1s == 1)
+
+
+def test_kat_hand_computed_ap():
+    # query 0 (clique 0): similarities to 1..5 are strictly decreasing; relevant = items 2 and 4
+    # ranks: item1 ->1, item2 ->2, item3 ->3, item4 ->4 ; AP = (1/2 + 2/4)/2 = 0.5 ; R1 = 2
+    ang = [0.0, 0.1, 0.2, 0.3, 0.4, 0.5]
+    z = _unit([[np.cos(a), np.sin(a)] for a in ang])
+    c = torch.tensor([0, 1, 0, 2, 0, 3]); i = torch.arange(6)
+    aps, r1s = oev.evaluate_argsort(c[:1], i[:1], z[:1], c, i, z)
+    assert abs(float(aps[0]) - 0.5) < 1e-12 and float(r1s[0]) == 2
+    a2, r2 = oev.evaluate_rankcount(c[:1], i[:1], z[:1], c, i, z)
+    assert abs(float(a2[0]) - 0.5) < 1e-12 and float(r2[0]) == 2
+
+
+def test_kat_worst_case():
+    # the single relevant item is the farthest of 4 candidates (self excluded): AP = 1/4, R1 = 4
+    ang = [0.0, 0.1, 0.2, 0.3, 1.5]
+    z = _unit([[np.cos(a), np.sin(a)] for a in ang])
+    c = torch.tensor([0, 1, 2, 3, 0]); i = torch.arange(5)
+    aps, r1s = oev.evaluate_argsort(c[:1], i[:1], z[:1], c, i, z)
+    assert abs(float(aps[0]) - 0.25) < 1e-12 and float(r1s[0]) == 4
+
+
+def test_self_is_by_id_not_position():
+    # a DIFFERENT track that collides on the version id is masked out like self (lib/losses.py:40-42)
+    ang = [0.0, 0.05, 0.2, 0.3]
+    z = _unit([[np.cos(a), np.sin(a)] for a in ang])
+    c = torch.tensor([0, 1, 0, 2]); i = torch.tensor([7, 7, 8, 9])   # item 1 collides with query 0
+    aps, r1s = oev.evaluate_argsort(c[:1], i[:1], z[:1], c, i, z)
+    assert float(r1s[0]) == 1 and float(aps[0]) == 1.0               # item 1 would otherwise rank first
+    # queries that are not part of the corpus: nothing is masked
+    aps2, r1s2 = oev.evaluate_argsort(torch.tensor([0]), torch.tensor([99]), z[:1], c[1:], i[1:], z[1:])
+    assert float(r1s2[0]) == 2
+
+
+def test_no_relevant_is_flagged():
+    z = torch.eye(3)
+    c = torch.tensor([0, 1, 2]); i = torch.arange(3)
+    with pytest.raises(ValueError):
+        oev.evaluate_argsort(c, i, z, c, i, z)
+
+
+def test_topk_matches_sort():
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(60, 16, generator=g)
+    c = torch.arange(60) // 3; i = torch.arange(60)
+    aps, r1s, idx, sim = oev.evaluate_argsort(c, i, z, c, i, z, topk=7)
+    assert idx.shape == (60, 7)
+    for q in (0, 17, 59):
+        s = torch.nn.functional.cosine_similarity(z[q:q + 1], z)
+        s[q] = -2
+        assert torch.equal(idx[q], torch.argsort(-s, stable=True)[:7])
+        assert q not in idx[q].tolist()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_argsort_equals_rankcount(seed):
+    g = torch.Generator().manual_seed(seed)
+    n, d = 300, 24
+    c = torch.randint(0, 60, (n,), generator=g)
+    # make sure every clique has >= 2 members
+    c = torch.cat([c, c])[:n] if False else c
+    counts = torch.bincount(c, minlength=60)
+    for k in torch.nonzero(counts == 1).flatten().tolist():
+        c[(c == k).nonzero()[0, 0]] = int(torch.argmax(counts))
+    z = torch.randn(n, d, generator=g, dtype=torch.float64)
+    i = torch.arange(n)
+    a1, r1 = oev.evaluate_argsort(c, i, z, c, i, z)
+    a2, r2 = oev.evaluate_rankcount(c, i, z, c, i, z)
+    assert torch.allclose(a1, a2, atol=1e-12) and torch.equal(r1, r2)
+
+
+def test_metamorphic_invariances():
+    g = torch.Generator().manual_seed(9)
+    n, d = 120, 16
+    c = torch.arange(n) // 4; i = torch.arange(n) + 1000
+    z = torch.randn(n, d, generator=g, dtype=torch.float64)
+    a0, r0 = oev.evaluate_argsort(c, i, z, c, i, z)
+    # permutation of the corpus does not change per-query results
+    perm = torch.randperm(n, generator=g)
+    a1, r1 = oev.evaluate_argsort(c, i, z, c[perm], i[perm], z[perm])
+    assert torch.allclose(a0, a1, atol=1e-12) and torch.equal(r0, r1)
+    # cosine ranking is invariant to per-row positive scaling
+    scale = torch.rand(n, 1, generator=g, dtype=torch.float64) * 5 + 0.1
+    a2, r2 = oev.evaluate_argsort(c, i, z * scale, c, i, z * scale)
+    assert torch.allclose(a0, a2, atol=1e-9) and torch.equal(r0, r2)
+    m, r = oev.mean_metrics(a0, r0)
+    assert 0 < m <= 1 and r >= 1

@@ -49,8 +49,8 @@ def stage_eval(precision, n, d, topk=0):
               f"max|dsim|={(sim - tk_sim_o).abs().max():.2e}", flush=True)
 
 
-def stage_time(precision, n, d, reps=3, topk=0):
-    s = synth.make_eval_set(n, d, seed=0, device="cuda", md5_ids=False)
+def stage_time(precision, n, d, reps=3, topk=0, sigma=2.4):
+    s = synth.make_eval_set(n, d, seed=0, device="cuda", md5_ids=False, sigma=sigma)
     plan = we.EvalPlan(s["c"], s["i"], s["c"], s["i"])
     for _ in range(2):
         out = plan.run(s["z"], s["z"], precision=precision, topk=(topk or None))
@@ -63,8 +63,78 @@ def stage_time(precision, n, d, reps=3, topk=0):
     torch.cuda.synchronize()
     ms = min(ev[r].elapsed_time(ev[r + 1]) for r in range(reps))
     m, r1 = we.mean_metrics(out["sums"])
-    print(f"time {precision} n={n} d={d} topk={topk}: {ms:.2f} ms  {n * n / ms / 1e6:.1f} Gpairs/s  MAP={m:.4f} MR1={r1:.2f} "
+    print(f"time {precision} n={n} d={d} topk={topk} sigma={sigma}: {ms:.2f} ms  {n * n / ms / 1e6:.1f} Gpairs/s  MAP={m:.4f} MR1={r1:.2f} "
           f"pairs={plan.total_pairs}", flush=True)
+
+
+def stage_loss(precision):
+    import numpy as np
+    from wealy_b200 import losses as wl
+    from oracle import losses as ol
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "losses.npz"))
+    for name in ("f64", "f32", "f32_big", "nopos", "single"):
+        z = torch.from_numpy(G[f"{name}_z"]).float()
+        lab = torch.from_numpy(G[f"{name}_label"]); idx = torch.from_numpy(G[f"{name}_idx"])
+        rows = torch.from_numpy(G[f"{name}_gradrows"])
+        for tag, mod, extra, kw in (("ntx", wl.NTXentLoss(0.1, precision=precision), None, {}),
+                                    ("ntx05", wl.NTXentLoss(0.5, precision=precision), None, {}),
+                                    ("clews", wl.CLEWSLoss(precision=precision), None, {}),
+                                    ("clews_step", wl.CLEWSLoss(gamma=6.0, b=0.5, uniformity_weight=0.8, warmup_steps=100, precision=precision), {"global_step": 9}, {}),
+                                    ("clews_nf", wl.CLEWSLoss(precision=precision), None, {"numerically_friendly": False})):
+            zz = z.cuda().requires_grad_(True)
+            lab_c = lab.cuda().clone()
+            loss, logd = mod(lab_c, idx.cuda(), zz, extra=extra, **kw)
+            loss.backward()
+            torch.cuda.synchronize()
+            ref_l = float(G[f"{name}_{tag}_loss"]); ref_g = torch.from_numpy(G[f"{name}_{tag}_grad"]).double()
+            g = zz.grad.cpu().double()[rows]
+            rel_l = abs(float(loss) - ref_l) / max(abs(ref_l), 1e-12)
+            rel_g = ((g - ref_g).norm() / ref_g.norm().clamp_min(1e-30)).item()
+            extra_s = ""
+            if tag in ("ntx", "clews"):
+                for k, v in logd.items():
+                    key = f"{name}_{tag}_log_{k}"
+                    if key in G.files:
+                        extra_s += f" {k}:{abs(float(v) - float(G[key])):.1e}"
+                extra_s += f" label_ok={bool((lab_c.cpu().numpy() == G[f'{name}_{tag}_label_after']).all())}"
+            print(f"loss {precision} {name}/{tag}: loss={float(loss):.6f} ref={ref_l:.6f} rel={rel_l:.2e} grad_relL2={rel_g:.2e}{extra_s}", flush=True)
+
+
+def stage_losstime(precision, b, d, dtype="bf16"):
+    from wealy_b200 import losses as wl
+    dt = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16}[dtype]
+    s = synth.make_loss_batch(b, d, seed=0, dtype=dt, device="cuda")
+    for nm, mod in (("ntxent", wl.NTXentLoss(0.1, precision=precision)), ("clews", wl.CLEWSLoss(precision=precision))):
+        z = s["z"].clone().requires_grad_(True)
+        for _ in range(3):
+            loss, _ = mod(s["label"], s["idx"], z); loss.backward()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            loss, _ = mod(s["label"], s["idx"], z)
+        e1.record()
+        for _ in range(reps):
+            loss, _ = mod(s["label"], s["idx"], z); loss.backward()
+        e2.record()
+        torch.cuda.synchronize()
+        print(f"losstime {nm} {precision} {dtype} b={b} d={d}: fwd {e0.elapsed_time(e1) / reps * 1e3:.1f} us  fwd+bwd {e1.elapsed_time(e2) / reps * 1e3:.1f} us loss={float(loss):.5f}", flush=True)
+
+
+def stage_simtime(precision, n, d):
+    x = torch.randn(n, d, device="cuda")
+    for _ in range(2):
+        out = wt.pairwise_distance_matrix(x, x, mode="cossim", precision=precision)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        out = wt.pairwise_distance_matrix(x, x, mode="cossim", precision=precision)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"simtime {precision} n={n} d={d}: {ms:.2f} ms {n * n / ms / 1e6:.1f} Gpairs/s  ({2 * n * n * d / ms / 1e9:.0f} TFLOP/s algorithmic)", flush=True)
 
 
 if __name__ == "__main__":
@@ -75,4 +145,10 @@ if __name__ == "__main__":
     elif st == "eval":
         stage_eval(a[0], int(a[1]), int(a[2]), int(a[3]) if len(a) > 3 else 0)
     elif st == "time":
-        stage_time(a[0], int(a[1]), int(a[2]), 3, int(a[3]) if len(a) > 3 else 0)
+        stage_time(a[0], int(a[1]), int(a[2]), 3, int(a[3]) if len(a) > 3 else 0, float(a[4]) if len(a) > 4 else 2.4)
+    elif st == "loss":
+        stage_loss(a[0])
+    elif st == "losstime":
+        stage_losstime(a[0], int(a[1]), int(a[2]), *(a[3:4]))
+    elif st == "simtime":
+        stage_simtime(a[0], int(a[1]), int(a[2]))
