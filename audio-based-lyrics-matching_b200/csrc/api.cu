@@ -282,6 +282,9 @@ struct wealy_eval_plan {
   size_t planes_cap = 0;
   void* topk_buf = nullptr;
   size_t topk_cap = 0;
+  // CUDA events bracketing the fused sweep of the last run (roofline accounting in bench.py)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
 };
 
 extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
@@ -294,6 +297,8 @@ extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
     if (p->c_c) cudaFree(p->c_c);
     if (p->c_i) cudaFree(p->c_i);
   }
+  if (p->ev0) cudaEventDestroy(p->ev0);
+  if (p->ev1) cudaEventDestroy(p->ev1);
   delete p;
 }
 
@@ -403,6 +408,14 @@ extern "C" int wealy_eval_plan_info(const wealy_eval_plan* p, int64_t* total_pai
   return WEALY_OK;
 }
 
+extern "C" int wealy_eval_plan_last_sweep_ms(const wealy_eval_plan* p, float* ms) {
+  if (!p || !ms) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (!p->timed) return fail(WEALY_ERR_BAD_ARG, "the plan has not been run yet");
+  CU_TRY(cudaEventSynchronize(p->ev1));
+  CU_TRY(cudaEventElapsedTime(ms, p->ev0, p->ev1));
+  return WEALY_OK;
+}
+
 static int topk_capacity(int k) { return (int)align_up((size_t)k + 96, 32); }
 
 extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
@@ -481,7 +494,14 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
     ep.cand_cnt = ep.cand_idx + slots;
     CU_TRY(cudaMemsetAsync(ep.cand_cnt, 0, (size_t)parts * nq * 4, s));
   }
+  if (!p->ev0) {
+    CU_TRY(cudaEventCreate(&p->ev0));
+    CU_TRY(cudaEventCreate(&p->ev1));
+  }
+  CU_TRY(cudaEventRecord(p->ev0, s));
   W_TRY(launch_gemm<EvalEpi>(passes, pq, pc, sh, ep, s));
+  CU_TRY(cudaEventRecord(p->ev1, s));
+  p->timed = true;
 
   {
     const int threads = 256;

@@ -122,7 +122,7 @@ struct LossStatsEpi {
 // ---------------------------------------------------------------------------------------------
 // W epilogue: W'_ij = scale * (dS_ij + dS_ji), stored as fp16 hi (+ lo) planes.
 //   NT-Xent rowstat = {M2, a', b', -}:  dS_ij = E_ij (b'_i - pos a'_i),  E_ij = exp2(l2_ij - M2_i)   (scale = B)
-//   CLEWS   rowstat = {ca', cu', -, -}: dS_ij = -pos ca'_i + X_ij neg cu'_i                          (scale = H)
+//   CLEWS   rowstat = {ca', cu', -, -}: dS_ij = -pos ca'_i + X_ij neg cu'_i                          (scale = S, see finalize)
 // ---------------------------------------------------------------------------------------------
 struct LossWEpi {
   using Params = LossParams;
@@ -190,7 +190,7 @@ struct LossWEpi {
 // finalize (single block): merge the partial records, reduce the loss and the logdict numbers,
 // write the per-row coefficients the W sweep needs.
 // out (double[WEALY_OUT_COUNT]) indices follow include/wealy_b200.h.
-// scal[0] = factor the Jacobian kernel applies to dU (1/(B tau) for NT-Xent, 1/H for CLEWS).
+// scal[0] = factor the Jacobian kernel applies to dU (1/(B tau) for NT-Xent, 1/S for CLEWS).
 // ---------------------------------------------------------------------------------------------
 struct LossCfgDev {
   int kind;
@@ -208,6 +208,24 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
   if (w == 0) {
     t = l < (int)(blockDim.x >> 5) ? sh[l] : 0.0;
     t = warp_sum_d(t);
+    if (l == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+
+__device__ __forceinline__ double block_max(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (w == 0) {
+    t = l < (int)(blockDim.x >> 5) ? sh[l] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
     if (l == 0) sh[32] = t;
   }
   __syncthreads();
@@ -272,13 +290,26 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(LossCfgDev cfg, int
     const double H = s_h > 0.0 ? s_h : 1.0;
     const double l_align = s_h > 0.0 ? s_align / s_h : 0.0;  // losses.py:239
     const double l_uni = s_uni / B;
+    // true coefficients: dS_ij = -pos ca_i + X_ij neg cu_i.  W is stored in fp16, so scale it by
+    // S = 1 / max_i max(ca_i, cu_i e^b): |W'| <= 2 whatever the batch looks like (no overflow, and the
+    // largest entries sit at the top of the fp16 range); the Jacobian kernel multiplies by 1/S.
+    float bound = 0.f;
     for (int i = threadIdx.x; i < b; i += blockDim.x) {
       const float4 r = reinterpret_cast<const float4*>(rowstat)[i];
       const float np = r.x, nn = r.y, uni = r.z;
-      const float ca = np > 0.f ? 1.f / np : 0.f;  // x H (the W scale) / (npos H)
+      const float ca = np > 0.f ? (float)(1.0 / ((double)np * H)) : 0.f;
       const float outer = cfg.numerically_friendly ? 1.f / (1.f + uni) : 1.f / (uni + cfg.epsilon);
-      const float cu = nn > 0.f ? (float)(H * (double)cfg.uw * (double)cfg.gamma / (B * (double)nn)) * outer : 0.f;
+      const float cu = nn > 0.f ? (float)((double)cfg.uw * (double)cfg.gamma / (B * (double)nn)) * outer : 0.f;
+      bound = fmaxf(bound, fmaxf(ca, fabsf(cu) * expf(cfg.b)));
       reinterpret_cast<float4*>(rowstat)[i] = make_float4(ca, cu, 0.f, 0.f);
+    }
+    bound = (float)block_max(bound, sh);
+    const float S = bound > 0.f ? 1.f / bound : 1.f;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+      float4 r = reinterpret_cast<const float4*>(rowstat)[i];
+      r.x *= S;
+      r.y *= S;
+      reinterpret_cast<float4*>(rowstat)[i] = r;
     }
     if (threadIdx.x == 0) {
       const double n2 = B * B;
@@ -291,7 +322,7 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(LossCfgDev cfg, int
       // tops.mmean(d, mask=pos_mask) averages over the COMPLEMENT of the mask (losses.py:267-268)
       out[9] = s_np > 0.0 ? (s_ad - s_pd) / fmax(n2 - s_np, 1e-7) : 0.0;
       out[10] = s_nn > 0.0 ? (s_ad - s_nd) / fmax(n2 - s_nn, 1e-7) : 0.0;
-      scal[0] = (float)(1.0 / H);
+      scal[0] = 1.f / S;
     }
   }
   if (threadIdx.x == 0) {

@@ -67,6 +67,12 @@ class EvalPlan:
         except Exception:
             pass
 
+    def last_sweep_ms(self):
+        """Device time of the fused similarity+ranking kernel of the last run (CUDA events)."""
+        ms = ctypes.c_float()
+        N.check(N.lib.wealy_eval_plan_last_sweep_ms(self._handle, ctypes.byref(ms)))
+        return ms.value
+
     def run(self, queries_z, candidates_z, *, topk=None, eps=1e-6, precision=None, allow_empty=False):
         """-> dict(aps, r1s, sums[, topk_idx, topk_sim]); `sums` = device doubles {sum AP, sum R1, #scored}."""
         if self.queries_without_relevant and not allow_empty:

@@ -90,6 +90,9 @@ int wealy_eval_plan_info(const wealy_eval_plan* plan, int64_t* total_pairs, int6
 int wealy_eval_run(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, const void* candidates_z, int64_t ld_c,
                    int64_t d, int dtype, float eps, int passes, int topk, float* aps, float* r1s, double* sums,
                    int64_t* topk_idx, float* topk_sim, void* stream);
+/* device time (CUDA events on the run's stream) of the fused similarity+ranking sweep of the last
+ * wealy_eval_run on this plan; blocks until that sweep has finished.                           */
+int wealy_eval_plan_last_sweep_ms(const wealy_eval_plan* plan, float* ms);
 void wealy_eval_plan_destroy(wealy_eval_plan* plan);
 
 /* ---- a5/a6: batch similarity-matrix contrastive losses -------------------------------------

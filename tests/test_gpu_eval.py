@@ -1,0 +1,199 @@
+"""-m gpu: fused evaluation (wealy_eval_run through the C ABI) vs the evaluator oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import evaluator as oev
+
+pytestmark = pytest.mark.gpu
+
+
+def _we():
+    from wealy_b200 import evaluation as we
+    return we
+
+
+def _synth():
+    from wealy_b200.data import synth
+    return synth
+
+
+def _gpu_eval(c, i, z, cc=None, ci=None, cz=None, **kw):
+    cc = c if cc is None else cc
+    ci = i if ci is None else ci
+    cz = z if cz is None else cz
+    same = cc is c and cz is z
+    cq, iq, zq = c.cuda(), i.cuda(), z.cuda()
+    if same:
+        res = _we().evaluate(cq, iq, zq, cq, iq, zq, **kw)
+    else:
+        res = _we().evaluate(cq, iq, zq, cc.cuda(), ci.cuda(), cz.cuda(), **kw)
+    torch.cuda.synchronize()
+    return [r.cpu() for r in res]
+
+
+def _unit(angles):
+    return torch.tensor([[np.cos(a), np.sin(a)] for a in angles], dtype=torch.float32)
+
+
+def test_kat_hand_computed():
+    # same cases as tests/test_oracle_evaluator.py, now through the CUDA path
+    z = torch.tensor([[1, 0.01, 0], [1, 0.02, 0], [1, 0.03, 0], [0, 1, 0.01], [0, 1, 0.02]], dtype=torch.float32)
+    c = torch.tensor([0, 0, 0, 1, 1]); i = torch.arange(5)
+    aps, r1s = _gpu_eval(c, i, z)
+    assert torch.allclose(aps, torch.ones(5)) and torch.all(r1s == 1)
+
+    z = _unit([0.0, 0.1, 0.2, 0.3, 0.4, 0.5])
+    c = torch.tensor([0, 1, 0, 2, 0, 3]); i = torch.arange(6)
+    aps, r1s = _gpu_eval(c[:1], i[:1], z[:1], c, i, z)
+    assert abs(float(aps[0]) - 0.5) < 1e-6 and float(r1s[0]) == 2
+
+    z = _unit([0.0, 0.1, 0.2, 0.3, 1.5])
+    c = torch.tensor([0, 1, 2, 3, 0]); i = torch.arange(5)
+    aps, r1s = _gpu_eval(c[:1], i[:1], z[:1], c, i, z)
+    assert abs(float(aps[0]) - 0.25) < 1e-6 and float(r1s[0]) == 4
+
+
+def test_self_is_by_id_not_position():
+    z = _unit([0.0, 0.05, 0.2, 0.3])
+    c = torch.tensor([0, 1, 0, 2]); i = torch.tensor([7, 7, 8, 9])
+    aps, r1s = _gpu_eval(c[:1], i[:1], z[:1], c, i, z)
+    assert float(r1s[0]) == 1 and float(aps[0]) == 1.0
+    aps, r1s = _gpu_eval(torch.tensor([0]), torch.tensor([99]), z[:1], c[1:], i[1:], z[1:])
+    assert float(r1s[0]) == 2
+
+
+def test_no_relevant_is_flagged():
+    z = torch.eye(3)
+    c = torch.tensor([0, 1, 2]); i = torch.arange(3)
+    with pytest.raises(ValueError):
+        _gpu_eval(c, i, z)
+    c = torch.tensor([0, 0, 2])
+    aps, r1s = _gpu_eval(c, i, z, allow_empty=True)
+    assert torch.isnan(aps[2]) and torch.isnan(r1s[2]) and float(aps[0]) == 1.0
+
+
+def _parity(s, precision="fp16x3", topk=None, d_map=1e-4, d_mr1=1e-4, gap=1e-5):
+    aps_o, r1_o = oev.evaluate_argsort(s["c"], s["i"], s["z"], s["c"], s["i"], s["z"])
+    res = _gpu_eval(s["c"], s["i"], s["z"], precision=precision, topk=topk)
+    aps, r1s = res[0].double(), res[1].double()
+    assert abs(float(aps.mean()) - float(aps_o.mean())) <= d_map            # MAP within 1e-4
+    assert abs(float(r1s.mean()) - float(r1_o.mean())) <= d_mr1 * max(1.0, float(r1_o.mean()))
+    if precision == "fp16x3":
+        # ranks bit-exact wherever the similarity gap exceeds 1e-5: R1 must lie in the range the
+        # candidates within 1e-5 of the best relevant item allow
+        lo, hi = oev.rank_tolerance(s["c"], s["i"], s["z"], s["c"], s["i"], s["z"], gap=gap)
+        assert bool(((r1s >= lo) & (r1s <= hi)).all())
+        exact = (lo == hi)
+        assert torch.equal(r1s[exact], r1_o[exact])
+    return res, aps_o, r1_o
+
+
+@pytest.mark.parametrize("n,d,seed", [(700, 64, 0), (2000, 128, 1), (3000, 1024, 2), (1300, 200, 3)])
+def test_parity_with_oracle(n, d, seed):
+    s = _synth().make_eval_set(n, d, seed=seed)
+    _parity(s)
+
+
+def test_single_pass_mode_is_map_accurate():
+    s = _synth().make_eval_set(3000, 256, seed=4)
+    _parity(s, precision="fp16", d_map=1e-4, d_mr1=2e-3)
+
+
+def test_topk_matches_oracle():
+    s = _synth().make_eval_set(2500, 256, seed=5)
+    k = 20
+    (aps, r1s, idx, sim), _, _ = _parity(s, topk=k)
+    _, _, idx_o, sim_o = oev.evaluate_argsort(s["c"], s["i"], s["z"], s["c"], s["i"], s["z"], topk=k)
+    assert idx.shape == (2500, k) and idx.dtype == torch.long
+    assert (sim - sim_o).abs().max() <= 4e-6                                  # the k best similarities agree
+    # indices exact wherever neighbouring similarities are more than 1e-5 apart
+    gaps_ok = torch.ones_like(idx_o, dtype=torch.bool)
+    gaps_ok[:, 1:] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    gaps_ok[:, :-1] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    assert torch.equal(idx[gaps_ok], idx_o[gaps_ok])
+    assert bool((idx != torch.arange(2500)[:, None]).all())                   # self never returned
+
+
+def test_topk_larger_than_corpus_and_k1():
+    s = _synth().make_eval_set(40, 16, seed=6)
+    aps, r1s, idx, sim = _gpu_eval(s["c"], s["i"], s["z"], topk=100)
+    assert idx.shape == (40, 40)
+    assert bool((idx[:, -1] == -1).all()) and bool(torch.isinf(sim[:, -1]).all())   # only 39 candidates exist
+    aps, r1s, idx1, sim1 = _gpu_eval(s["c"], s["i"], s["z"], topk=1)
+    assert torch.equal(idx1[:, 0], idx[:, 0])
+
+
+def test_queries_disjoint_from_corpus_and_collisions():
+    syn = _synth()
+    s = syn.make_eval_set(1500, 96, seed=7)
+    q = slice(0, 300)
+    cand = slice(300, 1500)
+    # give some candidates the version id of a query from ANOTHER clique (md5 id collisions at scale)
+    i2 = s["i"].clone()
+    i2[400] = s["i"][5]
+    i2[401] = s["i"][6]
+    # keep only queries that still have a relevant candidate in the reduced corpus
+    keep = torch.tensor([bool(((s["c"][cand] == s["c"][k]) & (i2[cand] != s["i"][k])).any()) for k in range(300)])
+    qc, qi, qz = s["c"][q][keep], s["i"][q][keep], s["z"][q][keep]
+    aps_o, r1_o = oev.evaluate_argsort(qc, qi, qz, s["c"][cand], i2[cand], s["z"][cand])
+    aps, r1s = _gpu_eval(qc, qi, qz, s["c"][cand], i2[cand], s["z"][cand])
+    assert abs(float(aps.double().mean()) - float(aps_o.mean())) <= 1e-4
+    assert (r1s.double() != r1_o).sum() <= 2
+
+
+def test_exact_duplicates_and_giant_clique():
+    g = torch.Generator().manual_seed(8)
+    n_big = 359                                         # largest clique of SHS100K-TRAIN
+    z = torch.randn(900, 64, generator=g)
+    c = torch.cat([torch.zeros(n_big, dtype=torch.long), 1 + torch.arange(900 - n_big) // 3])
+    z[:n_big] += 0.8 * torch.randn(1, 64, generator=g)
+    z[10] = z[11]                                       # exact duplicates inside the clique (ties)
+    z[500] = z[20]                                      # a negative that ties with a relevant item
+    i = torch.arange(900)
+    aps_o, r1_o = oev.evaluate_argsort(c, i, z, c, i, z)
+    aps, r1s = _gpu_eval(c, i, z)
+    assert abs(float(aps.double().mean()) - float(aps_o.mean())) <= 1e-4
+    lo, hi = oev.rank_tolerance(c, i, z, c, i, z, gap=1e-5)
+    assert bool(((r1s.double() >= lo) & (r1s.double() <= hi)).all())
+
+
+def test_plan_reuse_and_half_precision_inputs():
+    s = _synth().make_eval_set(1200, 128, seed=9)
+    we = _we()
+    c, i = s["c"].cuda(), s["i"].cuda()
+    plan = we.EvalPlan(c, i, c, i)
+    assert plan.total_pairs > 0 and plan.queries_without_relevant == 0 and plan.max_relevant >= 1
+    z1 = s["z"].cuda()
+    r1 = plan.run(z1, z1)
+    z2 = (s["z"] * 0.5 + 0.1).cuda()
+    r2 = plan.run(z2, z2)
+    r1b = plan.run(z1, z1)
+    assert torch.equal(r1["aps"], r1b["aps"]) and not torch.equal(r1["aps"], r2["aps"])
+    zh = s["z"].half().cuda()
+    rh = plan.run(zh, zh)
+    aps_o, _ = oev.evaluate_argsort(s["c"], s["i"], s["z"].half().float(), s["c"], s["i"], s["z"].half().float())
+    assert abs(float(rh["aps"].double().mean()) - float(aps_o.mean())) <= 1e-4
+    m, r = we.mean_metrics(r1["sums"])
+    assert abs(m - float(r1["aps"].double().mean())) < 1e-6
+    plan.close()
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] size (100k x 1024): per-query results are invariant under a permutation of
+    the corpus, and a query sample agrees with the CPU oracle."""
+    syn, we = _synth(), _we()
+    n = 100_000
+    s = syn.make_eval_set(n, 1024, seed=0, device="cuda", md5_ids=False)
+    z, c, i = s["z"], s["c"], s["i"]
+    aps, r1s = we.evaluate(c, i, z, c, i, z)
+    perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    aps_p, r1_p = we.evaluate(c, i, z, c[perm], i[perm], z[perm])
+    assert (aps - aps_p).abs().max() <= 1e-6 and torch.equal(r1s, r1_p)
+    nq = 128
+    zc, cc, ic = z.cpu(), c.cpu(), i.cpu()
+    aps_o, r1_o = oev.evaluate_argsort(cc[:nq], ic[:nq], zc[:nq], cc, ic, zc)
+    assert abs(float(aps[:nq].double().mean().cpu()) - float(aps_o.mean())) <= 1e-4
+    lo, hi = oev.rank_tolerance(cc[:nq], ic[:nq], zc[:nq], cc, ic, zc, gap=1e-5)
+    r = r1s[:nq].double().cpu()
+    assert bool(((r >= lo) & (r <= hi)).all())

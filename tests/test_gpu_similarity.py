@@ -1,0 +1,133 @@
+"""-m gpu: CUDA pairwise_distance_matrix (through the C ABI) vs the reference's outputs
+(tests/golden/sim_modes.npz) and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import similarity as osim
+
+pytestmark = pytest.mark.gpu
+
+MODES = ("fro", "nfro", "euc", "neuc", "sqeuc", "nsqeuc", "cos", "cossim", "dot", "dotsim")
+
+
+def _wt():
+    from wealy_b200 import tensor_ops as wt
+    return wt
+
+
+def _check_mode(got, ref, x, y, mode, single_pass=False):
+    """Tolerances: fp16x3 is fp32-grade (|err| ~ 1e-6 on unit vectors); everything is scaled by
+    the row norms for the un-normalised modes.  Euclidean modes are compared on squared values
+    (sqrt amplifies the cancellation error of |x|^2 - 2xy + |y|^2 near zero, as in the reference)."""
+    got, ref = got.double().cpu(), ref.double()
+    nx = x.double().norm(dim=-1)[:, None] if x.ndim == 2 else x.double().abs()[:, None]
+    ny = y.double().norm(dim=-1)[None, :] if y.ndim == 2 else y.double().abs()[None, :]
+    unit = 3e-4 if single_pass else 4e-6
+    d = x.shape[-1] if x.ndim == 2 else 1
+    if mode in ("cos", "cossim"):
+        assert (got - ref).abs().max() <= unit
+    elif mode in ("dot", "dotsim"):
+        assert ((got - ref).abs() <= unit * (nx * ny) + 1e-6).all()
+    else:
+        scale = {"sqeuc": 1.0, "nsqeuc": float(d), "fro": 1.0, "euc": 1.0, "nfro": d ** 0.5, "neuc": d ** 0.5}[mode]
+        g2, r2 = got * scale, ref * scale
+        if mode not in ("sqeuc", "nsqeuc"):
+            g2, r2 = g2 ** 2, r2 ** 2
+        assert ((g2 - r2).abs() <= 4 * unit * (nx ** 2 + ny ** 2) + 1e-6).all()
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c", "vec"])
+@pytest.mark.parametrize("mode", MODES)
+def test_modes_against_reference_outputs(golden, case, mode):
+    G = golden("sim_modes.npz")
+    x, y = torch.from_numpy(G[f"{case}_x"]), torch.from_numpy(G[f"{case}_y"])
+    got = _wt().pairwise_distance_matrix(x.cuda(), y.cuda(), mode=mode)
+    ref = torch.from_numpy(G[f"{case}_{mode}"])
+    assert got.shape == ref.shape and got.dtype == torch.float32 and got.is_cuda
+    assert not torch.isnan(got).any()
+    _check_mode(got, ref, x, y, mode)
+
+
+def test_zero_vector_and_duplicate(golden):
+    G = golden("sim_modes.npz")
+    x, y = torch.from_numpy(G["a_x"]).cuda(), torch.from_numpy(G["a_y"]).cuda()
+    cs = _wt().pairwise_distance_matrix(x, y, mode="cossim").cpu()
+    assert torch.all(cs[3] == 0)                        # zero vector -> exactly 0, never NaN
+    assert abs(float(cs[7, 5]) - 1.0) < 4e-6           # exact duplicate
+
+
+@pytest.mark.parametrize("tag,dt,tol", [("bf16", torch.bfloat16, 1.6e-2), ("f16", torch.float16, 2e-3)])
+def test_output_dtype_follows_input(golden, tag, dt, tol):
+    G = golden("sim_modes.npz")
+    x = torch.from_numpy(G["dt_x"]).to(dt).cuda()
+    got = _wt().pairwise_distance_matrix(x, x, mode="cossim")
+    assert got.dtype == dt
+    # the reference rounds every intermediate to the half type; we accumulate in fp32 -> compare
+    # against both the reference's output and the exact value with the half type's resolution
+    exact = osim.distance_matrix(x.cpu().double(), x.cpu().double(), mode="cossim")
+    assert (got.cpu().double() - exact).abs().max() <= tol / 2
+    assert (got.cpu().double() - torch.from_numpy(G[f"dt_{tag}"])).abs().max() <= tol
+
+
+def test_float64_is_rejected_loudly():
+    x = torch.randn(4, 8, dtype=torch.float64, device="cuda")
+    with pytest.raises(NotImplementedError):
+        _wt().pairwise_distance_matrix(x, x, mode="cossim")
+
+
+@pytest.mark.parametrize("n,m,d", [(1, 1, 1), (1, 300, 7), (129, 255, 65), (257, 513, 1024), (128, 256, 64), (5, 3, 2000)])
+@pytest.mark.parametrize("precision", ["fp16x3", "fp16"])
+def test_ragged_shapes_against_oracle(n, m, d, precision):
+    g = torch.Generator().manual_seed(n * 1000 + m + d)
+    x = torch.randn(n, d, generator=g) * 2
+    y = torch.randn(m, d, generator=g) * 0.5
+    for mode in ("cossim", "dot", "sqeuc"):
+        ref = osim.distance_matrix(x.double(), y.double(), mode=mode)
+        got = _wt().pairwise_distance_matrix(x.cuda(), y.cuda(), mode=mode, precision=precision)
+        _check_mode(got, ref, x, y, mode, single_pass=(precision == "fp16"))
+
+
+def test_empty_inputs():
+    x = torch.randn(0, 16, device="cuda")
+    y = torch.randn(5, 16, device="cuda")
+    assert _wt().pairwise_distance_matrix(x, y, mode="cos").shape == (0, 5)
+    assert _wt().pairwise_distance_matrix(y, x, mode="cos").shape == (5, 0)
+
+
+def test_row_strided_input_and_same_tensor_fast_path():
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(200, 96, generator=g).cuda()
+    x = big[:, :40]                                    # row stride 96, inner stride 1
+    ref = osim.distance_matrix(x.cpu().double(), x.cpu().double(), mode="cos")
+    got = _wt().pairwise_distance_matrix(x, x, mode="cos")
+    assert (got.cpu().double() - ref).abs().max() <= 4e-6
+    xt = big.t()[:50]                                  # inner stride != 1 -> made contiguous
+    ref = osim.distance_matrix(xt.cpu().double(), xt.cpu().double(), mode="cossim")
+    got = _wt().pairwise_distance_matrix(xt, xt, mode="cossim")
+    assert (got.cpu().double() - ref).abs().max() <= 4e-6
+
+
+def test_metamorphic_identities():
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(300, 128, generator=g).cuda()
+    y = torch.randn(200, 128, generator=g).cuda()
+    wt = _wt()
+    cs = wt.pairwise_distance_matrix(x, y, mode="cossim")
+    assert torch.equal(wt.pairwise_distance_matrix(x, y, mode="cos"), 1 - cs)          # cos == 1 - cossim
+    scaled = wt.pairwise_distance_matrix(x * 8.0, y * 0.25, mode="cossim")             # power-of-two scale invariance
+    assert (scaled - cs).abs().max() <= 2e-6
+    assert (wt.pairwise_distance_matrix(y, x, mode="cossim").t() - cs).abs().max() <= 2e-6   # symmetry
+    eu = wt.pairwise_euclidean_distance_matrix(x, y)
+    sq = wt.pairwise_euclidean_distance_matrix(x, y, squared=True)
+    assert (eu ** 2 - sq).abs().max() <= 1e-3
+
+
+def test_error_behaviour_matches_reference():
+    x = torch.randn(4, 8, device="cuda")
+    with pytest.raises(NotImplementedError):
+        _wt().pairwise_distance_matrix(x, x, mode="nope")          # lib/tensor_ops.py:175
+    with pytest.raises(NotImplementedError):
+        _wt().pairwise_distance_matrix(x, x, mode="fro", p=3)      # documented gap: cdist p != 2
+    with pytest.raises(AssertionError):
+        _wt().pairwise_distance_matrix(x[None], x[None])            # lib/tensor_ops.py:153
