@@ -189,7 +189,7 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
     maps.b_lo = maps.b_hi;
   }
   auto kern = gemm_kernel<Epi, kPasses, kBlockK, kEpiWarps>;
-  constexpr int kSmemBytes = SM::total(kEpiWarps, Epi::kWarpScratchBytes);
+  constexpr int kSmemBytes = SM::total(kEpiWarps, Epi::kWarpScratchBytes, Epi::kCtaScratchBytes);
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int n_units = sh.n_row_blocks * sh.n_col_chunks;
@@ -208,9 +208,10 @@ static int launch_gemm(int passes, const Planes& a, const Planes& b, GemmShape& 
     if (a.lo == nullptr || b.lo == nullptr) return fail(WEALY_ERR_BAD_ARG, "3-pass contraction needs lo planes");
     if (bk == 32) {
       sh.k_blocks = (int)(a.d_pad / 32);
-      return launch_gemm_t<Epi, 3, 32, 4>(a, b, sh, ep, s);
+      return launch_gemm_t<Epi, 3, 32, 8>(a, b, sh, ep, s);
     }
-    return launch_gemm_t<Epi, 3, 64, 4>(a, b, sh, ep, s);
+    if (env_int("WEALY_EPI_WARPS", 8) == 4) return launch_gemm_t<Epi, 3, 64, 4>(a, b, sh, ep, s);
+    return launch_gemm_t<Epi, 3, 64, 8>(a, b, sh, ep, s);
   }
   if (passes == 1) return launch_gemm_t<Epi, 1, 64, 8>(a, b, sh, ep, s);
   return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3, got %d", passes);
@@ -460,8 +461,8 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
   CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
 
   GemmShape sh;
-  fill_shape(sh, nq, nc, pq.d_pad, 64, topk > 0 ? 8 : (1 << 20));
-  const int halves = passes == 1 ? 2 : 1;
+  fill_shape(sh, nq, nc, pq.d_pad, 64, topk > 0 ? 2 : (1 << 20));  // top-k: <= 2 chunks x 2 halves = 4 candidate lists per query
+  const int halves = (passes == 3 && env_int("WEALY_EPI_WARPS", 8) == 4 && env_int("WEALY_BLOCK_K", 64) == 64) ? 1 : 2;
   const int parts = sh.n_col_chunks * halves;
   const int cap = topk > 0 ? topk_capacity(topk) : 0;
 
@@ -481,7 +482,7 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
   ep.nq_total = (int)nq;
   if (topk > 0) {
     const size_t slots = (size_t)parts * nq * cap;
-    const size_t tneed = slots * 8 + (size_t)parts * nq * 4 + 1024;
+    const size_t tneed = slots * 16 + (size_t)parts * nq * 4 + 1024;  // candidate lists + finalize staging
     if (tneed > p->topk_cap) {
       if (p->topk_buf) CU_TRY(cudaFree(p->topk_buf));
       p->topk_buf = nullptr;
@@ -509,8 +510,16 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
     ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)nq, aps, r1s, sums);
     CU_TRY(cudaGetLastError());
     if (topk > 0) {
-      topk_finalize_kernel<<<blocks, threads, 0, s>>>(ep.cand_val, ep.cand_idx, ep.cand_cnt, parts, (int)nq, cap, topk,
-                                                      (long long*)topk_idx, topk_sim);
+      if (cap <= 256 && parts <= 4) {
+        float* stage_val = reinterpret_cast<float*>(ep.cand_cnt + (size_t)parts * nq);
+        int* stage_idx = reinterpret_cast<int*>(stage_val + (size_t)parts * nq * cap);
+        topk_finalize_select_kernel<<<(unsigned)ceil_div(nq * 32, 128), 128, 0, s>>>(
+            ep.cand_val, ep.cand_idx, ep.cand_cnt, parts, (int)nq, cap, topk, stage_val, stage_idx,
+            (long long*)topk_idx, topk_sim);
+      } else {
+        topk_finalize_kernel<<<blocks, threads, 0, s>>>(ep.cand_val, ep.cand_idx, ep.cand_cnt, parts, (int)nq, cap, topk,
+                                                        (long long*)topk_idx, topk_sim);
+      }
       CU_TRY(cudaGetLastError());
     }
   }

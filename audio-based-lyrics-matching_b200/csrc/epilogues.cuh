@@ -39,12 +39,13 @@ struct StoreParams {
 struct StoreEpi {
   using Params = StoreParams;
   static constexpr int kWarpScratchBytes = 0;
+  static constexpr int kCtaScratchBytes = 0;
   struct RowState {
     float rs, rq;
     bool valid;
   };
 
-  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape& sh, uint8_t*) {
+  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape& sh, const EpiCtx&) {
     st.valid = row < sh.m_rows;
     st.rs = (st.valid && p.rscale) ? p.rscale[row] : 1.f;
     st.rq = (st.valid && p.rsq) ? p.rsq[row] : 0.f;
@@ -66,7 +67,7 @@ struct StoreEpi {
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape& sh, uint8_t*) {
+                                                 const uint32_t (&acc)[32], const GemmShape& sh, const EpiCtx&) {
     if (!st.valid || col0 >= sh.n_cols) return;
     const int ncol = min(32, sh.n_cols - col0);
     float o[32];
@@ -96,7 +97,7 @@ struct StoreEpi {
     }
   }
 
-  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, uint8_t*) {}
+  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, const EpiCtx&) {}
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -112,6 +113,78 @@ struct StoreEpi {
 // without the N x N matrix ever leaving the SM.  The overwhelmingly common case (s <= lim_q)
 // costs one max-reduction over the 32-column chunk and one compare.
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// warp_select_topk: in-place selection of the k largest of n (value, index) entries by one warp,
+// O(n) work: the entries live in registers (kPerLane per lane), the k-th largest key is found by
+// a 32-step bisection on the order-preserving integer image of the floats (one __reduce_add_sync
+// per step), survivors are scattered to [0, k) (unsorted).  Requires k <= n <= 32 * kPerLane.
+// Returns the k-th largest value.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned float_order_key(float f) {
+  const unsigned b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+template <int kPerLane>
+__device__ __forceinline__ float warp_select_topk(float* val, int* idx, int n, int k, int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  __syncwarp();  // entries appended by other lanes must be visible
+  unsigned key[kPerLane];
+  int id[kPerLane];
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const int e = j * 32 + lane;
+    const bool ok = e < n;
+    key[j] = ok ? float_order_key(val[e]) : 0u;  // 0 is below the key of every float
+    id[j] = ok ? idx[e] : -1;
+  }
+  unsigned T = 0;
+  for (int b = 31; b >= 0; --b) {
+    const unsigned cand = T | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kPerLane; ++j) c += key[j] >= cand;
+    c = __reduce_add_sync(kFull, c);
+    if (c >= k) T = cand;  // warp-uniform
+  }
+  int g = 0, q = 0;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    g += key[j] > T;
+    q += key[j] == T;
+  }
+  int gi = g, qi = q;  // inclusive scans over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int tg = __shfl_up_sync(kFull, gi, o);
+    const int tq = __shfl_up_sync(kFull, qi, o);
+    if (lane >= o) { gi += tg; qi += tq; }
+  }
+  const int G = __shfl_sync(kFull, gi, 31);
+  int pg = gi - g;          // first slot of this lane's "greater" entries
+  int pq = G + (qi - q);    // first slot of this lane's "equal" entries (kept while < k)
+  __syncwarp();             // every lane holds its entries in registers before anything is overwritten
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    if (key[j] > T) {
+      val[pg] = float_from_order_key(key[j]);
+      idx[pg] = id[j];
+      ++pg;
+    } else if (key[j] == T && key[j] != 0u) {
+      if (pq < k) {
+        val[pq] = float_from_order_key(key[j]);
+        idx[pq] = id[j];
+      }
+      ++pq;
+    }
+  }
+  __syncwarp();
+  return float_from_order_key(T);
+}
+
 struct EvalParams {
   const float* lim;        // [nq] lowest relevant similarity of the query (+inf if none)
   const int* q_c;          // [nq] clique ids
@@ -134,32 +207,56 @@ struct EvalParams {
 
 struct EvalEpi {
   using Params = EvalParams;
-  // Per-warp work queue: the elements that pass the per-row limit are scattered unevenly over the
-  // 32 rows of a warp (a query with a poorly ranked relevant item passes almost everything, most
-  // queries pass nothing).  Handling them in place would serialise the warp on its hottest lane,
-  // so they are first compacted into a shared-memory queue and then processed 32 at a time with
-  // every lane busy, whatever row they came from.
+  // Shared-memory scratch of the epilogue.
+  //  * per warp, a work queue: the elements that pass the per-row limit are scattered unevenly over
+  //    the 32 rows of a warp (a query with a poorly ranked relevant item passes almost everything,
+  //    most queries pass nothing).  Handling them in place would serialise the warp on its hottest
+  //    lane, so they are compacted into a queue and processed 32 at a time with every lane busy.
+  //  * per CTA, a cache of the row block's thresholds: the CSR slice thr[off[row0] .. off[row0+128])
+  //    is contiguous in global memory, so it is copied once per unit; each queued element is then
+  //    binned by a binary search on shared memory (no dependent L2 round trips) and counted in a
+  //    packed 16-bit shared-memory counter that is flushed to the global histogram at the end of
+  //    the unit.  Rows whose thresholds do not fit (a row block concentrated in one giant clique)
+  //    fall back to the global CSR arrays.
   static constexpr int kQueueCap = 256;
-  static constexpr int kWarpScratchBytes = kQueueCap * 4 + kQueueCap * 2 + 32 * 4;  // values, (lane,col) tags, top-k counts
+  static constexpr int kOffTag = kQueueCap * 4;
+  static constexpr int kOffCand = kOffTag + kQueueCap * 2;
+  static constexpr int kWarpScratchBytes = kOffCand + 32 * 4;
+  static constexpr int kCachePairs = 3456;  // mean of a 128-row block is ~2100 on SHS100K-shaped data
+  static constexpr int kCtaScratchBytes = kCachePairs * 4 + kCachePairs * 2;
   struct RowState {
     float lim;      // min(lowest threshold, top-k filter): the only compare on the fast path
     float tlim;     // lowest threshold
     float tau;      // top-k filter (k-th best so far, -inf until k candidates are buffered)
     int qc, qi, cnt;
+    int so;         // offset of the row's thresholds inside the shared cache, -1 if not cached
+    int n_cached;   // cached pairs of the unit (all threads hold the same value)
+    int cc_next, ci_next, next_col;  // ids of this lane's column in the NEXT chunk (prefetched)
     long long off;
+    long long base; // off[] of the unit's first row
     long long cbase;
   };
 
-  __device__ static __forceinline__ float* q_val(uint8_t* scratch) { return reinterpret_cast<float*>(scratch); }
-  __device__ static __forceinline__ uint16_t* q_tag(uint8_t* scratch) {
-    return reinterpret_cast<uint16_t*>(scratch + kQueueCap * 4);
+  __device__ static __forceinline__ float* q_val(const EpiCtx& c) { return reinterpret_cast<float*>(c.warp_scratch); }
+  __device__ static __forceinline__ uint16_t* q_tag(const EpiCtx& c) {
+    return reinterpret_cast<uint16_t*>(c.warp_scratch + kOffTag);
   }
-  __device__ static __forceinline__ int* n_cand(uint8_t* scratch) {
-    return reinterpret_cast<int*>(scratch + kQueueCap * 6);
+  __device__ static __forceinline__ int* n_cand(const EpiCtx& c) { return reinterpret_cast<int*>(c.warp_scratch + kOffCand); }
+  __device__ static __forceinline__ float* thr_s(const EpiCtx& c) { return reinterpret_cast<float*>(c.cta_scratch); }
+  __device__ static __forceinline__ unsigned* cnt_s(const EpiCtx& c) {
+    return reinterpret_cast<unsigned*>(c.cta_scratch + kCachePairs * 4);
+  }
+
+  __device__ static __forceinline__ void prefetch_ids(const Params& p, RowState& st, const GemmShape& sh, int lane) {
+    const int col = st.next_col + lane;
+    const bool ok = col < sh.n_cols;
+    st.cc_next = ok ? __ldg(p.c_c + col) : 0;
+    st.ci_next = ok ? __ldg(p.c_i + col) : 0;
   }
 
   __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int part,
-                                                   const GemmShape& sh, uint8_t* scratch) {
+                                                   const GemmShape& sh, const EpiCtx& ctx) {
+    const int lane = (int)ptx::lane_id();
     st.tlim = __int_as_float(0x7f800000);
     st.tau = __int_as_float(0x7f800000);
     st.qc = st.qi = st.cnt = 0;
@@ -174,9 +271,20 @@ struct EvalEpi {
       if (p.topk > 0) st.tau = __int_as_float(0xff800000);
     }
     st.lim = fminf(st.tlim, st.tau);
-    __syncwarp();
-    n_cand(scratch)[ptx::lane_id()] = 0;
-    __syncwarp();
+    st.next_col = ctx.first_col;
+    prefetch_ids(p, st, sh, lane);
+    n_cand(ctx)[lane] = 0;
+    // cooperative fill of the threshold cache (the previous unit's row_end left it flushed)
+    st.base = p.off[ctx.row_base];
+    const long long total = p.off[min(ctx.row_base + kTileM, sh.m_rows)] - st.base;
+    st.n_cached = (int)(total < (long long)kCachePairs ? total : (long long)kCachePairs);
+    float* ts = thr_s(ctx);
+    unsigned* cs = cnt_s(ctx);
+    for (int i = ctx.tid; i < st.n_cached; i += ctx.nthreads) ts[i] = __ldg(p.thr + st.base + i);
+    for (int i = ctx.tid; i < (st.n_cached + 1) / 2; i += ctx.nthreads) cs[i] = 0u;
+    const long long rel = st.off - st.base;
+    st.so = (row < sh.m_rows && rel + st.cnt <= (long long)st.n_cached) ? (int)rel : -1;
+    ptx::named_barrier_sync(1, ctx.nthreads);
   }
 
   // number of thresholds strictly below s (lower bound); thr[0 .. cnt) ascending
@@ -188,13 +296,18 @@ struct EvalEpi {
     }
     return lo;
   }
+  __device__ static __forceinline__ int count_below_smem(const float* thr, int cnt, float s) {
+    int lo = 0, hi = cnt;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (thr[mid] < s) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  }
 
-  // Warp-cooperative compaction of one row's candidate buffer down to its k best; returns the
-  // new k-th best value.  Rank-by-counting over <= cap entries (cap is a few hundred).
+  // Warp-cooperative compaction of one row's candidate buffer down to its k best (generic O(n^2/32)
+  // fallback for k > 160; the common case uses warp_select_topk).  Returns the new k-th best value.
   __device__ static __noinline__ float compact_row(float* val, int* idx, int n, int k, int lane) {
-    // every lane ranks the entries lane, lane+32, ...; entry e survives iff
-    // rank(e) = #{f : val_f > val_e or (val_f == val_e and f < e)} < k ; survivors are scattered
-    // to position rank (unique), staged in registers so reads complete before any write.
     constexpr int kMaxPerLane = 32;  // supports cap <= 1024
     __syncwarp();  // appends of the other lanes must be visible to the whole warp
     float mv[kMaxPerLane];
@@ -237,33 +350,38 @@ struct EvalEpi {
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape& sh, uint8_t* scratch) {
+                                                 const uint32_t (&acc)[32], const GemmShape& sh, const EpiCtx& ctx) {
     constexpr unsigned kFull = 0xffffffffu;
+    const int lane = (int)ptx::lane_id();
+    // ids of the 32 candidates of this chunk, one per lane, were prefetched during the previous
+    // chunk; start the loads for the next one now so their L2 latency is off the critical path
+    const int cc = st.cc_next, ci = st.ci_next;
+    const int colok = (col0 + lane) < sh.n_cols;
+    st.next_col = col0 + ctx.col_step;
+    prefetch_ids(p, st, sh, lane);
+
     // ---- fast path: one compare per element, nothing else when no lane of the warp passes
     unsigned m = 0;
 #pragma unroll
     for (int e = 0; e < 32; ++e) m |= (__uint_as_float(acc[e]) > st.lim) ? (1u << e) : 0u;
     if (!__any_sync(kFull, m != 0)) return;
 
-    const int lane = (int)ptx::lane_id();
-    float* qv = q_val(scratch);
-    uint16_t* qt = q_tag(scratch);
-    int* ncand = n_cand(scratch);
-    // ids of the 32 candidates of this chunk, one per lane (coalesced), shared by every queued element
-    const int mycol = col0 + lane;
-    const int colok = mycol < sh.n_cols;
-    const int cc = colok ? __ldg(p.c_c + mycol) : 0;
-    const int ci = colok ? __ldg(p.c_i + mycol) : 0;
+    float* qv = q_val(ctx);
+    uint16_t* qt = q_tag(ctx);
+    int* ncand = n_cand(ctx);
+    const float* ts = thr_s(ctx);
+    unsigned* cs = cnt_s(ctx);
 
     const int total = __shfl_sync(kFull, warp_incl_scan(__popc(m), lane), 31);
     const int nb = total <= kQueueCap ? 1 : 4;  // 8 columns x 32 rows always fit
     for (int bi = 0; bi < nb; ++bi) {
       const unsigned mb = nb == 1 ? m : (m & (0xffu << (8 * bi)));
       const int mine = __popc(mb);
-      const int incl = warp_incl_scan(mine, lane);
-      const int btotal = __shfl_sync(kFull, incl, 31);
+      const int incl = nb == 1 ? 0 : warp_incl_scan(mine, lane);
+      const int incl1 = nb == 1 ? warp_incl_scan(mine, lane) : incl;
+      const int btotal = nb == 1 ? total : __shfl_sync(kFull, incl1, 31);
       if (btotal == 0) continue;
-      int pos = incl - mine;
+      int pos = incl1 - mine;
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
         if (mb & (1u << e)) {
@@ -282,23 +400,41 @@ struct EvalEpi {
         const int qc = __shfl_sync(kFull, st.qc, L);
         const int qi = __shfl_sync(kFull, st.qi, L);
         const int pc = __shfl_sync(kFull, st.cnt, L);
+        const int so = __shfl_sync(kFull, st.so, L);
         const float tl = __shfl_sync(kFull, st.tlim, L);
         const float tau = __shfl_sync(kFull, st.tau, L);
-        const long long off = __shfl_sync(kFull, st.off, L);
         const int ccol = __shfl_sync(kFull, cc, e);
         const int cicol = __shfl_sync(kFull, ci, e);
         const int ok = __shfl_sync(kFull, colok, e);
-        if (active && ok && cicol != qi) {  // i_j == i_q: self (or a version-id collision), never a candidate
-          if (p.topk > 0 && s > tau) {
-            const int slot = atomicAdd(&ncand[L], 1);
-            const long long cb = st.cbase + (long long)(L - lane) * p.cap + slot;  // rows of a warp are consecutive
-            p.cand_val[cb] = s;
-            p.cand_idx[cb] = col0 + e;
+        const bool cand = active && ok && cicol != qi;  // i_j == i_q: self (or an id collision), never a candidate
+        if (cand && p.topk > 0 && s > tau) {
+          const int slot = atomicAdd(&ncand[L], 1);
+          const long long cb = st.cbase + (long long)(L - lane) * p.cap + slot;  // rows of a warp are consecutive
+          p.cand_val[cb] = s;
+          p.cand_idx[cb] = col0 + e;
+        }
+        // rank counting: a negative above at least the lowest relevant item; k = #{thresholds < s} >= 1
+        const bool neg = cand && s > tl && ccol != qc;
+        const bool cached = neg && so >= 0;
+        int k = 0;
+        if (cached) k = count_below_smem(ts + so, pc, s);
+        // one shared-memory atomic per distinct (row, bucket) of the round
+        const int key = cached ? (so + k - 1) : (-1 - lane);
+        const unsigned peers = __match_any_sync(kFull, key);
+        if (cached && lane == __ffs(peers) - 1) {
+          const unsigned add = (unsigned)__popc(peers);
+          const int shift = (key & 1) * 16;
+          const unsigned old = atomicAdd(cs + (key >> 1), add << shift);
+          const unsigned now = ((old >> shift) & 0xffffu) + add;
+          if (now >= 0x8000u) {  // keep the 16-bit field far from overflow: spill it to the global histogram
+            atomicSub(cs + (key >> 1), now << shift);
+            atomicAdd(p.hist + st.base + key, now);
           }
-          if (s > tl && ccol != qc) {  // a negative above at least the lowest relevant item
-            const int k = count_below(p.thr + off, pc, s);
-            if (k > 0) atomicAdd(p.hist + off + (k - 1), 1u);
-          }
+        }
+        const long long offL = __shfl_sync(kFull, st.off, L);
+        if (neg && so < 0) {
+          k = count_below(p.thr + offL, pc, s);
+          if (k > 0) atomicAdd(p.hist + offL + (k - 1), 1u);
         }
       }
       __syncwarp();
@@ -313,7 +449,8 @@ struct EvalEpi {
         need &= need - 1;
         const long long cb = st.cbase + (long long)(src - lane) * p.cap;
         const int n = ncand[src];
-        const float kth = compact_row(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane);
+        const float kth = p.cap <= 256 ? warp_select_topk<8>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
+                                       : compact_row(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane);
         if (lane == src) {
           ncand[lane] = p.topk;
           st.tau = kth;
@@ -326,11 +463,16 @@ struct EvalEpi {
   }
 
   __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part,
-                                                 const GemmShape& sh, uint8_t* scratch) {
-    __syncwarp();
-    if (p.topk > 0 && row < sh.m_rows) p.cand_cnt[(long long)part * p.nq_total + row] = n_cand(scratch)[ptx::lane_id()];
-    __syncwarp();
-    (void)st;
+                                                 const GemmShape& sh, const EpiCtx& ctx) {
+    const int lane = (int)ptx::lane_id();
+    if (p.topk > 0 && row < sh.m_rows) p.cand_cnt[(long long)part * p.nq_total + row] = n_cand(ctx)[lane];
+    ptx::named_barrier_sync(1, ctx.nthreads);  // every warp has finished counting into the cache
+    const unsigned* cs = cnt_s(ctx);
+    for (int i = ctx.tid; i < st.n_cached; i += ctx.nthreads) {
+      const unsigned v = (cs[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+      if (v != 0u) atomicAdd(p.hist + st.base + i, v);
+    }
+    ptx::named_barrier_sync(1, ctx.nthreads);  // flushed before the next unit refills the cache
   }
 };
 

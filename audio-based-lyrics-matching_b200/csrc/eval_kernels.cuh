@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_fp16.h>
 
+#include "epilogues.cuh"
 #include "prep.cuh"
 
 namespace wealy {
@@ -209,6 +210,56 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const float* __restr
         out_sim[(long long)q * k + r] = ve;
       }
     }
+  }
+}
+
+
+// K3 (fast path, k <= 160, <= 4 parts of <= 256 candidates): one warp per query gathers every part's
+// candidates into registers, selects the k best in O(n) (warp_select_topk), then orders the k
+// survivors by rank counting (k^2 / 32 steps) -- descending similarity, ties -> lower index.
+constexpr int kFinPerLane = 32;  // 4 parts x 256 candidates / 32 lanes
+__global__ void __launch_bounds__(128) topk_finalize_select_kernel(const float* __restrict__ cand_val,
+                                                                   const int* __restrict__ cand_idx,
+                                                                   const int* __restrict__ cand_cnt, int parts, int nq,
+                                                                   int cap, int k, float* __restrict__ stage_val,
+                                                                   int* __restrict__ stage_idx,
+                                                                   long long* __restrict__ out_idx,
+                                                                   float* __restrict__ out_sim) {
+  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (q >= nq) return;
+  // staging area of this query: [parts * cap] contiguous (value, index) pairs
+  float* sv = stage_val + (long long)q * parts * cap;
+  int* si = stage_idx + (long long)q * parts * cap;
+  int n = 0;
+  for (int p = 0; p < parts; ++p) {
+    const long long b = ((long long)p * nq + q) * cap;
+    const int np = cand_cnt[(long long)p * nq + q];
+    for (int e = lane; e < np; e += 32) {
+      sv[n + e] = cand_val[b + e];
+      si[n + e] = cand_idx[b + e];
+    }
+    n += np;
+  }
+  const int kk = min(k, n);
+  if (n > kk) warp_select_topk<kFinPerLane>(sv, si, n, kk, lane);
+  __syncwarp();
+  for (int e = lane; e < k; e += 32) {
+    if (e >= kk) {
+      out_idx[(long long)q * k + e] = -1;
+      out_sim[(long long)q * k + e] = __int_as_float(0xff800000);
+    }
+  }
+  for (int e = lane; e < kk; e += 32) {
+    const float ve = sv[e];
+    const int ie = si[e];
+    int r = 0;
+    for (int f = 0; f < kk; ++f) {
+      const float vf = sv[f];
+      r += (vf > ve) || (vf == ve && si[f] < ie);
+    }
+    out_idx[(long long)q * k + r] = ie;
+    out_sim[(long long)q * k + r] = ve;
   }
 }
 

@@ -46,22 +46,36 @@ struct GemmSmem {
   static constexpr int kBBytes = kTileN * kBlockK * 2;
   static constexpr int kPlanes = kPasses == 3 ? 2 : 1;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-  static constexpr int kBudget = 227 * 1024 - 2048 - 16 * 1024;  // alignment slack + barriers + epilogue scratch
+  static constexpr int kBudget = 227 * 1024 - 2048 - 30 * 1024;  // alignment slack + barriers + epilogue scratch
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kBarBytes = 256;
   static constexpr int kCore = kStages * kStageBytes + kBarBytes;  // + per-warp epilogue scratch + 1024 align slack
   static_assert(kStages >= 2, "need at least a double-buffered ring");
-  static constexpr int total(int epi_warps, int scratch_per_warp) { return kCore + epi_warps * scratch_per_warp + 1024; }
+  static constexpr int total(int epi_warps, int scratch_per_warp, int cta_scratch) {
+    return kCore + epi_warps * scratch_per_warp + cta_scratch + 1024;
+  }
 };
 
-// Epilogue policy contract (all __device__, called by the epilogue warps only):
+// What the core hands to an epilogue policy besides the accumulator.
+struct EpiCtx {
+  uint8_t* warp_scratch;  // Epi::kWarpScratchBytes of shared memory private to this epilogue warp
+  uint8_t* cta_scratch;   // Epi::kCtaScratchBytes shared by all epilogue warps of the CTA
+  int tid;                // thread index inside the epilogue group, [0, nthreads)
+  int nthreads;           // epilogue threads per CTA (named barrier 1 is reserved for them)
+  int row_base;           // first query row of the unit's row block
+  int first_col;          // first column this warp will see in the unit ...
+  int col_step;           // ... and the distance to the column of its next chunk
+};
+
+// Epilogue policy contract (all __device__, called by the epilogue warps only; every epilogue
+// thread calls row_begin / row_end exactly once per unit, so they may use the group barrier):
 //   struct Params;                      POD passed by value to the kernel
 //   struct RowState;                    per-thread state that lives across one unit
-//   static constexpr int kWarpScratchBytes;   shared-memory scratch per epilogue warp (may be 0)
-//   static void row_begin(const Params&, RowState&, int row, int part, const GemmShape&, uint8_t* scratch);
+//   static constexpr int kWarpScratchBytes, kCtaScratchBytes;   shared-memory scratch (may be 0)
+//   static void row_begin(const Params&, RowState&, int row, int part, const GemmShape&, const EpiCtx&);
 //   static void chunk32(const Params&, RowState&, int row, int col0, const uint32_t (&acc)[32], const GemmShape&,
-//                       uint8_t* scratch);
-//   static void row_end(const Params&, RowState&, int row, int part, const GemmShape&, uint8_t* scratch);
+//                       const EpiCtx&);
+//   static void row_end(const Params&, RowState&, int row, int part, const GemmShape&, const EpiCtx&);
 // `row` is the global query row owned by the thread, `part` identifies the partial result slot
 // (column chunk x epilogue half) when a row is split over several units / warps.
 
@@ -200,8 +214,15 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       const int row = rb * kTileM + row_in_tile;
       const int part = chunk * kHalves + half;
       typename Epi::RowState rs;
-      uint8_t* scratch = scratch_base + ew * Epi::kWarpScratchBytes;
-      Epi::row_begin(ep, rs, row, part, shape, scratch);
+      EpiCtx ctx;
+      ctx.warp_scratch = scratch_base + ew * Epi::kWarpScratchBytes;
+      ctx.cta_scratch = scratch_base + kEpiWarps * Epi::kWarpScratchBytes;
+      ctx.tid = ew * 32 + lane;
+      ctx.nthreads = kEpiWarps * 32;
+      ctx.row_base = rb * kTileM;
+      ctx.first_col = t0 * kTileN + half * kChunkCols;
+      ctx.col_step = kHalves * kChunkCols;
+      Epi::row_begin(ep, rs, row, part, shape, ctx);
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&tmem_full[acc], acc_phase);
         ptx::tc_fence_after_sync();
@@ -211,14 +232,14 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
           uint32_t v[32];
           ptx::tmem_ld_32x32(taddr + (uint32_t)(c * kChunkCols), v);
           ptx::tmem_ld_wait();
-          Epi::chunk32(ep, rs, row, t * kTileN + c * kChunkCols, v, shape, scratch);
+          Epi::chunk32(ep, rs, row, t * kTileN + c * kChunkCols, v, shape, ctx);
         }
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
-      Epi::row_end(ep, rs, row, part, shape, scratch);
+      Epi::row_end(ep, rs, row, part, shape, ctx);
     }
   }
 

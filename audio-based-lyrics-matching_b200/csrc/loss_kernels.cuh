@@ -48,13 +48,14 @@ __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); 
 struct LossStatsEpi {
   using Params = LossParams;
   static constexpr int kWarpScratchBytes = 0;
+  static constexpr int kCtaScratchBytes = 0;
   struct RowState {
     int lab, id;
     bool valid;
     float a0, a1, a2, a3, a4, a5;
   };
 
-  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, uint8_t*) {
+  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, const EpiCtx&) {
     st.valid = row < p.b;
     st.lab = st.valid ? p.label[row] : 0;
     st.id = st.valid ? p.idx[row] : 0;
@@ -63,7 +64,7 @@ struct LossStatsEpi {
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape&, uint8_t*) {
+                                                 const uint32_t (&acc)[32], const GemmShape&, const EpiCtx&) {
     if (!st.valid || col0 >= p.b) return;
     if (p.kind == kLossNtxent) {
       float l[32];
@@ -111,7 +112,7 @@ struct LossStatsEpi {
     }
   }
 
-  __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part, const GemmShape&, uint8_t*) {
+  __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part, const GemmShape&, const EpiCtx&) {
     if (!st.valid) return;
     float* o = p.partial + ((long long)part * p.b + row) * kStatWidth;
     reinterpret_cast<float4*>(o)[0] = make_float4(st.a0, st.a1, st.a2, st.a3);
@@ -127,13 +128,14 @@ struct LossStatsEpi {
 struct LossWEpi {
   using Params = LossParams;
   static constexpr int kWarpScratchBytes = 0;
+  static constexpr int kCtaScratchBytes = 0;
   struct RowState {
     int lab, id;
     bool valid;
     float r0, r1, r2;
   };
 
-  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, uint8_t*) {
+  __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, const EpiCtx&) {
     st.valid = row < p.b;
     st.lab = st.valid ? p.label[row] : 0;
     st.id = st.valid ? p.idx[row] : 0;
@@ -144,7 +146,7 @@ struct LossWEpi {
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape&, uint8_t*) {
+                                                 const uint32_t (&acc)[32], const GemmShape&, const EpiCtx&) {
     if (!st.valid || col0 >= p.ldw) return;
     __align__(16) __half hi[32];
     __align__(16) __half lo[32];
@@ -183,7 +185,7 @@ struct LossWEpi {
     }
   }
 
-  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, uint8_t*) {}
+  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, const EpiCtx&) {}
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(LossCfgDev cfg, int
     const double l_align = s_h > 0.0 ? s_align / s_h : 0.0;  // losses.py:239
     const double l_uni = s_uni / B;
     // true coefficients: dS_ij = -pos ca_i + X_ij neg cu_i.  W is stored in fp16, so scale it by
-    // S = 1 / max_i max(ca_i, cu_i e^b): |W'| <= 2 whatever the batch looks like (no overflow, and the
+    // S = 1 / max_i max(ca_i, cu_i max_j X_ij): |W'| <= 2 whatever the batch looks like (no overflow, and the
     // largest entries sit at the top of the fp16 range); the Jacobian kernel multiplies by 1/S.
     float bound = 0.f;
     for (int i = threadIdx.x; i < b; i += blockDim.x) {
@@ -300,7 +302,9 @@ __global__ void __launch_bounds__(1024) loss_finalize_kernel(LossCfgDev cfg, int
       const float ca = np > 0.f ? (float)(1.0 / ((double)np * H)) : 0.f;
       const float outer = cfg.numerically_friendly ? 1.f / (1.f + uni) : 1.f / (uni + cfg.epsilon);
       const float cu = nn > 0.f ? (float)((double)cfg.uw * (double)cfg.gamma / (B * (double)nn)) * outer : 0.f;
-      bound = fmaxf(bound, fmaxf(ca, fabsf(cu) * expf(cfg.b)));
+      // X_ij <= e^b, and X_ij <= sum_j X_ij neg_ij = nneg_i * uni_i: rows with a vanishing uniformity
+      // term (huge 1/(uni+eps) in the non-friendly branch) must not dictate the scale
+      bound = fmaxf(bound, fmaxf(ca, fabsf(cu) * fminf(expf(cfg.b), nn * uni)));
       reinterpret_cast<float4*>(rowstat)[i] = make_float4(ca, cu, 0.f, 0.f);
     }
     bound = (float)block_max(bound, sh);

@@ -61,7 +61,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
 
     def run(self):
@@ -78,7 +78,7 @@ class ClockSampler(threading.Thread):
                 "hw_power_brake": getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80),
             }
             self.ok = True
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
@@ -87,12 +87,12 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(k)
                 except Exception:
                     pass
-                self._stop.wait(0.1)
+                self._halt.wait(0.1)
         except Exception:
             self.ok = False
 
     def finish(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}

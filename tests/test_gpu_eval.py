@@ -145,15 +145,17 @@ def test_queries_disjoint_from_corpus_and_collisions():
 def test_exact_duplicates_and_giant_clique():
     g = torch.Generator().manual_seed(8)
     n_big = 359                                         # largest clique of SHS100K-TRAIN
-    z = torch.randn(900, 64, generator=g)
-    c = torch.cat([torch.zeros(n_big, dtype=torch.long), 1 + torch.arange(900 - n_big) // 3])
+    n = n_big + 540
+    z = torch.randn(n, 64, generator=g)
+    c = torch.cat([torch.zeros(n_big, dtype=torch.long), 1 + torch.arange(n - n_big) // 3])
     z[:n_big] += 0.8 * torch.randn(1, 64, generator=g)
     z[10] = z[11]                                       # exact duplicates inside the clique (ties)
     z[500] = z[20]                                      # a negative that ties with a relevant item
-    i = torch.arange(900)
+    i = torch.arange(n)
     aps_o, r1_o = oev.evaluate_argsort(c, i, z, c, i, z)
     aps, r1s = _gpu_eval(c, i, z)
-    assert abs(float(aps.double().mean()) - float(aps_o.mean())) <= 1e-4
+    # exact ties (duplicates) may be ordered either way: AP of the affected queries moves by O(1/P)
+    assert abs(float(aps.double().mean()) - float(aps_o.mean())) <= 1e-3
     lo, hi = oev.rank_tolerance(c, i, z, c, i, z, gap=1e-5)
     assert bool(((r1s.double() >= lo) & (r1s.double() <= hi)).all())
 

@@ -23,7 +23,8 @@ def _check_mode(got, ref, x, y, mode, single_pass=False):
     got, ref = got.double().cpu(), ref.double()
     nx = x.double().norm(dim=-1)[:, None] if x.ndim == 2 else x.double().abs()[:, None]
     ny = y.double().norm(dim=-1)[None, :] if y.ndim == 2 else y.double().abs()[None, :]
-    unit = 3e-4 if single_pass else 4e-6
+    # single pass: every element is rounded to fp16 (2^-11 relative), so short rows see ~1e-3 of |x||y|
+    unit = 1.2e-3 if single_pass else 4e-6
     d = x.shape[-1] if x.ndim == 2 else 1
     if mode in ("cos", "cossim"):
         assert (got - ref).abs().max() <= unit
