@@ -11,6 +11,7 @@
 #include "epilogues.cuh"
 #include "eval_kernels.cuh"
 #include "loss_kernels.cuh"
+#include "masked_kernels.cuh"
 #include "prep.cuh"
 
 using namespace wealy;
@@ -460,9 +461,12 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
   CU_TRY(cudaMemsetAsync(p->hist, 0, (size_t)(p->total_pairs > 0 ? p->total_pairs : 1) * 4, s));
   CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
 
+  const int epi_warps = env_int("WEALY_EVAL_EPI_WARPS", 8);  // 16 measured no faster (the sweep is not latency-starved)
+  const int halves = epi_warps == 16 ? 4
+                     : ((passes == 3 && env_int("WEALY_EPI_WARPS", 8) == 4 && env_int("WEALY_BLOCK_K", 64) == 64) ? 1 : 2);
   GemmShape sh;
-  fill_shape(sh, nq, nc, pq.d_pad, 64, topk > 0 ? 2 : (1 << 20));  // top-k: <= 2 chunks x 2 halves = 4 candidate lists per query
-  const int halves = (passes == 3 && env_int("WEALY_EPI_WARPS", 8) == 4 && env_int("WEALY_BLOCK_K", 64) == 64) ? 1 : 2;
+  // top-k keeps <= 4 candidate lists per query (column chunks x epilogue warps per row)
+  fill_shape(sh, nq, nc, pq.d_pad, 64, topk > 0 ? (4 / halves) : (1 << 20));
   const int parts = sh.n_col_chunks * halves;
   const int cap = topk > 0 ? topk_capacity(topk) : 0;
 
@@ -500,7 +504,13 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
     CU_TRY(cudaEventCreate(&p->ev1));
   }
   CU_TRY(cudaEventRecord(p->ev0, s));
-  W_TRY(launch_gemm<EvalEpi>(passes, pq, pc, sh, ep, s));
+  if (halves == 4) {
+    // 16 epilogue warps (4 per TMEM lane quadrant): the slow path is latency bound, more warps hide it
+    if (passes == 3) W_TRY((launch_gemm_t<EvalEpi16, 3, 64, 16>(pq, pc, sh, ep, s)));
+    else W_TRY((launch_gemm_t<EvalEpi16, 1, 64, 16>(pq, pc, sh, ep, s)));
+  } else {
+    W_TRY(launch_gemm<EvalEpi>(passes, pq, pc, sh, ep, s));
+  }
   CU_TRY(cudaEventRecord(p->ev1, s));
   p->timed = true;
 
@@ -524,6 +534,39 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
     }
   }
   return WEALY_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// a3: masked reductions
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_masked(const void* x, const unsigned char* mask, int64_t rows, int64_t cols, int op, float fill,
+                         float eps, void* out, cudaStream_t s) {
+  if (cols <= 2048 || rows >= 4096) {
+    const int threads = 256;
+    const unsigned blocks = (unsigned)ceil_div(rows * 32, threads);
+    masked_reduce_warp_kernel<T><<<blocks, threads, 0, s>>>((const T*)x, mask, rows, cols, op, fill, eps, (T*)out);
+  } else {
+    masked_reduce_block_kernel<T><<<(unsigned)rows, 1024, 0, s>>>((const T*)x, mask, rows, cols, op, fill, eps, (T*)out);
+  }
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+extern "C" int wealy_masked_reduce(const void* x, const uint8_t* mask, int64_t rows, int64_t cols, int dtype, int op,
+                                   float fill, float eps, void* out, void* stream) {
+  if (rows < 0 || cols < 0) return fail(WEALY_ERR_BAD_ARG, "bad shape rows=%lld cols=%lld", (long long)rows, (long long)cols);
+  if (rows == 0) return WEALY_OK;
+  if (!x || !out) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (op < WEALY_MASKED_SUM || op > WEALY_MASKED_MAX) return fail(WEALY_ERR_BAD_ARG, "unknown masked op %d", op);
+  if (rows > 2000000000ll) return fail(WEALY_ERR_UNSUPPORTED, "too many rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case WEALY_F32: return launch_masked<float>(x, mask, rows, cols, op, fill, eps, out, s);
+    case WEALY_F16: return launch_masked<__half>(x, mask, rows, cols, op, fill, eps, out, s);
+    case WEALY_BF16: return launch_masked<__nv_bfloat16>(x, mask, rows, cols, op, fill, eps, out, s);
+    default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
+  }
 }
 
 #include "loss_api.inl"

@@ -85,7 +85,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
   using SM = GemmSmem<kPasses, kBlockK>;
   constexpr int kStages = SM::kStages;
   constexpr int kHalves = kEpiWarps / 4;  // epilogue warps per TMEM lane quadrant
-  static_assert(kEpiWarps == 4 || kEpiWarps == 8, "4 or 8 epilogue warps");
+  static_assert(kEpiWarps == 4 || kEpiWarps == 8 || kEpiWarps == 16, "4, 8 or 16 epilogue warps");
   static_assert(kPasses == 1 || kPasses == 3, "1 (fp16) or 3 (fp16 hi/lo) passes");
 
   extern __shared__ uint8_t smem_raw[];
@@ -141,16 +141,17 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* st = smem + stage * SM::kStageBytes;
             ptx::mbar_expect_tx(&full_bar[stage], SM::kStageBytes);
-            // query tiles are re-read once per column tile (L2 hits); candidate tiles are shared
-            // by every resident CTA of the wave -> keep them in L2 preferentially
-            ptx::tma_load_2d(st, &tmaps.a_hi, &full_bar[stage], kb * kBlockK, rb * kTileM, ptx::kEvictNormal);
+            // the CTA's query tiles are re-read once per column tile of the unit (~100x): the 148
+            // resident row blocks (76 MB in fp16x3) are the L2 working set -> evict_last; a candidate
+            // tile only has to survive until every CTA of the wave has passed it -> normal priority
+            ptx::tma_load_2d(st, &tmaps.a_hi, &full_bar[stage], kb * kBlockK, rb * kTileM, ptx::kEvictLast);
             ptx::tma_load_2d(st + SM::kPlanes * SM::kABytes, &tmaps.b_hi, &full_bar[stage], kb * kBlockK,
-                             t * kTileN, ptx::kEvictLast);
+                             t * kTileN, ptx::kEvictNormal);
             if (kPasses == 3) {
               ptx::tma_load_2d(st + SM::kABytes, &tmaps.a_lo, &full_bar[stage], kb * kBlockK, rb * kTileM,
-                               ptx::kEvictNormal);
+                               ptx::kEvictLast);
               ptx::tma_load_2d(st + 2 * SM::kABytes + SM::kBBytes, &tmaps.b_lo, &full_bar[stage], kb * kBlockK,
-                               t * kTileN, ptx::kEvictLast);
+                               t * kTileN, ptx::kEvictNormal);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }

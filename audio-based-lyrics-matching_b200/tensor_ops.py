@@ -105,3 +105,152 @@ def pairwise_distance_matrix(x, y, mode="fro", p=2, eps=1e-6, precision=None):
         code = {"cossim": N.MODE_COSSIM, "cos": N.MODE_COS, "dotsim": N.MODE_DOTSIM, "dot": N.MODE_DOT}[mode]
         return _sim_matrix(x, y, code, eps, 1.0, precision)
     raise NotImplementedError
+
+
+# ------------------------------------------------------------------------------------------------
+# a3 / a4: masked reductions and the multi-chunk distance reduction
+#   lib/tensor_ops.py:182-282 (msum mmean mmin mmax mrand mbest mworst), :288-373 (distance_tensor_redux)
+# msum / mmean / mmin / mmax run in one HBM pass of the CUDA kernel behind wealy_masked_reduce; the
+# composite reductions (random pick, best-k, redux strategies) are thin compositions of those four
+# plus torch.topk / torch.rand_like, with the reference's quirks kept (mask True = EXCLUDED; mworst
+# returns 0 -- or NaN when fewer than k entries survive; "bestmin" is shadowed by "best").
+# ------------------------------------------------------------------------------------------------
+_INF = float("inf")
+_OPS = {"sum": 0, "mean": 1, "min": 2, "max": 3}
+
+
+def _reduce(x, mask, dim, keepdim, op, fill=0.0, eps=1e-7):
+    N.require_cuda(x)
+    code = N.dtype_code(x.dtype)
+    if mask is not None:
+        N.require_cuda(mask)
+        # like the reference's `included * x` / `torch.where(mask, ctt, x)`, x and mask broadcast together
+        # (minmean / meanmin reduce an already-reduced x against the full-size mask)
+        x, mask = torch.broadcast_tensors(x, mask)
+    nd = x.ndim
+    if dim is None:
+        red = list(range(nd))
+    else:
+        red = sorted({d % nd for d in ((dim,) if isinstance(dim, int) else tuple(dim))})
+    kept = [d for d in range(nd) if d not in red]
+    order = kept + red
+    kept_shape = [x.shape[d] for d in kept]
+    rows = 1
+    for s_ in kept_shape:
+        rows *= s_
+    cols = 1
+    for d in red:
+        cols *= x.shape[d]
+    xp = x.permute(order).contiguous()
+    mp = None
+    if mask is not None:
+        mp = mask.permute(order).contiguous().to(torch.uint8)
+    out = torch.empty(rows, dtype=x.dtype, device=x.device)
+    if rows and cols == 0:
+        out.fill_({0: 0.0, 1: 0.0, 2: _INF, 3: -_INF}[op])
+    elif rows:
+        with torch.cuda.device(x.device):
+            N.check(N.lib.wealy_masked_reduce(xp.data_ptr(), mp.data_ptr() if mp is not None else None, rows, cols,
+                                              code, op, float(fill), float(eps), out.data_ptr(),
+                                              N.stream_ptr(x.device)))
+    out = out.view(kept_shape)
+    if keepdim:
+        for d in red:
+            out = out.unsqueeze(d)
+    return out
+
+
+def msum(x, mask=None, dim=None, keepdim=False):
+    return _reduce(x, mask, dim, keepdim, _OPS["sum"])
+
+
+def mmean(x, mask=None, dim=None, keepdim=False, eps=1e-7):
+    return _reduce(x, mask, dim, keepdim, _OPS["mean"], eps=eps)
+
+
+def mmin(x, mask=None, dim=None, keepdim=False, ctt=torch.inf):
+    return _reduce(x, mask, dim, keepdim, _OPS["min"], fill=ctt)
+
+
+def mmax(x, mask=None, dim=None, keepdim=False, ctt=-torch.inf):
+    return _reduce(x, mask, dim, keepdim, _OPS["max"], fill=ctt)
+
+
+def mrand(x, mask=None, dim=None, keepdim=False, ctt=torch.inf, eps=1e-7):
+    keys = torch.rand_like(x)
+    if mask is not None:
+        keys = torch.where(mask, ctt, keys)
+    loser = keys > mmin(keys, mask=mask, dim=dim, keepdim=True, ctt=ctt)
+    return mmean(x, mask=loser, dim=dim, keepdim=keepdim, eps=eps)
+
+
+def mbest(x, k, mask=None, dim=None, keepdim=False, ctt=torch.inf, eps=1e-7):
+    assert type(dim) == int
+    if mask is not None:
+        x = torch.where(mask, ctt, x)
+    low = x.topk(k, dim=dim, largest=False)[0]
+    return mmean(low, mask=low >= ctt, dim=dim, keepdim=keepdim, eps=eps)
+
+
+def mworst(x, k, mask=None, dim=None, keepdim=False, ctt=-torch.inf, eps=1e-7):
+    assert type(dim) == int
+    if mask is not None:
+        x = torch.where(mask, ctt, x)
+    high = x.topk(k, dim=dim, largest=True)[0]
+    return mmean(high, mask=high >= ctt, dim=dim, keepdim=keepdim, eps=eps)   # upstream quirk: excludes everything
+
+
+def _redux_k(redux, limit):
+    return 1 if "-" not in redux else max(1, min(int(redux.split("-")[-1]), limit))
+
+
+def distance_tensor_redux(dist, redux, mask=None, squeeze=True, eps=1e-7, inf=1e12):
+    """(b1, b2, s1, s2) chunk-vs-chunk distances -> (b1, b2) track-vs-track (lib/tensor_ops.py:288-373)."""
+    both = (-1, -2)
+    if redux == "min":
+        out = mmin(dist, mask=mask, dim=both, keepdim=True, ctt=inf)
+    elif redux == "max":
+        out = mmax(dist, mask=mask, dim=both, keepdim=True, ctt=-inf)
+    elif redux == "mean":
+        out = mmean(dist, mask=mask, dim=both, keepdim=True, eps=eps)
+    elif redux == "minmean":
+        out = mmin(mmean(dist, mask=mask, dim=-1, keepdim=True, eps=eps), mask=mask, dim=both, keepdim=True, ctt=inf)
+    elif redux == "meanmin":
+        out = mmean(mmin(dist, mask=mask, dim=-1, keepdim=True, ctt=inf), mask=mask, dim=both, keepdim=True, eps=eps)
+    elif redux == "randmin":
+        out = mrand(mmin(dist, mask=mask, dim=-1, keepdim=True, ctt=inf), mask=mask, dim=both, keepdim=True, ctt=inf,
+                    eps=eps)
+    elif redux.startswith("bpwr"):  # greedy best pairs without replacement
+        if dist.size(3) < dist.size(2):
+            dist = dist.transpose(2, 3)
+            mask = None if mask is None else mask.transpose(2, 3)
+        rounds = dist.size(2) if "-" not in redux else _redux_k(redux, dist.size(2))
+        dist = dist + eps * torch.rand_like(dist)
+        if mask is None:
+            mask = dist > inf
+        picked = dist > inf
+        for it in range(rounds):
+            best = mmin(dist, mask=mask, dim=both, keepdim=True, ctt=inf)
+            picked = picked | ((dist <= best) & ~mask)
+            if it < rounds - 1:
+                mask = (mask | (mmin(dist, mask=mask, dim=-1, keepdim=True, ctt=inf) <= best)
+                        | (mmin(dist, mask=mask, dim=-2, keepdim=True, ctt=inf) <= best))
+        out = mmean(dist, mask=~picked, dim=both, keepdim=True, eps=eps)
+    elif redux.startswith("best"):   # also swallows "bestmin..." exactly like upstream
+        k = _redux_k(redux, dist.size(2) * dist.size(3))
+        flat = dist.flatten(2).unsqueeze(2)
+        fmask = None if mask is None else mask.flatten(2).unsqueeze(2)
+        out = mbest(flat, k, mask=fmask, dim=-1, keepdim=True, ctt=inf, eps=eps)
+    elif redux.startswith("worst"):
+        k = _redux_k(redux, dist.size(2) * dist.size(3))
+        flat = dist.flatten(2).unsqueeze(2)
+        fmask = None if mask is None else mask.flatten(2).unsqueeze(2)
+        out = mworst(flat, k, mask=fmask, dim=-1, keepdim=True, ctt=-inf, eps=eps)
+    elif redux[0] == "s":            # symmetrised variant
+        fwd = distance_tensor_redux(dist, redux[1:], mask=mask, squeeze=False)
+        bwd = distance_tensor_redux(dist.transpose(2, 3), redux[1:],
+                                    mask=None if mask is None else mask.transpose(2, 3), squeeze=False)
+        out = 0.5 * (fwd + bwd.transpose(2, 3))
+    else:
+        raise NotImplementedError
+    return out.squeeze((-1, -2)) if squeeze else out

@@ -95,6 +95,18 @@ int wealy_eval_run(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, c
 int wealy_eval_plan_last_sweep_ms(const wealy_eval_plan* plan, float* ms);
 void wealy_eval_plan_destroy(wealy_eval_plan* plan);
 
+/* ---- a3: masked reductions ---------------------------------------------------------------
+ * Replaces lib/tensor_ops.py:182-258 (msum / mmean / mmin / mmax): x [rows, cols] contiguous, reduced
+ * over cols; mask [rows, cols] bytes, non-zero = EXCLUDED (may be NULL); out [rows] in x's dtype.
+ * fill: value substituted for excluded entries in min / max (the reference's `ctt`); eps: the clamp
+ * of the mean's denominator.  One HBM pass.                                                     */
+#define WEALY_MASKED_SUM 0
+#define WEALY_MASKED_MEAN 1
+#define WEALY_MASKED_MIN 2
+#define WEALY_MASKED_MAX 3
+int wealy_masked_reduce(const void* x, const uint8_t* mask, int64_t rows, int64_t cols, int dtype, int op, float fill,
+                        float eps, void* out, void* stream);
+
 /* ---- a5/a6: batch similarity-matrix contrastive losses -------------------------------------
  * NT-Xent: lib/losses.py:19-73.  CLEWS: lib/losses.py:210-285.  Forward writes the loss terms
  * and logdict statistics into `out` (doubles, device) and keeps the per-row statistics the

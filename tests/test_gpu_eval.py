@@ -160,6 +160,27 @@ def test_exact_duplicates_and_giant_clique():
     assert bool(((r1s.double() >= lo) & (r1s.double() <= hi)).all())
 
 
+def test_counts_beyond_16_bits_and_topk_consistency():
+    """A query whose relevant item is ranked near the bottom of a 40k corpus: the per-unit rank counters
+    (16-bit fields in shared memory, spilled to the global histogram) must not wrap, with and without the
+    top-k path (which sweeps the whole corpus in a single unit)."""
+    g = torch.Generator().manual_seed(12)
+    n, d = 40000, 64
+    z = torch.randn(n, d, generator=g)
+    c = torch.arange(n) // 2
+    i = torch.arange(n)
+    z[1] = -z[0] + 0.01 * torch.randn(d, generator=g)      # query 0's only relevant item is its antipode
+    z[3] = z[2]
+    aps, r1s = _gpu_eval(c, i, z)
+    aps2, r1s2, idx, sim = _gpu_eval(c, i, z, topk=5)
+    assert torch.equal(r1s, r1s2) and torch.allclose(aps, aps2)
+    assert float(r1s[0]) == n - 1 and float(r1s[1]) == n - 1      # ranked last of the n - 1 candidates
+    assert float(r1s[2]) == 1 and float(r1s[3]) == 1
+    nq = 64
+    aps_o, r1_o = oev.evaluate_argsort(c[:nq], i[:nq], z[:nq], c, i, z)
+    assert torch.equal(r1s[:nq].double(), r1_o)
+
+
 def test_plan_reuse_and_half_precision_inputs():
     s = _synth().make_eval_set(1200, 128, seed=9)
     we = _we()

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+L=gpurun_out/diag7.log
+: > $L
+run() { echo "### $*" >> $L; timeout 900 "$@" >> $L 2>&1; echo "exit=$?" >> $L; }
+run python -m pytest tests -m gpu -q
+run python tools/gpu_diag.py time fp16x3 100000 1024
+run python tools/gpu_diag.py time fp16 100000 1024
+WEALY_EVAL_EPI_WARPS=8 run python tools/gpu_diag.py time fp16x3 100000 1024
+WEALY_EVAL_EPI_WARPS=8 run python tools/gpu_diag.py time fp16 100000 1024
+run python tools/gpu_diag.py time fp16x3 50000 1024 100
+tail -30 $L
