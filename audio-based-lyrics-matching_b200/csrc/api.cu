@@ -418,7 +418,8 @@ extern "C" int wealy_eval_plan_last_sweep_ms(const wealy_eval_plan* p, float* ms
   return WEALY_OK;
 }
 
-static int topk_capacity(int k) { return (int)align_up((size_t)k + 96, 32); }
+// a row may gain up to 4 deferred chunks x 32 candidates between two compaction checks
+static int topk_capacity(int k) { return (int)align_up((size_t)k + 156, 32); }
 
 extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
                               int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,

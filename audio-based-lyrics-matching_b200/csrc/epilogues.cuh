@@ -97,6 +97,7 @@ struct StoreEpi {
     }
   }
 
+  __device__ static __forceinline__ void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&) {}
   __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, const EpiCtx&) {}
 };
 
@@ -237,7 +238,12 @@ struct EvalEpiT {
     long long off;
     long long base; // off[] of the unit's first row
     long long cbase;
+    // deferred work: up to kSlots chunks are queued before the accumulator is released and drained after
+    int qn, nslot;                       // queued elements / chunks (warp-uniform)
+    int q_end[4], col0_q[4];             // per queued chunk: end of its queue range, first column (uniform)
+    int cc_q[4], ci_q[4], ok_q[4];       // per queued chunk: ids / validity of this lane's column
   };
+  static constexpr int kSlots = 4;
 
   __device__ static __forceinline__ float* q_val(const EpiCtx& c) { return reinterpret_cast<float*>(c.warp_scratch); }
   __device__ static __forceinline__ uint16_t* q_tag(const EpiCtx& c) {
@@ -274,6 +280,8 @@ struct EvalEpiT {
     }
     st.lim = fminf(st.tlim, st.tau);
     st.next_col = ctx.first_col;
+    st.qn = 0;
+    st.nslot = 0;
     prefetch_ids(p, st, sh, lane);
     n_cand(ctx)[lane] = 0;
     // cooperative fill of the threshold cache (the previous unit's row_end left it flushed)
@@ -353,6 +361,132 @@ struct EvalEpiT {
     return v;
   }
 
+  // Process the queue range [begin, end): 32 elements per round, every lane busy.  cc / ci / colok are the
+  // ids and validity of this lane's column in the chunk the range came from; col0 its first column.
+  __device__ static __forceinline__ void process_range(const Params& p, RowState& st, const EpiCtx& ctx, int begin,
+                                                       int end, int cc, int ci, int colok, int col0, int lane) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const float* qv = q_val(ctx);
+    const uint16_t* qt = q_tag(ctx);
+    int* ncand = n_cand(ctx);
+    const float* ts = thr_s(ctx);
+    unsigned* cs = cnt_s(ctx);
+    for (int r0 = begin; r0 < end; r0 += 32) {
+      const int r = r0 + lane;
+      const bool active = r < end;
+      const float s = active ? qv[r] : 0.f;
+      const int tag = active ? (int)qt[r] : 0;
+      const int L = tag >> 5, e = tag & 31;  // owner lane (row) and column of the element
+      const int qc = __shfl_sync(kFull, st.qc, L);
+      const int qi = __shfl_sync(kFull, st.qi, L);
+      const int pc = __shfl_sync(kFull, st.cnt, L);
+      const int so = __shfl_sync(kFull, st.so, L);
+      const float tl = __shfl_sync(kFull, st.tlim, L);
+      const float tau = __shfl_sync(kFull, st.tau, L);
+      const int ccol = __shfl_sync(kFull, cc, e);
+      const int cicol = __shfl_sync(kFull, ci, e);
+      const int ok = __shfl_sync(kFull, colok, e);
+      const bool cand = active && ok && cicol != qi;  // i_j == i_q: self (or an id collision), never a candidate
+      if (cand && p.topk > 0 && s > tau) {
+        const int slot = atomicAdd(&ncand[L], 1);
+        const long long cb = st.cbase + (long long)(L - lane) * p.cap + slot;  // rows of a warp are consecutive
+        p.cand_val[cb] = s;
+        p.cand_idx[cb] = col0 + e;
+      }
+      // rank counting: a negative above at least the lowest relevant item; k = #{thresholds < s} >= 1
+      const bool neg = cand && s > tl && ccol != qc;
+      const bool cached = neg && so >= 0;
+      int k = 0;
+      if (cached) k = count_below_smem(ts + so, pc, s);
+      // the elements of a round mostly come from one hot row and land in one bucket: the first
+      // cached lane counts all lanes that share its (row, bucket) key with a single shared-memory
+      // atomic, the others add their own
+      const int key = cached ? (so + k - 1) : -1;
+      const unsigned cm = __ballot_sync(kFull, cached);
+      if (cm != 0u) {
+        const int lead = __ffs(cm) - 1;
+        const int key_lead = __shfl_sync(kFull, key, lead);
+        const unsigned same = __ballot_sync(kFull, cached && key == key_lead);
+        if (cached && (lane == lead || key != key_lead)) {
+          const unsigned add = lane == lead ? (unsigned)__popc(same) : 1u;
+          const int shift = (key & 1) * 16;
+          const unsigned old = (atomicAdd(cs + (key >> 1), add << shift) >> shift) & 0xffffu;
+          // keep the 16-bit field far from overflow: the (single) adder that takes it across 0x8000
+          // moves exactly 0x8000 counts to the global histogram
+          if (old < 0x8000u && old + add >= 0x8000u) {
+            atomicSub(cs + (key >> 1), 0x8000u << shift);
+            atomicAdd(p.hist + st.base + key, 0x8000u);
+          }
+        }
+      }
+      const long long offL = __shfl_sync(kFull, st.off, L);
+      if (neg && so < 0) {
+        k = count_below(p.thr + offL, pc, s);
+        if (k > 0) atomicAdd(p.hist + offL + (k - 1), 1u);
+      }
+    }
+  }
+
+  // top-k: a row gains at most 32 candidates per chunk; select its k best in place (warp-cooperatively,
+  // one row at a time) as soon as fewer than kSlots * 32 free slots remain
+  __device__ static __forceinline__ void compact_topk(const Params& p, RowState& st, const EpiCtx& ctx, int lane) {
+    constexpr unsigned kFull = 0xffffffffu;
+    int* ncand = n_cand(ctx);
+    unsigned need = __ballot_sync(kFull, ncand[lane] > p.cap - kSlots * 32);
+    while (need) {
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      const long long cb = st.cbase + (long long)(src - lane) * p.cap;
+      const int n = ncand[src];
+      const float kth = p.cap <= 256 ? warp_select_topk<8>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
+                                     : compact_row(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane);
+      if (lane == src) {
+        ncand[lane] = p.topk;
+        st.tau = kth;
+        st.lim = fminf(st.tlim, st.tau);
+      }
+      __syncwarp();
+    }
+  }
+
+  // Drain the deferred chunks (called after the accumulator has been handed back to the MMA warp).
+  __device__ static __forceinline__ void drain(const Params& p, RowState& st, const EpiCtx& ctx) {
+    if (st.nslot == 0) return;
+    const int lane = (int)ptx::lane_id();
+    __syncwarp();
+    int begin = 0;
+#pragma unroll
+    for (int sl = 0; sl < kSlots; ++sl) {
+      if (sl < st.nslot) {
+        process_range(p, st, ctx, begin, st.q_end[sl], st.cc_q[sl], st.ci_q[sl], st.ok_q[sl], st.col0_q[sl], lane);
+        begin = st.q_end[sl];
+      }
+    }
+    __syncwarp();
+    st.qn = 0;
+    st.nslot = 0;
+    if (p.topk > 0) compact_topk(p, st, ctx, lane);
+  }
+
+  // scatter the elements selected by `mb` into the queue starting at `base`; returns their number
+  __device__ static __forceinline__ int push(const EpiCtx& ctx, const uint32_t (&acc)[32], unsigned mb, int base,
+                                             int lane) {
+    float* qv = q_val(ctx);
+    uint16_t* qt = q_tag(ctx);
+    const int mine = __popc(mb);
+    const int incl = warp_incl_scan(mine, lane);
+    int pos = base + incl - mine;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      if (mb & (1u << e)) {
+        qv[pos] = __uint_as_float(acc[e]);
+        qt[pos] = (uint16_t)((lane << 5) | e);
+        ++pos;
+      }
+    }
+    return __shfl_sync(0xffffffffu, incl, 31);
+  }
+
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
                                                  const uint32_t (&acc)[32], const GemmShape& sh, const EpiCtx& ctx) {
     constexpr unsigned kFull = 0xffffffffu;
@@ -370,108 +504,41 @@ struct EvalEpiT {
     for (int e = 0; e < 32; ++e) m |= (__uint_as_float(acc[e]) > st.lim) ? (1u << e) : 0u;
     if (!__any_sync(kFull, m != 0)) return;
 
-    float* qv = q_val(ctx);
-    uint16_t* qt = q_tag(ctx);
-    int* ncand = n_cand(ctx);
-    const float* ts = thr_s(ctx);
-    unsigned* cs = cnt_s(ctx);
-
-    const int total = __shfl_sync(kFull, warp_incl_scan(__popc(m), lane), 31);
-    const int nb = total <= kQueueCap ? 1 : 32 / kBatchCols;  // kBatchCols columns x 32 rows always fit
-    for (int bi = 0; bi < nb; ++bi) {
-      const unsigned mb = nb == 1 ? m : (m & (((1u << kBatchCols) - 1u) << (kBatchCols * bi)));
-      const int mine = __popc(mb);
-      const int incl = nb == 1 ? 0 : warp_incl_scan(mine, lane);
-      const int incl1 = nb == 1 ? warp_incl_scan(mine, lane) : incl;
-      const int btotal = nb == 1 ? total : __shfl_sync(kFull, incl1, 31);
-      if (btotal == 0) continue;
-      int pos = incl1 - mine;
+    // ---- collect: the passing elements go to the warp queue; they are binned in drain(), after the
+    // accumulator has been released, so the MMA warp never waits for a slow chunk
+    const int total = __reduce_add_sync(kFull, __popc(m));
+    if (st.nslot == kSlots || st.qn + total > kQueueCap) drain(p, st, ctx);
+    if (total <= kQueueCap) {
+      push(ctx, acc, m, st.qn, lane);
+      st.qn += total;
+      const int sl = st.nslot++;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        if (mb & (1u << e)) {
-          qv[pos] = __uint_as_float(acc[e]);
-          qt[pos] = (uint16_t)((lane << 5) | e);
-          ++pos;
+      for (int k = 0; k < kSlots; ++k) {
+        if (k == sl) {
+          st.q_end[k] = st.qn;
+          st.col0_q[k] = col0;
+          st.cc_q[k] = cc;
+          st.ci_q[k] = ci;
+          st.ok_q[k] = colok;
         }
       }
-      __syncwarp();
-      for (int r0 = 0; r0 < btotal; r0 += 32) {
-        const int r = r0 + lane;
-        const bool active = r < btotal;
-        const float s = active ? qv[r] : 0.f;
-        const int tag = active ? (int)qt[r] : 0;
-        const int L = tag >> 5, e = tag & 31;  // owner lane (row) and column of the element
-        const int qc = __shfl_sync(kFull, st.qc, L);
-        const int qi = __shfl_sync(kFull, st.qi, L);
-        const int pc = __shfl_sync(kFull, st.cnt, L);
-        const int so = __shfl_sync(kFull, st.so, L);
-        const float tl = __shfl_sync(kFull, st.tlim, L);
-        const float tau = __shfl_sync(kFull, st.tau, L);
-        const int ccol = __shfl_sync(kFull, cc, e);
-        const int cicol = __shfl_sync(kFull, ci, e);
-        const int ok = __shfl_sync(kFull, colok, e);
-        const bool cand = active && ok && cicol != qi;  // i_j == i_q: self (or an id collision), never a candidate
-        if (cand && p.topk > 0 && s > tau) {
-          const int slot = atomicAdd(&ncand[L], 1);
-          const long long cb = st.cbase + (long long)(L - lane) * p.cap + slot;  // rows of a warp are consecutive
-          p.cand_val[cb] = s;
-          p.cand_idx[cb] = col0 + e;
-        }
-        // rank counting: a negative above at least the lowest relevant item; k = #{thresholds < s} >= 1
-        const bool neg = cand && s > tl && ccol != qc;
-        const bool cached = neg && so >= 0;
-        int k = 0;
-        if (cached) k = count_below_smem(ts + so, pc, s);
-        // the elements of a round mostly come from one hot row and land in one bucket: the first
-        // cached lane counts all lanes that share its (row, bucket) key with a single shared-memory
-        // atomic, the others add their own
-        const int key = cached ? (so + k - 1) : -1;
-        const unsigned cm = __ballot_sync(kFull, cached);
-        if (cm != 0u) {
-          const int lead = __ffs(cm) - 1;
-          const int key_lead = __shfl_sync(kFull, key, lead);
-          const unsigned same = __ballot_sync(kFull, cached && key == key_lead);
-          if (cached && (lane == lead || key != key_lead)) {
-            const unsigned add = lane == lead ? (unsigned)__popc(same) : 1u;
-            const int shift = (key & 1) * 16;
-            const unsigned old = (atomicAdd(cs + (key >> 1), add << shift) >> shift) & 0xffffu;
-            // keep the 16-bit field far from overflow: the (single) adder that takes it across 0x8000
-            // moves exactly 0x8000 counts to the global histogram
-            if (old < 0x8000u && old + add >= 0x8000u) {
-              atomicSub(cs + (key >> 1), 0x8000u << shift);
-              atomicAdd(p.hist + st.base + key, 0x8000u);
-            }
-          }
-        }
-        const long long offL = __shfl_sync(kFull, st.off, L);
-        if (neg && so < 0) {
-          k = count_below(p.thr + offL, pc, s);
-          if (k > 0) atomicAdd(p.hist + offL + (k - 1), 1u);
-        }
-      }
-      __syncwarp();
-    }
-
-    if (p.topk > 0) {
-      // a row gains at most 32 candidates per chunk: compact (warp-cooperatively, one row at a time)
-      // as soon as fewer than 32 free slots remain
-      unsigned need = __ballot_sync(kFull, ncand[lane] > p.cap - 32);
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        const long long cb = st.cbase + (long long)(src - lane) * p.cap;
-        const int n = ncand[src];
-        const float kth = p.cap <= 256 ? warp_select_topk<8>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
-                                       : compact_row(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane);
-        if (lane == src) {
-          ncand[lane] = p.topk;
-          st.tau = kth;
-          st.lim = fminf(st.tlim, st.tau);
-        }
+    } else {
+      // a chunk denser than the whole queue: bin it now, kBatchCols columns at a time
+#pragma unroll 1
+      for (int bi = 0; bi < 32 / kBatchCols; ++bi) {
+        const unsigned mb = m & (((1u << kBatchCols) - 1u) << (kBatchCols * bi));
+        const int n = push(ctx, acc, mb, 0, lane);
+        __syncwarp();
+        process_range(p, st, ctx, 0, n, cc, ci, colok, col0, lane);
         __syncwarp();
       }
+      if (p.topk > 0) compact_topk(p, st, ctx, lane);
     }
     (void)row;
+  }
+
+  __device__ static __forceinline__ void tile_end(const Params& p, RowState& st, const GemmShape&, const EpiCtx& ctx) {
+    drain(p, st, ctx);
   }
 
   __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part,

@@ -75,6 +75,7 @@ struct EpiCtx {
 //   static void row_begin(const Params&, RowState&, int row, int part, const GemmShape&, const EpiCtx&);
 //   static void chunk32(const Params&, RowState&, int row, int col0, const uint32_t (&acc)[32], const GemmShape&,
 //                       const EpiCtx&);
+//   static void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&);   after the accumulator is released
 //   static void row_end(const Params&, RowState&, int row, int part, const GemmShape&, const EpiCtx&);
 // `row` is the global query row owned by the thread, `part` identifies the partial result slot
 // (column chunk x epilogue half) when a row is split over several units / warps.
@@ -239,6 +240,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        Epi::tile_end(ep, rs, shape, ctx);  // work deferred until the accumulator is back with the MMA warp
       }
       Epi::row_end(ep, rs, row, part, shape, ctx);
     }

@@ -15,6 +15,8 @@ struct LossWs {
   ZStats* zs;
   float* scal;
   int* bad;
+  double* acc;
+  unsigned int* acc_max;
   int64_t b_pad;
   int parts_max;
   size_t bytes;
@@ -41,6 +43,8 @@ static void loss_ws_layout(LossWs& w, uint8_t* base, int64_t b, int64_t d, int p
   w.zs = reinterpret_cast<ZStats*>(cur); cur += 256;
   w.scal = reinterpret_cast<float*>(cur); cur += 256;
   w.bad = reinterpret_cast<int*>(cur); cur += 256;
+  w.acc = reinterpret_cast<double*>(cur); cur += 256;
+  w.acc_max = reinterpret_cast<unsigned int*>(cur); cur += 256;
   w.bytes = (size_t)(cur - base);
 }
 
@@ -88,18 +92,15 @@ extern "C" int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int6
   LossWs w;
   loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes);
   const int T = 256;
-  CU_TRY(cudaMemsetAsync(w.zs, 0, 768, s));  // ZStats, scal, flags
+  CU_TRY(cudaMemsetAsync(w.zs, 0, 1280, s));  // ZStats, scal, flags, batch accumulators
   CU_TRY(cudaMemsetAsync(out, 0, WEALY_OUT_COUNT * sizeof(double), s));
-  // the padded k-columns (j >= b) of the transposed planes must be zero
-  CU_TRY(cudaMemsetAsync(w.ut_hi, 0, (size_t)d * w.b_pad * 2, s));
-  if (w.ut_lo) CU_TRY(cudaMemsetAsync(w.ut_lo, 0, (size_t)d * w.b_pad * 2, s));
   ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, w.label, (int)b, w.bad);
   ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_idx, w.idx, (int)b, w.bad);
   CU_TRY(cudaGetLastError());
   const bool ntx = cfg->kind == WEALY_LOSS_NTXENT;
   // NT-Xent: x/(|x|+1e-6) and statistics of the raw z; CLEWS: F.normalize (eps 1e-12), statistics of the normalised z
-  W_TRY(launch_prep(z, ldz, b, d, dtype, ntx ? kPrepL2AddEps : kPrepL2Clamp, ntx ? 1e-6f : 1e-12f, w.u, w.ut_hi,
-                    w.ut_lo, w.b_pad, w.zs, ntx ? 0 : 1, s));
+  W_TRY(launch_prep(z, ldz, b, d, dtype, ntx ? kPrepL2AddEps : kPrepL2Clamp, ntx ? 1e-6f : 1e-12f, w.u, nullptr,
+                    nullptr, 0, w.zs, ntx ? 0 : 1, s));
   LossParams lp;
   loss_params(lp, cfg, w, b);
   GemmShape sh;
@@ -116,7 +117,9 @@ extern "C" int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int6
   dc.epsilon = cfg->epsilon;
   dc.uw = cfg->uw;
   dc.numerically_friendly = cfg->numerically_friendly;
-  loss_finalize_kernel<<<1, 1024, 0, s>>>(dc, (int)b, (int)d, parts, w.partial, w.zs, w.rowstat, w.scal, out);
+  const unsigned fb = (unsigned)ceil_div(b, 256);
+  loss_merge_kernel<<<fb, 256, 0, s>>>(dc, (int)b, parts, w.partial, w.rowstat, w.acc, w.acc_max);
+  loss_finish_kernel<<<fb, 256, 0, s>>>(dc, (int)b, (int)d, w.acc, w.acc_max, w.zs, w.rowstat, w.scal, out);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
 }
@@ -135,7 +138,14 @@ extern "C" int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int
   GemmShape sh;
   fill_shape(sh, b, b, w.u.d_pad, 64, 1 << 20);
   W_TRY(launch_gemm<LossWEpi>(cfg->passes, w.u, w.u, sh, lp, s));
-  // 2) dU = W' * U   (A = W' [b][b_pad], B = U^T [d][b_pad], K = b_pad)
+  // 2) dU = W' * U   (A = W' [b][b_pad], B = U^T [d][b_pad], K = b_pad); the transposed planes are only
+  //    needed here, so they are built now (tiled transpose, zero k-padding) rather than in the forward
+  {
+    dim3 grid((unsigned)ceil_div(w.b_pad, 32), (unsigned)ceil_div(d, 32), w.u.lo ? 2 : 1);
+    transpose_plane_kernel<<<grid, 256, 0, s>>>(w.u.hi, w.u.lo, (int)b, (int)d, (long long)w.u.d_pad, w.ut_hi, w.ut_lo,
+                                                (long long)w.b_pad);
+    CU_TRY(cudaGetLastError());
+  }
   Planes pw, put;
   pw.hi = w.w_hi; pw.lo = w.w_lo; pw.rows = b; pw.d_pad = w.b_pad;
   put.hi = w.ut_hi; put.lo = w.ut_lo; put.rows = d; put.d_pad = w.b_pad;

@@ -112,6 +112,7 @@ struct LossStatsEpi {
     }
   }
 
+  __device__ static __forceinline__ void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&) {}
   __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part, const GemmShape&, const EpiCtx&) {
     if (!st.valid) return;
     float* o = p.partial + ((long long)part * p.b + row) * kStatWidth;
@@ -185,13 +186,16 @@ struct LossWEpi {
     }
   }
 
+  __device__ static __forceinline__ void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&) {}
   __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, const EpiCtx&) {}
 };
 
 // ---------------------------------------------------------------------------------------------
-// finalize (single block): merge the partial records, reduce the loss and the logdict numbers,
-// write the per-row coefficients the W sweep needs.
-// out (double[WEALY_OUT_COUNT]) indices follow include/wealy_b200.h.
+// finalize, two small multi-block kernels:
+//   loss_merge_kernel    one thread per anchor row: merge the partial records of the sweep, write the
+//                        per-row quantities, block-reduce the batch sums into `acc` (double atomics)
+//   loss_finish_kernel   turn the batch sums into the loss / logdict numbers (`out`, indices of
+//                        include/wealy_b200.h) and the per-row coefficients of the W sweep (`rowstat`)
 // scal[0] = factor the Jacobian kernel applies to dU (1/(B tau) for NT-Xent, 1/S for CLEWS).
 // ---------------------------------------------------------------------------------------------
 struct LossCfgDev {
@@ -200,141 +204,161 @@ struct LossCfgDev {
   int numerically_friendly;
 };
 
-__device__ __forceinline__ double block_sum(double v, double* sh) {
+// acc layout (doubles): 0 loss sum | 1 sum align | 2 sum uniform | 3 npos | 4 nneg | 5 anchors with pos
+//                       6 sum_pos d | 7 sum_all d | 8 sum_neg d ; acc_max (uint bits of floats): 0 max 1/npos, 1 max cu-term
+constexpr int kAccCount = 16;
+
+__device__ __forceinline__ void block_add(double v, double* target) {
+  __shared__ double sh[32];
   v = warp_sum_d(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   __syncthreads();
   if (l == 0) sh[w] = v;
   __syncthreads();
-  double t = 0.0;
   if (w == 0) {
-    t = l < (int)(blockDim.x >> 5) ? sh[l] : 0.0;
+    double t = l < (int)(blockDim.x >> 5) ? sh[l] : 0.0;
     t = warp_sum_d(t);
-    if (l == 0) sh[32] = t;
+    if (l == 0 && t != 0.0) atomicAdd(target, t);
   }
-  __syncthreads();
-  return sh[32];
 }
 
-__device__ __forceinline__ double block_max(double v, double* sh) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
-  if (l == 0) sh[w] = v;
-  __syncthreads();
-  double t = 0.0;
-  if (w == 0) {
-    t = l < (int)(blockDim.x >> 5) ? sh[l] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
-    if (l == 0) sh[32] = t;
-  }
-  __syncthreads();
-  return sh[32];
-}
-
-__global__ void __launch_bounds__(1024) loss_finalize_kernel(LossCfgDev cfg, int b, int d, int parts,
-                                                             const float* __restrict__ partial,
-                                                             const ZStats* __restrict__ zs, float* __restrict__ rowstat,
-                                                             float* __restrict__ scal, double* __restrict__ out) {
-  __shared__ double sh[33];
-  const double B = (double)b;
+__global__ void __launch_bounds__(256) loss_merge_kernel(LossCfgDev cfg, int b, int parts,
+                                                         const float* __restrict__ partial, float* __restrict__ rowstat,
+                                                         double* __restrict__ acc, unsigned int* __restrict__ acc_max) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < b;
   if (cfg.kind == kLossNtxent) {
-    double lsum = 0.0;
-    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    double term = 0.0;
+    if (live) {
       float M = neg_inf();
       for (int p = 0; p < parts; ++p) M = fmaxf(M, partial[((long long)p * b + i) * kStatWidth]);
       float A = 0.f, P = 0.f;
       for (int p = 0; p < parts; ++p) {
-        const float* r = partial + ((long long)p * b + i) * kStatWidth;
-        if (r[0] > neg_inf()) {
-          const float sc = exp2f(r[0] - M);
-          A = fmaf(r[1], sc, A);
-          P = fmaf(r[2], sc, P);
+        const float4 r = *reinterpret_cast<const float4*>(partial + ((long long)p * b + i) * kStatWidth);
+        if (r.x > neg_inf()) {
+          const float sc = exp2f(r.x - M);
+          A = fmaf(r.y, sc, A);
+          P = fmaf(r.z, sc, P);
         }
       }
-      const float Ae = A + 1e-8f;               // losses.py:65-66
+      const float Ae = A + 1e-8f;  // losses.py:65-66
       const float rho = P / Ae + 1e-8f;
-      lsum += -(double)logf(rho);
+      term = -(double)logf(rho);
       reinterpret_cast<float4*>(rowstat)[i] = make_float4(M, 1.f / (rho * Ae), P / (rho * Ae * Ae), 0.f);
     }
-    lsum = block_sum(lsum, sh);
-    if (threadIdx.x == 0) {
-      out[0] = lsum / B;
-      scal[0] = 1.f / ((float)b * cfg.temperature);
-    }
+    block_add(term, acc + 0);
   } else {
-    double s_align = 0.0, s_uni = 0.0, s_np = 0.0, s_nn = 0.0, s_h = 0.0, s_pd = 0.0, s_ad = 0.0, s_nd = 0.0;
-    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    double t_align = 0.0, t_uni = 0.0, t_np = 0.0, t_nn = 0.0, t_h = 0.0, t_pd = 0.0, t_ad = 0.0, t_nd = 0.0;
+    float m_inv_np = 0.f, m_cu = 0.f;
+    if (live) {
       float np = 0.f, nn = 0.f, pd = 0.f, nx = 0.f, ad = 0.f, nd = 0.f;
       for (int p = 0; p < parts; ++p) {
         const float* r = partial + ((long long)p * b + i) * kStatWidth;
-        np += r[0]; nn += r[1]; pd += r[2]; nx += r[3]; ad += r[4]; nd += r[5];
+        const float4 r0 = *reinterpret_cast<const float4*>(r);
+        const float2 r1 = *reinterpret_cast<const float2*>(r + 4);
+        np += r0.x; nn += r0.y; pd += r0.z; nx += r0.w; ad += r1.x; nd += r1.y;
       }
-      const float align = pd / fmaxf(np, cfg.eps);          // _per_anchor_mean, losses.py:202-208
+      const float align = pd / fmaxf(np, cfg.eps);  // _per_anchor_mean, losses.py:202-208
       const float uni = nx / fmaxf(nn, cfg.eps);
       const float lu = cfg.numerically_friendly ? log1pf(uni) : logf(uni + cfg.epsilon);
-      if (np > 0.f) { s_align += align; s_h += 1.0; }
-      s_uni += lu;
-      s_np += np; s_nn += nn; s_pd += pd; s_ad += ad; s_nd += nd;
-      // stash what phase 2 needs
-      reinterpret_cast<float4*>(rowstat)[i] = make_float4(np, nn, uni, 0.f);
-    }
-    s_align = block_sum(s_align, sh);
-    s_uni = block_sum(s_uni, sh);
-    s_np = block_sum(s_np, sh);
-    s_nn = block_sum(s_nn, sh);
-    s_h = block_sum(s_h, sh);
-    s_pd = block_sum(s_pd, sh);
-    s_ad = block_sum(s_ad, sh);
-    s_nd = block_sum(s_nd, sh);
-    const double H = s_h > 0.0 ? s_h : 1.0;
-    const double l_align = s_h > 0.0 ? s_align / s_h : 0.0;  // losses.py:239
-    const double l_uni = s_uni / B;
-    // true coefficients: dS_ij = -pos ca_i + X_ij neg cu_i.  W is stored in fp16, so scale it by
-    // S = 1 / max_i max(ca_i, cu_i max_j X_ij): |W'| <= 2 whatever the batch looks like (no overflow, and the
-    // largest entries sit at the top of the fp16 range); the Jacobian kernel multiplies by 1/S.
-    float bound = 0.f;
-    for (int i = threadIdx.x; i < b; i += blockDim.x) {
-      const float4 r = reinterpret_cast<const float4*>(rowstat)[i];
-      const float np = r.x, nn = r.y, uni = r.z;
-      const float ca = np > 0.f ? (float)(1.0 / ((double)np * H)) : 0.f;
+      if (np > 0.f) { t_align = align; t_h = 1.0; }
+      t_uni = lu; t_np = np; t_nn = nn; t_pd = pd; t_ad = ad; t_nd = nd;
+      // true coefficients: dS_ij = -pos ca_i + X_ij neg cu_i, ca_i = 1/(npos_i H) (H known in the finish kernel)
       const float outer = cfg.numerically_friendly ? 1.f / (1.f + uni) : 1.f / (uni + cfg.epsilon);
-      const float cu = nn > 0.f ? (float)((double)cfg.uw * (double)cfg.gamma / (B * (double)nn)) * outer : 0.f;
-      // X_ij <= e^b, and X_ij <= sum_j X_ij neg_ij = nneg_i * uni_i: rows with a vanishing uniformity
-      // term (huge 1/(uni+eps) in the non-friendly branch) must not dictate the scale
-      bound = fmaxf(bound, fmaxf(ca, fabsf(cu) * fminf(expf(cfg.b), nn * uni)));
-      reinterpret_cast<float4*>(rowstat)[i] = make_float4(ca, cu, 0.f, 0.f);
+      const float cu = nn > 0.f ? (float)((double)cfg.uw * (double)cfg.gamma / ((double)b * (double)nn)) * outer : 0.f;
+      // X_ij <= e^b and X_ij <= sum_j X_ij neg_ij = nneg_i uni_i: rows with a vanishing uniformity term
+      // (huge 1/(uni+eps) in the non-friendly branch) must not dictate the fp16 scale of W
+      m_inv_np = np > 0.f ? 1.f / np : 0.f;
+      m_cu = fabsf(cu) * fminf(expf(cfg.b), nn * uni);
+      reinterpret_cast<float4*>(rowstat)[i] = make_float4(m_inv_np, cu, 0.f, 0.f);
     }
-    bound = (float)block_max(bound, sh);
+    block_add(t_align, acc + 1);
+    block_add(t_uni, acc + 2);
+    block_add(t_np, acc + 3);
+    block_add(t_nn, acc + 4);
+    block_add(t_h, acc + 5);
+    block_add(t_pd, acc + 6);
+    block_add(t_ad, acc + 7);
+    block_add(t_nd, acc + 8);
+    m_inv_np = warp_max(m_inv_np);
+    m_cu = warp_max(m_cu);
+    if ((threadIdx.x & 31) == 0) {
+      atomicMax(acc_max + 0, __float_as_uint(m_inv_np));  // non-negative floats order like uints
+      atomicMax(acc_max + 1, __float_as_uint(m_cu));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) loss_finish_kernel(LossCfgDev cfg, int b, int d, const double* __restrict__ acc,
+                                                          const unsigned int* __restrict__ acc_max,
+                                                          const ZStats* __restrict__ zs, float* __restrict__ rowstat,
+                                                          float* __restrict__ scal, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double B = (double)b;
+  const bool writer = (i == 0);
+  if (cfg.kind == kLossNtxent) {
+    if (writer) {
+      out[0] = acc[0] / B;
+      scal[0] = 1.f / ((float)b * cfg.temperature);
+    }
+  } else {
+    const double H = acc[5] > 0.0 ? acc[5] : 1.0;
+    // W is stored in fp16: scale it by S = 1 / max_i max(ca_i, cu_i max_j X_ij) so that |W'| <= 2 whatever the
+    // batch looks like; the Jacobian kernel multiplies by 1/S
+    const float bound = fmaxf((float)((double)__uint_as_float(acc_max[0]) / H), __uint_as_float(acc_max[1]));
     const float S = bound > 0.f ? 1.f / bound : 1.f;
-    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+    if (i < b) {
       float4 r = reinterpret_cast<const float4*>(rowstat)[i];
-      r.x *= S;
-      r.y *= S;
+      r.x = (float)((double)r.x / H) * S;  // ca' = S / (npos_i H)
+      r.y = r.y * S;                       // cu'
       reinterpret_cast<float4*>(rowstat)[i] = r;
     }
-    if (threadIdx.x == 0) {
+    if (writer) {
+      const double l_align = acc[5] > 0.0 ? acc[1] / acc[5] : 0.0;  // losses.py:239
+      const double l_uni = acc[2] / B;
       const double n2 = B * B;
       out[0] = l_align + (double)cfg.uw * l_uni;
       out[4] = l_align;
       out[5] = l_uni;
-      out[6] = s_np;
-      out[7] = s_nn;
-      out[8] = s_h / B;
+      out[6] = acc[3];
+      out[7] = acc[4];
+      out[8] = acc[5] / B;
       // tops.mmean(d, mask=pos_mask) averages over the COMPLEMENT of the mask (losses.py:267-268)
-      out[9] = s_np > 0.0 ? (s_ad - s_pd) / fmax(n2 - s_np, 1e-7) : 0.0;
-      out[10] = s_nn > 0.0 ? (s_ad - s_nd) / fmax(n2 - s_nn, 1e-7) : 0.0;
+      out[9] = acc[3] > 0.0 ? (acc[7] - acc[6]) / fmax(n2 - acc[3], 1e-7) : 0.0;
+      out[10] = acc[4] > 0.0 ? (acc[7] - acc[8]) / fmax(n2 - acc[4], 1e-7) : 0.0;
       scal[0] = 1.f / S;
     }
   }
-  if (threadIdx.x == 0) {
+  if (writer) {
     const double n = B * (double)d;
     out[1] = (double)__uint_as_float(zs->maxabs_bits);
     out[2] = zs->sum / n;
     const double var = n > 1.0 ? (zs->sumsq - zs->sum * zs->sum / n) / (n - 1.0) : 0.0;
     out[3] = sqrt(var > 0.0 ? var : 0.0);
+  }
+}
+
+// [rows][ld_in] fp16 plane -> [cols][ld_out] (the K-major "B" operand of dU = W * U); columns
+// rows <= r < ld_out are written as zeros (k padding).  32 x 32 shared-memory tiles, coalesced both ways.
+__global__ void __launch_bounds__(256) transpose_plane_kernel(const __half* __restrict__ in0,
+                                                              const __half* __restrict__ in1, int rows, int cols,
+                                                              long long ld_in, __half* __restrict__ out0,
+                                                              __half* __restrict__ out1, long long ld_out) {
+  __shared__ __half tile[32][34];
+  const __half* in = blockIdx.z == 0 ? in0 : in1;
+  __half* out = blockIdx.z == 0 ? out0 : out1;
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int r = r0 + ty + k, c = c0 + tx;
+    tile[ty + k][tx] = (r < rows && c < cols) ? in[(long long)r * ld_in + c] : __float2half_rn(0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    const int c = c0 + ty + k, r = r0 + tx;
+    if (c < cols && r < ld_out) out[(long long)c * ld_out + r] = tile[tx][ty + k];
   }
 }
 
