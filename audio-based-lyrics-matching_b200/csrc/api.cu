@@ -172,6 +172,12 @@ static void fill_shape(GemmShape& sh, int64_t m, int64_t n, int64_t d_pad, int b
   if (sh.tiles_per_chunk < 1) sh.tiles_per_chunk = 1;
   sh.n_col_chunks = (int)ceil_div(sh.n_col_tiles, sh.tiles_per_chunk);
   if (sh.n_col_chunks < 1) sh.n_col_chunks = 1;
+  // row blocks per scheduling group: the CTAs resident together cover group_rows row blocks x all chunks
+  int gr = env_int("WEALY_GROUP_ROWS", 0);
+  if (gr <= 0) gr = num_sms() / sh.n_col_chunks;
+  if (gr < 1) gr = 1;
+  if (gr > sh.n_row_blocks) gr = sh.n_row_blocks > 0 ? sh.n_row_blocks : 1;
+  sh.group_rows = gr;
 }
 
 template <class Epi, int kPasses, int kBlockK, int kEpiWarps>

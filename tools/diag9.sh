@@ -1,0 +1,13 @@
+#!/bin/bash
+mkdir -p gpurun_out
+L=gpurun_out/diag9.log
+: > $L
+run() { echo "### $*" >> $L; timeout 900 "$@" >> $L 2>&1; echo "exit=$?" >> $L; }
+run python -m pytest tests -m gpu -q
+run python tools/gpu_diag.py time fp16x3 100000 1024
+WEALY_GROUP_ROWS=100000 run python tools/gpu_diag.py time fp16x3 100000 1024
+WEALY_GROUP_ROWS=18 run python tools/gpu_diag.py time fp16x3 100000 1024
+run python tools/gpu_diag.py time fp16x3 100000 1024 0 0.5
+WEALY_GROUP_ROWS=100000 run python tools/gpu_diag.py time fp16x3 100000 1024 0 0.5
+run python tools/gpu_diag.py time fp16 100000 1024
+tail -30 $L
