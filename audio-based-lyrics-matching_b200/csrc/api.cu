@@ -64,6 +64,27 @@ static int num_sms() {
   return cached;
 }
 
+// Stream-ordered device allocations from the default memory pool, configured once per device to keep
+// freed memory cached (no cudaMalloc / cudaFree round trips through the driver when an evaluation
+// plan is rebuilt every call, as the end-to-end path of bench.py does).
+static cudaError_t dev_alloc(void** ptr, size_t bytes, cudaStream_t s) {
+  static bool configured[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    configured[dev] = true;
+  }
+  return cudaMallocAsync(ptr, bytes, s);
+}
+static void dev_free(void* ptr, cudaStream_t s) {
+  if (ptr) cudaFreeAsync(ptr, s);
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA descriptors (driver entry point fetched through the runtime: no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------
@@ -155,7 +176,24 @@ static int launch_prep(const void* x, int64_t ld, int64_t n, int64_t d, int dtyp
 // ------------------------------------------------------------------------------------------
 // contraction launcher
 // ------------------------------------------------------------------------------------------
-static void fill_shape(GemmShape& sh, int64_t m, int64_t n, int64_t d_pad, int block_k, int max_chunks) {
+// per-launch work counters of the dynamic unit scheduler (one int per launch, zeroed stream-ordered)
+__device__ int g_unit_counters[4096];
+
+static int next_unit_counter(int** out, cudaStream_t s) {
+  static thread_local int* base[64] = {nullptr};
+  static int seq = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return fail(WEALY_ERR_UNSUPPORTED, "device index %d", dev);
+  if (!base[dev]) CU_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&base[dev]), g_unit_counters));
+  const int slot = __atomic_fetch_add(&seq, 1, __ATOMIC_RELAXED) & 4095;
+  *out = base[dev] + slot;
+  CU_TRY(cudaMemsetAsync(*out, 0, sizeof(int), s));
+  return WEALY_OK;
+}
+
+static void fill_shape(GemmShape& sh, int64_t m, int64_t n, int64_t d_pad, int block_k, int max_chunks,
+                       int tiles_per_unit = 0) {
   sh.m_rows = (int)m;
   sh.n_cols = (int)n;
   sh.k_blocks = (int)(d_pad / block_k);
@@ -165,6 +203,8 @@ static void fill_shape(GemmShape& sh, int64_t m, int64_t n, int64_t d_pad, int b
   // chunks than column tiles; CTAs resident together sweep the same chunk (L2 reuse of candidates)
   const int64_t target_units = (int64_t)num_sms() * env_int("WEALY_ROUNDS", 16);
   int64_t chunks = ceil_div(target_units, sh.n_row_blocks > 0 ? sh.n_row_blocks : 1);
+  // short units (a few column tiles) keep the CTAs that share candidate tiles within one unit of each other
+  if (tiles_per_unit > 0 && chunks < ceil_div(sh.n_col_tiles, tiles_per_unit)) chunks = ceil_div(sh.n_col_tiles, tiles_per_unit);
   if (chunks > sh.n_col_tiles) chunks = sh.n_col_tiles;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -174,7 +214,7 @@ static void fill_shape(GemmShape& sh, int64_t m, int64_t n, int64_t d_pad, int b
   if (sh.n_col_chunks < 1) sh.n_col_chunks = 1;
   // row blocks per scheduling group: the CTAs resident together cover group_rows row blocks x all chunks
   int gr = env_int("WEALY_GROUP_ROWS", 0);
-  if (gr <= 0) gr = num_sms() / sh.n_col_chunks;
+  if (gr <= 0) gr = num_sms() / (sh.n_col_chunks < 4 ? sh.n_col_chunks : 4);  // ~4 chunks in flight per group
   if (gr < 1) gr = 1;
   if (gr > sh.n_row_blocks) gr = sh.n_row_blocks > 0 ? sh.n_row_blocks : 1;
   sh.group_rows = gr;
@@ -202,7 +242,9 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
   const int n_units = sh.n_row_blocks * sh.n_col_chunks;
   if (n_units == 0) return WEALY_OK;
   const int grid = n_units < num_sms() ? n_units : num_sms();
-  kern<<<grid, 64 + kEpiWarps * 32, kSmemBytes, s>>>(maps, sh, ep);
+  GemmShape shl = sh;
+  W_TRY(next_unit_counter(&shl.unit_counter, s));
+  kern<<<grid, 64 + kEpiWarps * 32, kSmemBytes, s>>>(maps, shl, ep);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
 }
@@ -275,6 +317,7 @@ extern "C" int wealy_sim_matrix(const void* x, int64_t n, int64_t ldx, const voi
 // ------------------------------------------------------------------------------------------
 struct wealy_eval_plan {
   int64_t nq = 0, nc = 0;
+  cudaStream_t stream = nullptr;  // stream the plan was built on (frees are ordered on it)
   bool same_ids = false;
   int *q_c = nullptr, *q_i = nullptr, *c_c = nullptr, *c_i = nullptr;
   int *sorted_c = nullptr, *sorted_idx = nullptr;
@@ -299,11 +342,10 @@ extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
   if (!p) return;
   void* ptrs[] = {p->q_c, p->q_i, p->sorted_c, p->sorted_idx, p->seg_lo, p->seg_len, p->npos, p->off,
                   p->raw, p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf};
-  for (void* q : ptrs)
-    if (q) cudaFree(q);
+  for (void* q : ptrs) dev_free(q, p->stream);
   if (!p->same_ids) {
-    if (p->c_c) cudaFree(p->c_c);
-    if (p->c_i) cudaFree(p->c_i);
+    dev_free(p->c_c, p->stream);
+    dev_free(p->c_i, p->stream);
   }
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
@@ -316,11 +358,11 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   const int T = 256;
   int* bad = nullptr;
   unsigned long long* totals = nullptr;
-  CU_TRY(cudaMalloc(&bad, 256));
+  CU_TRY(dev_alloc((void**)&bad, 256, s));
   totals = reinterpret_cast<unsigned long long*>(bad + 16);
   CU_TRY(cudaMemsetAsync(bad, 0, 256, s));
-  CU_TRY(cudaMalloc(&p->q_c, (size_t)nq * 4 + 4));
-  CU_TRY(cudaMalloc(&p->q_i, (size_t)nq * 4 + 4));
+  CU_TRY(dev_alloc((void**)&p->q_c, (size_t)nq * 4 + 4, s));
+  CU_TRY(dev_alloc((void**)&p->q_i, (size_t)nq * 4 + 4, s));
   ids_to_i32_kernel<<<(unsigned)ceil_div(nq, T), T, 0, s>>>((const long long*)queries_c, p->q_c, nq, bad);
   ids_to_i32_kernel<<<(unsigned)ceil_div(nq, T), T, 0, s>>>((const long long*)queries_i, p->q_i, nq, bad);
   p->same_ids = (queries_c == candidates_c && queries_i == candidates_i && p->nq == p->nc);
@@ -328,8 +370,8 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
     p->c_c = p->q_c;
     p->c_i = p->q_i;
   } else {
-    CU_TRY(cudaMalloc(&p->c_c, (size_t)nc * 4 + 4));
-    CU_TRY(cudaMalloc(&p->c_i, (size_t)nc * 4 + 4));
+    CU_TRY(dev_alloc((void**)&p->c_c, (size_t)nc * 4 + 4, s));
+    CU_TRY(dev_alloc((void**)&p->c_i, (size_t)nc * 4 + 4, s));
     ids_to_i32_kernel<<<(unsigned)ceil_div(nc, T), T, 0, s>>>((const long long*)candidates_c, p->c_c, nc, bad);
     ids_to_i32_kernel<<<(unsigned)ceil_div(nc, T), T, 0, s>>>((const long long*)candidates_i, p->c_i, nc, bad);
   }
@@ -337,20 +379,20 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
 
   // candidates sorted by clique id (CUB radix sort: id-only preprocessing, not on the per-eval path)
   int* iota = nullptr;
-  CU_TRY(cudaMalloc(&iota, (size_t)nc * 4 + 4));
-  CU_TRY(cudaMalloc(&p->sorted_c, (size_t)nc * 4 + 4));
-  CU_TRY(cudaMalloc(&p->sorted_idx, (size_t)nc * 4 + 4));
+  CU_TRY(dev_alloc((void**)&iota, (size_t)nc * 4 + 4, s));
+  CU_TRY(dev_alloc((void**)&p->sorted_c, (size_t)nc * 4 + 4, s));
+  CU_TRY(dev_alloc((void**)&p->sorted_idx, (size_t)nc * 4 + 4, s));
   iota_kernel<<<(unsigned)ceil_div(nc, T), T, 0, s>>>(iota, nc);
   size_t tmp_bytes = 0;
   CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, p->c_c, p->sorted_c, iota, p->sorted_idx, nc, 0, 32, s));
   void* tmp = nullptr;
-  CU_TRY(cudaMalloc(&tmp, tmp_bytes + 16));
+  CU_TRY(dev_alloc((void**)&tmp, tmp_bytes + 16, s));
   CU_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p->c_c, p->sorted_c, iota, p->sorted_idx, nc, 0, 32, s));
 
-  CU_TRY(cudaMalloc(&p->seg_lo, (size_t)nq * 4 + 4));
-  CU_TRY(cudaMalloc(&p->seg_len, (size_t)nq * 4 + 4));
-  CU_TRY(cudaMalloc(&p->npos, (size_t)nq * 4 + 4));
-  CU_TRY(cudaMalloc(&p->off, ((size_t)nq + 1) * 8));
+  CU_TRY(dev_alloc((void**)&p->seg_lo, (size_t)nq * 4 + 4, s));
+  CU_TRY(dev_alloc((void**)&p->seg_len, (size_t)nq * 4 + 4, s));
+  CU_TRY(dev_alloc((void**)&p->npos, (size_t)nq * 4 + 4, s));
+  CU_TRY(dev_alloc((void**)&p->off, ((size_t)nq + 1) * 8, s));
   segment_lookup_kernel<<<(unsigned)ceil_div(nq, T), T, 0, s>>>(p->q_c, p->q_i, nq, p->sorted_c, p->sorted_idx, p->c_i,
                                                                nc, p->seg_lo, p->seg_len, p->npos, totals);
   CU_TRY(cudaGetLastError());
@@ -358,7 +400,7 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   size_t scan_bytes = 0;
   CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, p->npos, p->off, nq + 1, s));
   void* tmp2 = nullptr;
-  CU_TRY(cudaMalloc(&tmp2, scan_bytes + 16));
+  CU_TRY(dev_alloc((void**)&tmp2, scan_bytes + 16, s));
   // npos has nq valid entries; entry nq is read by the scan of nq+1 items -> zero it first
   CU_TRY(cudaMemsetAsync(p->npos + nq, 0, 4, s));
   CU_TRY(cub::DeviceScan::ExclusiveSum(tmp2, scan_bytes, p->npos, p->off, nq + 1, s));
@@ -370,20 +412,20 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   CU_TRY(cudaMemcpyAsync(totals_h, totals, sizeof(totals_h), cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaMemcpyAsync(&total, p->off + nq, 8, cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaStreamSynchronize(s));
-  cudaFree(tmp);
-  cudaFree(tmp2);
-  cudaFree(iota);
-  cudaFree(bad);
+  dev_free(tmp, s);
+  dev_free(tmp2, s);
+  dev_free(iota, s);
+  dev_free(bad, s);
   if (bad_h[0] != 0) return fail(WEALY_ERR_ID_RANGE, "%d clique/version ids do not fit in 32 bits", bad_h[0]);
   p->total_pairs = total;
   p->no_relevant = (int64_t)totals_h[0];
   p->max_relevant = (int64_t)totals_h[1];
   const size_t pairs = (size_t)(total > 0 ? total : 1);
-  CU_TRY(cudaMalloc(&p->raw, pairs * 4));
-  CU_TRY(cudaMalloc(&p->thr, pairs * 4));
-  CU_TRY(cudaMalloc(&p->hist, pairs * 4));
-  CU_TRY(cudaMalloc(&p->lim, (size_t)nq * 4 + 4));
-  CU_TRY(cudaMalloc(&p->cnt, (size_t)nq * 4 + 4));
+  CU_TRY(dev_alloc((void**)&p->raw, pairs * 4, s));
+  CU_TRY(dev_alloc((void**)&p->thr, pairs * 4, s));
+  CU_TRY(dev_alloc((void**)&p->hist, pairs * 4, s));
+  CU_TRY(dev_alloc((void**)&p->lim, (size_t)nq * 4 + 4, s));
+  CU_TRY(dev_alloc((void**)&p->cnt, (size_t)nq * 4 + 4, s));
   return WEALY_OK;
 }
 
@@ -398,6 +440,7 @@ extern "C" int wealy_eval_plan_create(const int64_t* queries_c, const int64_t* q
   wealy_eval_plan* p = new wealy_eval_plan();
   p->nq = nq;
   p->nc = nc;
+  p->stream = (cudaStream_t)stream;
   int st = plan_build(p, queries_c, queries_i, candidates_c, candidates_i, (cudaStream_t)stream);
   if (st != WEALY_OK) {
     wealy_eval_plan_destroy(p);
@@ -443,10 +486,10 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
   // operand planes (cached allocation)
   const size_t need = planes_bytes(nq, d, passes) + (same ? 0 : planes_bytes(nc, d, passes)) + 2048;
   if (need > p->planes_cap) {
-    if (p->planes_buf) CU_TRY(cudaFree(p->planes_buf));
+    dev_free(p->planes_buf, s);
     p->planes_buf = nullptr;
     p->planes_cap = 0;
-    CU_TRY(cudaMalloc(&p->planes_buf, need));
+    CU_TRY(dev_alloc((void**)&p->planes_buf, need, s));
     p->planes_cap = need;
   }
   uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)p->planes_buf, 1024));
@@ -473,7 +516,7 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
                      : ((passes == 3 && env_int("WEALY_EPI_WARPS", 8) == 4 && env_int("WEALY_BLOCK_K", 64) == 64) ? 1 : 2);
   GemmShape sh;
   // top-k keeps <= 4 candidate lists per query (column chunks x epilogue warps per row)
-  fill_shape(sh, nq, nc, pq.d_pad, 64, topk > 0 ? (4 / halves) : (1 << 20));
+  fill_shape(sh, nq, nc, pq.d_pad, 64, topk > 0 ? (4 / halves) : (1 << 20), topk > 0 ? 0 : env_int("WEALY_TILES_PER_UNIT", 8));
   const int parts = sh.n_col_chunks * halves;
   const int cap = topk > 0 ? topk_capacity(topk) : 0;
 
@@ -495,10 +538,10 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
     const size_t slots = (size_t)parts * nq * cap;
     const size_t tneed = slots * 16 + (size_t)parts * nq * 4 + 1024;  // candidate lists + finalize staging
     if (tneed > p->topk_cap) {
-      if (p->topk_buf) CU_TRY(cudaFree(p->topk_buf));
+      dev_free(p->topk_buf, s);
       p->topk_buf = nullptr;
       p->topk_cap = 0;
-      CU_TRY(cudaMalloc(&p->topk_buf, tneed));
+      CU_TRY(dev_alloc((void**)&p->topk_buf, tneed, s));
       p->topk_cap = tneed;
     }
     ep.cand_val = reinterpret_cast<float*>(p->topk_buf);

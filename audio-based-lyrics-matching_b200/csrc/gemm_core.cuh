@@ -38,10 +38,13 @@ struct GemmShape {
   int tiles_per_chunk;  // column tiles per unit
   int n_col_chunks;     // ceil(n_col_tiles / tiles_per_chunk)
   int group_rows;       // row blocks per scheduling group (see decode_unit)
+  int* unit_counter;    // global work counter of this launch (zeroed by the host): dynamic unit scheduling
 };
 
-// Unit order.  Units are dealt round-robin to the persistent grid, so ~148 consecutive units run
-// together.  They are enumerated group by group: a group is `group_rows` row blocks x ALL column
+// Unit order.  Units are handed out in sequence from a global atomic counter (the TMA warp fetches the
+// next index and publishes it to the MMA and epilogue warps through a 2-deep shared-memory mailbox), so
+// ~148 consecutive units run together and CTAs cannot drift apart by more than one unit -- which is
+// what keeps the candidate tiles they share alive in L2.  Units are enumerated group by group: a group is `group_rows` row blocks x ALL column
 // chunks, chunk-major inside the group.  With group_rows = #SMs / #chunks the CTAs resident together
 // cover few row blocks (their query tiles, re-read once per column tile, are the L2 working set:
 // 37 x 512 KB instead of 148 x 512 KB at C2) while each chunk's candidate tiles are still shared by
@@ -112,7 +115,10 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* unit_full = tmem_empty + 2;
+  uint64_t* unit_empty = unit_full + 2;
+  int* unit_slot = reinterpret_cast<int*>(unit_empty + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(unit_slot + 2);
   uint8_t* scratch_base = bar_base + SM::kBarBytes;
 
   const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -132,6 +138,8 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], kEpiWarps);
+      ptx::mbar_init(&unit_full[a], 1);
+      ptx::mbar_init(&unit_empty[a], 1 + kEpiWarps);  // MMA thread + one lane per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -148,7 +156,17 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      int us = 0;
+      uint32_t uphase = 0;
+      while (true) {
+        // fetch the next unit and publish it to the MMA / epilogue warps
+        ptx::mbar_wait(&unit_empty[us], uphase ^ 1u);
+        int u = atomicAdd(shape.unit_counter, 1);
+        if (u >= n_units) u = -1;
+        unit_slot[us] = u;
+        ptx::mbar_arrive(&unit_full[us]);
+        if (++us == 2) { us = 0; uphase ^= 1u; }
+        if (u < 0) break;
         int chunk, rb;
         decode_unit(shape, u, chunk, rb);
         const int t0 = chunk * shape.tiles_per_chunk;
@@ -183,7 +201,14 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      int us = 0;
+      uint32_t uphase = 0;
+      while (true) {
+        ptx::mbar_wait(&unit_full[us], uphase);
+        const int u = unit_slot[us];
+        ptx::mbar_arrive(&unit_empty[us]);
+        if (++us == 2) { us = 0; uphase ^= 1u; }
+        if (u < 0) break;
         int chunk, rb_unused;
         decode_unit(shape, u, chunk, rb_unused);
         const int t0 = chunk * shape.tiles_per_chunk;
@@ -225,7 +250,15 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
     const int row_in_tile = quad * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    int us = 0;
+    uint32_t uphase = 0;
+    while (true) {
+      ptx::mbar_wait(&unit_full[us], uphase);
+      const int u = unit_slot[us];
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&unit_empty[us]);
+      if (++us == 2) { us = 0; uphase ^= 1u; }
+      if (u < 0) break;
       int chunk, rb;
       decode_unit(shape, u, chunk, rb);
       const int t0 = chunk * shape.tiles_per_chunk;
