@@ -467,8 +467,13 @@ extern "C" int wealy_eval_plan_last_sweep_ms(const wealy_eval_plan* p, float* ms
   return WEALY_OK;
 }
 
-// a row may gain up to 4 deferred chunks x 32 candidates between two compaction checks
-static int topk_capacity(int k) { return (int)align_up((size_t)k + 156, 32); }
+// Candidate-list capacity per (row, part).  A row may gain up to 4 deferred chunks x 32 candidates between two
+// compaction checks (k + 128 <= cap is required); the slack beyond that sets how often a list is compacted.
+static int topk_capacity(int k) {
+  size_t cap = align_up((size_t)(2 * k > k + 192 ? 2 * k : k + 192), 32);
+  if (cap > 1024) cap = 1024;
+  return (int)cap;
+}
 
 extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
                               int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,
@@ -478,7 +483,7 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
   if (!queries_z || !candidates_z || !aps || !r1s || !sums) return fail(WEALY_ERR_BAD_ARG, "null pointer");
   if (d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad embedding size %lld", (long long)d);
   if (passes != 1 && passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
-  if (topk < 0 || topk > 900) return fail(WEALY_ERR_UNSUPPORTED, "topk must be in [0, 900], got %d", topk);
+  if (topk < 0 || topk > 800) return fail(WEALY_ERR_UNSUPPORTED, "topk must be in [0, 800], got %d", topk);
   if (topk > 0 && (!topk_idx || !topk_sim)) return fail(WEALY_ERR_BAD_ARG, "topk outputs are null");
   const int64_t nq = p->nq, nc = p->nc;
   const bool same = (queries_z == candidates_z && nq == nc && ld_q == ld_c);
@@ -570,7 +575,7 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
     ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)nq, aps, r1s, sums);
     CU_TRY(cudaGetLastError());
     if (topk > 0) {
-      if (cap <= 256 && parts <= 4) {
+      if (parts * cap <= 32 * kFinPerLane) {
         float* stage_val = reinterpret_cast<float*>(ep.cand_cnt + (size_t)parts * nq);
         int* stage_idx = reinterpret_cast<int*>(stage_val + (size_t)parts * nq * cap);
         topk_finalize_select_kernel<<<(unsigned)ceil_div(nq * 32, 128), 128, 0, s>>>(

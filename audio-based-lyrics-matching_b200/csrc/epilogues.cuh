@@ -186,6 +186,12 @@ __device__ __forceinline__ float warp_select_topk(float* val, int* idx, int n, i
   return float_from_order_key(T);
 }
 
+// out-of-line variants for the long candidate lists of large k (keeps the sweep kernel's hot path lean)
+template <int kPerLane>
+__device__ __noinline__ float warp_select_topk_big(float* val, int* idx, int n, int k, int lane) {
+  return warp_select_topk<kPerLane>(val, idx, n, k, lane);
+}
+
 struct EvalParams {
   const float* lim;        // [nq] lowest relevant similarity of the query (+inf if none)
   const int* q_c;          // [nq] clique ids
@@ -317,41 +323,6 @@ struct EvalEpiT {
     return lo;
   }
 
-  // Warp-cooperative compaction of one row's candidate buffer down to its k best (generic O(n^2/32)
-  // fallback for k > 160; the common case uses warp_select_topk).  Returns the new k-th best value.
-  __device__ static __noinline__ float compact_row(float* val, int* idx, int n, int k, int lane) {
-    constexpr int kMaxPerLane = 32;  // supports cap <= 1024
-    __syncwarp();  // appends of the other lanes must be visible to the whole warp
-    float mv[kMaxPerLane];
-    int mi[kMaxPerLane], mr[kMaxPerLane];
-    int cntl = 0;
-    for (int e = lane; e < n; e += 32) {
-      const float ve = val[e];
-      int r = 0;
-      for (int f = 0; f < n; ++f) {
-        const float vf = val[f];
-        r += (vf > ve) || (vf == ve && f < e);
-      }
-      mv[cntl] = ve;
-      mi[cntl] = idx[e];
-      mr[cntl] = r;
-      ++cntl;
-    }
-    __syncwarp();
-    float kth = __int_as_float(0x7f800000);
-    for (int c = 0; c < cntl; ++c) {
-      if (mr[c] < k) {
-        val[mr[c]] = mv[c];
-        idx[mr[c]] = mi[c];
-        if (mr[c] == k - 1) kth = mv[c];
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
-    return kth;
-  }
-
   __device__ static __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -438,8 +409,9 @@ struct EvalEpiT {
       need &= need - 1;
       const long long cb = st.cbase + (long long)(src - lane) * p.cap;
       const int n = ncand[src];
-      const float kth = p.cap <= 256 ? warp_select_topk<8>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
-                                     : compact_row(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane);
+      const float kth = p.cap <= 256   ? warp_select_topk<8>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
+                        : p.cap <= 512 ? warp_select_topk_big<16>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
+                                       : warp_select_topk_big<32>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane);
       if (lane == src) {
         ncand[lane] = p.topk;
         st.tau = kth;

@@ -214,10 +214,10 @@ __global__ void __launch_bounds__(256) topk_finalize_kernel(const float* __restr
 }
 
 
-// K3 (fast path, k <= 160, <= 4 parts of <= 256 candidates): one warp per query gathers every part's
+// K3 (fast path: the <= 4 candidate lists of a query hold <= 1536 entries in total, i.e. k <= ~190): one warp per query gathers every part's
 // candidates into registers, selects the k best in O(n) (warp_select_topk), then orders the k
 // survivors by rank counting (k^2 / 32 steps) -- descending similarity, ties -> lower index.
-constexpr int kFinPerLane = 32;  // 4 parts x 256 candidates / 32 lanes
+constexpr int kFinPerLane = 48;  // up to 1536 gathered candidates (4 lists of 384)
 __global__ void __launch_bounds__(128) topk_finalize_select_kernel(const float* __restrict__ cand_val,
                                                                    const int* __restrict__ cand_idx,
                                                                    const int* __restrict__ cand_cnt, int parts, int nq,

@@ -115,6 +115,21 @@ def test_topk_matches_oracle():
     assert bool((idx != torch.arange(2500)[:, None]).all())                   # self never returned
 
 
+@pytest.mark.parametrize("k", [150, 300, 800])
+def test_topk_large_k(k):
+    # long candidate lists: the out-of-line selection variants and the generic finalize kernel
+    s = _synth().make_eval_set(3000, 128, seed=11)
+    aps, r1s, idx, sim = _gpu_eval(s["c"], s["i"], s["z"], topk=k)
+    _, _, idx_o, sim_o = oev.evaluate_argsort(s["c"][:200], s["i"][:200], s["z"][:200], s["c"], s["i"], s["z"], topk=k)
+    assert (sim[:200] - sim_o).abs().max() <= 4e-6
+    ok = torch.ones_like(idx_o, dtype=torch.bool)
+    ok[:, 1:] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    ok[:, :-1] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    assert torch.equal(idx[:200][ok], idx_o[ok])
+    with pytest.raises(NotImplementedError):
+        _gpu_eval(s["c"], s["i"], s["z"], topk=801)
+
+
 def test_topk_larger_than_corpus_and_k1():
     s = _synth().make_eval_set(40, 16, seed=6)
     aps, r1s, idx, sim = _gpu_eval(s["c"], s["i"], s["z"], topk=100)
