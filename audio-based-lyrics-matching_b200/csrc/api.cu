@@ -218,12 +218,14 @@ static void fill_shape(GemmShape& sh, int64_t m, int64_t n, int64_t d_pad, int b
   if (gr < 1) gr = 1;
   if (gr > sh.n_row_blocks) gr = sh.n_row_blocks > 0 ? sh.n_row_blocks : 1;
   sh.group_rows = gr;
+  sh.sym = 0;
+  sh.unit_counter = nullptr;
 }
 
-template <class Epi, int kPasses, int kBlockK, int kEpiWarps>
+template <class Epi, int kPasses, int kBlockK, int kEpiWarps, int kMaxStages = 8>
 static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, const typename Epi::Params& ep,
                          cudaStream_t s) {
-  using SM = GemmSmem<kPasses, kBlockK>;
+  using SM = GemmSmem<kPasses, kBlockK, kMaxStages>;
   GemmTmaps maps;
   memset(&maps, 0, sizeof(maps));
   W_TRY(make_plane_tmap(&maps.a_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK));
@@ -235,7 +237,7 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
     maps.a_lo = maps.a_hi;
     maps.b_lo = maps.b_hi;
   }
-  auto kern = gemm_kernel<Epi, kPasses, kBlockK, kEpiWarps>;
+  auto kern = gemm_kernel<Epi, kPasses, kBlockK, kEpiWarps, kMaxStages>;
   constexpr int kSmemBytes = SM::total(kEpiWarps, Epi::kWarpScratchBytes, Epi::kCtaScratchBytes);
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -559,7 +561,19 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
     CU_TRY(cudaEventCreate(&p->ev1));
   }
   CU_TRY(cudaEventRecord(p->ev0, s));
-  if (halves == 4) {
+  // Symmetric all-vs-all: queries ARE the candidates (same ids, same embeddings), no top-k.  Only the tiles
+  // that reach above the diagonal are contracted (half the tensor work); every element scores both its row
+  // query and its column query.  Needs a second per-CTA threshold cache -> 3-stage ring of 48 KB stages.
+  const bool sym = same && p->same_ids && topk == 0 && halves == 2 && env_int("WEALY_SYM", 1) != 0;
+  if (sym) {
+    sh.sym = 1;
+    if (passes == 3) {
+      sh.k_blocks = (int)(pq.d_pad / 32);
+      W_TRY((launch_gemm_t<EvalEpiSym, 3, 32, 8, 3>(pq, pc, sh, ep, s)));
+    } else {
+      W_TRY((launch_gemm_t<EvalEpiSym, 1, 64, 8, 3>(pq, pc, sh, ep, s)));
+    }
+  } else if (halves == 4) {
     // 16 epilogue warps (4 per TMEM lane quadrant): the slow path is latency bound, more warps hide it
     if (passes == 3) W_TRY((launch_gemm_t<EvalEpi16, 3, 64, 16>(pq, pc, sh, ep, s)));
     else W_TRY((launch_gemm_t<EvalEpi16, 1, 64, 16>(pq, pc, sh, ep, s)));

@@ -39,7 +39,15 @@ struct GemmShape {
   int n_col_chunks;     // ceil(n_col_tiles / tiles_per_chunk)
   int group_rows;       // row blocks per scheduling group (see decode_unit)
   int* unit_counter;    // global work counter of this launch (zeroed by the host): dynamic unit scheduling
+  int sym;              // symmetric all-vs-all: only tiles that reach above the diagonal are computed
 };
+
+// First column tile a row block needs in symmetric mode: tile t holds columns [256 t, 256 t + 256) and row
+// block rb rows [128 rb, 128 rb + 128); it contains an element with col > row iff t >= rb / 2.
+__device__ __forceinline__ int first_tile(const GemmShape& sh, int rb, int t0) {
+  static_assert(kTileN == 2 * kTileM, "symmetric tile range assumes 256-wide column tiles over 128-row blocks");
+  return sh.sym ? max(t0, rb >> 1) : t0;
+}
 
 // Unit order.  Units are handed out in sequence from a global atomic counter (the TMA warp fetches the
 // next index and publishes it to the MMA and epilogue warps through a 2-deep shared-memory mailbox), so
@@ -58,7 +66,7 @@ __device__ __forceinline__ void decode_unit(const GemmShape& sh, int u, int& chu
   rb = g * sh.group_rows + (within - chunk * rows_here);
 }
 
-template <int kPasses, int kBlockK>
+template <int kPasses, int kBlockK, int kMaxStages = 8>
 struct GemmSmem {
   static constexpr int kSwizzle = kBlockK * 2;  // bytes per smem row == swizzle span
   static constexpr int kABytes = kTileM * kBlockK * 2;
@@ -66,7 +74,7 @@ struct GemmSmem {
   static constexpr int kPlanes = kPasses == 3 ? 2 : 1;
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kBudget = 227 * 1024 - 2048 - 30 * 1024;  // alignment slack + barriers + epilogue scratch
-  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  static constexpr int kStages = (kBudget / kStageBytes) > kMaxStages ? kMaxStages : (kBudget / kStageBytes);
   static constexpr int kBarBytes = 256;
   static constexpr int kCore = kStages * kStageBytes + kBarBytes;  // + per-warp epilogue scratch + 1024 align slack
   static_assert(kStages >= 2, "need at least a double-buffered ring");
@@ -94,15 +102,16 @@ struct EpiCtx {
 //   static void row_begin(const Params&, RowState&, int row, int part, const GemmShape&, const EpiCtx&);
 //   static void chunk32(const Params&, RowState&, int row, int col0, const uint32_t (&acc)[32], const GemmShape&,
 //                       const EpiCtx&);
+//   static void tile_begin(const Params&, RowState&, const GemmShape&, const EpiCtx&, int tile);  before the accumulator wait
 //   static void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&);   after the accumulator is released
 //   static void row_end(const Params&, RowState&, int row, int part, const GemmShape&, const EpiCtx&);
 // `row` is the global query row owned by the thread, `part` identifies the partial result slot
 // (column chunk x epilogue half) when a row is split over several units / warps.
 
-template <class Epi, int kPasses, int kBlockK, int kEpiWarps>
+template <class Epi, int kPasses, int kBlockK, int kEpiWarps, int kMaxStages = 8>
 __global__ void __launch_bounds__(64 + kEpiWarps * 32, 1)
 gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, const typename Epi::Params ep) {
-  using SM = GemmSmem<kPasses, kBlockK>;
+  using SM = GemmSmem<kPasses, kBlockK, kMaxStages>;
   constexpr int kStages = SM::kStages;
   constexpr int kHalves = kEpiWarps / 4;  // epilogue warps per TMEM lane quadrant
   static_assert(kEpiWarps == 4 || kEpiWarps == 8 || kEpiWarps == 16, "4, 8 or 16 epilogue warps");
@@ -169,8 +178,8 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
         if (u < 0) break;
         int chunk, rb;
         decode_unit(shape, u, chunk, rb);
-        const int t0 = chunk * shape.tiles_per_chunk;
-        const int t1 = min(t0 + shape.tiles_per_chunk, shape.n_col_tiles);
+        const int t1 = min((chunk + 1) * shape.tiles_per_chunk, shape.n_col_tiles);
+        const int t0 = first_tile(shape, rb, chunk * shape.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < shape.k_blocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -209,10 +218,10 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
         ptx::mbar_arrive(&unit_empty[us]);
         if (++us == 2) { us = 0; uphase ^= 1u; }
         if (u < 0) break;
-        int chunk, rb_unused;
-        decode_unit(shape, u, chunk, rb_unused);
-        const int t0 = chunk * shape.tiles_per_chunk;
-        const int t1 = min(t0 + shape.tiles_per_chunk, shape.n_col_tiles);
+        int chunk, rb;
+        decode_unit(shape, u, chunk, rb);
+        const int t1 = min((chunk + 1) * shape.tiles_per_chunk, shape.n_col_tiles);
+        const int t0 = first_tile(shape, rb, chunk * shape.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
           ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
           ptx::tc_fence_after_sync();
@@ -261,8 +270,9 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       if (u < 0) break;
       int chunk, rb;
       decode_unit(shape, u, chunk, rb);
-      const int t0 = chunk * shape.tiles_per_chunk;
-      const int t1 = min(t0 + shape.tiles_per_chunk, shape.n_col_tiles);
+      const int t1 = min((chunk + 1) * shape.tiles_per_chunk, shape.n_col_tiles);
+      const int t0 = first_tile(shape, rb, chunk * shape.tiles_per_chunk);
+      if (t0 >= t1) continue;  // symmetric mode: the whole unit lies below the diagonal
       const int row = rb * kTileM + row_in_tile;
       const int part = chunk * kHalves + half;
       typename Epi::RowState rs;
@@ -276,6 +286,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       ctx.col_step = kHalves * kChunkCols;
       Epi::row_begin(ep, rs, row, part, shape, ctx);
       for (int t = t0; t < t1; ++t) {
+        Epi::tile_begin(ep, rs, shape, ctx, t);
         ptx::mbar_wait(&tmem_full[acc], acc_phase);
         ptx::tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN);

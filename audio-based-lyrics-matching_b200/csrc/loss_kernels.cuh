@@ -112,6 +112,7 @@ struct LossStatsEpi {
     }
   }
 
+  __device__ static __forceinline__ void tile_begin(const Params&, RowState&, const GemmShape&, const EpiCtx&, int) {}
   __device__ static __forceinline__ void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&) {}
   __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part, const GemmShape&, const EpiCtx&) {
     if (!st.valid) return;
@@ -186,6 +187,7 @@ struct LossWEpi {
     }
   }
 
+  __device__ static __forceinline__ void tile_begin(const Params&, RowState&, const GemmShape&, const EpiCtx&, int) {}
   __device__ static __forceinline__ void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&) {}
   __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, const EpiCtx&) {}
 };
