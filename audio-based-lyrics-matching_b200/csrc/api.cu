@@ -219,6 +219,8 @@ static void fill_shape(GemmShape& sh, int64_t m, int64_t n, int64_t d_pad, int b
   if (gr > sh.n_row_blocks) gr = sh.n_row_blocks > 0 ? sh.n_row_blocks : 1;
   sh.group_rows = gr;
   sh.sym = 0;
+  sh.rb_stride = 1;
+  sh.rb_offset = 0;
   sh.unit_counter = nullptr;
 }
 
@@ -477,12 +479,17 @@ static int topk_capacity(int k) {
   return (int)cap;
 }
 
-extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
-                              int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,
-                              float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, void* stream) {
+// shard_world > 1: symmetric sweep restricted to the row blocks rb = shard_rank (mod shard_world); the rank
+// counts are left in the plan's histogram for the caller to sum over ranks (finish == false).
+static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
+                         int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,
+                         float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, int shard_rank,
+                         int shard_world, bool finish, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (!p) return fail(WEALY_ERR_BAD_ARG, "null plan");
-  if (!queries_z || !candidates_z || !aps || !r1s || !sums) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (!queries_z || !candidates_z) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (finish && (!aps || !r1s || !sums)) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(WEALY_ERR_BAD_ARG, "bad shard %d/%d", shard_rank, shard_world);
   if (d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad embedding size %lld", (long long)d);
   if (passes != 1 && passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
   if (topk < 0 || topk > 800) return fail(WEALY_ERR_UNSUPPORTED, "topk must be in [0, 800], got %d", topk);
@@ -516,7 +523,7 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
     CU_TRY(cudaGetLastError());
   }
   CU_TRY(cudaMemsetAsync(p->hist, 0, (size_t)(p->total_pairs > 0 ? p->total_pairs : 1) * 4, s));
-  CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
+  if (finish) CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
 
   const int epi_warps = env_int("WEALY_EVAL_EPI_WARPS", 8);  // 16 measured no faster (the sweep is not latency-starved)
   const int halves = epi_warps == 16 ? 4
@@ -564,7 +571,15 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
   // Symmetric all-vs-all: queries ARE the candidates (same ids, same embeddings), no top-k.  Only the tiles
   // that reach above the diagonal are contracted (half the tensor work); every element scores both its row
   // query and its column query.  Needs a second per-CTA threshold cache -> 3-stage ring of 48 KB stages.
-  const bool sym = same && p->same_ids && topk == 0 && halves == 2 && env_int("WEALY_SYM", 1) != 0;
+  const bool sym = same && p->same_ids && topk == 0 && halves == 2 && (shard_world > 1 || env_int("WEALY_SYM", 1) != 0);
+  if (shard_world > 1) {
+    if (!sym) return fail(WEALY_ERR_BAD_ARG, "a sharded sweep needs queries == candidates (ids and embeddings) and no top-k");
+    const int total_rb = sh.n_row_blocks;
+    sh.rb_stride = shard_world;
+    sh.rb_offset = shard_rank;
+    sh.n_row_blocks = shard_rank < total_rb ? (int)ceil_div(total_rb - shard_rank, shard_world) : 0;
+    if (sh.group_rows > sh.n_row_blocks) sh.group_rows = sh.n_row_blocks > 0 ? sh.n_row_blocks : 1;
+  }
   if (sym) {
     sh.sym = 1;
     if (passes == 3) {
@@ -583,7 +598,7 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
   CU_TRY(cudaEventRecord(p->ev1, s));
   p->timed = true;
 
-  {
+  if (finish) {
     const int threads = 256;
     const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
     ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)nq, aps, r1s, sums);
@@ -602,6 +617,41 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
       CU_TRY(cudaGetLastError());
     }
   }
+  return WEALY_OK;
+}
+
+extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
+                              int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,
+                              float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, void* stream) {
+  return eval_run_impl(p, queries_z, ld_q, candidates_z, ld_c, d, dtype, eps, passes, topk, aps, r1s, sums, topk_idx,
+                       topk_sim, 0, 1, true, stream);
+}
+
+// multi-GPU all-vs-all: every rank sweeps its share of the row blocks of the SAME symmetric problem ...
+extern "C" int wealy_eval_sweep_shard(wealy_eval_plan* p, const void* z, int64_t ld, int64_t d, int dtype, float eps,
+                                      int passes, int shard_rank, int shard_world, void* stream) {
+  return eval_run_impl(p, z, ld, z, ld, d, dtype, eps, passes, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                       shard_rank, shard_world, false, stream);
+}
+
+// ... the per-(query, relevant item) rank counts are then summed over the ranks by the caller (an all-reduce of
+// `count` uint32 values starting at `counts`) ...
+extern "C" int wealy_eval_plan_counts(const wealy_eval_plan* p, void** counts, int64_t* count) {
+  if (!p || !counts || !count) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  *counts = p->hist;
+  *count = p->total_pairs > 0 ? p->total_pairs : 1;
+  return WEALY_OK;
+}
+
+// ... and turned into AP / R1 / sums on every rank.
+extern "C" int wealy_eval_finish(wealy_eval_plan* p, float* aps, float* r1s, double* sums, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!p || !aps || !r1s || !sums) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
+  const int threads = 256;
+  const unsigned blocks = (unsigned)ceil_div(p->nq * 32, threads);
+  ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)p->nq, aps, r1s, sums);
+  CU_TRY(cudaGetLastError());
   return WEALY_OK;
 }
 

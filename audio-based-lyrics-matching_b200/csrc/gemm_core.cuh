@@ -40,6 +40,8 @@ struct GemmShape {
   int group_rows;       // row blocks per scheduling group (see decode_unit)
   int* unit_counter;    // global work counter of this launch (zeroed by the host): dynamic unit scheduling
   int sym;              // symmetric all-vs-all: only tiles that reach above the diagonal are computed
+  int rb_stride;        // multi-GPU symmetric sweep: this launch owns row blocks rb_offset + k * rb_stride
+  int rb_offset;        //   (n_row_blocks counts the owned ones)
 };
 
 // First column tile a row block needs in symmetric mode: tile t holds columns [256 t, 256 t + 256) and row
@@ -63,7 +65,7 @@ __device__ __forceinline__ void decode_unit(const GemmShape& sh, int u, int& chu
   const int within = u - g * per_group;
   const int rows_here = min(sh.group_rows, sh.n_row_blocks - g * sh.group_rows);
   chunk = within / rows_here;
-  rb = g * sh.group_rows + (within - chunk * rows_here);
+  rb = (g * sh.group_rows + (within - chunk * rows_here)) * sh.rb_stride + sh.rb_offset;
 }
 
 template <int kPasses, int kBlockK, int kMaxStages = 8>

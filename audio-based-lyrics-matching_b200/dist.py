@@ -1,4 +1,15 @@
-"""Multi-GPU evaluation: queries partitioned over ranks, corpus replicated.
+"""Multi-GPU evaluation: one process per GPU, torch.distributed (NCCL over NVLink / NVSwitch on
+the GPU box; gloo in the CPU tests of the merge logic).
+
+Two schemes:
+
+* all-vs-all (queries ARE the corpus, the headline case) -- `evaluate_all_vs_all`: every rank holds the whole
+  corpus and sweeps the row blocks rb = rank (mod world) of the SAME symmetric problem (only tiles above the
+  diagonal, each element scoring its row and its column query).  A rank therefore holds partial rank counts for
+  ALL queries; the one real exchange step of the path is an all-reduce (SUM) of those int32 counters -- the
+  "rank counts merged over NCCL" of the north star -- after which every rank owns the complete AP / R1.
+* general queries vs corpus -- `evaluate_sharded`: queries partitioned over ranks, corpus replicated
+  (no data-path collective; results merged as below).
 
 Queries are independent units, so the data path needs no collective: rank r scores the
 contiguous query slice shard_range(Nq, r, world) against the whole corpus with the single-GPU
@@ -40,6 +51,26 @@ def gather_rows(local, n_total, group=None):
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=None):
+    """All-vs-all evaluation of one set (clique ids c, version ids i, embeddings z) over all ranks of `group`.
+    Every rank passes the full tensors.  -> dict(map, mr1, count, aps, r1s, plan); identical on every rank."""
+    from .evaluation import EvalPlan, mean_metrics
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    if plan is None:
+        plan = EvalPlan(c, i, c, i)
+    if world == 1:
+        res = plan.run(z, z, eps=eps, precision=precision)
+    else:
+        plan.sweep_shard(z, rank, world, eps=eps, precision=precision)
+        counts = plan.counts_tensor()
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)   # the path's one exchange step
+        res = plan.finish()
+    m, r1 = mean_metrics(res["sums"])
+    return {"map": m, "mr1": r1, "count": int(res["sums"][2].item()), "aps": res["aps"], "r1s": res["r1s"], "plan": plan}
 
 
 def evaluate_sharded(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z, *, topk=None,

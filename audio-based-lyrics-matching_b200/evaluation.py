@@ -67,6 +67,40 @@ class EvalPlan:
         except Exception:
             pass
 
+    # ---- multi-GPU all-vs-all: symmetric sweep sharded by row blocks, rank counts summed over ranks ----
+    def sweep_shard(self, z, shard_rank, shard_world, *, eps=1e-6, precision=None):
+        """Sweep this rank's share (row blocks = shard_rank mod shard_world) of the symmetric all-vs-all
+        problem; the plan must have been built with queries == candidates."""
+        z = _to_device(z, self.device)
+        assert z.ndim == 2 and z.shape[0] == self.nq == self.nc
+        if z.stride(1) != 1:
+            z = z.contiguous()
+        with torch.cuda.device(self.device):
+            N.check(N.lib.wealy_eval_sweep_shard(
+                self._handle, z.data_ptr(), z.stride(0), z.shape[1], N.dtype_code(z.dtype), float(eps),
+                passes_of(precision), int(shard_rank), int(shard_world), N.stream_ptr(self.device)))
+        self._keepalive = z
+
+    def counts_tensor(self):
+        """int32 view (no copy) of the plan's per-(query, relevant item) rank counters: the buffer a
+        multi-GPU run all-reduces between sweep_shard() and finish()."""
+        ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+        N.check(N.lib.wealy_eval_plan_counts(self._handle, ctypes.byref(ptr), ctypes.byref(n)))
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<i4", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(_Dev(), device=self.device)
+
+    def finish(self):
+        """Rank counts -> dict(aps, r1s, sums) for ALL queries."""
+        aps = torch.empty(self.nq, dtype=torch.float32, device=self.device)
+        r1s = torch.empty(self.nq, dtype=torch.float32, device=self.device)
+        sums = torch.empty(3, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.wealy_eval_finish(self._handle, aps.data_ptr(), r1s.data_ptr(), sums.data_ptr(),
+                                            N.stream_ptr(self.device)))
+        return {"aps": aps, "r1s": r1s, "sums": sums}
+
     def last_sweep_ms(self):
         """Device time of the fused similarity+ranking kernel of the last run (CUDA events)."""
         ms = ctypes.c_float()

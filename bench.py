@@ -12,8 +12,10 @@ mask / rank-count epilogue -> AP reduce -> MAP) of the workload:
   N = 1 : BASELINE.json configs[1] -- Discogs-VI-YT-test-shaped all-vs-all, 100 000 x 1024-d fp32
           synthetic embeddings, clique sizes bootstrapped from the shipped SHS100K-TEST split.
   N > 1 : the same all-vs-all grown so that every GPU keeps 1e10 pairs (weak scaling):
-          N_total = 100 000 * sqrt(N) tracks, queries partitioned over ranks, corpus replicated,
-          no data-path collective; one all-reduce of {sum AP, sum R1, count} merges MAP / MR1.
+          N_total = 100 000 * sqrt(N) tracks, corpus replicated; every rank sweeps the row blocks
+          rank (mod N) of the symmetric problem and the per-(query, relevant item) rank counters are
+          summed with ONE NCCL all-reduce per step (the path's only exchange), after which every
+          rank holds the complete AP / R1.
 
 `value`  : whole-job Gpairs/s with embeddings and ids already resident in HBM (id-only plan built
            once, outside the timed region).
@@ -87,7 +89,7 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(k)
                 except Exception:
                     pass
-                self._halt.wait(0.1)
+                self._halt.wait(0.02)
         except Exception:
             self.ok = False
 
@@ -190,8 +192,7 @@ def run_gpu_arm(args):
     lo, hi = wd.shard_range(n_total, rank, world)
     s = synth.make_eval_set(n_total, DIM, seed=0, device=dev, md5_ids=False)
     z, c, i = s["z"], s["c"], s["i"]
-    zq, cq, iq = (z, c, i) if world == 1 else (z[lo:hi], c[lo:hi], i[lo:hi])
-    nq = hi - lo
+    nq = n_total if world == 1 else (hi - lo)          # queries whose row blocks this rank sweeps (about)
     pairs_total = float(n_total) * float(n_total)
 
     def sync_all():
@@ -201,16 +202,14 @@ def run_gpu_arm(args):
             torch.cuda.synchronize(dev)
 
     # ---- value: inputs resident in HBM, plan built once
-    plan = we.EvalPlan(cq, iq, c, i, device=dev)
+    plan = we.EvalPlan(c, i, c, i, device=dev)
 
     def step_resident():
-        res = plan.run(zq, z, precision=args.precision)
-        if world > 1:
-            sums = res["sums"].clone()
-            dist.all_reduce(sums)
-        else:
-            sums = res["sums"]
-        return sums
+        if world == 1:
+            return plan.run(z, z, precision=args.precision)["sums"]
+        plan.sweep_shard(z, rank, world, precision=args.precision)
+        dist.all_reduce(plan.counts_tensor())          # int32 rank counters, SUM over ranks
+        return plan.finish()["sums"]
 
     for _ in range(args.warmup):
         step_resident()
@@ -235,26 +234,24 @@ def run_gpu_arm(args):
     gpu_map, gpu_mr1 = float(s_host[0] / s_host[2]), float(s_host[1] / s_host[2])
 
     # ---- e2e: public API with HOST pinned buffers, copies + plan build + result read every step
-    z_h = zq.cpu().pin_memory()
-    c_h, i_h = cq.cpu().pin_memory(), iq.cpu().pin_memory()
-    if world == 1:
-        cz_h, cc_h, ci_h = z_h, c_h, i_h
-    else:
-        cz_h, cc_h, ci_h = z.cpu().pin_memory(), c.cpu().pin_memory(), i.cpu().pin_memory()
-    h2d = z_h.numel() * 4 + c_h.numel() * 8 + i_h.numel() * 8
-    if world > 1:
-        h2d += cz_h.numel() * 4 + cc_h.numel() * 8 + ci_h.numel() * 8
-    aps_h = torch.empty(nq, dtype=torch.float32).pin_memory()
-    r1s_h = torch.empty(nq, dtype=torch.float32).pin_memory()
-    d2h = 2 * nq * 4
+    z_h, c_h, i_h = z.cpu().pin_memory(), c.cpu().pin_memory(), i.cpu().pin_memory()
+    h2d = z_h.numel() * 4 + c_h.numel() * 8 + i_h.numel() * 8      # every rank uploads the (replicated) corpus
+    aps_h = torch.empty(n_total, dtype=torch.float32).pin_memory()
+    r1s_h = torch.empty(n_total, dtype=torch.float32).pin_memory()
+    d2h = 2 * n_total * 4
 
     def step_e2e():
-        # at 1 GPU queries and candidates are the same host tensors (copied once); at N > 1 every rank
-        # uploads its query slice and the replicated corpus
-        aps, r1s = we.evaluate(c_h, i_h, z_h, cc_h, ci_h, cz_h, precision=args.precision)
+        # public API, host tensors in, host tensors out: upload, id plan, evaluation, read-back every step
+        if world == 1:
+            aps, r1s = we.evaluate(c_h, i_h, z_h, c_h, i_h, z_h, precision=args.precision)
+        else:
+            out = wd.evaluate_all_vs_all(c_h, i_h, z_h, precision=args.precision)
+            aps, r1s = out["aps"], out["r1s"]
         aps_h.copy_(aps, non_blocking=True)
         r1s_h.copy_(r1s, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
+        if world > 1:
+            out["plan"].close()
 
     e2e_steps = max(2, min(args.steps, 5))
     step_e2e()
@@ -281,8 +278,14 @@ def run_gpu_arm(args):
     # ---- roofline of the dominant kernel (fused sweep), measured live with CUDA events on its stream
     peaks = load_peaks()
     passes = 3 if args.precision == "fp16x3" else 1
-    algo_flops = 2.0 * nq * n_total * DIM                       # 2*D flop per pair
+    # algorithmic work of this rank's launch: its share of the N_total^2 pairs, 2*D flop each
+    algo_flops = 2.0 * (float(n_total) * n_total / world) * DIM
     achieved = algo_flops / (last_sweep_ms * 1e-3) / 1e12
+    # tensor-core work actually issued: the symmetric sweep contracts only the 128 x 256 tiles that reach above
+    # the diagonal (row block rb needs column tiles >= rb / 2), times the passes of the precision mode
+    n_rb, n_ct = -(-n_total // 128), -(-n_total // 256)
+    tiles = sum(max(0, n_ct - rb // 2) for rb in range(rank, n_rb, world))
+    executed = 2.0 * 128 * 256 * DIM * tiles * passes / (last_sweep_ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -292,16 +295,17 @@ def run_gpu_arm(args):
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "gemm_kernel<EvalEpi> (tcgen05 similarity + mask + rank-count epilogue)",
+        "kernel": "gemm_kernel<EvalEpiSym> (symmetric tcgen05 similarity sweep + mask + rank-count epilogue)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": traffic,
         "peak_kind": f"{peaks['_source']} dense bf16/fp16 cuBLAS, sustained (kernel timed inside a long step); "
                      f"burst = {peaks['bf16_tflops']}",
         "kernel_ms": last_sweep_ms,
-        "executed_tflops": achieved * passes,
-        "frac_executed": achieved * passes / peak,
-        "note": "achieved = algorithmic 2*Nq*Nc*D flops / kernel time; the fp16x3 parity mode executes 3x "
-                "that on the tensor cores (hi*hi + hi*lo + lo*hi), reported as executed_tflops",
+        "executed_tflops": executed,
+        "frac_executed": executed / peak,
+        "note": "achieved = algorithmic flops (2*D per scored pair, both directions of the symmetric sweep) / "
+                "kernel time; executed_tflops = tensor-core work issued: half the tiles (symmetry) x 3 passes in "
+                "the fp16x3 parity mode (hi*hi + hi*lo + lo*hi)",
     }
 
     # ---- CPU baseline (oracle port) on a bounded sample of the same workload, rank 0, N = 1 only
@@ -316,7 +320,7 @@ def run_gpu_arm(args):
         cpu = {"value": nqs * n_total / sec / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"first {nqs} queries x {n_total} candidates in {sec:.1f} s: torch CPU matmul cosine "
                          f"similarity + per-query argsort AP/R1 (oracle/evaluator.py)"}
-        res = plan.run(zq, z, precision=args.precision)
+        res = plan.run(z, z, precision=args.precision)
         aps_g = res["aps"][:nqs].double().cpu()
         r1_g = res["r1s"][:nqs].double().cpu()
         parity = {"sample_queries": nqs,
@@ -335,15 +339,18 @@ def run_gpu_arm(args):
                         f"fp32 embeddings (BASELINE.json configs[1] shape at 1 GPU; N_total = 100000*sqrt(n_gpus), "
                         f"SHS100K-TEST clique-size bootstrap)",
             "queries_per_gpu": nq, "candidates": n_total, "pairs_per_step": pairs_total,
-            "parallelism": f"queries partitioned over {world} rank(s), corpus replicated, all-reduce of 3 doubles",
+            "parallelism": ("single GPU" if world == 1 else
+                            f"row blocks of the symmetric sweep dealt round-robin to {world} ranks, corpus replicated, "
+                            f"one NCCL all-reduce of the int32 rank counters per step"),
             "precision": args.precision,
             "l2": "operand planes %.0f MB per step >> 126 MB L2 (no flush needed)" % (n_total * DIM * 2 * (2 if passes == 3 else 1) / 1e6),
             "map": gpu_map, "mr1": gpu_mr1,
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms, "api": "wealy_b200.evaluation.evaluate (host pinned tensors in, host out)"},
-        "gpu_launches": 4 * args.steps,
+                "ms_per_step": e2e_ms, "api": ("wealy_b200.evaluation.evaluate" if world == 1 else "wealy_b200.dist.evaluate_all_vs_all")
+                       + " (host pinned tensors in, host out)"},
+        "gpu_launches": 4 * args.steps,   # prep, pos_thresholds, fused sweep, ap_reduce per step
         "roofline": roofline,
     }
     if cpu is not None:

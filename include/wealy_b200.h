@@ -90,6 +90,15 @@ int wealy_eval_plan_info(const wealy_eval_plan* plan, int64_t* total_pairs, int6
 int wealy_eval_run(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, const void* candidates_z, int64_t ld_c,
                    int64_t d, int dtype, float eps, int passes, int topk, float* aps, float* r1s, double* sums,
                    int64_t* topk_idx, float* topk_sim, void* stream);
+/* Multi-GPU all-vs-all (queries == candidates, no top-k).  Every rank holds the whole corpus and calls
+ * wealy_eval_sweep_shard with its (shard_rank, shard_world): the symmetric sweep is restricted to the row blocks
+ * rb = shard_rank (mod shard_world) and leaves this rank's share of the rank counts in the plan.  The caller
+ * then sums the `count` uint32 values at `counts` over the ranks (one NCCL all-reduce) and calls
+ * wealy_eval_finish, which yields the complete per-query AP / R1 / sums on every rank.                */
+int wealy_eval_sweep_shard(wealy_eval_plan* plan, const void* z, int64_t ld, int64_t d, int dtype, float eps,
+                           int passes, int shard_rank, int shard_world, void* stream);
+int wealy_eval_plan_counts(const wealy_eval_plan* plan, void** counts, int64_t* count);
+int wealy_eval_finish(wealy_eval_plan* plan, float* aps, float* r1s, double* sums, void* stream);
 /* device time (CUDA events on the run's stream) of the fused similarity+ranking sweep of the last
  * wealy_eval_run on this plan; blocks until that sweep has finished.                           */
 int wealy_eval_plan_last_sweep_ms(const wealy_eval_plan* plan, float* ms);

@@ -196,6 +196,33 @@ def test_counts_beyond_16_bits_and_topk_consistency():
     assert torch.equal(r1s[:nq].double(), r1_o)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_symmetric_sweep_emulated_on_one_gpu(world):
+    """The multi-GPU all-vs-all path: every rank sweeps the row blocks rank (mod world) of the symmetric
+    problem, the rank counters are summed (here by hand instead of the NCCL all-reduce), finish() yields the
+    complete result.  The ranks are emulated one after the other on a single GPU."""
+    s = _synth().make_eval_set(1700, 96, seed=13)
+    we = _we()
+    c, i, z = s["c"].cuda(), s["i"].cuda(), s["z"].cuda()
+    ref = we.EvalPlan(c, i, c, i).run(z, z)
+    total = None
+    plans = []
+    for r in range(world):
+        pl = we.EvalPlan(c, i, c, i)
+        pl.sweep_shard(z, r, world)
+        cnt = pl.counts_tensor()
+        assert cnt.dtype == torch.int32 and cnt.numel() == max(pl.total_pairs, 1)
+        total = cnt.clone() if total is None else total + cnt
+        plans.append(pl)
+    plans[0].counts_tensor().copy_(total)
+    out = plans[0].finish()
+    torch.cuda.synchronize()
+    assert torch.equal(out["aps"], ref["aps"]) and torch.equal(out["r1s"], ref["r1s"])
+    assert torch.allclose(out["sums"], ref["sums"], rtol=1e-9)
+    with pytest.raises(AssertionError):
+        we.EvalPlan(c[:100], i[:100], c, i).sweep_shard(z, 0, 2)      # needs queries == candidates
+
+
 def test_plan_reuse_and_half_precision_inputs():
     s = _synth().make_eval_set(1200, 128, seed=9)
     we = _we()
