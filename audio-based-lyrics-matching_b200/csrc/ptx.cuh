@@ -78,8 +78,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  int polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > WEALY_DEADLOCK_CYCLES) {
+    // a warp that keeps polling steals issue slots from the warps it is waiting for: back off after a few
+    // tries (the wake-up granularity this adds is far below one pipeline stage)
+    if (++polls > 4) __nanosleep(polls > 64 ? 256 : 32);
+    if ((polls & 63) == 0 && clock64() - t0 > WEALY_DEADLOCK_CYCLES) {
       printf("wealy: mbarrier deadlock block=%d thread=%d bar=0x%x parity=%u\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
