@@ -1,21 +1,36 @@
-"""In-tree build of lib/libwealy_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+"""In-tree build of lib/libwealy_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+
+Staleness is decided by a content hash of the sources (stored next to the library), not by mtimes:
+the library travels to the GPU box inside a snapshot whose timestamps are not preserved."""
+import hashlib
 import os
 import subprocess
 import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(PKG, "csrc")
+HDR = os.path.join(PKG, "..", "include", "wealy_b200.h")
 OUT = os.path.join(PKG, "lib", "libwealy_b200.so")
+STAMP = OUT + ".srchash"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 
 
+def source_hash():
+    h = hashlib.sha256()
+    for path in sorted(os.path.join(SRC, f) for f in os.listdir(SRC)) + [HDR]:
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.isfile(OUT):
+    if not (os.path.isfile(OUT) and os.path.isfile(STAMP)):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(PKG, "..", "include", "wealy_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -30,6 +45,8 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libwealy_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return OUT
 
 
