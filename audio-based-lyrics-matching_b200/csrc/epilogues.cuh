@@ -360,7 +360,7 @@ struct EvalEpiT {
 
   // Process the queue range [begin, end): 32 elements per round, every lane busy.  cc / ci / colok are the
   // ids and validity of this lane's column in the chunk the range came from; col0 its first column.
-  __device__ static __forceinline__ void process_range(const Params& p, RowState& st, const EpiCtx& ctx, int begin,
+  __device__ static __forceinline__ void process_range_single(const Params& p, RowState& st, const EpiCtx& ctx, int begin,
                                                        int end, int cc, int ci, int colok, int col0, int lane) {
     constexpr unsigned kFull = 0xffffffffu;
     const float* qv = q_val(ctx);
@@ -446,6 +446,149 @@ struct EvalEpiT {
     }
   }
 
+  // One queued element as seen by the lane that processes it.
+  struct Ent {
+    float s;
+    int L, e;          // row lane and column (within the chunk) the element came from
+    bool colq;         // column direction: the query is the column, the candidate the row
+    bool neg, cached;  // a negative above the query's lowest relevant item / its thresholds are in shared memory
+    int pc, so, k;     // number of thresholds, cache offset, #{thresholds < s}
+    const float* tsrc;
+    unsigned* csrc;
+    long long hbase;
+  };
+
+  // Fetch entry r of the queue and everything needed to bin it (warp-collective: shuffles).
+  __device__ static __forceinline__ void decode(const Params& p, RowState& st, const EpiCtx& ctx, Ent& en, int r,
+                                                int end, int cc, int ci, int colok, int col0, int lane) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const bool active = r < end;
+    en.s = active ? q_val(ctx)[r] : 0.f;
+    const int tag = active ? (int)q_tag(ctx)[r] : 0;
+    en.L = (tag >> 5) & 31;
+    en.e = tag & 31;
+    en.colq = kSym && ((tag >> 10) & 1);
+    const int rqc = __shfl_sync(kFull, st.qc, en.L);
+    const int rqi = __shfl_sync(kFull, st.qi, en.L);
+    const int rpc = __shfl_sync(kFull, st.cnt, en.L);
+    const int rso = __shfl_sync(kFull, st.so, en.L);
+    const float rtl = __shfl_sync(kFull, st.tlim, en.L);
+    const int ccol = __shfl_sync(kFull, cc, en.e);
+    const int cicol = __shfl_sync(kFull, ci, en.e);
+    const int ok = __shfl_sync(kFull, colok, en.e);
+    // i_j == i_q: self (or a version-id collision), never a candidate -- the test is symmetric
+    bool cand = active && ok && cicol != rqi;
+    en.pc = rpc;
+    en.so = rso;
+    float tl = rtl;
+    en.tsrc = thr_s(ctx);
+    en.csrc = cnt_s(ctx);
+    en.hbase = st.base;
+    if (kSym) {
+      const int rowL = st.row_glob - lane + en.L;
+      cand = cand && (col0 + en.e > rowL);  // each unordered pair is scored once, from above the diagonal
+      if (en.colq) {
+        const int cj = (col0 & (kTileN - 1)) + en.e;
+        en.pc = cnum_s(ctx)[cj];
+        en.so = cso_s(ctx)[cj];
+        tl = clim_s(ctx)[cj];
+        en.tsrc = cthr_s(ctx);
+        en.csrc = ccnt_s(ctx);
+        en.hbase = st.col_base;
+      }
+    }
+    if (!kSym && p.topk > 0) {
+      const float tau = __shfl_sync(kFull, st.tau, en.L);
+      if (cand && en.s > tau) {
+        const int slot = atomicAdd(&n_cand(ctx)[en.L], 1);
+        const long long cb = st.cbase + (long long)(en.L - lane) * p.cap + slot;  // rows of a warp are consecutive
+        p.cand_val[cb] = en.s;
+        p.cand_idx[cb] = col0 + en.e;
+      }
+    }
+    // rank counting: a negative above at least the lowest relevant item
+    en.neg = cand && en.s > tl && ccol != rqc;
+    en.cached = en.neg && en.so >= 0;
+    en.k = 0;
+  }
+
+  // Count the binned element: elements of a round mostly come from one hot query and land in one bucket, so the
+  // first cached lane counts all lanes that share its (cache, bucket) key with a single shared-memory atomic,
+  // the others add their own.  Elements whose thresholds are not cached (giant clique) use the global arrays.
+  __device__ static __forceinline__ void count(const Params& p, RowState& st, const Ent& en, int col0, int lane) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int slot_idx = en.so + en.k - 1;  // k >= 1 for a cached negative (s is above the lowest threshold)
+    const int key = en.cached ? (slot_idx | (en.colq ? 0x40000000 : 0)) : -1;
+    const unsigned cm = __ballot_sync(kFull, en.cached);
+    if (cm != 0u) {
+      const int lead = __ffs(cm) - 1;
+      const int key_lead = __shfl_sync(kFull, key, lead);
+      const unsigned same = __ballot_sync(kFull, en.cached && key == key_lead);
+      if (en.cached && (lane == lead || key != key_lead)) {
+        const unsigned add = lane == lead ? (unsigned)__popc(same) : 1u;
+        const int shift = (slot_idx & 1) * 16;
+        const unsigned old = (atomicAdd(en.csrc + (slot_idx >> 1), add << shift) >> shift) & 0xffffu;
+        // keep the 16-bit field far from overflow: the (single) adder that takes it across 0x8000
+        // moves exactly 0x8000 counts to the global histogram
+        if (old < 0x8000u && old + add >= 0x8000u) {
+          atomicSub(en.csrc + (slot_idx >> 1), 0x8000u << shift);
+          atomicAdd(p.hist + en.hbase + slot_idx, 0x8000u);
+        }
+      }
+    }
+    if (en.neg && en.so < 0) {
+      const int q = en.colq ? (col0 + en.e) : (st.row_glob - lane + en.L);
+      const long long o = __ldg(p.off + q);
+      const int k = count_below(p.thr + o, en.pc, en.s);
+      if (k > 0) atomicAdd(p.hist + o + (k - 1), 1u);
+    }
+  }
+
+  // Process the queue range [begin, end): every lane busy, TWO elements per lane and iteration so that the two
+  // shared-memory binary searches (dependent load -> compare chains) overlap.  cc / ci / colok are the ids and
+  // validity of this lane's column in the chunk the range came from; col0 its first column.
+  __device__ static __forceinline__ void process_range(const Params& p, RowState& st, const EpiCtx& ctx, int begin,
+                                                       int end, int cc, int ci, int colok, int col0, int lane) {
+    if constexpr (!kSym) {
+      // the full-rectangle sweeps (MMA-bound, and the top-k path) keep the one-element-per-lane round:
+      // measured equal or faster there; the two-element round pays off in the epilogue-bound symmetric sweep
+      process_range_single(p, st, ctx, begin, end, cc, ci, colok, col0, lane);
+    } else {
+    for (int r0 = begin; r0 < end; r0 += 64) {
+      Ent a, b;
+      decode(p, st, ctx, a, r0 + lane, end, cc, ci, colok, col0, lane);
+      const bool two = r0 + 32 < end;  // warp-uniform
+      if (two) {
+        decode(p, st, ctx, b, r0 + 32 + lane, end, cc, ci, colok, col0, lane);
+      } else {
+        b.cached = false;
+        b.neg = false;
+      }
+      // fused lower bounds: #{thresholds < s} over thr[so .. so + pc)
+      int loa = 0, hia = a.cached ? a.pc : 0;
+      int lob = 0, hib = (two && b.cached) ? b.pc : 0;
+      const float* ta = a.tsrc + a.so;
+      const float* tb = two ? b.tsrc + b.so : ta;
+      while (loa < hia || lob < hib) {
+        if (loa < hia) {
+          const int mid = (loa + hia) >> 1;
+          if (ta[mid] < a.s) loa = mid + 1; else hia = mid;
+        }
+        if (lob < hib) {
+          const int mid = (lob + hib) >> 1;
+          if (tb[mid] < b.s) lob = mid + 1; else hib = mid;
+        }
+      }
+      a.k = loa;
+      count(p, st, a, col0, lane);
+      if (two) {
+        b.k = lob;
+        count(p, st, b, col0, lane);
+      }
+    }
+    }
+  }
+
   // top-k: a row gains at most 32 candidates per chunk; select its k best in place (warp-cooperatively,
   // one row at a time) as soon as fewer than kSlots * 32 free slots remain
   __device__ static __forceinline__ void compact_topk(const Params& p, RowState& st, const EpiCtx& ctx, int lane) {
@@ -497,11 +640,17 @@ struct EvalEpiT {
     const int incl = warp_incl_scan(mine, lane);
     int pos = base + incl - mine;
 #pragma unroll
-    for (int e = 0; e < 32; ++e) {
-      if (mb & (1u << e)) {
-        qv[pos] = __uint_as_float(acc[e]);
-        qt[pos] = (uint16_t)((dir << 10) | (lane << 5) | e);
-        ++pos;
+    for (int g = 0; g < 4; ++g) {
+      // lukewarm chunks have a handful of passing elements: skip the 8-column groups nobody needs
+      if (__any_sync(0xffffffffu, (mb & (0xffu << (8 * g))) != 0u)) {
+#pragma unroll
+        for (int e = 8 * g; e < 8 * g + 8; ++e) {
+          if (mb & (1u << e)) {
+            qv[pos] = __uint_as_float(acc[e]);
+            qt[pos] = (uint16_t)((dir << 10) | (lane << 5) | e);
+            ++pos;
+          }
+        }
       }
     }
     return __shfl_sync(0xffffffffu, incl, 31);

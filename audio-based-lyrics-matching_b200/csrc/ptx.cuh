@@ -82,7 +82,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     // a warp that keeps polling steals issue slots from the warps it is waiting for: back off after a few
     // tries (the wake-up granularity this adds is far below one pipeline stage)
+#ifdef WEALY_WAIT_BACKOFF
     if (++polls > 4) __nanosleep(polls > 64 ? 256 : 32);
+#else
+    ++polls;
+#endif
     if ((polls & 63) == 0 && clock64() - t0 > WEALY_DEADLOCK_CYCLES) {
       printf("wealy: mbarrier deadlock block=%d thread=%d bar=0x%x parity=%u\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
