@@ -12,6 +12,7 @@
 #include "eval_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "masked_kernels.cuh"
+#include "pool_kernels.cuh"
 #include "prep.cuh"
 
 using namespace wealy;
@@ -256,14 +257,8 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
 template <class Epi>
 static int launch_gemm(int passes, const Planes& a, const Planes& b, GemmShape& sh, const typename Epi::Params& ep,
                        cudaStream_t s) {
-  const int bk = env_int("WEALY_BLOCK_K", 64);
   if (passes == 3) {
     if (a.lo == nullptr || b.lo == nullptr) return fail(WEALY_ERR_BAD_ARG, "3-pass contraction needs lo planes");
-    if (bk == 32) {
-      sh.k_blocks = (int)(a.d_pad / 32);
-      return launch_gemm_t<Epi, 3, 32, 8>(a, b, sh, ep, s);
-    }
-    if (env_int("WEALY_EPI_WARPS", 8) == 4) return launch_gemm_t<Epi, 3, 64, 4>(a, b, sh, ep, s);
     return launch_gemm_t<Epi, 3, 64, 8>(a, b, sh, ep, s);
   }
   if (passes == 1) return launch_gemm_t<Epi, 1, 64, 8>(a, b, sh, ep, s);
@@ -525,9 +520,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   CU_TRY(cudaMemsetAsync(p->hist, 0, (size_t)(p->total_pairs > 0 ? p->total_pairs : 1) * 4, s));
   if (finish) CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
 
-  const int epi_warps = env_int("WEALY_EVAL_EPI_WARPS", 8);  // 16 measured no faster (the sweep is not latency-starved)
-  const int halves = epi_warps == 16 ? 4
-                     : ((passes == 3 && env_int("WEALY_EPI_WARPS", 8) == 4 && env_int("WEALY_BLOCK_K", 64) == 64) ? 1 : 2);
+  const int halves = 2;  // two epilogue warps per TMEM lane quadrant (16 warps and 4 warps were measured no better)
   GemmShape sh;
   // top-k keeps <= 4 candidate lists per query (column chunks x epilogue warps per row)
   fill_shape(sh, nq, nc, pq.d_pad, 64, topk > 0 ? (4 / halves) : (1 << 20), topk > 0 ? 0 : env_int("WEALY_TILES_PER_UNIT", 8));
@@ -571,7 +564,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   // Symmetric all-vs-all: queries ARE the candidates (same ids, same embeddings), no top-k.  Only the tiles
   // that reach above the diagonal are contracted (half the tensor work); every element scores both its row
   // query and its column query.  Needs a second per-CTA threshold cache -> 3-stage ring of 48 KB stages.
-  const bool sym = same && p->same_ids && topk == 0 && halves == 2 && (shard_world > 1 || env_int("WEALY_SYM", 1) != 0);
+  const bool sym = same && p->same_ids && topk == 0 && (shard_world > 1 || env_int("WEALY_SYM", 1) != 0);
   if (shard_world > 1) {
     if (!sym) return fail(WEALY_ERR_BAD_ARG, "a sharded sweep needs queries == candidates (ids and embeddings) and no top-k");
     const int total_rb = sh.n_row_blocks;
@@ -588,10 +581,6 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     } else {
       W_TRY((launch_gemm_t<EvalEpiSym, 1, 64, 8, 3>(pq, pc, sh, ep, s)));
     }
-  } else if (halves == 4) {
-    // 16 epilogue warps (4 per TMEM lane quadrant): the slow path is latency bound, more warps hide it
-    if (passes == 3) W_TRY((launch_gemm_t<EvalEpi16, 3, 64, 16>(pq, pc, sh, ep, s)));
-    else W_TRY((launch_gemm_t<EvalEpi16, 1, 64, 16>(pq, pc, sh, ep, s)));
   } else {
     W_TRY(launch_gemm<EvalEpi>(passes, pq, pc, sh, ep, s));
   }
@@ -686,6 +675,126 @@ extern "C" int wealy_masked_reduce(const void* x, const uint8_t* mask, int64_t r
     case WEALY_BF16: return launch_masked<__nv_bfloat16>(x, mask, rows, cols, op, fill, eps, out, s);
     default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// f3 / f4: the steps either side of the path
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_mean_pool(const void* x, const uint8_t* mask, int64_t b, int64_t c, int64_t t, void* out, int backward,
+                            cudaStream_t s) {
+  const long long rows = b * c;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)ceil_div(rows * 32, threads);
+  if (backward)
+    mean_pool_bwd_kernel<T><<<blocks, threads, 0, s>>>((const T*)x, mask, rows, (int)c, (int)t, (T*)out);
+  else
+    mean_pool_fwd_kernel<T><<<blocks, threads, 0, s>>>((const T*)x, mask, rows, (int)c, (int)t, (T*)out);
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+extern "C" int wealy_mean_pool(const void* x, const uint8_t* mask, int64_t b, int64_t c, int64_t t, int dtype, void* out,
+                               int backward, void* stream) {
+  if (b < 0 || c < 0 || t <= 0) return fail(WEALY_ERR_BAD_ARG, "bad shape (%lld, %lld, %lld)", (long long)b, (long long)c, (long long)t);
+  if (b * c == 0) return WEALY_OK;
+  if (!x || !out) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (b * c > 60000000ll || t > 2000000000ll) return fail(WEALY_ERR_UNSUPPORTED, "too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case WEALY_F32: return launch_mean_pool<float>(x, mask, b, c, t, out, backward, s);
+    case WEALY_F16: return launch_mean_pool<__half>(x, mask, b, c, t, out, backward, s);
+    case WEALY_BF16: return launch_mean_pool<__nv_bfloat16>(x, mask, b, c, t, out, backward, s);
+    default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
+  }
+}
+
+extern "C" int wealy_segment_mean(const void* x, const int64_t* offsets, int64_t tracks, int64_t dim, int dtype,
+                                  float* out, void* stream) {
+  if (tracks < 0 || dim <= 0) return fail(WEALY_ERR_BAD_ARG, "bad shape tracks=%lld dim=%lld", (long long)tracks, (long long)dim);
+  if (tracks == 0) return WEALY_OK;
+  if (!x || !offsets || !out) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (tracks > 2000000000ll || dim > 2000000000ll) return fail(WEALY_ERR_UNSUPPORTED, "too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)tracks;
+  switch (dtype) {
+    case WEALY_F32: segment_mean_kernel<float><<<blocks, 256, 0, s>>>((const float*)x, (const long long*)offsets, (int)tracks, (int)dim, out); break;
+    case WEALY_F16: segment_mean_kernel<__half><<<blocks, 256, 0, s>>>((const __half*)x, (const long long*)offsets, (int)tracks, (int)dim, out); break;
+    case WEALY_BF16: segment_mean_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>((const __nv_bfloat16*)x, (const long long*)offsets, (int)tracks, (int)dim, out); break;
+    default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
+  }
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+extern "C" int wealy_triplet_mine(const int64_t* z_label, const int64_t* z_idx, int64_t b, int64_t* positives,
+                                  int64_t* negatives, void* stream) {
+  if (b < 0) return fail(WEALY_ERR_BAD_ARG, "bad batch size");
+  if (b == 0) return WEALY_OK;
+  if (!z_label || !z_idx || !positives || !negatives) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (b > 60000000ll) return fail(WEALY_ERR_UNSUPPORTED, "batch too large");
+  const int threads = 256;
+  triplet_mine_kernel<<<(unsigned)ceil_div(b * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+      (const long long*)z_label, (const long long*)z_idx, (int)b, (long long*)positives, (long long*)negatives);
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+template <typename T>
+static void launch_triplet_fwd(const void* z, int64_t ldz, int64_t b, int64_t d, const int64_t* pos, const int64_t* neg,
+                               float margin, float p, float eps, int swap, float* rows, double* acc, cudaStream_t s) {
+  triplet_fwd_kernel<T><<<(unsigned)ceil_div(b * 32, 256), 256, 0, s>>>((const T*)z, ldz, (int)b, (int)d, (const long long*)pos,
+                                                                      (const long long*)neg, margin, p, eps, swap,
+                                                                      (TripletRow*)rows, acc);
+}
+
+extern "C" int wealy_triplet_forward(const void* z, int64_t ldz, int64_t b, int64_t d, int dtype, const int64_t* positives,
+                                     const int64_t* negatives, float margin, float p, float eps, int swap, float* rows,
+                                     double* acc, void* stream) {
+  if (b < 0 || d <= 0 || !(p > 0.f)) return fail(WEALY_ERR_BAD_ARG, "bad shape / norm degree");
+  if (!acc) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU_TRY(cudaMemsetAsync(acc, 0, 2 * sizeof(double), s));
+  if (b == 0) return WEALY_OK;
+  if (!z || !positives || !negatives || !rows) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (b > 60000000ll || d > 2000000000ll) return fail(WEALY_ERR_UNSUPPORTED, "too large");
+  switch (dtype) {
+    case WEALY_F32: launch_triplet_fwd<float>(z, ldz, b, d, positives, negatives, margin, p, eps, swap, rows, acc, s); break;
+    case WEALY_F16: launch_triplet_fwd<__half>(z, ldz, b, d, positives, negatives, margin, p, eps, swap, rows, acc, s); break;
+    case WEALY_BF16: launch_triplet_fwd<__nv_bfloat16>(z, ldz, b, d, positives, negatives, margin, p, eps, swap, rows, acc, s); break;
+    default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
+  }
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+template <typename T>
+static void launch_triplet_bwd(const void* z, int64_t ldz, int64_t b, int64_t d, const int64_t* pos, const int64_t* neg,
+                               float p, float eps, int swap, const float* rows, const float* upstream, int per_anchor,
+                               int mean, const double* acc, float* dz, cudaStream_t s) {
+  triplet_bwd_kernel<T><<<(unsigned)ceil_div(b * 32, 256), 256, 0, s>>>((const T*)z, ldz, (int)b, (int)d, (const long long*)pos,
+                                                                      (const long long*)neg, p, eps, swap,
+                                                                      (const TripletRow*)rows, upstream, per_anchor, mean, acc, dz);
+}
+
+extern "C" int wealy_triplet_backward(const void* z, int64_t ldz, int64_t b, int64_t d, int dtype, const int64_t* positives,
+                                      const int64_t* negatives, float p, float eps, int swap, const float* rows,
+                                      const float* upstream, int per_anchor, int mean, const double* acc, float* dz,
+                                      void* stream) {
+  if (b < 0 || d <= 0 || !(p > 0.f)) return fail(WEALY_ERR_BAD_ARG, "bad shape / norm degree");
+  if (b == 0) return WEALY_OK;
+  if (!z || !positives || !negatives || !rows || !upstream || !acc || !dz) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (b > 60000000ll || d > 2000000000ll) return fail(WEALY_ERR_UNSUPPORTED, "too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU_TRY(cudaMemsetAsync(dz, 0, (size_t)b * d * sizeof(float), s));
+  switch (dtype) {
+    case WEALY_F32: launch_triplet_bwd<float>(z, ldz, b, d, positives, negatives, p, eps, swap, rows, upstream, per_anchor, mean, acc, dz, s); break;
+    case WEALY_F16: launch_triplet_bwd<__half>(z, ldz, b, d, positives, negatives, p, eps, swap, rows, upstream, per_anchor, mean, acc, dz, s); break;
+    case WEALY_BF16: launch_triplet_bwd<__nv_bfloat16>(z, ldz, b, d, positives, negatives, p, eps, swap, rows, upstream, per_anchor, mean, acc, dz, s); break;
+    default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
+  }
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
 }
 
 #include "loss_api.inl"

@@ -209,7 +209,6 @@ struct EvalParams {
   float* cand_val;         // [parts][nq][cap]
   int* cand_idx;
   int* cand_cnt;           // [parts][nq]
-  float* cand_tau;         // [parts][nq] running k-th best (lower bound filter)
   int nq_total;
 };
 
@@ -792,7 +791,6 @@ struct EvalEpiT {
 };
 
 using EvalEpi = EvalEpiT<256, 3456>;           // 8 epilogue warps
-using EvalEpi16 = EvalEpiT<128, 3328>;         // 16 epilogue warps
 using EvalEpiSym = EvalEpiT<256, 3456, true>;  // symmetric all-vs-all (8 epilogue warps, 3-stage ring)
 
 }  // namespace wealy

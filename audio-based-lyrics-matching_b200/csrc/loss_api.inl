@@ -105,7 +105,7 @@ extern "C" int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int6
   loss_params(lp, cfg, w, b);
   GemmShape sh;
   fill_shape(sh, b, b, w.u.d_pad, 64, w.parts_max / 2);
-  const int halves = (cfg->passes == 3 && env_int("WEALY_EPI_WARPS", 8) == 4 && env_int("WEALY_BLOCK_K", 64) == 64) ? 1 : 2;
+  const int halves = 2;  // epilogue warps per TMEM lane quadrant
   const int parts = sh.n_col_chunks * halves;
   W_TRY(launch_gemm<LossStatsEpi>(cfg->passes, w.u, w.u, sh, lp, s));
   LossCfgDev dc;

@@ -4,6 +4,9 @@ computed on sm_100a:
   NTXentLoss(temperature=0.1).forward(z_label, z_idx, z, extra=None) -> (loss, logdict)   lib/losses.py:10-73
   CLEWSLoss(gamma, b, eps, epsilon, uniformity_weight, warmup_steps)
       .forward(z_label, z_idx, z, extra=None, numerically_friendly=True) -> (loss, logdict) lib/losses.py:176-285
+  TripletLoss(margin=0.2, p=2, eps=1e-6, swap=False, reduction='mean')
+      .forward(z_label, z_idx, z, extra=None) -> (loss, logdict)                          lib/losses.py:76-171
+      (the Python mining loop becomes one kernel, the margin loss a fused fwd / bwd pair)
 
 Same constructor arguments, forward signature, logdict keys and side effects (a single-label batch
 mutates the caller's z_label in place, lib/losses.py:34-35 / 221-222).  Forward and backward run in
@@ -156,3 +159,86 @@ class CLEWSLoss(nn.Module):
             "z_std": stats[3],
         }
         return loss, logdict
+
+
+class _TripletFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, pos, neg, margin, p, eps, swap, reduction):
+        b, d = z.shape
+        zz = z if z.stride(1) == 1 else z.contiguous()
+        rows = torch.empty(b, 4, dtype=torch.float32, device=z.device)
+        acc = torch.empty(2, dtype=torch.float64, device=z.device)
+        with torch.cuda.device(z.device):
+            N.check(N.lib.wealy_triplet_forward(zz.data_ptr(), zz.stride(0), b, d, N.dtype_code(zz.dtype), pos.data_ptr(),
+                                                neg.data_ptr(), margin, p, eps, 1 if swap else 0, rows.data_ptr(),
+                                                acc.data_ptr(), N.stream_ptr(z.device)))
+        ctx.save_for_backward(zz, pos, neg, rows, acc)
+        ctx.cfg = (p, eps, swap, reduction)
+        out_dtype = torch.float32 if z.dtype in (torch.float16, torch.bfloat16) else z.dtype
+        if reduction == "none":
+            out = rows[:, 3].to(out_dtype)          # per anchor; -1 marks anchors without a triplet
+        elif reduction == "sum":
+            out = acc[0].to(out_dtype)
+        else:
+            out = (acc[0] / acc[1].clamp(min=1.0)).to(out_dtype)
+        ctx.mark_non_differentiable(acc)
+        return out, acc
+
+    @staticmethod
+    def backward(ctx, g, _gacc):
+        zz, pos, neg, rows, acc = ctx.saved_tensors
+        p, eps, swap, reduction = ctx.cfg
+        b, d = zz.shape
+        dz = torch.empty(b, d, dtype=torch.float32, device=zz.device)
+        up = g.detach().to(torch.float32).reshape(-1).contiguous()
+        with torch.cuda.device(zz.device):
+            N.check(N.lib.wealy_triplet_backward(zz.data_ptr(), zz.stride(0), b, d, N.dtype_code(zz.dtype), pos.data_ptr(),
+                                                 neg.data_ptr(), p, eps, 1 if swap else 0, rows.data_ptr(), up.data_ptr(),
+                                                 1 if reduction == "none" else 0, 1 if reduction == "mean" else 0,
+                                                 acc.data_ptr(), dz.data_ptr(), N.stream_ptr(zz.device)))
+        return dz.to(zz.dtype), None, None, None, None, None, None, None
+
+
+def mine_triplets(z_label, z_idx):
+    """lib/losses.py:140-171 without the Python loop: per anchor the FIRST index with the same label and a different
+    idx, and the FIRST index with a different label (-1 where there is none).  -> (positives[B], negatives[B]) int64."""
+    N.require_cuda(z_label, z_idx)
+    lab = z_label.to(torch.long).contiguous()
+    idx = z_idx.to(torch.long).contiguous()
+    b = lab.numel()
+    pos = torch.empty(b, dtype=torch.long, device=lab.device)
+    neg = torch.empty(b, dtype=torch.long, device=lab.device)
+    with torch.cuda.device(lab.device):
+        N.check(N.lib.wealy_triplet_mine(lab.data_ptr(), idx.data_ptr(), b, pos.data_ptr(), neg.data_ptr(),
+                                         N.stream_ptr(lab.device)))
+    return pos, neg
+
+
+class TripletLoss(nn.Module):
+    """lib/losses.py:76-171.  Same constructor / forward / logdict; one host read (the triplet count, needed for
+    the reference's empty-batch branch) instead of the reference's 2*B `.item()` calls."""
+
+    def __init__(self, margin=0.2, p=2, eps=1e-6, swap=False, reduction="mean"):
+        super().__init__()
+        assert reduction in ("mean", "sum", "none")
+        self.margin, self.p, self.eps, self.swap, self.reduction = float(margin), float(p), float(eps), bool(swap), reduction
+
+    def _create_triplets(self, z_label, z_idx):
+        """-> (anchors, positives, negatives) index tensors, as lib/losses.py:140-171."""
+        pos, neg = mine_triplets(z_label, z_idx)
+        anchors = torch.nonzero((pos >= 0) & (neg >= 0)).flatten()
+        return anchors, pos[anchors], neg[anchors]
+
+    def forward(self, z_label, z_idx, z, extra=None):
+        assert len(z_label) == len(z_idx) and len(z_label) == len(z)
+        N.require_cuda(z, z_label, z_idx)
+        _label_noise_(z_label)                                  # lib/losses.py:107-108
+        pos, neg = mine_triplets(z_label, z_idx)
+        out, acc = _TripletFn.apply(z, pos, neg, self.margin, self.p, self.eps, self.swap, self.reduction)
+        n_triplets = int(acc[1].item())
+        stats = {"v_zmax": z.detach().abs().max(), "v_zmean": z.detach().mean(), "v_zstd": z.detach().std()}
+        if n_triplets == 0:                                     # lib/losses.py:113-123
+            loss = torch.tensor(0.0, device=z.device, requires_grad=True)
+            return loss, {"l_main": loss, **stats, "n_triplets": 0}
+        loss = out[out >= 0] if self.reduction == "none" else out
+        return loss, {"l_main": loss, **stats}

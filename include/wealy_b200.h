@@ -116,6 +116,32 @@ void wealy_eval_plan_destroy(wealy_eval_plan* plan);
 int wealy_masked_reduce(const void* x, const uint8_t* mask, int64_t rows, int64_t cols, int dtype, int op, float fill,
                         float eps, void* out, void* stream);
 
+/* ---- f3 / f4: the steps either side of the path --------------------------
+ * wealy_mean_pool: lib/layers.py:6-30 MeanPool.  x [b, c, t] contiguous, mask [b, t] bytes (non-zero = VALID) or
+ *   NULL; backward == 0: out [b, c] = masked temporal mean; backward != 0: x is the upstream gradient [b, c] and
+ *   out [b, c, t] receives d/dx.
+ * wealy_segment_mean: the avg-pool collate (lib/embedding_dataset/collate_functions.py:131-172, emb.mean(dim=0)):
+ *   x [sum_T, dim] = the tracks' frames concatenated, offsets [tracks + 1] int64 -> out [tracks, dim] fp32.
+ * wealy_triplet_mine: lib/losses.py:140-171 `_create_triplets`: positives[i] / negatives[i] = first index with
+ *   the same label and a different idx / a different label, -1 if none.                                 */
+int wealy_mean_pool(const void* x, const uint8_t* mask, int64_t b, int64_t c, int64_t t, int dtype, void* out,
+                    int backward, void* stream);
+int wealy_segment_mean(const void* x, const int64_t* offsets, int64_t tracks, int64_t dim, int dtype, float* out,
+                       void* stream);
+int wealy_triplet_mine(const int64_t* z_label, const int64_t* z_idx, int64_t b, int64_t* positives,
+                       int64_t* negatives, void* stream);
+/* wealy_triplet_forward / _backward: lib/losses.py:76-137 (torch.nn.TripletMarginLoss on the mined triplets).
+ *   d(x, y) = ||x - y + eps||_p;  l_i = max(margin + d(a,p) - d_neg, 0), d_neg = d(a,n) or min(d(a,n), d(p,n)) (swap).
+ *   forward: rows [b][4] f32 = (d_ap, d_an, d_pn, l_i; l_i = -1 for anchors without a triplet), acc[2] doubles =
+ *   (sum of l_i, number of triplets).  backward: dz [b][d] fp32 (zeroed by the call) = sum_i g_i dl_i/dz with
+ *   g_i = upstream[0] (/ number of triplets if `mean`) or upstream[i] if `per_anchor`.                      */
+int wealy_triplet_forward(const void* z, int64_t ldz, int64_t b, int64_t d, int dtype, const int64_t* positives,
+                          const int64_t* negatives, float margin, float p, float eps, int swap, float* rows,
+                          double* acc, void* stream);
+int wealy_triplet_backward(const void* z, int64_t ldz, int64_t b, int64_t d, int dtype, const int64_t* positives,
+                           const int64_t* negatives, float p, float eps, int swap, const float* rows,
+                           const float* upstream, int per_anchor, int mean, const double* acc, float* dz, void* stream);
+
 /* ---- a5/a6: batch similarity-matrix contrastive losses -------------------------------------
  * NT-Xent: lib/losses.py:19-73.  CLEWS: lib/losses.py:210-285.  Forward writes the loss terms
  * and logdict statistics into `out` (doubles, device) and keeps the per-row statistics the

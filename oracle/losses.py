@@ -141,3 +141,32 @@ def clews_grad(z_label, z_idx, z, *, gamma=8.0, b=1.0, eps=1e-8, epsilon=1e-6, u
     dU = (dS + dS.t()) @ u
     proj = (u * dU).sum(dim=1, keepdim=True)
     return (dU - u * proj) / r
+
+
+def triplet_mine(z_label, z_idx):
+    """lib/losses.py:140-171 restated without the loop: per anchor the first positive (same label, different idx)
+    and the first negative (different label); anchors lacking either are dropped.  -> (anchors, positives, negatives)."""
+    pos, neg = _masks(z_label, z_idx)
+    has = pos.any(dim=1) & neg.any(dim=1)
+    first_pos = pos.float().argmax(dim=1)           # argmax returns the FIRST maximal index
+    first_neg = neg.float().argmax(dim=1)
+    anchors = torch.nonzero(has).flatten()
+    return anchors, first_pos[anchors], first_neg[anchors]
+
+
+def triplet(z_label, z_idx, z, margin=0.2, p=2, eps=1e-6, swap=False, reduction="mean"):
+    """-> (loss, logdict) as lib/losses.py:92-137 (torch.nn.TripletMarginLoss on the mined triplets)."""
+    assert len(z_label) == len(z_idx) == len(z)
+    _label_noise(z_label)                           # :107-108
+    a, pp, nn_ = triplet_mine(z_label, z_idx)
+    zmax, zmean, zstd = _zstats(z)
+    if len(a) == 0:                                 # :113-123
+        loss = torch.tensor(0.0, requires_grad=True)
+        return loss, {"l_main": loss, "v_zmax": zmax, "v_zmean": zmean, "v_zstd": zstd, "n_triplets": 0}
+    d_ap = torch.nn.functional.pairwise_distance(z[a], z[pp], p=p, eps=eps)
+    d_an = torch.nn.functional.pairwise_distance(z[a], z[nn_], p=p, eps=eps)
+    if swap:
+        d_an = torch.minimum(d_an, torch.nn.functional.pairwise_distance(z[pp], z[nn_], p=p, eps=eps))
+    li = torch.clamp_min(margin + d_ap - d_an, 0)
+    loss = li.mean() if reduction == "mean" else (li.sum() if reduction == "sum" else li)
+    return loss, {"l_main": loss, "v_zmax": zmax, "v_zmean": zmean, "v_zstd": zstd}

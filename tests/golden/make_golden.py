@@ -148,11 +148,62 @@ def gen_losses():
     np.savez_compressed(os.path.join(HERE, "losses.npz"), **out)
 
 
+def gen_pooling_triplet():
+    """f3 / f4: the reference's MeanPool (lib/layers.py:6-30) and TripletLoss (lib/losses.py:76-171), unmodified."""
+    import importlib
+    layers = importlib.import_module("lib.layers")
+    out = {}
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(5, 12, 37, generator=g)
+    mask = torch.rand(5, 37, generator=g) < 0.7
+    mask[2] = False                                   # a fully padded item: 0 / 1e-8
+    mask[3] = True
+    out["mp_x"], out["mp_mask"] = x.numpy(), mask.numpy()
+    mp = layers.MeanPool()
+    for tag, m in (("masked", mask), ("plain", None)):
+        xx = x.clone().requires_grad_(True)
+        y = mp(xx, m)
+        w = torch.randn(y.shape, generator=torch.Generator().manual_seed(3))
+        (gx,) = torch.autograd.grad((y * w).sum(), xx)
+        out[f"mp_{tag}_y"], out[f"mp_{tag}_w"], out[f"mp_{tag}_gx"] = y.detach().numpy(), w.numpy(), gx.numpy()
+    # triplet loss: clique batches incl. duplicates of idx, a clique of one (no positive) and a single-label batch
+    for name, (B, D, per, single) in {"t_a": (48, 64, 4, False), "t_b": (33, 40, 3, False), "t_single": (24, 16, 24, True),
+                                      "t_nopos": (12, 8, 1, False)}.items():
+        gg = torch.Generator().manual_seed(len(name) * 7 + B)
+        z = torch.randn(B, D, generator=gg) * 0.7
+        lab = (torch.arange(B) // per).long()
+        lab = lab[torch.randperm(B, generator=gg)]
+        if single:
+            lab[:] = 5
+        idx = torch.arange(B).long()
+        if B > 20:
+            idx[7] = idx[3]                            # duplicate version id
+        out[f"{name}_z"], out[f"{name}_label"], out[f"{name}_idx"] = z.numpy(), lab.numpy(), idx.numpy()
+        for tag, kw in (("def", {}), ("swap", {"swap": True, "margin": 0.5}), ("p1sum", {"p": 1, "reduction": "sum"}),
+                        ("p3", {"p": 3, "margin": 1.0})):
+            mod = rlosses.TripletLoss(**kw)
+            zz = z.clone().requires_grad_(True)
+            lab_in = lab.clone()
+            loss, logd = mod(lab_in, idx.clone(), zz)
+            (grad,) = torch.autograd.grad(loss, zz, allow_unused=True)
+            out[f"{name}_{tag}_loss"] = loss.detach().double().numpy()
+            out[f"{name}_{tag}_grad"] = (torch.zeros_like(zz) if grad is None else grad).numpy()
+            out[f"{name}_{tag}_label_after"] = lab_in.numpy()
+            a, pp, nn_ = mod._create_triplets(lab_in, idx)
+            out[f"{name}_{tag}_anchors"], out[f"{name}_{tag}_pos"], out[f"{name}_{tag}_neg"] = (
+                a.long().numpy(), pp.long().numpy(), nn_.long().numpy())
+            out[f"{name}_{tag}_ntrip_key"] = np.array(int("n_triplets" in logd))
+            for k in ("v_zmax", "v_zmean", "v_zstd"):
+                out[f"{name}_{tag}_log_{k}"] = logd[k].detach().double().numpy()
+    np.savez_compressed(os.path.join(HERE, "pooling_triplet.npz"), **out)
+
+
 if __name__ == "__main__":
     gen_similarity()
     gen_masked()
     gen_redux()
     gen_losses()
+    gen_pooling_triplet()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)) // 1024, "KiB")
