@@ -66,7 +66,7 @@ def avg_pool_tracks(frames, offsets=None):
     if offsets is None:
         lens = torch.tensor([0] + [int(f.shape[0]) for f in frames], dtype=torch.long)
         offsets = torch.cumsum(lens, 0)
-        frames = torch.cat([f.reshape(f.shape[0], -1) for f in frames], 0) if len(frames) else torch.empty(0, 1)
+        frames = torch.cat([f.reshape(f.shape[0], f.shape[-1]) for f in frames], 0) if len(frames) else torch.empty(0, 1)
         frames = frames.cuda() if not frames.is_cuda else frames
     N.require_cuda(frames)
     assert frames.dim() == 2
