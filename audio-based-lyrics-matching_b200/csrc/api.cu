@@ -9,6 +9,7 @@
 
 #include "../../include/wealy_b200.h"
 #include "epilogues.cuh"
+#include "eval_sym_epilogue.cuh"
 #include "eval_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "masked_kernels.cuh"
@@ -157,12 +158,12 @@ static void carve_planes(Planes& p, uint8_t*& cur, int64_t rows, int64_t d, int 
 
 static int launch_prep(const void* x, int64_t ld, int64_t n, int64_t d, int dtype, int mode, float eps,
                        const Planes& p, __half* hi_t, __half* lo_t, int64_t ld_t, ZStats* stats, int stats_on_scaled,
-                       cudaStream_t s) {
+                       cudaStream_t s, const int* gather = nullptr) {
   if (n == 0) return WEALY_OK;
   const int threads = 256;
   const unsigned blocks = (unsigned)ceil_div(n * 32, threads);
 #define PREP_ARGS (long long)ld, (int)n, (int)d, (int)p.d_pad, mode, eps, stats_on_scaled, p.hi, p.lo, hi_t, lo_t, \
-                  (long long)ld_t, p.norm, p.scale, p.sq, stats
+                  (long long)ld_t, p.norm, p.scale, p.sq, stats, gather
   switch (dtype) {
     case WEALY_F32: prep_rows_kernel<float><<<blocks, threads, 0, s>>>((const float*)x, PREP_ARGS); break;
     case WEALY_F16: prep_rows_kernel<__half><<<blocks, threads, 0, s>>>((const __half*)x, PREP_ARGS); break;
@@ -332,15 +333,25 @@ struct wealy_eval_plan {
   size_t planes_cap = 0;
   void* topk_buf = nullptr;
   size_t topk_cap = 0;
+  // clique-sorted view of an all-vs-all plan (same ids on both sides): the symmetric sweep runs in this row order
+  // (perm = sorted_idx: sorted position -> caller's row; clique ids = sorted_c)
+  int *s_i = nullptr, *s_seg_lo = nullptr, *s_seg_len = nullptr, *s_npos = nullptr;
+  long long* s_off = nullptr;
+  float4* s_lvl = nullptr;
+  uint2* s_cinfo = nullptr;
+  unsigned char* s_dirty = nullptr;
+  int64_t s_padded = 0;
   // CUDA events bracketing the fused sweep of the last run (roofline accounting in bench.py)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
+  bool last_sym = false;  // the last sweep ran in the clique-sorted view (its counters are in that CSR order)
 };
 
 extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
   if (!p) return;
   void* ptrs[] = {p->q_c, p->q_i, p->sorted_c, p->sorted_idx, p->seg_lo, p->seg_len, p->npos, p->off,
-                  p->raw, p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf};
+                  p->raw, p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf,
+                  p->s_i, p->s_seg_lo, p->s_seg_len, p->s_npos, p->s_off, p->s_lvl, p->s_cinfo, p->s_dirty};
   for (void* q : ptrs) dev_free(q, p->stream);
   if (!p->same_ids) {
     dev_free(p->c_c, p->stream);
@@ -404,6 +415,44 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   CU_TRY(cudaMemsetAsync(p->npos + nq, 0, 4, s));
   CU_TRY(cub::DeviceScan::ExclusiveSum(tmp2, scan_bytes, p->npos, p->off, nq + 1, s));
 
+  // ---- clique-sorted view for the symmetric all-vs-all sweep
+  void *tmp3 = nullptr, *tmp4 = nullptr;
+  int *vkeys = nullptr, *vpos = nullptr, *everything = nullptr;
+  if (p->same_ids) {
+    const int n = nq;
+    const int nrb = (int)ceil_div(n, kTileM), nct = (int)ceil_div(n, kTileN);
+    p->s_padded = (int64_t)nct * kTileN + kTileN;
+    CU_TRY(dev_alloc((void**)&p->s_i, (size_t)n * 4 + 4, s));
+    CU_TRY(dev_alloc((void**)&p->s_seg_lo, (size_t)n * 4 + 4, s));
+    CU_TRY(dev_alloc((void**)&p->s_seg_len, (size_t)n * 4 + 4, s));
+    CU_TRY(dev_alloc((void**)&p->s_npos, (size_t)n * 4 + 4, s));
+    CU_TRY(dev_alloc((void**)&p->s_off, ((size_t)n + 1) * 8, s));
+    CU_TRY(dev_alloc((void**)&p->s_lvl, (size_t)p->s_padded * 16, s));
+    CU_TRY(dev_alloc((void**)&p->s_cinfo, (size_t)p->s_padded * 8, s));
+    CU_TRY(dev_alloc((void**)&p->s_dirty, (size_t)nrb * nct, s));
+    gather_i32_kernel<<<(unsigned)ceil_div(n, T), T, 0, s>>>(p->q_i, p->sorted_idx, n, p->s_i);
+    // in sorted space the clique-sorted order is the identity (iota)
+    segment_lookup_kernel<<<(unsigned)ceil_div(n, T), T, 0, s>>>(p->sorted_c, p->s_i, n, p->sorted_c, iota, p->s_i, n,
+                                                                p->s_seg_lo, p->s_seg_len, p->s_npos, totals + 2);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemsetAsync(p->s_npos + n, 0, 4, s));
+    CU_TRY(cub::DeviceScan::ExclusiveSum(tmp2, scan_bytes, p->s_npos, p->s_off, n + 1, s));
+    // tiles that need id tests: clique ranges that intersect, ragged edges, version-id collisions
+    CU_TRY(cudaMemsetAsync(p->s_dirty, 0, (size_t)nrb * nct, s));
+    dirty_clique_kernel<<<(unsigned)ceil_div((int64_t)nrb * nct, T), T, 0, s>>>(p->sorted_c, n, nrb, nct, p->s_dirty);
+    CU_TRY(dev_alloc((void**)&vkeys, (size_t)n * 4 + 4, s));
+    CU_TRY(dev_alloc((void**)&vpos, (size_t)n * 4 + 4, s));
+    CU_TRY(dev_alloc((void**)&everything, 16, s));
+    CU_TRY(cudaMemsetAsync(everything, 0, 16, s));
+    size_t tb = 0;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, p->s_i, vkeys, iota, vpos, n, 0, 32, s));
+    CU_TRY(dev_alloc(&tmp3, tb + 16, s));
+    CU_TRY(cub::DeviceRadixSort::SortPairs(tmp3, tb, p->s_i, vkeys, iota, vpos, n, 0, 32, s));
+    dirty_collision_kernel<<<(unsigned)ceil_div(n, T), T, 0, s>>>(vkeys, vpos, n, nrb, nct, p->s_dirty, everything);
+    dirty_everything_kernel<<<(unsigned)ceil_div((int64_t)nrb * nct, T), T, 0, s>>>(everything, (long long)nrb * nct, p->s_dirty);
+    CU_TRY(cudaGetLastError());
+  }
+
   int bad_h[16];
   unsigned long long totals_h[2];
   long long total = 0;
@@ -413,6 +462,11 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   CU_TRY(cudaStreamSynchronize(s));
   dev_free(tmp, s);
   dev_free(tmp2, s);
+  dev_free(tmp3, s);
+  dev_free(tmp4, s);
+  dev_free(vkeys, s);
+  dev_free(vpos, s);
+  dev_free(everything, s);
   dev_free(iota, s);
   dev_free(bad, s);
   if (bad_h[0] != 0) return fail(WEALY_ERR_ID_RANGE, "%d clique/version ids do not fit in 32 bits", bad_h[0]);
@@ -492,6 +546,14 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   const int64_t nq = p->nq, nc = p->nc;
   const bool same = (queries_z == candidates_z && nq == nc && ld_q == ld_c);
 
+  // Symmetric all-vs-all: queries ARE the candidates (same ids, same embeddings), no top-k.  Only the tiles
+  // that reach above the diagonal are contracted (half the tensor work); every element scores both its row
+  // query and its column query.  Runs in the plan's clique-sorted row order (eval_sym_epilogue.cuh).
+  const bool sym = same && p->same_ids && topk == 0 && p->total_pairs < (1ll << 31) - 8 &&
+                   (shard_world > 1 || env_int("WEALY_SYM", 1) != 0);
+  if (shard_world > 1 && !sym)
+    return fail(WEALY_ERR_BAD_ARG, "a sharded sweep needs queries == candidates (ids and embeddings) and no top-k");
+
   // operand planes (cached allocation)
   const size_t need = planes_bytes(nq, d, passes) + (same ? 0 : planes_bytes(nc, d, passes)) + 2048;
   if (need > p->planes_cap) {
@@ -505,18 +567,27 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   Planes pq, pc;
   carve_planes(pq, cur, nq, d, passes);
   if (same) pc = pq; else carve_planes(pc, cur, nc, d, passes);
-  W_TRY(launch_prep(queries_z, ld_q, nq, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s));
+  W_TRY(launch_prep(queries_z, ld_q, nq, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s,
+                    sym ? p->sorted_idx : nullptr));
   if (!same) W_TRY(launch_prep(candidates_z, ld_c, nc, d, dtype, kPrepL2AddEps, eps, pc, nullptr, nullptr, 0, nullptr, 0, s));
 
   // K_pos: relevant similarities, sorted per query
   {
     const int threads = 256;
-    const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
-    pos_thresholds_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, p->q_i, (int)nq,
-                                                     p->sorted_idx, p->c_i, p->seg_lo, p->seg_len, p->off, p->raw,
-                                                     p->thr, p->lim, p->cnt);
+    if (sym) {
+      const unsigned blocks = (unsigned)ceil_div(p->s_padded * 32, threads);
+      pos_thresholds_sorted_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, (int)pq.d_pad, p->s_i, (int)nq,
+                                                              (int)p->s_padded, p->s_seg_lo, p->s_seg_len, p->s_off,
+                                                              p->raw, p->thr, p->cnt, p->s_lvl, p->s_cinfo);
+    } else {
+      const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
+      pos_thresholds_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, p->q_i, (int)nq,
+                                                       p->sorted_idx, p->c_i, p->seg_lo, p->seg_len, p->off, p->raw,
+                                                       p->thr, p->lim, p->cnt);
+    }
     CU_TRY(cudaGetLastError());
   }
+  p->last_sym = sym;
   CU_TRY(cudaMemsetAsync(p->hist, 0, (size_t)(p->total_pairs > 0 ? p->total_pairs : 1) * 4, s));
   if (finish) CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
 
@@ -561,12 +632,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     CU_TRY(cudaEventCreate(&p->ev1));
   }
   CU_TRY(cudaEventRecord(p->ev0, s));
-  // Symmetric all-vs-all: queries ARE the candidates (same ids, same embeddings), no top-k.  Only the tiles
-  // that reach above the diagonal are contracted (half the tensor work); every element scores both its row
-  // query and its column query.  Needs a second per-CTA threshold cache -> 3-stage ring of 48 KB stages.
-  const bool sym = same && p->same_ids && topk == 0 && (shard_world > 1 || env_int("WEALY_SYM", 1) != 0);
   if (shard_world > 1) {
-    if (!sym) return fail(WEALY_ERR_BAD_ARG, "a sharded sweep needs queries == candidates (ids and embeddings) and no top-k");
     const int total_rb = sh.n_row_blocks;
     sh.rb_stride = shard_world;
     sh.rb_offset = shard_rank;
@@ -575,11 +641,27 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   }
   if (sym) {
     sh.sym = 1;
+    EvalSymParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.lvl = p->s_lvl;
+    sp.cinfo = p->s_cinfo;
+    sp.s_c = p->sorted_c;
+    sp.s_i = p->s_i;
+    sp.thr = p->thr;
+    sp.hist = p->hist;
+    sp.dirty = p->s_dirty;
+    sp.n_col_tiles = sh.n_col_tiles;
+    sp.total_pairs = (unsigned)p->total_pairs;
+    const int lv = env_int("WEALY_SYM_LEVELS", 4);
     if (passes == 3) {
       sh.k_blocks = (int)(pq.d_pad / 32);
-      W_TRY((launch_gemm_t<EvalEpiSym, 3, 32, 8, 3>(pq, pc, sh, ep, s)));
+      if (lv == 2) W_TRY((launch_gemm_t<EvalSymEpi<2>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
+      else if (lv == 3) W_TRY((launch_gemm_t<EvalSymEpi<3>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
+      else W_TRY((launch_gemm_t<EvalSymEpi<4>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
     } else {
-      W_TRY((launch_gemm_t<EvalEpiSym, 1, 64, 8, 3>(pq, pc, sh, ep, s)));
+      if (lv == 2) W_TRY((launch_gemm_t<EvalSymEpi<2>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
+      else if (lv == 3) W_TRY((launch_gemm_t<EvalSymEpi<3>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
+      else W_TRY((launch_gemm_t<EvalSymEpi<4>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
     }
   } else {
     W_TRY(launch_gemm<EvalEpi>(passes, pq, pc, sh, ep, s));
@@ -590,7 +672,8 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   if (finish) {
     const int threads = 256;
     const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
-    ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)nq, aps, r1s, sums);
+    if (sym) ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->s_off, p->cnt, (int)nq, aps, r1s, sums, p->sorted_idx);
+    else ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)nq, aps, r1s, sums);
     CU_TRY(cudaGetLastError());
     if (topk > 0) {
       if (parts * cap <= 32 * kFinPerLane) {
@@ -639,7 +722,8 @@ extern "C" int wealy_eval_finish(wealy_eval_plan* p, float* aps, float* r1s, dou
   CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
   const int threads = 256;
   const unsigned blocks = (unsigned)ceil_div(p->nq * 32, threads);
-  ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)p->nq, aps, r1s, sums);
+  if (p->last_sym) ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->s_off, p->cnt, (int)p->nq, aps, r1s, sums, p->sorted_idx);
+  else ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)p->nq, aps, r1s, sums);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
 }

@@ -126,6 +126,130 @@ __global__ void __launch_bounds__(256) pos_thresholds_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Clique-sorted ("sorted space") view used by the symmetric all-vs-all sweep (eval_sym_epilogue.cuh)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void gather_i32_kernel(const int* __restrict__ src, const int* __restrict__ idx, int n, int* __restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = src[idx[t]];
+}
+
+// Tiles of the symmetric sweep that need id tests: row block rb x column tile t (t >= rb / 2) holds a self or
+// same-clique pair iff the clique ranges of its rows and columns intersect (ids ascending in sorted space); ragged
+// edge tiles are marked too (padded rows / columns must not be scored).
+__global__ void dirty_clique_kernel(const int* __restrict__ s_c, int n, int n_row_blocks, int n_col_tiles,
+                                    unsigned char* __restrict__ dirty) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_row_blocks * n_col_tiles) return;
+  const int rb = (int)(idx / n_col_tiles), t = (int)(idx - (long long)rb * n_col_tiles);
+  if (t < (rb >> 1)) return;
+  const int r0 = rb * kTileM, r1 = min(r0 + kTileM, n) - 1;
+  const int c0 = t * kTileN, c1 = min(c0 + kTileN, n) - 1;
+  const bool ragged = (r0 + kTileM > n) || (c0 + kTileN > n);
+  const bool overlap = max(s_c[r0], s_c[c0]) <= min(s_c[r1], s_c[c1]);
+  if (ragged || overlap) dirty[idx] = 1;
+}
+
+// Version-id collisions between different cliques can fall into any tile.  keys = version ids sorted ascending,
+// pos = their sorted-space positions: every pair of equal keys marks the tile its (smaller, larger) position hits.
+// A run longer than 16 equal ids (pathological input) marks everything.
+__global__ void dirty_collision_kernel(const int* __restrict__ keys, const int* __restrict__ pos, int n,
+                                       int n_row_blocks, int n_col_tiles, unsigned char* __restrict__ dirty,
+                                       int* __restrict__ everything) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n || k == 0) return;
+  const int key = keys[k];
+  for (int b = 1; b <= 17 && k - b >= 0; ++b) {
+    if (keys[k - b] != key) break;
+    if (b == 17) { atomicExch(everything, 1); break; }
+    const int p0 = min(pos[k], pos[k - b]), p1 = max(pos[k], pos[k - b]);
+    dirty[(long long)(p0 / kTileM) * n_col_tiles + p1 / kTileN] = 1;
+  }
+  (void)n_row_blocks;
+}
+
+__global__ void dirty_everything_kernel(const int* __restrict__ everything, long long count, unsigned char* __restrict__ dirty) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx < count && *everything) dirty[idx] = 1;
+}
+
+// K_pos in sorted space.  One warp per query: its clique is the contiguous segment [seg_lo, seg_lo + seg_len) of rows;
+// similarities come from the SAME fp16 planes the sweep consumes; rank-sorted ascending into thr (CSR); the lowest
+// four go to lvl[q] (+inf padded), {offset, count} to cinfo[q].  Rows q >= n (padding up to a whole column tile)
+// get lvl = +inf, cinfo = {total, 0}.
+__global__ void __launch_bounds__(256) pos_thresholds_sorted_kernel(
+    const __half* __restrict__ hi, const __half* __restrict__ lo, int d_pad, const int* __restrict__ s_i, int n,
+    int n_padded, const int* __restrict__ seg_lo, const int* __restrict__ seg_len, const long long* __restrict__ off,
+    float* __restrict__ raw, float* __restrict__ thr, int* __restrict__ cnt, float4* __restrict__ lvl,
+    uint2* __restrict__ cinfo) {
+  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (q >= n_padded) return;
+  const float inf = __int_as_float(0x7f800000);
+  if (q >= n) {
+    if (lane == 0) {
+      lvl[q] = make_float4(inf, inf, inf, inf);
+      cinfo[q] = make_uint2((unsigned)off[n], 0u);
+    }
+    return;
+  }
+  const int first = seg_lo[q], len = seg_len[q], qi = s_i[q];
+  const long long o = off[q];
+  const uint4* qh = reinterpret_cast<const uint4*>(hi + (long long)q * d_pad);
+  const uint4* ql = lo ? reinterpret_cast<const uint4*>(lo + (long long)q * d_pad) : nullptr;
+  const int nvec = d_pad >> 3;
+  int np = 0;
+  for (int m = 0; m < len; ++m) {
+    const int j = first + m;
+    if (s_i[j] == qi) continue;  // self / id collision
+    const uint4* ch = reinterpret_cast<const uint4*>(hi + (long long)j * d_pad);
+    const uint4* cl = lo ? reinterpret_cast<const uint4*>(lo + (long long)j * d_pad) : nullptr;
+    float acc = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+      const uint4 a = qh[v], b = ch[v];
+      const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+      const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+      uint4 al = make_uint4(0, 0, 0, 0), bl = make_uint4(0, 0, 0, 0);
+      if (ql) { al = ql[v]; bl = cl[v]; }
+      const __half2* al2 = reinterpret_cast<const __half2*>(&al);
+      const __half2* bl2 = reinterpret_cast<const __half2*>(&bl);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 fa = __half22float2(a2[e]), fb = __half22float2(b2[e]);
+        acc = fmaf(fa.x, fb.x, acc);
+        acc = fmaf(fa.y, fb.y, acc);
+        if (ql) {
+          const float2 fal = __half22float2(al2[e]), fbl = __half22float2(bl2[e]);
+          acc = fmaf(fa.x, fbl.x, acc);
+          acc = fmaf(fa.y, fbl.y, acc);
+          acc = fmaf(fal.x, fb.x, acc);
+          acc = fmaf(fal.y, fb.y, acc);
+        }
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) raw[o + np] = acc;
+    ++np;
+  }
+  __syncwarp();
+  for (int e = lane; e < np; e += 32) {
+    const float ve = raw[o + e];
+    int r = 0;
+    for (int f = 0; f < np; ++f) {
+      const float vf = raw[o + f];
+      r += (vf < ve) || (vf == ve && f < e);
+    }
+    thr[o + r] = ve;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    cnt[q] = np;
+    lvl[q] = make_float4(np > 0 ? thr[o] : inf, np > 1 ? thr[o + 1] : inf, np > 2 ? thr[o + 2] : inf,
+                         np > 3 ? thr[o + 3] : inf);
+    cinfo[q] = make_uint2((unsigned)o, (unsigned)np);
+  }
+}
+
 // K2.  One warp per query; warp-shuffle suffix scan over the rank histogram.
 //   above[r]    = sum_{m >= r} hist[m]            negatives ranked above the r-th lowest relevant item
 //   rank_all[r] = 1 + above[r] + (P - 1 - r)      relevant items above it are the ones sorted after it
@@ -134,7 +258,8 @@ __global__ void __launch_bounds__(256) pos_thresholds_kernel(
 __global__ void __launch_bounds__(256) ap_reduce_kernel(const unsigned int* __restrict__ hist,
                                                         const long long* __restrict__ off,
                                                         const int* __restrict__ cnt, int nq, float* __restrict__ ap,
-                                                        float* __restrict__ r1, double* __restrict__ sums) {
+                                                        float* __restrict__ r1, double* __restrict__ sums,
+                                                        const int* __restrict__ perm = nullptr) {
   const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (q >= nq) return;
@@ -165,8 +290,9 @@ __global__ void __launch_bounds__(256) ap_reduce_kernel(const unsigned int* __re
   if (lane == 0) {
     const float a = P > 0 ? acc / (float)P : __int_as_float(0x7fc00000);
     const float f = P > 0 ? first_rank : __int_as_float(0x7fc00000);
-    ap[q] = a;
-    r1[q] = f;
+    const int dst = perm ? perm[q] : q;  // sorted space -> the caller's row order
+    ap[dst] = a;
+    r1[dst] = f;
     if (P > 0) {
       atomicAdd(&sums[0], (double)a);
       atomicAdd(&sums[1], (double)f);

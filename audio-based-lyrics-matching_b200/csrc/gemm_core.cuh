@@ -77,7 +77,7 @@ struct GemmSmem {
   static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
   static constexpr int kBudget = 227 * 1024 - 2048 - 30 * 1024;  // alignment slack + barriers + epilogue scratch
   static constexpr int kStages = (kBudget / kStageBytes) > kMaxStages ? kMaxStages : (kBudget / kStageBytes);
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 512;
   static constexpr int kCore = kStages * kStageBytes + kBarBytes;  // + per-warp epilogue scratch + 1024 align slack
   static_assert(kStages >= 2, "need at least a double-buffered ring");
   static constexpr int total(int epi_warps, int scratch_per_warp, int cta_scratch) {
@@ -94,6 +94,18 @@ struct EpiCtx {
   int row_base;           // first query row of the unit's row block
   int first_col;          // first column this warp will see in the unit ...
   int col_step;           // ... and the distance to the column of its next chunk
+  const uint8_t* col_slot;  // Epi::kColSlots > 0: this tile's per-column data (bulk-copied by the TMA thread)
+};
+
+// Epilogues that want per-tile column data staged in shared memory declare kColSlots / kColSlotBytes /
+// kOffColSlots (offset inside their CTA scratch) and col_bulk_src(); the others get these defaults.
+template <class Epi, class = void>
+struct ColSlotTraits {
+  static constexpr int kSlots = 0, kBytes = 0, kOffset = 0;
+};
+template <class Epi>
+struct ColSlotTraits<Epi, decltype((void)Epi::kColSlots)> {
+  static constexpr int kSlots = Epi::kColSlots, kBytes = Epi::kColSlotBytes, kOffset = Epi::kOffColSlots;
 };
 
 // Epilogue policy contract (all __device__, called by the epilogue warps only; every epilogue
@@ -128,9 +140,15 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* unit_full = tmem_empty + 2;
   uint64_t* unit_empty = unit_full + 2;
-  int* unit_slot = reinterpret_cast<int*>(unit_empty + 2);
+  using CS = ColSlotTraits<Epi>;
+  constexpr int kColSlots = CS::kSlots;
+  uint64_t* col_full = unit_empty + 2;
+  uint64_t* col_empty = col_full + (kColSlots > 0 ? kColSlots : 1);
+  int* unit_slot = reinterpret_cast<int*>(col_empty + (kColSlots > 0 ? kColSlots : 1));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(unit_slot + 2);
+  static_assert((2 * kStages + 8 + 2 * (kColSlots > 0 ? kColSlots : 1)) * 8 + 16 <= SM::kBarBytes, "barrier area");
   uint8_t* scratch_base = bar_base + SM::kBarBytes;
+  uint8_t* col_slots = scratch_base + kEpiWarps * Epi::kWarpScratchBytes + CS::kOffset;
 
   const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = (int)ptx::lane_id();
@@ -152,6 +170,10 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       ptx::mbar_init(&unit_full[a], 1);
       ptx::mbar_init(&unit_empty[a], 1 + kEpiWarps);  // MMA thread + one lane per epilogue warp
     }
+    for (int c = 0; c < kColSlots; ++c) {
+      ptx::mbar_init(&col_full[c], 1);
+      ptx::mbar_init(&col_empty[c], kEpiWarps);
+    }
     ptx::fence_mbar_init();
   }
   if (warp_idx == 1) ptx::tmem_alloc<512>(tmem_slot);
@@ -169,6 +191,8 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       uint32_t phase = 0;
       int us = 0;
       uint32_t uphase = 0;
+      int cs = 0;
+      uint32_t cphase = 0;
       while (true) {
         // fetch the next unit and publish it to the MMA / epilogue warps
         ptx::mbar_wait(&unit_empty[us], uphase ^ 1u);
@@ -183,6 +207,17 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
         const int t1 = min((chunk + 1) * shape.tiles_per_chunk, shape.n_col_tiles);
         const int t0 = first_tile(shape, rb, chunk * shape.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
+          if constexpr (kColSlots > 0) {
+            // per-tile column data of the epilogue: contiguous arrays indexed by column -> 1-D bulk copies
+            ptx::mbar_wait(&col_empty[cs], cphase ^ 1u);
+            const void *s0, *s1;
+            Epi::col_bulk_src(ep, t, s0, s1);
+            uint8_t* dst = col_slots + cs * CS::kBytes;
+            ptx::mbar_expect_tx(&col_full[cs], CS::kBytes);
+            ptx::bulk_load(dst, s0, Epi::kLvlBytes, &col_full[cs]);
+            ptx::bulk_load(dst + Epi::kLvlBytes, s1, CS::kBytes - Epi::kLvlBytes, &col_full[cs]);
+            if (++cs == kColSlots) { cs = 0; cphase ^= 1u; }
+          }
           for (int kb = 0; kb < shape.k_blocks; ++kb) {
             ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* st = smem + stage * SM::kStageBytes;
@@ -263,6 +298,8 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
     uint32_t acc_phase = 0;
     int us = 0;
     uint32_t uphase = 0;
+    int cs = 0;
+    uint32_t cphase = 0;
     while (true) {
       ptx::mbar_wait(&unit_full[us], uphase);
       const int u = unit_slot[us];
@@ -286,8 +323,13 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       ctx.row_base = rb * kTileM;
       ctx.first_col = t0 * kTileN + half * kChunkCols;
       ctx.col_step = kHalves * kChunkCols;
+      ctx.col_slot = nullptr;
       Epi::row_begin(ep, rs, row, part, shape, ctx);
       for (int t = t0; t < t1; ++t) {
+        if constexpr (kColSlots > 0) {
+          ptx::mbar_wait(&col_full[cs], cphase);
+          ctx.col_slot = col_slots + cs * CS::kBytes;
+        }
         Epi::tile_begin(ep, rs, shape, ctx, t);
         ptx::mbar_wait(&tmem_full[acc], acc_phase);
         ptx::tc_fence_after_sync();
@@ -303,6 +345,10 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if constexpr (kColSlots > 0) {
+          if (lane == 0) ptx::mbar_arrive(&col_empty[cs]);  // (queued entries carry what they need)
+          if (++cs == kColSlots) { cs = 0; cphase ^= 1u; }
+        }
         Epi::tile_end(ep, rs, shape, ctx);  // work deferred until the accumulator is back with the MMA warp
       }
       Epi::row_end(ep, rs, row, part, shape, ctx);

@@ -62,11 +62,13 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ x,
                                                         __half* __restrict__ hi_t, __half* __restrict__ lo_t,
                                                         long long ld_t, float* __restrict__ norm_out,
                                                         float* __restrict__ scale_out, float* __restrict__ sq_out,
-                                                        ZStats* __restrict__ stats) {
+                                                        ZStats* __restrict__ stats,
+                                                        const int* __restrict__ gather = nullptr) {
   const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (warp >= n) return;
-  const T* row = x + (long long)warp * ld;
+  // `gather` (optional): output row r is built from input row gather[r] (clique-sorted planes of the evaluation sweep)
+  const T* row = x + (long long)(gather ? gather[warp] : warp) * ld;
 
   float ss = 0.f, mx = 0.f, sm = 0.f;
   for (int k = lane; k < d; k += 32) {
