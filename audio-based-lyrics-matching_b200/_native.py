@@ -3,7 +3,8 @@ pointers (tensor.data_ptr()), sizes and the current CUDA stream handle."""
 import ctypes
 import os
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libwealy_b200.so")
+_LIB_PATH = os.environ.get("WEALY_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib",
+                                                       "libwealy_b200.so")
 
 if not os.path.isfile(_LIB_PATH):
     raise ImportError(

@@ -13,7 +13,7 @@ HDR = os.path.join(PKG, "..", "include", "wealy_b200.h")
 OUT = os.path.join(PKG, "lib", "libwealy_b200.so")
 STAMP = OUT + ".srchash"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC"] + os.environ.get("WEALY_NVCC_EXTRA", "").split()
 
 
 def source_hash():

@@ -575,10 +575,14 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   {
     const int threads = 256;
     if (sym) {
+      // the plan's cnt array doubles as the per-query fill counter of step 1 (step 2 rewrites it)
+      CU_TRY(cudaMemsetAsync(p->cnt, 0, (size_t)nq * 4, s));
+      pos_pairs_sorted_kernel<<<(unsigned)ceil_div(nq, 16), threads, 0, s>>>(pq.hi, pq.lo, (int)pq.d_pad, p->sorted_c, p->s_i,
+                                                                         (int)nq, p->s_seg_lo, p->s_seg_len, p->s_off,
+                                                                         p->raw, p->cnt);
       const unsigned blocks = (unsigned)ceil_div(p->s_padded * 32, threads);
-      pos_thresholds_sorted_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, (int)pq.d_pad, p->s_i, (int)nq,
-                                                              (int)p->s_padded, p->s_seg_lo, p->s_seg_len, p->s_off,
-                                                              p->raw, p->thr, p->cnt, p->s_lvl, p->s_cinfo);
+      pos_sort_sorted_kernel<<<blocks, threads, 0, s>>>(p->s_npos, (int)nq, (int)p->s_padded, p->s_off, p->raw, p->thr,
+                                                        p->cnt, p->s_lvl, p->s_cinfo);
     } else {
       const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
       pos_thresholds_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, p->q_i, (int)nq,
@@ -652,7 +656,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     sp.dirty = p->s_dirty;
     sp.n_col_tiles = sh.n_col_tiles;
     sp.total_pairs = (unsigned)p->total_pairs;
-    const int lv = env_int("WEALY_SYM_LEVELS", 4);
+    const int lv = env_int("WEALY_SYM_LEVELS", 3);  // 3 measured best at C2 (2: 26.8 ms, 3: 25.5 ms, 4: 25.9 ms per step)
     if (passes == 3) {
       sh.k_blocks = (int)(pq.d_pad / 32);
       if (lv == 2) W_TRY((launch_gemm_t<EvalSymEpi<2>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));

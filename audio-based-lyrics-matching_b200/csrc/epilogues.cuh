@@ -212,7 +212,7 @@ struct EvalParams {
   int nq_total;
 };
 
-template <int kQueueCapT, int kCachePairsT, bool kSym = false>
+template <int kQueueCapT, int kCachePairsT>
 struct EvalEpiT {
   using Params = EvalParams;
   // Shared-memory scratch of the epilogue.
@@ -232,19 +232,7 @@ struct EvalEpiT {
   static constexpr int kOffCand = kOffTag + kQueueCap * 2;
   static constexpr int kWarpScratchBytes = kOffCand + 32 * 4;
   static constexpr int kCachePairs = kCachePairsT;  // mean of a 128-row block is ~2100 on SHS100K-shaped data
-  //  * symmetric all-vs-all (kSym): S is symmetric, so only the tiles that reach above the diagonal are
-  //    computed and every element (i, j), j > i, is scored twice: for query i against candidate j
-  //    ("row direction", as above) and for query j against candidate i ("column direction").  The
-  //    column queries change with every tile, so their thresholds (the contiguous CSR slice of the
-  //    tile's 256 columns), limits, counts and counters live in a second per-CTA cache that is flushed
-  //    and refilled at every tile boundary (tile_begin).
-  static constexpr int kColPairs = kSym ? 7680 : 0;  // mean of a 256-column tile is ~4300 on SHS100K-shaped data
-  static constexpr int kOffColThr = kCachePairs * 6;
-  static constexpr int kOffColCnt = kOffColThr + kColPairs * 4;
-  static constexpr int kOffColLim = kOffColCnt + kColPairs * 2;
-  static constexpr int kOffColNum = kOffColLim + (kSym ? kTileN * 4 : 0);
-  static constexpr int kOffColSo = kOffColNum + (kSym ? kTileN * 4 : 0);
-  static constexpr int kCtaScratchBytes = kOffColSo + (kSym ? kTileN * 4 : 0);
+  static constexpr int kCtaScratchBytes = kCachePairs * 6;
   static_assert(kCachePairs % 8 == 0, "cache regions stay 16-byte aligned");
   struct RowState {
     float lim;      // min(lowest threshold, top-k filter): the only compare on the fast path
@@ -261,10 +249,6 @@ struct EvalEpiT {
     int qn, nslot;                       // queued elements / chunks (warp-uniform)
     int q_end[4], col0_q[4];             // per queued chunk: end of its queue range, first column (uniform)
     int cc_q[4], ci_q[4], ok_q[4];       // per queued chunk: ids / validity of this lane's column
-    // symmetric mode: the column cache of the current tile (same values in every thread)
-    long long col_base;                  // off[] of the tile's first column
-    int col_n;                           // cached column pairs
-    int row_glob;                        // this thread's global row (position test col > row)
   };
   static constexpr int kSlots = 4;
 
@@ -277,12 +261,6 @@ struct EvalEpiT {
   __device__ static __forceinline__ unsigned* cnt_s(const EpiCtx& c) {
     return reinterpret_cast<unsigned*>(c.cta_scratch + kCachePairs * 4);
   }
-  __device__ static __forceinline__ float* cthr_s(const EpiCtx& c) { return reinterpret_cast<float*>(c.cta_scratch + kOffColThr); }
-  __device__ static __forceinline__ unsigned* ccnt_s(const EpiCtx& c) { return reinterpret_cast<unsigned*>(c.cta_scratch + kOffColCnt); }
-  __device__ static __forceinline__ float* clim_s(const EpiCtx& c) { return reinterpret_cast<float*>(c.cta_scratch + kOffColLim); }
-  __device__ static __forceinline__ int* cnum_s(const EpiCtx& c) { return reinterpret_cast<int*>(c.cta_scratch + kOffColNum); }
-  __device__ static __forceinline__ int* cso_s(const EpiCtx& c) { return reinterpret_cast<int*>(c.cta_scratch + kOffColSo); }
-
   __device__ static __forceinline__ void prefetch_ids(const Params& p, RowState& st, const GemmShape& sh, int lane) {
     const int col = st.next_col + lane;
     const bool ok = col < sh.n_cols;
@@ -310,9 +288,6 @@ struct EvalEpiT {
     st.next_col = ctx.first_col;
     st.qn = 0;
     st.nslot = 0;
-    st.col_base = 0;
-    st.col_n = 0;
-    st.row_glob = row;
     prefetch_ids(p, st, sh, lane);
     n_cand(ctx)[lane] = 0;
     // cooperative fill of the threshold cache (the previous unit's row_end left it flushed)
@@ -359,7 +334,7 @@ struct EvalEpiT {
 
   // Process the queue range [begin, end): 32 elements per round, every lane busy.  cc / ci / colok are the
   // ids and validity of this lane's column in the chunk the range came from; col0 its first column.
-  __device__ static __forceinline__ void process_range_single(const Params& p, RowState& st, const EpiCtx& ctx, int begin,
+  __device__ static __forceinline__ void process_range(const Params& p, RowState& st, const EpiCtx& ctx, int begin,
                                                        int end, int cc, int ci, int colok, int col0, int lane) {
     constexpr unsigned kFull = 0xffffffffu;
     const float* qv = q_val(ctx);
@@ -373,7 +348,6 @@ struct EvalEpiT {
       const float s = active ? qv[r] : 0.f;
       const int tag = active ? (int)qt[r] : 0;
       const int L = (tag >> 5) & 31, e = tag & 31;  // row lane and column of the element
-      const bool colq = kSym && ((tag >> 10) & 1);  // column direction: the query is column e, the candidate row L
       const int rqc = __shfl_sync(kFull, st.qc, L);
       const int rqi = __shfl_sync(kFull, st.qi, L);
       const int rpc = __shfl_sync(kFull, st.cnt, L);
@@ -384,26 +358,10 @@ struct EvalEpiT {
       const int cicol = __shfl_sync(kFull, ci, e);
       const int ok = __shfl_sync(kFull, colok, e);
       // i_j == i_q: self (or a version-id collision), never a candidate -- the test is symmetric
-      bool cand = active && ok && cicol != rqi;
-      int pc = rpc, so = rso;
-      float tl = rtl;
-      const float* tsrc = ts;
-      unsigned* csrc = cs;
-      long long hbase = st.base;
-      if (kSym) {
-        const int rowL = st.row_glob - lane + L;
-        cand = cand && (col0 + e > rowL);  // each unordered pair is scored once, from above the diagonal
-        if (colq) {
-          const int cj = (col0 & (kTileN - 1)) + e;
-          pc = cnum_s(ctx)[cj];
-          so = cso_s(ctx)[cj];
-          tl = clim_s(ctx)[cj];
-          tsrc = cthr_s(ctx);
-          csrc = ccnt_s(ctx);
-          hbase = st.col_base;
-        }
-      }
-      if (!kSym && cand && p.topk > 0 && s > tau) {
+      const bool cand = active && ok && cicol != rqi;
+      const int pc = rpc, so = rso;
+      const float tl = rtl;
+      if (cand && p.topk > 0 && s > tau) {
         const int slot = atomicAdd(&ncand[L], 1);
         const long long cb = st.cbase + (long long)(L - lane) * p.cap + slot;  // rows of a warp are consecutive
         p.cand_val[cb] = s;
@@ -413,12 +371,12 @@ struct EvalEpiT {
       const bool neg = cand && s > tl && ccol != rqc;
       const bool cached = neg && so >= 0;
       int k = 0;
-      if (cached) k = count_below_smem(tsrc + so, pc, s);
+      if (cached) k = count_below_smem(ts + so, pc, s);
       // the elements of a round mostly come from one hot query and land in one bucket: the first
       // cached lane counts all lanes that share its (cache, bucket) key with a single shared-memory
       // atomic, the others add their own
       const int slot_idx = so + k - 1;
-      const int key = cached ? (slot_idx | (colq ? 0x40000000 : 0)) : -1;
+      const int key = cached ? slot_idx : -1;
       const unsigned cm = __ballot_sync(kFull, cached);
       if (cm != 0u) {
         const int lead = __ffs(cm) - 1;
@@ -427,164 +385,21 @@ struct EvalEpiT {
         if (cached && (lane == lead || key != key_lead)) {
           const unsigned add = lane == lead ? (unsigned)__popc(same) : 1u;
           const int shift = (slot_idx & 1) * 16;
-          const unsigned old = (atomicAdd(csrc + (slot_idx >> 1), add << shift) >> shift) & 0xffffu;
+          const unsigned old = (atomicAdd(cs + (slot_idx >> 1), add << shift) >> shift) & 0xffffu;
           // keep the 16-bit field far from overflow: the (single) adder that takes it across 0x8000
           // moves exactly 0x8000 counts to the global histogram
           if (old < 0x8000u && old + add >= 0x8000u) {
-            atomicSub(csrc + (slot_idx >> 1), 0x8000u << shift);
-            atomicAdd(p.hist + hbase + slot_idx, 0x8000u);
+            atomicSub(cs + (slot_idx >> 1), 0x8000u << shift);
+            atomicAdd(p.hist + st.base + slot_idx, 0x8000u);
           }
         }
       }
       const long long offL = __shfl_sync(kFull, st.off, L);
       if (neg && so < 0) {  // thresholds not cached (giant clique): global CSR arrays
-        const long long o = colq ? __ldg(p.off + col0 + e) : offL;
+        const long long o = offL;
         k = count_below(p.thr + o, pc, s);
         if (k > 0) atomicAdd(p.hist + o + (k - 1), 1u);
       }
-    }
-  }
-
-  // One queued element as seen by the lane that processes it.
-  struct Ent {
-    float s;
-    int L, e;          // row lane and column (within the chunk) the element came from
-    bool colq;         // column direction: the query is the column, the candidate the row
-    bool neg, cached;  // a negative above the query's lowest relevant item / its thresholds are in shared memory
-    int pc, so, k;     // number of thresholds, cache offset, #{thresholds < s}
-    const float* tsrc;
-    unsigned* csrc;
-    long long hbase;
-  };
-
-  // Fetch entry r of the queue and everything needed to bin it (warp-collective: shuffles).
-  __device__ static __forceinline__ void decode(const Params& p, RowState& st, const EpiCtx& ctx, Ent& en, int r,
-                                                int end, int cc, int ci, int colok, int col0, int lane) {
-    constexpr unsigned kFull = 0xffffffffu;
-    const bool active = r < end;
-    en.s = active ? q_val(ctx)[r] : 0.f;
-    const int tag = active ? (int)q_tag(ctx)[r] : 0;
-    en.L = (tag >> 5) & 31;
-    en.e = tag & 31;
-    en.colq = kSym && ((tag >> 10) & 1);
-    const int rqc = __shfl_sync(kFull, st.qc, en.L);
-    const int rqi = __shfl_sync(kFull, st.qi, en.L);
-    const int rpc = __shfl_sync(kFull, st.cnt, en.L);
-    const int rso = __shfl_sync(kFull, st.so, en.L);
-    const float rtl = __shfl_sync(kFull, st.tlim, en.L);
-    const int ccol = __shfl_sync(kFull, cc, en.e);
-    const int cicol = __shfl_sync(kFull, ci, en.e);
-    const int ok = __shfl_sync(kFull, colok, en.e);
-    // i_j == i_q: self (or a version-id collision), never a candidate -- the test is symmetric
-    bool cand = active && ok && cicol != rqi;
-    en.pc = rpc;
-    en.so = rso;
-    float tl = rtl;
-    en.tsrc = thr_s(ctx);
-    en.csrc = cnt_s(ctx);
-    en.hbase = st.base;
-    if (kSym) {
-      const int rowL = st.row_glob - lane + en.L;
-      cand = cand && (col0 + en.e > rowL);  // each unordered pair is scored once, from above the diagonal
-      if (en.colq) {
-        const int cj = (col0 & (kTileN - 1)) + en.e;
-        en.pc = cnum_s(ctx)[cj];
-        en.so = cso_s(ctx)[cj];
-        tl = clim_s(ctx)[cj];
-        en.tsrc = cthr_s(ctx);
-        en.csrc = ccnt_s(ctx);
-        en.hbase = st.col_base;
-      }
-    }
-    if (!kSym && p.topk > 0) {
-      const float tau = __shfl_sync(kFull, st.tau, en.L);
-      if (cand && en.s > tau) {
-        const int slot = atomicAdd(&n_cand(ctx)[en.L], 1);
-        const long long cb = st.cbase + (long long)(en.L - lane) * p.cap + slot;  // rows of a warp are consecutive
-        p.cand_val[cb] = en.s;
-        p.cand_idx[cb] = col0 + en.e;
-      }
-    }
-    // rank counting: a negative above at least the lowest relevant item
-    en.neg = cand && en.s > tl && ccol != rqc;
-    en.cached = en.neg && en.so >= 0;
-    en.k = 0;
-  }
-
-  // Count the binned element: elements of a round mostly come from one hot query and land in one bucket, so the
-  // first cached lane counts all lanes that share its (cache, bucket) key with a single shared-memory atomic,
-  // the others add their own.  Elements whose thresholds are not cached (giant clique) use the global arrays.
-  __device__ static __forceinline__ void count(const Params& p, RowState& st, const Ent& en, int col0, int lane) {
-    constexpr unsigned kFull = 0xffffffffu;
-    const int slot_idx = en.so + en.k - 1;  // k >= 1 for a cached negative (s is above the lowest threshold)
-    const int key = en.cached ? (slot_idx | (en.colq ? 0x40000000 : 0)) : -1;
-    const unsigned cm = __ballot_sync(kFull, en.cached);
-    if (cm != 0u) {
-      const int lead = __ffs(cm) - 1;
-      const int key_lead = __shfl_sync(kFull, key, lead);
-      const unsigned same = __ballot_sync(kFull, en.cached && key == key_lead);
-      if (en.cached && (lane == lead || key != key_lead)) {
-        const unsigned add = lane == lead ? (unsigned)__popc(same) : 1u;
-        const int shift = (slot_idx & 1) * 16;
-        const unsigned old = (atomicAdd(en.csrc + (slot_idx >> 1), add << shift) >> shift) & 0xffffu;
-        // keep the 16-bit field far from overflow: the (single) adder that takes it across 0x8000
-        // moves exactly 0x8000 counts to the global histogram
-        if (old < 0x8000u && old + add >= 0x8000u) {
-          atomicSub(en.csrc + (slot_idx >> 1), 0x8000u << shift);
-          atomicAdd(p.hist + en.hbase + slot_idx, 0x8000u);
-        }
-      }
-    }
-    if (en.neg && en.so < 0) {
-      const int q = en.colq ? (col0 + en.e) : (st.row_glob - lane + en.L);
-      const long long o = __ldg(p.off + q);
-      const int k = count_below(p.thr + o, en.pc, en.s);
-      if (k > 0) atomicAdd(p.hist + o + (k - 1), 1u);
-    }
-  }
-
-  // Process the queue range [begin, end): every lane busy, TWO elements per lane and iteration so that the two
-  // shared-memory binary searches (dependent load -> compare chains) overlap.  cc / ci / colok are the ids and
-  // validity of this lane's column in the chunk the range came from; col0 its first column.
-  __device__ static __forceinline__ void process_range(const Params& p, RowState& st, const EpiCtx& ctx, int begin,
-                                                       int end, int cc, int ci, int colok, int col0, int lane) {
-    if constexpr (!kSym) {
-      // the full-rectangle sweeps (MMA-bound, and the top-k path) keep the one-element-per-lane round:
-      // measured equal or faster there; the two-element round pays off in the epilogue-bound symmetric sweep
-      process_range_single(p, st, ctx, begin, end, cc, ci, colok, col0, lane);
-    } else {
-    for (int r0 = begin; r0 < end; r0 += 64) {
-      Ent a, b;
-      decode(p, st, ctx, a, r0 + lane, end, cc, ci, colok, col0, lane);
-      const bool two = r0 + 32 < end;  // warp-uniform
-      if (two) {
-        decode(p, st, ctx, b, r0 + 32 + lane, end, cc, ci, colok, col0, lane);
-      } else {
-        b.cached = false;
-        b.neg = false;
-      }
-      // fused lower bounds: #{thresholds < s} over thr[so .. so + pc)
-      int loa = 0, hia = a.cached ? a.pc : 0;
-      int lob = 0, hib = (two && b.cached) ? b.pc : 0;
-      const float* ta = a.tsrc + a.so;
-      const float* tb = two ? b.tsrc + b.so : ta;
-      while (loa < hia || lob < hib) {
-        if (loa < hia) {
-          const int mid = (loa + hia) >> 1;
-          if (ta[mid] < a.s) loa = mid + 1; else hia = mid;
-        }
-        if (lob < hib) {
-          const int mid = (lob + hib) >> 1;
-          if (tb[mid] < b.s) lob = mid + 1; else hib = mid;
-        }
-      }
-      a.k = loa;
-      count(p, st, a, col0, lane);
-      if (two) {
-        b.k = lob;
-        count(p, st, b, col0, lane);
-      }
-    }
     }
   }
 
@@ -632,7 +447,7 @@ struct EvalEpiT {
 
   // scatter the elements selected by `mb` into the queue starting at `base`; returns their number
   __device__ static __forceinline__ int push(const EpiCtx& ctx, const uint32_t (&acc)[32], unsigned mb, int base,
-                                             int lane, int dir = 0) {
+                                             int lane) {
     float* qv = q_val(ctx);
     uint16_t* qt = q_tag(ctx);
     const int mine = __popc(mb);
@@ -646,7 +461,7 @@ struct EvalEpiT {
         for (int e = 8 * g; e < 8 * g + 8; ++e) {
           if (mb & (1u << e)) {
             qv[pos] = __uint_as_float(acc[e]);
-            qt[pos] = (uint16_t)((dir << 10) | (lane << 5) | e);
+            qt[pos] = (uint16_t)((lane << 5) | e);
             ++pos;
           }
         }
@@ -670,26 +485,14 @@ struct EvalEpiT {
     unsigned m = 0;
 #pragma unroll
     for (int e = 0; e < 32; ++e) m |= (__uint_as_float(acc[e]) > st.lim) ? (1u << e) : 0u;
-    unsigned mc = 0;  // symmetric mode: elements that pass the limit of their COLUMN's query
-    if (kSym) {
-      const float* cl = clim_s(ctx) + (col0 & (kTileN - 1));
-#pragma unroll
-      for (int e = 0; e < 32; ++e) mc |= (__uint_as_float(acc[e]) > cl[e]) ? (1u << e) : 0u;  // broadcast loads
-      // only the part of the tile above the diagonal counts (col0 + e > row)
-      const int d = st.row_glob - col0;  // columns 0..d of this chunk are on or below the diagonal
-      const unsigned above = d < 0 ? 0xffffffffu : (d >= 31 ? 0u : (0xffffffffu << (d + 1)));
-      m &= above;
-      mc &= above;
-    }
-    if (!__any_sync(kFull, (m | mc) != 0)) return;
+    if (!__any_sync(kFull, m != 0)) return;
 
     // ---- collect: the passing elements go to the warp queue; they are binned in drain(), after the
     // accumulator has been released, so the MMA warp never waits for a slow chunk
-    const int total = __reduce_add_sync(kFull, __popc(m) + __popc(mc));
+    const int total = __reduce_add_sync(kFull, __popc(m));
     if (st.nslot == kSlots || st.qn + total > kQueueCap) drain(p, st, ctx);
     if (total <= kQueueCap) {
-      int n = push(ctx, acc, m, st.qn, lane, 0);
-      if (kSym) n += push(ctx, acc, mc, st.qn + n, lane, 1);
+      push(ctx, acc, m, st.qn, lane);
       st.qn += total;
       const int sl = st.nslot++;
 #pragma unroll
@@ -704,65 +507,21 @@ struct EvalEpiT {
       }
     } else {
       // a chunk denser than the whole queue: bin it now, kBatchCols columns at a time
-      // (half as many in symmetric mode, where a column can contribute in both directions)
-      constexpr int kCols = kSym ? kBatchCols / 2 : kBatchCols;
+      constexpr int kCols = kBatchCols;
 #pragma unroll 1
       for (int bi = 0; bi < 32 / kCols; ++bi) {
         const unsigned sel = ((1u << kCols) - 1u) << (kCols * bi);
-        int n = push(ctx, acc, m & sel, 0, lane, 0);
-        if (kSym) n += push(ctx, acc, mc & sel, n, lane, 1);
+        const int n = push(ctx, acc, m & sel, 0, lane);
         __syncwarp();
         process_range(p, st, ctx, 0, n, cc, ci, colok, col0, lane);
         __syncwarp();
       }
-      if (!kSym && p.topk > 0) compact_topk(p, st, ctx, lane);
+      if (p.topk > 0) compact_topk(p, st, ctx, lane);
     }
     (void)row;
   }
 
-  // Symmetric mode: flush the column counters of the previous tile and load the column cache of tile `t`
-  // (thresholds, limits, counts, cache offsets of its 256 column queries).  Every epilogue thread calls
-  // this once per tile.  A thread only ever touches its own slots (index = tid mod nthreads) in the
-  // flush and in the reload, so one pass between two group barriers does both.
-  __device__ static __forceinline__ void tile_begin(const Params& p, RowState& st, const GemmShape& sh,
-                                                    const EpiCtx& ctx, int t) {
-    if (!kSym) return;
-    ptx::named_barrier_sync(1, ctx.nthreads);  // every warp has drained the previous tile
-    unsigned* cc_ = ccnt_s(ctx);
-    float* ct = cthr_s(ctx);
-    const int c0 = t * kTileN;
-    const int c1 = min(c0 + kTileN, sh.n_cols);
-    const long long nbase = p.off[c0];
-    const long long ntotal = p.off[c1] - nbase;
-    const int nn = (int)(ntotal < (long long)kColPairs ? ntotal : (long long)kColPairs);
-    const int words = (max(st.col_n, nn) + 1) >> 1;
-    for (int w = ctx.tid; w < words; w += ctx.nthreads) {
-      const unsigned v = (2 * w < st.col_n) ? cc_[w] : 0u;
-      if (v != 0u) {
-        if (v & 0xffffu) atomicAdd(p.hist + st.col_base + 2 * w, v & 0xffffu);
-        if (v >> 16) atomicAdd(p.hist + st.col_base + 2 * w + 1, v >> 16);
-      }
-      cc_[w] = 0u;
-    }
-    for (int i = ctx.tid; i < nn; i += ctx.nthreads) ct[i] = __ldg(p.thr + nbase + i);
-    for (int j = ctx.tid; j < kTileN; j += ctx.nthreads) {
-      const int col = c0 + j;
-      float lm = __int_as_float(0x7f800000);
-      int num = 0, so = -1;
-      if (col < sh.n_cols) {
-        lm = p.lim[col];
-        num = p.cnt[col];
-        const long long rel = p.off[col] - nbase;
-        so = (rel + num <= (long long)nn) ? (int)rel : -1;
-      }
-      clim_s(ctx)[j] = lm;
-      cnum_s(ctx)[j] = num;
-      cso_s(ctx)[j] = so;
-    }
-    st.col_base = nbase;
-    st.col_n = nn;
-    ptx::named_barrier_sync(1, ctx.nthreads);  // the new column cache is complete
-  }
+  __device__ static __forceinline__ void tile_begin(const Params&, RowState&, const GemmShape&, const EpiCtx&, int) {}
 
   __device__ static __forceinline__ void tile_end(const Params& p, RowState& st, const GemmShape&, const EpiCtx& ctx) {
     drain(p, st, ctx);
@@ -778,19 +537,10 @@ struct EvalEpiT {
       const unsigned v = (cs[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
       if (v != 0u) atomicAdd(p.hist + st.base + i, v);
     }
-    if (kSym) {  // column counters of the unit's last tile
-      const unsigned* cc_ = ccnt_s(ctx);
-      for (int i = ctx.tid; i < st.col_n; i += ctx.nthreads) {
-        const unsigned v = (cc_[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-        if (v != 0u) atomicAdd(p.hist + st.col_base + i, v);
-      }
-      st.col_n = 0;
-    }
     ptx::named_barrier_sync(1, ctx.nthreads);  // flushed before the next unit refills the cache
   }
 };
 
 using EvalEpi = EvalEpiT<256, 3456>;           // 8 epilogue warps
-using EvalEpiSym = EvalEpiT<256, 3456, true>;  // symmetric all-vs-all (8 epilogue warps, 3-stage ring)
 
 }  // namespace wealy

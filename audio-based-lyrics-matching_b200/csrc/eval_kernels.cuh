@@ -173,15 +173,82 @@ __global__ void dirty_everything_kernel(const int* __restrict__ everything, long
   if (idx < count && *everything) dirty[idx] = 1;
 }
 
-// K_pos in sorted space.  One warp per query: its clique is the contiguous segment [seg_lo, seg_lo + seg_len) of rows;
-// similarities come from the SAME fp16 planes the sweep consumes; rank-sorted ascending into thr (CSR); the lowest
-// four go to lvl[q] (+inf padded), {offset, count} to cinfo[q].  Rows q >= n (padding up to a whole column tile)
-// get lvl = +inf, cinfo = {total, 0}.
-__global__ void __launch_bounds__(256) pos_thresholds_sorted_kernel(
-    const __half* __restrict__ hi, const __half* __restrict__ lo, int d_pad, const int* __restrict__ s_i, int n,
-    int n_padded, const int* __restrict__ seg_lo, const int* __restrict__ seg_len, const long long* __restrict__ off,
-    float* __restrict__ raw, float* __restrict__ thr, int* __restrict__ cnt, float4* __restrict__ lvl,
-    uint2* __restrict__ cinfo) {
+// K_pos in sorted space, step 1: similarities of every (query, relevant item) pair.  A clique is a contiguous run
+// of rows, so the pairs of 16 consecutive queries form a dense 16 x |range| block of the Gram matrix around the
+// diagonal: one CTA per 16-query block, each warp takes 8 candidates at a time and contracts the block with
+// warp-level tensor-core MMAs (m16n8k16, fp32 accumulate) straight from the SAME fp16 planes the sweep consumes
+// (hi*hi + hi*lo + lo*hi), 5-10x less L2 traffic than one dot product per pair.  Valid pairs (same clique, version
+// ids differ) are appended to the query's CSR slice in arbitrary order (fill[q] counts them; step 2 sorts).
+__device__ __forceinline__ void mma_16x8x16(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(256) pos_pairs_sorted_kernel(
+    const __half* __restrict__ hi, const __half* __restrict__ lo, int d_pad, const int* __restrict__ s_c,
+    const int* __restrict__ s_i, int n, const int* __restrict__ seg_lo, const int* __restrict__ seg_len,
+    const long long* __restrict__ off, float* __restrict__ raw, int* __restrict__ fill) {
+  const int q0 = blockIdx.x * 16;
+  const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+  const int g = lane >> 2, tig = lane & 3;
+  const int qlast = min(q0 + 15, n - 1);
+  const int lo_row = seg_lo[q0], hi_row = seg_lo[qlast] + seg_len[qlast];  // candidates any of the 16 queries needs
+  const int qa = min(q0 + g, n - 1), qb = min(q0 + g + 8, n - 1);          // (clamped rows are discarded below)
+  const __half* a_hi0 = hi + (long long)qa * d_pad;
+  const __half* a_hi1 = hi + (long long)qb * d_pad;
+  const __half* a_lo0 = lo ? lo + (long long)qa * d_pad : nullptr;
+  const __half* a_lo1 = lo ? lo + (long long)qb * d_pad : nullptr;
+  for (int j0 = lo_row + warp * 8; j0 < hi_row; j0 += 64) {
+    const int jb = min(j0 + g, n - 1);
+    const __half* b_hi = hi + (long long)jb * d_pad;
+    const __half* b_lo = lo ? lo + (long long)jb * d_pad : nullptr;
+    float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = 0; k < d_pad; k += 16) {
+      const int ko = k + tig * 2;
+      unsigned ah[4], bh[2];
+      ah[0] = __ldg(reinterpret_cast<const unsigned*>(a_hi0 + ko));
+      ah[1] = __ldg(reinterpret_cast<const unsigned*>(a_hi1 + ko));
+      ah[2] = __ldg(reinterpret_cast<const unsigned*>(a_hi0 + ko + 8));
+      ah[3] = __ldg(reinterpret_cast<const unsigned*>(a_hi1 + ko + 8));
+      bh[0] = __ldg(reinterpret_cast<const unsigned*>(b_hi + ko));
+      bh[1] = __ldg(reinterpret_cast<const unsigned*>(b_hi + ko + 8));
+      mma_16x8x16(c, ah, bh);
+      if (lo) {
+        unsigned al[4], bl[2];
+        al[0] = __ldg(reinterpret_cast<const unsigned*>(a_lo0 + ko));
+        al[1] = __ldg(reinterpret_cast<const unsigned*>(a_lo1 + ko));
+        al[2] = __ldg(reinterpret_cast<const unsigned*>(a_lo0 + ko + 8));
+        al[3] = __ldg(reinterpret_cast<const unsigned*>(a_lo1 + ko + 8));
+        bl[0] = __ldg(reinterpret_cast<const unsigned*>(b_lo + ko));
+        bl[1] = __ldg(reinterpret_cast<const unsigned*>(b_lo + ko + 8));
+        mma_16x8x16(c, ah, bl);
+        mma_16x8x16(c, al, bh);
+      }
+    }
+    // c[0], c[1]: query q0 + g, candidates j0 + 2 tig, + 1;  c[2], c[3]: query q0 + g + 8, same candidates
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int q = q0 + g + (e >> 1) * 8;
+      const int j = j0 + tig * 2 + (e & 1);
+      if (q < n && j < hi_row && s_c[q] == s_c[j] && s_i[q] != s_i[j]) {
+        const int slot = atomicAdd(fill + q, 1);
+        raw[off[q] + slot] = c[e];
+      }
+    }
+  }
+}
+
+// K_pos step 2.  One warp per query: rank-sort its pair similarities ascending into thr (CSR); the lowest four go
+// to lvl[q] (+inf padded), {offset, count} to cinfo[q].  Rows q >= n (padding up to a whole column tile) get
+// lvl = +inf, cinfo = {total, 0}.
+__global__ void __launch_bounds__(256) pos_sort_sorted_kernel(const int* __restrict__ npos, int n, int n_padded,
+                                                              const long long* __restrict__ off,
+                                                              const float* __restrict__ raw, float* __restrict__ thr,
+                                                              int* __restrict__ cnt, float4* __restrict__ lvl,
+                                                              uint2* __restrict__ cinfo) {
   const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (q >= n_padded) return;
@@ -193,45 +260,9 @@ __global__ void __launch_bounds__(256) pos_thresholds_sorted_kernel(
     }
     return;
   }
-  const int first = seg_lo[q], len = seg_len[q], qi = s_i[q];
+  const int np = npos[q];
   const long long o = off[q];
-  const uint4* qh = reinterpret_cast<const uint4*>(hi + (long long)q * d_pad);
-  const uint4* ql = lo ? reinterpret_cast<const uint4*>(lo + (long long)q * d_pad) : nullptr;
-  const int nvec = d_pad >> 3;
-  int np = 0;
-  for (int m = 0; m < len; ++m) {
-    const int j = first + m;
-    if (s_i[j] == qi) continue;  // self / id collision
-    const uint4* ch = reinterpret_cast<const uint4*>(hi + (long long)j * d_pad);
-    const uint4* cl = lo ? reinterpret_cast<const uint4*>(lo + (long long)j * d_pad) : nullptr;
-    float acc = 0.f;
-    for (int v = lane; v < nvec; v += 32) {
-      const uint4 a = qh[v], b = ch[v];
-      const __half2* a2 = reinterpret_cast<const __half2*>(&a);
-      const __half2* b2 = reinterpret_cast<const __half2*>(&b);
-      uint4 al = make_uint4(0, 0, 0, 0), bl = make_uint4(0, 0, 0, 0);
-      if (ql) { al = ql[v]; bl = cl[v]; }
-      const __half2* al2 = reinterpret_cast<const __half2*>(&al);
-      const __half2* bl2 = reinterpret_cast<const __half2*>(&bl);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 fa = __half22float2(a2[e]), fb = __half22float2(b2[e]);
-        acc = fmaf(fa.x, fb.x, acc);
-        acc = fmaf(fa.y, fb.y, acc);
-        if (ql) {
-          const float2 fal = __half22float2(al2[e]), fbl = __half22float2(bl2[e]);
-          acc = fmaf(fa.x, fbl.x, acc);
-          acc = fmaf(fa.y, fbl.y, acc);
-          acc = fmaf(fal.x, fb.x, acc);
-          acc = fmaf(fal.y, fb.y, acc);
-        }
-      }
-    }
-    acc = warp_sum(acc);
-    if (lane == 0) raw[o + np] = acc;
-    ++np;
-  }
-  __syncwarp();
+  // rank sort ascending: position = #{f : v_f < v_e or (v_f == v_e and f < e)}
   for (int e = lane; e < np; e += 32) {
     const float ve = raw[o + e];
     int r = 0;
@@ -262,9 +293,9 @@ __global__ void __launch_bounds__(256) ap_reduce_kernel(const unsigned int* __re
                                                         const int* __restrict__ perm = nullptr) {
   const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
-  if (q >= nq) return;
-  const int P = cnt[q];
-  const unsigned int* h = hist + off[q];
+  const bool live = q < nq;  // (no early return: the block reduces the running sums together)
+  const int P = live ? cnt[q] : 0;
+  const unsigned int* h = hist + (live ? off[q] : 0);
   float acc = 0.f;
   unsigned int carry = 0;  // negatives above everything processed so far (higher r)
   float first_rank = 0.f;
@@ -287,17 +318,32 @@ __global__ void __launch_bounds__(256) ap_reduce_kernel(const unsigned int* __re
   }
   acc = warp_sum(acc);
   first_rank = warp_max(first_rank);
-  if (lane == 0) {
+  double s_ap = 0.0, s_r1 = 0.0, s_n = 0.0;
+  if (lane == 0 && live) {
     const float a = P > 0 ? acc / (float)P : __int_as_float(0x7fc00000);
     const float f = P > 0 ? first_rank : __int_as_float(0x7fc00000);
     const int dst = perm ? perm[q] : q;  // sorted space -> the caller's row order
     ap[dst] = a;
     r1[dst] = f;
     if (P > 0) {
-      atomicAdd(&sums[0], (double)a);
-      atomicAdd(&sums[1], (double)f);
-      atomicAdd(&sums[2], 1.0);
+      s_ap = (double)a;
+      s_r1 = (double)f;
+      s_n = 1.0;
     }
+  }
+  // running sums for MAP / MR1: one atomic triple per block, not per query (same-address atomics serialise)
+  __shared__ double part[3][8];
+  const int w = (int)(threadIdx.x >> 5);
+  if (lane == 0) {
+    part[0][w] = s_ap;
+    part[1][w] = s_r1;
+    part[2][w] = s_n;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += part[threadIdx.x][k];
+    if (t != 0.0) atomicAdd(&sums[threadIdx.x], t);
   }
 }
 

@@ -301,7 +301,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
     int cs = 0;
     uint32_t cphase = 0;
     while (true) {
-      ptx::mbar_wait(&unit_full[us], uphase);
+      ptx::mbar_wait_warp(&unit_full[us], uphase);
       const int u = unit_slot[us];
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&unit_empty[us]);
@@ -327,11 +327,11 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       Epi::row_begin(ep, rs, row, part, shape, ctx);
       for (int t = t0; t < t1; ++t) {
         if constexpr (kColSlots > 0) {
-          ptx::mbar_wait(&col_full[cs], cphase);
+          ptx::mbar_wait_warp(&col_full[cs], cphase);
           ctx.col_slot = col_slots + cs * CS::kBytes;
         }
         Epi::tile_begin(ep, rs, shape, ctx, t);
-        ptx::mbar_wait(&tmem_full[acc], acc_phase);
+        ptx::mbar_wait_warp(&tmem_full[acc], acc_phase);
         ptx::tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN);
 #pragma unroll 1

@@ -44,6 +44,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#ifdef WEALY_WAIT_HINT_NS
+  // suspend-time hint: the hardware parks the thread until the phase completes or the hint expires
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)WEALY_WAIT_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n"
       ".reg .pred P;\n"
@@ -53,6 +65,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+#endif
   return ok != 0;
 }
 
@@ -68,19 +81,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   int polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    // a warp that keeps polling steals issue slots from the warps it is waiting for: back off after a few
-    // tries (the wake-up granularity this adds is far below one pipeline stage)
-#ifdef WEALY_WAIT_BACKOFF
-    if (++polls > 4) __nanosleep(polls > 64 ? 256 : 32);
-#else
-    ++polls;
-#endif
-    if ((polls & 63) == 0 && clock64() - t0 > WEALY_DEADLOCK_CYCLES) {
+    if ((++polls & 63) == 0 && clock64() - t0 > WEALY_DEADLOCK_CYCLES) {
       printf("wealy: mbarrier deadlock block=%d thread=%d bar=0x%x parity=%u\n", (int)blockIdx.x,
              (int)threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
+}
+
+// The same for a whole warp: one lane polls, the others wait at the warp barrier (32x fewer polling lanes)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+#ifdef WEALY_WAIT_LANE0
+  if (lane_id() == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  mbar_wait(bar, parity);
+#endif
 }
 
 // barrier among a subset of the CTA's warps (id 0 is __syncthreads)
