@@ -295,7 +295,7 @@ def run_gpu_arm(args):
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "gemm_kernel<EvalEpiSym> (symmetric tcgen05 similarity sweep + mask + rank-count epilogue)",
+        "kernel": "gemm_kernel<EvalSymEpi> (symmetric tcgen05 similarity sweep over clique-sorted rows + mask + rank-count epilogue)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": traffic,
         "peak_kind": f"{peaks['_source']} dense bf16/fp16 cuBLAS, sustained (kernel timed inside a long step); "
@@ -350,7 +350,7 @@ def run_gpu_arm(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms, "api": ("wealy_b200.evaluation.evaluate" if world == 1 else "wealy_b200.dist.evaluate_all_vs_all")
                        + " (host pinned tensors in, host out)"},
-        "gpu_launches": 4 * args.steps,   # prep, pos_thresholds, fused sweep, ap_reduce per step
+        "gpu_launches": 5 * args.steps,   # prep, pos_pairs, pos_sort, fused sweep, ap_reduce per step
         "roofline": roofline,
     }
     if cpu is not None:

@@ -13,4 +13,4 @@ $CMD2 > gpurun_out/plain3.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 4 -c 1 -o gpurun_out/prof_fp16 $CMD2 > gpurun_out/ncu_full2.log 2>&1
 echo "full2 rc=$?"
 tail -2 gpurun_out/plain.log gpurun_out/plain3.log
-ls -la gpurun_out
+ls -la gpurun_out | tail -12
