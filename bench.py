@@ -135,7 +135,7 @@ def run_reference_arm(args):
         return
     from wealy_b200.data import synth
     world = args.gpus
-    n_total = int(round(BASE_N * (world ** 0.5)))
+    n_total = int(args.tracks) if args.tracks else int(round(BASE_N * (world ** 0.5)))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     s = synth.make_eval_set(n_total, DIM, seed=0, md5_ids=False)
@@ -188,7 +188,7 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n_total = int(round(BASE_N * (world ** 0.5)))
+    n_total = int(args.tracks) if args.tracks else int(round(BASE_N * (world ** 0.5)))
     lo, hi = wd.shard_range(n_total, rank, world)
     s = synth.make_eval_set(n_total, DIM, seed=0, device=dev, md5_ids=False)
     z, c, i = s["z"], s["c"], s["i"]
@@ -235,7 +235,8 @@ def run_gpu_arm(args):
 
     # ---- e2e: public API with HOST pinned buffers, copies + plan build + result read every step
     z_h, c_h, i_h = z.cpu().pin_memory(), c.cpu().pin_memory(), i.cpu().pin_memory()
-    h2d = z_h.numel() * 4 + c_h.numel() * 8 + i_h.numel() * 8      # every rank uploads the (replicated) corpus
+    # per rank: its 1/world slice of the embeddings (replicated afterwards by one NVLink all-gather) + all ids
+    h2d = -(-n_total // world) * DIM * 4 + c_h.numel() * 8 + i_h.numel() * 8
     aps_h = torch.empty(n_total, dtype=torch.float32).pin_memory()
     r1s_h = torch.empty(n_total, dtype=torch.float32).pin_memory()
     d2h = 2 * n_total * 4
@@ -368,6 +369,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tracks", type=int, default=0,
+                    help="override the corpus size (e.g. 500000 = BASELINE configs[2] on 8 GPUs); default: 100000 * sqrt(gpus)")
     ap.add_argument("--precision", default=os.environ.get("WEALY_PRECISION", "fp16x3"), choices=["fp16x3", "fp16"])
     ap.add_argument("--cpu-queries", type=int, default=512, help="queries in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -70,7 +70,10 @@ def _worker(rank, world, port, n, ret):
         m, r1, cnt = wd.merge_sums(sums)
         aps = wd.gather_rows(full_ap[lo:hi].clone(), n)
         tk = wd.gather_rows(torch.arange(lo, hi)[:, None].repeat(1, 3), n)
-        ok = (cnt == n and abs(m - float(full_ap.double().mean())) < 1e-12
+        # sharded upload: every rank contributes its 1/world slice of the rows, all ranks end with the full matrix
+        zfull = torch.arange(n * 5, dtype=torch.float32).reshape(n, 5)
+        zup = wd.upload_sharded(zfull, torch.device("cpu"))
+        ok = (torch.equal(zup, zfull) and cnt == n and abs(m - float(full_ap.double().mean())) < 1e-12
               and abs(r1 - float(full_r1.double().mean())) < 1e-9
               and torch.equal(aps, full_ap) and torch.equal(tk[:, 0], torch.arange(n)))
         ret[rank] = bool(ok)
