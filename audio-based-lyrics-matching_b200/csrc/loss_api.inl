@@ -22,7 +22,8 @@ struct LossWs {
   size_t bytes;
 };
 
-static void loss_ws_layout(LossWs& w, uint8_t* base, int64_t b, int64_t d, int passes) {
+static void loss_ws_layout(LossWs& w, uint8_t* base, int64_t b, int64_t d, int passes, int64_t nb = -1) {
+  if (nb < 0) nb = b;  // anchors owned by this rank (data-parallel: b is the global batch)
   uint8_t* cur = base;
   w.b_pad = pad_k(b);
   carve_planes(w.u, cur, b, d, passes);
@@ -30,15 +31,15 @@ static void loss_ws_layout(LossWs& w, uint8_t* base, int64_t b, int64_t d, int p
   w.ut_hi = reinterpret_cast<__half*>(cur); cur += tplane;
   w.ut_lo = nullptr;
   if (passes == 3) { w.ut_lo = reinterpret_cast<__half*>(cur); cur += tplane; }
-  const size_t wplane = align_up((size_t)b * w.b_pad * 2, 1024);
+  const size_t wplane = align_up((size_t)nb * w.b_pad * 2, 1024);
   w.w_hi = reinterpret_cast<__half*>(cur); cur += wplane;
   w.w_lo = nullptr;
   if (passes == 3) { w.w_lo = reinterpret_cast<__half*>(cur); cur += wplane; }
-  w.du = reinterpret_cast<float*>(cur); cur += align_up((size_t)b * d * 4, 1024);
+  w.du = reinterpret_cast<float*>(cur); cur += align_up((size_t)nb * d * 4, 1024);
   w.label = reinterpret_cast<int*>(cur); cur += align_up((size_t)b * 4, 256);
   w.idx = reinterpret_cast<int*>(cur); cur += align_up((size_t)b * 4, 256);
   w.parts_max = (int)ceil_div(b, kTileN) * 2;
-  w.partial = reinterpret_cast<float*>(cur); cur += align_up((size_t)w.parts_max * b * kStatWidth * 4, 1024);
+  w.partial = reinterpret_cast<float*>(cur); cur += align_up((size_t)w.parts_max * nb * kStatWidth * 4, 1024);
   w.rowstat = reinterpret_cast<float*>(cur); cur += align_up((size_t)b * 16, 256);
   w.zs = reinterpret_cast<ZStats*>(cur); cur += 256;
   w.scal = reinterpret_cast<float*>(cur); cur += 256;
@@ -48,29 +49,38 @@ static void loss_ws_layout(LossWs& w, uint8_t* base, int64_t b, int64_t d, int p
   w.bytes = (size_t)(cur - base);
 }
 
-extern "C" size_t wealy_loss_workspace_bytes(int64_t b, int64_t d, int passes) {
-  if (b <= 0 || d <= 0) return 0;
+static size_t loss_ws_bytes(int64_t b, int64_t d, int passes, int64_t nb) {
+  if (b <= 0 || d <= 0 || nb < 0 || nb > b) return 0;
   LossWs w;
-  loss_ws_layout(w, reinterpret_cast<uint8_t*>(uintptr_t(1024)), b, d, passes);
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(uintptr_t(1024)), b, d, passes, nb);
   return w.bytes + 1024;
 }
 
-static int loss_check(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t d, void* ws, size_t ws_bytes) {
+extern "C" size_t wealy_loss_workspace_bytes(int64_t b, int64_t d, int passes) { return loss_ws_bytes(b, d, passes, b); }
+extern "C" size_t wealy_loss_dp_workspace_bytes(int64_t b_global, int64_t d, int passes, int64_t nb) {
+  return loss_ws_bytes(b_global, d, passes, nb);
+}
+
+static int loss_check(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t d, void* ws, size_t ws_bytes,
+                      int64_t row0, int64_t nb) {
   if (!cfg || !z || !ws) return fail(WEALY_ERR_BAD_ARG, "null pointer");
   if (cfg->kind != WEALY_LOSS_NTXENT && cfg->kind != WEALY_LOSS_CLEWS) return fail(WEALY_ERR_BAD_ARG, "unknown loss kind %d", cfg->kind);
   if (cfg->passes != 1 && cfg->passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
   if (b <= 0 || d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad shape b=%lld d=%lld", (long long)b, (long long)d);
+  if (row0 < 0 || nb <= 0 || row0 + nb > b) return fail(WEALY_ERR_BAD_ARG, "bad shard [%lld, +%lld) of %lld", (long long)row0, (long long)nb, (long long)b);
   if (b >= (1 << 24)) return fail(WEALY_ERR_UNSUPPORTED, "batch too large");
-  if (ws_bytes < wealy_loss_workspace_bytes(b, d, cfg->passes))
-    return fail(WEALY_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, wealy_loss_workspace_bytes(b, d, cfg->passes));
+  if (ws_bytes < loss_ws_bytes(b, d, cfg->passes, nb))
+    return fail(WEALY_ERR_WORKSPACE, "workspace too small: %zu < %zu", ws_bytes, loss_ws_bytes(b, d, cfg->passes, nb));
   return WEALY_OK;
 }
 
-static void loss_params(LossParams& lp, const wealy_loss_cfg* cfg, const LossWs& w, int64_t b) {
+static void loss_params(LossParams& lp, const wealy_loss_cfg* cfg, const LossWs& w, int64_t b, int64_t row0, int64_t nb) {
   memset(&lp, 0, sizeof(lp));
   const float log2e = 1.4426950408889634f;
   lp.kind = cfg->kind;
   lp.b = (int)b;
+  lp.row0 = (int)row0;
+  lp.nb = (int)nb;
   lp.label = w.label;
   lp.idx = w.idx;
   lp.c2 = log2e / cfg->temperature;
@@ -83,31 +93,7 @@ static void loss_params(LossParams& lp, const wealy_loss_cfg* cfg, const LossWs&
   lp.ldw = w.b_pad;
 }
 
-extern "C" int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
-                                  const int64_t* z_label, const int64_t* z_idx, double* out, void* workspace,
-                                  size_t workspace_bytes, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  W_TRY(loss_check(cfg, z, b, d, workspace, workspace_bytes));
-  if (!z_label || !z_idx || !out) return fail(WEALY_ERR_BAD_ARG, "null pointer");
-  LossWs w;
-  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes);
-  const int T = 256;
-  CU_TRY(cudaMemsetAsync(w.zs, 0, 1280, s));  // ZStats, scal, flags, batch accumulators
-  CU_TRY(cudaMemsetAsync(out, 0, WEALY_OUT_COUNT * sizeof(double), s));
-  ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, w.label, (int)b, w.bad);
-  ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_idx, w.idx, (int)b, w.bad);
-  CU_TRY(cudaGetLastError());
-  const bool ntx = cfg->kind == WEALY_LOSS_NTXENT;
-  // NT-Xent: x/(|x|+1e-6) and statistics of the raw z; CLEWS: F.normalize (eps 1e-12), statistics of the normalised z
-  W_TRY(launch_prep(z, ldz, b, d, dtype, ntx ? kPrepL2AddEps : kPrepL2Clamp, ntx ? 1e-6f : 1e-12f, w.u, nullptr,
-                    nullptr, 0, w.zs, ntx ? 0 : 1, s));
-  LossParams lp;
-  loss_params(lp, cfg, w, b);
-  GemmShape sh;
-  fill_shape(sh, b, b, w.u.d_pad, 64, w.parts_max / 2);
-  const int halves = 2;  // epilogue warps per TMEM lane quadrant
-  const int parts = sh.n_col_chunks * halves;
-  W_TRY(launch_gemm<LossStatsEpi>(cfg->passes, w.u, w.u, sh, lp, s));
+static LossCfgDev loss_cfg_dev(const wealy_loss_cfg* cfg) {
   LossCfgDev dc;
   dc.kind = cfg->kind;
   dc.temperature = cfg->temperature;
@@ -117,28 +103,81 @@ extern "C" int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int6
   dc.epsilon = cfg->epsilon;
   dc.uw = cfg->uw;
   dc.numerically_friendly = cfg->numerically_friendly;
-  const unsigned fb = (unsigned)ceil_div(b, 256);
-  loss_merge_kernel<<<fb, 256, 0, s>>>(dc, (int)b, parts, w.partial, w.rowstat, w.acc, w.acc_max);
-  loss_finish_kernel<<<fb, 256, 0, s>>>(dc, (int)b, (int)d, w.acc, w.acc_max, w.zs, w.rowstat, w.scal, out);
+  return dc;
+}
+
+// The operand planes of the A side of a sharded launch: the anchors [row0, row0 + nb) of the global planes.
+static Planes plane_rows(const Planes& p, int64_t row0, int64_t nb) {
+  Planes q = p;
+  q.hi = p.hi + row0 * p.d_pad;
+  q.lo = p.lo ? p.lo + row0 * p.d_pad : nullptr;
+  q.norm = p.norm + row0;
+  q.scale = p.scale + row0;
+  q.sq = p.sq + row0;
+  q.rows = nb;
+  return q;
+}
+
+// forward, part 1 (everything before the batch-wide sums are known): ids, prep of ALL rows, statistics sweep of the
+// anchors [row0, row0 + nb) against all b columns, per-anchor merge -> rowstat[row0 .. row0 + nb), partial sums in acc
+static int loss_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
+                              const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb, void* workspace,
+                              size_t workspace_bytes, cudaStream_t s) {
+  W_TRY(loss_check(cfg, z, b, d, workspace, workspace_bytes, row0, nb));
+  if (!z_label || !z_idx) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  LossWs w;
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes, nb);
+  const int T = 256;
+  CU_TRY(cudaMemsetAsync(w.zs, 0, 1280, s));  // ZStats, scal, flags, batch accumulators
+  ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, w.label, (int)b, w.bad);
+  ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_idx, w.idx, (int)b, w.bad);
+  CU_TRY(cudaGetLastError());
+  const bool ntx = cfg->kind == WEALY_LOSS_NTXENT;
+  // NT-Xent: x/(|x|+1e-6) and statistics of the raw z; CLEWS: F.normalize (eps 1e-12), statistics of the normalised z
+  W_TRY(launch_prep(z, ldz, b, d, dtype, ntx ? kPrepL2AddEps : kPrepL2Clamp, ntx ? 1e-6f : 1e-12f, w.u, nullptr,
+                    nullptr, 0, w.zs, ntx ? 0 : 1, s));
+  LossParams lp;
+  loss_params(lp, cfg, w, b, row0, nb);
+  GemmShape sh;
+  fill_shape(sh, nb, b, w.u.d_pad, 64, w.parts_max / 2);
+  const int halves = 2;  // epilogue warps per TMEM lane quadrant
+  const int parts = sh.n_col_chunks * halves;
+  W_TRY(launch_gemm<LossStatsEpi>(cfg->passes, plane_rows(w.u, row0, nb), w.u, sh, lp, s));
+  loss_merge_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, s>>>(loss_cfg_dev(cfg), (int)nb, (int)b, parts, w.partial,
+                                                                w.rowstat + row0 * 4, w.acc, w.acc_max);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
 }
 
-extern "C" int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
-                                   const float* grad_out, void* dz, int64_t ld_dz, void* workspace,
-                                   size_t workspace_bytes, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  W_TRY(loss_check(cfg, z, b, d, workspace, workspace_bytes));
+// forward, part 2: batch sums (acc, acc_max) and the per-anchor records (rowstat) of ALL b anchors are in the
+// workspace (summed / gathered over the ranks by the caller when the batch is sharded) -> loss, logdict, coefficients
+static int loss_forward_finish(const wealy_loss_cfg* cfg, int64_t b, int64_t d, int64_t nb, double* out, void* workspace,
+                               cudaStream_t s) {
+  LossWs w;
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes, nb);
+  CU_TRY(cudaMemsetAsync(out, 0, WEALY_OUT_COUNT * sizeof(double), s));
+  loss_finish_kernel<<<(unsigned)ceil_div(b, 256), 256, 0, s>>>(loss_cfg_dev(cfg), (int)b, (int)d, w.acc, w.acc_max, w.zs,
+                                                                w.rowstat, w.scal, out);
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+// backward of the anchors [row0, row0 + nb): dz rows of this shard (complete: W is symmetrised, so the terms in
+// which these rows act as columns of other ranks' anchors are included -- no reduce-scatter)
+static int loss_backward_rows(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
+                              int64_t row0, int64_t nb, const float* grad_out, void* dz, int64_t ld_dz, void* workspace,
+                              size_t workspace_bytes, cudaStream_t s) {
+  W_TRY(loss_check(cfg, z, b, d, workspace, workspace_bytes, row0, nb));
   if (!dz) return fail(WEALY_ERR_BAD_ARG, "null pointer");
   LossWs w;
-  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes);
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes, nb);
   LossParams lp;
-  loss_params(lp, cfg, w, b);
-  // 1) W' = scale * (dL/dS + (dL/dS)^T): recompute S tile by tile, store fp16 hi/lo planes
+  loss_params(lp, cfg, w, b, row0, nb);
+  // 1) W' = scale * (dL/dS + (dL/dS)^T) for this shard's rows: recompute S tile by tile, store fp16 hi/lo planes
   GemmShape sh;
-  fill_shape(sh, b, b, w.u.d_pad, 64, 1 << 20);
-  W_TRY(launch_gemm<LossWEpi>(cfg->passes, w.u, w.u, sh, lp, s));
-  // 2) dU = W' * U   (A = W' [b][b_pad], B = U^T [d][b_pad], K = b_pad); the transposed planes are only
+  fill_shape(sh, nb, b, w.u.d_pad, 64, 1 << 20);
+  W_TRY(launch_gemm<LossWEpi>(cfg->passes, plane_rows(w.u, row0, nb), w.u, sh, lp, s));
+  // 2) dU = W' * U   (A = W' [nb][b_pad], B = U^T [d][b_pad], K = b_pad); the transposed planes are only
   //    needed here, so they are built now (tiled transpose, zero k-padding) rather than in the forward
   {
     dim3 grid((unsigned)ceil_div(w.b_pad, 32), (unsigned)ceil_div(d, 32), w.u.lo ? 2 : 1);
@@ -147,7 +186,7 @@ extern "C" int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int
     CU_TRY(cudaGetLastError());
   }
   Planes pw, put;
-  pw.hi = w.w_hi; pw.lo = w.w_lo; pw.rows = b; pw.d_pad = w.b_pad;
+  pw.hi = w.w_hi; pw.lo = w.w_lo; pw.rows = nb; pw.d_pad = w.b_pad;
   put.hi = w.ut_hi; put.lo = w.ut_lo; put.rows = d; put.d_pad = w.b_pad;
   StoreParams sp;
   memset(&sp, 0, sizeof(sp));
@@ -157,27 +196,84 @@ extern "C" int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int
   sp.out_dtype = kOutF32;
   sp.post = 1.f;
   GemmShape sh2;
-  fill_shape(sh2, b, d, w.b_pad, 64, 1 << 20);
+  fill_shape(sh2, nb, d, w.b_pad, 64, 1 << 20);
   W_TRY(launch_gemm<StoreEpi>(cfg->passes, pw, put, sh2, sp, s));
   // 3) normalisation Jacobian, upstream gradient, 1/(B tau) or 1/H
   const int T = 256;
-  const unsigned blocks = (unsigned)ceil_div(b * 32, T);
+  const unsigned blocks = (unsigned)ceil_div(nb * 32, T);
+  const size_t esz = dtype == WEALY_F32 ? 4 : 2;
+  const void* zrow = static_cast<const uint8_t*>(z) + (size_t)row0 * ldz * esz;
   switch (dtype) {
     case WEALY_F32:
-      loss_jacobian_kernel<float><<<blocks, T, 0, s>>>(cfg->kind, (const float*)z, (long long)ldz, (int)b, (int)d, w.u.norm,
-                                                       w.du, w.scal, grad_out, (float*)dz, (long long)ld_dz);
+      loss_jacobian_kernel<float><<<blocks, T, 0, s>>>(cfg->kind, (const float*)zrow, (long long)ldz, (int)nb, (int)d,
+                                                       w.u.norm + row0, w.du, w.scal, grad_out, (float*)dz, (long long)ld_dz);
       break;
     case WEALY_F16:
-      loss_jacobian_kernel<__half><<<blocks, T, 0, s>>>(cfg->kind, (const __half*)z, (long long)ldz, (int)b, (int)d,
-                                                        w.u.norm, w.du, w.scal, grad_out, (__half*)dz, (long long)ld_dz);
+      loss_jacobian_kernel<__half><<<blocks, T, 0, s>>>(cfg->kind, (const __half*)zrow, (long long)ldz, (int)nb, (int)d,
+                                                        w.u.norm + row0, w.du, w.scal, grad_out, (__half*)dz, (long long)ld_dz);
       break;
     case WEALY_BF16:
-      loss_jacobian_kernel<__nv_bfloat16><<<blocks, T, 0, s>>>(cfg->kind, (const __nv_bfloat16*)z, (long long)ldz, (int)b,
-                                                               (int)d, w.u.norm, w.du, w.scal, grad_out,
+      loss_jacobian_kernel<__nv_bfloat16><<<blocks, T, 0, s>>>(cfg->kind, (const __nv_bfloat16*)zrow, (long long)ldz, (int)nb,
+                                                               (int)d, w.u.norm + row0, w.du, w.scal, grad_out,
                                                                (__nv_bfloat16*)dz, (long long)ld_dz);
       break;
     default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
   }
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
+}
+
+// ---- single GPU: the whole batch is one shard
+extern "C" int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
+                                  const int64_t* z_label, const int64_t* z_idx, double* out, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  if (!out) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  W_TRY(loss_forward_local(cfg, z, b, ldz, d, dtype, z_label, z_idx, 0, b, workspace, workspace_bytes, (cudaStream_t)stream));
+  return loss_forward_finish(cfg, b, d, b, out, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
+                                   const float* grad_out, void* dz, int64_t ld_dz, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  return loss_backward_rows(cfg, z, b, ldz, d, dtype, 0, b, grad_out, dz, ld_dz, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+}
+
+// ---- data parallel: z / labels / ids are the GLOBAL batch (all-gathered by the caller), this
+// rank owns the anchors [row0, row0 + nb).  Between _local and _finish the caller sums `acc` (count_acc doubles, SUM)
+// and `acc_max` (2 x uint32, MAX) over the ranks and all-gathers `rowstat` (4 floats per anchor, rank r's rows at
+// [row0_r, row0_r + nb_r)): see wealy_loss_dp_buffers.
+extern "C" int wealy_loss_dp_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d,
+                                           int dtype, const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+  return loss_forward_local(cfg, z, b_global, ldz, d, dtype, z_label, z_idx, row0, nb, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int wealy_loss_dp_buffers(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global,
+                                     int64_t d, int64_t nb, double** acc, int64_t* count_acc, uint32_t** acc_max,
+                                     float** rowstat) {
+  if (!cfg || !workspace || !acc || !count_acc || !acc_max || !rowstat) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (workspace_bytes < loss_ws_bytes(b_global, d, cfg->passes, nb)) return fail(WEALY_ERR_WORKSPACE, "workspace too small");
+  LossWs w;
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b_global, d, cfg->passes, nb);
+  *acc = w.acc;
+  *count_acc = kAccCount;
+  *acc_max = w.acc_max;
+  *rowstat = w.rowstat;
+  return WEALY_OK;
+}
+
+extern "C" int wealy_loss_dp_forward_finish(const wealy_loss_cfg* cfg, int64_t b_global, int64_t d, int64_t nb, double* out,
+                                            void* workspace, size_t workspace_bytes, void* stream) {
+  if (!cfg || !out || !workspace) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (workspace_bytes < loss_ws_bytes(b_global, d, cfg->passes, nb)) return fail(WEALY_ERR_WORKSPACE, "workspace too small");
+  return loss_forward_finish(cfg, b_global, d, nb, out, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int wealy_loss_dp_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d,
+                                      int dtype, int64_t row0, int64_t nb, const float* grad_out, void* dz_rows,
+                                      int64_t ld_dz, void* workspace, size_t workspace_bytes, void* stream) {
+  return loss_backward_rows(cfg, z, b_global, ldz, d, dtype, row0, nb, grad_out, dz_rows, ld_dz, workspace, workspace_bytes,
+                            (cudaStream_t)stream);
 }

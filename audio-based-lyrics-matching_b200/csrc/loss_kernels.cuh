@@ -24,7 +24,8 @@ constexpr int kStatWidth = 8;  // floats per (part, row) partial record
 
 struct LossParams {
   int kind;
-  int b;                // batch size
+  int b;                // (global) batch size = number of columns
+  int row0, nb;         // data-parallel sharding: this launch owns anchors [row0, row0 + nb) (0, b on one GPU)
   const int* label;     // [b]
   const int* idx;       // [b]
   float c2;             // NT-Xent: log2(e) / tau
@@ -56,9 +57,9 @@ struct LossStatsEpi {
   };
 
   __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, const EpiCtx&) {
-    st.valid = row < p.b;
-    st.lab = st.valid ? p.label[row] : 0;
-    st.id = st.valid ? p.idx[row] : 0;
+    st.valid = row < p.nb;
+    st.lab = st.valid ? p.label[p.row0 + row] : 0;
+    st.id = st.valid ? p.idx[p.row0 + row] : 0;
     st.a0 = p.kind == kLossNtxent ? neg_inf() : 0.f;
     st.a1 = st.a2 = st.a3 = st.a4 = st.a5 = 0.f;
   }
@@ -72,7 +73,7 @@ struct LossStatsEpi {
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
         const int j = col0 + e;
-        const bool ok = (j < p.b) && (j != row);  // diagonal masked by POSITION (losses.py:52-53)
+        const bool ok = (j < p.b) && (j != p.row0 + row);  // diagonal masked by POSITION (losses.py:52-53)
         l[e] = ok ? __uint_as_float(acc[e]) * p.c2 : neg_inf();
         cm = fmaxf(cm, l[e]);
       }
@@ -116,7 +117,7 @@ struct LossStatsEpi {
   __device__ static __forceinline__ void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&) {}
   __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part, const GemmShape&, const EpiCtx&) {
     if (!st.valid) return;
-    float* o = p.partial + ((long long)part * p.b + row) * kStatWidth;
+    float* o = p.partial + ((long long)part * p.nb + row) * kStatWidth;
     reinterpret_cast<float4*>(o)[0] = make_float4(st.a0, st.a1, st.a2, st.a3);
     reinterpret_cast<float4*>(o)[1] = make_float4(st.a4, st.a5, 0.f, 0.f);
   }
@@ -138,10 +139,10 @@ struct LossWEpi {
   };
 
   __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, const EpiCtx&) {
-    st.valid = row < p.b;
-    st.lab = st.valid ? p.label[row] : 0;
-    st.id = st.valid ? p.idx[row] : 0;
-    const float4 r = st.valid ? reinterpret_cast<const float4*>(p.rowstat)[row] : make_float4(0.f, 0.f, 0.f, 0.f);
+    st.valid = row < p.nb;
+    st.lab = st.valid ? p.label[p.row0 + row] : 0;
+    st.id = st.valid ? p.idx[p.row0 + row] : 0;
+    const float4 r = st.valid ? reinterpret_cast<const float4*>(p.rowstat)[p.row0 + row] : make_float4(0.f, 0.f, 0.f, 0.f);
     st.r0 = r.x;
     st.r1 = r.y;
     st.r2 = r.z;
@@ -156,7 +157,7 @@ struct LossWEpi {
     for (int e = 0; e < 32; ++e) {
       const int j = col0 + e;
       float w = 0.f;
-      if (j < p.b && j != row) {
+      if (j < p.b && j != p.row0 + row) {
         const float s = __uint_as_float(acc[e]);
         const float4 cj = __ldg(reinterpret_cast<const float4*>(p.rowstat) + j);
         const bool same = __ldg(p.label + j) == st.lab;
@@ -224,7 +225,8 @@ __device__ __forceinline__ void block_add(double v, double* target) {
   }
 }
 
-__global__ void __launch_bounds__(256) loss_merge_kernel(LossCfgDev cfg, int b, int parts,
+// b = anchors of this launch (rowstat already points at the first of them), bg = global batch size
+__global__ void __launch_bounds__(256) loss_merge_kernel(LossCfgDev cfg, int b, int bg, int parts,
                                                          const float* __restrict__ partial, float* __restrict__ rowstat,
                                                          double* __restrict__ acc, unsigned int* __restrict__ acc_max) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(256) loss_merge_kernel(LossCfgDev cfg, int b, 
       t_uni = lu; t_np = np; t_nn = nn; t_pd = pd; t_ad = ad; t_nd = nd;
       // true coefficients: dS_ij = -pos ca_i + X_ij neg cu_i, ca_i = 1/(npos_i H) (H known in the finish kernel)
       const float outer = cfg.numerically_friendly ? 1.f / (1.f + uni) : 1.f / (uni + cfg.epsilon);
-      const float cu = nn > 0.f ? (float)((double)cfg.uw * (double)cfg.gamma / ((double)b * (double)nn)) * outer : 0.f;
+      const float cu = nn > 0.f ? (float)((double)cfg.uw * (double)cfg.gamma / ((double)bg * (double)nn)) * outer : 0.f;
       // X_ij <= e^b and X_ij <= sum_j X_ij neg_ij = nneg_i uni_i: rows with a vanishing uniformity term
       // (huge 1/(uni+eps) in the non-friendly branch) must not dictate the fp16 scale of W
       m_inv_np = np > 0.f ? 1.f / np : 0.f;

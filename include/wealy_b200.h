@@ -184,6 +184,27 @@ int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int
                         const float* grad_out, void* dz, int64_t ld_dz, void* workspace, size_t workspace_bytes,
                         void* stream);
 
+/* ---- f2: data-parallel losses (global-batch NT-Xent / CLEWS over the GPUs of one box; not in the reference, which is
+ * single-process -- SURVEY.md section 8(f)).  z / z_label / z_idx are the GLOBAL batch [b_global] (all-gathered by the
+ * caller over NCCL), this rank owns the anchors [row0, row0 + nb).
+ *   1. wealy_loss_dp_forward_local : prep of all rows, statistics sweep of this rank's anchors against all columns
+ *   2. caller: all-reduce `acc` (count_acc doubles, SUM) and `acc_max` (2 x uint32, MAX), all-gather `rowstat`
+ *      (4 floats per anchor; this rank wrote rows [row0, row0 + nb)) -- pointers from wealy_loss_dp_buffers
+ *   3. wealy_loss_dp_forward_finish: loss terms + logdict statistics of the GLOBAL batch into `out` (same on all ranks)
+ *   4. wealy_loss_dp_backward      : dz_rows [nb][d] = d(global loss)/dz of this rank's rows -- complete (the
+ *      symmetrised dL/dS carries the terms in which these rows are columns of other ranks' anchors): no reduce-scatter. */
+size_t wealy_loss_dp_workspace_bytes(int64_t b_global, int64_t d, int passes, int64_t nb);
+int wealy_loss_dp_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d,
+                                int dtype, const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb,
+                                void* workspace, size_t workspace_bytes, void* stream);
+int wealy_loss_dp_buffers(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global, int64_t d,
+                          int64_t nb, double** acc, int64_t* count_acc, uint32_t** acc_max, float** rowstat);
+int wealy_loss_dp_forward_finish(const wealy_loss_cfg* cfg, int64_t b_global, int64_t d, int64_t nb, double* out,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int wealy_loss_dp_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d, int dtype,
+                           int64_t row0, int64_t nb, const float* grad_out, void* dz_rows, int64_t ld_dz, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

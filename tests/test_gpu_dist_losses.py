@@ -1,0 +1,124 @@
+"""-m gpu: data-parallel (global-batch) NT-Xent / CLEWS -- SURVEY.md 8(f) row f2.
+
+* the ranks of a sharded loss emulated one after the other on ONE GPU (the collectives done by hand on the exposed
+  buffers): loss, logdict and the concatenated per-rank gradients must equal the single-GPU module on the global batch
+  and the reference's own outputs (tests/golden/losses.npz);
+* the real thing over NCCL on two GPUs when the box has them (skipped otherwise)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import losses as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfgs():
+    from wealy_b200 import _native as N
+    from wealy_b200.dist_losses import _cfg
+    return {
+        "ntx": _cfg(kind=N.LOSS_NTXENT, passes=3, temperature=0.1),
+        "clews": _cfg(kind=N.LOSS_CLEWS, passes=3, gamma=8.0, b=1.0, eps=1e-8, epsilon=1e-6, uw=0.5, numerically_friendly=1),
+    }
+
+
+def _emulated(cfg_items, z, lab, idx, bounds):
+    """Run the shards [bounds[r], bounds[r+1]) as if they were ranks; collectives by hand."""
+    from wealy_b200.dist_losses import ShardState
+    states = []
+    for r in range(len(bounds) - 1):
+        st = ShardState(cfg_items, z, lab, idx, bounds[r], bounds[r + 1] - bounds[r])
+        st.forward_local()
+        states.append(st)
+    bufs = [st.buffers() for st in states]
+    acc = sum(b[0].clone() for b in bufs)                                   # all-reduce SUM
+    accm = torch.stack([b[1] for b in bufs]).max(dim=0).values              # all-reduce MAX
+    rows = torch.cat([b[2][bounds[r]:bounds[r + 1]] for r, b in enumerate(bufs)])   # all-gather
+    outs, grads = [], []
+    for st, b in zip(states, bufs):
+        b[0].copy_(acc); b[1].copy_(accm); b[2].copy_(rows)
+        outs.append(st.forward_finish())
+        grads.append(st.backward(torch.ones((), device=z.device)))
+    torch.cuda.synchronize()
+    return outs, torch.cat(grads)
+
+
+@pytest.mark.parametrize("bounds", [[0, 256, 512], [0, 128, 256, 384, 512], [0, 100, 333, 512]])
+@pytest.mark.parametrize("kind", ["ntx", "clews"])
+def test_emulated_ranks_equal_single_gpu(kind, bounds):
+    from wealy_b200 import losses as wl
+    from wealy_b200.data import synth
+    s = synth.make_loss_batch(512, 192, seed=3, device="cuda")
+    z, lab, idx = s["z"], s["label"], s["idx"]
+    mod = wl.NTXentLoss(0.1) if kind == "ntx" else wl.CLEWSLoss()
+    zz = z.clone().requires_grad_(True)
+    loss, logd = mod(lab.clone(), idx, zz)
+    loss.backward()
+    outs, grad = _emulated(_cfgs()[kind], z, lab, idx, bounds)
+    for o in outs:
+        assert abs(float(o[0]) - float(loss)) <= 1e-6 * max(1.0, abs(float(loss)))
+        assert torch.allclose(o, outs[0])                                   # identical on every "rank"
+    assert float((grad - zz.grad).norm()) <= 2e-6 * float(zz.grad.norm())
+    # and against the oracle (autograd of the restated reference loss) on the global batch
+    zr = z.cpu().clone().requires_grad_(True)
+    lo, _ = (ol.ntxent(lab.cpu().clone(), idx.cpu(), zr) if kind == "ntx" else ol.clews(lab.cpu().clone(), idx.cpu(), zr))
+    lo.backward()
+    assert abs(float(outs[0][0]) - float(lo)) <= 1e-3 * abs(float(lo))
+    assert float((grad.cpu() - zr.grad).norm()) <= 1e-5 * float(zr.grad.norm())
+
+
+def test_emulated_ranks_against_reference_outputs(golden):
+    G = golden("losses.npz")
+    name = "f32_big"
+    z = torch.from_numpy(G[f"{name}_z"]).float().cuda()
+    lab, idx = torch.from_numpy(G[f"{name}_label"]).cuda(), torch.from_numpy(G[f"{name}_idx"]).cuda()
+    rows = torch.from_numpy(G[f"{name}_gradrows"])
+    b = z.shape[0]
+    bounds = [0, b // 4, b // 2, b]
+    for tag, kind in (("ntx", "ntx"), ("clews", "clews")):
+        outs, grad = _emulated(_cfgs()[kind], z, lab.clone(), idx, bounds)
+        ref_l = float(G[f"{name}_{tag}_loss"])
+        assert abs(float(outs[0][0]) - ref_l) <= 1e-3 * abs(ref_l)
+        ref_g = torch.from_numpy(G[f"{name}_{tag}_grad"]).double()
+        assert float((grad.cpu().double()[rows] - ref_g).norm()) <= 1e-5 * float(ref_g.norm())
+
+
+def _nccl_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from wealy_b200 import losses as wl
+        from wealy_b200.dist_losses import DistributedNTXentLoss, DistributedCLEWSLoss
+        from wealy_b200.data import synth
+        s = synth.make_loss_batch(1024, 256, seed=5, device="cuda")
+        nb = 1024 // world
+        sl = slice(rank * nb, (rank + 1) * nb)
+        ok = True
+        for single, multi in ((wl.NTXentLoss(0.1), DistributedNTXentLoss(0.1)), (wl.CLEWSLoss(), DistributedCLEWSLoss())):
+            zz = s["z"].clone().requires_grad_(True)
+            l1, d1 = single(s["label"].clone(), s["idx"], zz)
+            l1.backward()
+            zl = s["z"][sl].clone().requires_grad_(True)
+            l2, d2 = multi(s["label"][sl].clone(), s["idx"][sl].clone(), zl)
+            l2.backward()
+            torch.cuda.synchronize()
+            ok &= abs(float(l1) - float(l2)) <= 1e-6 * max(1.0, abs(float(l1)))
+            ok &= float((zl.grad - zz.grad[sl]).norm()) <= 2e-6 * float(zz.grad[sl].norm())
+            ok &= set(d1) == set(d2) and all(abs(float(d1[k]) - float(d2[k])) <= 1e-5 * max(1.0, abs(float(d1[k]))) for k in d1)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_nccl_two_ranks():
+    import torch.multiprocessing as mp
+    port = 29700 + (os.getpid() % 200)
+    ret = mp.Manager().dict()
+    mp.spawn(_nccl_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -73,7 +73,15 @@ def _worker(rank, world, port, n, ret):
         # sharded upload: every rank contributes its 1/world slice of the rows, all ranks end with the full matrix
         zfull = torch.arange(n * 5, dtype=torch.float32).reshape(n, 5)
         zup = wd.upload_sharded(zfull, torch.device("cpu"))
-        ok = (torch.equal(zup, zfull) and cnt == n and abs(m - float(full_ap.double().mean())) < 1e-12
+        # data-parallel loss: global labels in rank order, single-label noise applied to the GLOBAL batch and
+        # written back into the caller's local labels in place (lib/losses.py:34-35)
+        from wealy_b200.dist_losses import _gather_ids
+        lab_local = torch.full((6,), 3, dtype=torch.long)
+        labg, idxg = _gather_ids(lab_local, torch.arange(6) + 6 * rank, None)
+        want = torch.full((12,), 3, dtype=torch.long)
+        want[:2] = -1
+        dp_ok = torch.equal(labg, want) and torch.equal(idxg, torch.arange(12)) and torch.equal(lab_local, want[6 * rank:6 * rank + 6])
+        ok = (dp_ok and torch.equal(zup, zfull) and cnt == n and abs(m - float(full_ap.double().mean())) < 1e-12
               and abs(r1 - float(full_r1.double().mean())) < 1e-9
               and torch.equal(aps, full_ap) and torch.equal(tk[:, 0], torch.arange(n)))
         ret[rank] = bool(ok)
