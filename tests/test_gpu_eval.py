@@ -274,3 +274,50 @@ def test_full_size_properties():
     lo, hi = oev.rank_tolerance(cc[:nq], ic[:nq], zc[:nq], cc, ic, zc, gap=1e-5)
     r = r1s[:nq].double().cpu()
     assert bool(((r >= lo) & (r <= hi)).all())
+
+
+def _oracle_match(c, i, z, r1_slack=0):
+    aps_o, r1_o = oev.evaluate_argsort(c, i, z, c, i, z)
+    aps, r1s = _gpu_eval(c, i, z)
+    lo, hi = oev.rank_tolerance(c, i, z, c, i, z, gap=1e-5)
+    r = r1s.double()
+    assert bool(((r >= lo) & (r <= hi)).all())
+    assert abs(float(aps.double().mean()) - float(aps_o.mean())) <= 1e-4
+    return aps, r1s, aps_o, r1_o
+
+
+def test_symmetric_sweep_version_id_collisions_across_cliques():
+    """The clique-sorted symmetric sweep skips id tests in 'clean' tiles: pairs of DIFFERENT cliques that share a
+    version id (md5-derived 31-bit ids collide at scale, lib/embedding_dataset/utils.py:7-13) are not candidates of
+    each other and must be found by the plan wherever they fall (far from the diagonal included)."""
+    s = _synth().make_eval_set(6000, 64, seed=21, md5_ids=False)
+    c, i, z = s["c"], s["i"].clone(), s["z"].clone()
+    order = torch.argsort(c, stable=True)
+    far = [(int(order[10]), int(order[5500])), (int(order[700]), int(order[3100])), (int(order[4000]), int(order[4001 + 300]))]
+    for a, b in far:
+        assert c[a] != c[b]
+        i[b] = i[a]                       # collision between cliques
+        z[b] = z[a] * 1.5                 # ... of near-identical tracks: scoring the pair would put b at rank 1 of a
+    _, r1s, _, r1_o = _oracle_match(c, i, z)
+    for a, b in far:
+        assert float(r1s[a]) == float(r1_o[a]) and float(r1s[b]) == float(r1_o[b])
+
+
+def test_symmetric_sweep_many_equal_version_ids():
+    """More than 16 tracks with one version id (pathological input): the plan gives up on locating the colliding
+    pairs and runs every tile with id tests -- still the oracle's result."""
+    s = _synth().make_eval_set(2500, 48, seed=22, md5_ids=False)
+    c, i, z = s["c"], s["i"].clone(), s["z"]
+    i[torch.arange(0, 2500, 100)] = 123456789          # 25 tracks share a version id
+    keep = torch.ones(2500, dtype=torch.bool)
+    for q in range(2500):                              # drop queries left without a relevant candidate
+        keep[q] = bool(((c == c[q]) & (i != i[q])).any())
+    c, i, z = c[keep], i[keep], z[keep]
+    _oracle_match(c, i, z)
+
+
+@pytest.mark.parametrize("n", [127, 128, 129, 255, 257, 1000])
+def test_symmetric_sweep_ragged_sizes(n):
+    # partial row blocks / column tiles: padded rows and columns must never be scored
+    s = _synth().make_eval_set(n, 40, seed=30 + n)
+    _oracle_match(s["c"], s["i"], s["z"])
