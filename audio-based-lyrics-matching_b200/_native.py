@@ -17,6 +17,7 @@ OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_ID_RANGE = range(
 F32, F16, BF16 = 0, 1, 2
 MODE_COSSIM, MODE_COS, MODE_DOTSIM, MODE_DOT, MODE_SQEUC, MODE_EUC = range(6)
 LOSS_NTXENT, LOSS_CLEWS = 0, 1
+REDUX = {"min": 0, "max": 1, "mean": 2, "meanmin": 3, "minmean": 4}
 OUT_COUNT = 16
 
 c_i64, c_int, c_f32, c_vp, c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
@@ -38,6 +39,8 @@ SIGNATURES = {
     "wealy_eval_plan_info": (c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "wealy_eval_run": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_vp,
                                c_vp, c_vp, c_vp]),
+    "wealy_eval_run_chunked": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_int, c_int, c_int, c_vp,
+                                       c_vp, c_vp, c_vp, c_vp, c_vp]),
     "wealy_eval_sweep_shard": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_int, c_int, c_vp]),
     "wealy_eval_plan_counts": (c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64)]),
     "wealy_eval_finish": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -530,10 +530,18 @@ static int topk_capacity(int k) {
 
 // shard_world > 1: symmetric sweep restricted to the row blocks rb = shard_rank (mod shard_world); the rank
 // counts are left in the plan's histogram for the caller to sum over ranks (finish == false).
+// chunks > 1 (row f1): every track has `chunks` embeddings (rows t * chunks .. of the matrices), the kS x kS chunk
+// similarities are reduced to one per track pair inside the epilogue (redux: WEALY_REDUX_*), all ids / outputs per track.
+template <int kS>
+static int launch_eval_tracks(int passes, const Planes& a, const Planes& b, GemmShape& sh, const EvalParams& ep, cudaStream_t s) {
+  if (passes == 3) return launch_gemm_t<EvalTracksEpi<kS>, 3, 64, 8>(a, b, sh, ep, s);
+  return launch_gemm_t<EvalTracksEpi<kS>, 1, 64, 8>(a, b, sh, ep, s);
+}
+
 static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
                          int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,
                          float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, int shard_rank,
-                         int shard_world, bool finish, void* stream) {
+                         int shard_world, bool finish, void* stream, int chunks = 1, int redux = WEALY_REDUX_MIN) {
   cudaStream_t s = (cudaStream_t)stream;
   if (!p) return fail(WEALY_ERR_BAD_ARG, "null plan");
   if (!queries_z || !candidates_z) return fail(WEALY_ERR_BAD_ARG, "null pointer");
@@ -545,17 +553,32 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   if (topk > 0 && (!topk_idx || !topk_sim)) return fail(WEALY_ERR_BAD_ARG, "topk outputs are null");
   const int64_t nq = p->nq, nc = p->nc;
   const bool same = (queries_z == candidates_z && nq == nc && ld_q == ld_c);
+  if (chunks != 1 && chunks != 2 && chunks != 4 && chunks != 8 && chunks != 16)
+    return fail(WEALY_ERR_UNSUPPORTED, "chunks per track must be 1, 2, 4, 8 or 16, got %d", chunks);
+  if (redux < WEALY_REDUX_MIN || redux > WEALY_REDUX_MINMEAN) return fail(WEALY_ERR_BAD_ARG, "unknown redux %d", redux);
+  if ((nq * chunks) >= (1ll << 31) - 256 || (nc * chunks) >= (1ll << 31) - 256) return fail(WEALY_ERR_UNSUPPORTED, "more than 2^31 rows");
+  // similarity space: distance min <-> similarity max; {inner over the candidate's chunks, outer over the query's}
+  int red_inner = kRedMax, red_outer = kRedMax;
+  float red_scale = 1.f;
+  switch (redux) {
+    case WEALY_REDUX_MIN: break;
+    case WEALY_REDUX_MAX: red_inner = red_outer = kRedMin; break;
+    case WEALY_REDUX_MEAN: red_inner = red_outer = kRedSum; red_scale = 1.f / (float)(chunks * chunks); break;
+    case WEALY_REDUX_MEANMIN: red_inner = kRedMax; red_outer = kRedSum; red_scale = 1.f / (float)chunks; break;
+    case WEALY_REDUX_MINMEAN: red_inner = kRedSum; red_outer = kRedMax; red_scale = 1.f / (float)chunks; break;
+  }
 
   // Symmetric all-vs-all: queries ARE the candidates (same ids, same embeddings), no top-k.  Only the tiles
   // that reach above the diagonal are contracted (half the tensor work); every element scores both its row
   // query and its column query.  Runs in the plan's clique-sorted row order (eval_sym_epilogue.cuh).
-  const bool sym = same && p->same_ids && topk == 0 && p->total_pairs < (1ll << 31) - 8 &&
+  const bool sym = same && p->same_ids && topk == 0 && chunks == 1 && p->total_pairs < (1ll << 31) - 8 &&
                    (shard_world > 1 || env_int("WEALY_SYM", 1) != 0);
   if (shard_world > 1 && !sym)
     return fail(WEALY_ERR_BAD_ARG, "a sharded sweep needs queries == candidates (ids and embeddings) and no top-k");
 
   // operand planes (cached allocation)
-  const size_t need = planes_bytes(nq, d, passes) + (same ? 0 : planes_bytes(nc, d, passes)) + 2048;
+  const int64_t rq = nq * chunks, rc = nc * chunks;  // embedding rows
+  const size_t need = planes_bytes(rq, d, passes) + (same ? 0 : planes_bytes(rc, d, passes)) + 2048;
   if (need > p->planes_cap) {
     dev_free(p->planes_buf, s);
     p->planes_buf = nullptr;
@@ -565,11 +588,11 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   }
   uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)p->planes_buf, 1024));
   Planes pq, pc;
-  carve_planes(pq, cur, nq, d, passes);
-  if (same) pc = pq; else carve_planes(pc, cur, nc, d, passes);
-  W_TRY(launch_prep(queries_z, ld_q, nq, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s,
+  carve_planes(pq, cur, rq, d, passes);
+  if (same) pc = pq; else carve_planes(pc, cur, rc, d, passes);
+  W_TRY(launch_prep(queries_z, ld_q, rq, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s,
                     sym ? p->sorted_idx : nullptr));
-  if (!same) W_TRY(launch_prep(candidates_z, ld_c, nc, d, dtype, kPrepL2AddEps, eps, pc, nullptr, nullptr, 0, nullptr, 0, s));
+  if (!same) W_TRY(launch_prep(candidates_z, ld_c, rc, d, dtype, kPrepL2AddEps, eps, pc, nullptr, nullptr, 0, nullptr, 0, s));
 
   // K_pos: relevant similarities, sorted per query
   {
@@ -583,6 +606,12 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       const unsigned blocks = (unsigned)ceil_div(p->s_padded * 32, threads);
       pos_sort_sorted_kernel<<<blocks, threads, 0, s>>>(p->s_npos, (int)nq, (int)p->s_padded, p->s_off, p->raw, p->thr,
                                                         p->cnt, p->s_lvl, p->s_cinfo);
+    } else if (chunks > 1) {
+      const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
+      pos_thresholds_tracks_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, chunks, red_inner,
+                                                              red_outer, red_scale, p->q_i, (int)nq, p->sorted_idx,
+                                                              p->c_i, p->seg_lo, p->seg_len, p->off, p->raw, p->thr,
+                                                              p->lim, p->cnt);
     } else {
       const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
       pos_thresholds_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, p->q_i, (int)nq,
@@ -598,7 +627,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   const int halves = 2;  // two epilogue warps per TMEM lane quadrant (16 warps and 4 warps were measured no better)
   GemmShape sh;
   // top-k keeps <= 4 candidate lists per query (column chunks x epilogue warps per row)
-  fill_shape(sh, nq, nc, pq.d_pad, 64, topk > 0 ? (4 / halves) : (1 << 20), topk > 0 ? 0 : env_int("WEALY_TILES_PER_UNIT", 8));
+  fill_shape(sh, rq, rc, pq.d_pad, 64, topk > 0 ? (4 / halves) : (1 << 20), topk > 0 ? 0 : env_int("WEALY_TILES_PER_UNIT", 8));
   const int parts = sh.n_col_chunks * halves;
   const int cap = topk > 0 ? topk_capacity(topk) : 0;
 
@@ -616,6 +645,9 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   ep.topk = topk;
   ep.cap = cap;
   ep.nq_total = (int)nq;
+  ep.red_inner = red_inner;
+  ep.red_outer = red_outer;
+  ep.red_scale = red_scale;
   if (topk > 0) {
     const size_t slots = (size_t)parts * nq * cap;
     const size_t tneed = slots * 16 + (size_t)parts * nq * 4 + 1024;  // candidate lists + finalize staging
@@ -667,6 +699,14 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       else if (lv == 3) W_TRY((launch_gemm_t<EvalSymEpi<3>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
       else W_TRY((launch_gemm_t<EvalSymEpi<4>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
     }
+  } else if (chunks == 2) {
+    W_TRY(launch_eval_tracks<2>(passes, pq, pc, sh, ep, s));
+  } else if (chunks == 4) {
+    W_TRY(launch_eval_tracks<4>(passes, pq, pc, sh, ep, s));
+  } else if (chunks == 8) {
+    W_TRY(launch_eval_tracks<8>(passes, pq, pc, sh, ep, s));
+  } else if (chunks == 16) {
+    W_TRY(launch_eval_tracks<16>(passes, pq, pc, sh, ep, s));
   } else {
     W_TRY(launch_gemm<EvalEpi>(passes, pq, pc, sh, ep, s));
   }
@@ -701,6 +741,14 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
                               float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, void* stream) {
   return eval_run_impl(p, queries_z, ld_q, candidates_z, ld_c, d, dtype, eps, passes, topk, aps, r1s, sums, topk_idx,
                        topk_sim, 0, 1, true, stream);
+}
+
+extern "C" int wealy_eval_run_chunked(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
+                                      int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, int chunks,
+                                      int redux, float* aps, float* r1s, double* sums, int64_t* topk_idx, float* topk_sim,
+                                      void* stream) {
+  return eval_run_impl(p, queries_z, ld_q, candidates_z, ld_c, d, dtype, eps, passes, topk, aps, r1s, sums, topk_idx,
+                       topk_sim, 0, 1, true, stream, chunks, redux);
 }
 
 // multi-GPU all-vs-all: every rank sweeps its share of the row blocks of the SAME symmetric problem ...

@@ -210,10 +210,23 @@ struct EvalParams {
   int* cand_idx;
   int* cand_cnt;           // [parts][nq]
   int nq_total;
+  // chunked tracks: kS consecutive rows / columns are the chunks of one track; a tile's
+  // kS x kS blocks are reduced to one track-level similarity before ranking (distance_tensor_redux,
+  // lib/tensor_ops.py:288-373, in similarity space: min distance = max similarity).  All arrays above are per TRACK.
+  int red_inner, red_outer;  // kRedMax / kRedMin / kRedSum over the candidate's chunks, then over the query's
+  float red_scale;           // 1, 1/kS or 1/kS^2 (means)
 };
 
-template <int kQueueCapT, int kCachePairsT>
+enum : int { kRedMax = 0, kRedMin = 1, kRedSum = 2 };
+
+__device__ __forceinline__ float red_op(float a, float b, int op) {
+  return op == kRedMax ? fmaxf(a, b) : (op == kRedMin ? fminf(a, b) : a + b);
+}
+
+template <int kQueueCapT, int kCachePairsT, int kS = 1>
 struct EvalEpiT {
+  static_assert(kS == 1 || kS == 2 || kS == 4 || kS == 8 || kS == 16, "chunks per track: a power of two <= 16");
+  static constexpr int kGroups = 32 / kS;  // tracks per 32-row / 32-column chunk
   using Params = EvalParams;
   // Shared-memory scratch of the epilogue.
   //  * per warp, a work queue: the elements that pass the per-row limit are scattered unevenly over
@@ -262,8 +275,8 @@ struct EvalEpiT {
     return reinterpret_cast<unsigned*>(c.cta_scratch + kCachePairs * 4);
   }
   __device__ static __forceinline__ void prefetch_ids(const Params& p, RowState& st, const GemmShape& sh, int lane) {
-    const int col = st.next_col + lane;
-    const bool ok = col < sh.n_cols;
+    const int col = st.next_col / kS + lane;  // candidate (track) this lane stands for in the next chunk
+    const bool ok = lane < kGroups && col < sh.n_cols / kS;
     st.cc_next = ok ? __ldg(p.c_c + col) : 0;
     st.ci_next = ok ? __ldg(p.c_i + col) : 0;
   }
@@ -275,13 +288,15 @@ struct EvalEpiT {
     st.tau = __int_as_float(0x7f800000);
     st.qc = st.qi = st.cnt = 0;
     st.off = 0;
-    st.cbase = ((long long)part * p.nq_total + row) * p.cap;
-    if (row < sh.m_rows) {
-      st.tlim = p.lim[row];
-      st.qc = p.q_c[row];
-      st.qi = p.q_i[row];
-      st.cnt = p.cnt[row];
-      st.off = p.off[row];
+    const int q = row / kS;                                    // query (track) of this row
+    const bool own = row < sh.m_rows && (lane % kS) == 0;      // one lane per track carries its state
+    st.cbase = ((long long)part * p.nq_total + q) * p.cap;
+    if (own) {
+      st.tlim = p.lim[q];
+      st.qc = p.q_c[q];
+      st.qi = p.q_i[q];
+      st.cnt = p.cnt[q];
+      st.off = p.off[q];
       if (p.topk > 0) st.tau = __int_as_float(0xff800000);
     }
     st.lim = fminf(st.tlim, st.tau);
@@ -291,15 +306,15 @@ struct EvalEpiT {
     prefetch_ids(p, st, sh, lane);
     n_cand(ctx)[lane] = 0;
     // cooperative fill of the threshold cache (the previous unit's row_end left it flushed)
-    st.base = p.off[ctx.row_base];
-    const long long total = p.off[min(ctx.row_base + kTileM, sh.m_rows)] - st.base;
+    st.base = p.off[ctx.row_base / kS];
+    const long long total = p.off[min(ctx.row_base + kTileM, sh.m_rows) / kS] - st.base;
     st.n_cached = (int)(total < (long long)kCachePairs ? total : (long long)kCachePairs);
     float* ts = thr_s(ctx);
     unsigned* cs = cnt_s(ctx);
     for (int i = ctx.tid; i < st.n_cached; i += ctx.nthreads) ts[i] = __ldg(p.thr + st.base + i);
     for (int i = ctx.tid; i < (st.n_cached + 1) / 2; i += ctx.nthreads) cs[i] = 0u;
     const long long rel = st.off - st.base;
-    st.so = (row < sh.m_rows && rel + st.cnt <= (long long)st.n_cached) ? (int)rel : -1;
+    st.so = (own && rel + st.cnt <= (long long)st.n_cached) ? (int)rel : -1;
     ptx::named_barrier_sync(1, ctx.nthreads);
   }
 
@@ -363,7 +378,7 @@ struct EvalEpiT {
       const float tl = rtl;
       if (cand && p.topk > 0 && s > tau) {
         const int slot = atomicAdd(&ncand[L], 1);
-        const long long cb = st.cbase + (long long)(L - lane) * p.cap + slot;  // rows of a warp are consecutive
+        const long long cb = st.cbase + (long long)(L / kS - lane / kS) * p.cap + slot;  // tracks of a warp are consecutive
         p.cand_val[cb] = s;
         p.cand_idx[cb] = col0 + e;
       }
@@ -412,7 +427,7 @@ struct EvalEpiT {
     while (need) {
       const int src = __ffs(need) - 1;
       need &= need - 1;
-      const long long cb = st.cbase + (long long)(src - lane) * p.cap;
+      const long long cb = st.cbase + (long long)(src / kS - lane / kS) * p.cap;
       const int n = ncand[src];
       const float kth = p.cap <= 256   ? warp_select_topk<8>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
                         : p.cap <= 512 ? warp_select_topk_big<16>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
@@ -470,15 +485,45 @@ struct EvalEpiT {
     return __shfl_sync(0xffffffffu, incl, 31);
   }
 
+  // kS x kS blocks of the chunk -> one similarity per (query track, candidate track): first over the candidate's
+  // chunks (kS consecutive registers), then over the query's (kS adjacent lanes); entries >= kGroups are -inf
+  __device__ static __forceinline__ void reduce_tracks(const Params& p, const uint32_t (&raw)[32], uint32_t (&out)[32]) {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+      float v = __uint_as_float(raw[g * kS]);
+#pragma unroll
+      for (int b = 1; b < kS; ++b) v = red_op(v, __uint_as_float(raw[g * kS + b]), p.red_inner);
+      if (p.red_inner == kRedSum && p.red_outer != kRedSum) v *= p.red_scale;  // mean over the candidate's chunks first
+#pragma unroll
+      for (int o = 1; o < kS; o <<= 1) v = red_op(v, __shfl_xor_sync(0xffffffffu, v, o), p.red_outer);
+      if (p.red_outer == kRedSum) v *= p.red_scale;
+      out[g] = __float_as_uint(v);
+    }
+#pragma unroll
+    for (int g = kGroups; g < 32; ++g) out[g] = 0xff800000u;
+  }
+
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
                                                  const uint32_t (&acc)[32], const GemmShape& sh, const EpiCtx& ctx) {
+    if constexpr (kS > 1) {
+      uint32_t red[32];
+      reduce_tracks(p, acc, red);
+      chunk32_tracks(p, st, row, col0 / kS, red, sh, ctx);
+    } else {
+      chunk32_tracks(p, st, row, col0, acc, sh, ctx);
+    }
+  }
+
+  // col0: first candidate (track) of the chunk; acc[e] = similarity of this lane's query and candidate col0 + e
+  __device__ static __forceinline__ void chunk32_tracks(const Params& p, RowState& st, int row, int col0,
+                                                        const uint32_t (&acc)[32], const GemmShape& sh, const EpiCtx& ctx) {
     constexpr unsigned kFull = 0xffffffffu;
     const int lane = (int)ptx::lane_id();
     // ids of the 32 candidates of this chunk, one per lane, were prefetched during the previous
     // chunk; start the loads for the next one now so their L2 latency is off the critical path
     const int cc = st.cc_next, ci = st.ci_next;
-    const int colok = (col0 + lane) < sh.n_cols;
-    st.next_col = col0 + ctx.col_step;
+    const int colok = lane < kGroups && (col0 + lane) < sh.n_cols / kS;
+    st.next_col = col0 * kS + ctx.col_step;
     prefetch_ids(p, st, sh, lane);
 
     // ---- fast path: one compare per element, nothing else when no lane of the warp passes
@@ -530,7 +575,7 @@ struct EvalEpiT {
   __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part,
                                                  const GemmShape& sh, const EpiCtx& ctx) {
     const int lane = (int)ptx::lane_id();
-    if (p.topk > 0 && row < sh.m_rows) p.cand_cnt[(long long)part * p.nq_total + row] = n_cand(ctx)[lane];
+    if (p.topk > 0 && row < sh.m_rows && (lane % kS) == 0) p.cand_cnt[(long long)part * p.nq_total + row / kS] = n_cand(ctx)[lane];
     ptx::named_barrier_sync(1, ctx.nthreads);  // every warp has finished counting into the cache
     const unsigned* cs = cnt_s(ctx);
     for (int i = ctx.tid; i < st.n_cached; i += ctx.nthreads) {
@@ -542,5 +587,7 @@ struct EvalEpiT {
 };
 
 using EvalEpi = EvalEpiT<256, 3456>;           // 8 epilogue warps
+template <int kS>
+using EvalTracksEpi = EvalEpiT<256, 3456, kS>;  // kS chunk embeddings per track, reduced in the epilogue
 
 }  // namespace wealy

@@ -126,6 +126,91 @@ __global__ void __launch_bounds__(256) pos_thresholds_kernel(
   }
 }
 
+// K_pos for chunked tracks (row f1).  One warp per query track: for every relevant candidate track the kS x kS chunk
+// similarities (same planes, same three products as the sweep) are reduced exactly like the sweep's epilogue does
+// (red_inner over the candidate's chunks, red_outer over the query's), then rank-sorted ascending.
+__device__ __forceinline__ float warp_dot_planes(const __half* __restrict__ a_hi, const __half* __restrict__ a_lo,
+                                                 const __half* __restrict__ b_hi, const __half* __restrict__ b_lo,
+                                                 int nvec, int lane) {
+  const uint4* ah = reinterpret_cast<const uint4*>(a_hi);
+  const uint4* bh = reinterpret_cast<const uint4*>(b_hi);
+  const uint4* al = reinterpret_cast<const uint4*>(a_lo);
+  const uint4* bl = reinterpret_cast<const uint4*>(b_lo);
+  float acc = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    const uint4 a = ah[v], b = bh[v];
+    const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+    const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+    uint4 x = make_uint4(0, 0, 0, 0), y = make_uint4(0, 0, 0, 0);
+    if (a_lo) { x = al[v]; y = bl[v]; }
+    const __half2* x2 = reinterpret_cast<const __half2*>(&x);
+    const __half2* y2 = reinterpret_cast<const __half2*>(&y);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __half22float2(a2[e]), fb = __half22float2(b2[e]);
+      acc = fmaf(fa.x, fb.x, acc);
+      acc = fmaf(fa.y, fb.y, acc);
+      if (a_lo) {
+        const float2 fx = __half22float2(x2[e]), fy = __half22float2(y2[e]);
+        acc = fmaf(fa.x, fy.x, acc);
+        acc = fmaf(fa.y, fy.y, acc);
+        acc = fmaf(fx.x, fb.x, acc);
+        acc = fmaf(fx.y, fb.y, acc);
+      }
+    }
+  }
+  return warp_sum(acc);
+}
+
+__global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
+    const __half* __restrict__ q_hi, const __half* __restrict__ q_lo, const __half* __restrict__ c_hi,
+    const __half* __restrict__ c_lo, int d_pad, int ks, int red_inner, int red_outer, float red_scale,
+    const int* __restrict__ q_i, int nq, const int* __restrict__ sorted_idx, const int* __restrict__ c_i,
+    const int* __restrict__ seg_lo, const int* __restrict__ seg_len, const long long* __restrict__ off,
+    float* __restrict__ raw, float* __restrict__ thr, float* __restrict__ lim, int* __restrict__ cnt) {
+  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (q >= nq) return;
+  const int first = seg_lo[q], len = seg_len[q], qi = q_i[q];
+  const long long o = off[q];
+  const int nvec = d_pad >> 3;
+  int n = 0;
+  for (int m = 0; m < len; ++m) {
+    const int j = sorted_idx[first + m];
+    if (c_i[j] == qi) continue;  // self / id collision
+    float outer = 0.f;
+    for (int a = 0; a < ks; ++a) {
+      const long long ra = ((long long)q * ks + a) * d_pad;
+      float inner = 0.f;
+      for (int b = 0; b < ks; ++b) {
+        const long long rb = ((long long)j * ks + b) * d_pad;
+        const float v = warp_dot_planes(q_hi + ra, q_lo ? q_lo + ra : nullptr, c_hi + rb, c_lo ? c_lo + rb : nullptr, nvec, lane);
+        inner = b == 0 ? v : red_op(inner, v, red_inner);
+      }
+      if (red_inner == kRedSum && red_outer != kRedSum) inner *= red_scale;
+      outer = a == 0 ? inner : red_op(outer, inner, red_outer);
+    }
+    if (red_outer == kRedSum) outer *= red_scale;
+    if (lane == 0) raw[o + n] = outer;
+    ++n;
+  }
+  __syncwarp();
+  for (int e = lane; e < n; e += 32) {
+    const float ve = raw[o + e];
+    int r = 0;
+    for (int f = 0; f < n; ++f) {
+      const float vf = raw[o + f];
+      r += (vf < ve) || (vf == ve && f < e);
+    }
+    thr[o + r] = ve;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    cnt[q] = n;
+    lim[q] = n > 0 ? thr[o] : __int_as_float(0x7f800000);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Clique-sorted ("sorted space") view used by the symmetric all-vs-all sweep (eval_sym_epilogue.cuh)
 // ---------------------------------------------------------------------------------------------------------

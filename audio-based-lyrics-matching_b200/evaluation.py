@@ -107,16 +107,32 @@ class EvalPlan:
         N.check(N.lib.wealy_eval_plan_last_sweep_ms(self._handle, ctypes.byref(ms)))
         return ms.value
 
-    def run(self, queries_z, candidates_z, *, topk=None, eps=1e-6, precision=None, allow_empty=False):
-        """-> dict(aps, r1s, sums[, topk_idx, topk_sim]); `sums` = device doubles {sum AP, sum R1, #scored}."""
+    def run(self, queries_z, candidates_z, *, topk=None, eps=1e-6, precision=None, allow_empty=False, chunks=None,
+            redux="min"):
+        """-> dict(aps, r1s, sums[, topk_idx, topk_sim]); `sums` = device doubles {sum AP, sum R1, #scored}.
+
+        Chunked tracks: pass `[N, s, D]` embeddings (or `[N * s, D]` with `chunks=s`,
+        s in {2, 4, 8, 16}): the s x s chunk distances of every track pair are reduced like
+        `distance_tensor_redux(dist, redux)` (lib/tensor_ops.py:288-373; redux in min / max / mean / meanmin /
+        minmean) inside the sweep's epilogue before ranking; ids and results are per track."""
         if self.queries_without_relevant and not allow_empty:
             raise ValueError(f"{self.queries_without_relevant} queries have no relevant candidate "
                              "(every clique needs >= 2 versions; pass allow_empty=True to score the rest)")
         same = queries_z is candidates_z
         qz = _to_device(queries_z, self.device)
         cz = qz if same else _to_device(candidates_z, self.device)
+        if qz.ndim == 3:                                  # [N, s, D]: the chunks of a track
+            assert cz.ndim == 3 and cz.shape[1] == qz.shape[1] and (chunks is None or int(chunks) == qz.shape[1])
+            chunks = qz.shape[1]
+            qz = qz.reshape(-1, qz.shape[-1])
+            cz = qz if same else cz.reshape(-1, cz.shape[-1])
+        s = 1 if chunks is None else int(chunks)
+        if s not in (1, 2, 4, 8, 16):
+            raise NotImplementedError("chunks per track must be 1, 2, 4, 8 or 16")
+        if redux not in N.REDUX:
+            raise NotImplementedError(f"redux {redux!r} is not fused into the evaluation (min / max / mean / meanmin / minmean)")
         assert qz.ndim == 2 and cz.ndim == 2 and qz.shape[1] == cz.shape[1]
-        assert qz.shape[0] == self.nq and cz.shape[0] == self.nc
+        assert qz.shape[0] == self.nq * s and cz.shape[0] == self.nc * s
         if qz.dtype != cz.dtype:
             raise RuntimeError("queries_z and candidates_z must have the same dtype")
         if qz.stride(1) != 1:
@@ -131,10 +147,10 @@ class EvalPlan:
         tk_idx = torch.empty((self.nq, k), dtype=torch.long, device=self.device) if k else None
         tk_sim = torch.empty((self.nq, k), dtype=torch.float32, device=self.device) if k else None
         with torch.cuda.device(self.device):
-            N.check(N.lib.wealy_eval_run(
+            N.check(N.lib.wealy_eval_run_chunked(
                 self._handle, qz.data_ptr(), qz.stride(0), cz.data_ptr(), cz.stride(0), qz.shape[1],
-                N.dtype_code(qz.dtype), float(eps), passes_of(precision), k, aps.data_ptr(), r1s.data_ptr(),
-                sums.data_ptr(), tk_idx.data_ptr() if k else None, tk_sim.data_ptr() if k else None,
+                N.dtype_code(qz.dtype), float(eps), passes_of(precision), k, s, N.REDUX[redux], aps.data_ptr(),
+                r1s.data_ptr(), sums.data_ptr(), tk_idx.data_ptr() if k else None, tk_sim.data_ptr() if k else None,
                 N.stream_ptr(self.device)))
         out = {"aps": aps, "r1s": r1s, "sums": sums}
         if k:
@@ -143,7 +159,7 @@ class EvalPlan:
 
 
 def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z, *, topk=None, mode="cos",
-             eps=1e-6, precision=None, allow_empty=False, plan=None):
+             eps=1e-6, precision=None, allow_empty=False, plan=None, chunks=None, redux="min"):
     """-> (aps[Nq], r1s[Nq]) or (aps, r1s, topk_idx[Nq,k], topk_sim[Nq,k]) on the CUDA device.
 
     AP_q = 1/P sum_{p relevant} rank_rel(p) / rank_all(p); R1_q = rank of the best relevant item;
@@ -154,7 +170,8 @@ def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candid
     if own:
         plan = EvalPlan(queries_c, queries_i, candidates_c, candidates_i)
     try:
-        res = plan.run(queries_z, candidates_z, topk=topk, eps=eps, precision=precision, allow_empty=allow_empty)
+        res = plan.run(queries_z, candidates_z, topk=topk, eps=eps, precision=precision, allow_empty=allow_empty,
+                       chunks=chunks, redux=redux)
     finally:
         if own:
             torch.cuda.current_stream(plan.device).synchronize()

@@ -90,6 +90,16 @@ int wealy_eval_plan_info(const wealy_eval_plan* plan, int64_t* total_pairs, int6
 int wealy_eval_run(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, const void* candidates_z, int64_t ld_c,
                    int64_t d, int dtype, float eps, int passes, int topk, float* aps, float* r1s, double* sums,
                    int64_t* topk_idx, float* topk_sim, void* stream);
+
+/* f1: evaluation of CHUNKED tracks -- every track has `chunks` (1, 2, 4, 8 or 16) embeddings,
+ * queries_z [nq * chunks, d] / candidates_z [nc * chunks, d] (the chunks of a track are consecutive rows), the plan's ids
+ * are per track.  The chunk-level cosine distances of a track pair are reduced like
+ * distance_tensor_redux(dist[b1, b2, s1, s2], redux) of lib/tensor_ops.py:288-373 INSIDE the sweep's epilogue (the 4-D
+ * tensor is never materialised), then ranked as in wealy_eval_run.  topk_sim holds 1 - reduced distance.             */
+enum { WEALY_REDUX_MIN = 0, WEALY_REDUX_MAX = 1, WEALY_REDUX_MEAN = 2, WEALY_REDUX_MEANMIN = 3, WEALY_REDUX_MINMEAN = 4 };
+int wealy_eval_run_chunked(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, const void* candidates_z,
+                           int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, int chunks, int redux,
+                           float* aps, float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, void* stream);
 /* Multi-GPU all-vs-all (queries == candidates, no top-k).  Every rank holds the whole corpus and calls
  * wealy_eval_sweep_shard with its (shard_rank, shard_world): the symmetric sweep is restricted to the row blocks
  * rb = shard_rank (mod shard_world) and leaves this rank's share of the rank counts in the plan.  The caller

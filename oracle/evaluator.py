@@ -26,16 +26,26 @@ def _as_long(t):
     return torch.as_tensor(t).long().reshape(-1)
 
 
-def _sim_block(qz, cz, mode):
-    """similarity (higher = closer) of a block of queries against all candidates."""
+def _sim_block(qz, cz, mode, redux=None):
+    """similarity (higher = closer) of a block of queries against all candidates.
+
+    Chunked tracks (qz [b, s1, D], cz [nc, s2, D]): the chunk-level cosine DISTANCES (b, nc, s1, s2) are reduced with
+    the restated distance_tensor_redux (lib/tensor_ops.py:288-373) and returned as 1 - distance."""
     if mode not in ("cos", "cossim", "dot", "dotsim"):
         raise NotImplementedError(mode)
     base = "cossim" if mode in ("cos", "cossim") else "dotsim"
+    if qz.ndim == 3:
+        from .masked import distance_tensor_redux
+        b, s1, d = qz.shape
+        nc, s2, _ = cz.shape
+        dist = 1 - distance_matrix(qz.reshape(b * s1, d), cz.reshape(nc * s2, d), mode=base)
+        dist = dist.reshape(b, s1, nc, s2).permute(0, 2, 1, 3)            # (b1, b2, s1, s2)
+        return 1 - distance_tensor_redux(dist, redux or "min")
     return distance_matrix(qz, cz, mode=base)
 
 
 def evaluate_argsort(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z,
-                     *, topk=None, mode="cos", block=256):
+                     *, topk=None, mode="cos", block=256, redux=None):
     """Returns (aps[Nq], r1s[Nq]) and, when topk is given, (topk_idx[Nq,k], topk_sim[Nq,k]).
 
     A query without any relevant candidate raises ValueError (the reference data pipeline
@@ -51,7 +61,7 @@ def evaluate_argsort(queries_c, queries_i, queries_z, candidates_c, candidates_i
         tk_idx = torch.full((nq, k), -1, dtype=torch.long)
         tk_sim = torch.full((nq, k), float("-inf"), dtype=qz.dtype)
     for b0 in range(0, nq, block):
-        sim = _sim_block(qz[b0:b0 + block], cz, mode)          # (b, nc)
+        sim = _sim_block(qz[b0:b0 + block], cz, mode, redux)   # (b, nc)
         dist = 1 - sim                                          # "cos"/"dot" distance
         for r in range(sim.shape[0]):
             q = b0 + r
@@ -107,7 +117,7 @@ def evaluate_rankcount(queries_c, queries_i, queries_z, candidates_c, candidates
 
 
 def rank_tolerance(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z,
-                   *, gap=1e-5, mode="cos", block=256):
+                   *, gap=1e-5, mode="cos", block=256, redux=None):
     """For the parity rule "ranks exact wherever the similarity gap exceeds `gap`": per query,
     returns (r1_lo, r1_hi): the range the rank of the best relevant item may take when every
     candidate whose similarity is within `gap` of it may fall on either side."""
@@ -118,7 +128,7 @@ def rank_tolerance(queries_c, queries_i, queries_z, candidates_c, candidates_i, 
     lo = torch.empty(nq, dtype=torch.float64)
     hi = torch.empty(nq, dtype=torch.float64)
     for b0 in range(0, nq, block):
-        sim = _sim_block(qz[b0:b0 + block], cz, mode).double()
+        sim = _sim_block(qz[b0:b0 + block], cz, mode, redux).double()
         for r in range(sim.shape[0]):
             q = b0 + r
             is_self = ci == qi[q]

@@ -1,0 +1,71 @@
+"""-m gpu: evaluation of chunked tracks: the s x s chunk distances of every track pair are
+reduced like distance_tensor_redux (lib/tensor_ops.py:288-373) inside the sweep's epilogue.  Checked against the
+oracle evaluator fed with the reduced distance matrix of the restated (reference-pinned) distance_tensor_redux."""
+import pytest
+import torch
+
+from oracle import evaluator as oev
+
+pytestmark = pytest.mark.gpu
+
+
+def _chunked_set(n, s, d, seed):
+    from wealy_b200.data import synth
+    base = synth.make_eval_set(n, d, seed=seed)
+    g = torch.Generator().manual_seed(seed + 100)
+    # chunk embeddings = the track embedding + chunk-level noise (some chunks of a cover match better than others)
+    z = base["z"][:, None, :] + 0.8 * base["z"].norm(dim=1).mean() / d ** 0.5 * torch.randn(n, s, d, generator=g)
+    return base["c"], base["i"], z.contiguous()
+
+
+@pytest.mark.parametrize("redux", ["min", "max", "mean", "meanmin", "minmean"])
+@pytest.mark.parametrize("n,s,d", [(900, 4, 96), (333, 8, 64), (200, 16, 48), (1500, 2, 128)])
+def test_chunked_parity_with_oracle(n, s, d, redux):
+    from wealy_b200 import evaluation as we
+    c, i, z = _chunked_set(n, s, d, seed=n + s)
+    aps_o, r1_o = oev.evaluate_argsort(c, i, z, c, i, z, redux=redux)
+    cq, iq, zq = c.cuda(), i.cuda(), z.cuda()
+    aps, r1s = we.evaluate(cq, iq, zq, cq, iq, zq, redux=redux)
+    torch.cuda.synchronize()
+    aps, r1s = aps.cpu().double(), r1s.cpu().double()
+    assert abs(float(aps.mean()) - float(aps_o.mean())) <= 1e-4            # MAP within 1e-4
+    assert abs(float(r1s.mean()) - float(r1_o.mean())) <= 1e-4 * max(1.0, float(r1_o.mean()))
+    lo, hi = oev.rank_tolerance(c, i, z, c, i, z, gap=1e-5, redux=redux)
+    assert bool(((r1s >= lo) & (r1s <= hi)).all())
+    exact = lo == hi
+    assert torch.equal(r1s[exact], r1_o[exact])
+
+
+def test_chunked_topk_and_flat_layout():
+    from wealy_b200 import evaluation as we
+    n, s, d, k = 700, 4, 64, 10
+    c, i, z = _chunked_set(n, s, d, seed=7)
+    _, _, idx_o, sim_o = oev.evaluate_argsort(c, i, z, c, i, z, topk=k, redux="meanmin")
+    cq, iq = c.cuda(), i.cuda()
+    zf = z.reshape(n * s, d).cuda()                                         # flat [N * s, D] + chunks=
+    aps, r1s, idx, sim = we.evaluate(cq, iq, zf, cq, iq, zf, topk=k, chunks=s, redux="meanmin")
+    torch.cuda.synchronize()
+    idx, sim = idx.cpu(), sim.cpu()
+    assert (sim - sim_o).abs().max() <= 4e-6
+    ok = torch.ones_like(idx_o, dtype=torch.bool)
+    ok[:, 1:] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    ok[:, :-1] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    assert torch.equal(idx[ok], idx_o[ok])
+    assert bool((idx != torch.arange(n)[:, None]).all())                    # a track never retrieves itself
+
+
+def test_chunked_queries_disjoint_from_corpus_and_errors():
+    from wealy_b200 import evaluation as we
+    c, i, z = _chunked_set(600, 4, 48, seed=9)
+    q, cand = slice(0, 100), slice(100, 600)
+    keep = torch.tensor([bool((c[cand] == c[k]).any()) for k in range(100)])
+    qc, qi, qz = c[q][keep], i[q][keep], z[q][keep]
+    aps_o, r1_o = oev.evaluate_argsort(qc, qi, qz, c[cand], i[cand], z[cand], redux="min")
+    aps, r1s = we.evaluate(qc.cuda(), qi.cuda(), qz.cuda(), c[cand].cuda(), i[cand].cuda(), z[cand].cuda(), redux="min")
+    assert abs(float(aps.double().mean().cpu()) - float(aps_o.mean())) <= 1e-4
+    assert int((r1s.cpu().double() != r1_o).sum()) <= 1
+    with pytest.raises(NotImplementedError):
+        we.evaluate(c.cuda(), i.cuda(), z.cuda(), c.cuda(), i.cuda(), z.cuda(), redux="bpwr")
+    with pytest.raises(NotImplementedError):
+        z3 = z[:, :3].contiguous().cuda()
+        we.evaluate(c.cuda(), i.cuda(), z3, c.cuda(), i.cuda(), z3)
