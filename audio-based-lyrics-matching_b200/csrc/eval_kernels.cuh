@@ -126,42 +126,24 @@ __global__ void __launch_bounds__(256) pos_thresholds_kernel(
   }
 }
 
+// warp-level tensor-core tile D(16x8) += A(16x16, row major) * B(16x8, column major), fp16 in, fp32 accumulate
+__device__ __forceinline__ void mma_16x8x16(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ float red_neutral(int op) {
+  return op == kRedMax ? __int_as_float(0xff800000) : (op == kRedMin ? __int_as_float(0x7f800000) : 0.f);
+}
+
 // K_pos for chunked tracks (row f1).  One warp per query track: for every relevant candidate track the kS x kS chunk
 // similarities (same planes, same three products as the sweep) are reduced exactly like the sweep's epilogue does
 // (red_inner over the candidate's chunks, red_outer over the query's), then rank-sorted ascending.
-__device__ __forceinline__ float warp_dot_planes(const __half* __restrict__ a_hi, const __half* __restrict__ a_lo,
-                                                 const __half* __restrict__ b_hi, const __half* __restrict__ b_lo,
-                                                 int nvec, int lane) {
-  const uint4* ah = reinterpret_cast<const uint4*>(a_hi);
-  const uint4* bh = reinterpret_cast<const uint4*>(b_hi);
-  const uint4* al = reinterpret_cast<const uint4*>(a_lo);
-  const uint4* bl = reinterpret_cast<const uint4*>(b_lo);
-  float acc = 0.f;
-  for (int v = lane; v < nvec; v += 32) {
-    const uint4 a = ah[v], b = bh[v];
-    const __half2* a2 = reinterpret_cast<const __half2*>(&a);
-    const __half2* b2 = reinterpret_cast<const __half2*>(&b);
-    uint4 x = make_uint4(0, 0, 0, 0), y = make_uint4(0, 0, 0, 0);
-    if (a_lo) { x = al[v]; y = bl[v]; }
-    const __half2* x2 = reinterpret_cast<const __half2*>(&x);
-    const __half2* y2 = reinterpret_cast<const __half2*>(&y);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 fa = __half22float2(a2[e]), fb = __half22float2(b2[e]);
-      acc = fmaf(fa.x, fb.x, acc);
-      acc = fmaf(fa.y, fb.y, acc);
-      if (a_lo) {
-        const float2 fx = __half22float2(x2[e]), fy = __half22float2(y2[e]);
-        acc = fmaf(fa.x, fy.x, acc);
-        acc = fmaf(fa.y, fy.y, acc);
-        acc = fmaf(fx.x, fb.x, acc);
-        acc = fmaf(fx.y, fb.y, acc);
-      }
-    }
-  }
-  return warp_sum(acc);
-}
-
+// The kS x kS block of a (query track, candidate track) pair is one (kS <= 8) or two
+// (kS = 16) warp-level tensor-core tiles m16n8k16 (rows = the query's chunks, columns = the candidate's), read
+// straight from the planes: 16x less L2 traffic than kS^2 separate dot products.
 __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
     const __half* __restrict__ q_hi, const __half* __restrict__ q_lo, const __half* __restrict__ c_hi,
     const __half* __restrict__ c_lo, int d_pad, int ks, int red_inner, int red_outer, float red_scale,
@@ -171,27 +153,67 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
   const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (q >= nq) return;
+  const int g = lane >> 2, tig = lane & 3;
   const int first = seg_lo[q], len = seg_len[q], qi = q_i[q];
   const long long o = off[q];
-  const int nvec = d_pad >> 3;
+  // A rows: the query's chunks g and g + 8 (clamped: rows >= ks are masked out of the reduction)
+  const long long ra0 = ((long long)q * ks + min(g, ks - 1)) * d_pad, ra1 = ((long long)q * ks + min(g + 8, ks - 1)) * d_pad;
+  const int ntile = ks > 8 ? 2 : 1;
   int n = 0;
   for (int m = 0; m < len; ++m) {
     const int j = sorted_idx[first + m];
     if (c_i[j] == qi) continue;  // self / id collision
-    float outer = 0.f;
-    for (int a = 0; a < ks; ++a) {
-      const long long ra = ((long long)q * ks + a) * d_pad;
-      float inner = 0.f;
-      for (int b = 0; b < ks; ++b) {
-        const long long rb = ((long long)j * ks + b) * d_pad;
-        const float v = warp_dot_planes(q_hi + ra, q_lo ? q_lo + ra : nullptr, c_hi + rb, c_lo ? c_lo + rb : nullptr, nvec, lane);
-        inner = b == 0 ? v : red_op(inner, v, red_inner);
+    float v0 = red_neutral(red_inner), v1 = red_neutral(red_inner);  // inner reductions of rows g and g + 8
+    for (int t = 0; t < ntile; ++t) {
+      const long long rb = ((long long)j * ks + min(t * 8 + g, ks - 1)) * d_pad;  // B column g = candidate chunk t * 8 + g
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int k = 0; k < d_pad; k += 16) {
+        const int ko = k + tig * 2;
+        unsigned ah[4], bh[2];
+        ah[0] = __ldg(reinterpret_cast<const unsigned*>(q_hi + ra0 + ko));
+        ah[1] = __ldg(reinterpret_cast<const unsigned*>(q_hi + ra1 + ko));
+        ah[2] = __ldg(reinterpret_cast<const unsigned*>(q_hi + ra0 + ko + 8));
+        ah[3] = __ldg(reinterpret_cast<const unsigned*>(q_hi + ra1 + ko + 8));
+        bh[0] = __ldg(reinterpret_cast<const unsigned*>(c_hi + rb + ko));
+        bh[1] = __ldg(reinterpret_cast<const unsigned*>(c_hi + rb + ko + 8));
+        mma_16x8x16(c, ah, bh);
+        if (q_lo) {
+          unsigned al[4], bl[2];
+          al[0] = __ldg(reinterpret_cast<const unsigned*>(q_lo + ra0 + ko));
+          al[1] = __ldg(reinterpret_cast<const unsigned*>(q_lo + ra1 + ko));
+          al[2] = __ldg(reinterpret_cast<const unsigned*>(q_lo + ra0 + ko + 8));
+          al[3] = __ldg(reinterpret_cast<const unsigned*>(q_lo + ra1 + ko + 8));
+          bl[0] = __ldg(reinterpret_cast<const unsigned*>(c_lo + rb + ko));
+          bl[1] = __ldg(reinterpret_cast<const unsigned*>(c_lo + rb + ko + 8));
+          mma_16x8x16(c, ah, bl);
+          mma_16x8x16(c, al, bh);
+        }
       }
-      if (red_inner == kRedSum && red_outer != kRedSum) inner *= red_scale;
-      outer = a == 0 ? inner : red_op(outer, inner, red_outer);
+      // c[0], c[1]: row g, candidate chunks t*8 + 2 tig, + 1;  c[2], c[3]: row g + 8, same columns
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        if (t * 8 + tig * 2 + e < ks) {
+          v0 = red_op(v0, c[e], red_inner);
+          v1 = red_op(v1, c[2 + e], red_inner);
+        }
+      }
     }
-    if (red_outer == kRedSum) outer *= red_scale;
-    if (lane == 0) raw[o + n] = outer;
+    // inner: across the four lanes of a row group (the candidate's chunks)
+#pragma unroll
+    for (int x = 1; x < 4; x <<= 1) {
+      v0 = red_op(v0, __shfl_xor_sync(0xffffffffu, v0, x), red_inner);
+      v1 = red_op(v1, __shfl_xor_sync(0xffffffffu, v1, x), red_inner);
+    }
+    if (red_inner == kRedSum && red_outer != kRedSum) { v0 *= red_scale; v1 *= red_scale; }
+    // outer: across the query's chunks = rows g (v0) and g + 8 (v1) of all row groups
+    float w = red_neutral(red_outer);
+    if (g < ks) w = red_op(w, v0, red_outer);
+    if (g + 8 < ks) w = red_op(w, v1, red_outer);
+#pragma unroll
+    for (int x = 4; x < 32; x <<= 1) w = red_op(w, __shfl_xor_sync(0xffffffffu, w, x), red_outer);
+    if (red_outer == kRedSum) w *= red_scale;
+    if (lane == 0) raw[o + n] = w;
     ++n;
   }
   __syncwarp();
@@ -264,12 +286,6 @@ __global__ void dirty_everything_kernel(const int* __restrict__ everything, long
 // warp-level tensor-core MMAs (m16n8k16, fp32 accumulate) straight from the SAME fp16 planes the sweep consumes
 // (hi*hi + hi*lo + lo*hi), 5-10x less L2 traffic than one dot product per pair.  Valid pairs (same clique, version
 // ids differ) are appended to the query's CSR slice in arbitrary order (fill[q] counts them; step 2 sorts).
-__device__ __forceinline__ void mma_16x8x16(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
 
 __global__ void __launch_bounds__(256) pos_pairs_sorted_kernel(
     const __half* __restrict__ hi, const __half* __restrict__ lo, int d_pad, const int* __restrict__ s_c,
