@@ -44,7 +44,7 @@ __device__ __forceinline__ unsigned bit_transpose32(unsigned x, int lane) {
   return x;
 }
 
-template <int kLv, int kQueueCapT = 256, int kCachePairsT = 3456>
+template <int kLv, int kQueueCapT = 256, int kCachePairsT = 3072>
 struct EvalSymEpi {
   static_assert(kLv >= 2 && kLv <= 4, "2..4 register levels");
   using Params = EvalSymParams;
@@ -54,9 +54,13 @@ struct EvalSymEpi {
   // per warp: queue of (value, index | kGlobal, range length)
   static constexpr int kOffQx = kQueueCap * 4;
   static constexpr int kOffQn = kOffQx + kQueueCap * 4;
-  static constexpr int kWarpScratchBytes = kOffQn + kQueueCap * 4;
+  // + a staging area [16 columns][32 lanes]: the accumulator registers of half a chunk, so that a lane can fetch
+  //   the few elements it queues by (dynamic) column index instead of walking all 32 registers under predicates
+  static constexpr int kStageCols = 16;
+  static constexpr int kOffStage = kOffQn + kQueueCap * 4;
+  static constexpr int kWarpScratchBytes = kOffStage + kStageCols * 32 * 4;
   // per CTA: row-block threshold cache + packed 16-bit counters, then the ring of per-tile column slots
-  static constexpr int kColSlots = 4;
+  static constexpr int kColSlots = 3;
   static constexpr int kLvlBytes = kTileN * 16;
   static constexpr int kInfoBytes = kTileN * 8;
   static constexpr int kColSlotBytes = kLvlBytes + kInfoBytes;
@@ -85,6 +89,7 @@ struct EvalSymEpi {
   __device__ static __forceinline__ float* q_val(const EpiCtx& c) { return reinterpret_cast<float*>(c.warp_scratch); }
   __device__ static __forceinline__ unsigned* q_idx(const EpiCtx& c) { return reinterpret_cast<unsigned*>(c.warp_scratch + kOffQx); }
   __device__ static __forceinline__ int* q_len(const EpiCtx& c) { return reinterpret_cast<int*>(c.warp_scratch + kOffQn); }
+  __device__ static __forceinline__ float* stage(const EpiCtx& c) { return reinterpret_cast<float*>(c.warp_scratch + kOffStage); }
   __device__ static __forceinline__ float* thr_s(const EpiCtx& c) { return reinterpret_cast<float*>(c.cta_scratch); }
   __device__ static __forceinline__ unsigned* cnt_s(const EpiCtx& c) {
     return reinterpret_cast<unsigned*>(c.cta_scratch + kCachePairs * 4);
@@ -215,32 +220,41 @@ struct EvalSymEpi {
     st.qn = 0;
   }
 
-  // append the elements selected by the row-direction mask mr and the column-direction mask mcq
+  // append the elements selected by the row-direction mask mr and the column-direction mask mcq.  Few bits are set
+  // per lane (1.6 % of the pairs are deep), so the registers of half a chunk are parked in shared memory
+  // ([column][lane]: conflict free, every lane reads back only its own) and each lane walks its set bits.
   __device__ static __forceinline__ void push(const RowState& st, const EpiCtx& ctx, const uint32_t (&acc)[32], unsigned mr,
                                               unsigned mcq, const uint2* cinf, int pos) {
     float* qv = q_val(ctx);
     unsigned* qx = q_idx(ctx);
     int* ql = q_len(ctx);
+    float* stg = stage(ctx) + (ptx::lane_id());
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      if (__any_sync(0xffffffffu, ((mr | mcq) & (0xffu << (8 * g))) != 0u)) {
+    for (int h = 0; h < 32 / kStageCols; ++h) {
+      const unsigned sel = ((1u << kStageCols) - 1u) << (h * kStageCols);
+      if (!__any_sync(0xffffffffu, ((mr | mcq) & sel) != 0u)) continue;
 #pragma unroll
-        for (int e = 8 * g; e < 8 * g + 8; ++e) {
-          if (mr & (1u << e)) {
-            qv[pos] = __uint_as_float(acc[e]);
-            qx[pos] = st.rinfo;
-            ql[pos] = st.rpc;
-            ++pos;
-          }
-          if (mcq & (1u << e)) {
-            const uint2 c = cinf[e];
-            qv[pos] = __uint_as_float(acc[e]);
-            qx[pos] = kGlobal | (c.x + kLv);
-            ql[pos] = (int)c.y - kLv;
-            ++pos;
-          }
-        }
+      for (int e = 0; e < kStageCols; ++e) stg[e * 32] = __uint_as_float(acc[h * kStageCols + e]);
+      unsigned m = mr & sel;
+      while (m) {
+        const int e = __ffs(m) - 1;
+        m &= m - 1;
+        qv[pos] = stg[(e - h * kStageCols) * 32];
+        qx[pos] = st.rinfo;
+        ql[pos] = st.rpc;
+        ++pos;
       }
+      m = mcq & sel;
+      while (m) {
+        const int e = __ffs(m) - 1;
+        m &= m - 1;
+        const uint2 c = cinf[e];
+        qv[pos] = stg[(e - h * kStageCols) * 32];
+        qx[pos] = kGlobal | (c.x + kLv);
+        ql[pos] = (int)c.y - kLv;
+        ++pos;
+      }
+      __syncwarp();  // (reconverge before the next half overwrites the staging area)
     }
   }
 
