@@ -321,3 +321,28 @@ def test_symmetric_sweep_ragged_sizes(n):
     # partial row blocks / column tiles: padded rows and columns must never be scored
     s = _synth().make_eval_set(n, 40, seed=30 + n)
     _oracle_match(s["c"], s["i"], s["z"])
+
+
+@pytest.mark.parametrize("n,d,per", [(3000, 32, 6), (2500, 16, 12), (1100, 24, 40)])
+def test_symmetric_sweep_dense_deep_path(n, d, per):
+    """Uncorrelated clique members: a query's relevant items are scattered over the whole similarity range, so
+    about half of ALL pairs lie above its third-lowest threshold -- every chunk overflows the warp queue (the
+    batched 4-columns-at-a-time path), row caches overflow for the larger cliques, counters run high."""
+    g = torch.Generator().manual_seed(n + per)
+    z = torch.randn(n, d, generator=g)
+    c = torch.arange(n) // per
+    perm = torch.randperm(n, generator=g)
+    c, i = c[perm], torch.arange(n)
+    aps, r1s, aps_o, r1_o = _oracle_match(c, i, z)
+    assert float((aps.double() - aps_o).abs().max()) <= 5e-3      # per-query AP: only near-tie rank swaps may differ
+
+
+def test_symmetric_sweep_randomised_shapes():
+    """Many small random problems (md5-derived version ids, shuffled rows, ragged sizes) against the oracle."""
+    syn = _synth()
+    g = torch.Generator().manual_seed(99)
+    for trial in range(12):
+        n = int(torch.randint(60, 2600, (1,), generator=g))
+        d = int(torch.randint(8, 300, (1,), generator=g))
+        s = syn.make_eval_set(n, d, seed=1000 + trial, sigma=float(1.0 + 3.0 * torch.rand(1, generator=g)))
+        _oracle_match(s["c"], s["i"], s["z"])
