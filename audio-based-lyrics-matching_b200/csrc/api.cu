@@ -10,6 +10,7 @@
 #include "../../include/wealy_b200.h"
 #include "epilogues.cuh"
 #include "eval_sym_epilogue.cuh"
+#include "gemm_core2.cuh"
 #include "eval_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "masked_kernels.cuh"
@@ -248,6 +249,33 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
   const int n_units = sh.n_row_blocks * sh.n_col_chunks;
   if (n_units == 0) return WEALY_OK;
   const int grid = n_units < num_sms() ? n_units : num_sms();
+  GemmShape shl = sh;
+  W_TRY(next_unit_counter(&shl.unit_counter, s));
+  kern<<<grid, 64 + kEpiWarps * 32, kSmemBytes, s>>>(maps, shl, ep);
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+// CTA-pair kernel (gemm_core2.cuh): sh.n_row_blocks / group_rows / rb_stride / rb_offset are in SUPER row blocks
+template <class Epi, int kPasses, int kBlockK>
+static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename Epi::Params& ep, cudaStream_t s) {
+  constexpr int kStages = 4, kEpiWarps = 8;
+  using SM = PairSmem<kPasses, kBlockK, kStages>;
+  GemmTmaps maps;
+  memset(&maps, 0, sizeof(maps));
+  W_TRY(make_plane_tmap(&maps.a_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK));
+  if (kPasses == 3) W_TRY(make_plane_tmap(&maps.a_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK));
+  else maps.a_lo = maps.a_hi;
+  maps.b_hi = maps.a_hi;
+  maps.b_lo = maps.a_lo;
+  auto kern = gemm_pair_kernel<Epi, kPasses, kBlockK, kEpiWarps, kStages>;
+  constexpr int kSmemBytes = SM::total(kEpiWarps, Epi::kWarpScratchBytes, Epi::kCtaScratchBytes);
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  const int n_units = sh.n_row_blocks * sh.n_col_chunks;
+  if (n_units == 0) return WEALY_OK;
+  const int pairs = num_sms() / 2;
+  const int grid = 2 * (n_units < pairs ? n_units : pairs);
   GemmShape shl = sh;
   W_TRY(next_unit_counter(&shl.unit_counter, s));
   kern<<<grid, 64 + kEpiWarps * 32, kSmemBytes, s>>>(maps, shl, ep);
@@ -668,11 +696,18 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     CU_TRY(cudaEventCreate(&p->ev1));
   }
   CU_TRY(cudaEventRecord(p->ev0, s));
+  const bool pair = sym && env_int("WEALY_SYM_PAIR", 0) != 0;   // CTA-pair (cta_group::2) kernel
+  const int total_rb = sh.n_row_blocks;
+  if (pair) {
+    // the pair kernel works on super row blocks (two adjacent row blocks per CTA pair)
+    sh.n_row_blocks = (total_rb + 1) / 2;
+    sh.group_rows = (sh.group_rows + 1) / 2;
+  }
   if (shard_world > 1) {
-    const int total_rb = sh.n_row_blocks;
+    const int total_owned = sh.n_row_blocks;
     sh.rb_stride = shard_world;
     sh.rb_offset = shard_rank;
-    sh.n_row_blocks = shard_rank < total_rb ? (int)ceil_div(total_rb - shard_rank, shard_world) : 0;
+    sh.n_row_blocks = shard_rank < total_owned ? (int)ceil_div(total_owned - shard_rank, shard_world) : 0;
     if (sh.group_rows > sh.n_row_blocks) sh.group_rows = sh.n_row_blocks > 0 ? sh.n_row_blocks : 1;
   }
   if (sym) {
@@ -687,9 +722,17 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     sp.hist = p->hist;
     sp.dirty = p->s_dirty;
     sp.n_col_tiles = sh.n_col_tiles;
+    sp.n_row_blocks = total_rb;
     sp.total_pairs = (unsigned)p->total_pairs;
     const int lv = env_int("WEALY_SYM_LEVELS", 3);  // 3 measured best at C2 (2: 26.8 ms, 3: 25.5 ms, 4: 25.9 ms per step)
-    if (passes == 3) {
+    if (pair) {
+      if (passes == 3) {
+        sh.k_blocks = (int)(pq.d_pad / 32);
+        W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32>(pq, sh, sp, s)));
+      } else {
+        W_TRY((launch_gemm_pair<EvalSymEpi<3>, 1, 64>(pq, sh, sp, s)));
+      }
+    } else if (passes == 3) {
       sh.k_blocks = (int)(pq.d_pad / 32);
       if (lv == 2) W_TRY((launch_gemm_t<EvalSymEpi<2>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
       else if (lv == 3) W_TRY((launch_gemm_t<EvalSymEpi<3>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));

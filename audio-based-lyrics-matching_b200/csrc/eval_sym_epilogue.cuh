@@ -31,6 +31,7 @@ struct EvalSymParams {
   unsigned int* hist;          // CSR rank counters
   const unsigned char* dirty;  // [n_row_blocks][n_col_tiles] tiles that need id tests
   int n_col_tiles;
+  int n_row_blocks;            // row blocks of the whole problem (the CTA-pair kernel may be handed one past the end)
   unsigned int total_pairs;
 };
 
@@ -44,7 +45,7 @@ __device__ __forceinline__ unsigned bit_transpose32(unsigned x, int lane) {
   return x;
 }
 
-template <int kLv, int kQueueCapT = 256, int kCachePairsT = 3072>
+template <int kLv, int kQueueCapT = 256, int kCachePairsT = 4096>
 struct EvalSymEpi {
   static_assert(kLv >= 2 && kLv <= 4, "2..4 register levels");
   using Params = EvalSymParams;
@@ -59,12 +60,12 @@ struct EvalSymEpi {
   static constexpr int kStageCols = 16;
   static constexpr int kOffStage = kOffQn + kQueueCap * 4;
   static constexpr int kWarpScratchBytes = kOffStage + kStageCols * 32 * 4;
-  // per CTA: row-block threshold cache + packed 16-bit counters, then the ring of per-tile column slots
+  // per CTA: row-block threshold cache, then the ring of per-tile column slots
   static constexpr int kColSlots = 3;
   static constexpr int kLvlBytes = kTileN * 16;
   static constexpr int kInfoBytes = kTileN * 8;
   static constexpr int kColSlotBytes = kLvlBytes + kInfoBytes;
-  static constexpr int kOffColSlots = (kCachePairs * 6 + 15) / 16 * 16;
+  static constexpr int kOffColSlots = (kCachePairs * 4 + 15) / 16 * 16;
   static constexpr int kCtaScratchBytes = kOffColSlots + kColSlots * kColSlotBytes;
 
   // what the TMA thread copies into the column slot of tile t
@@ -91,9 +92,6 @@ struct EvalSymEpi {
   __device__ static __forceinline__ int* q_len(const EpiCtx& c) { return reinterpret_cast<int*>(c.warp_scratch + kOffQn); }
   __device__ static __forceinline__ float* stage(const EpiCtx& c) { return reinterpret_cast<float*>(c.warp_scratch + kOffStage); }
   __device__ static __forceinline__ float* thr_s(const EpiCtx& c) { return reinterpret_cast<float*>(c.cta_scratch); }
-  __device__ static __forceinline__ unsigned* cnt_s(const EpiCtx& c) {
-    return reinterpret_cast<unsigned*>(c.cta_scratch + kCachePairs * 4);
-  }
 
   __device__ static __forceinline__ float lvl_of(const float4& v, int j) {
     return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
@@ -130,9 +128,7 @@ struct EvalSymEpi {
     const unsigned total = end - st.base;
     st.n_cached = (int)(total < (unsigned)kCachePairs ? total : (unsigned)kCachePairs);
     float* ts = thr_s(ctx);
-    unsigned* cs = cnt_s(ctx);
     for (int i = ctx.tid; i < st.n_cached; i += ctx.nthreads) ts[i] = __ldg(p.thr + st.base + i);
-    for (int i = ctx.tid; i < (st.n_cached + 1) / 2; i += ctx.nthreads) cs[i] = 0u;
     const unsigned rel = st.off - st.base;
     const bool cached = st.row_ok && rel + (unsigned)cnt <= (unsigned)st.n_cached;
     st.rinfo = cached ? (rel + kLv) : (kGlobal | (st.off + kLv));
@@ -167,29 +163,11 @@ struct EvalSymEpi {
   }
   __device__ static __forceinline__ void count(const Params& p, const RowState& st, const EpiCtx& ctx, const Ent& en,
                                                int lb, int lane) {
-    constexpr unsigned kFull = 0xffffffffu;
+    (void)ctx; (void)lane;
     const bool glob = (en.idx & kGlobal) != 0u;
-    const unsigned slot = (en.idx & ~kGlobal) - 1u + (unsigned)lb;  // bucket = kLv - 1 + lower bound
-    if (en.on && glob) atomicAdd(p.hist + slot, 1u);
-    const bool cached = en.on && !glob;
-    // elements of a round often share a hot (row, bucket): the first lane counts every lane with its key
-    const unsigned cm = __ballot_sync(kFull, cached);
-    if (cm != 0u) {
-      const int lead = __ffs(cm) - 1;
-      const unsigned key_lead = __shfl_sync(kFull, slot, lead);
-      const unsigned same = __ballot_sync(kFull, cached && slot == key_lead);
-      if (cached && (lane == lead || slot != key_lead)) {
-        const unsigned add = lane == lead ? (unsigned)__popc(same) : 1u;
-        const int shift = (int)(slot & 1u) * 16;
-        unsigned* cs = cnt_s(ctx) + (slot >> 1);
-        const unsigned old = (atomicAdd(cs, add << shift) >> shift) & 0xffffu;
-        // keep the 16-bit field far from overflow: the adder that takes it across 0x8000 moves 0x8000 counts out
-        if (old < 0x8000u && old + add >= 0x8000u) {
-          atomicSub(cs, 0x8000u << shift);
-          atomicAdd(p.hist + st.base + slot, 0x8000u);
-        }
-      }
-    }
+    // bucket = kLv - 1 + lower bound; cached row entries carry an offset relative to the unit's first row
+    const unsigned slot = (en.idx & ~kGlobal) - 1u + (unsigned)lb + (glob ? 0u : st.base);
+    if (en.on) atomicAdd(p.hist + slot, 1u);
   }
 
   // Bin the queued elements: 2 x 32 per iteration so the two dependent load -> compare chains overlap.
@@ -261,7 +239,8 @@ struct EvalSymEpi {
   __device__ static __forceinline__ void tile_begin(const Params& p, RowState& st, const GemmShape& sh,
                                                     const EpiCtx& ctx, int t) {
     (void)sh;
-    st.dirty = (int)__ldg(p.dirty + (size_t)(ctx.row_base / kTileM) * p.n_col_tiles + t);
+    const int rbi = ctx.row_base / kTileM;
+    st.dirty = rbi < p.n_row_blocks ? (int)__ldg(p.dirty + (size_t)rbi * p.n_col_tiles + t) : 1;
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
@@ -360,13 +339,7 @@ struct EvalSymEpi {
       for (int j = 0; j < kLv - 1; ++j)
         if (st.rc[j] != 0u) atomicAdd(p.hist + st.off + j, st.rc[j]);
     }
-    ptx::named_barrier_sync(1, ctx.nthreads);  // every warp has finished counting into the cache
-    const unsigned* cs = cnt_s(ctx);
-    for (int i = ctx.tid; i < st.n_cached; i += ctx.nthreads) {
-      const unsigned v = (cs[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-      if (v != 0u) atomicAdd(p.hist + st.base + i, v);
-    }
-    ptx::named_barrier_sync(1, ctx.nthreads);  // flushed before the next unit refills the cache
+    ptx::named_barrier_sync(1, ctx.nthreads);  // every warp is done with the threshold cache before the next unit refills it
   }
 };
 

@@ -1,0 +1,284 @@
+// CTA-pair variant of the contraction core (gemm_core.cuh) for the symmetric evaluation sweep: two CTAs of a
+// cluster (two SMs of one TPC) work on one 256 x 256 tile with tcgen05.mma.cta_group::2.
+//
+//   * each CTA owns 128 rows of the tile (its own row block: rb = 2 S + cta_rank of the "super" row block S) and
+//     keeps the accumulator of those rows in its own TMEM -- the epilogue policy sees exactly what it sees in the
+//     single-CTA core;
+//   * each CTA loads its 128 A rows and only HALF of the tile's 256 B rows (columns 128 cta_rank .. +128); the
+//     tensor cores of both SMs read the two halves from both shared memories.  Per tile the pair moves
+//     2 x (A + B/2) instead of 2 x (A + B) through L2 -> shared memory, and a pipeline stage is 32 KB instead of
+//     48 KB (4 stages instead of 3 next to the same epilogue scratch);
+//   * the leader CTA (rank 0) issues the MMAs; TMA completions of both CTAs are counted on the leader's `full`
+//     barriers (cp.async.bulk.tensor.cta_group::2), tcgen05.commit multicasts to the `empty` / `tmem_full`
+//     barriers of both CTAs, the epilogue warps of both CTAs arrive on the leader's `tmem_empty`;
+//   * units are (super row block) x (chunk of column tiles), handed out dynamically by the leader's TMA thread,
+//     which publishes the unit index into the mailboxes of both CTAs (st.shared::cluster + remote mbarrier arrive).
+#pragma once
+#include "gemm_core.cuh"
+
+namespace wealy {
+
+template <int kPasses, int kBlockK, int kStages>
+struct PairSmem {
+  static constexpr int kSwizzle = kBlockK * 2;
+  static constexpr int kTileBytes = kTileM * kBlockK * 2;  // 128 rows of one plane (A rows, or half of the B rows)
+  static constexpr int kPlanes = kPasses == 3 ? 2 : 1;
+  static constexpr int kStageBytes = kPlanes * 2 * kTileBytes;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kCore = kStages * kStageBytes + kBarBytes;
+  static constexpr int total(int epi_warps, int scratch_per_warp, int cta_scratch) {
+    return kCore + epi_warps * scratch_per_warp + cta_scratch + 1024;
+  }
+};
+
+template <class Epi, int kPasses, int kBlockK, int kEpiWarps, int kStages>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + kEpiWarps * 32, 1)
+gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, const typename Epi::Params ep) {
+  using SM = PairSmem<kPasses, kBlockK, kStages>;
+  using CS = ColSlotTraits<Epi>;
+  constexpr int kHalves = kEpiWarps / 4;
+  constexpr int kColSlots = CS::kSlots;
+  static_assert(kEpiWarps == 8, "8 epilogue warps");
+  static_assert(kColSlots > 0, "the pair kernel serves the symmetric evaluation epilogue");
+
+  extern __shared__ uint8_t smem_raw[];
+  // (the dynamic shared memory of both CTAs starts at the same offset, so the aligned layouts coincide)
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* bar_base = smem + kStages * SM::kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bar_base);  // used in the leader only
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;                        // leader only: both CTAs' epilogue warps arrive
+  uint64_t* unit_full = tmem_empty + 2;
+  uint64_t* unit_empty = unit_full + 2;                        // leader only
+  uint64_t* col_full = unit_empty + 2;
+  uint64_t* col_empty = col_full + kColSlots;
+  int* unit_slot = reinterpret_cast<int*>(col_empty + kColSlots);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(unit_slot + 2);
+  static_assert((2 * kStages + 8 + 2 * kColSlots) * 8 + 16 <= SM::kBarBytes, "barrier area");
+  uint8_t* scratch_base = bar_base + SM::kBarBytes;
+  uint8_t* col_slots = scratch_base + kEpiWarps * Epi::kWarpScratchBytes + CS::kOffset;
+
+  const int warp_idx = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = (int)ptx::lane_id();
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (warp_idx == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmaps.a_hi);
+    if (kPasses == 3) ptx::prefetch_tensormap(&tmaps.a_lo);
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);   // the leader's producer arrives once, with the bytes of both CTAs
+      ptx::mbar_init(&empty_bar[s], 1);  // one multicast commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 2 * kEpiWarps);
+      ptx::mbar_init(&unit_full[a], 1);
+      ptx::mbar_init(&unit_empty[a], 2 * kEpiWarps + 2);  // leader: MMA thread + epilogue warps; peer: TMA thread + epilogue warps
+    }
+    for (int c = 0; c < kColSlots; ++c) {
+      ptx::mbar_init(&col_full[c], 1);
+      ptx::mbar_init(&col_empty[c], kEpiWarps);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp_idx == 1) ptx::tmem_alloc_pair<512>(tmem_slot);
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_units = shape.n_row_blocks * shape.n_col_chunks;  // n_row_blocks counts SUPER row blocks here
+
+  // unit -> (chunk, super row block S); this CTA's row block is 2 S + cta_rank, both need column tiles >= S
+  auto unit_tiles = [&](int u, int& rb, int& t0, int& t1) {
+    int chunk, S;
+    decode_unit(shape, u, chunk, S);
+    rb = 2 * S + (int)cta_rank;
+    t1 = min((chunk + 1) * shape.tiles_per_chunk, shape.n_col_tiles);
+    t0 = max(chunk * shape.tiles_per_chunk, S);
+  };
+
+  if (warp_idx == 0) {
+    // ===================================================== TMA producer (one thread per CTA)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int us = 0;
+      uint32_t uphase = 0;
+      int cs = 0;
+      uint32_t cphase = 0;
+      const uint32_t leader_full0 = ptx::map_to_cta(&full_bar[0], 0);
+      const uint32_t peer_unit_full0 = ptx::map_to_cta(&unit_full[0], 1);
+      const uint32_t peer_unit_slot0 = ptx::map_to_cta(&unit_slot[0], 1);
+      const uint32_t leader_unit_empty0 = ptx::map_to_cta(&unit_empty[0], 0);
+      while (true) {
+        int u;
+        if (leader) {
+          // fetch the next unit and publish it to the consumers of both CTAs
+          ptx::mbar_wait_cluster(&unit_empty[us], uphase ^ 1u);
+          u = atomicAdd(shape.unit_counter, 1);
+          if (u >= n_units) u = -1;
+          unit_slot[us] = u;
+          ptx::st_cluster_u32(peer_unit_slot0 + 4u * us, (uint32_t)u);
+          ptx::mbar_arrive(&unit_full[us]);
+          ptx::mbar_arrive_cluster(peer_unit_full0 + 8u * us);  // release.cluster: orders the slot write before it
+        } else {
+          ptx::mbar_wait_cluster(&unit_full[us], uphase);
+          u = unit_slot[us];
+          ptx::mbar_arrive_cluster(leader_unit_empty0 + 8u * us);
+        }
+        if (++us == 2) { us = 0; uphase ^= 1u; }
+        if (u < 0) break;
+        int rb, t0, t1;
+        unit_tiles(u, rb, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          {
+            ptx::mbar_wait(&col_empty[cs], cphase ^ 1u);
+            const void *s0, *s1;
+            Epi::col_bulk_src(ep, t, s0, s1);
+            uint8_t* dst = col_slots + cs * CS::kBytes;
+            ptx::mbar_expect_tx(&col_full[cs], CS::kBytes);
+            ptx::bulk_load(dst, s0, Epi::kLvlBytes, &col_full[cs]);
+            ptx::bulk_load(dst + Epi::kLvlBytes, s1, CS::kBytes - Epi::kLvlBytes, &col_full[cs]);
+            if (++cs == kColSlots) { cs = 0; cphase ^= 1u; }
+          }
+          for (int kb = 0; kb < shape.k_blocks; ++kb) {
+            ptx::mbar_wait_cluster(&empty_bar[stage], phase ^ 1u);
+            uint8_t* st = smem + stage * SM::kStageBytes;
+            if (leader) ptx::mbar_expect_tx(&full_bar[stage], 2 * SM::kStageBytes);
+            const uint32_t fb = leader_full0 + 8u * stage;
+            const int brow = t * kTileN + (int)cta_rank * kTileM;  // this CTA's half of the tile's candidate rows
+            // layout of a stage: A_hi | A_lo | B_hi(half) | B_lo(half)   (single pass: A_hi | B_hi)
+            ptx::tma_load_2d_pair(st, &tmaps.a_hi, fb, kb * kBlockK, rb * kTileM, ptx::kEvictLast);
+            ptx::tma_load_2d_pair(st + SM::kPlanes * SM::kTileBytes, &tmaps.a_hi, fb, kb * kBlockK, brow, ptx::kEvictNormal);
+            if (kPasses == 3) {
+              ptx::tma_load_2d_pair(st + SM::kTileBytes, &tmaps.a_lo, fb, kb * kBlockK, rb * kTileM, ptx::kEvictLast);
+              ptx::tma_load_2d_pair(st + 3 * SM::kTileBytes, &tmaps.a_lo, fb, kb * kBlockK, brow, ptx::kEvictNormal);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================================== MMA issuer (one thread of the leader CTA)
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kTileM, kTileN, false);  // M = 256 over the pair
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      int us = 0;
+      uint32_t uphase = 0;
+      while (true) {
+        ptx::mbar_wait(&unit_full[us], uphase);
+        const int u = unit_slot[us];
+        ptx::mbar_arrive(&unit_empty[us]);
+        if (++us == 2) { us = 0; uphase ^= 1u; }
+        if (u < 0) break;
+        int rb, t0, t1;
+        unit_tiles(u, rb, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+          ptx::tc_fence_after_sync();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTileN);
+          for (int kb = 0; kb < shape.k_blocks; ++kb) {
+            ptx::mbar_wait_cluster(&full_bar[stage], phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t st = ptx::smem_u32(smem + stage * SM::kStageBytes);
+            const uint64_t a_hi = ptx::make_smem_desc<SM::kSwizzle>(st);
+            const uint64_t a_lo = ptx::make_smem_desc<SM::kSwizzle>(st + SM::kTileBytes);
+            const uint64_t b_hi = ptx::make_smem_desc<SM::kSwizzle>(st + SM::kPlanes * SM::kTileBytes);
+            const uint64_t b_lo = ptx::make_smem_desc<SM::kSwizzle>(st + 3 * SM::kTileBytes);
+#pragma unroll
+            for (int kk = 0; kk < kBlockK / kUmmaK; ++kk) {
+              const uint64_t adv = (uint64_t)((kk * kUmmaK * 2) >> 4);
+              ptx::umma_f16_pair(d_tmem, a_hi + adv, b_hi + adv, idesc, (uint32_t)((kb | kk) != 0));
+              if (kPasses == 3) {
+                ptx::umma_f16_pair(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+                ptx::umma_f16_pair(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
+              }
+            }
+            ptx::umma_commit_pair(&empty_bar[stage]);  // both CTAs' slots are reusable once these MMAs retire
+            if (kb == shape.k_blocks - 1) ptx::umma_commit_pair(&tmem_full[acc]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps (both CTAs)
+    const int ew = warp_idx - 2;
+    const int quad = warp_idx & 3;
+    const int half = ew >> 2;
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int us = 0;
+    uint32_t uphase = 0;
+    int cs = 0;
+    uint32_t cphase = 0;
+    const uint32_t leader_unit_empty0 = ptx::map_to_cta(&unit_empty[0], 0);
+    const uint32_t leader_tmem_empty0 = ptx::map_to_cta(&tmem_empty[0], 0);
+    while (true) {
+      ptx::mbar_wait_cluster(&unit_full[us], uphase);
+      const int u = unit_slot[us];
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(leader_unit_empty0 + 8u * us);
+      if (++us == 2) { us = 0; uphase ^= 1u; }
+      if (u < 0) break;
+      int rb, t0, t1;
+      unit_tiles(u, rb, t0, t1);
+      if (t0 >= t1) continue;
+      const int row = rb * kTileM + row_in_tile;
+      typename Epi::RowState rs;
+      EpiCtx ctx;
+      ctx.warp_scratch = scratch_base + ew * Epi::kWarpScratchBytes;
+      ctx.cta_scratch = scratch_base + kEpiWarps * Epi::kWarpScratchBytes;
+      ctx.tid = ew * 32 + lane;
+      ctx.nthreads = kEpiWarps * 32;
+      ctx.row_base = rb * kTileM;
+      ctx.first_col = t0 * kTileN + half * kChunkCols;
+      ctx.col_step = kHalves * kChunkCols;
+      ctx.col_slot = nullptr;
+      Epi::row_begin(ep, rs, row, 0, shape, ctx);
+      for (int t = t0; t < t1; ++t) {
+        ptx::mbar_wait(&col_full[cs], cphase);
+        ctx.col_slot = col_slots + cs * CS::kBytes;
+        Epi::tile_begin(ep, rs, shape, ctx, t);
+        ptx::mbar_wait_cluster(&tmem_full[acc], acc_phase);
+        ptx::tc_fence_after_sync();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN);
+#pragma unroll 1
+        for (int c = half; c < kTileN / kChunkCols; c += kHalves) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * kChunkCols), v);
+          ptx::tmem_ld_wait();
+          Epi::chunk32(ep, rs, row, t * kTileN + c * kChunkCols, v, shape, ctx);
+        }
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::mbar_arrive_cluster(leader_tmem_empty0 + 8u * acc);
+          ptx::mbar_arrive(&col_empty[cs]);
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++cs == kColSlots) { cs = 0; cphase ^= 1u; }
+        Epi::tile_end(ep, rs, shape, ctx);
+      }
+      Epi::row_end(ep, rs, row, 0, shape, ctx);
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync_all();  // nobody leaves (or frees TMEM) while the peer may still signal or read
+  if (warp_idx == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair<512>(tmem_base);
+  }
+}
+
+}  // namespace wealy

@@ -1,0 +1,6 @@
+for p in 1 0; do
+echo "pair=$p"
+WEALY_SYM_PAIR=$p timeout 120 python tools/gpu_diag.py time fp16 100000 1024 0 1.0 2>&1 | tail -1
+WEALY_SYM_PAIR=$p timeout 120 python tools/gpu_diag.py time fp16 100000 1024 0 3.5 2>&1 | tail -1
+WEALY_SYM_PAIR=$p timeout 120 python tools/gpu_diag.py time fp16x3 100000 1024 0 3.5 2>&1 | tail -1
+done
