@@ -1,0 +1,6 @@
+for p in 0 1; do
+echo pair=$p
+WEALY_SYM_PAIR=$p timeout 120 python tools/gpu_diag.py time fp16 100000 1024 2>&1 | tail -1
+WEALY_SYM_PAIR=$p timeout 120 python tools/gpu_diag.py time fp16x3 100000 1024 2>&1 | tail -1
+WEALY_SYM_PAIR=$p timeout 120 python tools/gpu_diag.py time fp16x3 100000 1024 2>&1 | tail -1
+done
