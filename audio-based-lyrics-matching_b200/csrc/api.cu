@@ -444,7 +444,7 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   CU_TRY(cub::DeviceScan::ExclusiveSum(tmp2, scan_bytes, p->npos, p->off, nq + 1, s));
 
   // ---- clique-sorted view for the symmetric all-vs-all sweep
-  void *tmp3 = nullptr, *tmp4 = nullptr;
+  void* tmp3 = nullptr;
   int *vkeys = nullptr, *vpos = nullptr, *everything = nullptr;
   if (p->same_ids) {
     const int n = nq;
@@ -491,7 +491,6 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   dev_free(tmp, s);
   dev_free(tmp2, s);
   dev_free(tmp3, s);
-  dev_free(tmp4, s);
   dev_free(vkeys, s);
   dev_free(vpos, s);
   dev_free(everything, s);
