@@ -198,6 +198,6 @@ class DistributedCLEWSLoss(nn.Module):
         return loss, {
             "l_main": loss, "l_cent": stats[4], "l_cont": stats[5], "cnt_pos_pairs": stats[6],
             "cnt_neg_pairs": stats[7], "anchors_with_pos": stats[8], "v_dpos": stats[9], "v_dneg": stats[10],
-            "uniformity_weight": torch.tensor(uw, device=z.device), "z_max": stats[1], "z_mean": stats[2],
+            "uniformity_weight": torch.full((), uw, device=z.device), "z_max": stats[1], "z_mean": stats[2],
             "z_std": stats[3],
         }

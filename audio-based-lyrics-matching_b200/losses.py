@@ -153,7 +153,7 @@ class CLEWSLoss(nn.Module):
             "anchors_with_pos": stats[8],
             "v_dpos": stats[9],
             "v_dneg": stats[10],
-            "uniformity_weight": torch.tensor(uw, device=z.device),
+            "uniformity_weight": torch.full((), uw, device=z.device),
             "z_max": stats[1],
             "z_mean": stats[2],
             "z_std": stats[3],

@@ -136,3 +136,34 @@ def test_ragged_batch_sizes():
             lo.backward()
             assert abs(float(loss.detach()) - float(lo)) <= 1e-5 * max(1.0, abs(float(lo)))
             assert float((zc.grad.cpu() - zr.grad).norm()) <= 2e-5 * float(zr.grad.norm()) + 1e-9
+
+
+@pytest.mark.parametrize("kind", ["ntxent", "clews"])
+def test_forward_backward_is_cuda_graph_capturable(kind):
+    """The loss step is launch bound (about ten short kernels): it must be capturable in a CUDA graph -- no host
+    synchronisation, no pageable host copies anywhere between the call and z.grad."""
+    from wealy_b200.data import synth
+    wl = _wl()
+    s = synth.make_loss_batch(512, 256, seed=2, dtype=torch.bfloat16, device="cuda")
+    mod = wl.NTXentLoss(0.1) if kind == "ntxent" else wl.CLEWSLoss()
+    z = s["z"].clone().requires_grad_(True)
+    lab, idx = s["label"].clone(), s["idx"].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            z.grad = None
+            loss, _ = mod(lab, idx, z)
+            loss.backward()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    ref_loss, ref_grad = float(loss), z.grad.clone()
+    g = torch.cuda.CUDAGraph()
+    z.grad = None
+    with torch.cuda.graph(g):
+        loss_g, _ = mod(lab, idx, z)
+        loss_g.backward()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert float(loss_g) == ref_loss and torch.equal(z.grad, ref_grad)

@@ -36,6 +36,38 @@ def gpu_time(mod, s, reps, backward, flush):
     return ms[len(ms) // 2], float(loss.detach())
 
 
+def graph_time(mod, s, reps, flush):
+    """The same forward + backward captured once in a CUDA graph and replayed (the step is launch bound: ~10 short
+    kernels): device time per replay."""
+    z = s["z"].clone().requires_grad_(True)
+    lab, idx = s["label"].clone(), s["idx"].clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            z.grad = None
+            loss, _ = mod(lab, idx, z)
+            loss.backward()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    z.grad = None
+    with torch.cuda.graph(g):
+        loss, _ = mod(lab, idx, z)
+        loss.backward()
+    ms = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms.sort()
+    return ms[len(ms) // 2], float(loss.detach()), z.grad.detach().clone()
+
+
 def main():
     b, d = 4096, 1024
     cpu = "--no-cpu" not in sys.argv
@@ -50,7 +82,16 @@ def main():
         f, lv = gpu_time(mod, s, 20, False, flush)
         fb, _ = gpu_time(mod, s, 20, True, flush)
         passes = 3 if precision == "fp16x3" else 1  # auto resolves to 1 pass for the bf16 batch
-        out[name] = {"fwd_ms": f, "fwd_bwd_ms": fb, "loss": lv,
+        try:
+            gms, glv, ggrad = graph_time(mod, s, 20, flush)
+            z2 = s["z"].clone().requires_grad_(True)
+            l2, _ = mod(s["label"].clone(), s["idx"], z2)
+            l2.backward()
+            graph = {"fwd_bwd_graph_ms": gms, "graph_loss": glv,
+                     "graph_grad_rel_diff": float((ggrad.float() - z2.grad.float()).norm() / z2.grad.float().norm())}
+        except Exception as e:  # report, do not hide
+            graph = {"fwd_bwd_graph_ms": None, "graph_error": repr(e)[:200]}
+        out[name] = {"fwd_ms": f, "fwd_bwd_ms": fb, "loss": lv, **graph,
                      "algorithmic_tflops_fwd_bwd": 8.0 * b * b * d / (fb * 1e-3) / 1e12,
                      "executed_tflops_fwd_bwd": 8.0 * b * b * d * passes / (fb * 1e-3) / 1e12}
     if cpu:
