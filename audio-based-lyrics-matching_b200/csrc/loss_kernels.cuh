@@ -381,6 +381,27 @@ template <>
 __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 template <typename T>
+__device__ __forceinline__ void store4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+template <>
+__device__ __forceinline__ void store4<__half>(__half* p, float4 v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<const unsigned*>(&a);
+  o.y = *reinterpret_cast<const unsigned*>(&b);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 o;
+  o.x = *reinterpret_cast<const unsigned*>(&a);
+  o.y = *reinterpret_cast<const unsigned*>(&b);
+  *reinterpret_cast<uint2*>(p) = o;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256) loss_jacobian_kernel(int kind, const T* __restrict__ z, long long ldz, int b, int d,
                                                             const float* __restrict__ norm,
                                                             const float* __restrict__ du, const float* __restrict__ scal,
@@ -391,18 +412,37 @@ __global__ void __launch_bounds__(256) loss_jacobian_kernel(int kind, const T* _
   if (row >= b) return;
   const float r = norm[row];
   const float div = kind == kLossNtxent ? r + 1e-6f : fmaxf(r, 1e-12f);
+  const float inv = 1.f / div;
   const T* zr = z + (long long)row * ldz;
   const float* g = du + (long long)row * d;
+  T* o = dz + (long long)row * ld_dz;
+  // HBM-bound row pass: 4 elements per lane and access when the rows are suitably aligned (the usual case)
+  const bool vec = (d % 4 == 0) && (ldz % 4 == 0) && (ld_dz % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dz) & 15) == 0);
   float proj = 0.f;
-  for (int k = lane; k < d; k += 32) proj = fmaf(to_f32<T>(zr[k]) / div, g[k], proj);
+  if (vec) {
+    for (int k = lane * 4; k < d; k += 128) {
+      const float4 zv = load4<T>(zr + k), gv = *reinterpret_cast<const float4*>(g + k);
+      proj = fmaf(zv.x * inv, gv.x, proj);
+      proj = fmaf(zv.y * inv, gv.y, proj);
+      proj = fmaf(zv.z * inv, gv.z, proj);
+      proj = fmaf(zv.w * inv, gv.w, proj);
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) proj = fmaf(to_f32<T>(zr[k]) * inv, g[k], proj);
+  }
   proj = warp_sum(proj);
   // d(z/(r+eps))/dz has the extra (r+eps)/r on the radial term; r == 0 -> torch's norm subgradient is 0
   const float radial = kind == kLossNtxent ? (r > 0.f ? proj * div / r : 0.f) : proj;
-  const float f = scal[0] * (grad_out ? grad_out[0] : 1.f) / div;
-  T* o = dz + (long long)row * ld_dz;
-  for (int k = lane; k < d; k += 32) {
-    const float u = to_f32<T>(zr[k]) / div;
-    o[k] = from_f32<T>(f * (g[k] - u * radial));
+  const float f = scal[0] * (grad_out ? grad_out[0] : 1.f) * inv;
+  if (vec) {
+    for (int k = lane * 4; k < d; k += 128) {
+      const float4 zv = load4<T>(zr + k), gv = *reinterpret_cast<const float4*>(g + k);
+      store4<T>(o + k, make_float4(f * (gv.x - zv.x * inv * radial), f * (gv.y - zv.y * inv * radial),
+                                   f * (gv.z - zv.z * inv * radial), f * (gv.w - zv.w * inv * radial)));
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) o[k] = from_f32<T>(f * (g[k] - to_f32<T>(zr[k]) * inv * radial));
   }
 }
 

@@ -37,6 +37,24 @@ __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+// four consecutive elements as floats (16-bit types: one 8-byte access, fp32: one 16-byte access)
+template <typename T>
+__device__ __forceinline__ float4 load4(const T* p);
+template <>
+__device__ __forceinline__ float4 load4<float>(const float* p) { return *reinterpret_cast<const float4*>(p); }
+template <>
+__device__ __forceinline__ float4 load4<__half>(const __half* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <>
+__device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x)),
+               b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -70,12 +88,21 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ x,
   // `gather` (optional): output row r is built from input row gather[r] (clique-sorted planes of the evaluation sweep)
   const T* row = x + (long long)(gather ? gather[warp] : warp) * ld;
 
-  float ss = 0.f, mx = 0.f, sm = 0.f;
-  for (int k = lane; k < d; k += 32) {
-    const float v = to_f32<T>(row[k]);
-    ss = fmaf(v, v, ss);
-    mx = fmaxf(mx, fabsf(v));
-    sm += v;
+  // HBM-bound row passes: 4 elements per lane and access when the rows are suitably aligned (the usual case)
+  const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && hi_t == nullptr;
+  float ss = 0.f, mx = 0.f;
+  if (vec) {
+    for (int k = lane * 4; k < d; k += 128) {
+      const float4 v = load4<T>(row + k);
+      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+      mx = fmaxf(fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+  } else {
+    for (int k = lane; k < d; k += 32) {
+      const float v = to_f32<T>(row[k]);
+      ss = fmaf(v, v, ss);
+      mx = fmaxf(mx, fabsf(v));
+    }
   }
   ss = warp_sum(ss);
   mx = warp_max(mx);
@@ -98,6 +125,34 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ x,
   float smx = 0.f;
   __half* hrow = hi + (long long)warp * d_pad;
   __half* lrow = lo ? lo + (long long)warp * d_pad : nullptr;
+  if (vec) {
+    for (int k = lane * 4; k < d_pad; k += 128) {  // d_pad is a multiple of 64, d of 4: a group is all data or all padding
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f), v = r;
+      if (k < d) {
+        r = load4<T>(row + k);
+        v = make_float4(r.x / div, r.y / div, r.z / div, r.w / div);  // IEEE division, as torch does
+      }
+      const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+      uint2 oh;
+      oh.x = *reinterpret_cast<const unsigned*>(&h0);
+      oh.y = *reinterpret_cast<const unsigned*>(&h1);
+      *reinterpret_cast<uint2*>(hrow + k) = oh;
+      if (lrow) {
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+        uint2 ol;
+        ol.x = *reinterpret_cast<const unsigned*>(&l0);
+        ol.y = *reinterpret_cast<const unsigned*>(&l1);
+        *reinterpret_cast<uint2*>(lrow + k) = ol;
+      }
+      if (stats && k < d) {
+        const float4 sv = stats_on_scaled ? v : r;
+        s1 += (double)sv.x + (double)sv.y + (double)sv.z + (double)sv.w;
+        s2 += (double)sv.x * sv.x + (double)sv.y * sv.y + (double)sv.z * sv.z + (double)sv.w * sv.w;
+        smx = fmaxf(fmaxf(smx, fmaxf(fabsf(sv.x), fabsf(sv.y))), fmaxf(fabsf(sv.z), fabsf(sv.w)));
+      }
+    }
+  } else {
   for (int k = lane; k < d_pad; k += 32) {
     float v = 0.f;
     if (k < d) v = to_f32<T>(row[k]) / div;  // IEEE division, as torch does
@@ -119,6 +174,7 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ x,
       smx = fmaxf(smx, fabsf(sv));
     }
   }
+  }
   if (lane == 0) {
     if (norm_out) norm_out[warp] = nrm;
     if (scale_out) scale_out[warp] = escale;
@@ -134,7 +190,6 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ x,
       atomicMax(&stats->maxabs_bits, __float_as_uint(smx));
     }
   }
-  (void)sm;
 }
 
 }  // namespace wealy
