@@ -2,14 +2,14 @@
 //
 // Workspace layout (fixed by (b, d, passes) so that backward finds what forward left):
 //   U planes (hi[,lo] [b][d_pad], norm, scale, sq) | U^T planes (hi[,lo] [d][b_pad]) | W planes (hi[,lo] [b][b_pad])
-//   | dU [b][d] f32 | label, idx [b] i32 | partial [parts_max][b][8] f32 | rowstat [b][4] f32 | ZStats | scal | flags
+//   | dU [b][d] f32 | {label, idx} [b256] int2 | partial [parts_max][b][8] f32 | rowstat [b256][4] f32 | ZStats | scal | flags
 
 struct LossWs {
   Planes u;
   __half *ut_hi, *ut_lo;
   __half *w_hi, *w_lo;
   float* du;
-  int *label, *idx;
+  int2* lab_idx;
   float* partial;
   float* rowstat;
   ZStats* zs;
@@ -36,11 +36,11 @@ static void loss_ws_layout(LossWs& w, uint8_t* base, int64_t b, int64_t d, int p
   w.w_lo = nullptr;
   if (passes == 3) { w.w_lo = reinterpret_cast<__half*>(cur); cur += wplane; }
   w.du = reinterpret_cast<float*>(cur); cur += align_up((size_t)nb * d * 4, 1024);
-  w.label = reinterpret_cast<int*>(cur); cur += align_up((size_t)b * 4, 256);
-  w.idx = reinterpret_cast<int*>(cur); cur += align_up((size_t)b * 4, 256);
+  const size_t b256 = (size_t)ceil_div(b, kTileN) * kTileN;  // per-tile bulk copies read whole 256-column groups
+  w.lab_idx = reinterpret_cast<int2*>(cur); cur += align_up(b256 * 8, 256);
   w.parts_max = (int)ceil_div(b, kTileN) * 2;
   w.partial = reinterpret_cast<float*>(cur); cur += align_up((size_t)w.parts_max * nb * kStatWidth * 4, 1024);
-  w.rowstat = reinterpret_cast<float*>(cur); cur += align_up((size_t)b * 16, 256);
+  w.rowstat = reinterpret_cast<float*>(cur); cur += align_up(b256 * 16, 256);
   w.zs = reinterpret_cast<ZStats*>(cur); cur += 256;
   w.scal = reinterpret_cast<float*>(cur); cur += 256;
   w.bad = reinterpret_cast<int*>(cur); cur += 256;
@@ -81,8 +81,7 @@ static void loss_params(LossParams& lp, const wealy_loss_cfg* cfg, const LossWs&
   lp.b = (int)b;
   lp.row0 = (int)row0;
   lp.nb = (int)nb;
-  lp.label = w.label;
-  lp.idx = w.idx;
+  lp.lab_idx = w.lab_idx;
   lp.c2 = log2e / cfg->temperature;
   lp.g2 = cfg->gamma * log2e;
   lp.b2 = cfg->b * log2e;
@@ -129,8 +128,8 @@ static int loss_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t 
   loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes, nb);
   const int T = 256;
   CU_TRY(cudaMemsetAsync(w.zs, 0, 1280, s));  // ZStats, scal, flags, batch accumulators
-  ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, w.label, (int)b, w.bad);
-  ids_to_i32_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_idx, w.idx, (int)b, w.bad);
+  pack_ids_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, (const long long*)z_idx, w.lab_idx, (int)b,
+                                                        w.bad);
   CU_TRY(cudaGetLastError());
   const bool ntx = cfg->kind == WEALY_LOSS_NTXENT;
   // NT-Xent: x/(|x|+1e-6) and statistics of the raw z; CLEWS: F.normalize (eps 1e-12), statistics of the normalised z

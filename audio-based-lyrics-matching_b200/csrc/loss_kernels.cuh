@@ -26,17 +26,48 @@ struct LossParams {
   int kind;
   int b;                // (global) batch size = number of columns
   int row0, nb;         // data-parallel sharding: this launch owns anchors [row0, row0 + nb) (0, b on one GPU)
-  const int* label;     // [b]
-  const int* idx;       // [b]
+  const int2* lab_idx;  // [b padded to 256] {label, idx} (range-checked from int64)
   float c2;             // NT-Xent: log2(e) / tau
   float g2, b2;         // CLEWS: gamma * log2(e), b * log2(e)
   // statistics sweep
   float* partial;       // [parts][b][kStatWidth]
   // W sweep
-  const float* rowstat; // [b][4]
+  const float* rowstat; // [b padded to 256][4]
   __half* w_hi;         // [b][ldw] (ldw = b padded to the k-block)
   __half* w_lo;         // nullable
   long long ldw;
+};
+
+// int64 labels / ids -> packed int32 pairs (one 8-byte record per sample: the per-tile column slot is one bulk copy)
+__global__ void pack_ids_kernel(const long long* __restrict__ label, const long long* __restrict__ idx, int2* __restrict__ out,
+                                int n, int* bad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long a = label[t], b = idx[t];
+  if (a > 2147483647ll || a < -2147483648ll || b > 2147483647ll || b < -2147483648ll) atomicAdd(bad, 1);
+  out[t] = make_int2((int)a, (int)b);
+}
+
+// Per-tile column data of the loss epilogues, bulk-copied into shared memory by the TMA thread (gemm_core.cuh):
+// the 256 columns' backward records (float4 rowstat) and {label, idx} pairs -- instead of three global loads per
+// matrix element.
+struct LossColSlots {
+  static constexpr int kColSlots = 3;
+  static constexpr int kLvlBytes = kTileN * 16;   // rowstat
+  static constexpr int kInfoBytes = kTileN * 8;   // {label, idx}
+  static constexpr int kColSlotBytes = kLvlBytes + kInfoBytes;
+  static constexpr int kOffColSlots = 0;
+  static constexpr int kCtaScratchBytes = kColSlots * kColSlotBytes;
+  __device__ static __forceinline__ void col_bulk_src(const LossParams& p, int t, const void*& s0, const void*& s1) {
+    s0 = p.rowstat + (size_t)t * kTileN * 4;
+    s1 = p.lab_idx + (size_t)t * kTileN;
+  }
+  __device__ static __forceinline__ const float4* col_stat(const EpiCtx& c, int col0) {
+    return reinterpret_cast<const float4*>(c.col_slot) + (col0 & (kTileN - 1));
+  }
+  __device__ static __forceinline__ const int2* col_ids(const EpiCtx& c, int col0) {
+    return reinterpret_cast<const int2*>(c.col_slot + kLvlBytes) + (col0 & (kTileN - 1));
+  }
 };
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
@@ -46,10 +77,9 @@ __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); 
 //   NT-Xent partial: {m2 (running max of logits in log2 units), A = sum exp, P = sum_pos exp}
 //   CLEWS   partial: {npos, nneg, sum_pos d, sum_neg X, sum_all d, sum_neg d}
 // ---------------------------------------------------------------------------------------------
-struct LossStatsEpi {
+struct LossStatsEpi : LossColSlots {
   using Params = LossParams;
   static constexpr int kWarpScratchBytes = 0;
-  static constexpr int kCtaScratchBytes = 0;
   struct RowState {
     int lab, id;
     bool valid;
@@ -58,15 +88,17 @@ struct LossStatsEpi {
 
   __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, const EpiCtx&) {
     st.valid = row < p.nb;
-    st.lab = st.valid ? p.label[p.row0 + row] : 0;
-    st.id = st.valid ? p.idx[p.row0 + row] : 0;
+    const int2 li = st.valid ? p.lab_idx[p.row0 + row] : make_int2(0, 0);
+    st.lab = li.x;
+    st.id = li.y;
     st.a0 = p.kind == kLossNtxent ? neg_inf() : 0.f;
     st.a1 = st.a2 = st.a3 = st.a4 = st.a5 = 0.f;
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape&, const EpiCtx&) {
+                                                 const uint32_t (&acc)[32], const GemmShape&, const EpiCtx& ctx) {
     if (!st.valid || col0 >= p.b) return;
+    const int2* cid = col_ids(ctx, col0);  // broadcast shared-memory reads
     if (p.kind == kLossNtxent) {
       float l[32];
       float cm = neg_inf();
@@ -86,9 +118,9 @@ struct LossStatsEpi {
       if (st.a0 == neg_inf()) return;
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const int j = min(col0 + e, p.b - 1);
-        const float ex = exp2f(l[e] - st.a0);  // masked entries: exp2(-inf) = 0
-        const bool pos = (__ldg(p.label + j) == st.lab) && (__ldg(p.idx + j) != st.id);
+        const float ex = exp2f(l[e] - st.a0);  // masked entries (incl. columns >= b): exp2(-inf) = 0
+        const int2 cj = cid[e];
+        const bool pos = (cj.x == st.lab) && (cj.y != st.id);
         st.a1 += ex;
         st.a2 += pos ? ex : 0.f;
       }
@@ -99,8 +131,9 @@ struct LossStatsEpi {
         if (j < p.b) {
           const float s = __uint_as_float(acc[e]);
           const float d = 1.f - s;
-          const bool same = __ldg(p.label + j) == st.lab;
-          const bool pos = same && (__ldg(p.idx + j) != st.id);
+          const int2 cj = cid[e];
+          const bool same = cj.x == st.lab;
+          const bool pos = same && (cj.y != st.id);
           const float x = exp2f(fmaf(-p.g2, d, p.b2));  // exp(b - gamma d)
           st.a0 += pos ? 1.f : 0.f;
           st.a1 += same ? 0.f : 1.f;
@@ -128,10 +161,9 @@ struct LossStatsEpi {
 //   NT-Xent rowstat = {M2, a', b', -}:  dS_ij = E_ij (b'_i - pos a'_i),  E_ij = exp2(l2_ij - M2_i)   (scale = B)
 //   CLEWS   rowstat = {ca', cu', -, -}: dS_ij = -pos ca'_i + X_ij neg cu'_i                          (scale = S, see finalize)
 // ---------------------------------------------------------------------------------------------
-struct LossWEpi {
+struct LossWEpi : LossColSlots {
   using Params = LossParams;
   static constexpr int kWarpScratchBytes = 0;
-  static constexpr int kCtaScratchBytes = 0;
   struct RowState {
     int lab, id;
     bool valid;
@@ -140,8 +172,9 @@ struct LossWEpi {
 
   __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int, const GemmShape&, const EpiCtx&) {
     st.valid = row < p.nb;
-    st.lab = st.valid ? p.label[p.row0 + row] : 0;
-    st.id = st.valid ? p.idx[p.row0 + row] : 0;
+    const int2 li = st.valid ? p.lab_idx[p.row0 + row] : make_int2(0, 0);
+    st.lab = li.x;
+    st.id = li.y;
     const float4 r = st.valid ? reinterpret_cast<const float4*>(p.rowstat)[p.row0 + row] : make_float4(0.f, 0.f, 0.f, 0.f);
     st.r0 = r.x;
     st.r1 = r.y;
@@ -149,8 +182,10 @@ struct LossWEpi {
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
-                                                 const uint32_t (&acc)[32], const GemmShape&, const EpiCtx&) {
+                                                 const uint32_t (&acc)[32], const GemmShape&, const EpiCtx& ctx) {
     if (!st.valid || col0 >= p.ldw) return;
+    const float4* cst = col_stat(ctx, col0);  // broadcast shared-memory reads
+    const int2* cid = col_ids(ctx, col0);
     __align__(16) __half hi[32];
     __align__(16) __half lo[32];
 #pragma unroll
@@ -159,9 +194,10 @@ struct LossWEpi {
       float w = 0.f;
       if (j < p.b && j != p.row0 + row) {
         const float s = __uint_as_float(acc[e]);
-        const float4 cj = __ldg(reinterpret_cast<const float4*>(p.rowstat) + j);
-        const bool same = __ldg(p.label + j) == st.lab;
-        const bool pos = same && (__ldg(p.idx + j) != st.id);
+        const float4 cj = cst[e];
+        const int2 ci = cid[e];
+        const bool same = ci.x == st.lab;
+        const bool pos = same && (ci.y != st.id);
         if (p.kind == kLossNtxent) {
           const float l2 = s * p.c2;
           const float eij = exp2f(l2 - st.r0);
