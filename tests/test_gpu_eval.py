@@ -346,3 +346,12 @@ def test_symmetric_sweep_randomised_shapes():
         d = int(torch.randint(8, 300, (1,), generator=g))
         s = syn.make_eval_set(n, d, seed=1000 + trial, sigma=float(1.0 + 3.0 * torch.rand(1, generator=g)))
         _oracle_match(s["c"], s["i"], s["z"])
+
+
+def test_config1_shs100k_test_shape_full_parity():
+    """BASELINE.json configs[0]: the SHS100K-TEST-shaped evaluation the reference can run on CPU -- 10 547 versions in
+    1 692 cliques (the exact clique-size multiset of the shipped split), 1024-d.  Every query against the oracle."""
+    s = _synth().make_eval_set(10547, 1024, seed=0)
+    assert int(torch.bincount(s["c"]).gt(0).sum()) == 1692
+    aps, r1s, aps_o, r1_o = _oracle_match(s["c"], s["i"], s["z"])
+    assert abs(float(r1s.double().mean()) - float(r1_o.mean())) <= 1e-4 * float(r1_o.mean())      # MR1 within 1e-4
