@@ -167,27 +167,25 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
     for (int t = 0; t < ntile; ++t) {
       const long long rb = ((long long)j * ks + min(t * 8 + g, ks - 1)) * d_pad;  // B column g = candidate chunk t * 8 + g
       float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-      for (int k = 0; k < d_pad; k += 16) {
-        const int ko = k + tig * 2;
-        unsigned ah[4], bh[2];
-        ah[0] = __ldg(reinterpret_cast<const unsigned*>(q_hi + ra0 + ko));
-        ah[1] = __ldg(reinterpret_cast<const unsigned*>(q_hi + ra1 + ko));
-        ah[2] = __ldg(reinterpret_cast<const unsigned*>(q_hi + ra0 + ko + 8));
-        ah[3] = __ldg(reinterpret_cast<const unsigned*>(q_hi + ra1 + ko + 8));
-        bh[0] = __ldg(reinterpret_cast<const unsigned*>(c_hi + rb + ko));
-        bh[1] = __ldg(reinterpret_cast<const unsigned*>(c_hi + rb + ko + 8));
-        mma_16x8x16(c, ah, bh);
+      // (8 consecutive halves per lane, row and 32-wide k window: see pos_pairs_sorted_kernel)
+#pragma unroll 2
+      for (int k = 0; k < d_pad; k += 32) {
+        const int ko = k + tig * 8;
+        const uint4 ah0 = __ldg(reinterpret_cast<const uint4*>(q_hi + ra0 + ko)), ah1 = __ldg(reinterpret_cast<const uint4*>(q_hi + ra1 + ko));
+        const uint4 bh = __ldg(reinterpret_cast<const uint4*>(c_hi + rb + ko));
+        const unsigned a1[4] = {ah0.x, ah1.x, ah0.y, ah1.y}, a2[4] = {ah0.z, ah1.z, ah0.w, ah1.w};
+        const unsigned b1[2] = {bh.x, bh.y}, b2[2] = {bh.z, bh.w};
+        mma_16x8x16(c, a1, b1);
+        mma_16x8x16(c, a2, b2);
         if (q_lo) {
-          unsigned al[4], bl[2];
-          al[0] = __ldg(reinterpret_cast<const unsigned*>(q_lo + ra0 + ko));
-          al[1] = __ldg(reinterpret_cast<const unsigned*>(q_lo + ra1 + ko));
-          al[2] = __ldg(reinterpret_cast<const unsigned*>(q_lo + ra0 + ko + 8));
-          al[3] = __ldg(reinterpret_cast<const unsigned*>(q_lo + ra1 + ko + 8));
-          bl[0] = __ldg(reinterpret_cast<const unsigned*>(c_lo + rb + ko));
-          bl[1] = __ldg(reinterpret_cast<const unsigned*>(c_lo + rb + ko + 8));
-          mma_16x8x16(c, ah, bl);
-          mma_16x8x16(c, al, bh);
+          const uint4 al0 = __ldg(reinterpret_cast<const uint4*>(q_lo + ra0 + ko)), al1 = __ldg(reinterpret_cast<const uint4*>(q_lo + ra1 + ko));
+          const uint4 bl = __ldg(reinterpret_cast<const uint4*>(c_lo + rb + ko));
+          const unsigned l1[4] = {al0.x, al1.x, al0.y, al1.y}, l2[4] = {al0.z, al1.z, al0.w, al1.w};
+          const unsigned m1[2] = {bl.x, bl.y}, m2[2] = {bl.z, bl.w};
+          mma_16x8x16(c, a1, m1);
+          mma_16x8x16(c, a2, m2);
+          mma_16x8x16(c, l1, b1);
+          mma_16x8x16(c, l2, b2);
         }
       }
       // c[0], c[1]: row g, candidate chunks t*8 + 2 tig, + 1;  c[2], c[3]: row g + 8, same columns
@@ -306,27 +304,27 @@ __global__ void __launch_bounds__(256) pos_pairs_sorted_kernel(
     const __half* b_hi = hi + (long long)jb * d_pad;
     const __half* b_lo = lo ? lo + (long long)jb * d_pad : nullptr;
     float c[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
-    for (int k = 0; k < d_pad; k += 16) {
-      const int ko = k + tig * 2;
-      unsigned ah[4], bh[2];
-      ah[0] = __ldg(reinterpret_cast<const unsigned*>(a_hi0 + ko));
-      ah[1] = __ldg(reinterpret_cast<const unsigned*>(a_hi1 + ko));
-      ah[2] = __ldg(reinterpret_cast<const unsigned*>(a_hi0 + ko + 8));
-      ah[3] = __ldg(reinterpret_cast<const unsigned*>(a_hi1 + ko + 8));
-      bh[0] = __ldg(reinterpret_cast<const unsigned*>(b_hi + ko));
-      bh[1] = __ldg(reinterpret_cast<const unsigned*>(b_hi + ko + 8));
-      mma_16x8x16(c, ah, bh);
+    // A dot product does not care in which order k is visited as long as A and B agree: every lane loads 8
+    // CONSECUTIVE halves per row and 32-wide k window (one 16-byte access instead of four 4-byte ones) and feeds
+    // them to two MMAs as if they were the fragment's (2 tig, 2 tig + 1, 2 tig + 8, 2 tig + 9) elements.
+#pragma unroll 2
+    for (int k = 0; k < d_pad; k += 32) {
+      const int ko = k + tig * 8;
+      const uint4 ah0 = __ldg(reinterpret_cast<const uint4*>(a_hi0 + ko)), ah1 = __ldg(reinterpret_cast<const uint4*>(a_hi1 + ko));
+      const uint4 bh = __ldg(reinterpret_cast<const uint4*>(b_hi + ko));
+      const unsigned a1[4] = {ah0.x, ah1.x, ah0.y, ah1.y}, a2[4] = {ah0.z, ah1.z, ah0.w, ah1.w};
+      const unsigned b1[2] = {bh.x, bh.y}, b2[2] = {bh.z, bh.w};
+      mma_16x8x16(c, a1, b1);
+      mma_16x8x16(c, a2, b2);
       if (lo) {
-        unsigned al[4], bl[2];
-        al[0] = __ldg(reinterpret_cast<const unsigned*>(a_lo0 + ko));
-        al[1] = __ldg(reinterpret_cast<const unsigned*>(a_lo1 + ko));
-        al[2] = __ldg(reinterpret_cast<const unsigned*>(a_lo0 + ko + 8));
-        al[3] = __ldg(reinterpret_cast<const unsigned*>(a_lo1 + ko + 8));
-        bl[0] = __ldg(reinterpret_cast<const unsigned*>(b_lo + ko));
-        bl[1] = __ldg(reinterpret_cast<const unsigned*>(b_lo + ko + 8));
-        mma_16x8x16(c, ah, bl);
-        mma_16x8x16(c, al, bh);
+        const uint4 al0 = __ldg(reinterpret_cast<const uint4*>(a_lo0 + ko)), al1 = __ldg(reinterpret_cast<const uint4*>(a_lo1 + ko));
+        const uint4 bl = __ldg(reinterpret_cast<const uint4*>(b_lo + ko));
+        const unsigned l1[4] = {al0.x, al1.x, al0.y, al1.y}, l2[4] = {al0.z, al1.z, al0.w, al1.w};
+        const unsigned m1[2] = {bl.x, bl.y}, m2[2] = {bl.z, bl.w};
+        mma_16x8x16(c, a1, m1);
+        mma_16x8x16(c, a2, m2);
+        mma_16x8x16(c, l1, b1);
+        mma_16x8x16(c, l2, b2);
       }
     }
     // c[0], c[1]: query q0 + g, candidates j0 + 2 tig, + 1;  c[2], c[3]: query q0 + g + 8, same candidates
