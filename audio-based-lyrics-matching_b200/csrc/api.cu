@@ -341,6 +341,116 @@ extern "C" int wealy_sim_matrix(const void* x, int64_t n, int64_t ldx, const voi
 }
 
 // ------------------------------------------------------------------------------------------
+// a1 under autograd (lib/losses.py:45 differentiates through pairwise_distance_matrix): gradient of the cosine
+// modes.  S = X^ Y^T with x^ = x / (|x| + eps):  dX^ = G Y^,  dY^ = G^T X^,  then the normalisation Jacobian.
+// Both products run on the contraction core: the gradient matrix (and its transpose) are split into fp16 hi/lo
+// planes with an exact power-of-two row scale, the normalised operands are transposed into K-major planes.
+// ------------------------------------------------------------------------------------------
+static size_t tplane_bytes(int64_t rows, int64_t k, int passes) {
+  return align_up((size_t)rows * pad_k(k) * 2, 1024) * (passes == 3 ? 2 : 1);
+}
+
+extern "C" size_t wealy_sim_matrix_backward_workspace_bytes(int64_t n, int64_t m, int64_t d, int passes) {
+  if (n <= 0 || m <= 0 || d <= 0) return 0;
+  return planes_bytes(n, d, passes) + planes_bytes(m, d, passes) + planes_bytes(n, m, passes) + planes_bytes(m, n, passes) +
+         tplane_bytes(d, n, passes) + tplane_bytes(d, m, passes) + align_up((size_t)n * d * 4, 1024) +
+         align_up((size_t)m * d * 4, 1024) + 8192;
+}
+
+template <typename T>
+static void launch_jacobian(const void* z, int64_t ldz, int64_t rows, int64_t d, float eps, const float* norm, const float* du,
+                            const float* scal, void* dz, int64_t ld_dz, cudaStream_t s) {
+  loss_jacobian_kernel<T><<<(unsigned)ceil_div(rows * 32, 256), 256, 0, s>>>(kLossNtxent, eps, (const T*)z, (long long)ldz, (int)rows,
+                                                                           (int)d, norm, du, scal, nullptr, (T*)dz,
+                                                                           (long long)ld_dz);
+}
+
+__global__ void fill_f32_kernel(float* p, float v, int n) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) p[t] = v;
+}
+
+extern "C" int wealy_sim_matrix_backward(const void* x, int64_t n, int64_t ldx, const void* y, int64_t m, int64_t ldy,
+                                         int64_t d, int in_dtype, int mode, float eps, int passes, const void* grad,
+                                         int64_t ld_grad, const void* grad_t, int64_t ld_grad_t, void* dx, int64_t ld_dx,
+                                         void* dy, int64_t ld_dy, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n <= 0 || m <= 0 || d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad shape n=%lld m=%lld d=%lld", (long long)n, (long long)m, (long long)d);
+  if (!x || !y || !grad || !grad_t || !dx || !dy || !workspace) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (mode != WEALY_MODE_COSSIM && mode != WEALY_MODE_COS)
+    return fail(WEALY_ERR_UNSUPPORTED, "the gradient is built for the cosine modes (cos / cossim)");
+  if (passes != 1 && passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
+  if (workspace_bytes < wealy_sim_matrix_backward_workspace_bytes(n, m, d, passes)) return fail(WEALY_ERR_WORKSPACE, "workspace too small");
+  uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024));
+  Planes px, py, pg, pgt;
+  carve_planes(px, cur, n, d, passes);
+  carve_planes(py, cur, m, d, passes);
+  carve_planes(pg, cur, n, m, passes);    // G   [n][m_pad], row scale 2^e
+  carve_planes(pgt, cur, m, n, passes);   // G^T [m][n_pad]
+  const int64_t n_pad = pad_k(n), m_pad = pad_k(m);
+  auto carve_t = [&](__half*& h, __half*& l, int64_t k) {
+    const size_t plane = align_up((size_t)d * pad_k(k) * 2, 1024);
+    h = reinterpret_cast<__half*>(cur); cur += plane;
+    l = nullptr;
+    if (passes == 3) { l = reinterpret_cast<__half*>(cur); cur += plane; }
+  };
+  __half *xt_hi, *xt_lo, *yt_hi, *yt_lo;
+  carve_t(xt_hi, xt_lo, n);  // X^T [d][n_pad]
+  carve_t(yt_hi, yt_lo, m);  // Y^T [d][m_pad]
+  float* dxh = reinterpret_cast<float*>(cur); cur += align_up((size_t)n * d * 4, 1024);
+  float* dyh = reinterpret_cast<float*>(cur); cur += align_up((size_t)m * d * 4, 1024);
+  float* scal = reinterpret_cast<float*>(cur); cur += 256;
+
+  W_TRY(launch_prep(x, ldx, n, d, in_dtype, kPrepL2AddEps, eps, px, nullptr, nullptr, 0, nullptr, 0, s));
+  W_TRY(launch_prep(y, ldy, m, d, in_dtype, kPrepL2AddEps, eps, py, nullptr, nullptr, 0, nullptr, 0, s));
+  W_TRY(launch_prep(grad, ld_grad, n, m, in_dtype, kPrepRawPow2, 0.f, pg, nullptr, nullptr, 0, nullptr, 0, s));
+  W_TRY(launch_prep(grad_t, ld_grad_t, m, n, in_dtype, kPrepRawPow2, 0.f, pgt, nullptr, nullptr, 0, nullptr, 0, s));
+  {
+    dim3 gx((unsigned)ceil_div(n_pad, 32), (unsigned)ceil_div(d, 32), px.lo ? 2 : 1);
+    transpose_plane_kernel<<<gx, 256, 0, s>>>(px.hi, px.lo, (int)n, (int)d, (long long)px.d_pad, xt_hi, xt_lo, (long long)n_pad);
+    dim3 gy((unsigned)ceil_div(m_pad, 32), (unsigned)ceil_div(d, 32), py.lo ? 2 : 1);
+    transpose_plane_kernel<<<gy, 256, 0, s>>>(py.hi, py.lo, (int)m, (int)d, (long long)py.d_pad, yt_hi, yt_lo, (long long)m_pad);
+    fill_f32_kernel<<<1, 32, 0, s>>>(scal, mode == WEALY_MODE_COS ? -1.f : 1.f, 1);  // d(1 - S) = -dS
+    CU_TRY(cudaGetLastError());
+  }
+  auto product = [&](const Planes& g, __half* bt_hi, __half* bt_lo, int64_t rows, int64_t k_pad, float* out) -> int {
+    Planes pa = g, pb;
+    pa.rows = rows;
+    pb.hi = bt_hi; pb.lo = bt_lo; pb.rows = d; pb.d_pad = k_pad;
+    StoreParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.out = out;
+    sp.ld = d;
+    sp.mode = kSimDotsim;   // s * row scale (the transposed operands carry no scale)
+    sp.out_dtype = kOutF32;
+    sp.post = 1.f;
+    sp.rscale = g.scale;
+    GemmShape sh;
+    fill_shape(sh, rows, d, k_pad, 64, 1 << 20);
+    return launch_gemm<StoreEpi>(passes, pa, pb, sh, sp, s);
+  };
+  W_TRY(product(pg, yt_hi, yt_lo, n, m_pad, dxh));   // dX^ = G Y^
+  W_TRY(product(pgt, xt_hi, xt_lo, m, n_pad, dyh));  // dY^ = G^T X^
+  switch (in_dtype) {
+    case WEALY_F32:
+      launch_jacobian<float>(x, ldx, n, d, eps, px.norm, dxh, scal, dx, ld_dx, s);
+      launch_jacobian<float>(y, ldy, m, d, eps, py.norm, dyh, scal, dy, ld_dy, s);
+      break;
+    case WEALY_F16:
+      launch_jacobian<__half>(x, ldx, n, d, eps, px.norm, dxh, scal, dx, ld_dx, s);
+      launch_jacobian<__half>(y, ldy, m, d, eps, py.norm, dyh, scal, dy, ld_dy, s);
+      break;
+    case WEALY_BF16:
+      launch_jacobian<__nv_bfloat16>(x, ldx, n, d, eps, px.norm, dxh, scal, dx, ld_dx, s);
+      launch_jacobian<__nv_bfloat16>(y, ldy, m, d, eps, py.norm, dyh, scal, dy, ld_dy, s);
+      break;
+    default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", in_dtype);
+  }
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // a7: evaluation plan + run
 // ------------------------------------------------------------------------------------------
 struct wealy_eval_plan {

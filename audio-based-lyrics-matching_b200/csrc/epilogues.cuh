@@ -55,7 +55,7 @@ struct StoreEpi {
     switch (p.mode) {
       case kSimCossim: return s;
       case kSimCos: return 1.f - s;
-      case kSimDotsim: return s * st.rs * __ldg(p.cscale + col);
+      case kSimDotsim: return s * st.rs * (p.cscale ? __ldg(p.cscale + col) : 1.f);
       case kSimDot: return 1.f - s * st.rs * __ldg(p.cscale + col);
       default: {
         const float dot = s * st.rs * __ldg(p.cscale + col);

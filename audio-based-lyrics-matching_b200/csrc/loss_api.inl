@@ -202,17 +202,18 @@ static int loss_backward_rows(const wealy_loss_cfg* cfg, const void* z, int64_t 
   const unsigned blocks = (unsigned)ceil_div(nb * 32, T);
   const size_t esz = dtype == WEALY_F32 ? 4 : 2;
   const void* zrow = static_cast<const uint8_t*>(z) + (size_t)row0 * ldz * esz;
+  const float jeps = cfg->kind == WEALY_LOSS_NTXENT ? 1e-6f : 1e-12f;  // the normalisations of the forward (prep)
   switch (dtype) {
     case WEALY_F32:
-      loss_jacobian_kernel<float><<<blocks, T, 0, s>>>(cfg->kind, (const float*)zrow, (long long)ldz, (int)nb, (int)d,
+      loss_jacobian_kernel<float><<<blocks, T, 0, s>>>(cfg->kind, jeps, (const float*)zrow, (long long)ldz, (int)nb, (int)d,
                                                        w.u.norm + row0, w.du, w.scal, grad_out, (float*)dz, (long long)ld_dz);
       break;
     case WEALY_F16:
-      loss_jacobian_kernel<__half><<<blocks, T, 0, s>>>(cfg->kind, (const __half*)zrow, (long long)ldz, (int)nb, (int)d,
+      loss_jacobian_kernel<__half><<<blocks, T, 0, s>>>(cfg->kind, jeps, (const __half*)zrow, (long long)ldz, (int)nb, (int)d,
                                                         w.u.norm + row0, w.du, w.scal, grad_out, (__half*)dz, (long long)ld_dz);
       break;
     case WEALY_BF16:
-      loss_jacobian_kernel<__nv_bfloat16><<<blocks, T, 0, s>>>(cfg->kind, (const __nv_bfloat16*)zrow, (long long)ldz, (int)nb,
+      loss_jacobian_kernel<__nv_bfloat16><<<blocks, T, 0, s>>>(cfg->kind, jeps, (const __nv_bfloat16*)zrow, (long long)ldz, (int)nb,
                                                                (int)d, w.u.norm + row0, w.du, w.scal, grad_out,
                                                                (__nv_bfloat16*)dz, (long long)ld_dz);
       break;

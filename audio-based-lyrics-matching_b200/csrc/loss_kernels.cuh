@@ -438,7 +438,7 @@ __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) loss_jacobian_kernel(int kind, const T* __restrict__ z, long long ldz, int b, int d,
+__global__ void __launch_bounds__(256) loss_jacobian_kernel(int kind, float eps, const T* __restrict__ z, long long ldz, int b, int d,
                                                             const float* __restrict__ norm,
                                                             const float* __restrict__ du, const float* __restrict__ scal,
                                                             const float* __restrict__ grad_out, T* __restrict__ dz,
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(256) loss_jacobian_kernel(int kind, const T* _
   const int lane = (int)(threadIdx.x & 31);
   if (row >= b) return;
   const float r = norm[row];
-  const float div = kind == kLossNtxent ? r + 1e-6f : fmaxf(r, 1e-12f);
+  const float div = kind == kLossNtxent ? r + eps : fmaxf(r, eps);  // x / (|x| + eps)  or  x / max(|x|, eps)
   const float inv = 1.f / div;
   const T* zr = z + (long long)row * ldz;
   const float* g = du + (long long)row * d;

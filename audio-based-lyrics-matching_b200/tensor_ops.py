@@ -70,6 +70,38 @@ def _sim_matrix(x, y, mode, eps, post, precision):
     return out
 
 
+class _CosineMatrix(torch.autograd.Function):
+    """cos / cossim modes under autograd (the reference differentiates through them, lib/losses.py:45):
+    dX^ = G Y^ and dY^ = G^T X^ on the same tcgen05 core, then the Jacobian of x / (|x| + eps)."""
+
+    @staticmethod
+    def forward(ctx, x, y, mode, eps, precision):
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (mode, eps, precision)
+        return _sim_matrix(x.detach(), y.detach(), mode, eps, 1.0, precision)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        mode, eps, precision = ctx.cfg
+        xx, yy = _rows(x.detach()), _rows(y.detach())
+        n, d = xx.shape
+        m = yy.shape[0]
+        gg = g.to(xx.dtype).contiguous()
+        gt = gg.t().contiguous()
+        dx = torch.empty((n, d), dtype=xx.dtype, device=xx.device)
+        dy = torch.empty((m, d), dtype=xx.dtype, device=xx.device)
+        passes = passes_of(precision)
+        with torch.cuda.device(xx.device):
+            ws_bytes = N.lib.wealy_sim_matrix_backward_workspace_bytes(n, m, d, passes)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xx.device)
+            N.check(N.lib.wealy_sim_matrix_backward(
+                xx.data_ptr(), n, xx.stride(0), yy.data_ptr(), m, yy.stride(0), d, N.dtype_code(xx.dtype), mode,
+                float(eps), passes, gg.data_ptr(), gg.stride(0), gt.data_ptr(), gt.stride(0), dx.data_ptr(),
+                dx.stride(0), dy.data_ptr(), dy.stride(0), ws.data_ptr(), ws_bytes, N.stream_ptr(xx.device)))
+        return (dx if ctx.needs_input_grad[0] else None), (dy if ctx.needs_input_grad[1] else None), None, None, None
+
+
 def pairwise_euclidean_distance_matrix(x, y, squared=False, eps=1e-6, precision=None):
     """lib/tensor_ops.py:131-149: |x|^2 - 2 x.y + |y|^2, clamped at 0, optional sqrt (zeros stay 0).
     `eps` only guards the reference's autograd through sqrt(0); the forward value does not depend on it."""
@@ -87,9 +119,12 @@ def pairwise_distance_matrix(x, y, mode="fro", p=2, eps=1e-6, precision=None):
         y = y.unsqueeze(-1)
     if x.ndim == 0:
         raise NotImplementedError("wealy_b200: 0-d inputs")
-    if x.requires_grad or y.requires_grad:
-        raise NotImplementedError("wealy_b200.pairwise_distance_matrix: autograd is not provided; "
-                                  "use wealy_b200.losses for the fused differentiable losses")
+    if (x.requires_grad or y.requires_grad) and torch.is_grad_enabled():
+        if mode in ("cos", "cossim") and x.shape[0] > 0 and y.shape[0] > 0 and x.shape[1] > 0:
+            code = N.MODE_COSSIM if mode == "cossim" else N.MODE_COS
+            return _CosineMatrix.apply(x, y, code, eps, precision)
+        raise NotImplementedError("wealy_b200.pairwise_distance_matrix: autograd is provided for the cosine modes "
+                                  "(cos / cossim); use wealy_b200.losses for the fused differentiable losses")
     if mode == "euc" or mode == "neuc":
         p = 2
     d = x.size(-1)

@@ -63,6 +63,15 @@ int wealy_sim_matrix(const void* x, int64_t n, int64_t ldx, const void* y, int64
                      int in_dtype, int mode, float eps, float post, int passes, void* out, int64_t ld_out,
                      int out_dtype, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradient of the cosine modes of pairwise_distance_matrix (the reference differentiates through it,
+ * lib/losses.py:45).  grad [n][m] = dL/d(out) and grad_t [m][n] = its transpose (both with the input dtype);
+ * dx [n][d], dy [m][d] receive dL/dx, dL/dy (pass x == y twice and add the two when the operands are the same tensor). */
+size_t wealy_sim_matrix_backward_workspace_bytes(int64_t n, int64_t m, int64_t d, int passes);
+int wealy_sim_matrix_backward(const void* x, int64_t n, int64_t ldx, const void* y, int64_t m, int64_t ldy, int64_t d,
+                              int in_dtype, int mode, float eps, int passes, const void* grad, int64_t ld_grad,
+                              const void* grad_t, int64_t ld_grad_t, void* dx, int64_t ld_dx, void* dy, int64_t ld_dy,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- a7: fused retrieval evaluation -------------------------------------------------------
  * Self / same-clique masking by id, per-query ranking, AP / R1 (and optional top-k) without
  * materialising the Nq x Nc matrix.  The evaluator is not in the reference; argument vocabulary

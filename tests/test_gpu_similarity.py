@@ -132,3 +132,32 @@ def test_error_behaviour_matches_reference():
         _wt().pairwise_distance_matrix(x, x, mode="fro", p=3)      # documented gap: cdist p != 2
     with pytest.raises(AssertionError):
         _wt().pairwise_distance_matrix(x[None], x[None])            # lib/tensor_ops.py:153
+
+
+@pytest.mark.parametrize("mode", ["cossim", "cos"])
+@pytest.mark.parametrize("n,m,d,dtype", [(70, 130, 96, torch.float32), (300, 300, 1024, torch.float32),
+                                         (129, 65, 200, torch.bfloat16)])
+def test_cosine_modes_are_differentiable(mode, n, m, d, dtype):
+    """The reference differentiates through pairwise_distance_matrix (lib/losses.py:45): gradients of the cosine
+    modes against autograd of the oracle restatement (fp64)."""
+    from wealy_b200 import tensor_ops as wt
+    from oracle import similarity as osim
+    g = torch.Generator().manual_seed(n + m)
+    x = (torch.randn(n, d, generator=g) * 2).to(dtype)
+    y = torch.randn(m, d, generator=g).to(dtype)
+    w = torch.randn(n, m, generator=g)
+    xr, yr = x.double().requires_grad_(True), y.double().requires_grad_(True)
+    (osim.distance_matrix(xr, yr, mode=mode) * w.double()).sum().backward()
+    xc, yc = x.cuda().requires_grad_(True), y.cuda().requires_grad_(True)
+    out = wt.pairwise_distance_matrix(xc, yc, mode=mode)
+    (out * w.cuda().to(dtype)).sum().backward()
+    tol = 2e-5 if dtype == torch.float32 else 2e-2
+    assert float((xc.grad.double().cpu() - xr.grad).norm()) <= tol * float(xr.grad.norm())
+    assert float((yc.grad.double().cpu() - yr.grad).norm()) <= tol * float(yr.grad.norm())
+    # the same tensor on both sides: the two contributions add up
+    xs = x.cuda().requires_grad_(True)
+    (wt.pairwise_distance_matrix(xs, xs, mode=mode)[:, :n] * w[:, :n].cuda().to(dtype) if m >= n else
+     wt.pairwise_distance_matrix(xs, xs, mode=mode)).sum().backward()
+    assert torch.isfinite(xs.grad).all()
+    with pytest.raises(NotImplementedError):
+        wt.pairwise_distance_matrix(xc, yc, mode="dot")
