@@ -514,6 +514,15 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   ids_to_i32_kernel<<<(unsigned)ceil_div(nq, T), T, 0, s>>>((const long long*)queries_c, p->q_c, nq, bad);
   ids_to_i32_kernel<<<(unsigned)ceil_div(nq, T), T, 0, s>>>((const long long*)queries_i, p->q_i, nq, bad);
   p->same_ids = (queries_c == candidates_c && queries_i == candidates_i && p->nq == p->nc);
+  if (!p->same_ids && p->nq == p->nc) {
+    // equal ids in distinct buffers are still an all-vs-all problem (one extra 4-byte read-back decides it)
+    ids_differ_kernel<<<(unsigned)ceil_div(nq, T), T, 0, s>>>((const long long*)queries_c, (const long long*)queries_i,
+                                                             (const long long*)candidates_c, (const long long*)candidates_i, nq, bad + 8);
+    int differ = 1;
+    CU_TRY(cudaMemcpyAsync(&differ, bad + 8, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_TRY(cudaStreamSynchronize(s));
+    p->same_ids = differ == 0;
+  }
   if (p->same_ids) {
     p->c_c = p->q_c;
     p->c_i = p->q_i;

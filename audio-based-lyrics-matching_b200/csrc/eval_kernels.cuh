@@ -20,6 +20,13 @@ __global__ void ids_to_i32_kernel(const long long* __restrict__ in, int* __restr
   out[t] = (int)v;
 }
 
+// do two (clique, version) id sets hold the same values?  (an all-vs-all call may pass equal but distinct tensors)
+__global__ void ids_differ_kernel(const long long* __restrict__ a_c, const long long* __restrict__ a_i,
+                                  const long long* __restrict__ b_c, const long long* __restrict__ b_i, int n, int* differ) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && (a_c[t] != b_c[t] || a_i[t] != b_i[t])) *differ = 1;
+}
+
 __global__ void iota_kernel(int* out, int n) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) out[t] = t;

@@ -355,3 +355,17 @@ def test_config1_shs100k_test_shape_full_parity():
     assert int(torch.bincount(s["c"]).gt(0).sum()) == 1692
     aps, r1s, aps_o, r1_o = _oracle_match(s["c"], s["i"], s["z"])
     assert abs(float(r1s.double().mean()) - float(r1_o.mean())) <= 1e-4 * float(r1_o.mean())      # MR1 within 1e-4
+
+
+def test_equal_ids_in_distinct_tensors_take_the_all_vs_all_path():
+    we = _we()
+    s = _synth().make_eval_set(1500, 64, seed=41)
+    c, i, z = s["c"].cuda(), s["i"].cuda(), s["z"].cuda()
+    a1, r1 = we.evaluate(c, i, z, c, i, z)
+    a2, r2 = we.evaluate(c, i, z, c.clone(), i.clone(), z)          # same values, other buffers
+    assert torch.equal(a1, a2) and torch.equal(r1, r2)
+    p = we.EvalPlan(c, i, c.clone(), i.clone())
+    p.sweep_shard(z, 0, 1)                                          # the symmetric sweep needs an all-vs-all plan
+    i2 = i.clone(); i2[3] += 1
+    with pytest.raises(AssertionError):
+        we.EvalPlan(c, i, c.clone(), i2).sweep_shard(z, 0, 2)
