@@ -193,6 +193,76 @@ __device__ __noinline__ float warp_select_topk_big(float* val, int* idx, int n, 
   return warp_select_topk<kPerLane>(val, idx, n, k, lane);
 }
 
+// Streaming variant used while a sweep is running: the list only has to shrink to ABOUT k entries and the filter only
+// has to be a lower bound of the k-th best, so the bisection stops as soon as at most k + kSlackTopk entries lie at
+// or above the prefix found so far (16-20 of the 32 steps on similarity data; exact ties fall through to all 32).
+// Keeps every entry above the prefix (plus entries equal to it up to k); returns the filter, *kept = survivors.
+constexpr int kSlackTopk = 24;
+template <int kPerLane>
+__device__ __forceinline__ float warp_compact_topk(float* val, int* idx, int n, int k, int lane, int* kept) {
+  constexpr unsigned kFull = 0xffffffffu;
+  __syncwarp();
+  unsigned key[kPerLane];
+  int id[kPerLane];
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const int e = j * 32 + lane;
+    const bool ok = e < n;
+    key[j] = ok ? float_order_key(val[e]) : 0u;
+    id[j] = ok ? idx[e] : -1;
+  }
+  unsigned T = 0;
+  int at_or_above = n;  // entries with key >= T
+  for (int b = 31; b >= 0; --b) {
+    const unsigned cand = T | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kPerLane; ++j) c += key[j] >= cand;
+    c = __reduce_add_sync(kFull, c);
+    if (c >= k) { T = cand; at_or_above = c; }  // warp-uniform
+    if (at_or_above <= k + kSlackTopk) break;
+  }
+  int g = 0, q = 0;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    g += key[j] > T;
+    q += key[j] == T;
+  }
+  int gi = g, qi = q;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int tg = __shfl_up_sync(kFull, gi, o);
+    const int tq = __shfl_up_sync(kFull, qi, o);
+    if (lane >= o) { gi += tg; qi += tq; }
+  }
+  const int G = __shfl_sync(kFull, gi, 31), Q = __shfl_sync(kFull, qi, 31);
+  const int limit = G > k ? G : k;  // entries equal to the prefix are kept while fewer than k survive
+  int pg = gi - g;
+  int pq = G + (qi - q);
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    if (key[j] > T) {
+      val[pg] = float_from_order_key(key[j]);
+      idx[pg] = id[j];
+      ++pg;
+    } else if (key[j] == T && key[j] != 0u) {
+      if (pq < limit) {
+        val[pq] = float_from_order_key(key[j]);
+        idx[pq] = id[j];
+      }
+      ++pq;
+    }
+  }
+  __syncwarp();
+  *kept = G + Q < limit ? G + Q : limit;
+  return float_from_order_key(T);
+}
+template <int kPerLane>
+__device__ __noinline__ float warp_compact_topk_big(float* val, int* idx, int n, int k, int lane, int* kept) {
+  return warp_compact_topk<kPerLane>(val, idx, n, k, lane, kept);
+}
+
 struct EvalParams {
   const float* lim;        // [nq] lowest relevant similarity of the query (+inf if none)
   const int* q_c;          // [nq] clique ids
@@ -429,11 +499,12 @@ struct EvalEpiT {
       need &= need - 1;
       const long long cb = st.cbase + (long long)(src / kS - lane / kS) * p.cap;
       const int n = ncand[src];
-      const float kth = p.cap <= 256   ? warp_select_topk<8>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
-                        : p.cap <= 512 ? warp_select_topk_big<16>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane)
-                                       : warp_select_topk_big<32>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane);
+      int kept = p.topk;
+      const float kth = p.cap <= 256   ? warp_compact_topk<8>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane, &kept)
+                        : p.cap <= 512 ? warp_compact_topk_big<16>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane, &kept)
+                                       : warp_compact_topk_big<32>(p.cand_val + cb, p.cand_idx + cb, n, p.topk, lane, &kept);
       if (lane == src) {
-        ncand[lane] = p.topk;
+        ncand[lane] = kept;
         st.tau = kth;
         st.lim = fminf(st.tlim, st.tau);
       }
