@@ -108,13 +108,15 @@ static EncodeTiledFn encode_fn() {
 }
 
 // fp16 plane [rows][d_pad] row-major; box = [box_rows][block_k] with (2 * block_k)-byte swizzle
-static int make_plane_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t d_pad, int box_rows, int block_k) {
+static int make_plane_tmap(CUtensorMap* m, const void* base, int64_t rows, int64_t d_pad, int box_rows, int block_k,
+                           int row_stride = 1) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(WEALY_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)d_pad * 2};
-  cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
+  // row_stride > 1: every row_stride-th row of a (box_rows * row_stride)-row window lands in the box_rows smem rows
+  cuuint32_t box[2] = {(cuuint32_t)block_k, (cuuint32_t)(box_rows * row_stride)};
+  cuuint32_t estr[2] = {1, (cuuint32_t)row_stride};
   const CUtensorMapSwizzle sw = block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -159,12 +161,12 @@ static void carve_planes(Planes& p, uint8_t*& cur, int64_t rows, int64_t d, int 
 
 static int launch_prep(const void* x, int64_t ld, int64_t n, int64_t d, int dtype, int mode, float eps,
                        const Planes& p, __half* hi_t, __half* lo_t, int64_t ld_t, ZStats* stats, int stats_on_scaled,
-                       cudaStream_t s, const int* gather = nullptr) {
+                       cudaStream_t s, const int* gather = nullptr, int spread_n = 0) {
   if (n == 0) return WEALY_OK;
   const int threads = 256;
   const unsigned blocks = (unsigned)ceil_div(n * 32, threads);
 #define PREP_ARGS (long long)ld, (int)n, (int)d, (int)p.d_pad, mode, eps, stats_on_scaled, p.hi, p.lo, hi_t, lo_t, \
-                  (long long)ld_t, p.norm, p.scale, p.sq, stats, gather
+                  (long long)ld_t, p.norm, p.scale, p.sq, stats, gather, spread_n
   switch (dtype) {
     case WEALY_F32: prep_rows_kernel<float><<<blocks, threads, 0, s>>>((const float*)x, PREP_ARGS); break;
     case WEALY_F16: prep_rows_kernel<__half><<<blocks, threads, 0, s>>>((const __half*)x, PREP_ARGS); break;
@@ -263,11 +265,17 @@ static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename
   using SM = PairSmem<kPasses, kBlockK, kStages>;
   GemmTmaps maps;
   memset(&maps, 0, sizeof(maps));
-  W_TRY(make_plane_tmap(&maps.a_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK));
-  if (kPasses == 3) W_TRY(make_plane_tmap(&maps.a_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK));
-  else maps.a_lo = maps.a_hi;
-  maps.b_hi = maps.a_hi;
-  maps.b_lo = maps.a_lo;
+  // A side: the two CTAs of a pair take the even / odd rows of a 256-row super block (row-strided boxes), so that
+  // neighbouring rows -- same clique, same "hotness" -- are split evenly between the two coupled epilogues
+  W_TRY(make_plane_tmap(&maps.a_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK, 2));
+  W_TRY(make_plane_tmap(&maps.b_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK));
+  if (kPasses == 3) {
+    W_TRY(make_plane_tmap(&maps.a_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK, 2));
+    W_TRY(make_plane_tmap(&maps.b_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK));
+  } else {
+    maps.a_lo = maps.a_hi;
+    maps.b_lo = maps.b_hi;
+  }
   auto kern = gemm_pair_kernel<Epi, kPasses, kBlockK, kEpiWarps, kStages>;
   constexpr int kSmemBytes = SM::total(kEpiWarps, Epi::kWarpScratchBytes, Epi::kCtaScratchBytes);
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -724,7 +732,9 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
 
   // operand planes (cached allocation)
   const int64_t rq = nq * chunks, rc = nc * chunks;  // embedding rows
-  const size_t need = planes_bytes(rq, d, passes) + (same ? 0 : planes_bytes(rc, d, passes)) + 2048;
+  // the symmetric sweep stores its planes in spread order over whole 128-row blocks (gemm_core.cuh)
+  const int64_t rows_q = sym ? ceil_div(nq, kTileM) * kTileM : rq;
+  const size_t need = planes_bytes(rows_q, d, passes) + (same ? 0 : planes_bytes(rc, d, passes)) + 2048;
   if (need > p->planes_cap) {
     dev_free(p->planes_buf, s);
     p->planes_buf = nullptr;
@@ -734,10 +744,10 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   }
   uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)p->planes_buf, 1024));
   Planes pq, pc;
-  carve_planes(pq, cur, rq, d, passes);
+  carve_planes(pq, cur, rows_q, d, passes);
   if (same) pc = pq; else carve_planes(pc, cur, rc, d, passes);
-  W_TRY(launch_prep(queries_z, ld_q, rq, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s,
-                    sym ? p->sorted_idx : nullptr));
+  W_TRY(launch_prep(queries_z, ld_q, rows_q, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s,
+                    sym ? p->sorted_idx : nullptr, sym ? (int)nq : 0));
   if (!same) W_TRY(launch_prep(candidates_z, ld_c, rc, d, dtype, kPrepL2AddEps, eps, pc, nullptr, nullptr, 0, nullptr, 0, s));
 
   // K_pos: relevant similarities, sorted per query
@@ -853,12 +863,10 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     } else if (passes == 3) {
       sh.k_blocks = (int)(pq.d_pad / 32);
       if (lv == 2) W_TRY((launch_gemm_t<EvalSymEpi<2>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
-      else if (lv == 3) W_TRY((launch_gemm_t<EvalSymEpi<3>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
-      else W_TRY((launch_gemm_t<EvalSymEpi<4>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
+      else if (lv == 4) W_TRY((launch_gemm_t<EvalSymEpi<4>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
+      else W_TRY((launch_gemm_t<EvalSymEpi<3>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
     } else {
-      if (lv == 2) W_TRY((launch_gemm_t<EvalSymEpi<2>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
-      else if (lv == 3) W_TRY((launch_gemm_t<EvalSymEpi<3>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
-      else W_TRY((launch_gemm_t<EvalSymEpi<4>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
+      W_TRY((launch_gemm_t<EvalSymEpi<3>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
     }
   } else if (chunks == 2) {
     W_TRY(launch_eval_tracks<2>(passes, pq, pc, sh, ep, s));

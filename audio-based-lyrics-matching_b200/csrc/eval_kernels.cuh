@@ -302,12 +302,13 @@ __global__ void __launch_bounds__(256) pos_pairs_sorted_kernel(
   const int qlast = min(q0 + 15, n - 1);
   const int lo_row = seg_lo[q0], hi_row = seg_lo[qlast] + seg_len[qlast];  // candidates any of the 16 queries needs
   const int qa = min(q0 + g, n - 1), qb = min(q0 + g + 8, n - 1);          // (clamped rows are discarded below)
-  const __half* a_hi0 = hi + (long long)qa * d_pad;
-  const __half* a_hi1 = hi + (long long)qb * d_pad;
-  const __half* a_lo0 = lo ? lo + (long long)qa * d_pad : nullptr;
-  const __half* a_lo1 = lo ? lo + (long long)qb * d_pad : nullptr;
+  // (the planes are in the sweep's spread row order: sorted row s lives at plane row spread_plane_of(s))
+  const __half* a_hi0 = hi + (long long)spread_plane_of(qa) * d_pad;
+  const __half* a_hi1 = hi + (long long)spread_plane_of(qb) * d_pad;
+  const __half* a_lo0 = lo ? lo + (long long)spread_plane_of(qa) * d_pad : nullptr;
+  const __half* a_lo1 = lo ? lo + (long long)spread_plane_of(qb) * d_pad : nullptr;
   for (int j0 = lo_row + warp * 8; j0 < hi_row; j0 += 64) {
-    const int jb = min(j0 + g, n - 1);
+    const int jb = spread_plane_of(min(j0 + g, n - 1));
     const __half* b_hi = hi + (long long)jb * d_pad;
     const __half* b_lo = lo ? lo + (long long)jb * d_pad : nullptr;
     float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -359,10 +360,11 @@ __global__ void __launch_bounds__(256) pos_sort_sorted_kernel(const int* __restr
   const int lane = (int)(threadIdx.x & 31);
   if (q >= n_padded) return;
   const float inf = __int_as_float(0x7f800000);
+  const int pq = spread_plane_of(q);  // lvl / cinfo are read by plane row (per-tile bulk copies of the sweep)
   if (q >= n) {
     if (lane == 0) {
-      lvl[q] = make_float4(inf, inf, inf, inf);
-      cinfo[q] = make_uint2((unsigned)off[n], 0u);
+      lvl[pq] = make_float4(inf, inf, inf, inf);
+      cinfo[pq] = make_uint2((unsigned)off[n], 0u);
     }
     return;
   }
@@ -381,9 +383,9 @@ __global__ void __launch_bounds__(256) pos_sort_sorted_kernel(const int* __restr
   __syncwarp();
   if (lane == 0) {
     cnt[q] = np;
-    lvl[q] = make_float4(np > 0 ? thr[o] : inf, np > 1 ? thr[o + 1] : inf, np > 2 ? thr[o + 2] : inf,
-                         np > 3 ? thr[o + 3] : inf);
-    cinfo[q] = make_uint2((unsigned)o, (unsigned)np);
+    lvl[pq] = make_float4(np > 0 ? thr[o] : inf, np > 1 ? thr[o + 1] : inf, np > 2 ? thr[o + 2] : inf,
+                          np > 3 ? thr[o + 3] : inf);
+    cinfo[pq] = make_uint2((unsigned)o, (unsigned)np);
   }
 }
 

@@ -108,7 +108,10 @@ struct EvalSymEpi {
     st.qc = st.qi = 0;
     st.off = 0u;
     int cnt = 0;
-    st.row_ok = row < sh.m_rows;
+    // `row` (like every row / column index in here) is a PLANE row: rows are stored in spread order (gemm_core.cuh),
+    // lvl / cinfo are indexed the same way; ids and validity go through the sorted index
+    const int srow = spread_sorted_of(row);
+    st.row_ok = srow < sh.m_rows;
     if (st.row_ok) {
       const float4 v = __ldg(p.lvl + row);
 #pragma unroll
@@ -116,15 +119,15 @@ struct EvalSymEpi {
       const uint2 ci = __ldg(p.cinfo + row);
       st.off = ci.x;
       cnt = (int)ci.y;
-      st.qc = __ldg(p.s_c + row);
-      st.qi = __ldg(p.s_i + row);
+      st.qc = __ldg(p.s_c + srow);
+      st.qi = __ldg(p.s_i + srow);
     }
     st.qn = 0;
     st.row_glob = row;
     st.dirty = 0;
     // cooperative fill of the row block's threshold cache (the previous unit's row_end left it flushed)
     st.base = __ldg(p.cinfo + ctx.row_base).x;
-    const unsigned end = (ctx.row_base + kTileM < sh.m_rows) ? __ldg(p.cinfo + ctx.row_base + kTileM).x : p.total_pairs;
+    const unsigned end = (ctx.row_base + ctx.row_span < sh.m_rows) ? __ldg(p.cinfo + ctx.row_base + ctx.row_span).x : p.total_pairs;
     const unsigned total = end - st.base;
     st.n_cached = (int)(total < (unsigned)kCachePairs ? total : (unsigned)kCachePairs);
     float* ts = thr_s(ctx);
@@ -239,8 +242,10 @@ struct EvalSymEpi {
   __device__ static __forceinline__ void tile_begin(const Params& p, RowState& st, const GemmShape& sh,
                                                     const EpiCtx& ctx, int t) {
     (void)sh;
-    const int rbi = ctx.row_base / kTileM;
-    st.dirty = rbi < p.n_row_blocks ? (int)__ldg(p.dirty + (size_t)rbi * p.n_col_tiles + t) : 1;
+    // (the CTA-pair core draws this CTA's rows from two adjacent row blocks, possibly one past the end)
+    st.dirty = 0;
+    for (int rbi = ctx.row_base / kTileM; rbi < (ctx.row_base + ctx.row_span) / kTileM; ++rbi)
+      st.dirty |= rbi < p.n_row_blocks ? (int)__ldg(p.dirty + (size_t)rbi * p.n_col_tiles + t) : 1;
   }
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
@@ -266,10 +271,10 @@ struct EvalSymEpi {
     }
     if (st.dirty) {
       // tile with self / same-clique / colliding pairs, or ragged edges: candidates by id, above the diagonal only
-      const int col = col0 + lane;
-      const bool ok = col < sh.n_cols;
-      const int cc = ok ? __ldg(p.s_c + col) : 0;
-      const int ci = ok ? __ldg(p.s_i + col) : 0;
+      const int scol = spread_sorted_of(col0 + lane);
+      const bool ok = scol < sh.n_cols;
+      const int cc = ok ? __ldg(p.s_c + scol) : 0;
+      const int ci = ok ? __ldg(p.s_i + scol) : 0;
       unsigned valid = 0u;
 #pragma unroll
       for (int e = 0; e < 32; ++e) {

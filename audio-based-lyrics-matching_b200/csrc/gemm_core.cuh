@@ -25,6 +25,20 @@ constexpr int kTileN = 256;   // candidates per tile (TMEM columns per accumulat
 constexpr int kUmmaK = 16;    // K per tcgen05.mma for 16-bit inputs
 constexpr int kChunkCols = 32;  // columns handed to the epilogue per tcgen05.ld
 
+// "Spread" row order of the symmetric evaluation sweep.  In clique-sorted order equally hot rows are neighbours, and a
+// TMEM lane quadrant (32 consecutive accumulator rows = one pair of epilogue warps) would own a run of them and gate
+// the whole CTA.  The operand planes (and every per-row array the sweep reads) are therefore stored with the rows of
+// each 128-row block dealt round-robin to the four quadrants: plane row p of a block holds sorted row
+// 4 * (p % 32) + p / 32 of that block.  Blocks are unchanged as sets, so tiles, clique ranges and CSR slices are too.
+__host__ __device__ __forceinline__ int spread_sorted_of(int p) {
+  const int r = p & 127;
+  return (p & ~127) + ((r & 31) << 2) + (r >> 5);
+}
+__host__ __device__ __forceinline__ int spread_plane_of(int s) {
+  const int u = s & 127;
+  return (s & ~127) + ((u & 3) << 5) + (u >> 2);
+}
+
 struct GemmTmaps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
@@ -91,7 +105,8 @@ struct EpiCtx {
   uint8_t* cta_scratch;   // Epi::kCtaScratchBytes shared by all epilogue warps of the CTA
   int tid;                // thread index inside the epilogue group, [0, nthreads)
   int nthreads;           // epilogue threads per CTA (named barrier 1 is reserved for them)
-  int row_base;           // first query row of the unit's row block
+  int row_base;           // first query row of the unit's row block (of the 256-row super block in the CTA-pair core)
+  int row_span;           // consecutive rows [row_base, row_base + row_span) this CTA's rows are drawn from (128, or 256)
   int first_col;          // first column this warp will see in the unit ...
   int col_step;           // ... and the distance to the column of its next chunk
   const uint8_t* col_slot;  // Epi::kColSlots > 0: this tile's per-column data (bulk-copied by the TMA thread)
@@ -321,6 +336,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       ctx.tid = ew * 32 + lane;
       ctx.nthreads = kEpiWarps * 32;
       ctx.row_base = rb * kTileM;
+      ctx.row_span = kTileM;
       ctx.first_col = t0 * kTileN + half * kChunkCols;
       ctx.col_step = kHalves * kChunkCols;
       ctx.col_slot = nullptr;

@@ -1,9 +1,11 @@
 // CTA-pair variant of the contraction core (gemm_core.cuh) for the symmetric evaluation sweep: two CTAs of a
 // cluster (two SMs of one TPC) work on one 256 x 256 tile with tcgen05.mma.cta_group::2.
 //
-//   * each CTA owns 128 rows of the tile (its own row block: rb = 2 S + cta_rank of the "super" row block S) and
-//     keeps the accumulator of those rows in its own TMEM -- the epilogue policy sees exactly what it sees in the
-//     single-CTA core;
+//   * each CTA owns 128 rows of the tile -- the even (rank 0) or odd (rank 1) rows of the 256-row "super" row block
+//     S, loaded with row-strided TMA boxes -- and keeps the accumulator of those rows in its own TMEM.  The two
+//     epilogues are coupled through the shared accumulator hand-over (the pair advances at the pace of the slower
+//     one), and the data-dependent epilogue work is a property of the rows (neighbouring rows belong to the same
+//     clique): interleaving splits it evenly between the two CTAs;
 //   * each CTA loads its 128 A rows and only HALF of the tile's 256 B rows (columns 128 cta_rank .. +128); the
 //     tensor cores of both SMs read the two halves from both shared memories.  Per tile the pair moves
 //     2 x (A + B/2) instead of 2 x (A + B) through L2 -> shared memory, and a pipeline stage is 32 KB instead of
@@ -66,7 +68,11 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
 
   if (warp_idx == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmaps.a_hi);
-    if (kPasses == 3) ptx::prefetch_tensormap(&tmaps.a_lo);
+    ptx::prefetch_tensormap(&tmaps.b_hi);
+    if (kPasses == 3) {
+      ptx::prefetch_tensormap(&tmaps.a_lo);
+      ptx::prefetch_tensormap(&tmaps.b_lo);
+    }
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);   // the leader's producer arrives once, with the bytes of both CTAs
       ptx::mbar_init(&empty_bar[s], 1);  // one multicast commit
@@ -91,11 +97,10 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
 
   const int n_units = shape.n_row_blocks * shape.n_col_chunks;  // n_row_blocks counts SUPER row blocks here
 
-  // unit -> (chunk, super row block S); this CTA's row block is 2 S + cta_rank, both need column tiles >= S
-  auto unit_tiles = [&](int u, int& rb, int& t0, int& t1) {
-    int chunk, S;
+  // unit -> (chunk, super row block S): rows [256 S, 256 S + 256) need column tiles >= S
+  auto unit_tiles = [&](int u, int& S, int& t0, int& t1) {
+    int chunk;
     decode_unit(shape, u, chunk, S);
-    rb = 2 * S + (int)cta_rank;
     t1 = min((chunk + 1) * shape.tiles_per_chunk, shape.n_col_tiles);
     t0 = max(chunk * shape.tiles_per_chunk, S);
   };
@@ -151,11 +156,12 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
             const uint32_t fb = leader_full0 + 8u * stage;
             const int brow = t * kTileN + (int)cta_rank * kTileM;  // this CTA's half of the tile's candidate rows
             // layout of a stage: A_hi | A_lo | B_hi(half) | B_lo(half)   (single pass: A_hi | B_hi)
-            ptx::tma_load_2d_pair(st, &tmaps.a_hi, fb, kb * kBlockK, rb * kTileM, ptx::kEvictLast);
-            ptx::tma_load_2d_pair(st + SM::kPlanes * SM::kTileBytes, &tmaps.a_hi, fb, kb * kBlockK, brow, ptx::kEvictNormal);
+            const int arow = rb * 2 * kTileM + (int)cta_rank;  // every second row of the super block (rb), this rank's parity
+            ptx::tma_load_2d_pair(st, &tmaps.a_hi, fb, kb * kBlockK, arow, ptx::kEvictLast);
+            ptx::tma_load_2d_pair(st + SM::kPlanes * SM::kTileBytes, &tmaps.b_hi, fb, kb * kBlockK, brow, ptx::kEvictNormal);
             if (kPasses == 3) {
-              ptx::tma_load_2d_pair(st + SM::kTileBytes, &tmaps.a_lo, fb, kb * kBlockK, rb * kTileM, ptx::kEvictLast);
-              ptx::tma_load_2d_pair(st + 3 * SM::kTileBytes, &tmaps.a_lo, fb, kb * kBlockK, brow, ptx::kEvictNormal);
+              ptx::tma_load_2d_pair(st + SM::kTileBytes, &tmaps.a_lo, fb, kb * kBlockK, arow, ptx::kEvictLast);
+              ptx::tma_load_2d_pair(st + 3 * SM::kTileBytes, &tmaps.b_lo, fb, kb * kBlockK, brow, ptx::kEvictNormal);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
@@ -233,14 +239,15 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
       int rb, t0, t1;
       unit_tiles(u, rb, t0, t1);
       if (t0 >= t1) continue;
-      const int row = rb * kTileM + row_in_tile;
+      const int row = rb * 2 * kTileM + 2 * row_in_tile + (int)cta_rank;  // rb is the SUPER row block here
       typename Epi::RowState rs;
       EpiCtx ctx;
       ctx.warp_scratch = scratch_base + ew * Epi::kWarpScratchBytes;
       ctx.cta_scratch = scratch_base + kEpiWarps * Epi::kWarpScratchBytes;
       ctx.tid = ew * 32 + lane;
       ctx.nthreads = kEpiWarps * 32;
-      ctx.row_base = rb * kTileM;
+      ctx.row_base = rb * 2 * kTileM;
+      ctx.row_span = 2 * kTileM;
       ctx.first_col = t0 * kTileN + half * kChunkCols;
       ctx.col_step = kHalves * kChunkCols;
       ctx.col_slot = nullptr;

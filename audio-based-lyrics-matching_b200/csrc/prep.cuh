@@ -81,12 +81,30 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ x,
                                                         long long ld_t, float* __restrict__ norm_out,
                                                         float* __restrict__ scale_out, float* __restrict__ sq_out,
                                                         ZStats* __restrict__ stats,
-                                                        const int* __restrict__ gather = nullptr) {
+                                                        const int* __restrict__ gather = nullptr, int spread_n = 0) {
   const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (warp >= n) return;
-  // `gather` (optional): output row r is built from input row gather[r] (clique-sorted planes of the evaluation sweep)
-  const T* row = x + (long long)(gather ? gather[warp] : warp) * ld;
+  // `gather` (optional): output row r is built from input row gather[r] (clique-sorted planes of the evaluation sweep);
+  // spread_n > 0: the n output rows are in the sweep's spread order (gemm_core.cuh) over spread_n sorted rows --
+  // output row r holds sorted row spread_sorted_of(r), rows past the end are zero
+  int src = warp;
+  if (spread_n > 0) {
+    src = (warp & ~127) + (((warp & 127) & 31) << 2) + ((warp & 127) >> 5);
+    if (src >= spread_n) {
+      for (int k = lane; k < d_pad; k += 32) {
+        hi[(long long)warp * d_pad + k] = __float2half_rn(0.f);
+        if (lo) lo[(long long)warp * d_pad + k] = __float2half_rn(0.f);
+      }
+      if (lane == 0) {
+        if (norm_out) norm_out[warp] = 0.f;
+        if (scale_out) scale_out[warp] = 1.f;
+        if (sq_out) sq_out[warp] = 0.f;
+      }
+      return;
+    }
+  }
+  const T* row = x + (long long)(gather ? gather[src] : src) * ld;
 
   // HBM-bound row passes: 4 elements per lane and access when the rows are suitably aligned (the usual case)
   const bool vec = (d % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && hi_t == nullptr;

@@ -1,0 +1,7 @@
+WEALY_SYM_PAIR=1 timeout 300 python -m pytest tests/test_gpu_eval.py -x -q 2>&1 | tail -3
+for p in 1 0; do
+echo pair=$p
+WEALY_SYM_PAIR=$p timeout 120 python tools/gpu_diag.py time fp16 100000 1024 2>&1 | tail -1
+WEALY_SYM_PAIR=$p timeout 120 python tools/gpu_diag.py time fp16x3 100000 1024 2>&1 | tail -1
+WEALY_SYM_PAIR=$p timeout 120 python tools/gpu_diag.py time fp16x3 100000 1024 2>&1 | tail -1
+done
