@@ -262,15 +262,16 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
 template <class Epi, int kPasses, int kBlockK>
 static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename Epi::Params& ep, cudaStream_t s) {
   constexpr int kStages = 4, kEpiWarps = 8;
+  const int il = (sh.sym & 2) ? 2 : 1;  // row stride of the A boxes
   using SM = PairSmem<kPasses, kBlockK, kStages>;
   GemmTmaps maps;
   memset(&maps, 0, sizeof(maps));
   // A side: the two CTAs of a pair take the even / odd rows of a 256-row super block (row-strided boxes), so that
   // neighbouring rows -- same clique, same "hotness" -- are split evenly between the two coupled epilogues
-  W_TRY(make_plane_tmap(&maps.a_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK, 2));
+  W_TRY(make_plane_tmap(&maps.a_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK, il));
   W_TRY(make_plane_tmap(&maps.b_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK));
   if (kPasses == 3) {
-    W_TRY(make_plane_tmap(&maps.a_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK, 2));
+    W_TRY(make_plane_tmap(&maps.a_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK, il));
     W_TRY(make_plane_tmap(&maps.b_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK));
   } else {
     maps.a_lo = maps.a_hi;
@@ -854,6 +855,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     sp.total_pairs = (unsigned)p->total_pairs;
     const int lv = env_int("WEALY_SYM_LEVELS", 3);  // 3 measured best at C2 (2: 26.8 ms, 3: 25.5 ms, 4: 25.9 ms per step)
     if (pair) {
+      if (env_int("WEALY_PAIR_INTERLEAVE", 1) != 0) sh.sym |= 2;
       if (passes == 3) {
         sh.k_blocks = (int)(pq.d_pad / 32);
         W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32>(pq, sh, sp, s)));

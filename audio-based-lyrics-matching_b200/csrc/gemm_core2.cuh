@@ -156,7 +156,8 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
             const uint32_t fb = leader_full0 + 8u * stage;
             const int brow = t * kTileN + (int)cta_rank * kTileM;  // this CTA's half of the tile's candidate rows
             // layout of a stage: A_hi | A_lo | B_hi(half) | B_lo(half)   (single pass: A_hi | B_hi)
-            const int arow = rb * 2 * kTileM + (int)cta_rank;  // every second row of the super block (rb), this rank's parity
+            // interleaved: every second row of the super block (rb), this rank's parity; else this rank's half
+            const int arow = (shape.sym & 2) ? rb * 2 * kTileM + (int)cta_rank : rb * 2 * kTileM + (int)cta_rank * kTileM;
             ptx::tma_load_2d_pair(st, &tmaps.a_hi, fb, kb * kBlockK, arow, ptx::kEvictLast);
             ptx::tma_load_2d_pair(st + SM::kPlanes * SM::kTileBytes, &tmaps.b_hi, fb, kb * kBlockK, brow, ptx::kEvictNormal);
             if (kPasses == 3) {
@@ -239,7 +240,8 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
       int rb, t0, t1;
       unit_tiles(u, rb, t0, t1);
       if (t0 >= t1) continue;
-      const int row = rb * 2 * kTileM + 2 * row_in_tile + (int)cta_rank;  // rb is the SUPER row block here
+      const int row = (shape.sym & 2) ? rb * 2 * kTileM + 2 * row_in_tile + (int)cta_rank  // rb is the SUPER row block here
+                                      : rb * 2 * kTileM + (int)cta_rank * kTileM + row_in_tile;
       typename Epi::RowState rs;
       EpiCtx ctx;
       ctx.warp_scratch = scratch_base + ew * Epi::kWarpScratchBytes;
