@@ -17,6 +17,12 @@
 // self-describing entry (value, threshold range, counter index) is binned by a binary search 32 x 2 at a time.
 // Dirty tiles run the same code with a validity mask built from the ids (64 shuffles per chunk) and the
 // diagonal test col > row.
+//
+// Row order inside the sweep: every row / column index in this file is a PLANE row.  The planes, lvl and cinfo store
+// each 128-row block of the sorted order with its rows dealt round-robin to the four TMEM lane quadrants
+// (spread_sorted_of / spread_plane_of, gemm_core.cuh), because equally hot queries are neighbours in sorted space
+// and would otherwise pile up on one pair of epilogue warps.  Ids (s_c, s_i), validity (row < n) and the CSR
+// offsets stay in sorted order.
 #pragma once
 #include "gemm_core.cuh"
 
