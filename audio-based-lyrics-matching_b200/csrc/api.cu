@@ -259,9 +259,9 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
 }
 
 // CTA-pair kernel (gemm_core2.cuh): sh.n_row_blocks / group_rows / rb_stride / rb_offset are in SUPER row blocks
-template <class Epi, int kPasses, int kBlockK>
+template <class Epi, int kPasses, int kBlockK, int kEpiWarps = 8>
 static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename Epi::Params& ep, cudaStream_t s) {
-  constexpr int kStages = 4, kEpiWarps = 8;
+  constexpr int kStages = 4;
   const int il = (sh.sym & 2) ? 2 : 1;  // row stride of the A boxes
   using SM = PairSmem<kPasses, kBlockK, kStages>;
   GemmTmaps maps;
@@ -856,11 +856,15 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     const int lv = env_int("WEALY_SYM_LEVELS", 3);  // 3 measured best at C2 (2: 26.8 ms, 3: 25.5 ms, 4: 25.9 ms per step)
     if (pair) {
       if (env_int("WEALY_PAIR_INTERLEAVE", 1) != 0) sh.sym |= 2;
+      // three epilogue warps per TMEM lane quadrant (the pair's epilogue is the co-limiter; 16 warps were measured worse)
+      const bool w12 = env_int("WEALY_PAIR_EPI_WARPS", 12) == 12;
       if (passes == 3) {
         sh.k_blocks = (int)(pq.d_pad / 32);
-        W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32>(pq, sh, sp, s)));
+        if (w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12>(pq, sh, sp, s)));
+        else W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32>(pq, sh, sp, s)));
       } else {
-        W_TRY((launch_gemm_pair<EvalSymEpi<3>, 1, 64>(pq, sh, sp, s)));
+        if (w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 1, 64, 12>(pq, sh, sp, s)));
+        else W_TRY((launch_gemm_pair<EvalSymEpi<3>, 1, 64>(pq, sh, sp, s)));
       }
     } else if (passes == 3) {
       sh.k_blocks = (int)(pq.d_pad / 32);

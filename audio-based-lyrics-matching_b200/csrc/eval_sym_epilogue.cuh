@@ -323,10 +323,12 @@ struct EvalSymEpi {
       push(st, ctx, acc, dr, dc, cinf, st.qn + incl - mine);
       st.qn += total;
     } else {
-      // a chunk denser than the whole queue: four columns (<= 256 entries) at a time
+      // a chunk denser than the whole queue: kQueueCap / 64 columns (<= kQueueCap entries) at a time
+      constexpr int kBatchCols = kQueueCap / 64;
+      static_assert(kBatchCols >= 1 && 32 % kBatchCols == 0, "queue capacity: 64 .. 2048, a power of two");
 #pragma unroll 1
-      for (int g = 0; g < 8; ++g) {
-        const unsigned sel = 0xfu << (4 * g);
+      for (int g = 0; g < 32 / kBatchCols; ++g) {
+        const unsigned sel = ((1u << kBatchCols) - 1u) << (kBatchCols * g);
         const int mine_g = __popc(dr & sel) + __popc(dc & sel);
         const int incl_g = warp_incl_scan(mine_g, lane);
         push(st, ctx, acc, dr & sel, dc & sel, cinf, incl_g - mine_g);

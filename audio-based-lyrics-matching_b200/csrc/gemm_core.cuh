@@ -143,7 +143,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
   using SM = GemmSmem<kPasses, kBlockK, kMaxStages>;
   constexpr int kStages = SM::kStages;
   constexpr int kHalves = kEpiWarps / 4;  // epilogue warps per TMEM lane quadrant
-  static_assert(kEpiWarps == 4 || kEpiWarps == 8 || kEpiWarps == 16, "4, 8 or 16 epilogue warps");
+  static_assert(kEpiWarps == 4 || kEpiWarps == 8 || kEpiWarps == 12 || kEpiWarps == 16, "4, 8, 12 or 16 epilogue warps");
   static_assert(kPasses == 1 || kPasses == 3, "1 (fp16) or 3 (fp16 hi/lo) passes");
 
   extern __shared__ uint8_t smem_raw[];
