@@ -38,6 +38,9 @@ SIGNATURES = {
     "wealy_sim_matrix_backward_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "wealy_sim_matrix_backward": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_f32, c_int, c_vp, c_i64,
                                           c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_sz, c_vp]),
+    "wealy_dot_matrix_backward_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
+    "wealy_dot_matrix_backward": (c_int, [c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_int, c_int,
+                                          c_vp, c_i64, c_vp, c_i64, c_vp, c_sz, c_vp]),
     "wealy_eval_plan_create": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, ctypes.POINTER(c_vp)]),
     "wealy_eval_plan_info": (c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "wealy_eval_run": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_vp,

@@ -459,6 +459,52 @@ extern "C" int wealy_sim_matrix_backward(const void* x, int64_t n, int64_t ldx, 
   return WEALY_OK;
 }
 
+// Gradient of the dot modes (no normalisation): dX = G Y, dY = G^T X.  The caller passes the gradient and its
+// transpose (already negated for mode "dot" = 1 - x.y) and the TRANSPOSED operands xt [d][n], yt [d][m]: every
+// matrix is split row-wise with an exact power-of-two scale, so the products are plain K-major contractions.
+extern "C" size_t wealy_dot_matrix_backward_workspace_bytes(int64_t n, int64_t m, int64_t d, int passes) {
+  if (n <= 0 || m <= 0 || d <= 0) return 0;
+  return planes_bytes(n, m, passes) + planes_bytes(m, n, passes) + planes_bytes(d, n, passes) + planes_bytes(d, m, passes) + 8192;
+}
+
+extern "C" int wealy_dot_matrix_backward(const void* grad, int64_t ld_grad, const void* grad_t, int64_t ld_grad_t,
+                                         const void* xt, int64_t ld_xt, const void* yt, int64_t ld_yt, int64_t n, int64_t m,
+                                         int64_t d, int dtype, int passes, void* dx, int64_t ld_dx, void* dy, int64_t ld_dy,
+                                         void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n <= 0 || m <= 0 || d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad shape n=%lld m=%lld d=%lld", (long long)n, (long long)m, (long long)d);
+  if (!grad || !grad_t || !xt || !yt || !dx || !dy || !workspace) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (passes != 1 && passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
+  if (workspace_bytes < wealy_dot_matrix_backward_workspace_bytes(n, m, d, passes)) return fail(WEALY_ERR_WORKSPACE, "workspace too small");
+  uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024));
+  Planes pg, pgt, pxt, pyt;
+  carve_planes(pg, cur, n, m, passes);    // G    [n][m_pad]
+  carve_planes(pgt, cur, m, n, passes);   // G^T  [m][n_pad]
+  carve_planes(pxt, cur, d, n, passes);   // X^T  [d][n_pad]
+  carve_planes(pyt, cur, d, m, passes);   // Y^T  [d][m_pad]
+  W_TRY(launch_prep(grad, ld_grad, n, m, dtype, kPrepRawPow2, 0.f, pg, nullptr, nullptr, 0, nullptr, 0, s));
+  W_TRY(launch_prep(grad_t, ld_grad_t, m, n, dtype, kPrepRawPow2, 0.f, pgt, nullptr, nullptr, 0, nullptr, 0, s));
+  W_TRY(launch_prep(xt, ld_xt, d, n, dtype, kPrepRawPow2, 0.f, pxt, nullptr, nullptr, 0, nullptr, 0, s));
+  W_TRY(launch_prep(yt, ld_yt, d, m, dtype, kPrepRawPow2, 0.f, pyt, nullptr, nullptr, 0, nullptr, 0, s));
+  auto product = [&](const Planes& a, const Planes& b, int64_t rows, void* out, int64_t ld_out) -> int {
+    StoreParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.out = out;
+    sp.ld = ld_out;
+    sp.mode = kSimDotsim;  // s * row scale * column scale
+    sp.out_dtype = dtype == WEALY_F32 ? kOutF32 : (dtype == WEALY_F16 ? kOutF16 : kOutBF16);
+    sp.post = 1.f;
+    sp.rscale = a.scale;
+    sp.cscale = b.scale;
+    GemmShape sh;
+    fill_shape(sh, rows, d, a.d_pad, 64, 1 << 20);
+    return launch_gemm<StoreEpi>(passes, a, b, sh, sp, s);
+  };
+  W_TRY(product(pg, pyt, n, dx, ld_dx));    // dX = G Y      (K = m)
+  W_TRY(product(pgt, pxt, m, dy, ld_dy));   // dY = G^T X    (K = n)
+  return WEALY_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // a7: evaluation plan + run
 // ------------------------------------------------------------------------------------------

@@ -102,6 +102,40 @@ class _CosineMatrix(torch.autograd.Function):
         return (dx if ctx.needs_input_grad[0] else None), (dy if ctx.needs_input_grad[1] else None), None, None, None
 
 
+class _DotMatrix(torch.autograd.Function):
+    """dot / dotsim modes under autograd: dX = G Y, dY = G^T X on the contraction core (no normalisation)."""
+
+    @staticmethod
+    def forward(ctx, x, y, mode, eps, precision):
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (mode, precision)
+        return _sim_matrix(x.detach(), y.detach(), mode, eps, 1.0, precision)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = ctx.saved_tensors
+        mode, precision = ctx.cfg
+        n, d = x.shape
+        m = y.shape[0]
+        gg = g.to(x.dtype)
+        if mode == N.MODE_DOT:                      # out = 1 - x.y
+            gg = -gg
+        gg = gg.contiguous()
+        gt = gg.t().contiguous()
+        xt, yt = x.detach().t().contiguous(), y.detach().t().contiguous()
+        dx = torch.empty((n, d), dtype=x.dtype, device=x.device)
+        dy = torch.empty((m, d), dtype=x.dtype, device=x.device)
+        passes = passes_of(precision)
+        with torch.cuda.device(x.device):
+            ws_bytes = N.lib.wealy_dot_matrix_backward_workspace_bytes(n, m, d, passes)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            N.check(N.lib.wealy_dot_matrix_backward(
+                gg.data_ptr(), gg.stride(0), gt.data_ptr(), gt.stride(0), xt.data_ptr(), xt.stride(0), yt.data_ptr(),
+                yt.stride(0), n, m, d, N.dtype_code(x.dtype), passes, dx.data_ptr(), dx.stride(0), dy.data_ptr(),
+                dy.stride(0), ws.data_ptr(), ws_bytes, N.stream_ptr(x.device)))
+        return (dx if ctx.needs_input_grad[0] else None), (dy if ctx.needs_input_grad[1] else None), None, None, None
+
+
 def pairwise_euclidean_distance_matrix(x, y, squared=False, eps=1e-6, precision=None):
     """lib/tensor_ops.py:131-149: |x|^2 - 2 x.y + |y|^2, clamped at 0, optional sqrt (zeros stay 0).
     `eps` only guards the reference's autograd through sqrt(0); the forward value does not depend on it."""
@@ -123,8 +157,10 @@ def pairwise_distance_matrix(x, y, mode="fro", p=2, eps=1e-6, precision=None):
         if mode in ("cos", "cossim") and x.shape[0] > 0 and y.shape[0] > 0 and x.shape[1] > 0:
             code = N.MODE_COSSIM if mode == "cossim" else N.MODE_COS
             return _CosineMatrix.apply(x, y, code, eps, precision)
-        raise NotImplementedError("wealy_b200.pairwise_distance_matrix: autograd is provided for the cosine modes "
-                                  "(cos / cossim); use wealy_b200.losses for the fused differentiable losses")
+        if mode in ("dot", "dotsim") and x.shape[0] > 0 and y.shape[0] > 0 and x.shape[1] > 0:
+            return _DotMatrix.apply(x, y, N.MODE_DOTSIM if mode == "dotsim" else N.MODE_DOT, eps, precision)
+        raise NotImplementedError("wealy_b200.pairwise_distance_matrix: autograd is provided for the contraction modes "
+                                  "(cos / cossim / dot / dotsim); use wealy_b200.losses for the fused differentiable losses")
     if mode == "euc" or mode == "neuc":
         p = 2
     d = x.size(-1)

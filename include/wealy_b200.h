@@ -72,6 +72,15 @@ int wealy_sim_matrix_backward(const void* x, int64_t n, int64_t ldx, const void*
                               const void* grad_t, int64_t ld_grad_t, void* dx, int64_t ld_dx, void* dy, int64_t ld_dy,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradient of the dot modes (dot / dotsim): dx [n][d] = G y, dy [m][d] = G^T x.  grad [n][m] and grad_t [m][n] are the
+ * upstream gradient and its transpose (negated by the caller for mode "dot" = 1 - x.y), xt [d][n] / yt [d][m] the
+ * transposed operands; all with the input dtype.                                                                     */
+size_t wealy_dot_matrix_backward_workspace_bytes(int64_t n, int64_t m, int64_t d, int passes);
+int wealy_dot_matrix_backward(const void* grad, int64_t ld_grad, const void* grad_t, int64_t ld_grad_t, const void* xt,
+                              int64_t ld_xt, const void* yt, int64_t ld_yt, int64_t n, int64_t m, int64_t d, int dtype,
+                              int passes, void* dx, int64_t ld_dx, void* dy, int64_t ld_dy, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* ---- a7: fused retrieval evaluation -------------------------------------------------------
  * Self / same-clique masking by id, per-query ranking, AP / R1 (and optional top-k) without
  * materialising the Nq x Nc matrix.  The evaluator is not in the reference; argument vocabulary

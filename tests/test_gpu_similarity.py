@@ -134,7 +134,7 @@ def test_error_behaviour_matches_reference():
         _wt().pairwise_distance_matrix(x[None], x[None])            # lib/tensor_ops.py:153
 
 
-@pytest.mark.parametrize("mode", ["cossim", "cos"])
+@pytest.mark.parametrize("mode", ["cossim", "cos", "dotsim", "dot"])
 @pytest.mark.parametrize("n,m,d,dtype", [(70, 130, 96, torch.float32), (300, 300, 1024, torch.float32),
                                          (129, 65, 200, torch.bfloat16)])
 def test_cosine_modes_are_differentiable(mode, n, m, d, dtype):
@@ -160,4 +160,4 @@ def test_cosine_modes_are_differentiable(mode, n, m, d, dtype):
      wt.pairwise_distance_matrix(xs, xs, mode=mode)).sum().backward()
     assert torch.isfinite(xs.grad).all()
     with pytest.raises(NotImplementedError):
-        wt.pairwise_distance_matrix(xc, yc, mode="dot")
+        wt.pairwise_distance_matrix(xc, yc, mode="sqeuc")
