@@ -42,9 +42,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Waiting warps burn issue slots and power that the tensor pipe could use (the sweeps run at the power cap): the
+// poll carries a suspend-time hint (the hardware parks the thread until the phase completes or the hint expires) and
+// a waiting WARP polls with one lane only (mbar_wait_warp).  Measured on the MMA-bound symmetric sweep: 1-2 %.
+#ifndef WEALY_WAIT_HINT_NS
+#define WEALY_WAIT_HINT_NS 1000
+#endif
+#ifndef WEALY_WAIT_ALL_LANES
+#define WEALY_WAIT_LANE0
+#endif
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-#ifdef WEALY_WAIT_HINT_NS
+#if WEALY_WAIT_HINT_NS > 0
   // suspend-time hint: the hardware parks the thread until the phase completes or the hint expires
   asm volatile(
       "{\n"
