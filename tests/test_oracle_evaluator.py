@@ -107,3 +107,31 @@ def test_metamorphic_invariances():
     assert torch.allclose(a0, a2, atol=1e-9) and torch.equal(r0, r2)
     m, r = oev.mean_metrics(a0, r0)
     assert 0 < m <= 1 and r >= 1
+
+
+@pytest.mark.parametrize("redux", ["min", "max", "mean", "meanmin", "minmean"])
+def test_chunked_oracle_degenerates_to_the_plain_evaluator(redux):
+    """Chunked tracks: with one chunk per track, or with every chunk of a track equal, the
+    track-level distance of any redux is the plain cosine distance -- same AP / R1 as the unchunked evaluator."""
+    from wealy_b200.data import synth
+    s = synth.make_eval_set(180, 24, seed=5)
+    c, i, z = s["c"], s["i"], s["z"]
+    aps, r1s = oev.evaluate_argsort(c, i, z, c, i, z)
+    a1, r1 = oev.evaluate_argsort(c, i, z[:, None, :], c, i, z[:, None, :], redux=redux)
+    assert torch.allclose(a1, aps) and torch.equal(r1, r1s)
+    z4 = z[:, None, :].repeat(1, 4, 1).contiguous()
+    a4, r4 = oev.evaluate_argsort(c, i, z4, c, i, z4, redux=redux)
+    assert torch.allclose(a4, aps, atol=1e-6)
+    assert (r4 != r1s).sum() <= 2          # fp32 rounding of a mean of equal numbers may swap a near-tie
+
+
+def test_chunked_oracle_redux_ordering():
+    """min <= meanmin <= mean <= max and min <= minmean <= mean hold for the reduced DISTANCES of every track pair."""
+    from oracle.masked import distance_tensor_redux
+    g = torch.Generator().manual_seed(3)
+    d = torch.rand(7, 9, 4, 4, generator=g)
+    r = {k: distance_tensor_redux(d, k) for k in ("min", "max", "mean", "meanmin", "minmean")}
+    eps = 1e-6
+    assert bool((r["min"] <= r["meanmin"] + eps).all()) and bool((r["meanmin"] <= r["mean"] + eps).all())
+    assert bool((r["min"] <= r["minmean"] + eps).all()) and bool((r["minmean"] <= r["mean"] + eps).all())
+    assert bool((r["mean"] <= r["max"] + eps).all())
