@@ -742,7 +742,8 @@ static int launch_eval_tracks(int passes, const Planes& a, const Planes& b, Gemm
 static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
                          int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,
                          float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, int shard_rank,
-                         int shard_world, bool finish, void* stream, int chunks = 1, int redux = WEALY_REDUX_MIN) {
+                         int shard_world, bool finish, void* stream, int chunks = 1, int redux = WEALY_REDUX_MIN,
+                         const int* q_len = nullptr, const int* c_len = nullptr) {
   cudaStream_t s = (cudaStream_t)stream;
   if (!p) return fail(WEALY_ERR_BAD_ARG, "null plan");
   if (!queries_z || !candidates_z) return fail(WEALY_ERR_BAD_ARG, "null pointer");
@@ -757,6 +758,8 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   if (chunks != 1 && chunks != 2 && chunks != 4 && chunks != 8 && chunks != 16)
     return fail(WEALY_ERR_UNSUPPORTED, "chunks per track must be 1, 2, 4, 8 or 16, got %d", chunks);
   if (redux < WEALY_REDUX_MIN || redux > WEALY_REDUX_MINMEAN) return fail(WEALY_ERR_BAD_ARG, "unknown redux %d", redux);
+  if ((q_len == nullptr) != (c_len == nullptr)) return fail(WEALY_ERR_BAD_ARG, "q_len and c_len go together");
+  if (q_len && chunks == 1) return fail(WEALY_ERR_BAD_ARG, "chunk counts need chunks > 1");
   if ((nq * chunks) >= (1ll << 31) - 256 || (nc * chunks) >= (1ll << 31) - 256) return fail(WEALY_ERR_UNSUPPORTED, "more than 2^31 rows");
   // similarity space: distance min <-> similarity max; {inner over the candidate's chunks, outer over the query's}
   int red_inner = kRedMax, red_outer = kRedMax;
@@ -814,7 +817,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       pos_thresholds_tracks_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, chunks, red_inner,
                                                               red_outer, red_scale, p->q_i, (int)nq, p->sorted_idx,
                                                               p->c_i, p->seg_lo, p->seg_len, p->off, p->raw, p->thr,
-                                                              p->lim, p->cnt);
+                                                              p->lim, p->cnt, q_len, c_len);
     } else {
       const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
       pos_thresholds_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, p->q_i, (int)nq,
@@ -851,6 +854,8 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   ep.red_inner = red_inner;
   ep.red_outer = red_outer;
   ep.red_scale = red_scale;
+  ep.q_len = q_len;
+  ep.c_len = c_len;
   if (topk > 0) {
     const size_t slots = (size_t)parts * nq * cap;
     const size_t tneed = slots * 16 + (size_t)parts * nq * 4 + 1024;  // candidate lists + finalize staging
@@ -970,6 +975,15 @@ extern "C" int wealy_eval_run_chunked(wealy_eval_plan* p, const void* queries_z,
                                       void* stream) {
   return eval_run_impl(p, queries_z, ld_q, candidates_z, ld_c, d, dtype, eps, passes, topk, aps, r1s, sums, topk_idx,
                        topk_sim, 0, 1, true, stream, chunks, redux);
+}
+
+extern "C" int wealy_eval_run_ragged(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
+                                     int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, int chunks,
+                                     int redux, const int32_t* q_len, const int32_t* c_len, float* aps, float* r1s,
+                                     double* sums, int64_t* topk_idx, float* topk_sim, void* stream) {
+  if (!q_len || !c_len) return fail(WEALY_ERR_BAD_ARG, "null chunk counts");
+  return eval_run_impl(p, queries_z, ld_q, candidates_z, ld_c, d, dtype, eps, passes, topk, aps, r1s, sums, topk_idx,
+                       topk_sim, 0, 1, true, stream, chunks, redux, q_len, c_len);
 }
 
 // multi-GPU all-vs-all: every rank sweeps its share of the row blocks of the SAME symmetric problem ...

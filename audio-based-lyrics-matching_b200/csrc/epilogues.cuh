@@ -285,12 +285,19 @@ struct EvalParams {
   // lib/tensor_ops.py:288-373, in similarity space: min distance = max similarity).  All arrays above are per TRACK.
   int red_inner, red_outer;  // kRedMax / kRedMin / kRedSum over the candidate's chunks, then over the query's
   float red_scale;           // 1, 1/kS or 1/kS^2 (means)
+  // ragged tracks: valid chunks per query / candidate track (1 .. kS; chunks past the count are padding and are
+  // excluded like distance_tensor_redux's mask, lib/tensor_ops.py:288; means divide by the valid counts); null = all kS
+  const int* q_len;          // [nq]
+  const int* c_len;          // [nc]
 };
 
 enum : int { kRedMax = 0, kRedMin = 1, kRedSum = 2 };
 
 __device__ __forceinline__ float red_op(float a, float b, int op) {
   return op == kRedMax ? fmaxf(a, b) : (op == kRedMin ? fminf(a, b) : a + b);
+}
+__device__ __forceinline__ float red_neutral(int op) {
+  return op == kRedMax ? __int_as_float(0xff800000) : (op == kRedMin ? __int_as_float(0x7f800000) : 0.f);
 }
 
 template <int kQueueCapT, int kCachePairsT, int kS = 1>
@@ -558,17 +565,41 @@ struct EvalEpiT {
 
   // kS x kS blocks of the chunk -> one similarity per (query track, candidate track): first over the candidate's
   // chunks (kS consecutive registers), then over the query's (kS adjacent lanes); entries >= kGroups are -inf
-  __device__ static __forceinline__ void reduce_tracks(const Params& p, const uint32_t (&raw)[32], uint32_t (&out)[32]) {
+  __device__ static __forceinline__ void reduce_tracks(const Params& p, const uint32_t (&raw)[32], uint32_t (&out)[32],
+                                                       int row, int col0, const GemmShape& sh) {
+    if (p.c_len == nullptr) {
 #pragma unroll
-    for (int g = 0; g < kGroups; ++g) {
-      float v = __uint_as_float(raw[g * kS]);
+      for (int g = 0; g < kGroups; ++g) {
+        float v = __uint_as_float(raw[g * kS]);
 #pragma unroll
-      for (int b = 1; b < kS; ++b) v = red_op(v, __uint_as_float(raw[g * kS + b]), p.red_inner);
-      if (p.red_inner == kRedSum && p.red_outer != kRedSum) v *= p.red_scale;  // mean over the candidate's chunks first
+        for (int b = 1; b < kS; ++b) v = red_op(v, __uint_as_float(raw[g * kS + b]), p.red_inner);
+        if (p.red_inner == kRedSum && p.red_outer != kRedSum) v *= p.red_scale;  // mean over the candidate's chunks first
 #pragma unroll
-      for (int o = 1; o < kS; o <<= 1) v = red_op(v, __shfl_xor_sync(0xffffffffu, v, o), p.red_outer);
-      if (p.red_outer == kRedSum) v *= p.red_scale;
-      out[g] = __float_as_uint(v);
+        for (int o = 1; o < kS; o <<= 1) v = red_op(v, __shfl_xor_sync(0xffffffffu, v, o), p.red_outer);
+        if (p.red_outer == kRedSum) v *= p.red_scale;
+        out[g] = __float_as_uint(v);
+      }
+    } else {
+      // ragged tracks: chunks past a track's count never enter a reduction (selects, so padding may hold anything)
+      const int lane = (int)ptx::lane_id();
+      const int tc = col0 / kS + lane;
+      const int lq = row < sh.m_rows ? min(max(__ldg(p.q_len + row / kS), 1), kS) : kS;
+      const int lc_mine = (lane < kGroups && tc < sh.n_cols / kS) ? min(max(__ldg(p.c_len + tc), 1), kS) : kS;
+      const bool q_ok = (row & (kS - 1)) < lq;
+      const float rq = 1.f / (float)lq, neutral = red_neutral(p.red_outer);
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) {
+        const int lc = __shfl_sync(0xffffffffu, lc_mine, g);
+        float v = __uint_as_float(raw[g * kS]);
+#pragma unroll
+        for (int b = 1; b < kS; ++b) v = b < lc ? red_op(v, __uint_as_float(raw[g * kS + b]), p.red_inner) : v;
+        if (p.red_inner == kRedSum) v *= 1.f / (float)lc;
+        v = q_ok ? v : neutral;
+#pragma unroll
+        for (int o = 1; o < kS; o <<= 1) v = red_op(v, __shfl_xor_sync(0xffffffffu, v, o), p.red_outer);
+        if (p.red_outer == kRedSum) v *= rq;
+        out[g] = __float_as_uint(v);
+      }
     }
 #pragma unroll
     for (int g = kGroups; g < 32; ++g) out[g] = 0xff800000u;
@@ -578,7 +609,7 @@ struct EvalEpiT {
                                                  const uint32_t (&acc)[32], const GemmShape& sh, const EpiCtx& ctx) {
     if constexpr (kS > 1) {
       uint32_t red[32];
-      reduce_tracks(p, acc, red);
+      reduce_tracks(p, acc, red, row, col0, sh);
       chunk32_tracks(p, st, row, col0 / kS, red, sh, ctx);
     } else {
       chunk32_tracks(p, st, row, col0, acc, sh, ctx);

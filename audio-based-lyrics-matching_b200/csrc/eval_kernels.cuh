@@ -141,10 +141,6 @@ __device__ __forceinline__ void mma_16x8x16(float (&c)[4], const unsigned (&a)[4
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-__device__ __forceinline__ float red_neutral(int op) {
-  return op == kRedMax ? __int_as_float(0xff800000) : (op == kRedMin ? __int_as_float(0x7f800000) : 0.f);
-}
-
 // K_pos for chunked tracks (row f1).  One warp per query track: for every relevant candidate track the kS x kS chunk
 // similarities (same planes, same three products as the sweep) are reduced exactly like the sweep's epilogue does
 // (red_inner over the candidate's chunks, red_outer over the query's), then rank-sorted ascending.
@@ -156,12 +152,16 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
     const __half* __restrict__ c_lo, int d_pad, int ks, int red_inner, int red_outer, float red_scale,
     const int* __restrict__ q_i, int nq, const int* __restrict__ sorted_idx, const int* __restrict__ c_i,
     const int* __restrict__ seg_lo, const int* __restrict__ seg_len, const long long* __restrict__ off,
-    float* __restrict__ raw, float* __restrict__ thr, float* __restrict__ lim, int* __restrict__ cnt) {
+    float* __restrict__ raw, float* __restrict__ thr, float* __restrict__ lim, int* __restrict__ cnt,
+    const int* __restrict__ q_len, const int* __restrict__ c_len) {
   const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (q >= nq) return;
   const int g = lane >> 2, tig = lane & 3;
   const int first = seg_lo[q], len = seg_len[q], qi = q_i[q];
+  // ragged tracks (q_len / c_len given): valid chunks only, means over the valid counts -- same as the sweep's epilogue
+  const bool ragged = c_len != nullptr;
+  const int lq = ragged ? min(max(q_len[q], 1), ks) : ks;
   const long long o = off[q];
   // A rows: the query's chunks g and g + 8 (clamped: rows >= ks are masked out of the reduction)
   const long long ra0 = ((long long)q * ks + min(g, ks - 1)) * d_pad, ra1 = ((long long)q * ks + min(g + 8, ks - 1)) * d_pad;
@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
   for (int m = 0; m < len; ++m) {
     const int j = sorted_idx[first + m];
     if (c_i[j] == qi) continue;  // self / id collision
+    const int lc = ragged ? min(max(c_len[j], 1), ks) : ks;
     float v0 = red_neutral(red_inner), v1 = red_neutral(red_inner);  // inner reductions of rows g and g + 8
     for (int t = 0; t < ntile; ++t) {
       const long long rb = ((long long)j * ks + min(t * 8 + g, ks - 1)) * d_pad;  // B column g = candidate chunk t * 8 + g
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
       // c[0], c[1]: row g, candidate chunks t*8 + 2 tig, + 1;  c[2], c[3]: row g + 8, same columns
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        if (t * 8 + tig * 2 + e < ks) {
+        if (t * 8 + tig * 2 + e < lc) {
           v0 = red_op(v0, c[e], red_inner);
           v1 = red_op(v1, c[2 + e], red_inner);
         }
@@ -210,14 +211,19 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
       v0 = red_op(v0, __shfl_xor_sync(0xffffffffu, v0, x), red_inner);
       v1 = red_op(v1, __shfl_xor_sync(0xffffffffu, v1, x), red_inner);
     }
-    if (red_inner == kRedSum && red_outer != kRedSum) { v0 *= red_scale; v1 *= red_scale; }
+    if (ragged) {
+      if (red_inner == kRedSum) { v0 *= 1.f / (float)lc; v1 *= 1.f / (float)lc; }
+    } else if (red_inner == kRedSum && red_outer != kRedSum) {
+      v0 *= red_scale;
+      v1 *= red_scale;
+    }
     // outer: across the query's chunks = rows g (v0) and g + 8 (v1) of all row groups
     float w = red_neutral(red_outer);
-    if (g < ks) w = red_op(w, v0, red_outer);
-    if (g + 8 < ks) w = red_op(w, v1, red_outer);
+    if (g < lq) w = red_op(w, v0, red_outer);
+    if (g + 8 < lq) w = red_op(w, v1, red_outer);
 #pragma unroll
     for (int x = 4; x < 32; x <<= 1) w = red_op(w, __shfl_xor_sync(0xffffffffu, w, x), red_outer);
-    if (red_outer == kRedSum) w *= red_scale;
+    if (red_outer == kRedSum) w *= ragged ? 1.f / (float)lq : red_scale;
     if (lane == 0) raw[o + n] = w;
     ++n;
   }

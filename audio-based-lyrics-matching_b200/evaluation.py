@@ -108,13 +108,17 @@ class EvalPlan:
         return ms.value
 
     def run(self, queries_z, candidates_z, *, topk=None, eps=1e-6, precision=None, allow_empty=False, chunks=None,
-            redux="min"):
+            redux="min", q_chunks=None, c_chunks=None):
         """-> dict(aps, r1s, sums[, topk_idx, topk_sim]); `sums` = device doubles {sum AP, sum R1, #scored}.
 
         Chunked tracks: pass `[N, s, D]` embeddings (or `[N * s, D]` with `chunks=s`,
         s in {2, 4, 8, 16}): the s x s chunk distances of every track pair are reduced like
         `distance_tensor_redux(dist, redux)` (lib/tensor_ops.py:288-373; redux in min / max / mean / meanmin /
-        minmean) inside the sweep's epilogue before ranking; ids and results are per track."""
+        minmean) inside the sweep's epilogue before ranking; ids and results are per track.
+
+        Ragged tracks: `q_chunks[Nq]` / `c_chunks[Nc]` = valid chunks of every track (1 .. s; the remaining rows are
+        padding): reduced like `distance_tensor_redux(dist, redux, mask)` with mask = query chunk invalid | candidate
+        chunk invalid."""
         if self.queries_without_relevant and not allow_empty:
             raise ValueError(f"{self.queries_without_relevant} queries have no relevant candidate "
                              "(every clique needs >= 2 versions; pass allow_empty=True to score the rest)")
@@ -146,6 +150,28 @@ class EvalPlan:
         sums = torch.empty(3, dtype=torch.float64, device=self.device)
         tk_idx = torch.empty((self.nq, k), dtype=torch.long, device=self.device) if k else None
         tk_sim = torch.empty((self.nq, k), dtype=torch.float32, device=self.device) if k else None
+        if (q_chunks is None) != (c_chunks is None):
+            if not same:
+                raise ValueError("q_chunks and c_chunks go together")
+            q_chunks = c_chunks = q_chunks if c_chunks is None else c_chunks
+        if q_chunks is not None:
+            if s == 1:
+                raise ValueError("chunk counts need chunked tracks")
+            ql = torch.as_tensor(q_chunks).to(self.device, torch.int32).contiguous()
+            cl = ql if c_chunks is q_chunks else torch.as_tensor(c_chunks).to(self.device, torch.int32).contiguous()
+            assert ql.shape == (self.nq,) and cl.shape == (self.nc,)
+            with torch.cuda.device(self.device):
+                N.check(N.lib.wealy_eval_run_ragged(
+                    self._handle, qz.data_ptr(), qz.stride(0), cz.data_ptr(), cz.stride(0), qz.shape[1],
+                    N.dtype_code(qz.dtype), float(eps), passes_of(precision), k, s, N.REDUX[redux], ql.data_ptr(),
+                    cl.data_ptr(), aps.data_ptr(), r1s.data_ptr(), sums.data_ptr(), tk_idx.data_ptr() if k else None,
+                    tk_sim.data_ptr() if k else None, N.stream_ptr(self.device)))
+            ql.record_stream(torch.cuda.current_stream(self.device))
+            cl.record_stream(torch.cuda.current_stream(self.device))
+            out = {"aps": aps, "r1s": r1s, "sums": sums}
+            if k:
+                out["topk_idx"], out["topk_sim"] = tk_idx, tk_sim
+            return out
         with torch.cuda.device(self.device):
             N.check(N.lib.wealy_eval_run_chunked(
                 self._handle, qz.data_ptr(), qz.stride(0), cz.data_ptr(), cz.stride(0), qz.shape[1],
@@ -159,7 +185,8 @@ class EvalPlan:
 
 
 def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z, *, topk=None, mode="cos",
-             eps=1e-6, precision=None, allow_empty=False, plan=None, chunks=None, redux="min"):
+             eps=1e-6, precision=None, allow_empty=False, plan=None, chunks=None, redux="min", q_chunks=None,
+             c_chunks=None):
     """-> (aps[Nq], r1s[Nq]) or (aps, r1s, topk_idx[Nq,k], topk_sim[Nq,k]) on the CUDA device.
 
     AP_q = 1/P sum_{p relevant} rank_rel(p) / rank_all(p); R1_q = rank of the best relevant item;
@@ -171,7 +198,7 @@ def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candid
         plan = EvalPlan(queries_c, queries_i, candidates_c, candidates_i)
     try:
         res = plan.run(queries_z, candidates_z, topk=topk, eps=eps, precision=precision, allow_empty=allow_empty,
-                       chunks=chunks, redux=redux)
+                       chunks=chunks, redux=redux, q_chunks=q_chunks, c_chunks=c_chunks)
     finally:
         if own:
             torch.cuda.current_stream(plan.device).synchronize()

@@ -118,6 +118,15 @@ enum { WEALY_REDUX_MIN = 0, WEALY_REDUX_MAX = 1, WEALY_REDUX_MEAN = 2, WEALY_RED
 int wealy_eval_run_chunked(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, const void* candidates_z,
                            int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, int chunks, int redux,
                            float* aps, float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, void* stream);
+/* Ragged tracks: as wealy_eval_run_chunked, but track t has only q_len[t] / c_len[t] valid chunks (device int32
+ * [nq] / [nc], values 1 .. chunks; the rows of the remaining chunks are padding and may hold anything finite).
+ * Padding is excluded exactly like the mask argument of distance_tensor_redux (lib/tensor_ops.py:288-373, mask =
+ * query chunk invalid OR candidate chunk invalid; True = excluded, `:186`): min / max over the valid chunk pairs,
+ * means divided by the valid counts.                                                                            */
+int wealy_eval_run_ragged(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, const void* candidates_z,
+                          int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, int chunks, int redux,
+                          const int32_t* q_len, const int32_t* c_len, float* aps, float* r1s, double* sums,
+                          int64_t* topk_idx, float* topk_sim, void* stream);
 /* Multi-GPU all-vs-all (queries == candidates, no top-k).  Every rank holds the whole corpus and calls
  * wealy_eval_sweep_shard with its (shard_rank, shard_world): the symmetric sweep is restricted to the row blocks
  * rb = shard_rank (mod shard_world) and leaves this rank's share of the rank counts in the plan.  The caller

@@ -26,11 +26,13 @@ def _as_long(t):
     return torch.as_tensor(t).long().reshape(-1)
 
 
-def _sim_block(qz, cz, mode, redux=None):
+def _sim_block(qz, cz, mode, redux=None, q_len=None, c_len=None):
     """similarity (higher = closer) of a block of queries against all candidates.
 
     Chunked tracks (qz [b, s1, D], cz [nc, s2, D]): the chunk-level cosine DISTANCES (b, nc, s1, s2) are reduced with
-    the restated distance_tensor_redux (lib/tensor_ops.py:288-373) and returned as 1 - distance."""
+    the restated distance_tensor_redux (lib/tensor_ops.py:288-373) and returned as 1 - distance.  Ragged tracks:
+    q_len [b] / c_len [nc] valid chunks per track -> the redux's mask (True = excluded, lib/tensor_ops.py:186) is
+    "query chunk >= q_len or candidate chunk >= c_len"."""
     if mode not in ("cos", "cossim", "dot", "dotsim"):
         raise NotImplementedError(mode)
     base = "cossim" if mode in ("cos", "cossim") else "dotsim"
@@ -40,12 +42,17 @@ def _sim_block(qz, cz, mode, redux=None):
         nc, s2, _ = cz.shape
         dist = 1 - distance_matrix(qz.reshape(b * s1, d), cz.reshape(nc * s2, d), mode=base)
         dist = dist.reshape(b, s1, nc, s2).permute(0, 2, 1, 3)            # (b1, b2, s1, s2)
-        return 1 - distance_tensor_redux(dist, redux or "min")
+        mask = None
+        if q_len is not None:
+            qm = torch.arange(s1)[None, :] >= torch.as_tensor(q_len).long()[:, None]      # (b, s1)
+            cm = torch.arange(s2)[None, :] >= torch.as_tensor(c_len).long()[:, None]      # (nc, s2)
+            mask = qm[:, None, :, None] | cm[None, :, None, :]
+        return 1 - distance_tensor_redux(dist, redux or "min", mask)
     return distance_matrix(qz, cz, mode=base)
 
 
 def evaluate_argsort(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z,
-                     *, topk=None, mode="cos", block=256, redux=None):
+                     *, topk=None, mode="cos", block=256, redux=None, q_len=None, c_len=None):
     """Returns (aps[Nq], r1s[Nq]) and, when topk is given, (topk_idx[Nq,k], topk_sim[Nq,k]).
 
     A query without any relevant candidate raises ValueError (the reference data pipeline
@@ -61,7 +68,8 @@ def evaluate_argsort(queries_c, queries_i, queries_z, candidates_c, candidates_i
         tk_idx = torch.full((nq, k), -1, dtype=torch.long)
         tk_sim = torch.full((nq, k), float("-inf"), dtype=qz.dtype)
     for b0 in range(0, nq, block):
-        sim = _sim_block(qz[b0:b0 + block], cz, mode, redux)   # (b, nc)
+        sim = _sim_block(qz[b0:b0 + block], cz, mode, redux,
+                         None if q_len is None else torch.as_tensor(q_len)[b0:b0 + block], c_len)   # (b, nc)
         dist = 1 - sim                                          # "cos"/"dot" distance
         for r in range(sim.shape[0]):
             q = b0 + r
@@ -117,7 +125,7 @@ def evaluate_rankcount(queries_c, queries_i, queries_z, candidates_c, candidates
 
 
 def rank_tolerance(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z,
-                   *, gap=1e-5, mode="cos", block=256, redux=None):
+                   *, gap=1e-5, mode="cos", block=256, redux=None, q_len=None, c_len=None):
     """For the parity rule "ranks exact wherever the similarity gap exceeds `gap`": per query,
     returns (r1_lo, r1_hi): the range the rank of the best relevant item may take when every
     candidate whose similarity is within `gap` of it may fall on either side."""
@@ -128,7 +136,8 @@ def rank_tolerance(queries_c, queries_i, queries_z, candidates_c, candidates_i, 
     lo = torch.empty(nq, dtype=torch.float64)
     hi = torch.empty(nq, dtype=torch.float64)
     for b0 in range(0, nq, block):
-        sim = _sim_block(qz[b0:b0 + block], cz, mode, redux).double()
+        sim = _sim_block(qz[b0:b0 + block], cz, mode, redux,
+                         None if q_len is None else torch.as_tensor(q_len)[b0:b0 + block], c_len).double()
         for r in range(sim.shape[0]):
             q = b0 + r
             is_self = ci == qi[q]

@@ -69,3 +69,58 @@ def test_chunked_queries_disjoint_from_corpus_and_errors():
     with pytest.raises(NotImplementedError):
         z3 = z[:, :3].contiguous().cuda()
         we.evaluate(c.cuda(), i.cuda(), z3, c.cuda(), i.cuda(), z3)
+
+
+def _ragged(n, s, d, seed):
+    c, i, z = _chunked_set(n, s, d, seed)
+    g = torch.Generator().manual_seed(seed + 500)
+    lens = torch.randint(1, s + 1, (n,), generator=g)
+    for t in range(n):                                                      # padding chunks hold junk, not zeros
+        z[t, lens[t]:] = 23.0 * torch.randn(s - int(lens[t]), d, generator=g)
+    return c, i, z.contiguous(), lens
+
+
+@pytest.mark.parametrize("redux", ["min", "max", "mean", "meanmin", "minmean"])
+@pytest.mark.parametrize("n,s,d", [(700, 4, 96), (333, 8, 64), (200, 16, 48), (900, 2, 128)])
+def test_ragged_tracks_parity_with_oracle(n, s, d, redux):
+    """Tracks with 1 .. s valid chunks: padding is excluded like distance_tensor_redux's mask (lib/tensor_ops.py:288)."""
+    from wealy_b200 import evaluation as we
+    c, i, z, lens = _ragged(n, s, d, seed=n + s)
+    aps_o, r1_o = oev.evaluate_argsort(c, i, z, c, i, z, redux=redux, q_len=lens, c_len=lens)
+    cq, iq, zq = c.cuda(), i.cuda(), z.cuda()
+    aps, r1s = we.evaluate(cq, iq, zq, cq, iq, zq, redux=redux, q_chunks=lens, c_chunks=lens)
+    torch.cuda.synchronize()
+    aps, r1s = aps.cpu().double(), r1s.cpu().double()
+    assert abs(float(aps.mean()) - float(aps_o.mean())) <= 1e-4
+    assert abs(float(r1s.mean()) - float(r1_o.mean())) <= 1e-4 * max(1.0, float(r1_o.mean()))
+    lo, hi = oev.rank_tolerance(c, i, z, c, i, z, gap=1e-5, redux=redux, q_len=lens, c_len=lens)
+    assert bool(((r1s >= lo) & (r1s <= hi)).all())
+    exact = lo == hi
+    assert torch.equal(r1s[exact], r1_o[exact])
+
+
+def test_ragged_tracks_topk_disjoint_queries_and_full_counts():
+    from wealy_b200 import evaluation as we
+    n, s, d, k = 600, 4, 64, 8
+    c, i, z, lens = _ragged(n, s, d, seed=11)
+    q, cand = slice(0, 120), slice(120, 600)
+    keep = torch.tensor([bool((c[cand] == c[t]).any()) for t in range(120)])
+    qc, qi, qz, ql = c[q][keep], i[q][keep], z[q][keep].contiguous(), lens[q][keep]
+    _, _, idx_o, sim_o = oev.evaluate_argsort(qc, qi, qz, c[cand], i[cand], z[cand], topk=k, redux="meanmin",
+                                              q_len=ql, c_len=lens[cand])
+    _, _, idx, sim = we.evaluate(qc.cuda(), qi.cuda(), qz.cuda(), c[cand].cuda(), i[cand].cuda(), z[cand].cuda(), topk=k,
+                                 redux="meanmin", q_chunks=ql, c_chunks=lens[cand])
+    idx, sim = idx.cpu(), sim.cpu()
+    assert (sim - sim_o).abs().max() <= 4e-6
+    ok = torch.ones_like(idx_o, dtype=torch.bool)
+    ok[:, 1:] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    ok[:, :-1] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    assert torch.equal(idx[ok], idx_o[ok])
+    # all chunks valid == the dense chunked path (same ranks up to rounding of the means)
+    full = torch.full((n,), s)
+    cq, iq, zq = c.cuda(), i.cuda(), z.cuda()
+    a1, r1 = we.evaluate(cq, iq, zq, cq, iq, zq, redux="min", q_chunks=full, c_chunks=full)
+    a0, r0 = we.evaluate(cq, iq, zq, cq, iq, zq, redux="min")
+    assert torch.equal(a1, a0) and torch.equal(r1, r0)
+    with pytest.raises(ValueError):
+        we.evaluate(cq, iq, zq[:, 0].contiguous(), cq, iq, zq[:, 0].contiguous(), q_chunks=full, c_chunks=full)

@@ -135,3 +135,33 @@ def test_chunked_oracle_redux_ordering():
     assert bool((r["min"] <= r["meanmin"] + eps).all()) and bool((r["meanmin"] <= r["mean"] + eps).all())
     assert bool((r["min"] <= r["minmean"] + eps).all()) and bool((r["minmean"] <= r["mean"] + eps).all())
     assert bool((r["mean"] <= r["max"] + eps).all())
+
+
+def _ragged_set(n, s, d, seed):
+    from wealy_b200.data import synth
+    base = synth.make_eval_set(n, d, seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    z = base["z"][:, None, :] + 0.5 * base["z"].norm(dim=1).mean() / d ** 0.5 * torch.randn(n, s, d, generator=g)
+    lens = torch.randint(1, s + 1, (n,), generator=g)
+    return base["c"], base["i"], z.contiguous(), lens
+
+
+@pytest.mark.parametrize("redux", ["min", "max", "mean", "meanmin", "minmean"])
+def test_ragged_oracle_against_explicit_loops(redux):
+    """Ragged tracks: the mask handed to the restated distance_tensor_redux (True = excluded, lib/tensor_ops.py:186)
+    reproduces reductions written out over the valid chunks of every track pair; padding content is irrelevant."""
+    c, i, z, lens = _ragged_set(40, 4, 16, seed=2)
+    sim = oev._sim_block(z, z, "cos", redux, lens, lens)
+    zn = z / (z.norm(dim=-1, keepdim=True) + 1e-6)
+    for a in range(0, 40, 7):
+        for b in range(0, 40, 5):
+            dd = 1 - zn[a, :lens[a]] @ zn[b, :lens[b]].T               # valid chunk pairs only
+            want = {"min": dd.min(), "max": dd.max(), "mean": dd.mean(), "meanmin": dd.min(dim=1).values.mean(),
+                    "minmean": dd.mean(dim=1).min()}[redux]
+            assert abs(float(sim[a, b]) - float(1 - want)) < 1e-5
+    junk = z.clone()
+    for t in range(40):
+        junk[t, lens[t]:] = 37.0 * torch.randn(4 - int(lens[t]), 16)
+    assert torch.allclose(oev._sim_block(junk, junk, "cos", redux, lens, lens), sim, atol=1e-6)
+    full = torch.full((40,), 4)
+    assert torch.allclose(oev._sim_block(z, z, "cos", redux, full, full), oev._sim_block(z, z, "cos", redux), atol=1e-6)
