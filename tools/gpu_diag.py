@@ -64,7 +64,7 @@ def stage_time(precision, n, d, reps=3, topk=0, sigma=2.4):
     ms = min(ev[r].elapsed_time(ev[r + 1]) for r in range(reps))
     m, r1 = we.mean_metrics(out["sums"])
     print(f"time {precision} n={n} d={d} topk={topk} sigma={sigma}: {ms:.2f} ms  {n * n / ms / 1e6:.1f} Gpairs/s  MAP={m:.4f} MR1={r1:.2f} "
-          f"pairs={plan.total_pairs}", flush=True)
+          f"pairs={plan.total_pairs} sweep={plan.last_sweep_ms():.2f} ms", flush=True)
 
 
 def stage_time_chunked(precision, n, s_chunks, d, redux="min", reps=3):
