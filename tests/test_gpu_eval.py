@@ -369,3 +369,46 @@ def test_equal_ids_in_distinct_tensors_take_the_all_vs_all_path():
     i2 = i.clone(); i2[3] += 1
     with pytest.raises(AssertionError):
         we.EvalPlan(c, i, c.clone(), i2).sweep_shard(z, 0, 2)
+
+
+@pytest.mark.parametrize("d", [1, 7, 65, 4096])
+def test_tiny_sets_and_odd_embedding_sizes(d):
+    """Two tracks of one clique up to a few dozen tracks; D = 1, not a multiple of the k-block, and 64 k-blocks."""
+    g = torch.Generator().manual_seed(d)
+    z = torch.randn(2, d, generator=g) + 0.1
+    aps, r1s = _gpu_eval(torch.tensor([5, 5]), torch.tensor([10, 11]), z)
+    assert torch.equal(aps, torch.ones(2)) and torch.equal(r1s, torch.ones(2))
+    n = 37
+    c = torch.arange(n) // 3
+    c[-1] = c[-2]                                                         # 37 = 12 * 3 + 1: no singleton clique
+    i = torch.arange(n) + 100
+    z = torch.randn(n, d, generator=g)
+    aps_o, r1_o = oev.evaluate_argsort(c, i, z, c, i, z)
+    aps, r1s = _gpu_eval(c, i, z)
+    if d == 1:                                                            # every similarity is +-1: all ties
+        assert abs(float(aps.mean()) - float(aps_o.mean())) < 0.5
+        return
+    lo, hi = oev.rank_tolerance(c, i, z, c, i, z, gap=1e-5)
+    assert bool(((r1s.double() >= lo) & (r1s.double() <= hi)).all())
+    assert abs(float(aps.double().mean()) - float(aps_o.mean())) <= 1e-4
+    # general (queries != corpus tensors) path on the same data
+    aps2, r1s2 = _gpu_eval(c[:9], i[:9], z[:9].clone(), c, i, z)
+    assert bool(((r1s2.double() >= lo[:9]) & (r1s2.double() <= hi[:9])).all())
+
+
+def test_zero_vectors_and_float64_inputs():
+    """Adversarial rows: all-zero embeddings have similarity 0 to everything (x / (|x| + eps), lib/tensor_ops.py:152-176);
+    float64 embeddings are refused loudly (the CUDA path takes float32 / float16 / bfloat16), never computed on the CPU."""
+    s = _synth().make_eval_set(600, 48, seed=21)
+    z = s["z"].clone()
+    z[::50] = 0
+    aps_o, r1_o = oev.evaluate_argsort(s["c"], s["i"], z, s["c"], s["i"], z)
+    aps, r1s = _gpu_eval(s["c"], s["i"], z)
+    assert bool(torch.isfinite(aps).all())
+    lo, hi = oev.rank_tolerance(s["c"], s["i"], z, s["c"], s["i"], z, gap=1e-5)
+    nz = torch.ones(600, dtype=torch.bool)
+    nz[::50] = False                       # a zero query ties with every candidate: its rank is a tie-break, not compared
+    assert abs(float(aps.double()[nz].mean()) - float(aps_o[nz].mean())) <= 1e-4
+    assert bool(((r1s.double() >= lo) & (r1s.double() <= hi))[nz].all())
+    with pytest.raises(NotImplementedError):
+        _gpu_eval(s["c"], s["i"], s["z"].double())
