@@ -93,6 +93,25 @@ def gen_redux():
     np.savez_compressed(os.path.join(HERE, "redux.npz"), **out)
 
 
+def gen_redux_ragged():
+    """Ragged tracks: chunk-level cosine distances of [N, s, D] tracks whose last chunks are padding, reduced by the
+    reference with the rectangular mask `query chunk invalid | candidate chunk invalid` -- the case the fused
+    evaluation implements (wealy_eval_run_ragged)."""
+    out = {}
+    g = torch.Generator().manual_seed(23)
+    n, m, s, d = 9, 11, 4, 16
+    zq, zc = torch.randn(n, s, d, generator=g), torch.randn(m, s, d, generator=g)
+    lq, lc = torch.randint(1, s + 1, (n,), generator=g), torch.randint(1, s + 1, (m,), generator=g)
+    lq[0], lc[0] = 1, s
+    dist = tops.pairwise_distance_matrix(zq.reshape(n * s, d), zc.reshape(m * s, d), mode="cos")
+    dist = dist.reshape(n, s, m, s).permute(0, 2, 1, 3).contiguous()
+    mask = (torch.arange(s)[None, :] >= lq[:, None])[:, None, :, None] | (torch.arange(s)[None, :] >= lc[:, None])[None, :, None, :]
+    out["zq"], out["zc"], out["lq"], out["lc"] = zq.numpy(), zc.numpy(), lq.numpy(), lc.numpy()
+    for redux in ("min", "max", "mean", "minmean", "meanmin"):
+        out[f"r_{redux}"] = tops.distance_tensor_redux(dist, redux, mask=mask).numpy()
+    np.savez_compressed(os.path.join(HERE, "redux_ragged.npz"), **out)
+
+
 def _loss_case(B, D, dtype, seed, per_clique=4, dup_idx=True, single_label=False):
     g = torch.Generator().manual_seed(seed)
     z = (torch.randn(B, D, generator=g) * 1.5 + 0.1).to(dtype)
@@ -202,6 +221,7 @@ if __name__ == "__main__":
     gen_similarity()
     gen_masked()
     gen_redux()
+    gen_redux_ragged()
     gen_losses()
     gen_pooling_triplet()
     for f in sorted(os.listdir(HERE)):

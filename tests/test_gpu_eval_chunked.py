@@ -124,3 +124,23 @@ def test_ragged_tracks_topk_disjoint_queries_and_full_counts():
     assert torch.equal(a1, a0) and torch.equal(r1, r0)
     with pytest.raises(ValueError):
         we.evaluate(cq, iq, zq[:, 0].contiguous(), cq, iq, zq[:, 0].contiguous(), q_chunks=full, c_chunks=full)
+
+
+@pytest.mark.parametrize("redux", ["min", "max", "mean", "minmean", "meanmin"])
+def test_ragged_tracks_topk_similarities_against_reference_outputs(redux):
+    """Golden vectors produced by the unmodified reference (distance_tensor_redux with the ragged mask): the fused
+    sweep's top-k similarities over ALL candidates are 1 - those distances."""
+    import os
+    import numpy as np
+    from wealy_b200 import evaluation as we
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "redux_ragged.npz"))
+    zq, zc = torch.from_numpy(G["zq"]).cuda(), torch.from_numpy(G["zc"]).cuda()
+    lq, lc = torch.from_numpy(G["lq"]), torch.from_numpy(G["lc"])
+    n, m = zq.shape[0], zc.shape[0]
+    qc, qi = torch.zeros(n, dtype=torch.long).cuda(), (torch.arange(n) + 1000).cuda()     # one clique, no self matches
+    cc, ci = torch.zeros(m, dtype=torch.long).cuda(), torch.arange(m).cuda()
+    _, _, idx, sim = we.evaluate(qc, qi, zq, cc, ci, zc, topk=m, redux=redux, q_chunks=lq, c_chunks=lc)
+    want = 1 - torch.from_numpy(G[f"r_{redux}"])                                          # [n, m]
+    got = torch.empty_like(want)
+    got.scatter_(1, idx.cpu(), sim.cpu())
+    assert (got - want).abs().max() <= 4e-6
