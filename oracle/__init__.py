@@ -21,5 +21,7 @@ Parity status
   ``lib/losses.py:40-42``, the distance of ``lib/tensor_ops.py:167-173`` and the
   argument vocabulary of ``lib/audio_dataset/dataset.py:82-86,448-449``; it ships
   in two forms (argsort and rank-count) that are tested equal, plus hand-computed
-  known-answer cases.
+  known-answer cases.  What the reference does define is pinned: the ranking is
+  checked against an argsort of the reference's own "cos" distance goldens, the
+  chunk reduction (also with ragged masks) against its distance_tensor_redux goldens.
 """

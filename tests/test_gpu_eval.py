@@ -412,3 +412,35 @@ def test_zero_vectors_and_float64_inputs():
     assert bool(((r1s.double() >= lo) & (r1s.double() <= hi))[nz].all())
     with pytest.raises(NotImplementedError):
         _gpu_eval(s["c"], s["i"], s["z"].double())
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_ranking_follows_the_reference_distance_matrix(case):
+    """The reference has no evaluator, but it does define the distances the ranking is made of: the fused sweep's
+    full candidate order (top-k with k = Nc) and AP / R1 must be the ones an argsort of the UNMODIFIED reference's
+    pairwise_distance_matrix(x, y, mode="cos") output gives (tests/golden/sim_modes.npz; case a holds a zero vector
+    and an exact duplicate)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_modes.npz"))
+    x, y = torch.from_numpy(G[f"{case}_x"]), torch.from_numpy(G[f"{case}_y"])
+    dist = torch.from_numpy(G[f"{case}_cos"]).double()                       # [n, m], reference output
+    n, m = dist.shape
+    g = torch.Generator().manual_seed(5)
+    qc, cc = torch.randint(0, 6, (n,), generator=g), torch.randint(0, 6, (m,), generator=g)
+    qi, ci = torch.arange(n) + 10_000, torch.arange(m)                       # queries are not in the corpus
+    aps, r1s, idx, sim = _gpu_eval(qc, qi, x, cc, ci, y, topk=m)
+    got = torch.empty(n, m).scatter_(1, idx, sim)
+    assert (got.double() - (1 - dist)).abs().max() <= 4e-6
+    order = torch.argsort(dist, dim=1, stable=True)
+    sd = torch.gather(dist, 1, order)
+    ok = torch.ones(n, m, dtype=torch.bool)
+    ok[:, 1:] &= (sd[:, 1:] - sd[:, :-1]) > 1e-5
+    ok[:, :-1] &= (sd[:, 1:] - sd[:, :-1]) > 1e-5
+    assert torch.equal(idx[ok], order[ok])                                   # same order wherever the gap exceeds 1e-5
+    for q in range(n):
+        rel = (cc[order[q]] == qc[q]).double()
+        if rel.sum() == 0 or not bool(ok[q].all()):
+            continue
+        hits = torch.cumsum(rel, 0)
+        ap = float((hits / torch.arange(1, m + 1) * rel).sum() / rel.sum())
+        assert abs(float(aps[q]) - ap) <= 1e-6 and float(r1s[q]) == float(torch.nonzero(rel)[0, 0] + 1)

@@ -165,3 +165,28 @@ def test_ragged_oracle_against_explicit_loops(redux):
     assert torch.allclose(oev._sim_block(junk, junk, "cos", redux, lens, lens), sim, atol=1e-6)
     full = torch.full((40,), 4)
     assert torch.allclose(oev._sim_block(z, z, "cos", redux, full, full), oev._sim_block(z, z, "cos", redux), atol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["a", "b"])
+def test_oracle_ranks_by_the_reference_distance_matrix(case):
+    """The reference holds no evaluator, but the distances the ranking is made of are its own: AP / R1
+    of the oracle equal the ones read off an argsort of the UNMODIFIED reference's pairwise_distance_matrix(mode="cos")
+    output (tests/golden/sim_modes.npz)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "sim_modes.npz"))
+    x, y = torch.from_numpy(G[f"{case}_x"]), torch.from_numpy(G[f"{case}_y"])
+    dist = torch.from_numpy(G[f"{case}_cos"]).double()
+    n, m = dist.shape
+    g = torch.Generator().manual_seed(5)
+    qc, cc = torch.randint(0, 6, (n,), generator=g), torch.randint(0, 6, (m,), generator=g)
+    qi, ci = torch.arange(n) + 10_000, torch.arange(m)
+    aps, r1s = oev.evaluate_argsort(qc, qi, x, cc, ci, y)
+    order = torch.argsort(dist, dim=1, stable=True)
+    sd = torch.gather(dist, 1, order)
+    for q in range(n):
+        rel = (cc[order[q]] == qc[q]).double()
+        if rel.sum() == 0 or bool(((sd[q, 1:] - sd[q, :-1]) <= 1e-6).any()):
+            continue
+        hits = torch.cumsum(rel, 0)
+        ap = float((hits / torch.arange(1, m + 1) * rel).sum() / rel.sum())
+        assert abs(float(aps[q]) - ap) <= 1e-6 and float(r1s[q]) == float(torch.nonzero(rel)[0, 0] + 1)
