@@ -813,8 +813,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       pos_sort_sorted_kernel<<<blocks, threads, 0, s>>>(p->s_npos, (int)nq, (int)p->s_padded, p->s_off, p->raw, p->thr,
                                                         p->cnt, p->s_lvl, p->s_cinfo);
     } else if (chunks > 1) {
-      const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
-      pos_thresholds_tracks_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, chunks, red_inner,
+      if (nq > 0) pos_thresholds_tracks_kernel<<<(unsigned)nq, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, chunks, red_inner,
                                                               red_outer, red_scale, p->q_i, (int)nq, p->sorted_idx,
                                                               p->c_i, p->seg_lo, p->seg_len, p->off, p->raw, p->thr,
                                                               p->lim, p->cnt, q_len, c_len);

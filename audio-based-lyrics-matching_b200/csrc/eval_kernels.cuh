@@ -141,7 +141,7 @@ __device__ __forceinline__ void mma_16x8x16(float (&c)[4], const unsigned (&a)[4
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// K_pos for chunked tracks (row f1).  One warp per query track: for every relevant candidate track the kS x kS chunk
+// K_pos for chunked tracks (row f1).  One CTA (8 warps) per query track: for every relevant candidate track the kS x kS chunk
 // similarities (same planes, same three products as the sweep) are reduced exactly like the sweep's epilogue does
 // (red_inner over the candidate's chunks, red_outer over the query's), then rank-sorted ascending.
 // The kS x kS block of a (query track, candidate track) pair is one (kS <= 8) or two
@@ -154,9 +154,13 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
     const int* __restrict__ seg_lo, const int* __restrict__ seg_len, const long long* __restrict__ off,
     float* __restrict__ raw, float* __restrict__ thr, float* __restrict__ lim, int* __restrict__ cnt,
     const int* __restrict__ q_len, const int* __restrict__ c_len) {
-  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
-  const int lane = (int)(threadIdx.x & 31);
-  if (q >= nq) return;
+  // one CTA per query track, its 8 warps take the relevant candidates round-robin (a clique of 160 versions is 20
+  // sequential contractions per warp, not 160); slots of the query's CSR row are handed out by a shared counter
+  const int q = (int)blockIdx.x;
+  const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
+  __shared__ int n_sh;
+  if (threadIdx.x == 0) n_sh = 0;
+  __syncthreads();
   const int g = lane >> 2, tig = lane & 3;
   const int first = seg_lo[q], len = seg_len[q], qi = q_i[q];
   // ragged tracks (q_len / c_len given): valid chunks only, means over the valid counts -- same as the sweep's epilogue
@@ -166,8 +170,7 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
   // A rows: the query's chunks g and g + 8 (clamped: rows >= ks are masked out of the reduction)
   const long long ra0 = ((long long)q * ks + min(g, ks - 1)) * d_pad, ra1 = ((long long)q * ks + min(g + 8, ks - 1)) * d_pad;
   const int ntile = ks > 8 ? 2 : 1;
-  int n = 0;
-  for (int m = 0; m < len; ++m) {
+  for (int m = warp; m < len; m += 8) {
     const int j = sorted_idx[first + m];
     if (c_i[j] == qi) continue;  // self / id collision
     const int lc = ragged ? min(max(c_len[j], 1), ks) : ks;
@@ -179,14 +182,18 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
 #pragma unroll 2
       for (int k = 0; k < d_pad; k += 32) {
         const int ko = k + tig * 8;
-        const uint4 ah0 = __ldg(reinterpret_cast<const uint4*>(q_hi + ra0 + ko)), ah1 = __ldg(reinterpret_cast<const uint4*>(q_hi + ra1 + ko));
+        // (tile rows 8 .. 15 exist only for 16 chunks per track: zero, not loaded, otherwise)
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        const uint4 ah0 = __ldg(reinterpret_cast<const uint4*>(q_hi + ra0 + ko));
+        const uint4 ah1 = ks > 8 ? __ldg(reinterpret_cast<const uint4*>(q_hi + ra1 + ko)) : zero4;
         const uint4 bh = __ldg(reinterpret_cast<const uint4*>(c_hi + rb + ko));
         const unsigned a1[4] = {ah0.x, ah1.x, ah0.y, ah1.y}, a2[4] = {ah0.z, ah1.z, ah0.w, ah1.w};
         const unsigned b1[2] = {bh.x, bh.y}, b2[2] = {bh.z, bh.w};
         mma_16x8x16(c, a1, b1);
         mma_16x8x16(c, a2, b2);
         if (q_lo) {
-          const uint4 al0 = __ldg(reinterpret_cast<const uint4*>(q_lo + ra0 + ko)), al1 = __ldg(reinterpret_cast<const uint4*>(q_lo + ra1 + ko));
+          const uint4 al0 = __ldg(reinterpret_cast<const uint4*>(q_lo + ra0 + ko));
+          const uint4 al1 = ks > 8 ? __ldg(reinterpret_cast<const uint4*>(q_lo + ra1 + ko)) : zero4;
           const uint4 bl = __ldg(reinterpret_cast<const uint4*>(c_lo + rb + ko));
           const unsigned l1[4] = {al0.x, al1.x, al0.y, al1.y}, l2[4] = {al0.z, al1.z, al0.w, al1.w};
           const unsigned m1[2] = {bl.x, bl.y}, m2[2] = {bl.z, bl.w};
@@ -224,11 +231,11 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
 #pragma unroll
     for (int x = 4; x < 32; x <<= 1) w = red_op(w, __shfl_xor_sync(0xffffffffu, w, x), red_outer);
     if (red_outer == kRedSum) w *= ragged ? 1.f / (float)lq : red_scale;
-    if (lane == 0) raw[o + n] = w;
-    ++n;
+    if (lane == 0) raw[o + atomicAdd(&n_sh, 1)] = w;
   }
-  __syncwarp();
-  for (int e = lane; e < n; e += 32) {
+  __syncthreads();
+  const int n = n_sh;
+  for (int e = (int)threadIdx.x; e < n; e += (int)blockDim.x) {
     const float ve = raw[o + e];
     int r = 0;
     for (int f = 0; f < n; ++f) {
@@ -237,8 +244,8 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
     }
     thr[o + r] = ve;
   }
-  __syncwarp();
-  if (lane == 0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
     cnt[q] = n;
     lim[q] = n > 0 ? thr[o] : __int_as_float(0x7f800000);
   }

@@ -67,25 +67,29 @@ def stage_time(precision, n, d, reps=3, topk=0, sigma=2.4):
           f"pairs={plan.total_pairs} sweep={plan.last_sweep_ms():.2f} ms", flush=True)
 
 
-def stage_time_chunked(precision, n, s_chunks, d, redux="min", reps=3):
+def stage_time_chunked(precision, n, s_chunks, d, redux="min", reps=3, ragged=False):
     base = synth.make_eval_set(n, d, seed=0, device="cuda", md5_ids=False)
     g = torch.Generator(device="cuda").manual_seed(1)
     z = (base["z"][:, None, :] + 0.8 * base["z"].norm(dim=1).mean() / d ** 0.5
          * torch.randn(n, s_chunks, d, generator=g, device="cuda")).contiguous()
     plan = we.EvalPlan(base["c"], base["i"], base["c"], base["i"])
+    kw = {}
+    if ragged:                                  # 1 .. s valid chunks per track
+        lens = torch.randint(1, s_chunks + 1, (n,), generator=g, device="cuda").to(torch.int32)
+        kw = dict(q_chunks=lens, c_chunks=lens)
     for _ in range(2):
-        out = plan.run(z, z, precision=precision, redux=redux)
+        out = plan.run(z, z, precision=precision, redux=redux, **kw)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     ev[0].record()
     for r in range(reps):
-        out = plan.run(z, z, precision=precision, redux=redux)
+        out = plan.run(z, z, precision=precision, redux=redux, **kw)
         ev[r + 1].record()
     torch.cuda.synchronize()
     ms = min(ev[r].elapsed_time(ev[r + 1]) for r in range(reps))
     m, r1 = we.mean_metrics(out["sums"])
     rows = n * s_chunks
-    print(f"time_chunked {precision} tracks={n} chunks={s_chunks} d={d} redux={redux}: {ms:.2f} ms  "
+    print(f"time_chunked{' (ragged)' if ragged else ''} {precision} tracks={n} chunks={s_chunks} d={d} redux={redux}: {ms:.2f} ms  "
           f"{rows * rows / ms / 1e6:.1f} G chunk-pairs/s ({n * n / ms / 1e6:.2f} G track-pairs/s)  MAP={m:.4f} MR1={r1:.2f} "
           f"sweep={plan.last_sweep_ms():.2f} ms", flush=True)
 
@@ -170,7 +174,7 @@ if __name__ == "__main__":
     elif st == "time":
         stage_time(a[0], int(a[1]), int(a[2]), 3, int(a[3]) if len(a) > 3 else 0, float(a[4]) if len(a) > 4 else 2.4)
     elif st == "time_chunked":
-        stage_time_chunked(a[0], int(a[1]), int(a[2]), int(a[3]), *(a[4:5]))
+        stage_time_chunked(a[0], int(a[1]), int(a[2]), int(a[3]), *(a[4:5]), ragged=len(a) > 5 and a[5] == "ragged")
     elif st == "loss":
         stage_loss(a[0])
     elif st == "losstime":
