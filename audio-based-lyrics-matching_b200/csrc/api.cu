@@ -806,7 +806,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     if (sym) {
       // the plan's cnt array doubles as the per-query fill counter of step 1 (step 2 rewrites it)
       CU_TRY(cudaMemsetAsync(p->cnt, 0, (size_t)nq * 4, s));
-      pos_pairs_sorted_kernel<<<(unsigned)ceil_div(nq, 16), threads, 0, s>>>(pq.hi, pq.lo, (int)pq.d_pad, p->sorted_c, p->s_i,
+      pos_pairs_sorted_kernel<false><<<(unsigned)ceil_div(nq, 16), threads, 0, s>>>(pq.hi, pq.lo, (int)pq.d_pad, p->sorted_c, p->s_i,
                                                                          (int)nq, p->s_seg_lo, p->s_seg_len, p->s_off,
                                                                          p->raw, p->cnt);
       const unsigned blocks = (unsigned)ceil_div(p->s_padded * 32, threads);
@@ -817,6 +817,14 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
                                                               red_outer, red_scale, p->q_i, (int)nq, p->sorted_idx,
                                                               p->c_i, p->seg_lo, p->seg_len, p->off, p->raw, p->thr,
                                                               p->lim, p->cnt, q_len, c_len);
+    } else if (same && p->same_ids && nq > 0 && env_int("WEALY_KPOS_BLOCKS", 1) != 0) {
+      // all-vs-all through the rectangle sweep (top-k requested): the clique-block tensor-core K_pos of the symmetric
+      // path on the caller's row order (every unordered pair's operands are read once per 16 x 8 block, not per pair)
+      CU_TRY(cudaMemsetAsync(p->cnt, 0, (size_t)nq * 4, s));
+      pos_pairs_sorted_kernel<true><<<(unsigned)ceil_div(nq, 16), threads, 0, s>>>(
+          pq.hi, pq.lo, (int)pq.d_pad, p->sorted_c, p->s_i, (int)nq, p->s_seg_lo, p->s_seg_len, p->off, p->raw, p->cnt,
+          p->sorted_idx);
+      pos_sort_kernel<<<(unsigned)ceil_div(nq * 32, threads), threads, 0, s>>>((int)nq, p->off, p->raw, p->thr, p->lim, p->cnt);
     } else {
       const unsigned blocks = (unsigned)ceil_div(nq * 32, threads);
       pos_thresholds_kernel<<<blocks, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, p->q_i, (int)nq,

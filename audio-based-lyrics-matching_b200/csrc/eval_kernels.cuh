@@ -305,10 +305,15 @@ __global__ void dirty_everything_kernel(const int* __restrict__ everything, long
 // (hi*hi + hi*lo + lo*hi), 5-10x less L2 traffic than one dot product per pair.  Valid pairs (same clique, version
 // ids differ) are appended to the query's CSR slice in arbitrary order (fill[q] counts them; step 2 sorts).
 
+// kGather (all-vs-all through the rectangle sweep, e.g. with top-k): the planes are in the caller's row order, sorted
+// row s is plane row perm[s], and off / fill are indexed by the caller's query index perm[q].
+template <bool kGather>
 __global__ void __launch_bounds__(256) pos_pairs_sorted_kernel(
     const __half* __restrict__ hi, const __half* __restrict__ lo, int d_pad, const int* __restrict__ s_c,
     const int* __restrict__ s_i, int n, const int* __restrict__ seg_lo, const int* __restrict__ seg_len,
-    const long long* __restrict__ off, float* __restrict__ raw, int* __restrict__ fill) {
+    const long long* __restrict__ off, float* __restrict__ raw, int* __restrict__ fill,
+    const int* __restrict__ perm = nullptr) {
+  auto plane_row = [&](int srow) { return kGather ? __ldg(perm + srow) : spread_plane_of(srow); };
   const int q0 = blockIdx.x * 16;
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
   const int g = lane >> 2, tig = lane & 3;
@@ -316,12 +321,13 @@ __global__ void __launch_bounds__(256) pos_pairs_sorted_kernel(
   const int lo_row = seg_lo[q0], hi_row = seg_lo[qlast] + seg_len[qlast];  // candidates any of the 16 queries needs
   const int qa = min(q0 + g, n - 1), qb = min(q0 + g + 8, n - 1);          // (clamped rows are discarded below)
   // (the planes are in the sweep's spread row order: sorted row s lives at plane row spread_plane_of(s))
-  const __half* a_hi0 = hi + (long long)spread_plane_of(qa) * d_pad;
-  const __half* a_hi1 = hi + (long long)spread_plane_of(qb) * d_pad;
-  const __half* a_lo0 = lo ? lo + (long long)spread_plane_of(qa) * d_pad : nullptr;
-  const __half* a_lo1 = lo ? lo + (long long)spread_plane_of(qb) * d_pad : nullptr;
+  const int pa = plane_row(qa), pb = plane_row(qb);
+  const __half* a_hi0 = hi + (long long)pa * d_pad;
+  const __half* a_hi1 = hi + (long long)pb * d_pad;
+  const __half* a_lo0 = lo ? lo + (long long)pa * d_pad : nullptr;
+  const __half* a_lo1 = lo ? lo + (long long)pb * d_pad : nullptr;
   for (int j0 = lo_row + warp * 8; j0 < hi_row; j0 += 64) {
-    const int jb = spread_plane_of(min(j0 + g, n - 1));
+    const int jb = plane_row(min(j0 + g, n - 1));
     const __half* b_hi = hi + (long long)jb * d_pad;
     const __half* b_lo = lo ? lo + (long long)jb * d_pad : nullptr;
     float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -354,11 +360,35 @@ __global__ void __launch_bounds__(256) pos_pairs_sorted_kernel(
       const int q = q0 + g + (e >> 1) * 8;
       const int j = j0 + tig * 2 + (e & 1);
       if (q < n && j < hi_row && s_c[q] == s_c[j] && s_i[q] != s_i[j]) {
-        const int slot = atomicAdd(fill + q, 1);
-        raw[off[q] + slot] = c[e];
+        const int oq = kGather ? __ldg(perm + q) : q;
+        const int slot = atomicAdd(fill + oq, 1);
+        raw[off[oq] + slot] = c[e];
       }
     }
   }
+}
+
+// K_pos step 2 for the rectangle sweep after pos_pairs_sorted_kernel<true>: one warp per query rank-sorts the cnt[q]
+// appended similarities ascending into thr and sets lim[q] (the lowest, +inf if none).
+__global__ void __launch_bounds__(256) pos_sort_kernel(int nq, const long long* __restrict__ off, const float* __restrict__ raw,
+                                                       float* __restrict__ thr, float* __restrict__ lim,
+                                                       const int* __restrict__ cnt) {
+  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (q >= nq) return;
+  const int n = cnt[q];
+  const long long o = off[q];
+  for (int e = lane; e < n; e += 32) {
+    const float ve = raw[o + e];
+    int r = 0;
+    for (int f = 0; f < n; ++f) {
+      const float vf = raw[o + f];
+      r += (vf < ve) || (vf == ve && f < e);
+    }
+    thr[o + r] = ve;
+  }
+  __syncwarp();
+  if (lane == 0) lim[q] = n > 0 ? thr[o] : __int_as_float(0x7f800000);
 }
 
 // K_pos step 2.  One warp per query: rank-sort its pair similarities ascending into thr (CSR); the lowest four go
