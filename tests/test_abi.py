@@ -76,3 +76,16 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 if f != "make_clique_sizes.py":     # docstrings may CITE the reference, nothing may read it
                     assert not re.search(r"(open|listdir|insert|exists|isfile)\([^)]*reference", src), f
+
+
+def test_ctypes_signatures_match_the_header_argument_counts():
+    """Every prototype in include/wealy_b200.h has as many parameters as its ctypes signature in _native.py."""
+    import wealy_b200._native as N
+    src = open(os.path.join(ROOT, "include", "wealy_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = dict(re.findall(r"\b(wealy_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    assert set(protos) == set(N.SIGNATURES)
+    for name, params in protos.items():
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(N.SIGNATURES[name][1]), f"{name}: header has {n} parameters, ctypes {len(N.SIGNATURES[name][1])}"
