@@ -6,6 +6,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "../../include/wealy_b200.h"
 #include "epilogues.cuh"
@@ -67,26 +68,69 @@ static int num_sms() {
   return cached;
 }
 
-// Stream-ordered device allocations from the default memory pool, configured once per device to keep
-// freed memory cached (no cudaMalloc / cudaFree round trips through the driver when an evaluation
-// plan is rebuilt every call, as the end-to-end path of bench.py does).
+// Stream-ordered device allocations from a PRIVATE memory pool per device (the process-wide default pool and
+// torch's caching allocator are left alone).  Freed blocks stay cached in the pool so that an evaluation plan
+// rebuilt on every call (the end-to-end path of bench.py) costs no cudaMalloc / cudaFree round trips through the
+// driver; wealy_eval_plan_destroy trims the pool back to WEALY_POOL_KEEP_MB (default 4096) so that a training
+// process that evaluates now and then does not sit on the plan scratch for ever.
+static cudaMemPool_t g_pools[64] = {nullptr};
+
+static cudaMemPool_t device_pool(int dev) {
+  if (dev < 0 || dev >= 64) return nullptr;
+  if (!g_pools[dev]) {
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    unsigned long long keep = ~0ull;  // bounded by the explicit trim below, not by every stream synchronisation
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    g_pools[dev] = pool;
+  }
+  return g_pools[dev];
+}
+
 static cudaError_t dev_alloc(void** ptr, size_t bytes, cudaStream_t s) {
-  static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 64 && !configured[dev]) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
-    configured[dev] = true;
-  }
+  cudaMemPool_t pool = device_pool(dev);
+  if (pool) return cudaMallocFromPoolAsync(ptr, bytes, pool, s);
   return cudaMallocAsync(ptr, bytes, s);
 }
 static void dev_free(void* ptr, cudaStream_t s) {
   if (ptr) cudaFreeAsync(ptr, s);
 }
+static void pool_trim() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !g_pools[dev]) return;
+  const size_t keep = (size_t)env_int("WEALY_POOL_KEEP_MB", 4096) << 20;
+  cudaMemPoolTrimTo(g_pools[dev], keep);
+}
+
+// temporaries of one host function: freed (stream-ordered) on every return path
+struct TempAllocs {
+  cudaStream_t s;
+  void* ptrs[16];
+  int n = 0;
+  explicit TempAllocs(cudaStream_t stream) : s(stream) {}
+  cudaError_t alloc(void** ptr, size_t bytes) {
+    *ptr = nullptr;
+    if (n >= 16) return cudaErrorMemoryAllocation;
+    cudaError_t e = dev_alloc(ptr, bytes, s);
+    if (e == cudaSuccess) ptrs[n++] = *ptr;
+    return e;
+  }
+  ~TempAllocs() {
+    for (int k = 0; k < n; ++k) dev_free(ptrs[k], s);
+  }
+};
 
 // ------------------------------------------------------------------------------------------
 // TMA descriptors (driver entry point fetched through the runtime: no link-time libcuda dependency)
@@ -510,7 +554,8 @@ extern "C" int wealy_dot_matrix_backward(const void* grad, int64_t ld_grad, cons
 // ------------------------------------------------------------------------------------------
 struct wealy_eval_plan {
   int64_t nq = 0, nc = 0;
-  cudaStream_t stream = nullptr;  // stream the plan was built on (frees are ordered on it)
+  cudaStream_t stream = nullptr;  // stream the plan was built on
+  cudaStream_t last_stream = nullptr;  // stream of the last run (frees are ordered on it)
   bool same_ids = false;
   int *q_c = nullptr, *q_i = nullptr, *c_c = nullptr, *c_i = nullptr;
   int *sorted_c = nullptr, *sorted_idx = nullptr;
@@ -545,23 +590,34 @@ extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
   void* ptrs[] = {p->q_c, p->q_i, p->sorted_c, p->sorted_idx, p->seg_lo, p->seg_len, p->npos, p->off,
                   p->raw, p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf,
                   p->s_i, p->s_seg_lo, p->s_seg_len, p->s_npos, p->s_off, p->s_lvl, p->s_cinfo, p->s_dirty};
-  for (void* q : ptrs) dev_free(q, p->stream);
+  // frees are ordered behind the last work that touched the buffers: the stream of the last run
+  cudaStream_t fs = p->timed ? p->last_stream : p->stream;
+  for (void* q : ptrs) dev_free(q, fs);
   if (!p->same_ids) {
-    dev_free(p->c_c, p->stream);
-    dev_free(p->c_i, p->stream);
+    dev_free(p->c_c, fs);
+    dev_free(p->c_i, fs);
   }
+  pool_trim();
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   delete p;
 }
 
+// CSR offsets are 64-bit: the scan must ACCUMULATE in 64 bits too (one clique of ~46k versions already holds 2^31
+// relevant pairs), so the int32 counts are widened on the fly.
+struct WidenI32 {
+  __host__ __device__ __forceinline__ long long operator()(const int& v) const { return (long long)v; }
+};
+using WideCounts = cub::TransformInputIterator<long long, WidenI32, const int*>;
+
 static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_t* queries_i,
                       const int64_t* candidates_c, const int64_t* candidates_i, cudaStream_t s) {
   const int nq = (int)p->nq, nc = (int)p->nc;
   const int T = 256;
+  TempAllocs tmps(s);
   int* bad = nullptr;
   unsigned long long* totals = nullptr;
-  CU_TRY(dev_alloc((void**)&bad, 256, s));
+  CU_TRY(tmps.alloc((void**)&bad, 256));
   totals = reinterpret_cast<unsigned long long*>(bad + 16);
   CU_TRY(cudaMemsetAsync(bad, 0, 256, s));
   CU_TRY(dev_alloc((void**)&p->q_c, (size_t)nq * 4 + 4, s));
@@ -591,14 +647,14 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
 
   // candidates sorted by clique id (CUB radix sort: id-only preprocessing, not on the per-eval path)
   int* iota = nullptr;
-  CU_TRY(dev_alloc((void**)&iota, (size_t)nc * 4 + 4, s));
+  CU_TRY(tmps.alloc((void**)&iota, (size_t)nc * 4 + 4));
   CU_TRY(dev_alloc((void**)&p->sorted_c, (size_t)nc * 4 + 4, s));
   CU_TRY(dev_alloc((void**)&p->sorted_idx, (size_t)nc * 4 + 4, s));
   iota_kernel<<<(unsigned)ceil_div(nc, T), T, 0, s>>>(iota, nc);
   size_t tmp_bytes = 0;
   CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, p->c_c, p->sorted_c, iota, p->sorted_idx, nc, 0, 32, s));
   void* tmp = nullptr;
-  CU_TRY(dev_alloc((void**)&tmp, tmp_bytes + 16, s));
+  CU_TRY(tmps.alloc((void**)&tmp, tmp_bytes + 16));
   CU_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p->c_c, p->sorted_c, iota, p->sorted_idx, nc, 0, 32, s));
 
   CU_TRY(dev_alloc((void**)&p->seg_lo, (size_t)nq * 4 + 4, s));
@@ -610,12 +666,12 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   CU_TRY(cudaGetLastError());
   // CSR offsets over the per-query number of relevant candidates
   size_t scan_bytes = 0;
-  CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, p->npos, p->off, nq + 1, s));
+  CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, WideCounts(p->npos, WidenI32()), p->off, nq + 1, s));
   void* tmp2 = nullptr;
-  CU_TRY(dev_alloc((void**)&tmp2, scan_bytes + 16, s));
+  CU_TRY(tmps.alloc((void**)&tmp2, scan_bytes + 16));
   // npos has nq valid entries; entry nq is read by the scan of nq+1 items -> zero it first
   CU_TRY(cudaMemsetAsync(p->npos + nq, 0, 4, s));
-  CU_TRY(cub::DeviceScan::ExclusiveSum(tmp2, scan_bytes, p->npos, p->off, nq + 1, s));
+  CU_TRY(cub::DeviceScan::ExclusiveSum(tmp2, scan_bytes, WideCounts(p->npos, WidenI32()), p->off, nq + 1, s));
 
   // ---- clique-sorted view for the symmetric all-vs-all sweep
   void* tmp3 = nullptr;
@@ -638,17 +694,17 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
                                                                 p->s_seg_lo, p->s_seg_len, p->s_npos, totals + 2);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaMemsetAsync(p->s_npos + n, 0, 4, s));
-    CU_TRY(cub::DeviceScan::ExclusiveSum(tmp2, scan_bytes, p->s_npos, p->s_off, n + 1, s));
+    CU_TRY(cub::DeviceScan::ExclusiveSum(tmp2, scan_bytes, WideCounts(p->s_npos, WidenI32()), p->s_off, n + 1, s));
     // tiles that need id tests: clique ranges that intersect, ragged edges, version-id collisions
     CU_TRY(cudaMemsetAsync(p->s_dirty, 0, (size_t)nrb * nct, s));
     dirty_clique_kernel<<<(unsigned)ceil_div((int64_t)nrb * nct, T), T, 0, s>>>(p->sorted_c, n, nrb, nct, p->s_dirty);
-    CU_TRY(dev_alloc((void**)&vkeys, (size_t)n * 4 + 4, s));
-    CU_TRY(dev_alloc((void**)&vpos, (size_t)n * 4 + 4, s));
-    CU_TRY(dev_alloc((void**)&everything, 16, s));
+    CU_TRY(tmps.alloc((void**)&vkeys, (size_t)n * 4 + 4));
+    CU_TRY(tmps.alloc((void**)&vpos, (size_t)n * 4 + 4));
+    CU_TRY(tmps.alloc((void**)&everything, 16));
     CU_TRY(cudaMemsetAsync(everything, 0, 16, s));
     size_t tb = 0;
     CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, p->s_i, vkeys, iota, vpos, n, 0, 32, s));
-    CU_TRY(dev_alloc(&tmp3, tb + 16, s));
+    CU_TRY(tmps.alloc(&tmp3, tb + 16));
     CU_TRY(cub::DeviceRadixSort::SortPairs(tmp3, tb, p->s_i, vkeys, iota, vpos, n, 0, 32, s));
     dirty_collision_kernel<<<(unsigned)ceil_div(n, T), T, 0, s>>>(vkeys, vpos, n, nrb, nct, p->s_dirty, everything);
     dirty_everything_kernel<<<(unsigned)ceil_div((int64_t)nrb * nct, T), T, 0, s>>>(everything, (long long)nrb * nct, p->s_dirty);
@@ -662,14 +718,6 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   CU_TRY(cudaMemcpyAsync(totals_h, totals, sizeof(totals_h), cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaMemcpyAsync(&total, p->off + nq, 8, cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaStreamSynchronize(s));
-  dev_free(tmp, s);
-  dev_free(tmp2, s);
-  dev_free(tmp3, s);
-  dev_free(vkeys, s);
-  dev_free(vpos, s);
-  dev_free(everything, s);
-  dev_free(iota, s);
-  dev_free(bad, s);
   if (bad_h[0] != 0) return fail(WEALY_ERR_ID_RANGE, "%d clique/version ids do not fit in 32 bits", bad_h[0]);
   p->total_pairs = total;
   p->no_relevant = (int64_t)totals_h[0];
@@ -834,6 +882,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     CU_TRY(cudaGetLastError());
   }
   p->last_sym = sym;
+  p->last_stream = s;
   CU_TRY(cudaMemsetAsync(p->hist, 0, (size_t)(p->total_pairs > 0 ? p->total_pairs : 1) * 4, s));
   if (finish) CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
 
@@ -1018,6 +1067,23 @@ extern "C" int wealy_eval_finish(wealy_eval_plan* p, float* aps, float* r1s, dou
   const unsigned blocks = (unsigned)ceil_div(p->nq * 32, threads);
   if (p->last_sym) ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->s_off, p->cnt, (int)p->nq, aps, r1s, sums, p->sorted_idx);
   else ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)p->nq, aps, r1s, sums);
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+// Per-item ranks of the last run (all ranks' counters summed first in a sharded run): offsets [nq + 1] int64 = CSR
+// over the caller's queries, ranks / sims [total_pairs] = every query's relevant items, best first.
+extern "C" int wealy_eval_plan_ranks(const wealy_eval_plan* p, int64_t* offsets, int32_t* ranks, float* sims, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!p || !offsets || !ranks || !sims) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (!p->timed) return fail(WEALY_ERR_BAD_ARG, "the plan has not been run yet");
+  CU_TRY(cudaMemcpyAsync(offsets, p->off, ((size_t)p->nq + 1) * 8, cudaMemcpyDeviceToDevice, s));
+  const int threads = 256;
+  const unsigned blocks = (unsigned)ceil_div(p->nq * 32, threads);
+  if (p->last_sym)
+    rank_export_kernel<<<blocks, threads, 0, s>>>(p->hist, p->thr, p->s_off, p->cnt, (int)p->nq, p->off, p->sorted_idx, ranks, sims);
+  else
+    rank_export_kernel<<<blocks, threads, 0, s>>>(p->hist, p->thr, p->off, p->cnt, (int)p->nq, p->off, nullptr, ranks, sims);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
 }

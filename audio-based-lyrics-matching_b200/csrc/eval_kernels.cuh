@@ -498,6 +498,38 @@ __global__ void __launch_bounds__(256) ap_reduce_kernel(const unsigned int* __re
   }
 }
 
+// Per-item ranks (what AP is made of), exported for callers / parity tests: for every query, its relevant items
+// best first -- rank_all (1-based rank among all non-self candidates) and similarity.  Same suffix scan as K2.
+// `off` / `cnt` are in the order of the last sweep (sorted space when perm != nullptr), `out_off` is the CSR of
+// the caller's query order.
+__global__ void __launch_bounds__(256) rank_export_kernel(const unsigned int* __restrict__ hist, const float* __restrict__ thr,
+                                                          const long long* __restrict__ off, const int* __restrict__ cnt,
+                                                          int nq, const long long* __restrict__ out_off,
+                                                          const int* __restrict__ perm, int* __restrict__ ranks,
+                                                          float* __restrict__ sims) {
+  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = (int)(threadIdx.x & 31);
+  if (q >= nq) return;
+  const int P = cnt[q];
+  const long long o = off[q];
+  const long long oo = out_off[perm ? perm[q] : q];
+  unsigned int carry = 0;
+  for (int base = P - 1; base >= 0; base -= 32) {
+    const int r = base - lane;
+    unsigned int v = r >= 0 ? hist[o + r] : 0u;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, v, s);
+      if (lane >= s) v += t;
+    }
+    if (r >= 0) {
+      ranks[oo + (P - 1 - r)] = (int)(1u + carry + v + (unsigned)(P - 1 - r));
+      sims[oo + (P - 1 - r)] = thr[o + r];
+    }
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+
 // K3.  One warp per query: gather the candidates of every part, keep the k best (descending
 // similarity, ties -> lower candidate index, like a stable ascending-distance argsort).
 __global__ void __launch_bounds__(256) topk_finalize_kernel(const float* __restrict__ cand_val,

@@ -156,7 +156,7 @@ static int loss_forward_finish(const wealy_loss_cfg* cfg, int64_t b, int64_t d, 
   loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes, nb);
   CU_TRY(cudaMemsetAsync(out, 0, WEALY_OUT_COUNT * sizeof(double), s));
   loss_finish_kernel<<<(unsigned)ceil_div(b, 256), 256, 0, s>>>(loss_cfg_dev(cfg), (int)b, (int)d, w.acc, w.acc_max, w.zs,
-                                                                w.rowstat, w.scal, out);
+                                                                w.rowstat, w.scal, out, w.bad);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
 }

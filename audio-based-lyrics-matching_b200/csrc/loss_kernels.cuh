@@ -332,7 +332,8 @@ __global__ void __launch_bounds__(256) loss_merge_kernel(LossCfgDev cfg, int b, 
 __global__ void __launch_bounds__(256) loss_finish_kernel(LossCfgDev cfg, int b, int d, const double* __restrict__ acc,
                                                           const unsigned int* __restrict__ acc_max,
                                                           const ZStats* __restrict__ zs, float* __restrict__ rowstat,
-                                                          float* __restrict__ scal, double* __restrict__ out) {
+                                                          float* __restrict__ scal, double* __restrict__ out,
+                                                          const int* __restrict__ bad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const double B = (double)b;
   const bool writer = (i == 0);
@@ -375,6 +376,10 @@ __global__ void __launch_bounds__(256) loss_finish_kernel(LossCfgDev cfg, int b,
     out[2] = zs->sum / n;
     const double var = n > 1.0 ? (zs->sumsq - zs->sum * zs->sum / n) / (n - 1.0) : 0.0;
     out[3] = sqrt(var > 0.0 ? var : 0.0);
+    // labels / ids that do not fit in 32 bits were truncated by pack_ids_kernel: positives would be wrong, so the
+    // loss is poisoned (NaN) and the count reported -- no host sync on the training path
+    out[11] = (double)bad[0];
+    if (bad[0] != 0) out[0] = __longlong_as_double(0x7ff8000000000000ll);
   }
 }
 

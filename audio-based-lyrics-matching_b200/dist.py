@@ -8,15 +8,14 @@ Two schemes:
   diagonal, each element scoring its row and its column query).  A rank therefore holds partial rank counts for
   ALL queries; the one real exchange step of the path is an all-reduce (SUM) of those int32 counters -- the
   "rank counts merged over NCCL" of the north star -- after which every rank owns the complete AP / R1.
-* general queries vs corpus -- `evaluate_sharded`: queries partitioned over ranks, corpus replicated
-  (no data-path collective; results merged as below).
+* general queries vs corpus -- `evaluate_sharded`: queries are independent units, so rank r scores the contiguous
+  query slice shard_range(Nq, r, world) against the whole (replicated) corpus with the single-GPU fused kernel and
+  the data path needs no collective.  The only exchange is the result merge: one all-reduce of {sum AP, sum R1,
+  count} (24 bytes) for MAP / MR1 and, when per-query values are wanted, one all-gather of [Nq/world] x {ap, r1}
+  (and of the top-k lists).
 
-Queries are independent units, so the data path needs no collective: rank r scores the
-contiguous query slice shard_range(Nq, r, world) against the whole corpus with the single-GPU
-fused kernel.  The only exchange is the result merge -- one all-reduce of {sum AP, sum R1,
-count} (24 bytes) for MAP / MR1 and, when per-query values are wanted, one all-gather of
-[Nq/world] x {ap, r1} (and of the top-k lists).  One process per GPU, torch.distributed (NCCL
-over NVLink / NVSwitch on the GPU box; gloo in the CPU tests of the merge logic).
+Errors are raised on EVERY rank or on none: whatever one rank finds wrong with its share (a query without relevant
+candidates) is agreed on with a tiny all-reduce before any rank enters a data collective.
 """
 import torch
 import torch.distributed as dist
@@ -46,11 +45,16 @@ def gather_rows(local, n_total, group=None):
     world = dist.get_world_size(group)
     sizes = [shard_range(n_total, r, world) for r in range(world)]
     longest = max(hi - lo for lo, hi in sizes)
-    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    pad[: local.shape[0]] = local
+    # (gloo has no all_gather of CUDA tensors: results are staged through the host there -- CPU tests, and two
+    #  processes sharing one GPU)
+    via_host = local.is_cuda and dist.get_backend(group) == "gloo"
+    src = local.cpu() if via_host else local
+    pad = torch.zeros((longest,) + tuple(src.shape[1:]), dtype=src.dtype, device=src.device)
+    pad[: src.shape[0]] = src
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
-    return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+    full = torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+    return full.to(local.device) if via_host else full
 
 
 def upload_sharded(z_host, device, group=None):
@@ -78,42 +82,78 @@ def upload_sharded(z_host, device, group=None):
     return full[:n]
 
 
-def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=None):
+def _agree(flag, device, group=None):
+    """MAX of a small non-negative integer over the ranks: every rank learns whether ANY rank wants to raise."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return int(flag)
+    t = torch.tensor([int(flag)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return int(t.item())
+
+
+def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=None, allow_empty=False):
     """All-vs-all evaluation of one set (clique ids c, version ids i, embeddings z) over all ranks of `group`.
     Every rank passes the full tensors (host embeddings are uploaded 1/world per rank and all-gathered over
-    NVLink).  -> dict(map, mr1, count, aps, r1s, plan); identical on every rank."""
-    from .evaluation import EvalPlan, mean_metrics
+    NVLink).  -> dict(map, mr1, count, aps, r1s, plan); identical on every rank.
+
+    Like EvalPlan.run, a query without any relevant candidate raises ValueError unless allow_empty -- on every
+    rank (all ranks build the same id plan), before the first collective."""
+    from .evaluation import EvalPlan
     on = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if on else 0
     world = dist.get_world_size(group) if on else 1
     if plan is None:
         plan = EvalPlan(c, i, c, i)
+    if plan.queries_without_relevant and not allow_empty:
+        raise ValueError(f"{plan.queries_without_relevant} queries have no relevant candidate "
+                         "(every clique needs >= 2 versions; pass allow_empty=True to score the rest)")
     if world > 1 and not torch.as_tensor(z).is_cuda:
         z = upload_sharded(torch.as_tensor(z), plan.device, group)   # 1/world of the rows per rank + NVLink all-gather
     if world == 1:
-        res = plan.run(z, z, eps=eps, precision=precision)
+        res = plan.run(z, z, eps=eps, precision=precision, allow_empty=allow_empty)
     else:
         plan.sweep_shard(z, rank, world, eps=eps, precision=precision)
         counts = plan.counts_tensor()
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)   # the path's one exchange step
         res = plan.finish()
-    m, r1 = mean_metrics(res["sums"])
-    return {"map": m, "mr1": r1, "count": int(res["sums"][2].item()), "aps": res["aps"], "r1s": res["r1s"], "plan": plan}
+    s = res["sums"].cpu()                                            # one 24-byte device -> host read
+    n = max(float(s[2]), 1.0)
+    return {"map": float(s[0]) / n, "mr1": float(s[1]) / n, "count": int(s[2]), "aps": res["aps"], "r1s": res["r1s"],
+            "plan": plan}
 
 
 def evaluate_sharded(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z, *, topk=None,
-                     precision=None, eps=1e-6, gather=True, group=None, plan=None):
+                     precision=None, eps=1e-6, gather=True, group=None, plan=None, allow_empty=False):
     """Every rank passes the FULL query / candidate tensors (or its own copy of them); rank r
-    scores its slice.  Returns dict(map, mr1, count[, aps, r1s, topk_idx, topk_sim]) on every rank."""
+    scores its slice.  Returns dict(map, mr1, count[, aps, r1s, topk_idx, topk_sim]) on every rank.
+
+    A rank whose slice is empty (world > Nq) contributes nothing; a query without relevant candidates raises
+    ValueError on EVERY rank (agreed on before the merge collectives) unless allow_empty."""
     from .evaluation import EvalPlan
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
     nq = len(queries_c)
     lo, hi = shard_range(nq, rank, world)
+    device = plan.device if plan is not None else torch.device("cuda", torch.cuda.current_device())
     own = plan is None
-    if own:
-        plan = EvalPlan(queries_c[lo:hi], queries_i[lo:hi], candidates_c, candidates_i)
-    res = plan.run(queries_z[lo:hi], candidates_z, topk=topk, eps=eps, precision=precision)
+    if own and hi > lo:
+        plan = EvalPlan(queries_c[lo:hi], queries_i[lo:hi], candidates_c, candidates_i, device=device)
+    bad = 0 if plan is None else int(plan.queries_without_relevant)
+    bad = _agree(bad if not allow_empty else 0, device, group)
+    if bad:
+        raise ValueError("some queries have no relevant candidate (every clique needs >= 2 versions; "
+                         "pass allow_empty=True to score the rest)")
+    k = 0 if topk is None else min(int(topk), len(candidates_c))
+    if hi > lo:
+        res = plan.run(queries_z[lo:hi], candidates_z, topk=topk, eps=eps, precision=precision, allow_empty=allow_empty)
+    else:                                                            # empty shard: neutral contribution
+        res = {"aps": torch.empty(0, dtype=torch.float32, device=device),
+               "r1s": torch.empty(0, dtype=torch.float32, device=device),
+               "sums": torch.zeros(3, dtype=torch.float64, device=device)}
+        if k:
+            res["topk_idx"] = torch.empty((0, k), dtype=torch.long, device=device)
+            res["topk_sim"] = torch.empty((0, k), dtype=torch.float32, device=device)
     m, r1, cnt = merge_sums(res["sums"], group)
     out = {"map": m, "mr1": r1, "count": cnt, "plan": plan}
     if gather:

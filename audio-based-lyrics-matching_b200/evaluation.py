@@ -101,6 +101,19 @@ class EvalPlan:
                                             N.stream_ptr(self.device)))
         return {"aps": aps, "r1s": r1s, "sums": sums}
 
+    def ranks(self):
+        """Per-item ranks of the last run: (offsets[nq + 1] int64, ranks[total_pairs] int32, sims[total_pairs] f32);
+        query q's relevant candidates, best first, are ranks[offsets[q]:offsets[q + 1]] (1-based rank among all
+        non-self candidates) with their cosine similarities."""
+        n = max(int(self.total_pairs), 1)
+        offsets = torch.empty(self.nq + 1, dtype=torch.long, device=self.device)
+        ranks = torch.empty(n, dtype=torch.int32, device=self.device)
+        sims = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.wealy_eval_plan_ranks(self._handle, offsets.data_ptr(), ranks.data_ptr(), sims.data_ptr(),
+                                                N.stream_ptr(self.device)))
+        return offsets, ranks[: self.total_pairs], sims[: self.total_pairs]
+
     def last_sweep_ms(self):
         """Device time of the fused similarity+ranking kernel of the last run (CUDA events)."""
         ms = ctypes.c_float()

@@ -136,6 +136,11 @@ int wealy_eval_sweep_shard(wealy_eval_plan* plan, const void* z, int64_t ld, int
                            int passes, int shard_rank, int shard_world, void* stream);
 int wealy_eval_plan_counts(const wealy_eval_plan* plan, void** counts, int64_t* count);
 int wealy_eval_finish(wealy_eval_plan* plan, float* aps, float* r1s, double* sums, void* stream);
+/* Per-item ranks of the last run -- the quantities AP and R1 are made of.  offsets [nq + 1] int64 (CSR over the
+ * caller's queries; offsets[nq] = total_pairs of wealy_eval_plan_info), ranks / sims [total_pairs]: for every query its
+ * relevant candidates best first, rank = 1 + #{non-self candidates with a larger similarity}, sim = cosine similarity.
+ * After a sharded sweep call it once the counters have been summed over the ranks.                             */
+int wealy_eval_plan_ranks(const wealy_eval_plan* plan, int64_t* offsets, int32_t* ranks, float* sims, void* stream);
 /* device time (CUDA events on the run's stream) of the fused similarity+ranking sweep of the last
  * wealy_eval_run on this plan; blocks until that sweep has finished.                           */
 int wealy_eval_plan_last_sweep_ms(const wealy_eval_plan* plan, float* ms);
@@ -201,6 +206,7 @@ int wealy_triplet_backward(const void* z, int64_t ldz, int64_t b, int64_t d, int
 #define WEALY_OUT_ANCHORS 8   /* anchors_with_pos */
 #define WEALY_OUT_DPOS 9      /* v_dpos */
 #define WEALY_OUT_DNEG 10     /* v_dneg */
+#define WEALY_OUT_BAD_IDS 11  /* number of z_label / z_idx values that do not fit in 32 bits; non-zero => loss is NaN */
 #define WEALY_OUT_COUNT 16
 
 typedef struct wealy_loss_cfg {

@@ -150,5 +150,45 @@ def rank_tolerance(queries_c, queries_i, queries_z, candidates_c, candidates_i, 
     return lo, hi
 
 
+def rank_bands(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z,
+               *, gap=1e-5, mode="cos", block=256, redux=None, q_len=None, c_len=None):
+    """The parity rule "ranks bit-exact wherever the similarity gap exceeds `gap`" for EVERY relevant item (the
+    quantities AP is made of, not only R1).  Per query the relevant candidates are taken best first (descending
+    similarity; lib/losses.py:40-42 defines relevant / self, lib/tensor_ops.py:167-173 the similarity) and for the
+    k-th best, with similarity s_k:
+        exact[k] = 1 + #{j != self : s_j > s_k}                      (rank among all non-self candidates)
+        lo[k]    = 1 + #{j != self : s_j > s_k + gap}                every candidate within `gap` of s_k may fall
+        hi[k]    =     #{j != self : s_j > s_k - gap}                on either side (the item itself is in that set)
+    An implementation whose similarities are within gap/2 of these has its k-th best relevant rank inside [lo, hi]
+    (order statistics are 1-Lipschitz under sup-norm perturbations), and equal to exact[k] where lo == hi.
+    -> (offsets[nq + 1], sims, exact, lo, hi): CSR over the queries, float64 / int64 tensors."""
+    qc, qi, cc, ci = map(_as_long, (queries_c, queries_i, candidates_c, candidates_i))
+    qz = torch.as_tensor(queries_z)
+    cz = torch.as_tensor(candidates_z)
+    nq = qz.shape[0]
+    offsets = [0]
+    sims, exact, lo, hi = [], [], [], []
+    for b0 in range(0, nq, block):
+        sim = _sim_block(qz[b0:b0 + block], cz, mode, redux,
+                         None if q_len is None else torch.as_tensor(q_len)[b0:b0 + block], c_len).double()
+        for r in range(sim.shape[0]):
+            q = b0 + r
+            is_self = ci == qi[q]
+            rel = (cc == qc[q]) & ~is_self
+            s = sim[r]
+            thr = torch.sort(s[rel], descending=True).values
+            others = torch.sort(s[~is_self]).values
+            n = others.numel()
+            above = lambda x: n - torch.searchsorted(others, x.contiguous(), right=True)   # #{s_j > x}
+            sims.append(thr)
+            exact.append(1 + above(thr))
+            lo.append(1 + above(thr + gap))
+            hi.append(above(thr - gap))
+            offsets.append(offsets[-1] + thr.numel())
+    cat = lambda xs, dt: torch.cat(xs).to(dt) if xs else torch.empty(0, dtype=dt)
+    return (torch.tensor(offsets, dtype=torch.long), cat(sims, torch.float64), cat(exact, torch.long),
+            cat(lo, torch.long), cat(hi, torch.long))
+
+
 def mean_metrics(aps, r1s):
     return float(torch.as_tensor(aps).double().mean()), float(torch.as_tensor(r1s).double().mean())

@@ -73,6 +73,41 @@ def test_no_relevant_is_flagged():
     assert torch.isnan(aps[2]) and torch.isnan(r1s[2]) and float(aps[0]) == 1.0
 
 
+def _check_all_item_ranks(plan, c, i, z, cc=None, ci=None, cz=None, queries=None, gap=1e-5, sim_tol=4e-6):
+    """The parity contract on the quantities AP is made of: the rank of EVERY relevant item (not only the best one)
+    must lie in the band the candidates within `gap` of it allow, and be exact where that band is a single rank.
+    `plan` has just been run; `queries` (index tensor) restricts the oracle to a sample of the queries."""
+    cc, ci, cz = (c if cc is None else cc), (i if ci is None else ci), (z if cz is None else cz)
+    off_g, ranks_g, sims_g = (t.cpu() for t in plan.ranks())
+    qsel = torch.arange(len(c)) if queries is None else torch.as_tensor(queries).long().cpu()
+    off_o, sims_o, exact, lo, hi = oev.rank_bands(c[qsel], i[qsel], z[qsel], cc, ci, cz, gap=gap)
+    # gather the sampled queries' CSR slices of the device result
+    lens = off_g[qsel + 1] - off_g[qsel]
+    assert torch.equal(lens, off_o[1:] - off_o[:-1])                 # same relevant sets
+    pos = torch.cat([torch.arange(int(off_g[q]), int(off_g[q + 1])) for q in qsel.tolist()]) if len(qsel) else torch.empty(0, dtype=torch.long)
+    r, sg = ranks_g[pos].long(), sims_g[pos].double()
+    assert float((sg - sims_o).abs().max()) <= sim_tol               # k-th best relevant similarity
+    assert bool(((r >= lo) & (r <= hi)).all()), "a relevant item's rank left the band its 1e-5 neighbours allow"
+    single = lo == hi
+    assert torch.equal(r[single], exact[single])                     # bit-exact ranks wherever the gap exceeds 1e-5
+    return int(single.sum()), int(single.numel())
+
+
+def _run_plan(c, i, z, cc=None, ci=None, cz=None, **kw):
+    """Like _gpu_eval, but keeps the plan (for plan.ranks())."""
+    we = _we()
+    same = cc is None
+    cq, iq, zq = c.cuda(), i.cuda(), z.cuda()
+    if same:
+        plan = we.EvalPlan(cq, iq, cq, iq)
+        res = plan.run(zq, zq, **kw)
+    else:
+        plan = we.EvalPlan(cq, iq, cc.cuda(), ci.cuda())
+        res = plan.run(zq, cz.cuda(), **kw)
+    torch.cuda.synchronize()
+    return plan, res
+
+
 def _parity(s, precision="fp16x3", topk=None, d_map=1e-4, d_mr1=1e-4, gap=1e-5):
     aps_o, r1_o = oev.evaluate_argsort(s["c"], s["i"], s["z"], s["c"], s["i"], s["z"])
     res = _gpu_eval(s["c"], s["i"], s["z"], precision=precision, topk=topk)
@@ -86,6 +121,10 @@ def _parity(s, precision="fp16x3", topk=None, d_map=1e-4, d_mr1=1e-4, gap=1e-5):
         assert bool(((r1s >= lo) & (r1s <= hi)).all())
         exact = (lo == hi)
         assert torch.equal(r1s[exact], r1_o[exact])
+        # ... and so must the rank of every other relevant item (what AP is made of)
+        plan, _ = _run_plan(s["c"], s["i"], s["z"], precision=precision, topk=topk)
+        _check_all_item_ranks(plan, s["c"], s["i"], s["z"], gap=gap)
+        plan.close()
     return res, aps_o, r1_o
 
 
@@ -278,11 +317,14 @@ def test_full_size_properties():
 
 def _oracle_match(c, i, z, r1_slack=0):
     aps_o, r1_o = oev.evaluate_argsort(c, i, z, c, i, z)
-    aps, r1s = _gpu_eval(c, i, z)
+    plan, res = _run_plan(c, i, z)
+    aps, r1s = res["aps"].cpu(), res["r1s"].cpu()
     lo, hi = oev.rank_tolerance(c, i, z, c, i, z, gap=1e-5)
     r = r1s.double()
     assert bool(((r >= lo) & (r <= hi)).all())
     assert abs(float(aps.double().mean()) - float(aps_o.mean())) <= 1e-4
+    _check_all_item_ranks(plan, c, i, z)                              # every relevant item, not only the best
+    plan.close()
     return aps, r1s, aps_o, r1_o
 
 
@@ -444,3 +486,79 @@ def test_ranking_follows_the_reference_distance_matrix(case):
         hits = torch.cumsum(rel, 0)
         ap = float((hits / torch.arange(1, m + 1) * rel).sum() / rel.sum())
         assert abs(float(aps[q]) - ap) <= 1e-6 and float(r1s[q]) == float(torch.nonzero(rel)[0, 0] + 1)
+
+
+def test_all_item_ranks_general_and_topk_paths():
+    """plan.ranks() through the other two kernels: queries disjoint from the corpus (rectangle sweep) and the
+    all-vs-all top-k sweep; bands for every relevant item."""
+    s = _synth().make_eval_set(2600, 160, seed=51)
+    q, cand = slice(0, 500), slice(500, 2600)
+    keep = torch.tensor([bool((s["c"][cand] == s["c"][k]).any()) for k in range(500)])
+    qc, qi, qz = s["c"][q][keep], s["i"][q][keep], s["z"][q][keep]
+    plan, res = _run_plan(qc, qi, qz, s["c"][cand], s["i"][cand], s["z"][cand])
+    single, total = _check_all_item_ranks(plan, qc, qi, qz, s["c"][cand], s["i"][cand], s["z"][cand])
+    assert single > 0.9 * total                                      # the exactness clause is not vacuous
+    plan.close()
+    plan, res = _run_plan(s["c"], s["i"], s["z"], topk=10)
+    _check_all_item_ranks(plan, s["c"], s["i"], s["z"])
+    plan.close()
+
+
+def _topk_sample_parity(s, k, n_sample, seed):
+    """Top-k of the whole set on the GPU vs the oracle on a query sample: similarities within 4e-6, indices exact
+    wherever neighbouring similarities differ by more than 1e-5, self never returned."""
+    we = _we()
+    n = s["c"].numel()
+    c, i, z = s["c"].cuda(), s["i"].cuda(), s["z"].cuda()
+    plan = we.EvalPlan(c, i, c, i)
+    res = plan.run(z, z, topk=k)
+    torch.cuda.synchronize()
+    qs = torch.randperm(n, generator=torch.Generator().manual_seed(seed))[:n_sample]
+    cc, ic, zc = s["c"].cpu(), s["i"].cpu(), s["z"].cpu()
+    aps_o, r1_o, idx_o, sim_o = oev.evaluate_argsort(cc[qs], ic[qs], zc[qs], cc, ic, zc, topk=k)
+    idx, sim = res["topk_idx"][qs.cuda()].cpu(), res["topk_sim"][qs.cuda()].cpu()
+    assert (sim - sim_o).abs().max() <= 4e-6
+    ok = torch.ones_like(idx_o, dtype=torch.bool)
+    ok[:, 1:] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    ok[:, :-1] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+    assert float(ok.float().mean()) > 0.5
+    assert torch.equal(idx[ok], idx_o[ok])
+    assert bool((idx != qs[:, None]).all())
+    aps, r1s = res["aps"][qs.cuda()].double().cpu(), res["r1s"][qs.cuda()].double().cpu()
+    assert abs(float(aps.mean()) - float(aps_o.mean())) <= 1e-4
+    assert abs(float(r1s.mean()) - float(r1_o.mean())) <= 1e-4 * max(1.0, float(r1_o.mean()))
+    _check_all_item_ranks(plan, cc, ic, zc, queries=qs)
+    plan.close()
+
+
+def test_config5_lyric_covers_shape_top100():
+    """BASELINE.json configs[4]: lyric-covers multimodal retrieval -- ~50k tracks, 2048-d (text + audio concatenated),
+    top-100 output; clique sizes bootstrapped from the shipped lyric-covers test split.  256 sampled queries against
+    the oracle: top-100 indices / similarities, AP / R1 and the rank band of every relevant item."""
+    s = _synth().make_eval_set(50_000, 2048, seed=5, dist="lyric_covers_test", device="cuda", md5_ids=False)
+    _topk_sample_parity(s, 100, 256, seed=17)
+
+
+def test_config3_discogs_full_scale_shape():
+    """BASELINE.json configs[2]: Discogs-VI full scale, 500k x 1024 all-vs-all on one GPU (2.5e11 pairs): 64 sampled
+    queries against the oracle -- MAP / MR1 within 1e-4, rank bands of every relevant item."""
+    we = _we()
+    n = 500_000
+    s = _synth().make_eval_set(n, 1024, seed=3, device="cuda", md5_ids=False)
+    c, i, z = s["c"], s["i"], s["z"]
+    plan = we.EvalPlan(c, i, c, i)
+    res = plan.run(z, z)
+    torch.cuda.synchronize()
+    qs = torch.randperm(n, generator=torch.Generator().manual_seed(23))[:64]
+    cc, ic, zc = c.cpu(), i.cpu(), z.cpu()
+    aps_o, r1_o = oev.evaluate_argsort(cc[qs], ic[qs], zc[qs], cc, ic, zc)
+    aps, r1s = res["aps"][qs.cuda()].double().cpu(), res["r1s"][qs.cuda()].double().cpu()
+    assert abs(float(aps.mean()) - float(aps_o.mean())) <= 1e-4
+    assert abs(float(r1s.mean()) - float(r1_o.mean())) <= 1e-4 * max(1.0, float(r1_o.mean()))
+    lo, hi = oev.rank_tolerance(cc[qs], ic[qs], zc[qs], cc, ic, zc, gap=1e-5)
+    assert bool(((r1s >= lo) & (r1s <= hi)).all())
+    _check_all_item_ranks(plan, cc, ic, zc, queries=qs)
+    # size-independent property at full scale: the sums behind MAP / MR1 equal the per-query outputs
+    sm = res["sums"].cpu()
+    assert int(sm[2]) == n and abs(float(sm[0]) - float(res["aps"].double().sum())) <= 1e-6 * n
+    plan.close()

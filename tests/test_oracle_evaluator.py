@@ -190,3 +190,31 @@ def test_oracle_ranks_by_the_reference_distance_matrix(case):
         hits = torch.cumsum(rel, 0)
         ap = float((hits / torch.arange(1, m + 1) * rel).sum() / rel.sum())
         assert abs(float(aps[q]) - ap) <= 1e-6 and float(r1s[q]) == float(torch.nonzero(rel)[0, 0] + 1)
+
+
+def test_rank_bands_cover_every_relevant_item():
+    """rank_bands: the per-item form of the parity rule.  Its exact ranks reproduce AP / R1 of the rank-count
+    evaluator, bands contain the exact rank, and a perturbation below gap / 2 keeps every k-th best rank inside."""
+    from wealy_b200.data import synth  # noqa: F401  (needs the built library only for the package import)
+    s = synth.make_eval_set(400, 32, seed=77)
+    c, i, z = s["c"], s["i"], s["z"]
+    off, sims, exact, lo, hi = oev.rank_bands(c, i, z, c, i, z, gap=1e-5)
+    aps, r1s = oev.evaluate_rankcount(c, i, z, c, i, z)
+    assert off.numel() == 401 and int(off[-1]) == exact.numel()
+    assert bool(((lo <= exact) & (exact <= hi)).all())
+    for q in range(400):
+        r = exact[off[q]:off[q + 1]].double()
+        k = torch.arange(1, r.numel() + 1, dtype=torch.float64)
+        assert abs(float((k / r).mean()) - float(aps[q])) < 1e-12 and float(r[0]) == float(r1s[q])
+        assert bool((sims[off[q]:off[q + 1]][:-1] >= sims[off[q]:off[q + 1]][1:]).all())     # best first
+    # perturbed similarities (|err| < gap / 2): recompute the ranks of the k-th best relevant items by brute force
+    g = torch.Generator().manual_seed(1)
+    zn = z / (z.norm(dim=1, keepdim=True) + 1e-6)
+    S = (zn @ zn.T).double() + (torch.rand(400, 400, generator=g).double() - 0.5) * 0.9e-5
+    for q in range(0, 400, 7):
+        is_self = i == i[q]
+        rel = (c == c[q]) & ~is_self
+        thr = torch.sort(S[q][rel], descending=True).values
+        others = S[q][~is_self]
+        r = 1 + (others[None, :] > thr[:, None]).sum(1)
+        assert bool(((r >= lo[off[q]:off[q + 1]]) & (r <= hi[off[q]:off[q + 1]])).all())
