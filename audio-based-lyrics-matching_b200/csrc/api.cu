@@ -581,7 +581,10 @@ struct wealy_eval_plan {
   int64_t s_padded = 0;
   // CUDA events bracketing the fused sweep of the last run (roofline accounting in bench.py)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // ... and the stages around it: [0] before prep, [1] before K_pos, [2] after ap_reduce, [3] after the top-k finalize
+  cudaEvent_t evs[4] = {nullptr, nullptr, nullptr, nullptr};
   bool timed = false;
+  bool finished = false;  // the last run included ap_reduce (+ top-k finalize)
   bool last_sym = false;  // the last sweep ran in the clique-sorted view (its counters are in that CSR order)
 };
 
@@ -600,6 +603,8 @@ extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
   pool_trim();
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
+  for (cudaEvent_t e : p->evs)
+    if (e) cudaEventDestroy(e);
   delete p;
 }
 
@@ -844,11 +849,18 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   Planes pq, pc;
   carve_planes(pq, cur, rows_q, d, passes);
   if (same) pc = pq; else carve_planes(pc, cur, rc, d, passes);
+  if (!p->ev0) {
+    CU_TRY(cudaEventCreate(&p->ev0));
+    CU_TRY(cudaEventCreate(&p->ev1));
+    for (cudaEvent_t& e : p->evs) CU_TRY(cudaEventCreate(&e));
+  }
+  CU_TRY(cudaEventRecord(p->evs[0], s));
   W_TRY(launch_prep(queries_z, ld_q, rows_q, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s,
                     sym ? p->sorted_idx : nullptr, sym ? (int)nq : 0));
   if (!same) W_TRY(launch_prep(candidates_z, ld_c, rc, d, dtype, kPrepL2AddEps, eps, pc, nullptr, nullptr, 0, nullptr, 0, s));
 
   // K_pos: relevant similarities, sorted per query
+  CU_TRY(cudaEventRecord(p->evs[1], s));
   {
     const int threads = 256;
     if (sym) {
@@ -927,10 +939,6 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     ep.cand_cnt = ep.cand_idx + slots;
     CU_TRY(cudaMemsetAsync(ep.cand_cnt, 0, (size_t)parts * nq * 4, s));
   }
-  if (!p->ev0) {
-    CU_TRY(cudaEventCreate(&p->ev0));
-    CU_TRY(cudaEventCreate(&p->ev1));
-  }
   CU_TRY(cudaEventRecord(p->ev0, s));
   const bool pair = sym && env_int("WEALY_SYM_PAIR", 0) != 0;   // CTA-pair (cta_group::2) kernel
   const int total_rb = sh.n_row_blocks;
@@ -994,6 +1002,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   }
   CU_TRY(cudaEventRecord(p->ev1, s));
   p->timed = true;
+  p->finished = finish;
 
   if (finish) {
     const int threads = 256;
@@ -1001,6 +1010,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     if (sym) ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->s_off, p->cnt, (int)nq, aps, r1s, sums, p->sorted_idx);
     else ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)nq, aps, r1s, sums);
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(p->evs[2], s));
     if (topk > 0) {
       if (parts * cap <= 32 * kFinPerLane) {
         float* stage_val = reinterpret_cast<float*>(ep.cand_cnt + (size_t)parts * nq);
@@ -1014,6 +1024,23 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       }
       CU_TRY(cudaGetLastError());
     }
+    CU_TRY(cudaEventRecord(p->evs[3], s));
+  }
+  return WEALY_OK;
+}
+
+// device time of the stages of the last run: {prep, K_pos (+ counter reset), fused sweep, ap_reduce, top-k finalize}
+extern "C" int wealy_eval_plan_stage_ms(const wealy_eval_plan* p, float* ms) {
+  if (!p || !ms) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (!p->timed) return fail(WEALY_ERR_BAD_ARG, "the plan has not been run yet");
+  CU_TRY(cudaEventSynchronize(p->finished ? p->evs[3] : p->ev1));
+  CU_TRY(cudaEventElapsedTime(&ms[0], p->evs[0], p->evs[1]));
+  CU_TRY(cudaEventElapsedTime(&ms[1], p->evs[1], p->ev0));
+  CU_TRY(cudaEventElapsedTime(&ms[2], p->ev0, p->ev1));
+  ms[3] = ms[4] = 0.f;
+  if (p->finished) {
+    CU_TRY(cudaEventElapsedTime(&ms[3], p->ev1, p->evs[2]));
+    CU_TRY(cudaEventElapsedTime(&ms[4], p->evs[2], p->evs[3]));
   }
   return WEALY_OK;
 }

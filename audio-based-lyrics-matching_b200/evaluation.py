@@ -120,6 +120,12 @@ class EvalPlan:
         N.check(N.lib.wealy_eval_plan_last_sweep_ms(self._handle, ctypes.byref(ms)))
         return ms.value
 
+    def stage_ms(self):
+        """Device time of the stages of the last run: dict(prep, kpos, sweep, ap_reduce, topk_finalize) in ms."""
+        ms = (ctypes.c_float * 5)()
+        N.check(N.lib.wealy_eval_plan_stage_ms(self._handle, ms))
+        return dict(zip(("prep", "kpos", "sweep", "ap_reduce", "topk_finalize"), (float(v) for v in ms)))
+
     def run(self, queries_z, candidates_z, *, topk=None, eps=1e-6, precision=None, allow_empty=False, chunks=None,
             redux="min", q_chunks=None, c_chunks=None):
         """-> dict(aps, r1s, sums[, topk_idx, topk_sim]); `sums` = device doubles {sum AP, sum R1, #scored}.

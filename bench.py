@@ -2,6 +2,7 @@
 """bench.py -- headline benchmark of the WEALY retrieval-and-scoring hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp16x3|fp16]
+                    [--legs main,c1,c3,c4,c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -22,11 +23,22 @@ mask / rank-count epilogue -> AP reduce -> MAP) of the workload:
 `e2e`    : the same metric through the public API `wealy_b200.evaluation.evaluate()` with HOST
            (pinned) buffers: every step pays the host->device copy of embeddings and ids, the plan
            build, the evaluation and the device->host read of per-query AP / R1.
+`parity` : at every N, rank 0 scores a query sample with the CPU oracle and compares MAP / MR1, R1 and the
+           rank of EVERY relevant item (bit-exact wherever the similarity gap exceeds 1e-5).
+
+The other BASELINE.json configs ride on the same JSON line as extra keys (each a few steps):
+  `c1_shs100k`  configs[0]: 10 547 x 1024 (the exact SHS100K-TEST clique multiset), GPU vs the FULL CPU run
+  `c3_500k`     configs[2]: 500 000 x 1024 all-vs-all on the N GPUs of this run (strong-scaling series)
+  `c4_loss`     configs[3]: NT-Xent / CLEWS forward + backward, batch 4096 x 1024 bf16 (N = 1 only)
+  `c5_topk100`  configs[4]: 50 000 x 2048, top-100 output (N = 1 only)
+
 `--impl reference`: the reference's CPU implementation of the path (it is pure Python / torch, so
            the timed code is the oracle port: torch matmul similarity + per-query argsort
-           evaluator) on all host cores, on a bounded query sample of the same workload.
+           evaluator) on all host cores, on a bounded query sample of the same workload.  This arm
+           never loads the CUDA library.
 """
 import argparse
+import importlib.util
 import json
 import os
 import sys
@@ -56,8 +68,32 @@ def load_peaks():
     return p
 
 
+def load_synth():
+    """The synthetic-input generator, loaded by path: importing it through the `wealy_b200` package would load
+    libwealy_b200.so, which the reference arm must never touch."""
+    path = os.path.join(ROOT, "audio-based-lyrics-matching_b200", "data", "synth.py")
+    spec = importlib.util.spec_from_file_location("_wealy_synth", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_config(n_total, world, tracks_override):
+    """`config` of the JSON line -- identical for the GPU arm and the reference arm of the same command."""
+    if tracks_override:
+        what = f"--tracks {n_total} (BASELINE.json configs[2] when 500000)"
+    else:
+        what = ("BASELINE.json configs[1]" if world == 1 else
+                "BASELINE.json configs[1] grown for weak scaling: N_total = 100000*sqrt(n_gpus)")
+    return {
+        "workload": f"all-vs-all cosine similarity + self/clique mask + rank + AP/MAP/MR1, {n_total} x {DIM} fp32 "
+                    f"embeddings, SHS100K-TEST clique-size bootstrap ({what})",
+        "tracks": n_total, "dim": DIM, "pairs_per_step": float(n_total) * float(n_total), "n_gpus": world,
+    }
+
+
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU every 20 ms while the timed region runs."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -113,19 +149,24 @@ def physical_gpu_index(local_rank):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own CPU path (oracle port), bounded sample
+# CPU arm: the reference's own CPU path, bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_sample(z, c, i, n_queries, threads=None):
-    """Scores the first `n_queries` queries against the full corpus with the reference's CPU
-    arithmetic (torch matmul cosine similarity, lib/tensor_ops.py:167-173, + per-query argsort
-    evaluator).  -> (seconds, aps, r1s)"""
-    import torch
-    from oracle import evaluator as oev
-    if threads:
-        torch.set_num_threads(threads)
-    t0 = time.perf_counter()
-    aps, r1s = oev.evaluate_argsort(c[:n_queries], i[:n_queries], z[:n_queries], c, i, z)
-    return time.perf_counter() - t0, aps, r1s
+def reference_modules():
+    """(tensor_ops, losses) of the UNMODIFIED reference installed under baseline/_ref by baseline/install_ref.py, or
+    (None, None): then the CPU legs time the oracle port (kind "port")."""
+    try:
+        from baseline import install_ref
+        mods = install_ref.load()
+        return mods if mods else (None, None)
+    except Exception:
+        return None, None
+
+
+def cpu_kind(ref_tops):
+    if ref_tops is not None:
+        return "reference", ("the unmodified reference's lib/tensor_ops.py pairwise_distance_matrix (baseline/_ref) + "
+                             "per-query argsort AP/R1 of oracle/evaluator.py (the reference has no evaluator of its own)")
+    return "port", "oracle port: torch CPU matmul cosine similarity + per-query argsort AP/R1 (oracle/evaluator.py)"
 
 
 def run_reference_arm(args):
@@ -133,7 +174,11 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from wealy_b200.data import synth
+    from oracle import evaluator as oev
+    synth = load_synth()
+    ref_tops, _ = reference_modules()
+    dist_fn = ref_tops.pairwise_distance_matrix if ref_tops is not None else None
+    kind, how = cpu_kind(ref_tops)
     world = args.gpus
     n_total = int(args.tracks) if args.tracks else int(round(BASE_N * (world ** 0.5)))
     cores = os.cpu_count() or 1
@@ -144,9 +189,8 @@ def run_reference_arm(args):
     for it in range(args.warmup + args.steps):
         lo = (it * sample) % max(1, n_total - sample)
         t0 = time.perf_counter()
-        from oracle import evaluator as oev
         oev.evaluate_argsort(s["c"][lo:lo + sample], s["i"][lo:lo + sample], s["z"][lo:lo + sample],
-                             s["c"], s["i"], s["z"])
+                             s["c"], s["i"], s["z"], dist_fn=dist_fn)
         dt = time.perf_counter() - t0
         if it >= args.warmup:
             times.append(dt)
@@ -156,15 +200,245 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"all-vs-all cosine similarity + MAP/MR1, {n_total} x {DIM} fp32 "
-                               f"(BASELINE.json configs[1] shape, SHS100K-TEST clique sizes)",
-                   "step_sample": f"{sample} queries x {n_total} candidates per step (bounded sample of the workload)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{sample} queries x {n_total} candidates, torch CPU matmul + per-query argsort"},
+        "config": workload_config(n_total, world, args.tracks),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": f"each step: {sample} queries x {n_total} candidates (bounded sample of the workload); {how}"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# parity of a finished plan against the CPU oracle on a query sample
+# ------------------------------------------------------------------------------------------------
+def parity_sample(plan, aps, r1s, z_c, c_c, i_c, qsel, *, topk=None, topk_idx=None, topk_sim=None, timed=False):
+    """GPU results vs the oracle for the queries `qsel` (CPU index tensor) against the full corpus.
+    -> (dict, seconds of the oracle's evaluate_argsort)."""
+    import torch
+    from oracle import evaluator as oev
+    ref_tops, _ = reference_modules()
+    t0 = time.perf_counter()
+    res_o = oev.evaluate_argsort(c_c[qsel], i_c[qsel], z_c[qsel], c_c, i_c, z_c, topk=topk,
+                                 dist_fn=ref_tops.pairwise_distance_matrix if ref_tops is not None else None)
+    sec = time.perf_counter() - t0
+    aps_o, r1_o = res_o[0], res_o[1]
+    qd = qsel.to(aps.device)
+    aps_g, r1_g = aps[qd].double().cpu(), r1s[qd].double().cpu()
+    out = {"sample_queries": int(qsel.numel()),
+           "abs_dMAP": abs(float(aps_g.mean()) - float(aps_o.mean())),
+           "rel_dMR1": abs(float(r1_g.mean()) - float(r1_o.mean())) / max(1.0, float(r1_o.mean())),
+           "max_abs_dAP": float((aps_g - aps_o).abs().max())}
+    # ranks of EVERY relevant item: inside the band its 1e-5 neighbours allow, exact where the band is one rank
+    off_g, ranks_g, sims_g = (t.cpu() for t in plan.ranks())
+    off_o, sims_o, exact, lo, hi = oev.rank_bands(c_c[qsel], i_c[qsel], z_c[qsel], c_c, i_c, z_c, gap=1e-5)
+    pos = torch.cat([torch.arange(int(off_g[q]), int(off_g[q + 1])) for q in qsel.tolist()])
+    r, sg = ranks_g[pos].long(), sims_g[pos].double()
+    single = lo == hi
+    out.update({"item_ranks_checked": int(r.numel()),
+                "item_ranks_out_of_band": int(((r < lo) | (r > hi)).sum()),
+                "item_ranks_exact_where_gap_gt_1e-5": int(single.sum()),
+                "item_ranks_exact_mismatches": int((r[single] != exact[single]).sum()),
+                "max_abs_dsim_relevant": float((sg - sims_o).abs().max()),
+                "note": "max_abs_dAP > 0 comes from ranks that moved INSIDE their band (candidates within 1e-5 of a "
+                        "relevant item); out_of_band and exact_mismatches must be 0"})
+    if topk:
+        idx_o, sim_o = res_o[2], res_o[3]
+        idx_g, sim_g = topk_idx[qd].cpu(), topk_sim[qd].cpu()
+        ok = torch.ones_like(idx_o, dtype=torch.bool)
+        ok[:, 1:] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+        ok[:, :-1] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+        out.update({"topk": int(topk), "topk_max_abs_dsim": float((sim_g - sim_o).abs().max()),
+                    "topk_idx_compared_where_gap_gt_1e-5": int(ok.sum()),
+                    "topk_idx_mismatches": int((idx_g[ok] != idx_o[ok]).sum())})
+    return out, sec
+
+
+def stage_roofline(plan, n, d, passes, total_pairs, peaks, topk=0, parts=4, cap=0):
+    """Achieved HBM GB/s of the stages around the sweep (CUDA events inside wealy_eval_run), against the measured
+    copy bandwidth.  Algorithmic bytes per stage: DESIGN.md section 4."""
+    ms = plan.stage_ms()
+    d_pad = -(-d // 64) * 64
+    planes = 2 if passes == 3 else 1
+    by = {
+        "prep": n * d * 4 + n * d_pad * 2 * planes + n * 12,
+        "kpos": total_pairs * 2 * d_pad * 2 * planes / 2 + total_pairs * 12,   # every unordered relevant pair's two rows, once
+        "ap_reduce": total_pairs * 4 + n * 8,
+    }
+    if topk:
+        by["topk_finalize"] = n * parts * cap * 8 + n * topk * 12
+    hbm = float(peaks["hbm_gbs"])
+    out = {}
+    for k, b in by.items():
+        t = ms.get(k, 0.0)
+        gbs = b / (t * 1e-3) / 1e9 if t > 0 else None
+        out[k] = {"ms": t, "bytes": float(b), "gbs": gbs, "frac_of_hbm_peak": (gbs / hbm) if gbs else None}
+    out["sweep_ms"] = ms["sweep"]
+    out["note"] = ("kpos gathers operand rows of relevant pairs out of L2 (the planes were just written by prep), so its "
+                   "'GB/s' is L2-side; ap_reduce / topk_finalize move KB..MB and are launch-latency bound")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# extra legs: the other BASELINE.json configs
+# ------------------------------------------------------------------------------------------------
+def timed_steps(fn, warmup, steps, dev, sync_all):
+    import torch
+    for _ in range(warmup):
+        fn()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    sync_all()
+    return e0.elapsed_time(e1) / steps, out
+
+
+def leg_c1(dev, peaks, precision):
+    """configs[0]: SHS100K-TEST-shaped, the case the reference runs on CPU: FULL CPU run beside the GPU."""
+    import torch
+    from wealy_b200 import evaluation as we
+    from wealy_b200.data import synth
+    n = 10547
+    s = synth.make_eval_set(n, DIM, seed=0)
+    c, i, z = s["c"].to(dev), s["i"].to(dev), s["z"].to(dev)
+    plan = we.EvalPlan(c, i, c, i, device=dev)
+    ms, res = timed_steps(lambda: plan.run(z, z, precision=precision), 3, 10, dev, lambda: torch.cuda.synchronize(dev))
+    par, sec = parity_sample(plan, res["aps"], res["r1s"], s["z"], s["c"], s["i"], torch.arange(n))
+    plan.close()
+    return {"workload": f"{n} x {DIM} all-vs-all, exact SHS100K-TEST clique multiset (1692 cliques)",
+            "ms_per_step": ms, "gpairs_per_s": n * n / (ms * 1e-3) / 1e9,
+            "cpu_full_run_s": sec, "cpu_gpairs_per_s": n * n / sec / 1e9, "cpu_cores": torch.get_num_threads(),
+            "parity_all_queries": par}
+
+
+def leg_c3(dev, world, rank, peaks, precision, sync_all):
+    """configs[2]: 500 000 x 1024 all-vs-all over the N GPUs of this run (strong scaling: total work fixed)."""
+    import torch
+    import torch.distributed as dist
+    from wealy_b200 import evaluation as we
+    from wealy_b200.data import synth
+    n = 500_000
+    s = synth.make_eval_set(n, DIM, seed=3, device=dev, md5_ids=False)
+    c, i, z = s["c"], s["i"], s["z"]
+    plan = we.EvalPlan(c, i, c, i, device=dev)
+
+    def step():
+        if world == 1:
+            return plan.run(z, z, precision=precision)
+        plan.sweep_shard(z, rank, world, precision=precision)
+        dist.all_reduce(plan.counts_tensor())
+        return plan.finish()
+
+    ms, res = timed_steps(step, 1, 3, dev, sync_all)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    sweep_ms = plan.last_sweep_ms()
+    out = None
+    if rank == 0:
+        qs = torch.randperm(n, generator=torch.Generator().manual_seed(23))[:64]
+        par, _ = parity_sample(plan, res["aps"], res["r1s"], z.cpu(), c.cpu(), i.cpu(), qs)
+        peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        tf = 2.0 * n * n / world * DIM / (sweep_ms * 1e-3) / 1e12
+        sm = res["sums"].cpu()
+        out = {"workload": f"{n} x {DIM} all-vs-all (Discogs-VI full scale), {world} GPU(s), row blocks of the symmetric "
+                           f"sweep dealt round-robin, corpus replicated, one all-reduce of the rank counters",
+               "scaling": "strong", "n_gpus": world, "ms_per_step": ms, "gpairs_per_s": float(n) * n / (ms * 1e-3) / 1e9,
+               "sweep_ms_rank0": sweep_ms, "sweep_algorithmic_tflops_per_gpu": tf, "roofline_frac": tf / peak,
+               "map": float(sm[0] / sm[2]), "mr1": float(sm[1] / sm[2]), "parity": par}
+    plan.close()
+    del s, c, i, z
+    torch.cuda.empty_cache()
+    return out
+
+
+def leg_c4(dev, peaks):
+    """configs[3]: contrastive loss forward / backward, batch 4096 x 1024 bf16, 4 items per clique."""
+    import torch
+    from wealy_b200 import losses as wl
+    from wealy_b200.data import synth
+    from oracle import losses as ol
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import loss_bench as lb
+    b, d = 4096, 1024
+    s = synth.make_loss_batch(b, d, seed=0, dtype=torch.bfloat16, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    out = {"workload": f"NT-Xent / CLEWS forward + backward, batch {b} x {d} bf16, 4 items per clique, L2 flushed between "
+                       f"iterations; bf16 inputs take one fp16 tensor-core pass (their 8 significant bits are fewer than it keeps)",
+           "algorithmic_flops_fwd_bwd": 8.0 * b * b * d}
+    zc = s["z"].float().cpu()
+    lab_c, idx_c = s["label"].cpu(), s["idx"].cpu()
+    torch.set_num_threads(os.cpu_count() or 1)
+    _, ref_losses = reference_modules()
+    if ref_losses is not None:      # the unmodified reference modules (baseline/_ref) on the host cores
+        out["cpu_kind"] = "reference (lib/losses.py NTXentLoss / CLEWSLoss, fp32, all host cores)"
+        ntx_ref, clews_ref = ref_losses.NTXentLoss(0.1), ref_losses.CLEWSLoss()
+        cpu_fns = {"ntxent": lambda z: ntx_ref(lab_c.clone(), idx_c, z)[0], "clews": lambda z: clews_ref(lab_c.clone(), idx_c, z)[0]}
+    else:
+        out["cpu_kind"] = "port (oracle/losses.py, fp32, all host cores)"
+        cpu_fns = {"ntxent": lambda z: ol.ntxent(lab_c.clone(), idx_c, z, 0.1)[0], "clews": lambda z: ol.clews(lab_c.clone(), idx_c, z)[0]}
+    for name, mod in (("ntxent", wl.NTXentLoss(0.1)), ("clews", wl.CLEWSLoss())):
+        fn = cpu_fns[name]
+        f, lv = lb.gpu_time(mod, s, 20, False, flush)
+        fb, _ = lb.gpu_time(mod, s, 20, True, flush)
+        rec = {"fwd_ms": f, "fwd_bwd_eager_ms": fb, "loss": lv}
+        try:
+            gms, glv, ggrad = lb.graph_time(mod, s, 20, flush)
+            rec.update({"fwd_bwd_graph_ms": gms, "tflops_graph": 8.0 * b * b * d / (gms * 1e-3) / 1e12,
+                        "frac_graph": 8.0 * b * b * d / (gms * 1e-3) / 1e12 / peak})
+        except Exception as e:  # report, do not hide
+            rec.update({"fwd_bwd_graph_ms": None, "graph_error": repr(e)[:200]})
+            ggrad = None
+        rec["tflops_eager"] = 8.0 * b * b * d / (fb * 1e-3) / 1e12
+        rec["frac_eager"] = rec["tflops_eager"] / peak
+        best_f = best_fb = 1e9
+        for _ in range(3):
+            zz = zc.clone().requires_grad_(True)
+            t0 = time.perf_counter(); lo = fn(zz); t1 = time.perf_counter(); lo.backward(); t2 = time.perf_counter()
+            best_f, best_fb = min(best_f, t1 - t0), min(best_fb, t2 - t0)
+        rec.update({"cpu_fwd_ms": best_f * 1e3, "cpu_fwd_bwd_ms": best_fb * 1e3, "cpu_cores": torch.get_num_threads(),
+                    "loss_rel_err_vs_cpu_fp32": abs(lv - float(lo)) / abs(float(lo))})
+        if ggrad is not None:
+            rec["grad_rel_l2_vs_cpu_fp32"] = float((ggrad.float().cpu() - zz.grad).norm() / zz.grad.norm())
+        out[name] = rec
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
+def leg_c5(dev, peaks, precision):
+    """configs[4]: lyric-covers multimodal retrieval (text + audio concatenated, 2048-d), ~50k tracks, top-100."""
+    import torch
+    from wealy_b200 import evaluation as we
+    from wealy_b200.data import synth
+    n, d, k = 50_000, 2048, 100
+    s = synth.make_eval_set(n, d, seed=5, dist="lyric_covers_test", device=dev, md5_ids=False)
+    c, i, z = s["c"], s["i"], s["z"]
+    plan = we.EvalPlan(c, i, c, i, device=dev)
+    ms, res = timed_steps(lambda: plan.run(z, z, topk=k, precision=precision), 3, 5, dev, lambda: torch.cuda.synchronize(dev))
+    st = plan.stage_ms()
+    qs = torch.randperm(n, generator=torch.Generator().manual_seed(17))[:256]
+    par, sec = parity_sample(plan, res["aps"], res["r1s"], z.cpu(), c.cpu(), i.cpu(), qs, topk=k,
+                             topk_idx=res["topk_idx"], topk_sim=res["topk_sim"])
+    peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    tf = 2.0 * n * n * d / (st["sweep"] * 1e-3) / 1e12
+    passes = 3 if precision == "fp16x3" else 1
+    out = {"workload": f"{n} x {d} all-vs-all, top-{k} output + AP/R1, lyric-covers-test clique-size bootstrap",
+           "ms_per_step": ms, "gpairs_per_s": float(n) * n / (ms * 1e-3) / 1e9,
+           "sweep_ms": st["sweep"], "sweep_algorithmic_tflops": tf, "roofline_frac": tf / peak,
+           "ceiling_gpairs_per_s_at_d2048": peak * 1e12 / (2.0 * d) / 1e9,
+           "stages": stage_roofline(plan, n, d, passes, plan.total_pairs, peaks, topk=k, parts=4, cap=320),
+           "cpu_sample_gpairs_per_s": 256 * n / sec / 1e9, "cpu_cores": torch.get_num_threads(),
+           "parity": par}
+    plan.close()
+    del s, c, i, z
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -187,6 +461,8 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    legs = set(args.legs.split(","))
+    torch.set_num_threads(os.cpu_count() or 1)
 
     n_total = int(args.tracks) if args.tracks else int(round(BASE_N * (world ** 0.5)))
     lo, hi = wd.shard_range(n_total, rank, world)
@@ -206,10 +482,10 @@ def run_gpu_arm(args):
 
     def step_resident():
         if world == 1:
-            return plan.run(z, z, precision=args.precision)["sums"]
+            return plan.run(z, z, precision=args.precision)
         plan.sweep_shard(z, rank, world, precision=args.precision)
         dist.all_reduce(plan.counts_tensor())          # int32 rank counters, SUM over ranks
-        return plan.finish()["sums"]
+        return plan.finish()
 
     for _ in range(args.warmup):
         step_resident()
@@ -219,7 +495,7 @@ def run_gpu_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        sums = step_resident()
+        res = step_resident()
     e1.record()
     sync_all()
     clocks = sampler.finish()
@@ -230,8 +506,23 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     value = pairs_total / (ms_step * 1e-3) / 1e9
-    s_host = sums.double().cpu()
+    s_host = res["sums"].double().cpu()
     gpu_map, gpu_mr1 = float(s_host[0] / s_host[2]), float(s_host[1] / s_host[2])
+    passes = 3 if args.precision == "fp16x3" else 1
+    peaks = load_peaks()
+    stages = stage_roofline(plan, n_total, DIM, passes, plan.total_pairs, peaks) if rank == 0 else None
+
+    # ---- parity at every N: rank 0 scores a query sample with the CPU oracle (also the cpu_baseline sample at N = 1)
+    parity = cpu = None
+    if rank == 0 and not args.no_cpu:
+        nqs = args.cpu_queries if world == 1 else min(args.cpu_queries, 256)
+        qs = torch.arange(nqs) if world == 1 else torch.randperm(n_total, generator=torch.Generator().manual_seed(7))[:nqs]
+        parity, sec = parity_sample(plan, res["aps"], res["r1s"], z.cpu(), c.cpu(), i.cpu(), qs)
+        if world == 1:
+            kind, how = cpu_kind(reference_modules()[0])
+            cpu = {"value": nqs * n_total / sec / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                   "sample": f"first {nqs} queries x {n_total} candidates in {sec:.1f} s; {how}"}
+    sync_all()
 
     # ---- e2e: public API with HOST pinned buffers, copies + plan build + result read every step
     z_h, c_h, i_h = z.cpu().pin_memory(), c.cpu().pin_memory(), i.cpu().pin_memory()
@@ -256,6 +547,7 @@ def run_gpu_arm(args):
 
     e2e_steps = max(2, min(args.steps, 5))
     step_e2e()
+    step_e2e()
     sync_all()
     t0 = time.perf_counter()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -270,15 +562,36 @@ def run_gpu_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps
     e2e_value = pairs_total / (e2e_ms * 1e-3) / 1e9
+    e2e_parity = None
+    if rank == 0 and parity is not None:
+        # the end-to-end path's own output (host buffers), same sample
+        a = aps_h[qs].double()
+        e2e_parity = {"abs_dMAP_vs_resident_path": abs(float(a.mean()) - float(res["aps"][qs.to(dev)].double().mean().cpu()))}
+    plan.close()
+    del z_h, s
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs
+    extra = {}
+    if "c3" in legs and not args.tracks:
+        r = leg_c3(dev, world, rank, peaks, args.precision, sync_all)
+        if r is not None:
+            extra["c3_500k"] = r
+    if world == 1:
+        if "c1" in legs:
+            extra["c1_shs100k"] = leg_c1(dev, peaks, args.precision)
+        if "c4" in legs:
+            extra["c4_loss"] = leg_c4(dev, peaks)
+        if "c5" in legs:
+            extra["c5_topk100"] = leg_c5(dev, peaks, args.precision)
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
     # ---- roofline of the dominant kernel (fused sweep), measured live with CUDA events on its stream
-    peaks = load_peaks()
-    passes = 3 if args.precision == "fp16x3" else 1
     # algorithmic work of this rank's launch: its share of the N_total^2 pairs, 2*D flop each
     algo_flops = 2.0 * (float(n_total) * n_total / world) * DIM
     achieved = algo_flops / (last_sweep_ms * 1e-3) / 1e12
@@ -288,62 +601,45 @@ def run_gpu_arm(args):
     tiles = sum(max(0, n_ct - rb // 2) for rb in range(rank, n_rb, world))
     executed = 2.0 * 128 * 256 * DIM * tiles * passes / (last_sweep_ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-    traffic = None
+    variant = "pair" if os.environ.get("WEALY_SYM_PAIR", "") not in ("", "0") else "single"
+    traffic, traffic_note = None, "no ncu capture of this exact configuration is committed"
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tpath):
+    if os.path.isfile(tpath) and world == 1 and not args.tracks:
         try:
-            traffic = json.load(open(tpath)).get(args.precision)
+            rec = json.load(open(tpath)).get(f"{n_total}x{DIM}_{args.precision}_{variant}_1gpu")
+            if rec:
+                traffic, traffic_note = rec["dram_bytes_per_launch"], f"dram__bytes_read.sum + dram__bytes_write.sum, {rec['source']}"
         except Exception:
-            traffic = None
+            pass
     roofline = {
         "kernel": "gemm_kernel<EvalSymEpi> (symmetric tcgen05 similarity sweep over clique-sorted rows + mask + rank-count epilogue)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-        "traffic": traffic,
+        "traffic": traffic, "traffic_note": traffic_note,
         "peak_kind": f"{peaks['_source']} dense bf16/fp16 cuBLAS, sustained (kernel timed inside a long step); "
                      f"burst = {peaks['bf16_tflops']}",
+        "frac_of_burst": achieved / float(peaks["bf16_tflops"]),
         "kernel_ms": last_sweep_ms,
         "executed_tflops": executed,
         "frac_executed": executed / peak,
+        "stages": stages,
         "note": "achieved = algorithmic flops (2*D per scored pair, both directions of the symmetric sweep) / "
                 "kernel time; executed_tflops = tensor-core work issued: half the tiles (symmetry) x 3 passes in "
                 "the fp16x3 parity mode (hi*hi + hi*lo + lo*hi)",
     }
 
-    # ---- CPU baseline (oracle port) on a bounded sample of the same workload, rank 0, N = 1 only
-    cpu = None
-    parity = None
-    if world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        nqs = args.cpu_queries
-        z_c, c_c, i_c = z.cpu(), c.cpu(), i.cpu()
-        sec, aps_o, r1_o = cpu_reference_sample(z_c, c_c, i_c, nqs)
-        cpu = {"value": nqs * n_total / sec / 1e9, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"first {nqs} queries x {n_total} candidates in {sec:.1f} s: torch CPU matmul cosine "
-                         f"similarity + per-query argsort AP/R1 (oracle/evaluator.py)"}
-        res = plan.run(z, z, precision=args.precision)
-        aps_g = res["aps"][:nqs].double().cpu()
-        r1_g = res["r1s"][:nqs].double().cpu()
-        parity = {"sample_queries": nqs,
-                  "abs_dMAP": abs(float(aps_g.mean()) - float(aps_o.mean())),
-                  "abs_dMR1": abs(float(r1_g.mean()) - float(r1_o.mean())),
-                  "max_abs_dAP": float((aps_g - aps_o).abs().max()),
-                  "r1_mismatches": int((r1_g != r1_o).sum())}
-
+    cfg = workload_config(n_total, world, args.tracks)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 tensor-core hi/lo split x3, f32 accumulate" if passes == 3 else "f16 tensor-core, f32 accumulate",
         "data": "synthetic",
-        "config": {
-            "workload": f"all-vs-all cosine similarity + self/clique mask + rank + AP/MAP/MR1, {n_total} x {DIM} "
-                        f"fp32 embeddings (BASELINE.json configs[1] shape at 1 GPU; N_total = 100000*sqrt(n_gpus), "
-                        f"SHS100K-TEST clique-size bootstrap)",
-            "queries_per_gpu": nq, "candidates": n_total, "pairs_per_step": pairs_total,
+        "config": cfg,
+        "run": {
+            "queries_per_gpu": nq,
             "parallelism": ("single GPU" if world == 1 else
                             f"row blocks of the symmetric sweep dealt round-robin to {world} ranks, corpus replicated, "
                             f"one NCCL all-reduce of the int32 rank counters per step"),
-            "precision": args.precision,
+            "precision": args.precision, "sweep_kernel": variant,
             "l2": "operand planes %.0f MB per step >> 126 MB L2 (no flush needed)" % (n_total * DIM * 2 * (2 if passes == 3 else 1) / 1e6),
             "map": gpu_map, "mr1": gpu_mr1,
         },
@@ -354,12 +650,16 @@ def run_gpu_arm(args):
         "gpu_launches": 5 * args.steps,   # prep, pos_pairs, pos_sort, fused sweep, ap_reduce per step
         "roofline": roofline,
     }
+    if e2e_parity:
+        line["e2e"].update(e2e_parity)
     if cpu is not None:
         line["cpu_baseline"] = cpu
     if parity is not None:
         line["parity"] = parity
+    line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -370,10 +670,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tracks", type=int, default=0,
-                    help="override the corpus size (e.g. 500000 = BASELINE configs[2] on 8 GPUs); default: 100000 * sqrt(gpus)")
+                    help="override the corpus size of the headline leg; default: 100000 * sqrt(gpus)")
     ap.add_argument("--precision", default=os.environ.get("WEALY_PRECISION", "fp16x3"), choices=["fp16x3", "fp16"])
     ap.add_argument("--cpu-queries", type=int, default=512, help="queries in the bounded CPU sample")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
+    ap.add_argument("--legs", default="main,c1,c3,c4,c5",
+                    help="which BASELINE configs to run besides the headline (c1, c3, c4, c5); 'main' = headline only")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -144,6 +144,9 @@ int wealy_eval_plan_ranks(const wealy_eval_plan* plan, int64_t* offsets, int32_t
 /* device time (CUDA events on the run's stream) of the fused similarity+ranking sweep of the last
  * wealy_eval_run on this plan; blocks until that sweep has finished.                           */
 int wealy_eval_plan_last_sweep_ms(const wealy_eval_plan* plan, float* ms);
+/* the same for the stages of the last run: ms[5] = {prep (normalise + fp16 split), K_pos (relevant similarities +
+ * counter reset), fused sweep, ap_reduce, top-k finalize}; the last two are 0 after wealy_eval_sweep_shard.  */
+int wealy_eval_plan_stage_ms(const wealy_eval_plan* plan, float* ms);
 void wealy_eval_plan_destroy(wealy_eval_plan* plan);
 
 /* ---- a3: masked reductions ---------------------------------------------------------------

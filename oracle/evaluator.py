@@ -26,7 +26,7 @@ def _as_long(t):
     return torch.as_tensor(t).long().reshape(-1)
 
 
-def _sim_block(qz, cz, mode, redux=None, q_len=None, c_len=None):
+def _sim_block(qz, cz, mode, redux=None, q_len=None, c_len=None, dist_fn=None):
     """similarity (higher = closer) of a block of queries against all candidates.
 
     Chunked tracks (qz [b, s1, D], cz [nc, s2, D]): the chunk-level cosine DISTANCES (b, nc, s1, s2) are reduced with
@@ -48,12 +48,16 @@ def _sim_block(qz, cz, mode, redux=None, q_len=None, c_len=None):
             cm = torch.arange(s2)[None, :] >= torch.as_tensor(c_len).long()[:, None]      # (nc, s2)
             mask = qm[:, None, :, None] | cm[None, :, None, :]
         return 1 - distance_tensor_redux(dist, redux or "min", mask)
+    if dist_fn is not None:   # the unmodified reference's pairwise_distance_matrix (baseline/_ref), when installed
+        return dist_fn(qz, cz, mode=base)
     return distance_matrix(qz, cz, mode=base)
 
 
 def evaluate_argsort(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z,
-                     *, topk=None, mode="cos", block=256, redux=None, q_len=None, c_len=None):
+                     *, topk=None, mode="cos", block=256, redux=None, q_len=None, c_len=None, dist_fn=None):
     """Returns (aps[Nq], r1s[Nq]) and, when topk is given, (topk_idx[Nq,k], topk_sim[Nq,k]).
+    `dist_fn`: similarity backend with the signature of lib/tensor_ops.py:152 (default: the restatement in
+    oracle/similarity.py; bench.py passes the unmodified reference function when baseline/_ref is installed).
 
     A query without any relevant candidate raises ValueError (the reference data pipeline
     guarantees >= 2 versions per clique: lib/embedding_dataset/filters.py:87-109)."""
@@ -69,7 +73,7 @@ def evaluate_argsort(queries_c, queries_i, queries_z, candidates_c, candidates_i
         tk_sim = torch.full((nq, k), float("-inf"), dtype=qz.dtype)
     for b0 in range(0, nq, block):
         sim = _sim_block(qz[b0:b0 + block], cz, mode, redux,
-                         None if q_len is None else torch.as_tensor(q_len)[b0:b0 + block], c_len)   # (b, nc)
+                         None if q_len is None else torch.as_tensor(q_len)[b0:b0 + block], c_len, dist_fn)   # (b, nc)
         dist = 1 - sim                                          # "cos"/"dot" distance
         for r in range(sim.shape[0]):
             q = b0 + r
