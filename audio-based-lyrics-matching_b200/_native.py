@@ -54,6 +54,7 @@ SIGNATURES = {
     "wealy_eval_finish": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "wealy_eval_plan_ranks": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "wealy_eval_plan_last_sweep_ms": (c_int, [c_vp, ctypes.POINTER(c_f32)]),
+    "wealy_eval_plan_last_topk_path": (c_int, [c_vp, ctypes.POINTER(c_int)]),
     "wealy_eval_plan_stage_ms": (c_int, [c_vp, ctypes.POINTER(c_f32)]),
     "wealy_eval_plan_destroy": (None, [c_vp]),
     "wealy_masked_reduce": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_int, c_f32, c_f32, c_vp, c_vp]),

@@ -17,6 +17,7 @@
 #include "masked_kernels.cuh"
 #include "pool_kernels.cuh"
 #include "prep.cuh"
+#include "topk_sym_kernels.cuh"
 
 using namespace wealy;
 
@@ -571,6 +572,9 @@ struct wealy_eval_plan {
   size_t planes_cap = 0;
   void* topk_buf = nullptr;
   size_t topk_cap = 0;
+  void* tks_buf = nullptr;   // top-k in the symmetric sweep: sample operand, pre-pass lists, bounds, candidate lists
+  size_t tks_cap = 0;
+  int last_topk_path = 0;    // 0 none, 1 symmetric sweep, 2 rectangle sweep, 3 symmetric failed -> rectangle
   // clique-sorted view of an all-vs-all plan (same ids on both sides): the symmetric sweep runs in this row order
   // (perm = sorted_idx: sorted position -> caller's row; clique ids = sorted_c)
   int *s_i = nullptr, *s_seg_lo = nullptr, *s_seg_len = nullptr, *s_npos = nullptr;
@@ -591,7 +595,7 @@ struct wealy_eval_plan {
 extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
   if (!p) return;
   void* ptrs[] = {p->q_c, p->q_i, p->sorted_c, p->sorted_idx, p->seg_lo, p->seg_len, p->npos, p->off,
-                  p->raw, p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf,
+                  p->raw, p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf, p->tks_buf,
                   p->s_i, p->s_seg_lo, p->s_seg_len, p->s_npos, p->s_off, p->s_lvl, p->s_cinfo, p->s_dirty};
   // frees are ordered behind the last work that touched the buffers: the stream of the last run
   cudaStream_t fs = p->timed ? p->last_stream : p->stream;
@@ -796,7 +800,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
                          int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,
                          float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, int shard_rank,
                          int shard_world, bool finish, void* stream, int chunks = 1, int redux = WEALY_REDUX_MIN,
-                         const int* q_len = nullptr, const int* c_len = nullptr) {
+                         const int* q_len = nullptr, const int* c_len = nullptr, bool allow_sym_topk = true) {
   cudaStream_t s = (cudaStream_t)stream;
   if (!p) return fail(WEALY_ERR_BAD_ARG, "null plan");
   if (!queries_z || !candidates_z) return fail(WEALY_ERR_BAD_ARG, "null pointer");
@@ -828,8 +832,13 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   // Symmetric all-vs-all: queries ARE the candidates (same ids, same embeddings), no top-k.  Only the tiles
   // that reach above the diagonal are contracted (half the tensor work); every element scores both its row
   // query and its column query.  Runs in the plan's clique-sorted row order (eval_sym_epilogue.cuh).
-  const bool sym = same && p->same_ids && topk == 0 && chunks == 1 && p->total_pairs < (1ll << 31) - 8 &&
-                   (shard_world > 1 || env_int("WEALY_SYM", 1) != 0);
+  const bool can_sym = same && p->same_ids && chunks == 1 && p->total_pairs < (1ll << 31) - 8;
+  // ... with top-k (topk_sym_kernels.cuh): a sampled pre-pass bounds every query's k-th best similarity from below, the
+  // sweep appends what lies above the bound to per-query lists in both directions.  Worth it (and statistically sound)
+  // for large sets and moderate k; everything else keeps the rectangle sweep with its streaming top-k.
+  const bool sym_topk = can_sym && topk > 0 && topk <= 128 && nq >= env_int("WEALY_SYM_TOPK_MIN_ROWS", 16384) && finish &&
+                        shard_world == 1 && allow_sym_topk && env_int("WEALY_SYM_TOPK", 1) != 0;
+  const bool sym = can_sym && (topk == 0 ? (shard_world > 1 || env_int("WEALY_SYM", 1) != 0) : sym_topk);
   if (shard_world > 1 && !sym)
     return fail(WEALY_ERR_BAD_ARG, "a sharded sweep needs queries == candidates (ids and embeddings) and no top-k");
 
@@ -893,6 +902,106 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     }
     CU_TRY(cudaGetLastError());
   }
+  // ---- top-k in the symmetric sweep: sampled pre-pass -> per-query lower bound of the k-th best similarity
+  float* tk_val = nullptr;
+  int *tk_idx = nullptr, *tk_cnt = nullptr, *tk_fail = nullptr;
+  float* tk_beta = nullptr;
+  int tk_cap2 = 0;
+  if (sym_topk) {
+    const int n = (int)nq, rows = (int)rows_q;
+    int S = (int)(nq / 8);
+    if (S < 8192) S = 8192;
+    S = (int)ceil_div(S, kTileN) * kTileN;
+    if (S > n) S = n;
+    const double frac = (double)S / (double)n;
+    int r = (int)ceil(3.0 * topk * frac);
+    if (r < 32) r = 32;
+    if (r > 64) {  // the bound kernel merges <= 4 lists of <= 256 entries: shrink the sample instead
+      S = (int)((64.0 * n) / (3.0 * topk)) / kTileN * kTileN;
+      r = 64;
+    }
+    const double fr = (double)S / (double)n;
+    const double mean = r / fr, sd = sqrt(r * (1.0 - fr)) / fr;
+    tk_cap2 = (int)align_up((size_t)(mean + 8.0 * sd + 32.0), 32);
+    if (tk_cap2 > 1024) tk_cap2 = 1024;
+    const int cap_r = topk_capacity(r);  // 256 for r <= 64
+    const int parts_r = 4;
+    // carve the scratch
+    size_t need_tk = 0;
+    auto reserve = [&](size_t bytes) { const size_t o = need_tk; need_tk += align_up(bytes, 1024); return o; };
+    const size_t o_samp = reserve((size_t)S * pq.d_pad * 2);
+    const size_t o_si = reserve((size_t)S * 4);
+    const size_t o_qi = reserve((size_t)rows * 4);
+    const size_t o_lim = reserve((size_t)rows * 4);
+    const size_t o_zi = reserve((size_t)(rows > S ? rows : S) * 4);
+    const size_t o_zl = reserve(((size_t)rows + 1) * 8);
+    const size_t o_beta = reserve((size_t)rows * 4);
+    const size_t o_cv = reserve((size_t)parts_r * rows * cap_r * 4);
+    const size_t o_ci = reserve((size_t)parts_r * rows * cap_r * 4);
+    const size_t o_cc = reserve((size_t)parts_r * rows * 4);
+    const size_t o_tv = reserve((size_t)rows * tk_cap2 * 4);
+    const size_t o_ti = reserve((size_t)rows * tk_cap2 * 4);
+    const size_t o_tc = reserve((size_t)rows * 4);
+    const size_t o_fail = reserve(256);
+    if (need_tk > p->tks_cap) {
+      dev_free(p->tks_buf, s);
+      p->tks_buf = nullptr;
+      p->tks_cap = 0;
+      CU_TRY(dev_alloc(&p->tks_buf, need_tk + 1024, s));
+      p->tks_cap = need_tk;
+    }
+    uint8_t* tb = reinterpret_cast<uint8_t*>(align_up((size_t)p->tks_buf, 1024));
+    __half* samp = reinterpret_cast<__half*>(tb + o_samp);
+    int* samp_i = reinterpret_cast<int*>(tb + o_si);
+    int* qi_plane = reinterpret_cast<int*>(tb + o_qi);
+    float* lim_inf = reinterpret_cast<float*>(tb + o_lim);
+    int* zeros_i = reinterpret_cast<int*>(tb + o_zi);
+    long long* zeros_ll = reinterpret_cast<long long*>(tb + o_zl);
+    tk_beta = reinterpret_cast<float*>(tb + o_beta);
+    float* cv = reinterpret_cast<float*>(tb + o_cv);
+    int* ci = reinterpret_cast<int*>(tb + o_ci);
+    int* cc = reinterpret_cast<int*>(tb + o_cc);
+    tk_val = reinterpret_cast<float*>(tb + o_tv);
+    tk_idx = reinterpret_cast<int*>(tb + o_ti);
+    tk_cnt = reinterpret_cast<int*>(tb + o_tc);
+    tk_fail = reinterpret_cast<int*>(tb + o_fail);
+    const int T = 256;
+    CU_TRY(cudaMemsetAsync(zeros_i, 0, (size_t)(rows > S ? rows : S) * 4, s));
+    CU_TRY(cudaMemsetAsync(cc, 0, (size_t)parts_r * rows * 4, s));
+    CU_TRY(cudaMemsetAsync(tk_fail, 0, 4, s));
+    sample_rows_kernel<<<(unsigned)ceil_div((int64_t)S * 32, T), T, 0, s>>>(pq.hi, (int)pq.d_pad, n, S, p->s_i, samp, samp_i);
+    plane_ids_kernel<<<(unsigned)ceil_div(rows + 1, T), T, 0, s>>>(p->s_i, n, rows, qi_plane, lim_inf, zeros_i, zeros_ll);
+    CU_TRY(cudaGetLastError());
+    Planes pa = pq, pb;
+    pa.lo = nullptr;
+    pb.hi = samp; pb.lo = nullptr; pb.rows = S; pb.d_pad = pq.d_pad;
+    pb.norm = pb.scale = pb.sq = nullptr;
+    GemmShape shp;
+    fill_shape(shp, rows, S, pq.d_pad, 64, 2, 0);
+    EvalParams pe;
+    memset(&pe, 0, sizeof(pe));
+    pe.lim = lim_inf;
+    pe.q_c = zeros_i;
+    pe.q_i = qi_plane;
+    pe.c_c = zeros_i;
+    pe.c_i = samp_i;
+    pe.thr = p->thr;
+    pe.off = zeros_ll;
+    pe.cnt = zeros_i;
+    pe.hist = p->hist;
+    pe.topk = r;
+    pe.cap = cap_r;
+    pe.nq_total = rows;
+    pe.cand_val = cv;
+    pe.cand_idx = ci;
+    pe.cand_cnt = cc;
+    if (shp.n_col_chunks * 2 > parts_r) return fail(WEALY_ERR_UNSUPPORTED, "top-k pre-pass: %d parts", shp.n_col_chunks * 2);
+    W_TRY(launch_gemm<EvalEpi>(1, pa, pb, shp, pe, s));
+    topk_beta_kernel<<<(unsigned)ceil_div(p->s_padded * 32, 128), 128, 0, s>>>(cv, cc, shp.n_col_chunks * 2, rows, cap_r, r, n, tk_beta,
+                                                                              p->s_lvl, (int)p->s_padded, tk_cnt);
+    CU_TRY(cudaGetLastError());
+  }
+  p->last_topk_path = topk > 0 ? (sym_topk ? 1 : 2) : 0;
   p->last_sym = sym;
   p->last_stream = s;
   CU_TRY(cudaMemsetAsync(p->hist, 0, (size_t)(p->total_pairs > 0 ? p->total_pairs : 1) * 4, s));
@@ -901,9 +1010,10 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   const int halves = 2;  // two epilogue warps per TMEM lane quadrant (16 warps and 4 warps were measured no better)
   GemmShape sh;
   // top-k keeps <= 4 candidate lists per query (column chunks x epilogue warps per row)
-  fill_shape(sh, rq, rc, pq.d_pad, 64, topk > 0 ? (4 / halves) : (1 << 20), topk > 0 ? 0 : env_int("WEALY_TILES_PER_UNIT", 8));
+  const bool rect_topk = topk > 0 && !sym_topk;
+  fill_shape(sh, rq, rc, pq.d_pad, 64, rect_topk ? (4 / halves) : (1 << 20), rect_topk ? 0 : env_int("WEALY_TILES_PER_UNIT", 8));
   const int parts = sh.n_col_chunks * halves;
-  const int cap = topk > 0 ? topk_capacity(topk) : 0;
+  const int cap = rect_topk ? topk_capacity(topk) : 0;
 
   EvalParams ep;
   memset(&ep, 0, sizeof(ep));
@@ -924,7 +1034,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   ep.red_scale = red_scale;
   ep.q_len = q_len;
   ep.c_len = c_len;
-  if (topk > 0) {
+  if (rect_topk) {
     const size_t slots = (size_t)parts * nq * cap;
     const size_t tneed = slots * 16 + (size_t)parts * nq * 4 + 1024;  // candidate lists + finalize staging
     if (tneed > p->topk_cap) {
@@ -940,7 +1050,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     CU_TRY(cudaMemsetAsync(ep.cand_cnt, 0, (size_t)parts * nq * 4, s));
   }
   CU_TRY(cudaEventRecord(p->ev0, s));
-  const bool pair = sym && env_int("WEALY_SYM_PAIR", 0) != 0;   // CTA-pair (cta_group::2) kernel
+  const bool pair = sym && !sym_topk && env_int("WEALY_SYM_PAIR", 0) != 0;   // CTA-pair (cta_group::2) kernel
   const int total_rb = sh.n_row_blocks;
   if (pair) {
     // the pair kernel works on super row blocks (two adjacent row blocks per CTA pair)
@@ -968,8 +1078,20 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     sp.n_col_tiles = sh.n_col_tiles;
     sp.n_row_blocks = total_rb;
     sp.total_pairs = (unsigned)p->total_pairs;
+    sp.beta = tk_beta;
+    sp.tk_val = tk_val;
+    sp.tk_idx = tk_idx;
+    sp.tk_cnt = tk_cnt;
+    sp.tk_cap = tk_cap2;
     const int lv = env_int("WEALY_SYM_LEVELS", 3);  // 3 measured best at C2 (2: 26.8 ms, 3: 25.5 ms, 4: 25.9 ms per step)
-    if (pair) {
+    if (sym_topk) {
+      if (passes == 3) {
+        sh.k_blocks = (int)(pq.d_pad / 32);
+        W_TRY((launch_gemm_t<EvalSymEpi<3, 256, 4096, true>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));
+      } else {
+        W_TRY((launch_gemm_t<EvalSymEpi<3, 256, 4096, true>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
+      }
+    } else if (pair) {
       if (env_int("WEALY_PAIR_INTERLEAVE", 1) != 0) sh.sym |= 2;
       // three epilogue warps per TMEM lane quadrant (the pair's epilogue is the co-limiter; 16 warps were measured worse)
       const bool w12 = env_int("WEALY_PAIR_EPI_WARPS", 12) == 12;
@@ -1011,6 +1133,23 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     else ap_reduce_kernel<<<blocks, threads, 0, s>>>(p->hist, p->off, p->cnt, (int)nq, aps, r1s, sums);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(p->evs[2], s));
+    if (sym_topk) {
+      topk_sym_finalize_kernel<<<(unsigned)ceil_div(rows_q * 32, 128), 128, 0, s>>>(tk_val, tk_idx, tk_cnt, tk_cap2, (int)rows_q, (int)nq,
+                                                                                   topk, p->sorted_idx, (long long*)topk_idx, topk_sim,
+                                                                                   tk_fail);
+      CU_TRY(cudaGetLastError());
+      CU_TRY(cudaEventRecord(p->evs[3], s));
+      // the one host round trip of this path: 4 bytes that say whether every list held its k best (see topk_sym_kernels.cuh)
+      int failed = 0;
+      CU_TRY(cudaMemcpyAsync(&failed, tk_fail, 4, cudaMemcpyDeviceToHost, s));
+      CU_TRY(cudaStreamSynchronize(s));
+      if (failed != 0) {
+        W_TRY(eval_run_impl(p, queries_z, ld_q, candidates_z, ld_c, d, dtype, eps, passes, topk, aps, r1s, sums, topk_idx, topk_sim,
+                            shard_rank, shard_world, finish, stream, chunks, redux, q_len, c_len, false));
+        p->last_topk_path = 3;
+      }
+      return WEALY_OK;
+    }
     if (topk > 0) {
       if (parts * cap <= 32 * kFinPerLane) {
         float* stage_val = reinterpret_cast<float*>(ep.cand_cnt + (size_t)parts * nq);
@@ -1026,6 +1165,14 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     }
     CU_TRY(cudaEventRecord(p->evs[3], s));
   }
+  return WEALY_OK;
+}
+
+// which kernel produced the top-k lists of the last run: 0 none, 1 symmetric sweep with sampled bounds, 2 rectangle sweep
+// (streaming top-k), 3 symmetric sweep whose lists failed the check and were recomputed by the rectangle sweep
+extern "C" int wealy_eval_plan_last_topk_path(const wealy_eval_plan* p, int* path) {
+  if (!p || !path) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  *path = p->last_topk_path;
   return WEALY_OK;
 }
 

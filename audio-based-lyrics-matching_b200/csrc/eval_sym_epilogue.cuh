@@ -39,6 +39,16 @@ struct EvalSymParams {
   int n_col_tiles;
   int n_row_blocks;            // row blocks of the whole problem (the CTA-pair kernel may be handed one past the end)
   unsigned int total_pairs;
+  // top-k in the symmetric sweep (EvalSymEpi<..., kTopk = true>): every query p (plane row) has a static lower bound
+  // beta[p] of its k-th best similarity (sampled pre-pass; for the tile's columns it rides in lvl[].w); every
+  // candidate above the bound is appended -- row direction and column direction alike -- to the query's list
+  // tk_val / tk_idx [p][tk_cap] through the atomic cursor tk_cnt[p] (entries beyond tk_cap are dropped and the
+  // finalize kernel reports the query as overflowed).  Candidates are plane rows too.
+  const float* beta;
+  float* tk_val;
+  int* tk_idx;
+  int* tk_cnt;
+  int tk_cap;
 };
 
 __device__ __forceinline__ unsigned bit_transpose32(unsigned x, int lane) {
@@ -51,9 +61,10 @@ __device__ __forceinline__ unsigned bit_transpose32(unsigned x, int lane) {
   return x;
 }
 
-template <int kLv, int kQueueCapT = 256, int kCachePairsT = 4096>
+template <int kLv, int kQueueCapT = 256, int kCachePairsT = 4096, bool kTopk = false>
 struct EvalSymEpi {
   static_assert(kLv >= 2 && kLv <= 4, "2..4 register levels");
+  static_assert(!kTopk || kLv <= 3, "the top-k bound of the columns rides in the 4th threshold slot");
   using Params = EvalSymParams;
   static constexpr int kQueueCap = kQueueCapT;
   static constexpr int kCachePairs = kCachePairsT;
@@ -91,6 +102,7 @@ struct EvalSymEpi {
     int n_cached;
     unsigned base;           // CSR offset of the unit's first row
     int row_glob, row_ok, dirty;
+    float beta;              // kTopk: lower bound of this row's k-th best similarity
   };
 
   __device__ static __forceinline__ float* q_val(const EpiCtx& c) { return reinterpret_cast<float*>(c.warp_scratch); }
@@ -113,6 +125,7 @@ struct EvalSymEpi {
     for (int j = 0; j < kLv - 1; ++j) st.rc[j] = 0u;
     st.qc = st.qi = 0;
     st.off = 0u;
+    st.beta = inf;
     int cnt = 0;
     // `row` (like every row / column index in here) is a PLANE row: rows are stored in spread order (gemm_core.cuh),
     // lvl / cinfo are indexed the same way; ids and validity go through the sorted index
@@ -127,6 +140,7 @@ struct EvalSymEpi {
       cnt = (int)ci.y;
       st.qc = __ldg(p.s_c + srow);
       st.qi = __ldg(p.s_i + srow);
+      if constexpr (kTopk) st.beta = __ldg(p.beta + row);
     }
     st.qn = 0;
     st.row_glob = row;
@@ -156,10 +170,13 @@ struct EvalSymEpi {
 
   // One queued element: s lies above the kLv lowest thresholds of its query; idx addresses the kLv-th threshold
   // slot + 1 (shared-memory cache offset, or global CSR index with kGlobal), len thresholds remain to search.
+  // (kTopk: a queue entry with a NEGATIVE length is a top-k candidate: idx = the query's plane row, -1 - len = the
+  //  candidate's plane row; it is appended to the query's list instead of being binned)
   struct Ent {
     float s;
     unsigned idx;
     int len;
+    int cand;
     bool on;
     const float* tp;
   };
@@ -167,12 +184,26 @@ struct EvalSymEpi {
     en.on = r < end;
     en.s = en.on ? q_val(ctx)[r] : 0.f;
     en.idx = en.on ? q_idx(ctx)[r] : 0u;
-    en.len = en.on ? max(q_len(ctx)[r], 0) : 0;
+    const int raw = en.on ? q_len(ctx)[r] : 0;
+    en.len = max(raw, 0);
+    en.cand = kTopk ? -1 - raw : -1;   // >= 0 for a top-k entry
     en.tp = (en.idx & kGlobal) ? (p.thr + (en.idx & ~kGlobal)) : (thr_s(ctx) + en.idx);
   }
   __device__ static __forceinline__ void count(const Params& p, const RowState& st, const EpiCtx& ctx, const Ent& en,
                                                int lb, int lane) {
     (void)ctx; (void)lane;
+    if constexpr (kTopk) {
+      if (en.cand >= 0) {
+        if (en.on) {
+          const int pos = atomicAdd(p.tk_cnt + en.idx, 1);
+          if (pos < p.tk_cap) {
+            p.tk_val[(size_t)en.idx * p.tk_cap + pos] = en.s;
+            p.tk_idx[(size_t)en.idx * p.tk_cap + pos] = en.cand;
+          }
+        }
+        return;
+      }
+    }
     const bool glob = (en.idx & kGlobal) != 0u;
     // bucket = kLv - 1 + lower bound; cached row entries carry an offset relative to the unit's first row
     const unsigned slot = (en.idx & ~kGlobal) - 1u + (unsigned)lb + (glob ? 0u : st.base);
@@ -211,7 +242,8 @@ struct EvalSymEpi {
   // per lane (1.6 % of the pairs are deep), so the registers of half a chunk are parked in shared memory
   // ([column][lane]: conflict free, every lane reads back only its own) and each lane walks its set bits.
   __device__ static __forceinline__ void push(const RowState& st, const EpiCtx& ctx, const uint32_t (&acc)[32], unsigned mr,
-                                              unsigned mcq, const uint2* cinf, int pos) {
+                                              unsigned mcq, const uint2* cinf, int pos, unsigned tkr = 0u, unsigned tkc = 0u,
+                                              int col0 = 0) {
     float* qv = q_val(ctx);
     unsigned* qx = q_idx(ctx);
     int* ql = q_len(ctx);
@@ -219,7 +251,7 @@ struct EvalSymEpi {
 #pragma unroll
     for (int h = 0; h < 32 / kStageCols; ++h) {
       const unsigned sel = ((1u << kStageCols) - 1u) << (h * kStageCols);
-      if (!__any_sync(0xffffffffu, ((mr | mcq) & sel) != 0u)) continue;
+      if (!__any_sync(0xffffffffu, ((mr | mcq | tkr | tkc) & sel) != 0u)) continue;
 #pragma unroll
       for (int e = 0; e < kStageCols; ++e) stg[e * 32] = __uint_as_float(acc[h * kStageCols + e]);
       unsigned m = mr & sel;
@@ -240,6 +272,26 @@ struct EvalSymEpi {
         qx[pos] = kGlobal | (c.x + kLv);
         ql[pos] = (int)c.y - kLv;
         ++pos;
+      }
+      if constexpr (kTopk) {
+        m = tkr & sel;   // this row's candidates: the columns
+        while (m) {
+          const int e = __ffs(m) - 1;
+          m &= m - 1;
+          qv[pos] = stg[(e - h * kStageCols) * 32];
+          qx[pos] = (unsigned)st.row_glob;
+          ql[pos] = -1 - (col0 + e);
+          ++pos;
+        }
+        m = tkc & sel;   // the columns' candidate: this row
+        while (m) {
+          const int e = __ffs(m) - 1;
+          m &= m - 1;
+          qv[pos] = stg[(e - h * kStageCols) * 32];
+          qx[pos] = (unsigned)(col0 + e);
+          ql[pos] = -1 - st.row_glob;
+          ++pos;
+        }
       }
       __syncwarp();  // (reconverge before the next half overwrites the staging area)
     }
@@ -263,6 +315,7 @@ struct EvalSymEpi {
     const uint2* cinf = reinterpret_cast<const uint2*>(ctx.col_slot + kLvlBytes) + (col0 & (kTileN - 1));
 
     unsigned m[kLv], mc[kLv];
+    unsigned tkr = 0u, tkc = 0u;  // kTopk: elements above the row's / the column's top-k bound
 #pragma unroll
     for (int j = 0; j < kLv; ++j) m[j] = mc[j] = 0u;
 #pragma unroll
@@ -274,6 +327,10 @@ struct EvalSymEpi {
         m[j] |= (s > st.t[j]) ? (1u << e) : 0u;
         mc[j] |= (s > lvl_of(c, j)) ? (1u << e) : 0u;
       }
+      if constexpr (kTopk) {
+        tkr |= (s > st.beta) ? (1u << e) : 0u;
+        tkc |= (s > c.w) ? (1u << e) : 0u;
+      }
     }
     if (st.dirty) {
       // tile with self / same-clique / colliding pairs, or ragged edges: candidates by id, above the diagonal only
@@ -281,24 +338,33 @@ struct EvalSymEpi {
       const bool ok = scol < sh.n_cols;
       const int cc = ok ? __ldg(p.s_c + scol) : 0;
       const int ci = ok ? __ldg(p.s_i + scol) : 0;
-      unsigned valid = 0u;
+      unsigned valid = 0u, validk = 0u;  // negatives for the rank counts / top-k candidates (a relevant item is one)
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
         const int cce = __shfl_sync(kFull, cc, e);
         const int cie = __shfl_sync(kFull, ci, e);
         const int oke = __shfl_sync(kFull, (int)ok, e);
         valid |= (oke && cce != st.qc && cie != st.qi) ? (1u << e) : 0u;
+        if constexpr (kTopk) validk |= (oke && cie != st.qi) ? (1u << e) : 0u;
       }
       const int d = st.row_glob - col0;  // columns 0..d of this chunk are on or below the diagonal
-      valid &= d < 0 ? 0xffffffffu : (d >= 31 ? 0u : (0xffffffffu << (d + 1)));
-      if (!st.row_ok) valid = 0u;
+      const unsigned above = d < 0 ? 0xffffffffu : (d >= 31 ? 0u : (0xffffffffu << (d + 1)));
+      valid &= above;
+      validk &= above;
+      if (!st.row_ok) valid = validk = 0u;
 #pragma unroll
       for (int j = 0; j < kLv; ++j) {
         m[j] &= valid;
         mc[j] &= valid;
       }
+      tkr &= validk;
+      tkc &= validk;
     }
-    if (!__any_sync(kFull, (m[0] | mc[0]) != 0u)) return;
+    if constexpr (kTopk) {
+      if (!__any_sync(kFull, (m[0] | mc[0] | tkr | tkc) != 0u)) return;
+    } else {
+      if (!__any_sync(kFull, (m[0] | mc[0]) != 0u)) return;
+    }
 
     // ---- buckets 0 .. kLv-2, counted directly
 #pragma unroll
@@ -312,26 +378,26 @@ struct EvalSymEpi {
       }
     }
 
-    // ---- deeper elements: queue
+    // ---- deeper elements (and top-k candidates): queue
     const unsigned dr = m[kLv - 1], dc = mc[kLv - 1];
-    if (!__any_sync(kFull, (dr | dc) != 0u)) return;
-    const int mine = __popc(dr) + __popc(dc);
+    if (!__any_sync(kFull, (dr | dc | tkr | tkc) != 0u)) return;
+    const int mine = __popc(dr) + __popc(dc) + __popc(tkr) + __popc(tkc);
     const int incl = warp_incl_scan(mine, lane);
     const int total = __shfl_sync(kFull, incl, 31);
     if (st.qn + total > kQueueCap) drain(p, st, ctx);
     if (total <= kQueueCap) {
-      push(st, ctx, acc, dr, dc, cinf, st.qn + incl - mine);
+      push(st, ctx, acc, dr, dc, cinf, st.qn + incl - mine, tkr, tkc, col0);
       st.qn += total;
     } else {
       // a chunk denser than the whole queue: kQueueCap / 64 columns (<= kQueueCap entries) at a time
-      constexpr int kBatchCols = kQueueCap / 64;
-      static_assert(kBatchCols >= 1 && 32 % kBatchCols == 0, "queue capacity: 64 .. 2048, a power of two");
+      constexpr int kBatchCols = kQueueCap / (kTopk ? 128 : 64);
+      static_assert(kBatchCols >= 1 && 32 % kBatchCols == 0, "queue capacity: 64 (128 with top-k) .. 2048, a power of two");
 #pragma unroll 1
       for (int g = 0; g < 32 / kBatchCols; ++g) {
         const unsigned sel = ((1u << kBatchCols) - 1u) << (kBatchCols * g);
-        const int mine_g = __popc(dr & sel) + __popc(dc & sel);
+        const int mine_g = __popc(dr & sel) + __popc(dc & sel) + __popc(tkr & sel) + __popc(tkc & sel);
         const int incl_g = warp_incl_scan(mine_g, lane);
-        push(st, ctx, acc, dr & sel, dc & sel, cinf, incl_g - mine_g);
+        push(st, ctx, acc, dr & sel, dc & sel, cinf, incl_g - mine_g, tkr & sel, tkc & sel, col0);
         st.qn = __shfl_sync(kFull, incl_g, 31);
         drain(p, st, ctx);
       }

@@ -120,6 +120,12 @@ class EvalPlan:
         N.check(N.lib.wealy_eval_plan_last_sweep_ms(self._handle, ctypes.byref(ms)))
         return ms.value
 
+    def last_topk_path(self):
+        """0 none, 1 symmetric sweep (sampled bounds), 2 rectangle sweep (streaming top-k), 3 symmetric failed -> rectangle."""
+        v = ctypes.c_int()
+        N.check(N.lib.wealy_eval_plan_last_topk_path(self._handle, ctypes.byref(v)))
+        return v.value
+
     def stage_ms(self):
         """Device time of the stages of the last run: dict(prep, kpos, sweep, ap_reduce, topk_finalize) in ms."""
         ms = (ctypes.c_float * 5)()

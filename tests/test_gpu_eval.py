@@ -73,11 +73,16 @@ def test_no_relevant_is_flagged():
     assert torch.isnan(aps[2]) and torch.isnan(r1s[2]) and float(aps[0]) == 1.0
 
 
-def _check_all_item_ranks(plan, c, i, z, cc=None, ci=None, cz=None, queries=None, gap=1e-5, sim_tol=4e-6):
+def _check_all_item_ranks(plan, c, i, z, cc=None, ci=None, cz=None, queries=None, gap=1e-5, sim_tol=4e-6, truth64=False):
     """The parity contract on the quantities AP is made of: the rank of EVERY relevant item (not only the best one)
     must lie in the band the candidates within `gap` of it allow, and be exact where that band is a single rank.
-    `plan` has just been run; `queries` (index tensor) restricts the oracle to a sample of the queries."""
+    `plan` has just been run; `queries` (index tensor) restricts the oracle to a sample of the queries.
+    truth64: bands and similarities from the float64 evaluation of the same formula (the arbiter between two
+    fp32-accumulating implementations; then |GPU - truth| <= gap / 2 is exactly the condition under which the band
+    property is guaranteed)."""
     cc, ci, cz = (c if cc is None else cc), (i if ci is None else ci), (z if cz is None else cz)
+    if truth64:
+        z, cz = z.double(), cz.double()
     off_g, ranks_g, sims_g = (t.cpu() for t in plan.ranks())
     qsel = torch.arange(len(c)) if queries is None else torch.as_tensor(queries).long().cpu()
     off_o, sims_o, exact, lo, hi = oev.rank_bands(c[qsel], i[qsel], z[qsel], cc, ci, cz, gap=gap)
@@ -504,7 +509,7 @@ def test_all_item_ranks_general_and_topk_paths():
     plan.close()
 
 
-def _topk_sample_parity(s, k, n_sample, seed):
+def _topk_sample_parity(s, k, n_sample, seed, sim_tol=4e-6, expect_path=None):
     """Top-k of the whole set on the GPU vs the oracle on a query sample: similarities within 4e-6, indices exact
     wherever neighbouring similarities differ by more than 1e-5, self never returned."""
     we = _we()
@@ -513,11 +518,13 @@ def _topk_sample_parity(s, k, n_sample, seed):
     plan = we.EvalPlan(c, i, c, i)
     res = plan.run(z, z, topk=k)
     torch.cuda.synchronize()
+    if expect_path is not None:
+        assert plan.last_topk_path() == expect_path
     qs = torch.randperm(n, generator=torch.Generator().manual_seed(seed))[:n_sample]
     cc, ic, zc = s["c"].cpu(), s["i"].cpu(), s["z"].cpu()
     aps_o, r1_o, idx_o, sim_o = oev.evaluate_argsort(cc[qs], ic[qs], zc[qs], cc, ic, zc, topk=k)
     idx, sim = res["topk_idx"][qs.cuda()].cpu(), res["topk_sim"][qs.cuda()].cpu()
-    assert (sim - sim_o).abs().max() <= 4e-6
+    assert (sim - sim_o).abs().max() <= sim_tol
     ok = torch.ones_like(idx_o, dtype=torch.bool)
     ok[:, 1:] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
     ok[:, :-1] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
@@ -527,7 +534,7 @@ def _topk_sample_parity(s, k, n_sample, seed):
     aps, r1s = res["aps"][qs.cuda()].double().cpu(), res["r1s"][qs.cuda()].double().cpu()
     assert abs(float(aps.mean()) - float(aps_o.mean())) <= 1e-4
     assert abs(float(r1s.mean()) - float(r1_o.mean())) <= 1e-4 * max(1.0, float(r1_o.mean()))
-    _check_all_item_ranks(plan, cc, ic, zc, queries=qs)
+    _check_all_item_ranks(plan, cc, ic, zc, queries=qs, sim_tol=sim_tol, truth64=sim_tol > 4e-6)
     plan.close()
 
 
@@ -536,7 +543,9 @@ def test_config5_lyric_covers_shape_top100():
     top-100 output; clique sizes bootstrapped from the shipped lyric-covers test split.  256 sampled queries against
     the oracle: top-100 indices / similarities, AP / R1 and the rank band of every relevant item."""
     s = _synth().make_eval_set(50_000, 2048, seed=5, dist="lyric_covers_test", device="cuda", md5_ids=False)
-    _topk_sample_parity(s, 100, 256, seed=17)
+    # 2048-term fp32 accumulations on both sides: similarities within gap / 2 = 5e-6 (of the float64 value for the
+    # relevant items, of the oracle's float32 value for the top-k lists); this size takes the symmetric top-k sweep
+    _topk_sample_parity(s, 100, 256, seed=17, sim_tol=5e-6, expect_path=1)
 
 
 def test_config3_discogs_full_scale_shape():
@@ -561,4 +570,53 @@ def test_config3_discogs_full_scale_shape():
     # size-independent property at full scale: the sums behind MAP / MR1 equal the per-query outputs
     sm = res["sums"].cpu()
     assert int(sm[2]) == n and abs(float(sm[0]) - float(res["aps"].double().sum())) <= 1e-6 * n
+    plan.close()
+
+
+@pytest.mark.parametrize("n,d,k", [(20000, 96, 10), (17000, 64, 128), (33000, 128, 50)])
+def test_symmetric_topk_sweep_matches_oracle_and_rectangle(n, d, k):
+    """All-vs-all top-k through the SYMMETRIC sweep (sampled per-query bounds, candidates collected in both directions;
+    csrc/topk_sym_kernels.cuh) vs the oracle on a query sample and vs the rectangle sweep's streaming top-k on ALL
+    queries (md5-derived version ids: collisions between cliques are candidates of nobody)."""
+    import os
+    we = _we()
+    s = _synth().make_eval_set(n, d, seed=60 + k, device="cuda")
+    _topk_sample_parity(s, k, 96, seed=k, expect_path=1)
+    c, i, z = s["c"], s["i"], s["z"]
+    plan = we.EvalPlan(c, i, c, i)
+    a = plan.run(z, z, topk=k)
+    assert plan.last_topk_path() == 1
+    os.environ["WEALY_SYM_TOPK"] = "0"
+    try:
+        b = plan.run(z, z, topk=k)
+        assert plan.last_topk_path() == 2
+    finally:
+        del os.environ["WEALY_SYM_TOPK"]
+    torch.cuda.synchronize()
+    assert float((a["topk_sim"] - b["topk_sim"]).abs().max()) <= 2e-6         # same planes, other accumulation order
+    gap_ok = torch.ones_like(a["topk_idx"], dtype=torch.bool)
+    sb = b["topk_sim"]
+    gap_ok[:, 1:] &= (sb[:, :-1] - sb[:, 1:]) > 1e-5
+    gap_ok[:, :-1] &= (sb[:, :-1] - sb[:, 1:]) > 1e-5
+    assert torch.equal(a["topk_idx"][gap_ok], b["topk_idx"][gap_ok])
+    assert abs(float(a["aps"].double().mean() - b["aps"].double().mean())) <= 1e-5
+    plan.close()
+
+
+def test_symmetric_topk_falls_back_when_a_list_overflows():
+    """Thousands of exact duplicates of one track: every one of them has thousands of candidates tied at similarity 1,
+    far more than a candidate list holds -- the overflow is detected and the call recomputed by the rectangle sweep."""
+    we = _we()
+    s = _synth().make_eval_set(18000, 64, seed=71, device="cuda", md5_ids=False)
+    c, i, z = s["c"], s["i"], s["z"].clone()
+    z[:3000] = z[0]
+    plan = we.EvalPlan(c, i, c, i)
+    res = plan.run(z, z, topk=20)
+    torch.cuda.synchronize()
+    assert plan.last_topk_path() == 3
+    sim = res["topk_sim"].cpu()
+    assert bool((sim[:3000] > 1 - 1e-5).all())                               # the duplicates fill each other's lists
+    qs = torch.arange(3000, 3064)
+    _, _, idx_o, sim_o = oev.evaluate_argsort(c.cpu()[qs], i.cpu()[qs], z.cpu()[qs], c.cpu(), i.cpu(), z.cpu(), topk=20)
+    assert (sim[qs] - sim_o).abs().max() <= 4e-6
     plan.close()
