@@ -14,13 +14,14 @@ if not os.path.isfile(_LIB_PATH):
 lib = ctypes.CDLL(_LIB_PATH)
 
 OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_ID_RANGE = range(6)
-F32, F16, BF16 = 0, 1, 2
+F32, F16, BF16, F64 = 0, 1, 2, 3
 MODE_COSSIM, MODE_COS, MODE_DOTSIM, MODE_DOT, MODE_SQEUC, MODE_EUC = range(6)
 LOSS_NTXENT, LOSS_CLEWS = 0, 1
 REDUX = {"min": 0, "max": 1, "mean": 2, "meanmin": 3, "minmean": 4}
 OUT_COUNT = 16
 
 c_i64, c_int, c_f32, c_vp, c_sz = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+c_f64 = ctypes.c_double
 
 
 class LossCfg(ctypes.Structure):
@@ -35,6 +36,9 @@ SIGNATURES = {
     "wealy_sim_matrix_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "wealy_sim_matrix": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_f32, c_f32, c_int,
                                  c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),
+    "wealy_sim_matrix_f64_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "wealy_sim_matrix_f64": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_f64, c_f64, c_vp, c_i64, c_vp, c_sz,
+                                     c_vp]),
     "wealy_sim_matrix_backward_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "wealy_sim_matrix_backward": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_f32, c_int, c_vp, c_i64,
                                           c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_sz, c_vp]),
@@ -108,13 +112,16 @@ def check(status):
     raise WealyError(f"wealy_b200 native call failed (status {status}): {msg}")
 
 
-def dtype_code(t):
+def dtype_code(t, allow_f64=False):
     import torch
+    table = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+    if allow_f64:
+        table[torch.float64] = F64
     try:
-        return {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}[t]
+        return table[t]
     except KeyError:
-        raise NotImplementedError(f"wealy_b200: dtype {t} is not supported by the CUDA path "
-                                  "(float32 / float16 / bfloat16 only)") from None
+        raise NotImplementedError(f"wealy_b200: dtype {t} is not supported by this CUDA entry point "
+                                  "(float32 / float16 / bfloat16" + (" / float64" if allow_f64 else "") + " only)") from None
 
 
 def require_cuda(*tensors):

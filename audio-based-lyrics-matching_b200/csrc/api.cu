@@ -13,6 +13,7 @@
 #include "eval_sym_epilogue.cuh"
 #include "gemm_core2.cuh"
 #include "eval_kernels.cuh"
+#include "f64_kernels.cuh"
 #include "loss_kernels.cuh"
 #include "masked_kernels.cuh"
 #include "pool_kernels.cuh"
@@ -392,6 +393,37 @@ extern "C" int wealy_sim_matrix(const void* x, int64_t n, int64_t ldx, const voi
   GemmShape sh;
   fill_shape(sh, n, m, px.d_pad, 64, 1 << 20);
   return launch_gemm<StoreEpi>(passes, px, py, sh, sp, s);
+}
+
+// float64 operands (the reference returns the input dtype): CUDA-core DGEMM with the same mode epilogue.
+// workspace: 2 (n + m) doubles.
+extern "C" size_t wealy_sim_matrix_f64_workspace_bytes(int64_t n, int64_t m) {
+  if (n < 0 || m < 0) return 0;
+  return (size_t)(2 * (n + m)) * 8 + 256;
+}
+
+extern "C" int wealy_sim_matrix_f64(const double* x, int64_t n, int64_t ldx, const double* y, int64_t m, int64_t ldy, int64_t d,
+                                    int mode, double eps, double post, double* out, int64_t ld_out, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n < 0 || m < 0 || d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad shape n=%lld m=%lld d=%lld", (long long)n, (long long)m, (long long)d);
+  if (n == 0 || m == 0) return WEALY_OK;
+  if (!x || !y || !out || !workspace) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (mode < WEALY_MODE_COSSIM || mode > WEALY_MODE_EUC) return fail(WEALY_ERR_BAD_ARG, "unknown mode %d", mode);
+  if (n >= (1ll << 31) - 256 || m >= (1ll << 31) - 256 || m > 64ll * 65535 * 64) return fail(WEALY_ERR_UNSUPPORTED, "too many rows");
+  if (workspace_bytes < wealy_sim_matrix_f64_workspace_bytes(n, m)) return fail(WEALY_ERR_WORKSPACE, "workspace too small");
+  double* xn = reinterpret_cast<double*>(align_up((size_t)workspace, 16));
+  double* xs = xn + n;
+  double* yn = xs + n;
+  double* ys = yn + m;
+  row_norm_f64_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, s>>>(x, (long long)ldx, (int)n, (int)d, xn, xs);
+  row_norm_f64_kernel<<<(unsigned)ceil_div(m * 32, 256), 256, 0, s>>>(y, (long long)ldy, (int)m, (int)d, yn, ys);
+  dim3 grid((unsigned)ceil_div(m, 64), (unsigned)ceil_div(n, 64));
+  if (grid.y > 65535) return fail(WEALY_ERR_UNSUPPORTED, "too many rows for the float64 path");
+  sim_matrix_f64_kernel<<<grid, 256, 0, s>>>(x, (long long)ldx, (int)n, y, (long long)ldy, (int)m, (int)d, mode, eps, post, xn, xs, yn,
+                                             ys, out, (long long)ld_out);
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -909,13 +941,14 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   int tk_cap2 = 0;
   if (sym_topk) {
     const int n = (int)nq, rows = (int)rows_q;
-    int S = (int)(nq / 8);
-    if (S < 8192) S = 8192;
-    S = (int)ceil_div(S, kTileN) * kTileN;
+    // sample ~N/16 rows (>= 4096): the pre-pass is one fp16 pass of N x S pairs, L2-bandwidth bound.  r-th best of the
+    // sample with r = 3 k S / N (>= 24): about max(3 k, 24 N / S) corpus candidates lie above it; the count's relative
+    // spread is 1 / sqrt(r), the lists hold mean + 8 sigma.
+    int S = (int)ceil_div(nq / 16, kTileN) * kTileN;
+    if (S < 4096) S = 4096;
     if (S > n) S = n;
-    const double frac = (double)S / (double)n;
-    int r = (int)ceil(3.0 * topk * frac);
-    if (r < 32) r = 32;
+    int r = (int)ceil(3.0 * topk * (double)S / (double)n);
+    if (r < 24) r = 24;
     if (r > 64) {  // the bound kernel merges <= 4 lists of <= 256 entries: shrink the sample instead
       S = (int)((64.0 * n) / (3.0 * topk)) / kTileN * kTileN;
       r = 64;
@@ -1291,6 +1324,11 @@ extern "C" int wealy_masked_reduce(const void* x, const uint8_t* mask, int64_t r
     case WEALY_F32: return launch_masked<float>(x, mask, rows, cols, op, fill, eps, out, s);
     case WEALY_F16: return launch_masked<__half>(x, mask, rows, cols, op, fill, eps, out, s);
     case WEALY_BF16: return launch_masked<__nv_bfloat16>(x, mask, rows, cols, op, fill, eps, out, s);
+    case WEALY_F64:
+      masked_reduce_f64_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, s>>>((const double*)x, mask, rows, cols, op, (double)fill,
+                                                                                 (double)eps, (double*)out);
+      CU_TRY(cudaGetLastError());
+      return WEALY_OK;
     default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
   }
 }

@@ -6,10 +6,10 @@
 // column query, so a query's candidates arrive from many CTAs in no particular order.  What makes top-k possible
 // there is a STATIC per-query lower bound beta_q of the k-th best similarity, known before the sweep starts:
 //
-//   1. sample:   S candidates, evenly spaced in clique-sorted order (S ~ N / 8, at least 8192);
+//   1. sample:   S candidates, evenly spaced in clique-sorted order (S ~ N / 16, at least 4096);
 //   2. pre-pass: every query against the sample with the rectangle kernel's streaming top-r (one fp16 pass: the
-//                bound does not have to be exact), r = 3 k S / N, so that about 3 k candidates of the whole corpus
-//                lie above the sample's r-th best;
+//                bound does not have to be exact), r = max(24, 3 k S / N), so that about 3 k candidates of the whole
+//                corpus lie above the sample's r-th best (relative spread of that count: 1 / sqrt(r));
 //   3. sweep:    EvalSymEpi<..., kTopk = true> appends every element above beta_row / beta_col to the row's / the
 //                column's list (atomic cursor; lists hold 3 k + 8 sigma entries);
 //   4. finalize: per query, select the k best of its list, order them, translate plane rows to the caller's indices.

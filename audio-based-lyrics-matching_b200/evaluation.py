@@ -10,7 +10,9 @@ evaluation tensors it prepares (`candidates_c`, `candidates_i`: lib/audio_datase
     aps, r1s, topk_idx, topk_sim = evaluate(..., topk=100)
 
 Host tensors are accepted and copied to the current CUDA device (that copy is part of the
-end-to-end measurement in bench.py); the computation itself has no CPU path.
+end-to-end measurement in bench.py); the computation itself has no CPU path.  float64 embeddings are
+rounded to float32 on entry: the outputs are ranks, AP / R1 and float32 top-k similarities, and the rounding
+moves a similarity by < 2e-7, far inside the 1e-5 gap below which ranks are allowed to differ.
 """
 import ctypes
 
@@ -72,6 +74,8 @@ class EvalPlan:
         """Sweep this rank's share (row blocks = shard_rank mod shard_world) of the symmetric all-vs-all
         problem; the plan must have been built with queries == candidates."""
         z = _to_device(z, self.device)
+        if z.dtype == torch.float64:
+            z = z.float()
         assert z.ndim == 2 and z.shape[0] == self.nq == self.nc
         if z.stride(1) != 1:
             z = z.contiguous()
@@ -150,6 +154,9 @@ class EvalPlan:
         same = queries_z is candidates_z
         qz = _to_device(queries_z, self.device)
         cz = qz if same else _to_device(candidates_z, self.device)
+        if qz.dtype == torch.float64:                     # (see the module docstring)
+            qz = qz.float()
+            cz = qz if same else cz.float()
         if qz.ndim == 3:                                  # [N, s, D]: the chunks of a track
             assert cz.ndim == 3 and cz.shape[1] == qz.shape[1] and (chunks is None or int(chunks) == qz.shape[1])
             chunks = qz.shape[1]

@@ -13,8 +13,12 @@ mutates the caller's z_label in place, lib/losses.py:34-35 / 221-222).  Forward 
 the fused tcgen05 kernels behind wealy_loss_forward / wealy_loss_backward (include/wealy_b200.h):
 the B x B similarity matrix is never stored; the backward recomputes it on the tensor cores.
 `loss` is differentiable w.r.t. z through a torch.autograd.Function; the logdict entries are
-detached diagnostics.  For fp16 / bf16 inputs the loss is returned in fp32 (the kernels accumulate
-in fp32; the reference would round it to the input dtype).  Inputs must be CUDA tensors.
+detached diagnostics.  Output dtype: like the reference (lib/losses.py:65-66 computes the loss from z's
+own dtype), `loss` and the logdict entries carry z's dtype -- the kernels accumulate in fp32 / fp64 and the
+result is rounded once at the end; pass `loss_dtype=torch.float32` to the constructor to keep the unrounded
+value for fp16 / bf16 batches.  float64 batches are rounded to float32 on entry (the tensor-core path is
+fp32-grade: loss within 1e-6 relative of the float64 value) and loss / gradient are returned as float64.
+Inputs must be CUDA tensors.
 """
 import ctypes
 
@@ -37,9 +41,12 @@ def _label_noise_(z_label):
 
 class _FusedLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, z_label, z_idx, cfg_items):
+    def forward(ctx, z, z_label, z_idx, cfg_items, loss_dtype):
         cfg = N.LossCfg(**dict(cfg_items))
         N.require_cuda(z, z_label, z_idx)
+        ctx.in_dtype = z.dtype
+        if z.dtype == torch.float64:
+            z = z.float()
         code = N.dtype_code(z.dtype)
         zz = z if z.stride(1) == 1 else z.contiguous()
         lab = z_label.to(torch.long).contiguous()
@@ -54,8 +61,7 @@ class _FusedLoss(torch.autograd.Function):
                                              N.stream_ptr(zz.device)))
         ctx.save_for_backward(zz, ws)
         ctx.cfg_items = cfg_items
-        loss_dtype = torch.float32 if z.dtype in (torch.float16, torch.bfloat16) else z.dtype
-        loss = out[0].to(loss_dtype)
+        loss = out[0].to(ctx.in_dtype if loss_dtype is None else loss_dtype)
         ctx.mark_non_differentiable(out)
         return loss, out
 
@@ -70,7 +76,7 @@ class _FusedLoss(torch.autograd.Function):
             N.check(N.lib.wealy_loss_backward(ctypes.byref(cfg), zz.data_ptr(), b, zz.stride(0), d,
                                               N.dtype_code(zz.dtype), g.data_ptr(), dz.data_ptr(), dz.stride(0),
                                               ws.data_ptr(), ws.numel(), N.stream_ptr(zz.device)))
-        return dz, None, None, None
+        return dz.to(ctx.in_dtype), None, None, None, None
 
 
 def _passes(precision, z):
@@ -81,26 +87,27 @@ def _passes(precision, z):
     return passes_of(precision)
 
 
-def _run(z, z_label, z_idx, **cfg):
+def _run(z, z_label, z_idx, loss_dtype=None, **cfg):
     base = dict(kind=0, passes=3, temperature=1.0, gamma=0.0, b=0.0, eps=1e-8, epsilon=1e-6, uw=0.0,
                 numerically_friendly=1)
     base.update(cfg)
-    return _FusedLoss.apply(z, z_label, z_idx, tuple(sorted(base.items())))
+    return _FusedLoss.apply(z, z_label, z_idx, tuple(sorted(base.items())), loss_dtype)
 
 
 class NTXentLoss(nn.Module):
     """lib/losses.py:10-73."""
 
-    def __init__(self, temperature=0.1, precision=None):
+    def __init__(self, temperature=0.1, precision=None, loss_dtype=None):
         super().__init__()
         self.tau = temperature
         self.precision = precision
+        self.loss_dtype = loss_dtype
 
     def forward(self, z_label, z_idx, z, extra=None):
         assert len(z_label) == len(z_idx) and len(z_label) == len(z)
         N.require_cuda(z, z_label, z_idx)
         _label_noise_(z_label)
-        loss, st = _run(z, z_label, z_idx, kind=N.LOSS_NTXENT, passes=_passes(self.precision, z),
+        loss, st = _run(z, z_label, z_idx, self.loss_dtype, kind=N.LOSS_NTXENT, passes=_passes(self.precision, z),
                         temperature=float(self.tau))
         stats = st.to(loss.dtype)
         logdict = {"l_main": loss, "v_zmax": stats[1], "v_zmean": stats[2], "v_zstd": stats[3]}
@@ -111,7 +118,7 @@ class CLEWSLoss(nn.Module):
     """lib/losses.py:176-285 (CLEWS-style alignment + uniformity on cosine distances)."""
 
     def __init__(self, gamma: float = 8.0, b: float = 1.0, eps: float = 1e-8, epsilon: float = 1e-6,
-                 uniformity_weight: float = 0.5, warmup_steps: int = 1000, precision=None):
+                 uniformity_weight: float = 0.5, warmup_steps: int = 1000, precision=None, loss_dtype=None):
         super().__init__()
         self.gamma = float(gamma)
         self.b = float(b)
@@ -120,6 +127,7 @@ class CLEWSLoss(nn.Module):
         self.uniformity_weight = float(uniformity_weight)
         self.warmup_steps = int(warmup_steps)
         self.precision = precision
+        self.loss_dtype = loss_dtype
 
     def forward(self, z_label, z_idx, z, extra=None, numerically_friendly=True):
         if z.dim() == 3:
@@ -140,7 +148,7 @@ class CLEWSLoss(nn.Module):
                 step = int(self.global_step)
             if step is not None:
                 uw = float(min(self.uniformity_weight, self.uniformity_weight * (step + 1) / self.warmup_steps))
-        loss, st = _run(z, z_label, z_idx, kind=N.LOSS_CLEWS, passes=_passes(self.precision, z), gamma=self.gamma,
+        loss, st = _run(z, z_label, z_idx, self.loss_dtype, kind=N.LOSS_CLEWS, passes=_passes(self.precision, z), gamma=self.gamma,
                         b=self.b, eps=self.eps, epsilon=self.epsilon, uw=uw,
                         numerically_friendly=1 if numerically_friendly else 0)
         stats = st.to(loss.dtype)

@@ -7,6 +7,11 @@ Same names, argument meaning, return shape / dtype and error behaviour as the re
 (AssertionError for rank violations, NotImplementedError for unknown modes).  The contraction runs
 in the tcgen05 kernel behind wealy_sim_matrix (include/wealy_b200.h); `precision` selects the
 tensor-core mode ("fp16x3": fp32-grade hi/lo split, the default; "fp16": one pass, ~1e-4 abs error).
+float64 inputs return float64 like the reference: they take a CUDA-core double-precision kernel
+(wealy_sim_matrix_f64), gradients included.  Every mode is differentiable (the reference's are: plain
+torch ops): cos / cossim / dot / dotsim and the euclidean family (sqeuc / nsqeuc / fro / nfro / euc / neuc
+with p = 2, pairwise_euclidean_distance_matrix) run their two gradient products on the same contraction
+core.  cdist with p != 2 is not a contraction and raises NotImplementedError (WEALY_ERR_UNSUPPORTED).
 Inputs must be CUDA tensors -- there is no CPU fallback.
 """
 import ctypes
@@ -43,12 +48,35 @@ def _rows(t):
     return t
 
 
+def _sim_matrix_f64(x, y, mode, eps, post):
+    """float64 operands: CUDA-core DGEMM with the mode epilogue (wealy_sim_matrix_f64)."""
+    n, d = x.shape
+    m = y.shape[0]
+    out = torch.empty((n, m), dtype=torch.float64, device=x.device)
+    if n == 0 or m == 0:
+        return out
+    if d == 0:
+        raise NotImplementedError("wealy_b200: zero-width embeddings")
+    same = x is y
+    x = _rows(x)
+    y = x if same else _rows(y)
+    with torch.cuda.device(x.device):
+        ws_bytes = N.lib.wealy_sim_matrix_f64_workspace_bytes(n, m)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        N.check(N.lib.wealy_sim_matrix_f64(x.data_ptr(), n, x.stride(0), y.data_ptr(), m, y.stride(0), d, mode, float(eps),
+                                           float(post), out.data_ptr(), out.stride(0), ws.data_ptr(), ws_bytes,
+                                           N.stream_ptr(x.device)))
+    return out
+
+
 def _sim_matrix(x, y, mode, eps, post, precision):
     N.require_cuda(x, y)
     if x.dtype != y.dtype:
         raise RuntimeError(f"expected x and y to have the same dtype, got {x.dtype} and {y.dtype}")
     if x.shape[1] != y.shape[1]:
         raise RuntimeError(f"size mismatch: x is {tuple(x.shape)}, y is {tuple(y.shape)}")
+    if x.dtype == torch.float64:
+        return _sim_matrix_f64(x, y, mode, eps, post)
     code = N.dtype_code(x.dtype)
     n, d = x.shape
     m = y.shape[0]
@@ -136,31 +164,118 @@ class _DotMatrix(torch.autograd.Function):
         return (dx if ctx.needs_input_grad[0] else None), (dy if ctx.needs_input_grad[1] else None), None, None, None
 
 
+def _grad_products(h, x, y, precision):
+    """(h @ y, h.T @ x) for an upstream-gradient-like matrix h [n, m] on the contraction core (the float64 kernel for
+    doubles): the two products every mode's backward is made of."""
+    if x.dtype == torch.float64:
+        h = h.contiguous()
+        return (_sim_matrix_f64(h, y.t().contiguous(), N.MODE_DOTSIM, 0.0, 1.0),
+                _sim_matrix_f64(h.t().contiguous(), x.t().contiguous(), N.MODE_DOTSIM, 0.0, 1.0))
+    n, d = x.shape
+    m = y.shape[0]
+    hh = h.to(x.dtype).contiguous()
+    ht = hh.t().contiguous()
+    xt, yt = x.t().contiguous(), y.t().contiguous()
+    hy = torch.empty((n, d), dtype=x.dtype, device=x.device)
+    htx = torch.empty((m, d), dtype=x.dtype, device=x.device)
+    passes = passes_of(precision)
+    with torch.cuda.device(x.device):
+        ws_bytes = N.lib.wealy_dot_matrix_backward_workspace_bytes(n, m, d, passes)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        N.check(N.lib.wealy_dot_matrix_backward(
+            hh.data_ptr(), hh.stride(0), ht.data_ptr(), ht.stride(0), xt.data_ptr(), xt.stride(0), yt.data_ptr(),
+            yt.stride(0), n, m, d, N.dtype_code(x.dtype), passes, hy.data_ptr(), hy.stride(0), htx.data_ptr(),
+            htx.stride(0), ws.data_ptr(), ws_bytes, N.stream_ptr(x.device)))
+    return hy, htx
+
+
+class _EucMatrix(torch.autograd.Function):
+    """Euclidean family under autograd (lib/tensor_ops.py:131-149 and the p = 2 cdist modes, :159-166):
+    out = post * D2 (squared) or post * sqrt(D2), D2 = max(|x|^2 - 2 x.y + |y|^2, 0).  With H = dL/dD2 -- zero where the
+    distance is zero, like the reference's clamp + masked safe sqrt and like cdist's backward --
+        dx = 2 (rowsum(H) x - H y),   dy = 2 (colsum(H) y - H^T x):  the two products run on the contraction core."""
+
+    @staticmethod
+    def forward(ctx, x, y, mode, post, precision):
+        out = _sim_matrix(x.detach(), y.detach(), mode, 0.0, post, precision)
+        ctx.save_for_backward(x, y, out)
+        ctx.cfg = (mode, post, precision)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y, out = ctx.saved_tensors
+        mode, post, precision = ctx.cfg
+        acc = torch.float64 if x.dtype == torch.float64 else torch.float32
+        g, o = g.to(acc), out.to(acc)
+        xd, yd = x.detach(), y.detach()
+        # a distance inside the forward's rounding noise of zero (|x|^2 - 2 x.y + |y|^2 cancels to ~1e-6 of the norms on
+        # the fp32-grade path) is a zero distance: no gradient, as for the exact zeros the reference masks out
+        noise = (1e-13 if acc == torch.float64 else 1e-6) * \
+            ((xd.to(acc) ** 2).sum(dim=1, keepdim=True) + (yd.to(acc) ** 2).sum(dim=1)[None, :])
+        d2 = o / post if mode == N.MODE_SQEUC else (o / post) ** 2
+        pos = d2 > noise
+        if mode == N.MODE_SQEUC:
+            h = torch.where(pos, g * post, torch.zeros_like(g))
+        else:
+            h = torch.where(pos, g * (post * post * 0.5) / torch.where(pos, o, torch.ones_like(o)), torch.zeros_like(g))
+        hy, htx = _grad_products(h, xd, yd, precision)
+        dx = 2.0 * (h.sum(dim=1, keepdim=True) * xd.to(acc) - hy.to(acc))
+        dy = 2.0 * (h.sum(dim=0)[:, None] * yd.to(acc) - htx.to(acc))
+        return (dx.to(x.dtype) if ctx.needs_input_grad[0] else None), (dy.to(y.dtype) if ctx.needs_input_grad[1] else None), \
+            None, None, None
+
+
+class _F64Matrix(torch.autograd.Function):
+    """cos / cossim / dot / dotsim on float64 operands under autograd: same closed forms as _CosineMatrix / _DotMatrix,
+    products on the float64 kernel, the normalisation Jacobian of x / (|x| + eps) as elementwise torch ops."""
+
+    @staticmethod
+    def forward(ctx, x, y, mode, eps):
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (mode, eps)
+        return _sim_matrix_f64(x.detach(), y.detach(), mode, eps, 1.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, y = (t.detach() for t in ctx.saved_tensors)
+        mode, eps = ctx.cfg
+        if mode in (N.MODE_COS, N.MODE_DOT):                       # out = 1 - s
+            g = -g
+        if mode in (N.MODE_DOTSIM, N.MODE_DOT):
+            dx, dy = _grad_products(g, x, y, None)
+            return (dx if ctx.needs_input_grad[0] else None), (dy if ctx.needs_input_grad[1] else None), None, None
+        rx, ry = x.norm(dim=1, keepdim=True), y.norm(dim=1, keepdim=True)
+        xh, yh = x / (rx + eps), y / (ry + eps)
+        dxh, dyh = _grad_products(g, xh, yh, None)
+
+        def jac(v, r, dvh):                                        # d/dv of v / (|v| + eps), zero radial term at v = 0
+            radial = (v * dvh).sum(dim=1, keepdim=True) / (torch.where(r > 0, r, torch.ones_like(r)) * (r + eps) ** 2)
+            return dvh / (r + eps) - torch.where(r > 0, radial, torch.zeros_like(radial)) * v
+        return (jac(x, rx, dxh) if ctx.needs_input_grad[0] else None), (jac(y, ry, dyh) if ctx.needs_input_grad[1] else None), \
+            None, None
+
+
 def pairwise_euclidean_distance_matrix(x, y, squared=False, eps=1e-6, precision=None):
     """lib/tensor_ops.py:131-149: |x|^2 - 2 x.y + |y|^2, clamped at 0, optional sqrt (zeros stay 0).
-    `eps` only guards the reference's autograd through sqrt(0); the forward value does not depend on it."""
-    if x.requires_grad or y.requires_grad:
-        raise NotImplementedError("wealy_b200.pairwise_euclidean_distance_matrix: autograd is not provided; "
-                                  "use wealy_b200.losses for the fused differentiable losses")
-    return _sim_matrix(x, y, N.MODE_SQEUC if squared else N.MODE_EUC, 0.0, 1.0, precision)
+    `eps` only guards the reference's autograd through sqrt(0); neither the forward value nor the gradient (zero at
+    zero distance) depends on it."""
+    mode = N.MODE_SQEUC if squared else N.MODE_EUC
+    if (x.requires_grad or y.requires_grad) and torch.is_grad_enabled() and x.shape[0] > 0 and y.shape[0] > 0:
+        return _EucMatrix.apply(x, y, mode, 1.0, precision)
+    return _sim_matrix(x, y, mode, 0.0, 1.0, precision)
 
 
 def pairwise_distance_matrix(x, y, mode="fro", p=2, eps=1e-6, precision=None):
-    """lib/tensor_ops.py:152-176.  Returns an (n, m) tensor with x's dtype."""
+    """lib/tensor_ops.py:152-176.  Returns an (n, m) tensor with x's dtype; differentiable in every mode."""
     assert x.ndim == y.ndim and x.ndim <= 2
     if x.ndim == 1:  # :154-156 -- 1-D inputs are n x 1 column vectors
         x = x.unsqueeze(-1)
         y = y.unsqueeze(-1)
     if x.ndim == 0:
         raise NotImplementedError("wealy_b200: 0-d inputs")
-    if (x.requires_grad or y.requires_grad) and torch.is_grad_enabled():
-        if mode in ("cos", "cossim") and x.shape[0] > 0 and y.shape[0] > 0 and x.shape[1] > 0:
-            code = N.MODE_COSSIM if mode == "cossim" else N.MODE_COS
-            return _CosineMatrix.apply(x, y, code, eps, precision)
-        if mode in ("dot", "dotsim") and x.shape[0] > 0 and y.shape[0] > 0 and x.shape[1] > 0:
-            return _DotMatrix.apply(x, y, N.MODE_DOTSIM if mode == "dotsim" else N.MODE_DOT, eps, precision)
-        raise NotImplementedError("wealy_b200.pairwise_distance_matrix: autograd is provided for the contraction modes "
-                                  "(cos / cossim / dot / dotsim); use wealy_b200.losses for the fused differentiable losses")
+    grad = (x.requires_grad or y.requires_grad) and torch.is_grad_enabled() and \
+        x.shape[0] > 0 and y.shape[0] > 0 and x.shape[1] > 0
     if mode == "euc" or mode == "neuc":
         p = 2
     d = x.size(-1)
@@ -169,11 +284,22 @@ def pairwise_distance_matrix(x, y, mode="fro", p=2, eps=1e-6, precision=None):
             raise NotImplementedError("wealy_b200: cdist modes are built for p=2 only (p-norms with p != 2 are "
                                       "not a contraction; out of the hot path)")
         post = 1.0 if mode in ("fro", "euc") else 1.0 / (d ** (1 / p))
+        if grad:
+            return _EucMatrix.apply(x, y, N.MODE_EUC, post, precision)
         return _sim_matrix(x, y, N.MODE_EUC, 0.0, post, precision)
     if mode in ("sqeuc", "nsqeuc"):
-        return _sim_matrix(x, y, N.MODE_SQEUC, 0.0, 1.0 if mode == "sqeuc" else 1.0 / d, precision)
+        post = 1.0 if mode == "sqeuc" else 1.0 / d
+        if grad:
+            return _EucMatrix.apply(x, y, N.MODE_SQEUC, post, precision)
+        return _sim_matrix(x, y, N.MODE_SQEUC, 0.0, post, precision)
     if mode in ("cos", "cossim", "dot", "dotsim"):
         code = {"cossim": N.MODE_COSSIM, "cos": N.MODE_COS, "dotsim": N.MODE_DOTSIM, "dot": N.MODE_DOT}[mode]
+        if grad and x.dtype == torch.float64:
+            return _F64Matrix.apply(x, y, code, eps)
+        if grad and mode in ("cos", "cossim"):
+            return _CosineMatrix.apply(x, y, code, eps, precision)
+        if grad:
+            return _DotMatrix.apply(x, y, code, eps, precision)
         return _sim_matrix(x, y, code, eps, 1.0, precision)
     raise NotImplementedError
 
@@ -192,7 +318,7 @@ _OPS = {"sum": 0, "mean": 1, "min": 2, "max": 3}
 
 def _reduce(x, mask, dim, keepdim, op, fill=0.0, eps=1e-7):
     N.require_cuda(x)
-    code = N.dtype_code(x.dtype)
+    code = N.dtype_code(x.dtype, allow_f64=True)
     if mask is not None:
         N.require_cuda(mask)
         # like the reference's `included * x` / `torch.where(mask, ctt, x)`, x and mask broadcast together

@@ -253,6 +253,7 @@ def parity_sample(plan, aps, r1s, z_c, c_c, i_c, qsel, *, topk=None, topk_idx=No
         ok = torch.ones_like(idx_o, dtype=torch.bool)
         ok[:, 1:] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
         ok[:, :-1] &= (sim_o[:, :-1] - sim_o[:, 1:]) > 1e-5
+        ok[:, -1] = False   # the last position also depends on the (k+1)-th best, which the lists do not show
         out.update({"topk": int(topk), "topk_max_abs_dsim": float((sim_g - sim_o).abs().max()),
                     "topk_idx_compared_where_gap_gt_1e-5": int(ok.sum()),
                     "topk_idx_mismatches": int((idx_g[ok] != idx_o[ok]).sum())})
@@ -271,7 +272,8 @@ def stage_roofline(plan, n, d, passes, total_pairs, peaks, topk=0, parts=4, cap=
         "ap_reduce": total_pairs * 4 + n * 8,
     }
     if topk:
-        by["topk_finalize"] = n * parts * cap * 8 + n * topk * 12
+        # rectangle sweep: 4 streaming lists of `cap` entries per query; symmetric sweep (cap = 0): ~3k + 8 sigma entries
+        by["topk_finalize"] = n * (parts * cap if cap else 7 * topk) * 8 + n * topk * 12
     hbm = float(peaks["hbm_gbs"])
     out = {}
     for k, b in by.items():
@@ -279,7 +281,8 @@ def stage_roofline(plan, n, d, passes, total_pairs, peaks, topk=0, parts=4, cap=
         gbs = b / (t * 1e-3) / 1e9 if t > 0 else None
         out[k] = {"ms": t, "bytes": float(b), "gbs": gbs, "frac_of_hbm_peak": (gbs / hbm) if gbs else None}
     out["sweep_ms"] = ms["sweep"]
-    out["note"] = ("kpos gathers operand rows of relevant pairs out of L2 (the planes were just written by prep), so its "
+    out["note"] = ("with top-k in the symmetric sweep the kpos window also holds the sampled pre-pass (one fp16 pass of every query "
+                   "against ~N/8 candidates); kpos gathers operand rows of relevant pairs out of L2 (the planes were just written by prep), so its "
                    "'GB/s' is L2-side; ap_reduce / topk_finalize move KB..MB and are launch-latency bound")
     return out
 
@@ -437,7 +440,10 @@ def leg_c5(dev, peaks, precision):
            "ms_per_step": ms, "gpairs_per_s": float(n) * n / (ms * 1e-3) / 1e9,
            "sweep_ms": st["sweep"], "sweep_algorithmic_tflops": tf, "roofline_frac": tf / peak,
            "ceiling_gpairs_per_s_at_d2048": peak * 1e12 / (2.0 * d) / 1e9,
-           "stages": stage_roofline(plan, n, d, passes, plan.total_pairs, peaks, topk=k, parts=4, cap=320),
+           "topk_path": {1: "symmetric sweep, sampled per-query bounds (csrc/topk_sym_kernels.cuh)", 2: "rectangle sweep, streaming top-k",
+                         3: "symmetric sweep overflowed -> rectangle sweep"}.get(plan.last_topk_path(), "?"),
+           "stages": stage_roofline(plan, n, d, passes, plan.total_pairs, peaks, topk=k, parts=4,
+                                    cap=0 if plan.last_topk_path() == 1 else 320),
            "cpu_sample_gpairs_per_s": 256 * n / sec / 1e9, "cpu_cores": torch.get_num_threads(),
            "parity": par}
     plan.close()

@@ -35,6 +35,7 @@ extern "C" {
 #define WEALY_F32 0
 #define WEALY_F16 1
 #define WEALY_BF16 2
+#define WEALY_F64 3 /* accepted by wealy_masked_reduce; matrices of doubles go through wealy_sim_matrix_f64 */
 
 /* pairwise_distance_matrix modes -- lib/tensor_ops.py:157-173 */
 #define WEALY_MODE_COSSIM 0
@@ -62,6 +63,14 @@ size_t wealy_sim_matrix_workspace_bytes(int64_t n, int64_t m, int64_t d, int pas
 int wealy_sim_matrix(const void* x, int64_t n, int64_t ldx, const void* y, int64_t m, int64_t ldy, int64_t d,
                      int in_dtype, int mode, float eps, float post, int passes, void* out, int64_t ld_out,
                      int out_dtype, void* workspace, size_t workspace_bytes, void* stream);
+
+/* float64 operands (the reference returns its input dtype): the same modes on a CUDA-core DGEMM, every number a double.
+ * workspace: wealy_sim_matrix_f64_workspace_bytes(n, m) bytes.  The evaluation and loss entry points take
+ * float32 / float16 / bfloat16 only: their Python mirrors round float64 inputs to float32 (documented there).        */
+size_t wealy_sim_matrix_f64_workspace_bytes(int64_t n, int64_t m);
+int wealy_sim_matrix_f64(const double* x, int64_t n, int64_t ldx, const double* y, int64_t m, int64_t ldy, int64_t d, int mode,
+                         double eps, double post, double* out, int64_t ld_out, void* workspace, size_t workspace_bytes,
+                         void* stream);
 
 /* Gradient of the cosine modes of pairwise_distance_matrix (the reference differentiates through it,
  * lib/losses.py:45).  grad [n][m] = dL/d(out) and grad_t [m][n] = its transpose (both with the input dtype);

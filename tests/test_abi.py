@@ -78,14 +78,80 @@ def test_product_never_imports_oracle():
                     assert not re.search(r"(open|listdir|insert|exists|isfile)\([^)]*reference", src), f
 
 
-def test_ctypes_signatures_match_the_header_argument_counts():
-    """Every prototype in include/wealy_b200.h has as many parameters as its ctypes signature in _native.py."""
+def _ctype_of(decl):
+    """C parameter / return declaration from include/wealy_b200.h -> the ctypes type a binding must use."""
+    import ctypes
+    decl = " ".join(decl.replace("const", " ").split())
+    name_stripped = re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", decl).strip() if not decl.endswith("*") else decl
+    t = name_stripped if name_stripped else decl          # (a bare type without a parameter name)
+    t = t.replace(" *", "*").strip()
+    stars = t.count("*")
+    base = t.replace("*", "").strip()
+    scalars = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "int32_t": ctypes.c_int32, "float": ctypes.c_float,
+               "double": ctypes.c_double, "size_t": ctypes.c_size_t, "uint32_t": ctypes.c_uint32}
+    if stars == 0:
+        return scalars[base]
+    if base == "char" and stars == 1:
+        return ctypes.c_char_p
+    return "pointer:" + base + "*" * stars
+
+
+def _compatible(c_decl_type, ctypes_type):
+    """A pointer parameter may be bound as c_void_p (raw device / handle pointers) or as POINTER(T) of its pointee
+    (host out-parameters, the config struct); a scalar must be bound with exactly its C type."""
+    import ctypes
+    if not isinstance(c_decl_type, str):
+        return c_decl_type is ctypes_type
+    if ctypes_type is ctypes.c_void_p:
+        return True
+    if not hasattr(ctypes_type, "_type_"):
+        return False
+    base, stars = c_decl_type[len("pointer:"):].rstrip("*"), c_decl_type.count("*")
+    pointee = ctypes_type._type_
+    if stars >= 2:                                           # T** out-parameter: POINTER(c_void_p)
+        return pointee is ctypes.c_void_p
+    table = {"int64_t": ctypes.c_int64, "int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double,
+             "uint32_t": ctypes.c_uint32, "int32_t": ctypes.c_int32}
+    if base in table:
+        return pointee is table[base]
+    return base in ("wealy_loss_cfg", "wealy_eval_plan") and issubclass(pointee, ctypes.Structure) or pointee is ctypes.c_void_p
+
+
+def test_ctypes_signatures_match_the_header_types():
+    """Every prototype in include/wealy_b200.h against its ctypes signature in _native.py: same symbol set, same
+    parameter count, and parameter by parameter the same C type (a swapped int64_t / int pair must not pass)."""
+    import ctypes
     import wealy_b200._native as N
     src = open(os.path.join(ROOT, "include", "wealy_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    protos = dict(re.findall(r"\b(wealy_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
-    assert set(protos) == set(N.SIGNATURES)
-    for name, params in protos.items():
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)\b(wealy_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    names = [n for _, n, _ in protos]
+    assert set(names) == set(N.SIGNATURES) and len(names) == len(set(names))
+    checked = 0
+    for ret, name, params in protos:
+        res, args = N.SIGNATURES[name]
+        ret = " ".join(ret.split())
+        if ret == "void":
+            assert res is None, name
+        else:
+            assert _compatible(_ctype_of(ret + " x") if not ret.endswith("*") else _ctype_of(ret), res) or \
+                (ret.replace("const", "").strip() == "char*" and res is ctypes.c_char_p), (name, ret, res)
         params = " ".join(params.split())
-        n = 0 if params in ("", "void") else params.count(",") + 1
-        assert n == len(N.SIGNATURES[name][1]), f"{name}: header has {n} parameters, ctypes {len(N.SIGNATURES[name][1])}"
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, ctypes {len(args)}"
+        for k, (decl, ct) in enumerate(zip(plist, args)):
+            assert _compatible(_ctype_of(decl), ct), f"{name}: parameter {k} is `{decl}` in the header but {ct} in _native.py"
+            checked += 1
+    assert checked > 300
+
+
+def test_type_check_catches_a_swapped_pair():
+    import ctypes
+    assert not _compatible(_ctype_of("int64_t n"), ctypes.c_int)
+    assert not _compatible(_ctype_of("int mode"), ctypes.c_int64)
+    assert not _compatible(_ctype_of("float eps"), ctypes.c_double)
+    assert not _compatible(_ctype_of("const void* x"), ctypes.c_int64)
+    assert _compatible(_ctype_of("const int64_t* offsets"), ctypes.c_void_p)
+    assert _compatible(_ctype_of("int64_t* total_pairs"), ctypes.POINTER(ctypes.c_int64))
+    assert not _compatible(_ctype_of("int64_t* total_pairs"), ctypes.POINTER(ctypes.c_int))
+    assert _compatible(_ctype_of("wealy_eval_plan** plan"), ctypes.POINTER(ctypes.c_void_p))

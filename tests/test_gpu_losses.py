@@ -72,16 +72,20 @@ def test_c4_shape_bf16_batch():
     from wealy_b200.data import synth
     wl = _wl()
     s = synth.make_loss_batch(4096, 1024, seed=0, dtype=torch.bfloat16)
-    for make, oracle in ((lambda: wl.NTXentLoss(0.1), lambda l, i, z: ol.ntxent(l, i, z, 0.1)),
-                         (lambda: wl.CLEWSLoss(), lambda l, i, z: ol.clews(l, i, z))):
+    for make, oracle in ((lambda **kw: wl.NTXentLoss(0.1, **kw), lambda l, i, z: ol.ntxent(l, i, z, 0.1)),
+                         (lambda **kw: wl.CLEWSLoss(**kw), lambda l, i, z: ol.clews(l, i, z))):
+        # default: the loss carries z's dtype, like the reference (lib/losses.py:65-66 builds it from z's own dtype)
+        l16, logd16 = make()(s["label"].cuda(), s["idx"].cuda(), s["z"].cuda())
+        assert l16.dtype == torch.bfloat16 and all(v.dtype == torch.bfloat16 for k, v in logd16.items() if k != "uniformity_weight")
         z = s["z"].cuda().requires_grad_(True)
-        loss, logd = make()(s["label"].cuda(), s["idx"].cuda(), z)
+        loss, logd = make(loss_dtype=torch.float32)(s["label"].cuda(), s["idx"].cuda(), z)     # unrounded value
         loss.backward()
         torch.cuda.synchronize()
         zr = s["z"].float().requires_grad_(True)          # the same bf16 values, reference arithmetic in fp32
         loss_o, _ = oracle(s["label"].clone(), s["idx"], zr)
         loss_o.backward()
         assert loss.dtype == torch.float32 and z.grad.dtype == torch.bfloat16
+        assert abs(float(l16) - float(loss_o)) <= 2 ** -8 * abs(float(loss_o))      # one bf16 rounding of the fp32 result
         assert abs(float(loss.detach()) - float(loss_o)) <= LOSS_RTOL * abs(float(loss_o))
         rel = float((z.grad.cpu().float() - zr.grad).norm() / zr.grad.norm())
         assert rel <= 4e-3, rel                           # bf16 output rounding: 2^-9 per element
@@ -167,3 +171,26 @@ def test_forward_backward_is_cuda_graph_capturable(kind):
         g.replay()
     torch.cuda.synchronize()
     assert float(loss_g) == ref_loss and torch.equal(z.grad, ref_grad)
+
+
+def test_float64_batch_and_id_overflow():
+    """float64 batches: rounded to float32 on entry, loss / gradient come back as float64 (the reference returns the
+    input dtype).  Labels / ids beyond 32 bits would be truncated by the packed id records: the loss is NaN, loudly."""
+    from wealy_b200.data import synth
+    wl = _wl()
+    s = synth.make_loss_batch(256, 64, seed=4)
+    for mod, oracle in ((wl.NTXentLoss(0.1), lambda l, i, z: ol.ntxent(l, i, z, 0.1)), (wl.CLEWSLoss(), lambda l, i, z: ol.clews(l, i, z))):
+        z = s["z"].double().cuda().requires_grad_(True)
+        loss, _ = mod(s["label"].cuda(), s["idx"].cuda(), z)
+        loss.backward()
+        zr = s["z"].double().requires_grad_(True)
+        lo, _ = oracle(s["label"].clone(), s["idx"], zr)
+        lo.backward()
+        assert loss.dtype == torch.float64 and z.grad.dtype == torch.float64
+        assert abs(float(loss) - float(lo)) <= 1e-6 * abs(float(lo))
+        assert float((z.grad.cpu() - zr.grad).norm()) <= 1e-5 * float(zr.grad.norm())
+        big = s["label"].cuda() + (1 << 32)                       # equal low 32 bits would alias labels 2^32 apart
+        bad, _ = mod(big, s["idx"].cuda(), s["z"].cuda())
+        assert torch.isnan(bad)
+        bad, _ = mod(s["label"].cuda(), s["idx"].cuda() - (1 << 33), s["z"].cuda())
+        assert torch.isnan(bad)

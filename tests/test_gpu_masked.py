@@ -80,3 +80,18 @@ def test_long_rows_and_half_dtypes():
     out = wt.mmax(xb, mask=m[:, :1000], dim=1)
     assert out.dtype == torch.bfloat16
     assert torch.equal(out, torch.where(m[:, :1000], torch.full_like(xb, -float("inf")), xb).max(dim=1)[0])
+
+
+def test_float64_masked_reductions():
+    """float64 inputs keep their dtype (double accumulators), like the reference's torch ops."""
+    from wealy_b200 import tensor_ops as wt
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(37, 300, generator=g, dtype=torch.float64)
+    m = torch.rand(37, 300, generator=g) < 0.3
+    xc, mc = x.cuda(), m.cuda()
+    inc = (~m).double()
+    assert wt.msum(xc, mask=mc, dim=1).dtype == torch.float64
+    assert (wt.msum(xc, mask=mc, dim=1).cpu() - (x * inc).sum(1)).abs().max() < 1e-12
+    assert (wt.mmean(xc, mask=mc, dim=1).cpu() - (x * inc).sum(1) / inc.sum(1)).abs().max() < 1e-12
+    assert torch.equal(wt.mmin(xc, mask=mc, dim=1).cpu(), torch.where(m, torch.full_like(x, float("inf")), x).min(1).values)
+    assert torch.equal(wt.mmax(xc, mask=mc, dim=1).cpu(), torch.where(m, torch.full_like(x, float("-inf")), x).max(1).values)
