@@ -305,7 +305,7 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
 }
 
 // CTA-pair kernel (gemm_core2.cuh): sh.n_row_blocks / group_rows / rb_stride / rb_offset are in SUPER row blocks
-template <class Epi, int kPasses, int kBlockK, int kEpiWarps = 8>
+template <class Epi, int kPasses, int kBlockK, int kEpiWarps = 8, bool kDyn = false>
 static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename Epi::Params& ep, cudaStream_t s) {
   constexpr int kStages = 4;
   const int il = (sh.sym & 2) ? 2 : 1;  // row stride of the A boxes
@@ -323,7 +323,7 @@ static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename
     maps.a_lo = maps.a_hi;
     maps.b_lo = maps.b_hi;
   }
-  auto kern = gemm_pair_kernel<Epi, kPasses, kBlockK, kEpiWarps, kStages>;
+  auto kern = gemm_pair_kernel<Epi, kPasses, kBlockK, kEpiWarps, kStages, kDyn>;
   constexpr int kSmemBytes = SM::total(kEpiWarps, Epi::kWarpScratchBytes, Epi::kCtaScratchBytes);
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -1126,14 +1126,20 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       }
     } else if (pair) {
       if (env_int("WEALY_PAIR_INTERLEAVE", 1) != 0) sh.sym |= 2;
-      // three epilogue warps per TMEM lane quadrant (the pair's epilogue is the co-limiter; 16 warps were measured worse)
+      // three epilogue warps per TMEM lane quadrant (the pair's epilogue is the co-limiter; 16 warps were measured worse);
+      // WEALY_PAIR_DYN: the warps of a quadrant claim 32-column chunks dynamically instead of owning fixed ones
       const bool w12 = env_int("WEALY_PAIR_EPI_WARPS", 12) == 12;
+      const bool dyn = env_int("WEALY_PAIR_DYN", 1) != 0;
       if (passes == 3) {
         sh.k_blocks = (int)(pq.d_pad / 32);
-        if (w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12>(pq, sh, sp, s)));
+        if (dyn && w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12, true>(pq, sh, sp, s)));
+        else if (dyn) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 8, true>(pq, sh, sp, s)));
+        else if (w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12>(pq, sh, sp, s)));
         else W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32>(pq, sh, sp, s)));
       } else {
-        if (w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 1, 64, 12>(pq, sh, sp, s)));
+        if (dyn && w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 1, 64, 12, true>(pq, sh, sp, s)));
+        else if (dyn) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 1, 64, 8, true>(pq, sh, sp, s)));
+        else if (w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 1, 64, 12>(pq, sh, sp, s)));
         else W_TRY((launch_gemm_pair<EvalSymEpi<3>, 1, 64>(pq, sh, sp, s)));
       }
     } else if (passes == 3) {

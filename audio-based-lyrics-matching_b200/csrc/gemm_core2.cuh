@@ -14,7 +14,13 @@
 //     barriers (cp.async.bulk.tensor.cta_group::2), tcgen05.commit multicasts to the `empty` / `tmem_full`
 //     barriers of both CTAs, the epilogue warps of both CTAs arrive on the leader's `tmem_empty`;
 //   * units are (super row block) x (chunk of column tiles), handed out dynamically by the leader's TMA thread,
-//     which publishes the unit index into the mailboxes of both CTAs (st.shared::cluster + remote mbarrier arrive).
+//     which publishes the unit index into the mailboxes of both CTAs (st.shared::cluster + remote mbarrier arrive);
+//   * kDynChunks: the epilogue warps of a TMEM lane quadrant do not own fixed 32-column chunks of a tile; they CLAIM
+//     the chunks of the unit's tiles one by one from a shared-memory counter (chunk stream g -> tile g / 8, chunk
+//     g % 8).  The rows of a quadrant are the same for all its warps, so any of them can score any chunk; a warp
+//     held up by a hot chunk (deep queue, dirty tile) simply claims fewer, and a fast one runs ahead into the next
+//     tile as soon as its accumulator is ready.  The accumulator hand-over then waits for the SUM of the warps'
+//     work, not for the slowest warp of 2 x kEpiWarps: every chunk arrives on `tmem_empty` on its own.
 #pragma once
 #include "gemm_core.cuh"
 
@@ -33,7 +39,7 @@ struct PairSmem {
   }
 };
 
-template <class Epi, int kPasses, int kBlockK, int kEpiWarps, int kStages>
+template <class Epi, int kPasses, int kBlockK, int kEpiWarps, int kStages, bool kDynChunks = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + kEpiWarps * 32, 1)
 gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, const typename Epi::Params ep) {
   using SM = PairSmem<kPasses, kBlockK, kStages>;
@@ -57,7 +63,9 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
   uint64_t* col_empty = col_full + kColSlots;
   int* unit_slot = reinterpret_cast<int*>(col_empty + kColSlots);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(unit_slot + 2);
-  static_assert((2 * kStages + 8 + 2 * kColSlots) * 8 + 16 <= SM::kBarBytes, "barrier area");
+  int* chunk_ctr = reinterpret_cast<int*>(tmem_slot + 2);      // [2 unit slots][4 quadrants] chunk claim counters
+  static_assert((2 * kStages + 8 + 2 * kColSlots) * 8 + 16 + 32 <= SM::kBarBytes, "barrier area");
+  constexpr int kChunksPerTile = kTileN / kChunkCols;          // per quadrant
   uint8_t* scratch_base = bar_base + SM::kBarBytes;
   uint8_t* col_slots = scratch_base + kEpiWarps * Epi::kWarpScratchBytes + CS::kOffset;
 
@@ -79,14 +87,15 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 2 * kEpiWarps);
+      ptx::mbar_init(&tmem_empty[a], kDynChunks ? 2 * 4 * kChunksPerTile : 2 * kEpiWarps);  // per chunk / per warp
       ptx::mbar_init(&unit_full[a], 1);
       ptx::mbar_init(&unit_empty[a], 2 * kEpiWarps + 2);  // leader: MMA thread + epilogue warps; peer: TMA thread + epilogue warps
     }
     for (int c = 0; c < kColSlots; ++c) {
       ptx::mbar_init(&col_full[c], 1);
-      ptx::mbar_init(&col_empty[c], kEpiWarps);
+      ptx::mbar_init(&col_empty[c], kDynChunks ? 4 * kChunksPerTile : kEpiWarps);
     }
+    for (int k = 0; k < 8; ++k) chunk_ctr[k] = 0;
     ptx::fence_mbar_init();
   }
   if (warp_idx == 1) ptx::tmem_alloc_pair<512>(tmem_slot);
@@ -118,6 +127,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
       const uint32_t peer_unit_full0 = ptx::map_to_cta(&unit_full[0], 1);
       const uint32_t peer_unit_slot0 = ptx::map_to_cta(&unit_slot[0], 1);
       const uint32_t leader_unit_empty0 = ptx::map_to_cta(&unit_empty[0], 0);
+      const uint32_t peer_chunk_ctr0 = ptx::map_to_cta(&chunk_ctr[0], 1);
       while (true) {
         int u;
         if (leader) {
@@ -127,6 +137,13 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
           if (u >= n_units) u = -1;
           unit_slot[us] = u;
           ptx::st_cluster_u32(peer_unit_slot0 + 4u * us, (uint32_t)u);
+          if constexpr (kDynChunks) {
+            // (every consumer of the slot's previous unit has arrived on unit_empty: nobody claims from these any more)
+            for (int k = 0; k < 4; ++k) {
+              chunk_ctr[us * 4 + k] = 0;
+              ptx::st_cluster_u32(peer_chunk_ctr0 + 4u * (us * 4 + k), 0u);
+            }
+          }
           ptx::mbar_arrive(&unit_full[us]);
           ptx::mbar_arrive_cluster(peer_unit_full0 + 8u * us);  // release.cluster: orders the slot write before it
         } else {
@@ -230,11 +247,21 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
     uint32_t cphase = 0;
     const uint32_t leader_unit_empty0 = ptx::map_to_cta(&unit_empty[0], 0);
     const uint32_t leader_tmem_empty0 = ptx::map_to_cta(&tmem_empty[0], 0);
+    unsigned tile_seq = 0;  // kDynChunks: tiles this CTA has been through (every role counts the same)
+    int pending_slot = -1;  // kDynChunks: unit slot whose release is deferred until the unit's chunks are all claimed
     while (true) {
       ptx::mbar_wait_cluster(&unit_full[us], uphase);
       const int u = unit_slot[us];
+      const int us_claim = us;
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(leader_unit_empty0 + 8u * us);
+      if constexpr (kDynChunks) {
+        // the slot's claim counters stay in use for the whole unit: release the PREVIOUS unit's slot now, this one
+        // after its last chunk has been claimed (2-deep mailbox: the producer is then at most one unit ahead)
+        if (pending_slot >= 0 && lane == 0) ptx::mbar_arrive_cluster(leader_unit_empty0 + 8u * pending_slot);
+        pending_slot = us;
+      } else {
+        if (lane == 0) ptx::mbar_arrive_cluster(leader_unit_empty0 + 8u * us);
+      }
       if (++us == 2) { us = 0; uphase ^= 1u; }
       if (u < 0) break;
       int rb, t0, t1;
@@ -254,6 +281,47 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
       ctx.col_step = kHalves * kChunkCols;
       ctx.col_slot = nullptr;
       Epi::row_begin(ep, rs, row, 0, shape, ctx);
+      if constexpr (kDynChunks) {
+        // chunk stream of this quadrant: g -> (tile g / 8, chunk g % 8); tiles are numbered through the CTA's
+        // lifetime (tile_seq) so that barrier slots and phases follow from the number alone
+        const int n_tiles = t1 - t0;
+        const int total = n_tiles * kChunksPerTile;
+        int* ctr = &chunk_ctr[us_claim * 4 + quad];
+        int cur = -1, a_cur = 0, c_cur = 0;
+        while (true) {
+          int g = 0;
+          if (lane == 0) g = atomicAdd(ctr, 1);
+          g = __shfl_sync(0xffffffffu, g, 0);
+          if (g >= total) break;
+          const int tile = g / kChunksPerTile, c = g - tile * kChunksPerTile;
+          if (tile != cur) {
+            if (cur >= 0) Epi::tile_end(ep, rs, shape, ctx);
+            const unsigned seq = tile_seq + (unsigned)tile;
+            a_cur = (int)(seq & 1u);
+            c_cur = (int)(seq % (unsigned)kColSlots);
+            ptx::mbar_wait_warp(&col_full[c_cur], (seq / (unsigned)kColSlots) & 1u);
+            ctx.col_slot = col_slots + c_cur * CS::kBytes;
+            Epi::tile_begin(ep, rs, shape, ctx, t0 + tile);
+            if (lane == 0) ptx::mbar_wait_cluster(&tmem_full[a_cur], (seq >> 1) & 1u);
+            __syncwarp();
+            ptx::tc_fence_after_sync();
+            cur = tile;
+          }
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a_cur * kTileN);
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + (uint32_t)(c * kChunkCols), v);
+          ptx::tmem_ld_wait();
+          Epi::chunk32(ep, rs, row, (t0 + tile) * kTileN + c * kChunkCols, v, shape, ctx);
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::mbar_arrive_cluster(leader_tmem_empty0 + 8u * a_cur);
+            ptx::mbar_arrive(&col_empty[c_cur]);
+          }
+        }
+        if (cur >= 0) Epi::tile_end(ep, rs, shape, ctx);
+        tile_seq += (unsigned)n_tiles;
+      } else {
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&col_full[cs], cphase);
         ctx.col_slot = col_slots + cs * CS::kBytes;
@@ -277,6 +345,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         if (++cs == kColSlots) { cs = 0; cphase ^= 1u; }
         Epi::tile_end(ep, rs, shape, ctx);
+      }
       }
       Epi::row_end(ep, rs, row, 0, shape, ctx);
     }

@@ -390,7 +390,8 @@ def leg_c4(dev, peaks):
     else:
         out["cpu_kind"] = "port (oracle/losses.py, fp32, all host cores)"
         cpu_fns = {"ntxent": lambda z: ol.ntxent(lab_c.clone(), idx_c, z, 0.1)[0], "clews": lambda z: ol.clews(lab_c.clone(), idx_c, z)[0]}
-    for name, mod in (("ntxent", wl.NTXentLoss(0.1)), ("clews", wl.CLEWSLoss())):
+    # (loss_dtype = fp32: the unrounded value; by default the modules round the loss to z's dtype like the reference)
+    for name, mod in (("ntxent", wl.NTXentLoss(0.1, loss_dtype=torch.float32)), ("clews", wl.CLEWSLoss(loss_dtype=torch.float32))):
         fn = cpu_fns[name]
         f, lv = lb.gpu_time(mod, s, 20, False, flush)
         fb, _ = lb.gpu_time(mod, s, 20, True, flush)

@@ -102,7 +102,7 @@ def test_every_mode_is_differentiable(mode, dtype):
     y = torch.randn(70, 48, generator=g).to(dtype)
     y[3] = x[5]                                            # a zero-distance pair
     w = torch.randn(90, 70, generator=g)
-    xr, yr = x.double().requires_grad_(True), y.double().requires_grad_(True)
+    xr, yr = x.double().clone().requires_grad_(True), y.double().clone().requires_grad_(True)
     (osim.distance_matrix(xr, yr, mode=mode) * w.double()).sum().backward()
     xc, yc = x.cuda().requires_grad_(True), y.cuda().requires_grad_(True)
     out = wt.pairwise_distance_matrix(xc, yc, mode=mode)
