@@ -478,7 +478,7 @@ def run_gpu_arm(args):
 
     n_total = int(args.tracks) if args.tracks else int(round(BASE_N * (world ** 0.5)))
     lo, hi = wd.shard_range(n_total, rank, world)
-    s = synth.make_eval_set(n_total, DIM, seed=0, device=dev, md5_ids=False)
+    s = synth.make_eval_set(n_total, DIM, seed=0, device=dev, md5_ids=False, **({"sigma": args.sigma} if args.sigma else {}))
     z, c, i = s["z"], s["c"], s["i"]
     nq = n_total if world == 1 else (hi - lo)          # queries whose row blocks this rank sweeps (about)
     pairs_total = float(n_total) * float(n_total)
@@ -686,6 +686,9 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("WEALY_PRECISION", "fp16x3"), choices=["fp16x3", "fp16"])
     ap.add_argument("--cpu-queries", type=int, default=512, help="queries in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity legs")
+    ap.add_argument("--sigma", type=float, default=0.0,
+                    help="within-clique noise of the synthetic embeddings (default 2.4: MAP ~0.67; larger = harder data, "
+                         "more candidates above the relevant items; diagnostic only)")
     ap.add_argument("--legs", default="main,c1,c3,c4,c5",
                     help="which BASELINE configs to run besides the headline (c1, c3, c4, c5); 'main' = headline only")
     args = ap.parse_args()
