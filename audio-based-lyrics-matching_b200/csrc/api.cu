@@ -868,7 +868,8 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   // ... with top-k (topk_sym_kernels.cuh): a sampled pre-pass bounds every query's k-th best similarity from below, the
   // sweep appends what lies above the bound to per-query lists in both directions.  Worth it (and statistically sound)
   // for large sets and moderate k; everything else keeps the rectangle sweep with its streaming top-k.
-  const bool sym_topk = can_sym && topk > 0 && topk <= 128 && nq >= env_int("WEALY_SYM_TOPK_MIN_ROWS", 16384) && finish &&
+  const bool sym_topk = can_sym && topk > 0 && topk <= 128 && nq >= env_int("WEALY_SYM_TOPK_MIN_ROWS", 16384) &&
+                        nq >= 192ll * topk && finish &&
                         shard_world == 1 && allow_sym_topk && env_int("WEALY_SYM_TOPK", 1) != 0;
   const bool sym = can_sym && (topk == 0 ? (shard_world > 1 || env_int("WEALY_SYM", 1) != 0) : sym_topk);
   if (shard_world > 1 && !sym)
@@ -941,37 +942,27 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   int tk_cap2 = 0;
   if (sym_topk) {
     const int n = (int)nq, rows = (int)rows_q;
-    // sample ~N/16 rows (>= 4096): the pre-pass is one fp16 pass of N x S pairs, L2-bandwidth bound.  r-th best of the
-    // sample with r = 3 k S / N (>= 24): about max(3 k, 24 N / S) corpus candidates lie above it; the count's relative
-    // spread is 1 / sqrt(r), the lists hold mean + 8 sigma.
+    // sample ~N/16 rows (>= 4096): the pre-pass is one fp16 pass of N x S pairs.  Target: t = max(24, 3 k S / N) of the
+    // sample's similarities above the bound, i.e. about t N / S >= 3 k of the corpus; the bound is the m-th largest of
+    // the G = S / 32 group maxima, and the top t of S values occupy about G (1 - exp(-t / G)) distinct groups.
     int S = (int)ceil_div(nq / 16, kTileN) * kTileN;
     if (S < 4096) S = 4096;
-    if (S > n) S = n;
-    int r = (int)ceil(3.0 * topk * (double)S / (double)n);
-    if (r < 24) r = 24;
-    if (r > 64) {  // the bound kernel merges <= 4 lists of <= 256 entries: shrink the sample instead
-      S = (int)((64.0 * n) / (3.0 * topk)) / kTileN * kTileN;
-      r = 64;
-    }
-    const double fr = (double)S / (double)n;
-    const double mean = r / fr, sd = sqrt(r * (1.0 - fr)) / fr;
+    if (S > 32768) S = 32768;
+    if (S > n) S = n / kTileN * kTileN;
+    const double fr = (double)S / (double)n, G = (double)(S / kChunkCols);
+    double t = 3.0 * topk * fr;
+    if (t < 24.0) t = 24.0;
+    const int r = (int)ceil(G * (1.0 - exp(-t / G)));
+    const double mean = t / fr, sd = 1.15 * sqrt(t * (1.0 - fr)) / fr;
     tk_cap2 = (int)align_up((size_t)(mean + 8.0 * sd + 32.0), 32);
     if (tk_cap2 > 1024) tk_cap2 = 1024;
-    const int cap_r = topk_capacity(r);  // 256 for r <= 64
-    const int parts_r = 4;
+    const int n_groups = S / kChunkCols;
     // carve the scratch
     size_t need_tk = 0;
     auto reserve = [&](size_t bytes) { const size_t o = need_tk; need_tk += align_up(bytes, 1024); return o; };
     const size_t o_samp = reserve((size_t)S * pq.d_pad * 2);
-    const size_t o_si = reserve((size_t)S * 4);
-    const size_t o_qi = reserve((size_t)rows * 4);
-    const size_t o_lim = reserve((size_t)rows * 4);
-    const size_t o_zi = reserve((size_t)(rows > S ? rows : S) * 4);
-    const size_t o_zl = reserve(((size_t)rows + 1) * 8);
+    const size_t o_gmax = reserve((size_t)rows * n_groups * 4);
     const size_t o_beta = reserve((size_t)rows * 4);
-    const size_t o_cv = reserve((size_t)parts_r * rows * cap_r * 4);
-    const size_t o_ci = reserve((size_t)parts_r * rows * cap_r * 4);
-    const size_t o_cc = reserve((size_t)parts_r * rows * 4);
     const size_t o_tv = reserve((size_t)rows * tk_cap2 * 4);
     const size_t o_ti = reserve((size_t)rows * tk_cap2 * 4);
     const size_t o_tc = reserve((size_t)rows * 4);
@@ -985,53 +976,28 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     }
     uint8_t* tb = reinterpret_cast<uint8_t*>(align_up((size_t)p->tks_buf, 1024));
     __half* samp = reinterpret_cast<__half*>(tb + o_samp);
-    int* samp_i = reinterpret_cast<int*>(tb + o_si);
-    int* qi_plane = reinterpret_cast<int*>(tb + o_qi);
-    float* lim_inf = reinterpret_cast<float*>(tb + o_lim);
-    int* zeros_i = reinterpret_cast<int*>(tb + o_zi);
-    long long* zeros_ll = reinterpret_cast<long long*>(tb + o_zl);
+    float* gmax = reinterpret_cast<float*>(tb + o_gmax);
     tk_beta = reinterpret_cast<float*>(tb + o_beta);
-    float* cv = reinterpret_cast<float*>(tb + o_cv);
-    int* ci = reinterpret_cast<int*>(tb + o_ci);
-    int* cc = reinterpret_cast<int*>(tb + o_cc);
     tk_val = reinterpret_cast<float*>(tb + o_tv);
     tk_idx = reinterpret_cast<int*>(tb + o_ti);
     tk_cnt = reinterpret_cast<int*>(tb + o_tc);
     tk_fail = reinterpret_cast<int*>(tb + o_fail);
     const int T = 256;
-    CU_TRY(cudaMemsetAsync(zeros_i, 0, (size_t)(rows > S ? rows : S) * 4, s));
-    CU_TRY(cudaMemsetAsync(cc, 0, (size_t)parts_r * rows * 4, s));
     CU_TRY(cudaMemsetAsync(tk_fail, 0, 4, s));
-    sample_rows_kernel<<<(unsigned)ceil_div((int64_t)S * 32, T), T, 0, s>>>(pq.hi, (int)pq.d_pad, n, S, p->s_i, samp, samp_i);
-    plane_ids_kernel<<<(unsigned)ceil_div(rows + 1, T), T, 0, s>>>(p->s_i, n, rows, qi_plane, lim_inf, zeros_i, zeros_ll);
+    sample_rows_kernel<<<(unsigned)ceil_div((int64_t)S * 32, T), T, 0, s>>>(pq.hi, (int)pq.d_pad, n, S, samp);
     CU_TRY(cudaGetLastError());
     Planes pa = pq, pb;
     pa.lo = nullptr;
     pb.hi = samp; pb.lo = nullptr; pb.rows = S; pb.d_pad = pq.d_pad;
     pb.norm = pb.scale = pb.sq = nullptr;
     GemmShape shp;
-    fill_shape(shp, rows, S, pq.d_pad, 64, 2, 0);
-    EvalParams pe;
-    memset(&pe, 0, sizeof(pe));
-    pe.lim = lim_inf;
-    pe.q_c = zeros_i;
-    pe.q_i = qi_plane;
-    pe.c_c = zeros_i;
-    pe.c_i = samp_i;
-    pe.thr = p->thr;
-    pe.off = zeros_ll;
-    pe.cnt = zeros_i;
-    pe.hist = p->hist;
-    pe.topk = r;
-    pe.cap = cap_r;
-    pe.nq_total = rows;
-    pe.cand_val = cv;
-    pe.cand_idx = ci;
-    pe.cand_cnt = cc;
-    if (shp.n_col_chunks * 2 > parts_r) return fail(WEALY_ERR_UNSUPPORTED, "top-k pre-pass: %d parts", shp.n_col_chunks * 2);
-    W_TRY(launch_gemm<EvalEpi>(1, pa, pb, shp, pe, s));
-    topk_beta_kernel<<<(unsigned)ceil_div(p->s_padded * 32, 128), 128, 0, s>>>(cv, cc, shp.n_col_chunks * 2, rows, cap_r, r, n, tk_beta,
-                                                                              p->s_lvl, (int)p->s_padded, tk_cnt);
+    fill_shape(shp, rows, S, pq.d_pad, 64, 1 << 20, 8);
+    GroupMaxParams gp;
+    gp.gmax = gmax;
+    gp.n_groups = n_groups;
+    W_TRY(launch_gemm<GroupMaxEpi>(1, pa, pb, shp, gp, s));
+    topk_beta_kernel<<<(unsigned)ceil_div(p->s_padded * 32, 128), 128, 0, s>>>(gmax, n_groups, rows, r + 1, n, tk_beta, p->s_lvl,
+                                                                              (int)p->s_padded, tk_cnt);
     CU_TRY(cudaGetLastError());
   }
   p->last_topk_path = topk > 0 ? (sym_topk ? 1 : 2) : 0;

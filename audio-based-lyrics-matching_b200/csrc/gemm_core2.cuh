@@ -149,7 +149,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
         } else {
           ptx::mbar_wait_cluster(&unit_full[us], uphase);
           u = unit_slot[us];
-          ptx::mbar_arrive_cluster(leader_unit_empty0 + 8u * us);
+          ptx::mbar_arrive_cluster_relaxed(leader_unit_empty0 + 8u * us);
         }
         if (++us == 2) { us = 0; uphase ^= 1u; }
         if (u < 0) break;
@@ -250,17 +250,17 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
     unsigned tile_seq = 0;  // kDynChunks: tiles this CTA has been through (every role counts the same)
     int pending_slot = -1;  // kDynChunks: unit slot whose release is deferred until the unit's chunks are all claimed
     while (true) {
-      ptx::mbar_wait_cluster(&unit_full[us], uphase);
+      ptx::mbar_wait_cluster_warp(&unit_full[us], uphase);
       const int u = unit_slot[us];
       const int us_claim = us;
       __syncwarp();
       if constexpr (kDynChunks) {
         // the slot's claim counters stay in use for the whole unit: release the PREVIOUS unit's slot now, this one
         // after its last chunk has been claimed (2-deep mailbox: the producer is then at most one unit ahead)
-        if (pending_slot >= 0 && lane == 0) ptx::mbar_arrive_cluster(leader_unit_empty0 + 8u * pending_slot);
+        if (pending_slot >= 0 && lane == 0) ptx::mbar_arrive_cluster_relaxed(leader_unit_empty0 + 8u * pending_slot);
         pending_slot = us;
       } else {
-        if (lane == 0) ptx::mbar_arrive_cluster(leader_unit_empty0 + 8u * us);
+        if (lane == 0) ptx::mbar_arrive_cluster_relaxed(leader_unit_empty0 + 8u * us);
       }
       if (++us == 2) { us = 0; uphase ^= 1u; }
       if (u < 0) break;
@@ -302,8 +302,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
             ptx::mbar_wait_warp(&col_full[c_cur], (seq / (unsigned)kColSlots) & 1u);
             ctx.col_slot = col_slots + c_cur * CS::kBytes;
             Epi::tile_begin(ep, rs, shape, ctx, t0 + tile);
-            if (lane == 0) ptx::mbar_wait_cluster(&tmem_full[a_cur], (seq >> 1) & 1u);
-            __syncwarp();
+            ptx::mbar_wait_cluster_warp(&tmem_full[a_cur], (seq >> 1) & 1u);
             ptx::tc_fence_after_sync();
             cur = tile;
           }
@@ -315,7 +314,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
           ptx::tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) {
-            ptx::mbar_arrive_cluster(leader_tmem_empty0 + 8u * a_cur);
+            ptx::mbar_arrive_cluster_relaxed(leader_tmem_empty0 + 8u * a_cur);
             ptx::mbar_arrive(&col_empty[c_cur]);
           }
         }
@@ -323,10 +322,10 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
         tile_seq += (unsigned)n_tiles;
       } else {
       for (int t = t0; t < t1; ++t) {
-        ptx::mbar_wait(&col_full[cs], cphase);
+        ptx::mbar_wait_warp(&col_full[cs], cphase);
         ctx.col_slot = col_slots + cs * CS::kBytes;
         Epi::tile_begin(ep, rs, shape, ctx, t);
-        ptx::mbar_wait_cluster(&tmem_full[acc], acc_phase);
+        ptx::mbar_wait_cluster_warp(&tmem_full[acc], acc_phase);
         ptx::tc_fence_after_sync();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kTileN);
 #pragma unroll 1
@@ -339,7 +338,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {
-          ptx::mbar_arrive_cluster(leader_tmem_empty0 + 8u * acc);
+          ptx::mbar_arrive_cluster_relaxed(leader_tmem_empty0 + 8u * acc);
           ptx::mbar_arrive(&col_empty[cs]);
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }

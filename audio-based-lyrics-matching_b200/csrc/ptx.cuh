@@ -231,6 +231,13 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// The same without release semantics: for hand-overs that publish nothing through memory (an epilogue warp telling the
+// MMA thread that it has read its accumulator chunk: the tcgen05.ld data already sits in registers).  The release
+// form compiles to MEMBAR.ALL.GPU + ERRBAR and waits for every outstanding global RED of the warp -- measured as
+// 12 % of all stall samples of the pair kernel.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void st_cluster_u32(uint32_t cluster_addr, uint32_t v) {
   asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(cluster_addr), "r"(v) : "memory");
 }
@@ -240,14 +247,15 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   int polls = 0;
   while (true) {
     uint32_t ok;
+    // (with the suspend-time hint of mbar_try_wait: an un-hinted poll loop was 25 % of the pair kernel's instructions)
     asm volatile(
         "{\n"
         ".reg .pred P;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, P;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)(WEALY_WAIT_HINT_NS > 0 ? WEALY_WAIT_HINT_NS : 1))
         : "memory");
     if (ok) return;
     if ((++polls & 63) == 0 && clock64() - t0 > WEALY_DEADLOCK_CYCLES) {
@@ -256,6 +264,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
       __trap();
     }
   }
+}
+
+// a whole warp waiting on a cluster-scope barrier: one lane polls (see mbar_wait_warp)
+__device__ __forceinline__ void mbar_wait_cluster_warp(uint64_t* bar, uint32_t parity) {
+  if (lane_id() == 0) mbar_wait_cluster(bar, parity);
+  __syncwarp();
 }
 
 // 2-D tiled load issued by either CTA of a pair; completion bytes are counted on the barrier at `leader_bar_addr`

@@ -7,9 +7,10 @@
 // there is a STATIC per-query lower bound beta_q of the k-th best similarity, known before the sweep starts:
 //
 //   1. sample:   S candidates, evenly spaced in clique-sorted order (S ~ N / 16, at least 4096);
-//   2. pre-pass: every query against the sample with the rectangle kernel's streaming top-r (one fp16 pass: the
-//                bound does not have to be exact), r = max(24, 3 k S / N), so that about 3 k candidates of the whole
-//                corpus lie above the sample's r-th best (relative spread of that count: 1 / sqrt(r));
+//   2. pre-pass: every query against the sample in one fp16 pass (the bound does not have to be exact) with an epilogue
+//                that keeps the maximum of every 32-column group; beta_q = the (r + 1)-th largest group maximum, a lower
+//                bound of the sample's (r + 1)-th best, r = max(24, 3 k S / N): about 3 k candidates of the whole
+//                corpus lie above it (relative spread of that count: 1 / sqrt(r));
 //   3. sweep:    EvalSymEpi<..., kTopk = true> appends every element above beta_row / beta_col to the row's / the
 //                column's list (atomic cursor; lists hold 3 k + 8 sigma entries);
 //   4. finalize: per query, select the k best of its list, order them, translate plane rows to the caller's indices.
@@ -21,10 +22,9 @@
 namespace wealy {
 
 // rows of the sample: sorted positions k * n / S, k = 0 .. S - 1 (distinct for S <= n) -> their plane rows copied into
-// a dense [S][d_pad] operand (hi plane only: the pre-pass runs one fp16 pass); ids for the self test
+// a dense [S][d_pad] operand (hi plane only: the pre-pass runs one fp16 pass)
 __global__ void __launch_bounds__(256) sample_rows_kernel(const __half* __restrict__ hi, int d_pad, int n, int n_sample,
-                                                          const int* __restrict__ s_i, __half* __restrict__ out,
-                                                          int* __restrict__ out_i) {
+                                                          __half* __restrict__ out) {
   const int k = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (k >= n_sample) return;
@@ -32,28 +32,38 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const __half* __restri
   const uint4* src = reinterpret_cast<const uint4*>(hi + (long long)spread_plane_of(srow) * d_pad);
   uint4* dst = reinterpret_cast<uint4*>(out + (long long)k * d_pad);
   for (int v = lane; v < (d_pad >> 3); v += 32) dst[v] = __ldg(src + v);
-  if (lane == 0) out_i[k] = s_i[srow];
 }
 
-// per-plane-row arrays the rectangle epilogue wants for the pre-pass: version id of the row (by sorted index),
-// "no relevant item" limits (+inf: the pre-pass does no rank counting), zero counts / offsets
-__global__ void plane_ids_kernel(const int* __restrict__ s_i, int n, int n_rows, int* __restrict__ qi_plane,
-                                 float* __restrict__ lim_inf, int* __restrict__ zeros_i, long long* __restrict__ zeros_ll) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p > n_rows) return;
-  zeros_ll[p] = 0;
-  if (p == n_rows) return;
-  const int srow = spread_sorted_of(p);
-  qi_plane[p] = srow < n ? s_i[srow] : -1;
-  lim_inf[p] = __int_as_float(0x7f800000);
-  zeros_i[p] = 0;
-}
+// Pre-pass epilogue: the maximum of every 32-column chunk ("group") of the sample, per query row -- one FMNMX per
+// element, no lists, no ids.  The m-th largest of a row's group maxima is one of the sample's similarities with at
+// least m - 1 others above it, hence a LOWER bound of the sample's m-th best (and, the top few of thousands rarely
+// sharing a group, nearly equal to it).
+struct GroupMaxParams {
+  float* gmax;   // [rows][n_groups]
+  int n_groups;  // sample columns / 32
+};
+struct GroupMaxEpi {
+  using Params = GroupMaxParams;
+  static constexpr int kWarpScratchBytes = 0;
+  static constexpr int kCtaScratchBytes = 0;
+  struct RowState {};
+  __device__ static __forceinline__ void row_begin(const Params&, RowState&, int, int, const GemmShape&, const EpiCtx&) {}
+  __device__ static __forceinline__ void chunk32(const Params& p, RowState&, int row, int col0, const uint32_t (&acc)[32],
+                                                 const GemmShape& sh, const EpiCtx&) {
+    float m = __uint_as_float(acc[0]);
+#pragma unroll
+    for (int e = 1; e < 32; ++e) m = fmaxf(m, __uint_as_float(acc[e]));
+    if (row < sh.m_rows && col0 < sh.n_cols) p.gmax[(long long)row * p.n_groups + (col0 >> 5)] = m;
+  }
+  __device__ static __forceinline__ void tile_begin(const Params&, RowState&, const GemmShape&, const EpiCtx&, int) {}
+  __device__ static __forceinline__ void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&) {}
+  __device__ static __forceinline__ void row_end(const Params&, RowState&, int, int, const GemmShape&, const EpiCtx&) {}
+};
 
-// beta[p] = r-th best similarity of plane row p against the sample (from the pre-pass's candidate lists), also written
-// into lvl[p].w where the sweep's per-tile column slots pick it up; padded rows keep +inf; a row with fewer than r
-// candidates gets -inf (everything passes: its list overflows and the call falls back).  parts * cap <= 1024.
-__global__ void __launch_bounds__(128) topk_beta_kernel(const float* __restrict__ cand_val, const int* __restrict__ cand_cnt,
-                                                        int parts, int n_rows, int cap, int r, int n,
+// beta[p] = the m-th largest group maximum of plane row p (m = r + 1: the query itself may sit in the sample with
+// similarity 1 and is simply skipped over), also written into lvl[p].w where the sweep's per-tile column slots pick it
+// up; padded rows keep +inf.  n_groups <= 1024.
+__global__ void __launch_bounds__(128) topk_beta_kernel(const float* __restrict__ gmax, int n_groups, int n_rows, int m, int n,
                                                         float* __restrict__ beta, float4* __restrict__ lvl, int n_lvl,
                                                         int* __restrict__ tk_cnt) {
   __shared__ float sv_all[4][1024];
@@ -66,28 +76,12 @@ __global__ void __launch_bounds__(128) topk_beta_kernel(const float* __restrict_
   if (lane == 0 && p < n_rows) tk_cnt[p] = 0;
   float b = __int_as_float(0x7f800000);
   if (p < n_rows && spread_sorted_of(p) < n) {
-    int m = 0;
-    for (int part = 0; part < parts; ++part) {
-      const long long base = ((long long)part * n_rows + p) * cap;
-      const int np = min(cand_cnt[(long long)part * n_rows + p], cap);
-      for (int e = lane; e < np; e += 32) {
-        sv[m + e] = cand_val[base + e];
-        si[m + e] = e;
-      }
-      m += np;
+    for (int e = lane; e < n_groups; e += 32) {
+      sv[e] = gmax[(long long)p * n_groups + e];
+      si[e] = e;
     }
     __syncwarp();
-    if (m > r) {
-      b = warp_select_topk<32>(sv, si, m, r, lane);
-    } else if (m == r) {
-      float lo = __int_as_float(0x7f800000);
-      for (int e = lane; e < m; e += 32) lo = fminf(lo, sv[e]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-      b = lo;
-    } else {
-      b = __int_as_float(0xff800000);
-    }
+    b = n_groups > m ? warp_select_topk<32>(sv, si, n_groups, m, lane) : __int_as_float(0xff800000);
   }
   if (lane == 0) {
     if (p < n_rows) beta[p] = b;

@@ -153,7 +153,7 @@ int wealy_eval_plan_ranks(const wealy_eval_plan* plan, int64_t* offsets, int32_t
 /* device time (CUDA events on the run's stream) of the fused similarity+ranking sweep of the last
  * wealy_eval_run on this plan; blocks until that sweep has finished.                           */
 int wealy_eval_plan_last_sweep_ms(const wealy_eval_plan* plan, float* ms);
-/* which kernel produced the top-k lists of the last run: 0 none, 1 the symmetric sweep (all-vs-all, N >= 16384,
+/* which kernel produced the top-k lists of the last run: 0 none, 1 the symmetric sweep (all-vs-all, N >= max(16384, 192 k),
  * k <= 128: sampled per-query bounds, candidates collected in both directions; synchronises the stream once to read a
  * 4-byte overflow flag), 2 the rectangle sweep with its streaming top-k, 3 = 1 failed its check and 2 recomputed.  */
 int wealy_eval_plan_last_topk_path(const wealy_eval_plan* plan, int* path);
