@@ -77,6 +77,8 @@ SIGNATURES = {
     "wealy_loss_dp_workspace_bytes": (c_sz, [c_i64, c_i64, c_int, c_i64]),
     "wealy_loss_dp_forward_local": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_i64,
                                             c_i64, c_vp, c_sz, c_vp]),
+    "wealy_loss_dp_forward_phase": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_i64,
+                                            c_i64, c_int, c_vp, c_sz, c_vp]),
     "wealy_loss_dp_buffers": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_sz, c_i64, c_i64, c_i64, ctypes.POINTER(c_vp),
                                       ctypes.POINTER(c_i64), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
     "wealy_loss_dp_forward_finish": (c_int, [ctypes.POINTER(LossCfg), c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),

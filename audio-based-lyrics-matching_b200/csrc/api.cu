@@ -273,6 +273,9 @@ static void fill_shape(GemmShape& sh, int64_t m, int64_t n, int64_t d_pad, int b
   sh.rb_stride = 1;
   sh.rb_offset = 0;
   sh.unit_counter = nullptr;
+  sh.win0 = 0;
+  sh.win1 = 0x7fffffff;
+  sh.skip0 = sh.skip1 = 0;
 }
 
 template <class Epi, int kPasses, int kBlockK, int kEpiWarps, int kMaxStages = 8>
@@ -1049,7 +1052,9 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     CU_TRY(cudaMemsetAsync(ep.cand_cnt, 0, (size_t)parts * nq * 4, s));
   }
   CU_TRY(cudaEventRecord(p->ev0, s));
-  const bool pair = sym && !sym_topk && env_int("WEALY_SYM_PAIR", 0) != 0;   // CTA-pair (cta_group::2) kernel
+  // CTA-pair (cta_group::2) kernel: the default for the symmetric sweep (half the B-operand shared-memory traffic;
+  // WEALY_SYM_PAIR=0 selects the single-CTA kernel)
+  const bool pair = sym && env_int("WEALY_SYM_PAIR", 1) != 0;
   const int total_rb = sh.n_row_blocks;
   if (pair) {
     // the pair kernel works on super row blocks (two adjacent row blocks per CTA pair)
@@ -1083,7 +1088,16 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     sp.tk_cnt = tk_cnt;
     sp.tk_cap = tk_cap2;
     const int lv = env_int("WEALY_SYM_LEVELS", 3);  // 3 measured best at C2 (2: 26.8 ms, 3: 25.5 ms, 4: 25.9 ms per step)
-    if (sym_topk) {
+    if (sym_topk && pair) {
+      // (8 epilogue warps: the top-k epilogue needs 160 registers per thread)
+      if (env_int("WEALY_PAIR_INTERLEAVE", 1) != 0) sh.sym |= 2;
+      if (passes == 3) {
+        sh.k_blocks = (int)(pq.d_pad / 32);
+        W_TRY((launch_gemm_pair<EvalSymEpi<3, 256, 4096, true>, 3, 32, 8, true>(pq, sh, sp, s)));
+      } else {
+        W_TRY((launch_gemm_pair<EvalSymEpi<3, 256, 4096, true>, 1, 64, 8, true>(pq, sh, sp, s)));
+      }
+    } else if (sym_topk) {
       if (passes == 3) {
         sh.k_blocks = (int)(pq.d_pad / 32);
         W_TRY((launch_gemm_t<EvalSymEpi<3, 256, 4096, true>, 3, 32, 8, 3>(pq, pc, sh, sp, s)));

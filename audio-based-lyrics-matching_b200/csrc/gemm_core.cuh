@@ -56,7 +56,15 @@ struct GemmShape {
   int sym;              // symmetric all-vs-all: only tiles that reach above the diagonal are computed
   int rb_stride;        // multi-GPU symmetric sweep: this launch owns row blocks rb_offset + k * rb_stride
   int rb_offset;        //   (n_row_blocks counts the owned ones)
+  // column-tile window of this launch: only tiles in [win0, win1) and outside [skip0, skip1) are contracted (the
+  // data-parallel losses sweep the rank's own column block while the other ranks' rows are still in flight, then
+  // everything but that block); the defaults of fill_shape select every tile
+  int win0, win1, skip0, skip1;
 };
+
+__device__ __forceinline__ bool tile_selected(const GemmShape& sh, int t) {
+  return t >= sh.win0 && t < sh.win1 && !(t >= sh.skip0 && t < sh.skip1);
+}
 
 // First column tile a row block needs in symmetric mode: tile t holds columns [256 t, 256 t + 256) and row
 // block rb rows [128 rb, 128 rb + 128); it contains an element with col > row iff t >= rb / 2.
@@ -222,6 +230,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
         const int t1 = min((chunk + 1) * shape.tiles_per_chunk, shape.n_col_tiles);
         const int t0 = first_tile(shape, rb, chunk * shape.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
+          if (!tile_selected(shape, t)) continue;
           if constexpr (kColSlots > 0) {
             // per-tile column data of the epilogue: contiguous arrays indexed by column -> 1-D bulk copies
             ptx::mbar_wait(&col_empty[cs], cphase ^ 1u);
@@ -275,6 +284,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
         const int t1 = min((chunk + 1) * shape.tiles_per_chunk, shape.n_col_tiles);
         const int t0 = first_tile(shape, rb, chunk * shape.tiles_per_chunk);
         for (int t = t0; t < t1; ++t) {
+          if (!tile_selected(shape, t)) continue;
           ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);  // epilogue has drained this accumulator
           ptx::tc_fence_after_sync();
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTileN);
@@ -342,6 +352,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
       ctx.col_slot = nullptr;
       Epi::row_begin(ep, rs, row, part, shape, ctx);
       for (int t = t0; t < t1; ++t) {
+        if (!tile_selected(shape, t)) continue;
         if constexpr (kColSlots > 0) {
           ptx::mbar_wait_warp(&col_full[cs], cphase);
           ctx.col_slot = col_slots + cs * CS::kBytes;

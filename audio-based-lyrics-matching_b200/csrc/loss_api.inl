@@ -38,7 +38,9 @@ static void loss_ws_layout(LossWs& w, uint8_t* base, int64_t b, int64_t d, int p
   w.du = reinterpret_cast<float*>(cur); cur += align_up((size_t)nb * d * 4, 1024);
   const size_t b256 = (size_t)ceil_div(b, kTileN) * kTileN;  // per-tile bulk copies read whole 256-column groups
   w.lab_idx = reinterpret_cast<int2*>(cur); cur += align_up(b256 * 8, 256);
-  w.parts_max = (int)ceil_div(b, kTileN) * 2;
+  // partial records: 2 per column tile (one per epilogue warp of a lane quadrant), for the whole-batch sweep plus --
+  // when the forward is split into "own column block first, the rest behind the all-gather" -- the own block's sweep
+  w.parts_max = (int)(ceil_div(b, kTileN) + ceil_div(nb, kTileN)) * 2;
   w.partial = reinterpret_cast<float*>(cur); cur += align_up((size_t)w.parts_max * nb * kStatWidth * 4, 1024);
   w.rowstat = reinterpret_cast<float*>(cur); cur += align_up(b256 * 16, 256);
   w.zs = reinterpret_cast<ZStats*>(cur); cur += 256;
@@ -118,31 +120,73 @@ static Planes plane_rows(const Planes& p, int64_t row0, int64_t nb) {
 }
 
 // forward, part 1 (everything before the batch-wide sums are known): ids, prep of ALL rows, statistics sweep of the
-// anchors [row0, row0 + nb) against all b columns, per-anchor merge -> rowstat[row0 .. row0 + nb), partial sums in acc
+// anchors [row0, row0 + nb) against all b columns, per-anchor merge -> rowstat[row0 .. row0 + nb), partial sums in acc.
+// phase 0: all of it.  Split form for the data-parallel path (the other ranks' rows arrive by all-gather):
+//   phase 1: ids + prep of the rank's OWN rows + sweep of its anchors against its own column block -- needs nothing
+//            from the other ranks, runs while the all-gather is in flight;
+//   phase 2: prep of the other rows + sweep against every other column block + merge.
+// (own block not aligned to the 256-column tiles: phase 1 only packs the ids, phase 2 does everything.)
 static int loss_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
                               const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb, void* workspace,
-                              size_t workspace_bytes, cudaStream_t s) {
+                              size_t workspace_bytes, cudaStream_t s, int phase = 0) {
   W_TRY(loss_check(cfg, z, b, d, workspace, workspace_bytes, row0, nb));
   if (!z_label || !z_idx) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (phase < 0 || phase > 2) return fail(WEALY_ERR_BAD_ARG, "phase must be 0, 1 or 2");
   LossWs w;
   loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes, nb);
   const int T = 256;
-  CU_TRY(cudaMemsetAsync(w.zs, 0, 1280, s));  // ZStats, scal, flags, batch accumulators
-  pack_ids_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, (const long long*)z_idx, w.lab_idx, (int)b,
-                                                        w.bad);
-  CU_TRY(cudaGetLastError());
   const bool ntx = cfg->kind == WEALY_LOSS_NTXENT;
-  // NT-Xent: x/(|x|+1e-6) and statistics of the raw z; CLEWS: F.normalize (eps 1e-12), statistics of the normalised z
-  W_TRY(launch_prep(z, ldz, b, d, dtype, ntx ? kPrepL2AddEps : kPrepL2Clamp, ntx ? 1e-6f : 1e-12f, w.u, nullptr,
-                    nullptr, 0, w.zs, ntx ? 0 : 1, s));
+  const bool split = phase != 0 && (row0 % kTileN) == 0 && ((nb % kTileN) == 0 || row0 + nb == b) && nb < b;
+  const size_t esz = dtype == WEALY_F32 ? 4 : 2;
+  auto prep_rows = [&](int64_t r0, int64_t nr) -> int {
+    if (nr <= 0) return WEALY_OK;
+    // NT-Xent: x/(|x|+1e-6) and statistics of the raw z; CLEWS: F.normalize (eps 1e-12), statistics of the normalised z
+    return launch_prep(static_cast<const uint8_t*>(z) + (size_t)r0 * ldz * esz, ldz, nr, d, dtype, ntx ? kPrepL2AddEps : kPrepL2Clamp,
+                       ntx ? 1e-6f : 1e-12f, plane_rows(w.u, r0, nr), nullptr, nullptr, 0, w.zs, ntx ? 0 : 1, s);
+  };
   LossParams lp;
   loss_params(lp, cfg, w, b, row0, nb);
-  GemmShape sh;
-  fill_shape(sh, nb, b, w.u.d_pad, 64, w.parts_max / 2);
   const int halves = 2;  // epilogue warps per TMEM lane quadrant
+  const int local_parts = (int)ceil_div(nb, kTileN) * halves;
+  if (phase != 2) {
+    CU_TRY(cudaMemsetAsync(w.zs, 0, 1280, s));  // ZStats, scal, flags, batch accumulators
+    pack_ids_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, (const long long*)z_idx, w.lab_idx, (int)b,
+                                                          w.bad);
+    CU_TRY(cudaGetLastError());
+  }
+  if (phase == 1) {
+    if (!split) return WEALY_OK;
+    W_TRY(prep_rows(row0, nb));
+    GemmShape sh;
+    fill_shape(sh, nb, nb, w.u.d_pad, 64, local_parts / halves);
+    lp.col_tile_off = (int)(row0 / kTileN);
+    lp.part_base = 0;
+    if (sh.n_col_chunks * halves > local_parts) return fail(WEALY_ERR_UNSUPPORTED, "loss sweep: %d parts", sh.n_col_chunks * halves);
+    // neutral records in the slots this launch does not write (it may use fewer column chunks than tiles)
+    W_TRY(launch_gemm<LossStatsEpi>(cfg->passes, plane_rows(w.u, row0, nb), plane_rows(w.u, row0, nb), sh, lp, s));
+    // remember how many slots were written: slot count is a pure function of the shape, recomputed in phase 2
+    return WEALY_OK;
+  }
+  int parts_local_used = 0;
+  if (phase == 2 && split) {
+    W_TRY(prep_rows(0, row0));
+    W_TRY(prep_rows(row0 + nb, b - row0 - nb));
+    GemmShape shl;
+    fill_shape(shl, nb, nb, w.u.d_pad, 64, local_parts / halves);
+    parts_local_used = shl.n_col_chunks * halves;
+  } else {
+    W_TRY(prep_rows(0, b));
+  }
+  GemmShape sh;
+  fill_shape(sh, nb, b, w.u.d_pad, 64, (w.parts_max - local_parts) / halves);
+  if (parts_local_used > 0) {
+    sh.skip0 = (int)(row0 / kTileN);
+    sh.skip1 = (int)ceil_div(row0 + nb, kTileN);
+  }
+  lp.part_base = parts_local_used;
   const int parts = sh.n_col_chunks * halves;
   W_TRY(launch_gemm<LossStatsEpi>(cfg->passes, plane_rows(w.u, row0, nb), w.u, sh, lp, s));
-  loss_merge_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, s>>>(loss_cfg_dev(cfg), (int)nb, (int)b, parts, w.partial,
+  loss_merge_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, s>>>(loss_cfg_dev(cfg), (int)nb, (int)b, parts_local_used + parts, w.partial,
                                                                 w.rowstat + row0 * 4, w.acc, w.acc_max);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
@@ -248,6 +292,16 @@ extern "C" int wealy_loss_dp_forward_local(const wealy_loss_cfg* cfg, const void
                                            void* workspace, size_t workspace_bytes, void* stream) {
   return loss_forward_local(cfg, z, b_global, ldz, d, dtype, z_label, z_idx, row0, nb, workspace, workspace_bytes,
                             (cudaStream_t)stream);
+}
+
+// The same in two phases, so that the rank's own column block is swept while the all-gather of the other ranks' rows is
+// still in flight: phase 1 reads only rows [row0, row0 + nb) of z, phase 2 everything else (call it once z is complete).
+extern "C" int wealy_loss_dp_forward_phase(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d,
+                                           int dtype, const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb,
+                                           int phase, void* workspace, size_t workspace_bytes, void* stream) {
+  if (phase != 1 && phase != 2) return fail(WEALY_ERR_BAD_ARG, "phase must be 1 or 2");
+  return loss_forward_local(cfg, z, b_global, ldz, d, dtype, z_label, z_idx, row0, nb, workspace, workspace_bytes,
+                            (cudaStream_t)stream, phase);
 }
 
 extern "C" int wealy_loss_dp_buffers(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global,

@@ -31,6 +31,8 @@ struct LossParams {
   float g2, b2;         // CLEWS: gamma * log2(e), b * log2(e)
   // statistics sweep
   float* partial;       // [parts][b][kStatWidth]
+  int part_base;        // first partial slot of this launch (a sweep split into two launches: local block, then the rest)
+  int col_tile_off;     // this launch's column 0 is column 256 * col_tile_off of the batch (local-block launch)
   // W sweep
   const float* rowstat; // [b padded to 256][4]
   __half* w_hi;         // [b][ldw] (ldw = b padded to the k-block)
@@ -59,8 +61,8 @@ struct LossColSlots {
   static constexpr int kOffColSlots = 0;
   static constexpr int kCtaScratchBytes = kColSlots * kColSlotBytes;
   __device__ static __forceinline__ void col_bulk_src(const LossParams& p, int t, const void*& s0, const void*& s1) {
-    s0 = p.rowstat + (size_t)t * kTileN * 4;
-    s1 = p.lab_idx + (size_t)t * kTileN;
+    s0 = p.rowstat + (size_t)(t + p.col_tile_off) * kTileN * 4;
+    s1 = p.lab_idx + (size_t)(t + p.col_tile_off) * kTileN;
   }
   __device__ static __forceinline__ const float4* col_stat(const EpiCtx& c, int col0) {
     return reinterpret_cast<const float4*>(c.col_slot) + (col0 & (kTileN - 1));
@@ -97,14 +99,15 @@ struct LossStatsEpi : LossColSlots {
 
   __device__ static __forceinline__ void chunk32(const Params& p, RowState& st, int row, int col0,
                                                  const uint32_t (&acc)[32], const GemmShape&, const EpiCtx& ctx) {
-    if (!st.valid || col0 >= p.b) return;
+    const int gcol0 = col0 + p.col_tile_off * kTileN;  // column index in the (global) batch
+    if (!st.valid || gcol0 >= p.b) return;
     const int2* cid = col_ids(ctx, col0);  // broadcast shared-memory reads
     if (p.kind == kLossNtxent) {
       float l[32];
       float cm = neg_inf();
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const int j = col0 + e;
+        const int j = gcol0 + e;
         const bool ok = (j < p.b) && (j != p.row0 + row);  // diagonal masked by POSITION (losses.py:52-53)
         l[e] = ok ? __uint_as_float(acc[e]) * p.c2 : neg_inf();
         cm = fmaxf(cm, l[e]);
@@ -127,7 +130,7 @@ struct LossStatsEpi : LossColSlots {
     } else {
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
-        const int j = col0 + e;
+        const int j = gcol0 + e;
         if (j < p.b) {
           const float s = __uint_as_float(acc[e]);
           const float d = 1.f - s;
@@ -150,7 +153,7 @@ struct LossStatsEpi : LossColSlots {
   __device__ static __forceinline__ void tile_end(const Params&, RowState&, const GemmShape&, const EpiCtx&) {}
   __device__ static __forceinline__ void row_end(const Params& p, RowState& st, int row, int part, const GemmShape&, const EpiCtx&) {
     if (!st.valid) return;
-    float* o = p.partial + ((long long)part * p.nb + row) * kStatWidth;
+    float* o = p.partial + ((long long)(p.part_base + part) * p.nb + row) * kStatWidth;
     reinterpret_cast<float4*>(o)[0] = make_float4(st.a0, st.a1, st.a2, st.a3);
     reinterpret_cast<float4*>(o)[1] = make_float4(st.a4, st.a5, 0.f, 0.f);
   }

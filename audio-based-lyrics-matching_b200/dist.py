@@ -102,13 +102,24 @@ def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=N
     on = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if on else 0
     world = dist.get_world_size(group) if on else 1
+    side = None
+    if world > 1 and not torch.as_tensor(z).is_cuda:
+        # 1/world of the rows per rank + NVLink all-gather, issued on a side stream BEFORE the id plan is built: the
+        # copy engine and NCCL move the embeddings while the plan's small kernels and host read-backs run
+        device = plan.device if plan is not None else torch.device("cuda", torch.cuda.current_device())
+        from .evaluation import side_stream
+        side = side_stream(device)
+        side.wait_stream(torch.cuda.current_stream(device))
+        with torch.cuda.stream(side):
+            z = upload_sharded(torch.as_tensor(z), device, group)
     if plan is None:
         plan = EvalPlan(c, i, c, i)
+    if side is not None:
+        torch.cuda.current_stream(plan.device).wait_stream(side)
+        z.record_stream(torch.cuda.current_stream(plan.device))
     if plan.queries_without_relevant and not allow_empty:
         raise ValueError(f"{plan.queries_without_relevant} queries have no relevant candidate "
                          "(every clique needs >= 2 versions; pass allow_empty=True to score the rest)")
-    if world > 1 and not torch.as_tensor(z).is_cuda:
-        z = upload_sharded(torch.as_tensor(z), plan.device, group)   # 1/world of the rows per rank + NVLink all-gather
     if world == 1:
         res = plan.run(z, z, eps=eps, precision=precision, allow_empty=allow_empty)
     else:

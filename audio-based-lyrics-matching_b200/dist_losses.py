@@ -4,7 +4,10 @@ The reference trains single-process (lib/losses.py sees one batch).  With one pr
 B/G anchors; the contrastive losses want ALL B columns (negatives from every rank).  Scheme, one process per GPU:
 
   1. all-gather z, labels, ids over NCCL (NVLink / NVSwitch)               -> the global batch on every rank
-  2. this rank's anchors [row0, row0 + nb) are swept against all B columns   (wealy_loss_dp_forward_local)
+     -- the all-gather of z is asynchronous: while it is in flight the rank already normalises its OWN rows and sweeps
+     its anchors against its OWN column block (wealy_loss_dp_forward_phase 1: needs nothing from the other ranks)
+  2. this rank's anchors [row0, row0 + nb) are swept against the other B - nb columns (phase 2, behind the all-gather;
+     the two launches write disjoint partial records that one merge kernel folds)
   3. all-reduce the batch sums (16 doubles + 2 maxima), all-gather the per-anchor records (4 floats per anchor)
   4. loss + logdict of the GLOBAL batch, identical on every rank             (wealy_loss_dp_forward_finish)
   5. backward: dz of this rank's rows only, and complete -- the symmetrised dL/dS contains the terms in which these
@@ -14,6 +17,7 @@ B/G anchors; the contrastive losses want ALL B columns (negatives from every ran
 `z.grad` is d(global loss)/dz for the local rows.  Same logdict keys as the single-GPU modules.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -51,6 +55,15 @@ class ShardState:
             N.check(N.lib.wealy_loss_dp_forward_local(
                 ctypes.byref(self.cfg), self.zg.data_ptr(), self.bg, self.zg.stride(0), self.d, self.code,
                 self.labg.data_ptr(), self.idxg.data_ptr(), self.row0, self.nb, self.ws.data_ptr(), self.ws_bytes,
+                N.stream_ptr(self.zg.device)))
+
+    def forward_phase(self, phase):
+        """phase 1: own rows / own column block only (run it while the all-gather of the other rows is in flight);
+        phase 2: everything else + merge (zg must be complete)."""
+        with torch.cuda.device(self.zg.device):
+            N.check(N.lib.wealy_loss_dp_forward_phase(
+                ctypes.byref(self.cfg), self.zg.data_ptr(), self.bg, self.zg.stride(0), self.d, self.code,
+                self.labg.data_ptr(), self.idxg.data_ptr(), self.row0, self.nb, int(phase), self.ws.data_ptr(), self.ws_bytes,
                 N.stream_ptr(self.zg.device)))
 
     def buffers(self):
@@ -104,9 +117,23 @@ class _DistLoss(torch.autograd.Function):
     def forward(ctx, z, labg, idxg, cfg_items, group):
         world, rank = _world(group)
         nb = z.shape[0]
-        zg = _all_gather_rows(z.detach(), group)                     # exchange 1: the global batch
-        st = ShardState(cfg_items, zg, labg, idxg, rank * nb, nb)
-        st.forward_local()
+        overlap = world > 1 and os.environ.get("WEALY_DP_OVERLAP", "1") != "0" and dist.get_backend(group) == "nccl"
+        if overlap:
+            # exchange 1, asynchronous and in place: the rank's rows sit in their slot of the global batch, NCCL fills the
+            # other slots on its own stream while this stream already works on the local block
+            zd = z.detach()
+            zg = torch.empty((world * nb,) + tuple(zd.shape[1:]), dtype=zd.dtype, device=zd.device)
+            mine = zg[rank * nb:(rank + 1) * nb]
+            mine.copy_(zd)
+            work = dist.all_gather_into_tensor(zg, mine, group=group, async_op=True)
+            st = ShardState(cfg_items, zg, labg, idxg, rank * nb, nb)
+            st.forward_phase(1)
+            work.wait()                                              # the compute stream waits for the gathered rows
+            st.forward_phase(2)
+        else:
+            zg = _all_gather_rows(z.detach(), group)                 # exchange 1: the global batch
+            st = ShardState(cfg_items, zg, labg, idxg, rank * nb, nb)
+            st.forward_local()
         if world > 1:
             acc, accm, rs = st.buffers()
             dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)  # exchange 2: batch sums ...

@@ -227,7 +227,14 @@ def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candid
         raise NotImplementedError("wealy_b200.evaluate ranks by cosine distance (mode='cos')")
     own = plan is None
     if own:
+        # host embeddings: start their upload on a side stream FIRST, so that the copy engine moves them while the id
+        # plan is built (a handful of small kernels and two host read-backs on the current stream)
+        queries_z, candidates_z, side = _prefetch_to_device(queries_z, candidates_z)
         plan = EvalPlan(queries_c, queries_i, candidates_c, candidates_i)
+        if side is not None:
+            torch.cuda.current_stream(plan.device).wait_stream(side)
+            for t in {id(queries_z): queries_z, id(candidates_z): candidates_z}.values():
+                t.record_stream(torch.cuda.current_stream(plan.device))
     try:
         res = plan.run(queries_z, candidates_z, topk=topk, eps=eps, precision=precision, allow_empty=allow_empty,
                        chunks=chunks, redux=redux, q_chunks=q_chunks, c_chunks=c_chunks)
@@ -238,6 +245,35 @@ def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candid
     if topk is None:
         return res["aps"], res["r1s"]
     return res["aps"], res["r1s"], res["topk_idx"], res["topk_sim"]
+
+
+_side_streams = {}
+
+
+def side_stream(device):
+    """One upload stream per device, kept for the life of the process: torch's caching allocator hands a block back only
+    to the stream it was allocated on, so a fresh stream per call would cudaMalloc the embeddings' buffer every time."""
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device)
+    return _side_streams[key]
+
+
+def _prefetch_to_device(queries_z, candidates_z):
+    """Host tensors -> device copies issued on a side stream (pinned memory makes them asynchronous); returns the
+    (possibly replaced) tensors and the stream to wait on, or None when nothing had to move."""
+    qz, cz = torch.as_tensor(queries_z), torch.as_tensor(candidates_z)
+    if qz.is_cuda and cz.is_cuda:
+        return queries_z, candidates_z, None
+    device = torch.device("cuda", torch.cuda.current_device())
+    side = side_stream(device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    same = queries_z is candidates_z
+    with torch.cuda.stream(side):
+        qd = qz if qz.is_cuda else qz.to(device, non_blocking=True)
+        cd = qd if same else (cz if cz.is_cuda else cz.to(device, non_blocking=True))
+    return qd, cd, side
 
 
 def mean_metrics(sums):

@@ -613,7 +613,7 @@ def run_gpu_arm(args):
     tiles = sum(max(0, n_ct - rb // 2) for rb in range(rank, n_rb, world))
     executed = 2.0 * 128 * 256 * DIM * tiles * passes / (last_sweep_ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-    variant = "pair" if os.environ.get("WEALY_SYM_PAIR", "") not in ("", "0") else "single"
+    variant = "pair" if os.environ.get("WEALY_SYM_PAIR", "1") != "0" else "single"
     traffic, traffic_note = None, "no ncu capture of this exact configuration is committed"
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath) and world == 1 and not args.tracks:
@@ -624,7 +624,9 @@ def run_gpu_arm(args):
         except Exception:
             pass
     roofline = {
-        "kernel": "gemm_kernel<EvalSymEpi> (symmetric tcgen05 similarity sweep over clique-sorted rows + mask + rank-count epilogue)",
+        "kernel": ("gemm_pair_kernel<EvalSymEpi> (symmetric tcgen05 cta_group::2 similarity sweep over clique-sorted rows + mask + "
+                   "rank-count epilogue)" if variant == "pair" else
+                   "gemm_kernel<EvalSymEpi> (symmetric tcgen05 similarity sweep over clique-sorted rows + mask + rank-count epilogue)"),
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": traffic, "traffic_note": traffic_note,
         "peak_kind": f"{peaks['_source']} dense bf16/fp16 cuBLAS, sustained (kernel timed inside a long step); "

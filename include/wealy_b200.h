@@ -256,6 +256,12 @@ size_t wealy_loss_dp_workspace_bytes(int64_t b_global, int64_t d, int passes, in
 int wealy_loss_dp_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d,
                                 int dtype, const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb,
                                 void* workspace, size_t workspace_bytes, void* stream);
+/* wealy_loss_dp_forward_local split in two, so that the exchange of z overlaps the first part of the sweep: phase 1 reads
+ * only this rank's own rows [row0, row0 + nb) of z (ids of the whole batch must be there) and sweeps its anchors against
+ * its own column block; phase 2 -- once the all-gather has delivered the other rows -- preps them and sweeps the rest. */
+int wealy_loss_dp_forward_phase(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d, int dtype,
+                                const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb, int phase,
+                                void* workspace, size_t workspace_bytes, void* stream);
 int wealy_loss_dp_buffers(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global, int64_t d,
                           int64_t nb, double** acc, int64_t* count_acc, uint32_t** acc_max, float** rowstat);
 int wealy_loss_dp_forward_finish(const wealy_loss_cfg* cfg, int64_t b_global, int64_t d, int64_t nb, double* out,

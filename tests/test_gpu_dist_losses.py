@@ -24,13 +24,23 @@ def _cfgs():
     }
 
 
-def _emulated(cfg_items, z, lab, idx, bounds):
-    """Run the shards [bounds[r], bounds[r+1]) as if they were ranks; collectives by hand."""
+def _emulated(cfg_items, z, lab, idx, bounds, phased=False):
+    """Run the shards [bounds[r], bounds[r+1]) as if they were ranks; collectives by hand.  phased: the forward in the
+    two phases of the overlapped path -- phase 1 sees a batch in which ONLY the shard's own rows are valid."""
     from wealy_b200.dist_losses import ShardState
     states = []
     for r in range(len(bounds) - 1):
-        st = ShardState(cfg_items, z, lab, idx, bounds[r], bounds[r + 1] - bounds[r])
-        st.forward_local()
+        if phased:
+            zz = torch.full_like(z, float("nan"))                   # rows of the other ranks: not arrived yet
+            zz[bounds[r]:bounds[r + 1]] = z[bounds[r]:bounds[r + 1]]
+            st = ShardState(cfg_items, zz, lab, idx, bounds[r], bounds[r + 1] - bounds[r])
+            st.forward_phase(1)
+            torch.cuda.synchronize()
+            zz.copy_(z)                                             # "all-gather complete"
+            st.forward_phase(2)
+        else:
+            st = ShardState(cfg_items, z, lab, idx, bounds[r], bounds[r + 1] - bounds[r])
+            st.forward_local()
         states.append(st)
     bufs = [st.buffers() for st in states]
     acc = sum(b[0].clone() for b in bufs)                                   # all-reduce SUM
@@ -67,6 +77,23 @@ def test_emulated_ranks_equal_single_gpu(kind, bounds):
     lo.backward()
     assert abs(float(outs[0][0]) - float(lo)) <= 1e-3 * abs(float(lo))
     assert float((grad.cpu() - zr.grad).norm()) <= 1e-5 * float(zr.grad.norm())
+
+
+@pytest.mark.parametrize("bounds", [[0, 256, 512], [0, 256, 512, 768, 1000], [0, 100, 333, 512]])
+@pytest.mark.parametrize("kind", ["ntx", "clews"])
+def test_two_phase_forward_equals_one_shot(kind, bounds):
+    """The overlapped data-parallel forward (own column block while the all-gather is in flight, the rest behind it)
+    gives the loss / logdict / gradients of the one-shot forward; unaligned shards fall back to doing everything in
+    phase 2.  Phase 1 is run on a batch whose foreign rows are NaN: it must not read them."""
+    from wealy_b200.data import synth
+    b = bounds[-1]
+    s = synth.make_loss_batch(b, 160, seed=9, device="cuda")
+    z, lab, idx = s["z"], s["label"], s["idx"]
+    o1, g1 = _emulated(_cfgs()[kind], z, lab, idx, bounds)
+    o2, g2 = _emulated(_cfgs()[kind], z, lab, idx, bounds, phased=True)
+    for a, c in zip(o1, o2):
+        assert torch.isfinite(c[:11]).all() and torch.allclose(a, c, rtol=1e-6, atol=1e-9)
+    assert torch.isfinite(g2).all() and float((g1 - g2).norm()) <= 1e-6 * float(g1.norm())
 
 
 def test_emulated_ranks_against_reference_outputs(golden):
