@@ -26,7 +26,8 @@ c_f64 = ctypes.c_double
 
 class LossCfg(ctypes.Structure):
     _fields_ = [("kind", c_int), ("passes", c_int), ("temperature", c_f32), ("gamma", c_f32), ("b", c_f32),
-                ("eps", c_f32), ("epsilon", c_f32), ("uw", c_f32), ("numerically_friendly", c_int)]
+                ("eps", c_f32), ("epsilon", c_f32), ("uw", c_f32), ("numerically_friendly", c_int),
+                ("label_noise", c_int), ("grad_dtype", c_int)]
 
 
 # every symbol include/wealy_b200.h declares: (restype, argtypes)
@@ -70,7 +71,7 @@ SIGNATURES = {
     "wealy_triplet_backward": (c_int, [c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_f32, c_f32, c_int, c_vp, c_vp,
                                        c_int, c_int, c_vp, c_vp, c_vp]),
     "wealy_loss_workspace_bytes": (c_sz, [c_i64, c_i64, c_int]),
-    "wealy_loss_forward": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp,
+    "wealy_loss_forward": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
                                    c_sz, c_vp]),
     "wealy_loss_backward": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_i64, c_i64, c_i64, c_int, c_vp, c_vp, c_i64,
                                     c_vp, c_sz, c_vp]),
@@ -81,7 +82,11 @@ SIGNATURES = {
                                             c_i64, c_int, c_vp, c_sz, c_vp]),
     "wealy_loss_dp_buffers": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_sz, c_i64, c_i64, c_i64, ctypes.POINTER(c_vp),
                                       ctypes.POINTER(c_i64), ctypes.POINTER(c_vp), ctypes.POINTER(c_vp)]),
-    "wealy_loss_dp_forward_finish": (c_int, [ctypes.POINTER(LossCfg), c_i64, c_i64, c_i64, c_vp, c_vp, c_sz, c_vp]),
+    "wealy_loss_dp_record_bytes": (c_sz, [c_i64]),
+    "wealy_loss_dp_pack": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_sz, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "wealy_loss_dp_unpack": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_sz, c_i64, c_i64, c_i64, c_vp, c_int, c_vp]),
+    "wealy_loss_dp_forward_finish": (c_int, [ctypes.POINTER(LossCfg), c_i64, c_i64, c_i64, c_vp, c_vp, c_int, c_vp, c_sz,
+                                             c_vp]),
     "wealy_loss_dp_backward": (c_int, [ctypes.POINTER(LossCfg), c_vp, c_i64, c_i64, c_i64, c_int, c_i64, c_i64, c_vp, c_vp,
                                        c_i64, c_vp, c_sz, c_vp]),
 }

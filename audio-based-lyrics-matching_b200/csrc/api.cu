@@ -227,19 +227,21 @@ static int launch_prep(const void* x, int64_t ld, int64_t n, int64_t d, int dtyp
 // ------------------------------------------------------------------------------------------
 // contraction launcher
 // ------------------------------------------------------------------------------------------
-// per-launch work counters of the dynamic unit scheduler (one int per launch, zeroed stream-ordered)
+// per-launch work counters of the dynamic unit scheduler: {next unit, CTAs through} pairs, zero at load time and reset
+// by the last CTA of every launch (gemm_core.cuh: release_unit_counter) -- no memset in front of a launch.  A slot is
+// reused after 2048 launches of this thread's device, long after its previous kernel has retired.
 __device__ int g_unit_counters[4096];
 
 static int next_unit_counter(int** out, cudaStream_t s) {
+  (void)s;
   static thread_local int* base[64] = {nullptr};
   static int seq = 0;
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64) return fail(WEALY_ERR_UNSUPPORTED, "device index %d", dev);
   if (!base[dev]) CU_TRY(cudaGetSymbolAddress(reinterpret_cast<void**>(&base[dev]), g_unit_counters));
-  const int slot = __atomic_fetch_add(&seq, 1, __ATOMIC_RELAXED) & 4095;
-  *out = base[dev] + slot;
-  CU_TRY(cudaMemsetAsync(*out, 0, sizeof(int), s));
+  const int slot = __atomic_fetch_add(&seq, 1, __ATOMIC_RELAXED) & 2047;
+  *out = base[dev] + 2 * slot;
   return WEALY_OK;
 }
 

@@ -52,7 +52,9 @@ struct GemmShape {
   int tiles_per_chunk;  // column tiles per unit
   int n_col_chunks;     // ceil(n_col_tiles / tiles_per_chunk)
   int group_rows;       // row blocks per scheduling group (see decode_unit)
-  int* unit_counter;    // global work counter of this launch (zeroed by the host): dynamic unit scheduling
+  int* unit_counter;    // global work counter of this launch: dynamic unit scheduling.  unit_counter[1] counts the
+                        //   CTAs that are through; the last one zeroes both again, so the host never has to (no memset
+                        //   in front of every launch; the slots start out zero)
   int sym;              // symmetric all-vs-all: only tiles that reach above the diagonal are computed
   int rb_stride;        // multi-GPU symmetric sweep: this launch owns row blocks rb_offset + k * rb_stride
   int rb_offset;        //   (n_row_blocks counts the owned ones)
@@ -88,6 +90,18 @@ __device__ __forceinline__ void decode_unit(const GemmShape& sh, int u, int& chu
   const int rows_here = min(sh.group_rows, sh.n_row_blocks - g * sh.group_rows);
   chunk = within / rows_here;
   rb = (g * sh.group_rows + (within - chunk * rows_here)) * sh.rb_stride + sh.rb_offset;
+}
+
+// Every CTA calls this once, after its last fetch from the unit counter: the last CTA through resets the pair of
+// counters for the slot's next launch (stream order makes the reset visible to it).
+__device__ __forceinline__ void release_unit_counter(const GemmShape& sh) {
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(sh.unit_counter + 1, 1);
+    if (done == (int)gridDim.x - 1) {
+      sh.unit_counter[0] = 0;
+      sh.unit_counter[1] = 0;
+    }
+  }
 }
 
 template <int kPasses, int kBlockK, int kMaxStages = 8>
@@ -389,6 +403,7 @@ gemm_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape, cons
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<512>(tmem_base);
   }
+  release_unit_counter(shape);
 }
 
 }  // namespace wealy

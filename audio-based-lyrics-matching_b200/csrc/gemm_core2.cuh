@@ -356,6 +356,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc_pair<512>(tmem_base);
   }
+  release_unit_counter(shape);
 }
 
 }  // namespace wealy

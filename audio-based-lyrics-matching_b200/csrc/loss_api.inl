@@ -127,7 +127,7 @@ static Planes plane_rows(const Planes& p, int64_t row0, int64_t nb) {
 //   phase 2: prep of the other rows + sweep against every other column block + merge.
 // (own block not aligned to the 256-column tiles: phase 1 only packs the ids, phase 2 does everything.)
 static int loss_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
-                              const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb, void* workspace,
+                              int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb, void* workspace,
                               size_t workspace_bytes, cudaStream_t s, int phase = 0) {
   W_TRY(loss_check(cfg, z, b, d, workspace, workspace_bytes, row0, nb));
   if (!z_label || !z_idx) return fail(WEALY_ERR_BAD_ARG, "null pointer");
@@ -149,9 +149,16 @@ static int loss_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t 
   const int halves = 2;  // epilogue warps per TMEM lane quadrant
   const int local_parts = (int)ceil_div(nb, kTileN) * halves;
   if (phase != 2) {
-    CU_TRY(cudaMemsetAsync(w.zs, 0, 1280, s));  // ZStats, scal, flags, batch accumulators
-    pack_ids_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, (const long long*)z_idx, w.lab_idx, (int)b,
-                                                          w.bad);
+    if (b <= 65536) {
+      // one CTA: zero {ZStats, scal, flags, batch accumulators}, optional single-label noise (in place), pack the ids
+      pack_ids_noise_kernel<<<1, 1024, 0, s>>>((long long*)z_label, (const long long*)z_idx, w.lab_idx, (int)b,
+                                               cfg->label_noise ? 1 : 0, reinterpret_cast<int*>(w.zs), 1280 / 4, w.bad);
+    } else {
+      if (cfg->label_noise) return fail(WEALY_ERR_UNSUPPORTED, "label_noise is fused for batches of up to 65536 rows");
+      CU_TRY(cudaMemsetAsync(w.zs, 0, 1280, s));
+      pack_ids_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, (const long long*)z_idx, w.lab_idx, (int)b,
+                                                            w.bad);
+    }
     CU_TRY(cudaGetLastError());
   }
   if (phase == 1) {
@@ -194,13 +201,13 @@ static int loss_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t 
 
 // forward, part 2: batch sums (acc, acc_max) and the per-anchor records (rowstat) of ALL b anchors are in the
 // workspace (summed / gathered over the ranks by the caller when the batch is sharded) -> loss, logdict, coefficients
-static int loss_forward_finish(const wealy_loss_cfg* cfg, int64_t b, int64_t d, int64_t nb, double* out, void* workspace,
-                               cudaStream_t s) {
+static int loss_forward_finish(const wealy_loss_cfg* cfg, int64_t b, int64_t d, int64_t nb, double* out, void* out_cast,
+                               int cast_dtype, void* workspace, cudaStream_t s) {
   LossWs w;
   loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes, nb);
-  CU_TRY(cudaMemsetAsync(out, 0, WEALY_OUT_COUNT * sizeof(double), s));
+  if (out_cast && (cast_dtype < WEALY_F32 || cast_dtype > WEALY_BF16)) return fail(WEALY_ERR_BAD_ARG, "out_cast element type %d", cast_dtype);
   loss_finish_kernel<<<(unsigned)ceil_div(b, 256), 256, 0, s>>>(loss_cfg_dev(cfg), (int)b, (int)d, w.acc, w.acc_max, w.zs,
-                                                                w.rowstat, w.scal, out, w.bad);
+                                                                w.rowstat, w.scal, out, w.bad, out_cast, cast_dtype);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;
 }
@@ -208,10 +215,12 @@ static int loss_forward_finish(const wealy_loss_cfg* cfg, int64_t b, int64_t d, 
 // backward of the anchors [row0, row0 + nb): dz rows of this shard (complete: W is symmetrised, so the terms in
 // which these rows act as columns of other ranks' anchors are included -- no reduce-scatter)
 static int loss_backward_rows(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
-                              int64_t row0, int64_t nb, const float* grad_out, void* dz, int64_t ld_dz, void* workspace,
+                              int64_t row0, int64_t nb, const void* grad_out, void* dz, int64_t ld_dz, void* workspace,
                               size_t workspace_bytes, cudaStream_t s) {
   W_TRY(loss_check(cfg, z, b, d, workspace, workspace_bytes, row0, nb));
   if (!dz) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  const int gdt = cfg->grad_dtype;
+  if (gdt < WEALY_F32 || gdt > WEALY_BF16) return fail(WEALY_ERR_BAD_ARG, "grad_dtype %d", gdt);
   LossWs w;
   loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b, d, cfg->passes, nb);
   LossParams lp;
@@ -250,16 +259,16 @@ static int loss_backward_rows(const wealy_loss_cfg* cfg, const void* z, int64_t 
   switch (dtype) {
     case WEALY_F32:
       loss_jacobian_kernel<float><<<blocks, T, 0, s>>>(cfg->kind, jeps, (const float*)zrow, (long long)ldz, (int)nb, (int)d,
-                                                       w.u.norm + row0, w.du, w.scal, grad_out, (float*)dz, (long long)ld_dz);
+                                                       w.u.norm + row0, w.du, w.scal, grad_out, (float*)dz, (long long)ld_dz, gdt);
       break;
     case WEALY_F16:
       loss_jacobian_kernel<__half><<<blocks, T, 0, s>>>(cfg->kind, jeps, (const __half*)zrow, (long long)ldz, (int)nb, (int)d,
-                                                        w.u.norm + row0, w.du, w.scal, grad_out, (__half*)dz, (long long)ld_dz);
+                                                        w.u.norm + row0, w.du, w.scal, grad_out, (__half*)dz, (long long)ld_dz, gdt);
       break;
     case WEALY_BF16:
       loss_jacobian_kernel<__nv_bfloat16><<<blocks, T, 0, s>>>(cfg->kind, jeps, (const __nv_bfloat16*)zrow, (long long)ldz, (int)nb,
                                                                (int)d, w.u.norm + row0, w.du, w.scal, grad_out,
-                                                               (__nv_bfloat16*)dz, (long long)ld_dz);
+                                                               (__nv_bfloat16*)dz, (long long)ld_dz, gdt);
       break;
     default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
   }
@@ -269,15 +278,15 @@ static int loss_backward_rows(const wealy_loss_cfg* cfg, const void* z, int64_t 
 
 // ---- single GPU: the whole batch is one shard
 extern "C" int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
-                                  const int64_t* z_label, const int64_t* z_idx, double* out, void* workspace,
+                                  int64_t* z_label, const int64_t* z_idx, double* out, void* out_cast, void* workspace,
                                   size_t workspace_bytes, void* stream) {
   if (!out) return fail(WEALY_ERR_BAD_ARG, "null pointer");
   W_TRY(loss_forward_local(cfg, z, b, ldz, d, dtype, z_label, z_idx, 0, b, workspace, workspace_bytes, (cudaStream_t)stream));
-  return loss_forward_finish(cfg, b, d, b, out, workspace, (cudaStream_t)stream);
+  return loss_forward_finish(cfg, b, d, b, out, out_cast, dtype, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
-                                   const float* grad_out, void* dz, int64_t ld_dz, void* workspace,
+                                   const void* grad_out, void* dz, int64_t ld_dz, void* workspace,
                                    size_t workspace_bytes, void* stream) {
   return loss_backward_rows(cfg, z, b, ldz, d, dtype, 0, b, grad_out, dz, ld_dz, workspace, workspace_bytes,
                             (cudaStream_t)stream);
@@ -290,8 +299,9 @@ extern "C" int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int
 extern "C" int wealy_loss_dp_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d,
                                            int dtype, const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb,
                                            void* workspace, size_t workspace_bytes, void* stream) {
-  return loss_forward_local(cfg, z, b_global, ldz, d, dtype, z_label, z_idx, row0, nb, workspace, workspace_bytes,
-                            (cudaStream_t)stream);
+  if (cfg && cfg->label_noise) return fail(WEALY_ERR_BAD_ARG, "label noise acts on the GLOBAL batch: apply it before the call");
+  return loss_forward_local(cfg, z, b_global, ldz, d, dtype, const_cast<int64_t*>(z_label), z_idx, row0, nb, workspace,
+                            workspace_bytes, (cudaStream_t)stream);
 }
 
 // The same in two phases, so that the rank's own column block is swept while the all-gather of the other ranks' rows is
@@ -300,8 +310,9 @@ extern "C" int wealy_loss_dp_forward_phase(const wealy_loss_cfg* cfg, const void
                                            int dtype, const int64_t* z_label, const int64_t* z_idx, int64_t row0, int64_t nb,
                                            int phase, void* workspace, size_t workspace_bytes, void* stream) {
   if (phase != 1 && phase != 2) return fail(WEALY_ERR_BAD_ARG, "phase must be 1 or 2");
-  return loss_forward_local(cfg, z, b_global, ldz, d, dtype, z_label, z_idx, row0, nb, workspace, workspace_bytes,
-                            (cudaStream_t)stream, phase);
+  if (cfg && cfg->label_noise) return fail(WEALY_ERR_BAD_ARG, "label noise acts on the GLOBAL batch: apply it before the call");
+  return loss_forward_local(cfg, z, b_global, ldz, d, dtype, const_cast<int64_t*>(z_label), z_idx, row0, nb, workspace,
+                            workspace_bytes, (cudaStream_t)stream, phase);
 }
 
 extern "C" int wealy_loss_dp_buffers(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global,
@@ -318,15 +329,49 @@ extern "C" int wealy_loss_dp_buffers(const wealy_loss_cfg* cfg, void* workspace,
   return WEALY_OK;
 }
 
+// Exchange 2 as a single collective (equal shards: rank r owns anchors [r nb, (r + 1) nb)): pack this rank's record,
+// all-gather the records (wealy_loss_dp_record_bytes(nb) bytes each, rank order), unpack them on every rank.
+extern "C" size_t wealy_loss_dp_record_bytes(int64_t nb) { return nb < 0 ? 0 : (size_t)kDpRecordHeader + (size_t)nb * 16; }
+
+extern "C" int wealy_loss_dp_pack(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global, int64_t d,
+                                  int64_t row0, int64_t nb, void* record, void* stream) {
+  if (!cfg || !workspace || !record) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (nb <= 0 || row0 < 0 || row0 + nb > b_global) return fail(WEALY_ERR_BAD_ARG, "bad shard");
+  if (workspace_bytes < loss_ws_bytes(b_global, d, cfg->passes, nb)) return fail(WEALY_ERR_WORKSPACE, "workspace too small");
+  LossWs w;
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b_global, d, cfg->passes, nb);
+  const int n = (int)(nb > kAccCount ? nb : kAccCount);
+  loss_dp_pack_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(w.acc, w.acc_max, w.rowstat + row0 * 4, (int)nb,
+                                                                                  reinterpret_cast<unsigned char*>(record));
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+extern "C" int wealy_loss_dp_unpack(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global, int64_t d,
+                                    int64_t nb, const void* records, int world, void* stream) {
+  if (!cfg || !workspace || !records) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (world < 1 || nb <= 0 || (int64_t)world * nb != b_global) return fail(WEALY_ERR_BAD_ARG, "equal shards: world * nb must be the global batch");
+  if (workspace_bytes < loss_ws_bytes(b_global, d, cfg->passes, nb)) return fail(WEALY_ERR_WORKSPACE, "workspace too small");
+  LossWs w;
+  loss_ws_layout(w, reinterpret_cast<uint8_t*>(align_up((size_t)workspace, 1024)), b_global, d, cfg->passes, nb);
+  const int n = (int)(b_global > kAccCount ? b_global : kAccCount);
+  loss_dp_unpack_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const unsigned char*>(records), (long long)wealy_loss_dp_record_bytes(nb), world, (int)nb, w.acc, w.acc_max,
+      w.rowstat);
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
 extern "C" int wealy_loss_dp_forward_finish(const wealy_loss_cfg* cfg, int64_t b_global, int64_t d, int64_t nb, double* out,
-                                            void* workspace, size_t workspace_bytes, void* stream) {
+                                            void* out_cast, int cast_dtype, void* workspace, size_t workspace_bytes,
+                                            void* stream) {
   if (!cfg || !out || !workspace) return fail(WEALY_ERR_BAD_ARG, "null pointer");
   if (workspace_bytes < loss_ws_bytes(b_global, d, cfg->passes, nb)) return fail(WEALY_ERR_WORKSPACE, "workspace too small");
-  return loss_forward_finish(cfg, b_global, d, nb, out, workspace, (cudaStream_t)stream);
+  return loss_forward_finish(cfg, b_global, d, nb, out, out_cast, cast_dtype, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int wealy_loss_dp_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d,
-                                      int dtype, int64_t row0, int64_t nb, const float* grad_out, void* dz_rows,
+                                      int dtype, int64_t row0, int64_t nb, const void* grad_out, void* dz_rows,
                                       int64_t ld_dz, void* workspace, size_t workspace_bytes, void* stream) {
   return loss_backward_rows(cfg, z, b_global, ldz, d, dtype, row0, nb, grad_out, dz_rows, ld_dz, workspace, workspace_bytes,
                             (cudaStream_t)stream);

@@ -50,6 +50,35 @@ __global__ void pack_ids_kernel(const long long* __restrict__ label, const long 
   out[t] = make_int2((int)a, (int)b);
 }
 
+// The same for training-size batches, in ONE CTA, with the reference's single-label noise folded in (lib/losses.py:34-35:
+// a batch that holds a single label gets its first max(2, n / 100) labels overwritten with -1, IN PLACE) and the
+// workspace's statistics block zeroed -- what used to be five ATen launches and a memset in front of every forward.
+__global__ void __launch_bounds__(1024) pack_ids_noise_kernel(long long* __restrict__ label, const long long* __restrict__ idx,
+                                                              int2* __restrict__ out, int n, int noise, int* __restrict__ zero,
+                                                              int zero_words, int* __restrict__ bad) {
+  for (int t = threadIdx.x; t < zero_words; t += blockDim.x) zero[t] = 0;
+  int differs = 0;
+  if (noise) {
+    const long long first = label[0];
+    for (int t = threadIdx.x; t < n; t += blockDim.x) differs |= (label[t] != first);
+  }
+  const int single = noise && !__syncthreads_or(differs);   // (also orders the zeroing before the range-check atomics)
+  if (!noise) __syncthreads();
+  const int k = max(2, n / 100);
+  int nbad = 0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    long long a = label[t];
+    const long long b = idx[t];
+    if (single && t < k) {
+      a = -1;
+      label[t] = -1;
+    }
+    nbad += (a > 2147483647ll || a < -2147483648ll || b > 2147483647ll || b < -2147483648ll);
+    out[t] = make_int2((int)a, (int)b);
+  }
+  if (nbad) atomicAdd(bad, nbad);
+}
+
 // Per-tile column data of the loss epilogues, bulk-copied into shared memory by the TMA thread (gemm_core.cuh):
 // the 256 columns' backward records (float4 rowstat) and {label, idx} pairs -- instead of three global loads per
 // matrix element.
@@ -332,17 +361,33 @@ __global__ void __launch_bounds__(256) loss_merge_kernel(LossCfgDev cfg, int b, 
   }
 }
 
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+
+__device__ __forceinline__ void store_cast(void* dst, int dtype, int k, double v) {
+  // dtype codes of include/wealy_b200.h: 0 f32, 1 f16, 2 bf16
+  if (dtype == 0) reinterpret_cast<float*>(dst)[k] = (float)v;
+  else if (dtype == 1) reinterpret_cast<__half*>(dst)[k] = __float2half_rn((float)v);
+  else reinterpret_cast<__nv_bfloat16*>(dst)[k] = __float2bfloat16_rn((float)v);
+}
+
+// `out` receives all WEALY_OUT_COUNT doubles (no memset needed in front); out_cast (nullable) the same numbers in the
+// batch's own element type, which is what the reference's modules return (lib/losses.py:65-72)
 __global__ void __launch_bounds__(256) loss_finish_kernel(LossCfgDev cfg, int b, int d, const double* __restrict__ acc,
                                                           const unsigned int* __restrict__ acc_max,
                                                           const ZStats* __restrict__ zs, float* __restrict__ rowstat,
                                                           float* __restrict__ scal, double* __restrict__ out,
-                                                          const int* __restrict__ bad) {
+                                                          const int* __restrict__ bad, void* __restrict__ out_cast,
+                                                          int cast_dtype) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const double B = (double)b;
   const bool writer = (i == 0);
+  double o[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) o[k] = 0.0;
   if (cfg.kind == kLossNtxent) {
     if (writer) {
-      out[0] = acc[0] / B;
+      o[0] = acc[0] / B;
       scal[0] = 1.f / ((float)b * cfg.temperature);
     }
   } else {
@@ -361,28 +406,64 @@ __global__ void __launch_bounds__(256) loss_finish_kernel(LossCfgDev cfg, int b,
       const double l_align = acc[5] > 0.0 ? acc[1] / acc[5] : 0.0;  // losses.py:239
       const double l_uni = acc[2] / B;
       const double n2 = B * B;
-      out[0] = l_align + (double)cfg.uw * l_uni;
-      out[4] = l_align;
-      out[5] = l_uni;
-      out[6] = acc[3];
-      out[7] = acc[4];
-      out[8] = acc[5] / B;
+      o[0] = l_align + (double)cfg.uw * l_uni;
+      o[4] = l_align;
+      o[5] = l_uni;
+      o[6] = acc[3];
+      o[7] = acc[4];
+      o[8] = acc[5] / B;
       // tops.mmean(d, mask=pos_mask) averages over the COMPLEMENT of the mask (losses.py:267-268)
-      out[9] = acc[3] > 0.0 ? (acc[7] - acc[6]) / fmax(n2 - acc[3], 1e-7) : 0.0;
-      out[10] = acc[4] > 0.0 ? (acc[7] - acc[8]) / fmax(n2 - acc[4], 1e-7) : 0.0;
+      o[9] = acc[3] > 0.0 ? (acc[7] - acc[6]) / fmax(n2 - acc[3], 1e-7) : 0.0;
+      o[10] = acc[4] > 0.0 ? (acc[7] - acc[8]) / fmax(n2 - acc[4], 1e-7) : 0.0;
       scal[0] = 1.f / S;
     }
   }
   if (writer) {
     const double n = B * (double)d;
-    out[1] = (double)__uint_as_float(zs->maxabs_bits);
-    out[2] = zs->sum / n;
+    o[1] = (double)__uint_as_float(zs->maxabs_bits);
+    o[2] = zs->sum / n;
     const double var = n > 1.0 ? (zs->sumsq - zs->sum * zs->sum / n) / (n - 1.0) : 0.0;
-    out[3] = sqrt(var > 0.0 ? var : 0.0);
+    o[3] = sqrt(var > 0.0 ? var : 0.0);
     // labels / ids that do not fit in 32 bits were truncated by pack_ids_kernel: positives would be wrong, so the
     // loss is poisoned (NaN) and the count reported -- no host sync on the training path
-    out[11] = (double)bad[0];
-    if (bad[0] != 0) out[0] = __longlong_as_double(0x7ff8000000000000ll);
+    o[11] = (double)bad[0];
+    if (bad[0] != 0) o[0] = __longlong_as_double(0x7ff8000000000000ll);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      out[k] = o[k];
+      if (out_cast) store_cast(out_cast, cast_dtype, k, o[k]);
+    }
+  }
+}
+
+// Data-parallel exchange 2 as ONE all-gather: every rank packs {batch sums, maxima, its anchors' records} into one
+// record, the records of all ranks are gathered, and every rank folds them back into its workspace.
+//   record layout (bytes): [0, 128) acc (16 doubles) | [128, 136) acc_max (2 x uint32) | [256, 256 + nb * 16) rowstat rows
+constexpr int kDpRecordHeader = 256;
+__global__ void loss_dp_pack_kernel(const double* __restrict__ acc, const unsigned int* __restrict__ acc_max,
+                                    const float* __restrict__ rowstat_local, int nb, unsigned char* __restrict__ rec) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < kAccCount) reinterpret_cast<double*>(rec)[t] = acc[t];
+  if (t < 2) reinterpret_cast<unsigned int*>(rec + 128)[t] = acc_max[t];
+  if (t < nb) reinterpret_cast<float4*>(rec + kDpRecordHeader)[t] = reinterpret_cast<const float4*>(rowstat_local)[t];
+}
+__global__ void loss_dp_unpack_kernel(const unsigned char* __restrict__ recs, long long rec_bytes, int world, int nb,
+                                      double* __restrict__ acc, unsigned int* __restrict__ acc_max,
+                                      float* __restrict__ rowstat) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < kAccCount) {
+    double v = 0.0;
+    for (int r = 0; r < world; ++r) v += reinterpret_cast<const double*>(recs + r * rec_bytes)[t];
+    acc[t] = v;
+  }
+  if (t < 2) {
+    unsigned int v = 0u;
+    for (int r = 0; r < world; ++r) v = max(v, reinterpret_cast<const unsigned int*>(recs + r * rec_bytes + 128)[t]);
+    acc_max[t] = v;
+  }
+  if (t < world * nb) {
+    const int r = t / nb, i = t - r * nb;
+    reinterpret_cast<float4*>(rowstat)[t] = reinterpret_cast<const float4*>(recs + r * rec_bytes + kDpRecordHeader)[i];
   }
 }
 
@@ -449,8 +530,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) loss_jacobian_kernel(int kind, float eps, const T* __restrict__ z, long long ldz, int b, int d,
                                                             const float* __restrict__ norm,
                                                             const float* __restrict__ du, const float* __restrict__ scal,
-                                                            const float* __restrict__ grad_out, T* __restrict__ dz,
-                                                            long long ld_dz) {
+                                                            const void* __restrict__ grad_out, T* __restrict__ dz,
+                                                            long long ld_dz, int grad_dtype = 0) {
   const int row = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (row >= b) return;
@@ -478,7 +559,14 @@ __global__ void __launch_bounds__(256) loss_jacobian_kernel(int kind, float eps,
   proj = warp_sum(proj);
   // d(z/(r+eps))/dz has the extra (r+eps)/r on the radial term; r == 0 -> torch's norm subgradient is 0
   const float radial = kind == kLossNtxent ? (r > 0.f ? proj * div / r : 0.f) : proj;
-  const float f = scal[0] * (grad_out ? grad_out[0] : 1.f) * inv;
+  // upstream gradient of the scalar loss, in whatever type autograd hands it over (the loss carries z's dtype)
+  float up = 1.f;
+  if (grad_out) {
+    up = grad_dtype == 0 ? reinterpret_cast<const float*>(grad_out)[0]
+         : grad_dtype == 1 ? __half2float(reinterpret_cast<const __half*>(grad_out)[0])
+                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(grad_out)[0]);
+  }
+  const float f = scal[0] * up * inv;
   if (vec) {
     for (int k = lane * 4; k < d; k += 128) {
       const float4 zv = load4<T>(zr + k), gv = *reinterpret_cast<const float4*>(g + k);

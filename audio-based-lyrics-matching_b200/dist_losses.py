@@ -77,11 +77,27 @@ class ShardState:
         return (_dev_view(acc.value, (cnt.value,), "<f8", dev), _dev_view(accm.value, (2,), "<i4", dev),
                 _dev_view(rs.value, (self.bg, 4), "<f4", dev))
 
+    def exchange(self, group, world):
+        """Exchange 2 in one collective: pack this rank's {batch sums, maxima, anchor records}, all-gather the records,
+        fold all of them back into the workspace (equal shards)."""
+        dev = self.zg.device
+        rec_bytes = N.lib.wealy_loss_dp_record_bytes(self.nb)
+        recs = torch.empty((world, rec_bytes), dtype=torch.uint8, device=dev)
+        mine = recs[self.row0 // self.nb]
+        with torch.cuda.device(dev):
+            N.check(N.lib.wealy_loss_dp_pack(ctypes.byref(self.cfg), self.ws.data_ptr(), self.ws_bytes, self.bg, self.d,
+                                             self.row0, self.nb, mine.data_ptr(), N.stream_ptr(dev)))
+        dist.all_gather_into_tensor(recs, mine, group=group)             # in place: every rank's record in rank order
+        with torch.cuda.device(dev):
+            N.check(N.lib.wealy_loss_dp_unpack(ctypes.byref(self.cfg), self.ws.data_ptr(), self.ws_bytes, self.bg, self.d,
+                                               self.nb, recs.data_ptr(), world, N.stream_ptr(dev)))
+        recs.record_stream(torch.cuda.current_stream(dev))
+
     def forward_finish(self):
         out = torch.empty(N.OUT_COUNT, dtype=torch.float64, device=self.zg.device)
         with torch.cuda.device(self.zg.device):
-            N.check(N.lib.wealy_loss_dp_forward_finish(ctypes.byref(self.cfg), self.bg, self.d, self.nb, out.data_ptr(),
-                                                       self.ws.data_ptr(), self.ws_bytes, N.stream_ptr(self.zg.device)))
+            N.check(N.lib.wealy_loss_dp_forward_finish(ctypes.byref(self.cfg), self.bg, self.d, self.nb, out.data_ptr(), None,
+                                                       0, self.ws.data_ptr(), self.ws_bytes, N.stream_ptr(self.zg.device)))
         return out
 
     def backward(self, grad_loss):
@@ -134,16 +150,17 @@ class _DistLoss(torch.autograd.Function):
             zg = _all_gather_rows(z.detach(), group)                 # exchange 1: the global batch
             st = ShardState(cfg_items, zg, labg, idxg, rank * nb, nb)
             st.forward_local()
-        if world > 1:
+        if world > 1 and dist.get_backend(group) == "nccl":
+            st.exchange(group, world)                                # exchange 2: batch sums + anchor records, one all-gather
+        elif world > 1:
             acc, accm, rs = st.buffers()
-            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)  # exchange 2: batch sums ...
+            dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
             dist.all_reduce(accm, op=dist.ReduceOp.MAX, group=group)
-            dist.all_gather_into_tensor(rs, rs[rank * nb:(rank + 1) * nb].clone(), group=group)  # ... anchor records
+            dist.all_gather_into_tensor(rs, rs[rank * nb:(rank + 1) * nb].clone(), group=group)
         out = st.forward_finish()
         ctx.st = st
-        loss_dtype = torch.float32 if z.dtype in (torch.float16, torch.bfloat16) else z.dtype
         ctx.mark_non_differentiable(out)
-        return out[0].to(loss_dtype), out
+        return out[0].to(z.dtype), out              # like the single-GPU modules: the loss carries z's dtype
 
     @staticmethod
     def backward(ctx, grad_loss, _g):
@@ -154,8 +171,12 @@ def _gather_ids(z_label, z_idx, group):
     """Global labels / ids (rank order) with the reference's single-label noise applied to the GLOBAL batch
     (lib/losses.py:34-35); the local slice of the caller's z_label is updated in place like upstream."""
     world, rank = _world(group)
-    labg = _all_gather_rows(z_label.to(torch.long), group)
-    idxg = _all_gather_rows(z_idx.to(torch.long), group)
+    if world > 1:
+        both = _all_gather_rows(torch.stack((z_label.to(torch.long), z_idx.to(torch.long))), group)   # ONE collective
+        both = both.view(world, 2, -1)
+        labg, idxg = both[:, 0].reshape(-1), both[:, 1].reshape(-1)
+    else:
+        labg, idxg = z_label.to(torch.long), z_idx.to(torch.long)
     if labg.data_ptr() == z_label.data_ptr():
         _label_noise_(z_label)
         return z_label, idxg

@@ -39,44 +39,63 @@ def _label_noise_(z_label):
     head.copy_(torch.where(single, torch.full_like(head, -1), head))
 
 
+_HALF = (torch.float16, torch.bfloat16)
+
+
 class _FusedLoss(torch.autograd.Function):
+    """forward: ONE C call (ids packed + single-label noise in place + prep + statistics sweep + merge + finish) that also
+    writes the loss / logdict numbers in z's dtype; backward: ONE C call that reads the upstream gradient in whatever
+    dtype autograd hands it over.  No ATen kernel runs between the module call and z.grad."""
+
     @staticmethod
-    def forward(ctx, z, z_label, z_idx, cfg_items, loss_dtype):
-        cfg = N.LossCfg(**dict(cfg_items))
+    def forward(ctx, z, z_label, z_idx, cfg_items, loss_dtype, noise):
         N.require_cuda(z, z_label, z_idx)
         ctx.in_dtype = z.dtype
         if z.dtype == torch.float64:
             z = z.float()
         code = N.dtype_code(z.dtype)
         zz = z if z.stride(1) == 1 else z.contiguous()
-        lab = z_label.to(torch.long).contiguous()
-        idx = z_idx.to(torch.long).contiguous()
         b, d = zz.shape
+        # the single-label noise of lib/losses.py:34-35 mutates the CALLER's labels: fused into the id-packing kernel when
+        # they are an int64 tensor the kernel can write in place, applied up front otherwise
+        fuse = noise and z_label.dtype == torch.long and z_label.is_contiguous() and b <= 65536
+        if noise and not fuse:
+            _label_noise_(z_label)
+        lab = z_label if fuse else z_label.to(torch.long).contiguous()
+        idx = z_idx.to(torch.long).contiguous()
+        cfg = N.LossCfg(**dict(cfg_items), label_noise=1 if fuse else 0)
+        want = z.dtype if loss_dtype is None else loss_dtype
         with torch.cuda.device(zz.device):
             ws_bytes = N.lib.wealy_loss_workspace_bytes(b, d, cfg.passes)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=zz.device)
             out = torch.empty(N.OUT_COUNT, dtype=torch.float64, device=zz.device)
+            cast = torch.empty(N.OUT_COUNT, dtype=z.dtype, device=zz.device)
             N.check(N.lib.wealy_loss_forward(ctypes.byref(cfg), zz.data_ptr(), b, zz.stride(0), d, code, lab.data_ptr(),
-                                             idx.data_ptr(), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                             idx.data_ptr(), out.data_ptr(), cast.data_ptr(), ws.data_ptr(), ws_bytes,
                                              N.stream_ptr(zz.device)))
         ctx.save_for_backward(zz, ws)
         ctx.cfg_items = cfg_items
-        loss = out[0].to(ctx.in_dtype if loss_dtype is None else loss_dtype)
-        ctx.mark_non_differentiable(out)
-        return loss, out
+        if ctx.in_dtype == torch.float64 and loss_dtype is None:
+            want = torch.float64
+        stats = cast if want == z.dtype else out.to(want)
+        ctx.mark_non_differentiable(stats)
+        return stats[0], stats
 
     @staticmethod
     def backward(ctx, grad_loss, _grad_stats):
         zz, ws = ctx.saved_tensors
-        cfg = N.LossCfg(**dict(ctx.cfg_items))
         b, d = zz.shape
         dz = torch.empty_like(zz)
-        g = grad_loss.detach().to(torch.float32).reshape(1).contiguous()
+        g = grad_loss.detach()
+        if g.dtype not in (torch.float32,) + _HALF:
+            g = g.to(torch.float32)
+        g = g.reshape(1)
+        cfg = N.LossCfg(**dict(ctx.cfg_items), grad_dtype=N.dtype_code(g.dtype))
         with torch.cuda.device(zz.device):
             N.check(N.lib.wealy_loss_backward(ctypes.byref(cfg), zz.data_ptr(), b, zz.stride(0), d,
                                               N.dtype_code(zz.dtype), g.data_ptr(), dz.data_ptr(), dz.stride(0),
                                               ws.data_ptr(), ws.numel(), N.stream_ptr(zz.device)))
-        return dz.to(ctx.in_dtype), None, None, None, None
+        return (dz if ctx.in_dtype == zz.dtype else dz.to(ctx.in_dtype)), None, None, None, None, None
 
 
 def _passes(precision, z):
@@ -87,11 +106,12 @@ def _passes(precision, z):
     return passes_of(precision)
 
 
-def _run(z, z_label, z_idx, loss_dtype=None, **cfg):
+def _run(z, z_label, z_idx, loss_dtype=None, noise=True, **cfg):
+    """-> (loss, stats[WEALY_OUT_COUNT]) both in the output dtype (z's unless loss_dtype says otherwise)."""
     base = dict(kind=0, passes=3, temperature=1.0, gamma=0.0, b=0.0, eps=1e-8, epsilon=1e-6, uw=0.0,
                 numerically_friendly=1)
     base.update(cfg)
-    return _FusedLoss.apply(z, z_label, z_idx, tuple(sorted(base.items())), loss_dtype)
+    return _FusedLoss.apply(z, z_label, z_idx, tuple(sorted(base.items())), loss_dtype, noise)
 
 
 class NTXentLoss(nn.Module):
@@ -106,10 +126,8 @@ class NTXentLoss(nn.Module):
     def forward(self, z_label, z_idx, z, extra=None):
         assert len(z_label) == len(z_idx) and len(z_label) == len(z)
         N.require_cuda(z, z_label, z_idx)
-        _label_noise_(z_label)
-        loss, st = _run(z, z_label, z_idx, self.loss_dtype, kind=N.LOSS_NTXENT, passes=_passes(self.precision, z),
-                        temperature=float(self.tau))
-        stats = st.to(loss.dtype)
+        loss, stats = _run(z, z_label, z_idx, self.loss_dtype, kind=N.LOSS_NTXENT, passes=_passes(self.precision, z),
+                           temperature=float(self.tau))            # (label noise of :34-35 happens inside)
         logdict = {"l_main": loss, "v_zmax": stats[1], "v_zmean": stats[2], "v_zstd": stats[3]}
         return loss, logdict
 
@@ -137,8 +155,7 @@ class CLEWSLoss(nn.Module):
         B = z.size(0)
         assert len(z_label) == len(z_idx) == B and B >= 4
         N.require_cuda(z, z_label, z_idx)
-        _label_noise_(z_label)
-        # warm-up of the uniformity weight (lib/losses.py:248-258)
+        # warm-up of the uniformity weight (lib/losses.py:248-258); the label noise of :221-222 happens inside _run
         uw = self.uniformity_weight
         if self.warmup_steps > 0:
             step = None
@@ -148,10 +165,9 @@ class CLEWSLoss(nn.Module):
                 step = int(self.global_step)
             if step is not None:
                 uw = float(min(self.uniformity_weight, self.uniformity_weight * (step + 1) / self.warmup_steps))
-        loss, st = _run(z, z_label, z_idx, self.loss_dtype, kind=N.LOSS_CLEWS, passes=_passes(self.precision, z), gamma=self.gamma,
-                        b=self.b, eps=self.eps, epsilon=self.epsilon, uw=uw,
-                        numerically_friendly=1 if numerically_friendly else 0)
-        stats = st.to(loss.dtype)
+        loss, stats = _run(z, z_label, z_idx, self.loss_dtype, kind=N.LOSS_CLEWS, passes=_passes(self.precision, z),
+                           gamma=self.gamma, b=self.b, eps=self.eps, epsilon=self.epsilon, uw=uw,
+                           numerically_friendly=1 if numerically_friendly else 0)
         logdict = {
             "l_main": loss,
             "l_cent": stats[4],

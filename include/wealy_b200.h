@@ -233,14 +233,20 @@ typedef struct wealy_loss_cfg {
   float eps, epsilon;
   float uw;          /* CLEWS resolved uniformity weight */
   int numerically_friendly;
+  int label_noise;   /* forward: apply lib/losses.py:34-35 inside the call -- a batch with a single label gets its first
+                        max(2, b / 100) labels overwritten with -1 IN PLACE (single-GPU entry point, b <= 65536) */
+  int grad_dtype;    /* backward: element type of *grad_out (WEALY_F32 / F16 / BF16) */
 } wealy_loss_cfg;
 
 size_t wealy_loss_workspace_bytes(int64_t b, int64_t d, int passes);
+/* out: WEALY_OUT_COUNT doubles (all written); out_cast (nullable): the same numbers in z's element type -- what the
+ * reference's modules hand back (loss and logdict carry z's dtype, lib/losses.py:65-72).  z_label is written only
+ * when cfg->label_noise is set.  grad_out: one element of type cfg->grad_dtype.                                  */
 int wealy_loss_forward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
-                       const int64_t* z_label, const int64_t* z_idx, double* out, void* workspace,
+                       int64_t* z_label, const int64_t* z_idx, double* out, void* out_cast, void* workspace,
                        size_t workspace_bytes, void* stream);
 int wealy_loss_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b, int64_t ldz, int64_t d, int dtype,
-                        const float* grad_out, void* dz, int64_t ld_dz, void* workspace, size_t workspace_bytes,
+                        const void* grad_out, void* dz, int64_t ld_dz, void* workspace, size_t workspace_bytes,
                         void* stream);
 
 /* ---- f2: data-parallel losses (global-batch NT-Xent / CLEWS over the GPUs of one box; not in the reference, which is
@@ -264,10 +270,18 @@ int wealy_loss_dp_forward_phase(const wealy_loss_cfg* cfg, const void* z, int64_
                                 void* workspace, size_t workspace_bytes, void* stream);
 int wealy_loss_dp_buffers(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global, int64_t d,
                           int64_t nb, double** acc, int64_t* count_acc, uint32_t** acc_max, float** rowstat);
+/* Step 2 as ONE collective for equal shards (rank r owns anchors [r nb, (r + 1) nb)): wealy_loss_dp_pack writes this
+ * rank's {acc, acc_max, rowstat rows} into `record` (wealy_loss_dp_record_bytes(nb) bytes), the caller all-gathers the
+ * records in rank order, wealy_loss_dp_unpack folds `world` of them back into the workspace (sums, maxima, all rows). */
+size_t wealy_loss_dp_record_bytes(int64_t nb);
+int wealy_loss_dp_pack(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global, int64_t d,
+                       int64_t row0, int64_t nb, void* record, void* stream);
+int wealy_loss_dp_unpack(const wealy_loss_cfg* cfg, void* workspace, size_t workspace_bytes, int64_t b_global, int64_t d,
+                         int64_t nb, const void* records, int world, void* stream);
 int wealy_loss_dp_forward_finish(const wealy_loss_cfg* cfg, int64_t b_global, int64_t d, int64_t nb, double* out,
-                                 void* workspace, size_t workspace_bytes, void* stream);
+                                 void* out_cast, int cast_dtype, void* workspace, size_t workspace_bytes, void* stream);
 int wealy_loss_dp_backward(const wealy_loss_cfg* cfg, const void* z, int64_t b_global, int64_t ldz, int64_t d, int dtype,
-                           int64_t row0, int64_t nb, const float* grad_out, void* dz_rows, int64_t ld_dz, void* workspace,
+                           int64_t row0, int64_t nb, const void* grad_out, void* dz_rows, int64_t ld_dz, void* workspace,
                            size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

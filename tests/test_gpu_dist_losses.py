@@ -24,7 +24,7 @@ def _cfgs():
     }
 
 
-def _emulated(cfg_items, z, lab, idx, bounds, phased=False):
+def _emulated(cfg_items, z, lab, idx, bounds, phased=False, packed=False):
     """Run the shards [bounds[r], bounds[r+1]) as if they were ranks; collectives by hand.  phased: the forward in the
     two phases of the overlapped path -- phase 1 sees a batch in which ONLY the shard's own rows are valid."""
     from wealy_b200.dist_losses import ShardState
@@ -42,6 +42,25 @@ def _emulated(cfg_items, z, lab, idx, bounds, phased=False):
             st = ShardState(cfg_items, z, lab, idx, bounds[r], bounds[r + 1] - bounds[r])
             st.forward_local()
         states.append(st)
+    sizes = {bounds[r + 1] - bounds[r] for r in range(len(bounds) - 1)}
+    if packed and len(sizes) == 1:
+        # exchange 2 as the product does it over NCCL: one record per rank, "all-gathered" by hand, unpacked everywhere
+        import ctypes
+        from wealy_b200 import _native as N
+        nb, world = sizes.pop(), len(states)
+        rec = N.lib.wealy_loss_dp_record_bytes(nb)
+        recs = torch.zeros((world, rec), dtype=torch.uint8, device=z.device)
+        for r, st in enumerate(states):
+            N.check(N.lib.wealy_loss_dp_pack(ctypes.byref(st.cfg), st.ws.data_ptr(), st.ws_bytes, st.bg, st.d, st.row0, st.nb,
+                                             recs[r].data_ptr(), N.stream_ptr(z.device)))
+        outs, grads = [], []
+        for st in states:
+            N.check(N.lib.wealy_loss_dp_unpack(ctypes.byref(st.cfg), st.ws.data_ptr(), st.ws_bytes, st.bg, st.d, st.nb,
+                                               recs.data_ptr(), world, N.stream_ptr(z.device)))
+            outs.append(st.forward_finish())
+            grads.append(st.backward(torch.ones((), device=z.device)))
+        torch.cuda.synchronize()
+        return outs, torch.cat(grads)
     bufs = [st.buffers() for st in states]
     acc = sum(b[0].clone() for b in bufs)                                   # all-reduce SUM
     accm = torch.stack([b[1] for b in bufs]).max(dim=0).values              # all-reduce MAX
@@ -91,9 +110,12 @@ def test_two_phase_forward_equals_one_shot(kind, bounds):
     z, lab, idx = s["z"], s["label"], s["idx"]
     o1, g1 = _emulated(_cfgs()[kind], z, lab, idx, bounds)
     o2, g2 = _emulated(_cfgs()[kind], z, lab, idx, bounds, phased=True)
-    for a, c in zip(o1, o2):
+    o3, g3 = _emulated(_cfgs()[kind], z, lab, idx, bounds, phased=True, packed=True)   # + exchange 2 as one packed record per rank
+    for a, c, e in zip(o1, o2, o3):
         assert torch.isfinite(c[:11]).all() and torch.allclose(a, c, rtol=1e-6, atol=1e-9)
+        assert torch.allclose(a, e, rtol=1e-6, atol=1e-9)
     assert torch.isfinite(g2).all() and float((g1 - g2).norm()) <= 1e-6 * float(g1.norm())
+    assert float((g1 - g3).norm()) <= 1e-6 * float(g1.norm())
 
 
 def test_emulated_ranks_against_reference_outputs(golden):
