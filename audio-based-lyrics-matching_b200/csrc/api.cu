@@ -1,4 +1,5 @@
 // C-ABI entry points (include/wealy_b200.h) and host-side launch logic.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -617,6 +618,7 @@ struct wealy_eval_plan {
   int *s_i = nullptr, *s_seg_lo = nullptr, *s_seg_len = nullptr, *s_npos = nullptr;
   long long* s_off = nullptr;
   float4* s_lvl = nullptr;
+  void* lvl_thr_buf = nullptr;  // all-vs-all plans: [s_lvl | thr] in one allocation (one all-reduce sums both over the ranks)
   uint2* s_cinfo = nullptr;
   unsigned char* s_dirty = nullptr;
   int64_t s_padded = 0;
@@ -632,8 +634,9 @@ struct wealy_eval_plan {
 extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
   if (!p) return;
   void* ptrs[] = {p->q_c, p->q_i, p->sorted_c, p->sorted_idx, p->seg_lo, p->seg_len, p->npos, p->off,
-                  p->raw, p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf, p->tks_buf,
-                  p->s_i, p->s_seg_lo, p->s_seg_len, p->s_npos, p->s_off, p->s_lvl, p->s_cinfo, p->s_dirty};
+                  p->raw, p->lvl_thr_buf ? nullptr : (void*)p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf, p->tks_buf,
+                  p->s_i, p->s_seg_lo, p->s_seg_len, p->s_npos, p->s_off, p->lvl_thr_buf ? p->lvl_thr_buf : (void*)p->s_lvl,
+                  p->s_cinfo, p->s_dirty};
   // frees are ordered behind the last work that touched the buffers: the stream of the last run
   cudaStream_t fs = p->timed ? p->last_stream : p->stream;
   for (void* q : ptrs) dev_free(q, fs);
@@ -731,7 +734,7 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
     CU_TRY(dev_alloc((void**)&p->s_seg_len, (size_t)n * 4 + 4, s));
     CU_TRY(dev_alloc((void**)&p->s_npos, (size_t)n * 4 + 4, s));
     CU_TRY(dev_alloc((void**)&p->s_off, ((size_t)n + 1) * 8, s));
-    CU_TRY(dev_alloc((void**)&p->s_lvl, (size_t)p->s_padded * 16, s));
+    // (allocated below, next to the thresholds, once their number is known)
     CU_TRY(dev_alloc((void**)&p->s_cinfo, (size_t)p->s_padded * 8, s));
     CU_TRY(dev_alloc((void**)&p->s_dirty, (size_t)nrb * nct, s));
     gather_i32_kernel<<<(unsigned)ceil_div(n, T), T, 0, s>>>(p->q_i, p->sorted_idx, n, p->s_i);
@@ -770,7 +773,13 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   p->max_relevant = (int64_t)totals_h[1];
   const size_t pairs = (size_t)(total > 0 ? total : 1);
   CU_TRY(dev_alloc((void**)&p->raw, pairs * 4, s));
-  CU_TRY(dev_alloc((void**)&p->thr, pairs * 4, s));
+  if (p->same_ids) {
+    CU_TRY(dev_alloc(&p->lvl_thr_buf, (size_t)p->s_padded * 16 + pairs * 4, s));
+    p->s_lvl = reinterpret_cast<float4*>(p->lvl_thr_buf);
+    p->thr = reinterpret_cast<float*>(p->s_lvl + p->s_padded);
+  } else {
+    CU_TRY(dev_alloc((void**)&p->thr, pairs * 4, s));
+  }
   CU_TRY(dev_alloc((void**)&p->hist, pairs * 4, s));
   CU_TRY(dev_alloc((void**)&p->lim, (size_t)nq * 4 + 4, s));
   CU_TRY(dev_alloc((void**)&p->cnt, (size_t)nq * 4 + 4, s));
@@ -837,10 +846,14 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
                          int64_t ld_c, int64_t d, int dtype, float eps, int passes, int topk, float* aps,
                          float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, int shard_rank,
                          int shard_world, bool finish, void* stream, int chunks = 1, int redux = WEALY_REDUX_MIN,
-                         const int* q_len = nullptr, const int* c_len = nullptr, bool allow_sym_topk = true) {
+                         const int* q_len = nullptr, const int* c_len = nullptr, bool allow_sym_topk = true, int stage = 0) {
+  // stage (sharded symmetric sweep only): 0 = everything in one call; 1 = prep + the relevant similarities of THIS
+  // rank's share of the queries, then return (the caller sums the threshold buffer over the ranks); 2 = the sweep,
+  // on the planes and thresholds stage 1 left in the plan
   cudaStream_t s = (cudaStream_t)stream;
   if (!p) return fail(WEALY_ERR_BAD_ARG, "null plan");
-  if (!queries_z || !candidates_z) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (stage != 2 && (!queries_z || !candidates_z)) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (stage == 2) queries_z = candidates_z = p;  // (not dereferenced: the planes are in the plan)
   if (finish && (!aps || !r1s || !sums)) return fail(WEALY_ERR_BAD_ARG, "null pointer");
   if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(WEALY_ERR_BAD_ARG, "bad shard %d/%d", shard_rank, shard_world);
   if (d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad embedding size %lld", (long long)d);
@@ -901,24 +914,37 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     CU_TRY(cudaEventCreate(&p->ev1));
     for (cudaEvent_t& e : p->evs) CU_TRY(cudaEventCreate(&e));
   }
-  CU_TRY(cudaEventRecord(p->evs[0], s));
-  W_TRY(launch_prep(queries_z, ld_q, rows_q, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s,
-                    sym ? p->sorted_idx : nullptr, sym ? (int)nq : 0));
-  if (!same) W_TRY(launch_prep(candidates_z, ld_c, rc, d, dtype, kPrepL2AddEps, eps, pc, nullptr, nullptr, 0, nullptr, 0, s));
+  if (stage != 0 && !(sym && shard_world > 1)) return fail(WEALY_ERR_BAD_ARG, "staged runs belong to the sharded symmetric sweep");
+  if (stage != 2) CU_TRY(cudaEventRecord(p->evs[0], s));
+  if (stage != 2) {
+    W_TRY(launch_prep(queries_z, ld_q, rows_q, d, dtype, kPrepL2AddEps, eps, pq, nullptr, nullptr, 0, nullptr, 0, s,
+                      sym ? p->sorted_idx : nullptr, sym ? (int)nq : 0));
+    if (!same) W_TRY(launch_prep(candidates_z, ld_c, rc, d, dtype, kPrepL2AddEps, eps, pc, nullptr, nullptr, 0, nullptr, 0, s));
+  }
 
   // K_pos: relevant similarities, sorted per query
-  CU_TRY(cudaEventRecord(p->evs[1], s));
-  {
+  if (stage != 2) CU_TRY(cudaEventRecord(p->evs[1], s));
+  if (stage != 2) {
     const int threads = 256;
     if (sym) {
+      // stage 1: this rank's share of the 16-query blocks only; the buffer {lvl, thr} is zeroed first so that the sum
+      // over the ranks assembles the whole of it
+      int q_lo = 0, q_hi = (int)nq;
+      if (stage == 1) {
+        const int64_t nblk = ceil_div(nq, 16);
+        q_lo = (int)(nblk * shard_rank / shard_world) * 16;
+        q_hi = (int)std::min<int64_t>((nblk * (shard_rank + 1) / shard_world) * 16, nq);
+        CU_TRY(cudaMemsetAsync(p->lvl_thr_buf, 0, (size_t)p->s_padded * 16 + (size_t)(p->total_pairs > 0 ? p->total_pairs : 1) * 4, s));
+      }
       // the plan's cnt array doubles as the per-query fill counter of step 1 (step 2 rewrites it)
       CU_TRY(cudaMemsetAsync(p->cnt, 0, (size_t)nq * 4, s));
-      pos_pairs_sorted_kernel<false><<<(unsigned)ceil_div(nq, 16), threads, 0, s>>>(pq.hi, pq.lo, (int)pq.d_pad, p->sorted_c, p->s_i,
-                                                                         (int)nq, p->s_seg_lo, p->s_seg_len, p->s_off,
-                                                                         p->raw, p->cnt);
+      if (q_hi > q_lo)
+        pos_pairs_sorted_kernel<false><<<(unsigned)ceil_div(q_hi - q_lo, 16), threads, 0, s>>>(
+            pq.hi, pq.lo, (int)pq.d_pad, p->sorted_c, p->s_i, (int)nq, p->s_seg_lo, p->s_seg_len, p->s_off, p->raw, p->cnt, nullptr,
+            q_lo, q_hi);
       const unsigned blocks = (unsigned)ceil_div(p->s_padded * 32, threads);
       pos_sort_sorted_kernel<<<blocks, threads, 0, s>>>(p->s_npos, (int)nq, (int)p->s_padded, p->s_off, p->raw, p->thr,
-                                                        p->cnt, p->s_lvl, p->s_cinfo);
+                                                        p->cnt, p->s_lvl, p->s_cinfo, q_lo, q_hi);
     } else if (chunks > 1) {
       if (nq > 0) pos_thresholds_tracks_kernel<<<(unsigned)nq, threads, 0, s>>>(pq.hi, pq.lo, pc.hi, pc.lo, (int)pq.d_pad, chunks, red_inner,
                                                               red_outer, red_scale, p->q_i, (int)nq, p->sorted_idx,
@@ -939,6 +965,11 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
                                                        p->thr, p->lim, p->cnt);
     }
     CU_TRY(cudaGetLastError());
+  }
+  if (stage == 1) {
+    p->last_sym = true;
+    p->last_stream = s;
+    return WEALY_OK;
   }
   // ---- top-k in the symmetric sweep: sampled pre-pass -> per-query lower bound of the k-th best similarity
   float* tk_val = nullptr;
@@ -1235,6 +1266,31 @@ extern "C" int wealy_eval_run_ragged(wealy_eval_plan* p, const void* queries_z, 
   if (!q_len || !c_len) return fail(WEALY_ERR_BAD_ARG, "null chunk counts");
   return eval_run_impl(p, queries_z, ld_q, candidates_z, ld_c, d, dtype, eps, passes, topk, aps, r1s, sums, topk_idx,
                        topk_sim, 0, 1, true, stream, chunks, redux, q_len, c_len);
+}
+
+// The same in two stages, so that the relevant similarities (K_pos) are computed ONCE across the ranks instead of once
+// per rank: _prepare preps the planes and fills this rank's share of the threshold buffer (zeros elsewhere), the caller
+// sums the buffer of wealy_eval_plan_thresholds over the ranks (one all-reduce of floats), _sweep runs the rank's
+// share of the row blocks on the result.
+extern "C" int wealy_eval_shard_prepare(wealy_eval_plan* p, const void* z, int64_t ld, int64_t d, int dtype, float eps,
+                                        int passes, int shard_rank, int shard_world, void* stream) {
+  if (shard_world < 2) return fail(WEALY_ERR_BAD_ARG, "staged sweeps are for two or more ranks");
+  return eval_run_impl(p, z, ld, z, ld, d, dtype, eps, passes, 0, nullptr, nullptr, nullptr, nullptr, nullptr, shard_rank,
+                       shard_world, false, stream, 1, WEALY_REDUX_MIN, nullptr, nullptr, true, 1);
+}
+
+extern "C" int wealy_eval_plan_thresholds(const wealy_eval_plan* p, void** values, int64_t* count) {
+  if (!p || !values || !count) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (!p->lvl_thr_buf) return fail(WEALY_ERR_BAD_ARG, "the plan is not an all-vs-all plan");
+  *values = p->lvl_thr_buf;
+  *count = p->s_padded * 4 + (p->total_pairs > 0 ? p->total_pairs : 1);
+  return WEALY_OK;
+}
+
+extern "C" int wealy_eval_shard_sweep(wealy_eval_plan* p, int64_t d, int passes, int shard_rank, int shard_world, void* stream) {
+  if (shard_world < 2) return fail(WEALY_ERR_BAD_ARG, "staged sweeps are for two or more ranks");
+  return eval_run_impl(p, nullptr, 0, nullptr, 0, d, WEALY_F32, 0.f, passes, 0, nullptr, nullptr, nullptr, nullptr, nullptr,
+                       shard_rank, shard_world, false, stream, 1, WEALY_REDUX_MIN, nullptr, nullptr, true, 2);
 }
 
 // multi-GPU all-vs-all: every rank sweeps its share of the row blocks of the SAME symmetric problem ...

@@ -312,9 +312,11 @@ __global__ void __launch_bounds__(256) pos_pairs_sorted_kernel(
     const __half* __restrict__ hi, const __half* __restrict__ lo, int d_pad, const int* __restrict__ s_c,
     const int* __restrict__ s_i, int n, const int* __restrict__ seg_lo, const int* __restrict__ seg_len,
     const long long* __restrict__ off, float* __restrict__ raw, int* __restrict__ fill,
-    const int* __restrict__ perm = nullptr) {
+    const int* __restrict__ perm = nullptr, int q_lo = 0, int q_hi = 0x7fffffff) {
+  // [q_lo, q_hi): the queries this launch computes (multi-GPU: every rank takes a range of 16-query blocks, the
+  // thresholds are then summed over the ranks -- the other ranks contribute zeros)
   auto plane_row = [&](int srow) { return kGather ? __ldg(perm + srow) : spread_plane_of(srow); };
-  const int q0 = blockIdx.x * 16;
+  const int q0 = q_lo + blockIdx.x * 16;
   const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
   const int g = lane >> 2, tig = lane & 3;
   const int qlast = min(q0 + 15, n - 1);
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(256) pos_pairs_sorted_kernel(
     for (int e = 0; e < 4; ++e) {
       const int q = q0 + g + (e >> 1) * 8;
       const int j = j0 + tig * 2 + (e & 1);
-      if (q < n && j < hi_row && s_c[q] == s_c[j] && s_i[q] != s_i[j]) {
+      if (q < n && q < q_hi && j < hi_row && s_c[q] == s_c[j] && s_i[q] != s_i[j]) {
         const int oq = kGather ? __ldg(perm + q) : q;
         const int slot = atomicAdd(fill + oq, 1);
         raw[off[oq] + slot] = c[e];
@@ -398,12 +400,21 @@ __global__ void __launch_bounds__(256) pos_sort_sorted_kernel(const int* __restr
                                                               const long long* __restrict__ off,
                                                               const float* __restrict__ raw, float* __restrict__ thr,
                                                               int* __restrict__ cnt, float4* __restrict__ lvl,
-                                                              uint2* __restrict__ cinfo) {
+                                                              uint2* __restrict__ cinfo, int q_lo = 0, int q_hi = 0x7fffffff) {
   const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (q >= n_padded) return;
   const float inf = __int_as_float(0x7f800000);
   const int pq = spread_plane_of(q);  // lvl / cinfo are read by plane row (per-tile bulk copies of the sweep)
+  if (q < n && (q < q_lo || q >= q_hi)) {
+    // another rank's query: id-only data here, zeros where the sum over the ranks will put that rank's thresholds
+    if (lane == 0) {
+      cnt[q] = npos[q];
+      lvl[pq] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cinfo[pq] = make_uint2((unsigned)off[q], (unsigned)npos[q]);
+    }
+    return;
+  }
   if (q >= n) {
     if (lane == 0) {
       lvl[pq] = make_float4(inf, inf, inf, inf);

@@ -91,6 +91,17 @@ def _agree(flag, device, group=None):
     return int(t.item())
 
 
+def sharded_step(plan, z, rank, world, *, eps=1e-6, precision=None, group=None):
+    """The multi-GPU all-vs-all sweep up to (not including) finish(): the relevant similarities are computed once across
+    the ranks (each rank its share of the queries; one all-reduce of floats assembles them -- every element has a single
+    non-zero contribution, so the sum is exact), every rank sweeps the row blocks rank (mod world) of the symmetric
+    problem, and the per-(query, relevant item) rank counters are summed (the second all-reduce)."""
+    plan.shard_prepare(z, rank, world, eps=eps, precision=precision)
+    dist.all_reduce(plan.thresholds_tensor(), op=dist.ReduceOp.SUM, group=group)
+    plan.shard_sweep(rank, world)
+    dist.all_reduce(plan.counts_tensor(), op=dist.ReduceOp.SUM, group=group)
+
+
 def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=None, allow_empty=False):
     """All-vs-all evaluation of one set (clique ids c, version ids i, embeddings z) over all ranks of `group`.
     Every rank passes the full tensors (host embeddings are uploaded 1/world per rank and all-gathered over
@@ -123,9 +134,7 @@ def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=N
     if world == 1:
         res = plan.run(z, z, eps=eps, precision=precision, allow_empty=allow_empty)
     else:
-        plan.sweep_shard(z, rank, world, eps=eps, precision=precision)
-        counts = plan.counts_tensor()
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)   # the path's one exchange step
+        sharded_step(plan, z, rank, world, eps=eps, precision=precision, group=group)
         res = plan.finish()
     s = res["sums"].cpu()                                            # one 24-byte device -> host read
     n = max(float(s[2]), 1.0)

@@ -85,6 +85,38 @@ class EvalPlan:
                 passes_of(precision), int(shard_rank), int(shard_world), N.stream_ptr(self.device)))
         self._keepalive = z
 
+    def shard_prepare(self, z, shard_rank, shard_world, *, eps=1e-6, precision=None):
+        """Stage 1 of the sharded sweep: planes of the whole corpus, thresholds of THIS rank's share of the queries.
+        Then sum thresholds_tensor() over the ranks and call shard_sweep()."""
+        z = _to_device(z, self.device)
+        if z.dtype == torch.float64:
+            z = z.float()
+        assert z.ndim == 2 and z.shape[0] == self.nq == self.nc
+        if z.stride(1) != 1:
+            z = z.contiguous()
+        self._shard_dim, self._shard_passes = z.shape[1], passes_of(precision)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.wealy_eval_shard_prepare(
+                self._handle, z.data_ptr(), z.stride(0), z.shape[1], N.dtype_code(z.dtype), float(eps), self._shard_passes,
+                int(shard_rank), int(shard_world), N.stream_ptr(self.device)))
+        self._keepalive = z
+
+    def thresholds_tensor(self):
+        """float32 view (no copy) of {lowest thresholds, all thresholds}: what a multi-GPU run all-reduces (SUM) between
+        shard_prepare() and shard_sweep()."""
+        ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+        N.check(N.lib.wealy_eval_plan_thresholds(self._handle, ctypes.byref(ptr), ctypes.byref(n)))
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(_Dev(), device=self.device)
+
+    def shard_sweep(self, shard_rank, shard_world):
+        """Stage 2: this rank's row blocks of the symmetric sweep on the planes / thresholds stage 1 left in the plan."""
+        with torch.cuda.device(self.device):
+            N.check(N.lib.wealy_eval_shard_sweep(self._handle, self._shard_dim, self._shard_passes, int(shard_rank),
+                                                 int(shard_world), N.stream_ptr(self.device)))
+
     def counts_tensor(self):
         """int32 view (no copy) of the plan's per-(query, relevant item) rank counters: the buffer a
         multi-GPU run all-reduces between sweep_shard() and finish()."""

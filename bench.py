@@ -326,7 +326,7 @@ def leg_c3(dev, world, rank, peaks, precision, sync_all):
     """configs[2]: 500 000 x 1024 all-vs-all over the N GPUs of this run (strong scaling: total work fixed)."""
     import torch
     import torch.distributed as dist
-    from wealy_b200 import evaluation as we
+    from wealy_b200 import evaluation as we, dist as wd
     from wealy_b200.data import synth
     n = 500_000
     s = synth.make_eval_set(n, DIM, seed=3, device=dev, md5_ids=False)
@@ -336,8 +336,7 @@ def leg_c3(dev, world, rank, peaks, precision, sync_all):
     def step():
         if world == 1:
             return plan.run(z, z, precision=precision)
-        plan.sweep_shard(z, rank, world, precision=precision)
-        dist.all_reduce(plan.counts_tensor())
+        wd.sharded_step(plan, z, rank, world, precision=precision)
         return plan.finish()
 
     ms, res = timed_steps(step, 1, 3, dev, sync_all)
@@ -495,8 +494,7 @@ def run_gpu_arm(args):
     def step_resident():
         if world == 1:
             return plan.run(z, z, precision=args.precision)
-        plan.sweep_shard(z, rank, world, precision=args.precision)
-        dist.all_reduce(plan.counts_tensor())          # int32 rank counters, SUM over ranks
+        wd.sharded_step(plan, z, rank, world, precision=args.precision)   # two all-reduces: thresholds, rank counters
         return plan.finish()
 
     for _ in range(args.warmup):

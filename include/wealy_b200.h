@@ -144,6 +144,15 @@ int wealy_eval_run_ragged(wealy_eval_plan* plan, const void* queries_z, int64_t 
 int wealy_eval_sweep_shard(wealy_eval_plan* plan, const void* z, int64_t ld, int64_t d, int dtype, float eps,
                            int passes, int shard_rank, int shard_world, void* stream);
 int wealy_eval_plan_counts(const wealy_eval_plan* plan, void** counts, int64_t* count);
+/* The sharded sweep in two stages: the relevant similarities (the thresholds the ranks are counted against) are computed
+ * once ACROSS the ranks instead of once per rank.  _prepare: normalise + split the whole corpus, thresholds of this
+ * rank's share of the queries (zeros elsewhere); the caller sums the `count` floats at `values`
+ * (wealy_eval_plan_thresholds) over the ranks -- every element has exactly one non-zero contribution, so the sum is
+ * exact --; _sweep: the rank's row blocks, as wealy_eval_sweep_shard; then counts / finish as above.            */
+int wealy_eval_shard_prepare(wealy_eval_plan* plan, const void* z, int64_t ld, int64_t d, int dtype, float eps, int passes,
+                             int shard_rank, int shard_world, void* stream);
+int wealy_eval_plan_thresholds(const wealy_eval_plan* plan, void** values, int64_t* count);
+int wealy_eval_shard_sweep(wealy_eval_plan* plan, int64_t d, int passes, int shard_rank, int shard_world, void* stream);
 int wealy_eval_finish(wealy_eval_plan* plan, float* aps, float* r1s, double* sums, void* stream);
 /* Per-item ranks of the last run -- the quantities AP and R1 are made of.  offsets [nq + 1] int64 (CSR over the
  * caller's queries; offsets[nq] = total_pairs of wealy_eval_plan_info), ranks / sims [total_pairs]: for every query its

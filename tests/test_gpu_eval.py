@@ -625,3 +625,35 @@ def test_symmetric_topk_falls_back_when_a_list_overflows():
     _, _, idx_o, sim_o = oev.evaluate_argsort(c.cpu()[qs], i.cpu()[qs], z.cpu()[qs], c.cpu(), i.cpu(), z.cpu(), topk=20)
     assert (sim[qs] - sim_o).abs().max() <= 4e-6
     plan.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_staged_sharded_sweep_emulated_on_one_gpu(world):
+    """The multi-GPU path as the product runs it: the relevant similarities are computed ONCE across the ranks (each rank
+    its share of the queries, the float buffer summed -- every element has one non-zero contribution), then every rank
+    sweeps its row blocks and the rank counters are summed.  Ranks emulated one after the other on a single GPU."""
+    s = _synth().make_eval_set(2300, 96, seed=14)
+    we = _we()
+    c, i, z = s["c"].cuda(), s["i"].cuda(), s["z"].cuda()
+    ref = we.EvalPlan(c, i, c, i).run(z, z)
+    plans = [we.EvalPlan(c, i, c, i) for _ in range(world)]
+    for r, pl in enumerate(plans):
+        pl.shard_prepare(z, r, world)
+    thr = [pl.thresholds_tensor() for pl in plans]
+    nz = torch.stack([(t != 0) & torch.isfinite(t) for t in thr]).sum(0)
+    assert int(nz.max()) <= 1                                       # disjoint shares: the sum is exact
+    total = torch.stack(thr).sum(0)
+    for t in thr:
+        t.copy_(total)
+    counts = None
+    for r, pl in enumerate(plans):
+        pl.shard_sweep(r, world)
+        cnt = pl.counts_tensor()
+        counts = cnt.clone() if counts is None else counts + cnt
+    plans[0].counts_tensor().copy_(counts)
+    out = plans[0].finish()
+    torch.cuda.synchronize()
+    assert torch.equal(out["aps"], ref["aps"]) and torch.equal(out["r1s"], ref["r1s"])
+    _check_all_item_ranks(plans[0], s["c"], s["i"], s["z"])         # plan.ranks() after a staged run
+    for pl in plans:
+        pl.close()
