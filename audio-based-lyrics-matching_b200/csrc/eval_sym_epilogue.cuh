@@ -210,39 +210,31 @@ struct EvalSymEpi {
     if (en.on) atomicAdd(p.hist + slot, 1u);
   }
 
-  // Bin the queued elements: kChains x 32 per iteration -- every lane walks kChains independent binary searches, so
-  // that their dependent loads (shared-memory cache for row entries, the global CSR through L2 for column entries:
-  // ~10 % of the kernel's stall samples with two chains) overlap.
-  static constexpr int kChains = 4;
+  // Bin the queued elements: 2 x 32 per iteration so the two dependent load -> compare chains overlap (four chains were
+  // measured slower: 23.6 vs 22.7 ms per sweep at C2, 66 vs 48 ms on MAP-0.1 data -- the loop then runs to the depth of
+  // the deepest of four searches and the extra registers cost more than the overlap returns).
   __device__ static __forceinline__ void drain(const Params& p, RowState& st, const EpiCtx& ctx) {
     if (st.qn == 0) return;
     const int lane = (int)ptx::lane_id();
     __syncwarp();
     const int end = st.qn;
-    for (int r0 = 0; r0 < end; r0 += 32 * kChains) {
-      Ent en[kChains];
-      int lo[kChains], hi[kChains];
-#pragma unroll
-      for (int k = 0; k < kChains; ++k) {
-        fetch(p, ctx, en[k], r0 + 32 * k + lane, end);
-        lo[k] = 0;
-        hi[k] = en[k].len;
-      }
-      bool more = true;
-      while (more) {
-        more = false;
-#pragma unroll
-        for (int k = 0; k < kChains; ++k) {
-          if (lo[k] < hi[k]) {
-            const int mid = (lo[k] + hi[k]) >> 1;
-            if (en[k].tp[mid] < en[k].s) lo[k] = mid + 1; else hi[k] = mid;
-            more |= lo[k] < hi[k];
-          }
+    for (int r0 = 0; r0 < end; r0 += 64) {
+      Ent a, b;
+      fetch(p, ctx, a, r0 + lane, end);
+      fetch(p, ctx, b, r0 + 32 + lane, end);
+      int loa = 0, hia = a.len, lob = 0, hib = b.len;
+      while (loa < hia || lob < hib) {
+        if (loa < hia) {
+          const int mid = (loa + hia) >> 1;
+          if (a.tp[mid] < a.s) loa = mid + 1; else hia = mid;
+        }
+        if (lob < hib) {
+          const int mid = (lob + hib) >> 1;
+          if (b.tp[mid] < b.s) lob = mid + 1; else hib = mid;
         }
       }
-#pragma unroll
-      for (int k = 0; k < kChains; ++k)
-        if (r0 + 32 * k < end) count(p, st, ctx, en[k], lo[k], lane);
+      count(p, st, ctx, a, loa, lane);
+      if (r0 + 32 < end) count(p, st, ctx, b, lob, lane);
     }
     __syncwarp();
     st.qn = 0;
