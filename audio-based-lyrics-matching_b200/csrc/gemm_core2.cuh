@@ -196,8 +196,16 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
       uint32_t acc_phase = 0;
       int us = 0;
       uint32_t uphase = 0;
+#ifdef WEALY_PROFILE_WAITS
+      // where the MMA thread waits (diagnostic build: -DWEALY_PROFILE_WAITS, printed by a few CTAs)
+      long long w_unit = 0, w_acc = 0, w_full = 0, n_tiles_done = 0;
+      const long long t_begin = clock64();
+#define WEALY_TIMED(var, stmt) { const long long _t = clock64(); stmt; var += clock64() - _t; }
+#else
+#define WEALY_TIMED(var, stmt) stmt;
+#endif
       while (true) {
-        ptx::mbar_wait(&unit_full[us], uphase);
+        WEALY_TIMED(w_unit, ptx::mbar_wait(&unit_full[us], uphase))
         const int u = unit_slot[us];
         ptx::mbar_arrive(&unit_empty[us]);
         if (++us == 2) { us = 0; uphase ^= 1u; }
@@ -205,11 +213,14 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
         int rb, t0, t1;
         unit_tiles(u, rb, t0, t1);
         for (int t = t0; t < t1; ++t) {
-          ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u);  // both CTAs' epilogues have drained this accumulator
+          WEALY_TIMED(w_acc, ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1u))  // both CTAs' epilogues have drained this accumulator
           ptx::tc_fence_after_sync();
+#ifdef WEALY_PROFILE_WAITS
+          ++n_tiles_done;
+#endif
           const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kTileN);
           for (int kb = 0; kb < shape.k_blocks; ++kb) {
-            ptx::mbar_wait_cluster(&full_bar[stage], phase);
+            WEALY_TIMED(w_full, ptx::mbar_wait_cluster(&full_bar[stage], phase))
             ptx::tc_fence_after_sync();
             const uint32_t st = ptx::smem_u32(smem + stage * SM::kStageBytes);
             const uint64_t a_hi = ptx::make_smem_desc<SM::kSwizzle>(st);
@@ -232,6 +243,11 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
           if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
       }
+#ifdef WEALY_PROFILE_WAITS
+      if ((blockIdx.x % 37) == 0)
+        printf("wealy waits: cta %d tiles %lld total %lld cyc | wait unit %lld acc(epilogue) %lld full(tma) %lld\n", (int)blockIdx.x,
+               n_tiles_done, clock64() - t_begin, w_unit, w_acc, w_full);
+#endif
     }
   } else {
     // ===================================================== epilogue warps (both CTAs)

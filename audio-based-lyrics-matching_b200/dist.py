@@ -102,10 +102,14 @@ def sharded_step(plan, z, rank, world, *, eps=1e-6, precision=None, group=None):
     dist.all_reduce(plan.counts_tensor(), op=dist.ReduceOp.SUM, group=group)
 
 
-def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=None, allow_empty=False):
+def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=None, allow_empty=False, topk=None):
     """All-vs-all evaluation of one set (clique ids c, version ids i, embeddings z) over all ranks of `group`.
     Every rank passes the full tensors (host embeddings are uploaded 1/world per rank and all-gathered over
     NVLink).  -> dict(map, mr1, count, aps, r1s, plan); identical on every rank.
+
+    topk: per-query top-k lists are per-query state, not additive counters, so with more than one rank they take the
+    query-partitioned scheme (`evaluate_sharded`: every rank scores its slice of the queries against the replicated
+    corpus with the streaming top-k, the lists are all-gathered) -> also topk_idx / topk_sim.
 
     Like EvalPlan.run, a query without any relevant candidate raises ValueError unless allow_empty -- on every
     rank (all ranks build the same id plan), before the first collective."""
@@ -113,6 +117,11 @@ def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=N
     on = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if on else 0
     world = dist.get_world_size(group) if on else 1
+    if topk and world > 1:
+        if not torch.as_tensor(z).is_cuda:
+            z = upload_sharded(torch.as_tensor(z), torch.device("cuda", torch.cuda.current_device()), group)
+        return evaluate_sharded(c, i, z, c, i, z, topk=topk, precision=precision, eps=eps, group=group,
+                                allow_empty=allow_empty)
     side = None
     if world > 1 and not torch.as_tensor(z).is_cuda:
         # 1/world of the rows per rank + NVLink all-gather, issued on a side stream BEFORE the id plan is built: the
@@ -132,14 +141,17 @@ def evaluate_all_vs_all(c, i, z, *, precision=None, eps=1e-6, group=None, plan=N
         raise ValueError(f"{plan.queries_without_relevant} queries have no relevant candidate "
                          "(every clique needs >= 2 versions; pass allow_empty=True to score the rest)")
     if world == 1:
-        res = plan.run(z, z, eps=eps, precision=precision, allow_empty=allow_empty)
+        res = plan.run(z, z, eps=eps, precision=precision, allow_empty=allow_empty, topk=topk)
     else:
         sharded_step(plan, z, rank, world, eps=eps, precision=precision, group=group)
         res = plan.finish()
     s = res["sums"].cpu()                                            # one 24-byte device -> host read
     n = max(float(s[2]), 1.0)
-    return {"map": float(s[0]) / n, "mr1": float(s[1]) / n, "count": int(s[2]), "aps": res["aps"], "r1s": res["r1s"],
-            "plan": plan}
+    out = {"map": float(s[0]) / n, "mr1": float(s[1]) / n, "count": int(s[2]), "aps": res["aps"], "r1s": res["r1s"],
+           "plan": plan}
+    if topk and "topk_idx" in res:
+        out["topk_idx"], out["topk_sim"] = res["topk_idx"], res["topk_sim"]
+    return out
 
 
 def evaluate_sharded(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z, *, topk=None,

@@ -84,6 +84,11 @@ def _gloo_worker(rank, world, port, ret):
         ref_q = we.EvalPlan(c[q], i[q], c, i).run(z[q], z, topk=5)
         got = wd.evaluate_sharded(c[q], i[q], z[q], c, i, z, topk=5)
         ok &= torch.equal(got["aps"], ref_q["aps"]) and torch.equal(got["topk_idx"], ref_q["topk_idx"]) and got["count"] == 701
+        # all-vs-all with top-k on several ranks: query-partitioned underneath, lists gathered
+        ref_k = we.EvalPlan(c, i, c, i).run(z, z, topk=6)
+        got_k = wd.evaluate_all_vs_all(c, i, z, topk=6)
+        ok &= got_k["topk_idx"].shape == (3000, 6) and float((got_k["topk_sim"] - ref_k["topk_sim"]).abs().max()) <= 2e-6
+        ok &= abs(got_k["map"] - float(ref["aps"].double().mean())) <= 1e-6
         # a query without relevant candidates in ONE rank's slice: every rank raises (no rank is left in a collective)
         c_bad = c.clone()
         c_bad[0] = 10_000_000                                 # query 0 (rank 0's slice) loses its clique
