@@ -312,8 +312,10 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
 
 // CTA-pair kernel (gemm_core2.cuh): sh.n_row_blocks / group_rows / rb_stride / rb_offset are in SUPER row blocks
 template <class Epi, int kPasses, int kBlockK, int kEpiWarps = 8, bool kDyn = false>
-static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename Epi::Params& ep, cudaStream_t s) {
+static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename Epi::Params& ep, cudaStream_t s,
+                            const Planes* b_planes = nullptr) {
   constexpr int kStages = 4;
+  const Planes& b = b_planes ? *b_planes : a;  // (the symmetric sweep contracts one set of planes with itself)
   const int il = (sh.sym & 2) ? 2 : 1;  // row stride of the A boxes
   using SM = PairSmem<kPasses, kBlockK, kStages>;
   GemmTmaps maps;
@@ -321,10 +323,10 @@ static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename
   // A side: the two CTAs of a pair take the even / odd rows of a 256-row super block (row-strided boxes), so that
   // neighbouring rows -- same clique, same "hotness" -- are split evenly between the two coupled epilogues
   W_TRY(make_plane_tmap(&maps.a_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK, il));
-  W_TRY(make_plane_tmap(&maps.b_hi, a.hi, a.rows, a.d_pad, kTileM, kBlockK));
+  W_TRY(make_plane_tmap(&maps.b_hi, b.hi, b.rows, b.d_pad, kTileM, kBlockK));
   if (kPasses == 3) {
     W_TRY(make_plane_tmap(&maps.a_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK, il));
-    W_TRY(make_plane_tmap(&maps.b_lo, a.lo, a.rows, a.d_pad, kTileM, kBlockK));
+    W_TRY(make_plane_tmap(&maps.b_lo, b.lo, b.rows, b.d_pad, kTileM, kBlockK));
   } else {
     maps.a_lo = maps.a_hi;
     maps.b_lo = maps.b_hi;
@@ -344,6 +346,13 @@ static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename
   return WEALY_OK;
 }
 
+// Rectangle sweeps (queries != corpus, streaming top-k, chunked tracks) on the CTA-pair core: 256 x 256 tiles per pair
+// of SMs, each SM loads its 128 query rows and half of the tile's candidate rows -- 2/3 of the L2 -> shared-memory
+// traffic of the single-CTA kernel, which is what bounds these sweeps (WEALY_RECT_PAIR=0 selects the single-CTA kernel).
+template <class Epi>
+static int launch_gemm_rect(int passes, const Planes& a, const Planes& b, GemmShape& sh, const typename Epi::Params& ep,
+                            cudaStream_t s);
+
 template <class Epi>
 static int launch_gemm(int passes, const Planes& a, const Planes& b, GemmShape& sh, const typename Epi::Params& ep,
                        cudaStream_t s) {
@@ -352,6 +361,22 @@ static int launch_gemm(int passes, const Planes& a, const Planes& b, GemmShape& 
     return launch_gemm_t<Epi, 3, 64, 8>(a, b, sh, ep, s);
   }
   if (passes == 1) return launch_gemm_t<Epi, 1, 64, 8>(a, b, sh, ep, s);
+  return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3, got %d", passes);
+}
+
+template <class Epi>
+static int launch_gemm_rect(int passes, const Planes& a, const Planes& b, GemmShape& sh, const typename Epi::Params& ep,
+                            cudaStream_t s) {
+  if (env_int("WEALY_RECT_PAIR", 1) == 0 || sh.n_row_blocks < 2) return launch_gemm<Epi>(passes, a, b, sh, ep, s);
+  GemmShape shp = sh;
+  shp.n_row_blocks = (sh.n_row_blocks + 1) / 2;  // super row blocks of 256 queries
+  shp.group_rows = (sh.group_rows + 1) / 2;
+  if (passes == 3) {
+    if (a.lo == nullptr || b.lo == nullptr) return fail(WEALY_ERR_BAD_ARG, "3-pass contraction needs lo planes");
+    shp.k_blocks = (int)(a.d_pad / 32);
+    return launch_gemm_pair<Epi, 3, 32, 8, false>(a, shp, ep, s, &b);
+  }
+  if (passes == 1) return launch_gemm_pair<Epi, 1, 64, 8, false>(a, shp, ep, s, &b);
   return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3, got %d", passes);
 }
 
@@ -838,8 +863,7 @@ static int topk_capacity(int k) {
 // similarities are reduced to one per track pair inside the epilogue (redux: WEALY_REDUX_*), all ids / outputs per track.
 template <int kS>
 static int launch_eval_tracks(int passes, const Planes& a, const Planes& b, GemmShape& sh, const EvalParams& ep, cudaStream_t s) {
-  if (passes == 3) return launch_gemm_t<EvalTracksEpi<kS>, 3, 64, 8>(a, b, sh, ep, s);
-  return launch_gemm_t<EvalTracksEpi<kS>, 1, 64, 8>(a, b, sh, ep, s);
+  return launch_gemm_rect<EvalTracksEpi<kS>>(passes, a, b, sh, ep, s);
 }
 
 static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
@@ -1172,7 +1196,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   } else if (chunks == 16) {
     W_TRY(launch_eval_tracks<16>(passes, pq, pc, sh, ep, s));
   } else {
-    W_TRY(launch_gemm<EvalEpi>(passes, pq, pc, sh, ep, s));
+    W_TRY(launch_gemm_rect<EvalEpi>(passes, pq, pc, sh, ep, s));
   }
   CU_TRY(cudaEventRecord(p->ev1, s));
   p->timed = true;

@@ -383,7 +383,8 @@ struct EvalEpiT {
     prefetch_ids(p, st, sh, lane);
     n_cand(ctx)[lane] = 0;
     // cooperative fill of the threshold cache (the previous unit's row_end left it flushed)
-    st.base = p.off[ctx.row_base / kS];
+    // (the CTA-pair core may hand a CTA a row block that lies entirely past the last query)
+    st.base = p.off[min(ctx.row_base, sh.m_rows) / kS];
     const long long total = p.off[min(ctx.row_base + kTileM, sh.m_rows) / kS] - st.base;
     st.n_cached = (int)(total < (long long)kCachePairs ? total : (long long)kCachePairs);
     float* ts = thr_s(ctx);

@@ -47,7 +47,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
   constexpr int kHalves = kEpiWarps / 4;
   constexpr int kColSlots = CS::kSlots;
   static_assert(kEpiWarps == 8 || kEpiWarps == 12, "8 or 12 epilogue warps (2 or 3 per TMEM lane quadrant)");
-  static_assert(kColSlots > 0, "the pair kernel serves the symmetric evaluation epilogue");
+  static_assert(kColSlots > 0 || !kDynChunks, "dynamic chunk claiming belongs to the symmetric evaluation epilogue");
 
   extern __shared__ uint8_t smem_raw[];
   // (the dynamic shared memory of both CTAs starts at the same offset, so the aligned layouts coincide)
@@ -60,11 +60,11 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
   uint64_t* unit_full = tmem_empty + 2;
   uint64_t* unit_empty = unit_full + 2;                        // leader only
   uint64_t* col_full = unit_empty + 2;
-  uint64_t* col_empty = col_full + kColSlots;
-  int* unit_slot = reinterpret_cast<int*>(col_empty + kColSlots);
+  uint64_t* col_empty = col_full + (kColSlots > 0 ? kColSlots : 1);
+  int* unit_slot = reinterpret_cast<int*>(col_empty + (kColSlots > 0 ? kColSlots : 1));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(unit_slot + 2);
   int* chunk_ctr = reinterpret_cast<int*>(tmem_slot + 2);      // [2 unit slots][4 quadrants] chunk claim counters
-  static_assert((2 * kStages + 8 + 2 * kColSlots) * 8 + 16 + 32 <= SM::kBarBytes, "barrier area");
+  static_assert((2 * kStages + 8 + 2 * (kColSlots > 0 ? kColSlots : 1)) * 8 + 16 + 32 <= SM::kBarBytes, "barrier area");
   constexpr int kChunksPerTile = kTileN / kChunkCols;          // per quadrant
   uint8_t* scratch_base = bar_base + SM::kBarBytes;
   uint8_t* col_slots = scratch_base + kEpiWarps * Epi::kWarpScratchBytes + CS::kOffset;
@@ -106,12 +106,15 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
 
   const int n_units = shape.n_row_blocks * shape.n_col_chunks;  // n_row_blocks counts SUPER row blocks here
 
-  // unit -> (chunk, super row block S): rows [256 S, 256 S + 256) need column tiles >= S
-  auto unit_tiles = [&](int u, int& S, int& t0, int& t1) {
-    int chunk;
+  // unit -> (chunk, super row block S); symmetric sweeps: rows [256 S, 256 S + 256) need column tiles >= S
+  auto unit_tiles_c = [&](int u, int& S, int& t0, int& t1, int& chunk) {
     decode_unit(shape, u, chunk, S);
     t1 = min((chunk + 1) * shape.tiles_per_chunk, shape.n_col_tiles);
-    t0 = max(chunk * shape.tiles_per_chunk, S);
+    t0 = shape.sym ? max(chunk * shape.tiles_per_chunk, S) : chunk * shape.tiles_per_chunk;
+  };
+  auto unit_tiles = [&](int u, int& S, int& t0, int& t1) {
+    int chunk;
+    unit_tiles_c(u, S, t0, t1, chunk);
   };
 
   if (warp_idx == 0) {
@@ -156,7 +159,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
         int rb, t0, t1;
         unit_tiles(u, rb, t0, t1);
         for (int t = t0; t < t1; ++t) {
-          {
+          if constexpr (kColSlots > 0) {
             ptx::mbar_wait(&col_empty[cs], cphase ^ 1u);
             const void *s0, *s1;
             Epi::col_bulk_src(ep, t, s0, s1);
@@ -280,23 +283,25 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
       }
       if (++us == 2) { us = 0; uphase ^= 1u; }
       if (u < 0) break;
-      int rb, t0, t1;
-      unit_tiles(u, rb, t0, t1);
+      int rb, t0, t1, chunk;
+      unit_tiles_c(u, rb, t0, t1, chunk);
       if (t0 >= t1) continue;
       const int row = (shape.sym & 2) ? rb * 2 * kTileM + 2 * row_in_tile + (int)cta_rank  // rb is the SUPER row block here
                                       : rb * 2 * kTileM + (int)cta_rank * kTileM + row_in_tile;
+      const int part = chunk * kHalves + half;  // partial-result slot of epilogues that keep per-(chunk, warp) state
       typename Epi::RowState rs;
       EpiCtx ctx;
       ctx.warp_scratch = scratch_base + ew * Epi::kWarpScratchBytes;
       ctx.cta_scratch = scratch_base + kEpiWarps * Epi::kWarpScratchBytes;
       ctx.tid = ew * 32 + lane;
       ctx.nthreads = kEpiWarps * 32;
-      ctx.row_base = rb * 2 * kTileM;
-      ctx.row_span = 2 * kTileM;
+      // symmetric sweeps: the pair's 256-row super block (the CTAs' rows interleave); otherwise this CTA's own 128 rows
+      ctx.row_base = shape.sym ? rb * 2 * kTileM : rb * 2 * kTileM + (int)cta_rank * kTileM;
+      ctx.row_span = shape.sym ? 2 * kTileM : kTileM;
       ctx.first_col = t0 * kTileN + half * kChunkCols;
       ctx.col_step = kHalves * kChunkCols;
       ctx.col_slot = nullptr;
-      Epi::row_begin(ep, rs, row, 0, shape, ctx);
+      Epi::row_begin(ep, rs, row, part, shape, ctx);
       if constexpr (kDynChunks) {
         // chunk stream of this quadrant: g -> (tile g / 8, chunk g % 8); tiles are numbered through the CTA's
         // lifetime (tile_seq) so that barrier slots and phases follow from the number alone
@@ -338,8 +343,10 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
         tile_seq += (unsigned)n_tiles;
       } else {
       for (int t = t0; t < t1; ++t) {
-        ptx::mbar_wait_warp(&col_full[cs], cphase);
-        ctx.col_slot = col_slots + cs * CS::kBytes;
+        if constexpr (kColSlots > 0) {
+          ptx::mbar_wait_warp(&col_full[cs], cphase);
+          ctx.col_slot = col_slots + cs * CS::kBytes;
+        }
         Epi::tile_begin(ep, rs, shape, ctx, t);
         ptx::mbar_wait_cluster_warp(&tmem_full[acc], acc_phase);
         ptx::tc_fence_after_sync();
@@ -355,14 +362,16 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
         __syncwarp();
         if (lane == 0) {
           ptx::mbar_arrive_cluster_relaxed(leader_tmem_empty0 + 8u * acc);
-          ptx::mbar_arrive(&col_empty[cs]);
+          if constexpr (kColSlots > 0) ptx::mbar_arrive(&col_empty[cs]);
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-        if (++cs == kColSlots) { cs = 0; cphase ^= 1u; }
+        if constexpr (kColSlots > 0) {
+          if (++cs == kColSlots) { cs = 0; cphase ^= 1u; }
+        }
         Epi::tile_end(ep, rs, shape, ctx);
       }
       }
-      Epi::row_end(ep, rs, row, 0, shape, ctx);
+      Epi::row_end(ep, rs, row, part, shape, ctx);
     }
   }
 

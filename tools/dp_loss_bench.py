@@ -60,6 +60,7 @@ def main():
         ms, loss = timed(step)
         os.environ["WEALY_DP_OVERLAP"] = "0"
         ms_serial, loss_s = timed(step)
+        os.environ["WEALY_DP_OVERLAP"] = "auto"
         # the same shard computed from an already gathered global batch: no collective at all (the compute-only floor)
         one = torch.ones((), device=dev)
 
