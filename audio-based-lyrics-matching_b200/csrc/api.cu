@@ -1166,10 +1166,12 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       // three epilogue warps per TMEM lane quadrant (the pair's epilogue is the co-limiter; 16 warps were measured worse);
       // WEALY_PAIR_DYN: the warps of a quadrant claim 32-column chunks dynamically instead of owning fixed ones
       const bool w12 = env_int("WEALY_PAIR_EPI_WARPS", 12) == 12;
+      const bool w16 = env_int("WEALY_PAIR_EPI_WARPS", 12) == 16;
       const bool dyn = env_int("WEALY_PAIR_DYN", 1) != 0;
       if (passes == 3) {
         sh.k_blocks = (int)(pq.d_pad / 32);
-        if (dyn && w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12, true>(pq, sh, sp, s)));
+        if (w16) W_TRY((launch_gemm_pair<EvalSymEpi<3, 128, 4096>, 3, 32, 16, true>(pq, sh, sp, s)));
+        else if (dyn && w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12, true>(pq, sh, sp, s)));
         else if (dyn) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 8, true>(pq, sh, sp, s)));
         else if (w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12>(pq, sh, sp, s)));
         else W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32>(pq, sh, sp, s)));
