@@ -19,6 +19,7 @@
 #include "masked_kernels.cuh"
 #include "pool_kernels.cuh"
 #include "prep.cuh"
+#include "redux_kernels.cuh"
 #include "topk_sym_kernels.cuh"
 
 using namespace wealy;
@@ -1166,12 +1167,10 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       // three epilogue warps per TMEM lane quadrant (the pair's epilogue is the co-limiter; 16 warps were measured worse);
       // WEALY_PAIR_DYN: the warps of a quadrant claim 32-column chunks dynamically instead of owning fixed ones
       const bool w12 = env_int("WEALY_PAIR_EPI_WARPS", 12) == 12;
-      const bool w16 = env_int("WEALY_PAIR_EPI_WARPS", 12) == 16;
       const bool dyn = env_int("WEALY_PAIR_DYN", 1) != 0;
       if (passes == 3) {
         sh.k_blocks = (int)(pq.d_pad / 32);
-        if (w16) W_TRY((launch_gemm_pair<EvalSymEpi<3, 128, 4096>, 3, 32, 16, true>(pq, sh, sp, s)));
-        else if (dyn && w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12, true>(pq, sh, sp, s)));
+        if (dyn && w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12, true>(pq, sh, sp, s)));
         else if (dyn) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 8, true>(pq, sh, sp, s)));
         else if (w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12>(pq, sh, sp, s)));
         else W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32>(pq, sh, sp, s)));
@@ -1401,6 +1400,30 @@ extern "C" int wealy_masked_reduce(const void* x, const uint8_t* mask, int64_t r
       return WEALY_OK;
     default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
   }
+}
+
+// a4: distance_tensor_redux (lib/tensor_ops.py:288-373) in one launch -- csrc/redux_kernels.cuh
+extern "C" int wealy_distance_redux(const void* dist, const uint8_t* mask, int64_t pairs, int s1, int s2, int dtype, int op,
+                                    int karg, int symmetric, float eps, float inf, void* out, void* stream) {
+  if (pairs < 0 || s1 < 1 || s2 < 1) return fail(WEALY_ERR_BAD_ARG, "bad shape pairs=%lld s1=%d s2=%d", (long long)pairs, s1, s2);
+  if (s1 > kReduxMaxS || s2 > kReduxMaxS) return fail(WEALY_ERR_UNSUPPORTED, "more than %d chunks per track", kReduxMaxS);
+  if (op < WEALY_RDX_MIN || op > WEALY_RDX_BPWR) return fail(WEALY_ERR_BAD_ARG, "unknown redux op %d", op);
+  if (pairs == 0) return WEALY_OK;
+  if (!dist || !out) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (pairs > 4ll * 2000000000ll) return fail(WEALY_ERR_UNSUPPORTED, "too many pairs");
+  cudaStream_t s = (cudaStream_t)stream;
+#define WEALY_RDX(T, A) \
+  redux_pairs_kernel<T, A><<<(unsigned)ceil_div(pairs, redux_warps<A>()), 32 * redux_warps<A>(), 0, s>>>((const T*)dist, mask, (long long)pairs, s1, s2, op, karg, symmetric, (A)eps, (A)inf, (T*)out)
+  switch (dtype) {
+    case WEALY_F32: WEALY_RDX(float, float); break;
+    case WEALY_F16: WEALY_RDX(__half, float); break;
+    case WEALY_BF16: WEALY_RDX(__nv_bfloat16, float); break;
+    case WEALY_F64: WEALY_RDX(double, double); break;
+    default: return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
+  }
+#undef WEALY_RDX
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
 }
 
 // ------------------------------------------------------------------------------------------

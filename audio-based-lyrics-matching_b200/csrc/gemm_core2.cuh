@@ -46,7 +46,7 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
   using CS = ColSlotTraits<Epi>;
   constexpr int kHalves = kEpiWarps / 4;
   constexpr int kColSlots = CS::kSlots;
-  static_assert(kEpiWarps == 8 || kEpiWarps == 12 || kEpiWarps == 16, "8, 12 or 16 epilogue warps (2 .. 4 per TMEM lane quadrant)");
+  static_assert(kEpiWarps == 8 || kEpiWarps == 12, "8 or 12 epilogue warps (2 or 3 per TMEM lane quadrant)");
   static_assert(kColSlots > 0 || !kDynChunks, "dynamic chunk claiming belongs to the symmetric evaluation epilogue");
 
   extern __shared__ uint8_t smem_raw[];

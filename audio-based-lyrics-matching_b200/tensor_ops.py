@@ -401,8 +401,62 @@ def _redux_k(redux, limit):
     return 1 if "-" not in redux else max(1, min(int(redux.split("-")[-1]), limit))
 
 
-def distance_tensor_redux(dist, redux, mask=None, squeeze=True, eps=1e-7, inf=1e12):
-    """(b1, b2, s1, s2) chunk-vs-chunk distances -> (b1, b2) track-vs-track (lib/tensor_ops.py:288-373)."""
+_RDX = {"min": 0, "max": 1, "mean": 2, "minmean": 3, "meanmin": 4}
+
+
+def _redux_plan(redux):
+    """redux string -> (op, karg, symmetric) of wealy_distance_redux, or None when the strategy stays a composition
+    (random pick, nested "s" prefixes).  The order of the tests is the reference's (lib/tensor_ops.py:291-368): "best"
+    swallows "bestmin", the "s" prefix comes last."""
+    sym = 0
+    name = redux
+    for _ in range(2):
+        if name in _RDX:
+            return _RDX[name], 0, sym
+        if name == "randmin":
+            return None
+        if name.startswith("bpwr"):
+            return 7, (0 if "-" not in name else max(1, int(name.split("-")[-1]))), sym
+        if name.startswith("best"):
+            return 5, (1 if "-" not in name else max(1, int(name.split("-")[-1]))), sym
+        if name.startswith("worst"):
+            return 6, (1 if "-" not in name else max(1, int(name.split("-")[-1]))), sym
+        if name[:1] == "s" and not sym:
+            sym, name = 1, name[1:]
+            continue
+        break
+    return None
+
+
+def _redux_fused(dist, plan, mask, eps, inf):
+    """One launch of the fused kernel (csrc/redux_kernels.cuh) -> (b1, b2, 1, 1)."""
+    op, karg, sym = plan
+    b1, b2, s1, s2 = dist.shape
+    if op == 7:                                         # bpwr: the reference's tie jitter (lib/tensor_ops.py:318)
+        dist = dist + eps * torch.rand_like(dist)
+    d = dist.contiguous()
+    m = None
+    if mask is not None:
+        m = torch.broadcast_to(mask, dist.shape).contiguous().to(torch.uint8)
+    out = torch.empty((b1, b2), dtype=dist.dtype, device=dist.device)
+    with torch.cuda.device(dist.device):
+        N.check(N.lib.wealy_distance_redux(d.data_ptr(), m.data_ptr() if m is not None else None, b1 * b2, s1, s2,
+                                           N.dtype_code(dist.dtype, allow_f64=True), op, min(karg, 1 << 30), sym, float(eps),
+                                           float(inf), out.data_ptr(), N.stream_ptr(dist.device)))
+    return out.view(b1, b2, 1, 1)
+
+
+def distance_tensor_redux(dist, redux, mask=None, squeeze=True, eps=1e-7, inf=1e12, fused=True):
+    """(b1, b2, s1, s2) chunk-vs-chunk distances -> (b1, b2) track-vs-track (lib/tensor_ops.py:288-373).
+
+    Up to 32 chunks per side, every strategy except the random pick runs as ONE kernel launch (one warp per track
+    pair, wealy_distance_redux); `fused=False` keeps the composition of masked reductions below (also the path for
+    "randmin", nested "s" prefixes and larger blocks), which mirrors the reference branch for branch."""
+    if fused and dist.ndim == 4 and dist.is_cuda and 1 <= dist.shape[2] <= 32 and 1 <= dist.shape[3] <= 32:
+        plan = _redux_plan(redux)
+        if plan is not None:
+            out = _redux_fused(dist, plan, mask, eps, inf)
+            return out.squeeze((-1, -2)) if squeeze else out
     both = (-1, -2)
     if redux == "min":
         out = mmin(dist, mask=mask, dim=both, keepdim=True, ctt=inf)

@@ -183,6 +183,24 @@ void wealy_eval_plan_destroy(wealy_eval_plan* plan);
 int wealy_masked_reduce(const void* x, const uint8_t* mask, int64_t rows, int64_t cols, int dtype, int op, float fill,
                         float eps, void* out, void* stream);
 
+/* ---- a4: multi-chunk distance reduction -----------------------------------------------------
+ * Replaces lib/tensor_ops.py:288-373 `distance_tensor_redux(dist, redux, mask, ...)`: dist [pairs, s1, s2] contiguous
+ * (the (b1, b2) leading dimensions flattened), mask [pairs, s1, s2] bytes (non-zero = EXCLUDED; may be NULL), out [pairs]
+ * in dist's dtype; s1, s2 <= 32.  op / karg: the strategy ("best-k" / "worst-k": k; "bpwr-n": n, 0 = all rounds;
+ * for WEALY_RDX_BPWR the caller adds the reference's eps * rand tie-jitter to dist beforehand); symmetric != 0: the
+ * "s" prefix (mean of the strategy on the block and on its transpose); eps: clamp of the means' denominators;
+ * inf: the reference's `inf` stand-in (1e12).  "randmin" needs a random stream and stays a composition on the caller's side. */
+#define WEALY_RDX_MIN 0
+#define WEALY_RDX_MAX 1
+#define WEALY_RDX_MEAN 2
+#define WEALY_RDX_MINMEAN 3
+#define WEALY_RDX_MEANMIN 4
+#define WEALY_RDX_BEST 5
+#define WEALY_RDX_WORST 6
+#define WEALY_RDX_BPWR 7
+int wealy_distance_redux(const void* dist, const uint8_t* mask, int64_t pairs, int s1, int s2, int dtype, int op, int karg,
+                         int symmetric, float eps, float inf, void* out, void* stream);
+
 /* ---- f3 / f4: the steps either side of the path --------------------------
  * wealy_mean_pool: lib/layers.py:6-30 MeanPool.  x [b, c, t] contiguous, mask [b, t] bytes (non-zero = VALID) or
  *   NULL; backward == 0: out [b, c] = masked temporal mean; backward != 0: x is the upstream gradient [b, c] and

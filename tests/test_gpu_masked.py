@@ -95,3 +95,30 @@ def test_float64_masked_reductions():
     assert (wt.mmean(xc, mask=mc, dim=1).cpu() - (x * inc).sum(1) / inc.sum(1)).abs().max() < 1e-12
     assert torch.equal(wt.mmin(xc, mask=mc, dim=1).cpu(), torch.where(m, torch.full_like(x, float("inf")), x).min(1).values)
     assert torch.equal(wt.mmax(xc, mask=mc, dim=1).cpu(), torch.where(m, torch.full_like(x, float("-inf")), x).max(1).values)
+
+
+@pytest.mark.parametrize("redux", ["min", "max", "mean", "minmean", "meanmin", "best", "best-3", "best-100", "worst-2", "bpwr",
+                                   "bpwr-2", "smin", "smeanmin", "sminmean", "sbest-4", "sbpwr", "bestmin-2"])
+@pytest.mark.parametrize("shape", [(3, 4, 5, 6), (2, 3, 7, 2), (5, 1, 1, 9), (2, 2, 16, 16), (1, 3, 32, 32)])
+def test_fused_redux_equals_the_composition(redux, shape):
+    """wealy_distance_redux (one launch, one warp per track pair) against the branch-for-branch composition of masked
+    reductions (`fused=False`), with and without a mask that also empties whole rows, columns and blocks."""
+    wt = _wt()
+    g = torch.Generator().manual_seed(sum(shape) + len(redux))
+    dist = (torch.rand(*shape, generator=g) * 2).cuda()
+    mask = (torch.rand(*shape, generator=g) < 0.35).cuda()
+    mask[0, 0, 0, :] = True                                    # a fully excluded row
+    mask[-1, -1, :, -1] = True                                 # ... column
+    if shape[0] > 1:
+        mask[1, 0] = True                                      # ... block
+    tol = 1e-5 if "bpwr" in redux else 2e-6                    # (the tie jitter of bpwr is drawn anew in each call)
+    for m in (None, mask):
+        a = wt.distance_tensor_redux(dist, redux, mask=m)
+        b = wt.distance_tensor_redux(dist, redux, mask=m, fused=False)
+        assert a.shape == b.shape == shape[:2]
+        _close(a, b, tol=tol)
+    a = wt.distance_tensor_redux(dist, redux, mask=mask, squeeze=False)
+    assert a.shape == shape[:2] + (1, 1)
+    _close(wt.distance_tensor_redux(dist.double(), redux, mask=mask), wt.distance_tensor_redux(dist, redux, mask=mask).double(), tol=1e-5)
+    h = wt.distance_tensor_redux(dist.half(), redux, mask=mask)
+    assert h.dtype == torch.float16
