@@ -14,7 +14,7 @@ def _wt():
 
 def _close(a, b, tol=2e-6):
     a = a.detach().cpu().double()
-    b = torch.as_tensor(b).double()
+    b = torch.as_tensor(b).detach().cpu().double()
     assert a.shape == b.shape, (a.shape, b.shape)
     nan_a, nan_b = torch.isnan(a), torch.isnan(b)
     assert torch.equal(nan_a, nan_b)
