@@ -4,6 +4,9 @@
 //   U planes (hi[,lo] [b][d_pad], norm, scale, sq) | U^T planes (hi[,lo] [d][b_pad]) | W planes (hi[,lo] [b][b_pad])
 //   | dU [b][d] f32 | {label, idx} [b256] int2 | partial [parts_max][b][8] f32 | rowstat [b256][4] f32 | ZStats | scal | flags
 
+constexpr int kLossZeroBytes = 1024 + 4 * 256;  // ZStats | scal | bad | acc | acc_max
+static_assert(sizeof(ZStats) <= 1024, "ZStats block");
+
 struct LossWs {
   Planes u;
   __half *ut_hi, *ut_lo;
@@ -43,7 +46,7 @@ static void loss_ws_layout(LossWs& w, uint8_t* base, int64_t b, int64_t d, int p
   w.parts_max = (int)(ceil_div(b, kTileN) + ceil_div(nb, kTileN)) * 2;
   w.partial = reinterpret_cast<float*>(cur); cur += align_up((size_t)w.parts_max * nb * kStatWidth * 4, 1024);
   w.rowstat = reinterpret_cast<float*>(cur); cur += align_up(b256 * 16, 256);
-  w.zs = reinterpret_cast<ZStats*>(cur); cur += 256;
+  w.zs = reinterpret_cast<ZStats*>(cur); cur += 1024;  // (the blocks from here to acc_max are zeroed together: kLossZeroBytes)
   w.scal = reinterpret_cast<float*>(cur); cur += 256;
   w.bad = reinterpret_cast<int*>(cur); cur += 256;
   w.acc = reinterpret_cast<double*>(cur); cur += 256;
@@ -152,10 +155,10 @@ static int loss_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t 
     if (b <= 65536) {
       // one CTA: zero {ZStats, scal, flags, batch accumulators}, optional single-label noise (in place), pack the ids
       pack_ids_noise_kernel<<<1, 1024, 0, s>>>((long long*)z_label, (const long long*)z_idx, w.lab_idx, (int)b,
-                                               cfg->label_noise ? 1 : 0, reinterpret_cast<int*>(w.zs), 1280 / 4, w.bad);
+                                               cfg->label_noise ? 1 : 0, reinterpret_cast<int*>(w.zs), kLossZeroBytes / 4, w.bad);
     } else {
       if (cfg->label_noise) return fail(WEALY_ERR_UNSUPPORTED, "label_noise is fused for batches of up to 65536 rows");
-      CU_TRY(cudaMemsetAsync(w.zs, 0, 1280, s));
+      CU_TRY(cudaMemsetAsync(w.zs, 0, kLossZeroBytes, s));
       pack_ids_kernel<<<(unsigned)ceil_div(b, T), T, 0, s>>>((const long long*)z_label, (const long long*)z_idx, w.lab_idx, (int)b,
                                                             w.bad);
     }
@@ -193,7 +196,8 @@ static int loss_forward_local(const wealy_loss_cfg* cfg, const void* z, int64_t 
   lp.part_base = parts_local_used;
   const int parts = sh.n_col_chunks * halves;
   W_TRY(launch_gemm<LossStatsEpi>(cfg->passes, plane_rows(w.u, row0, nb), w.u, sh, lp, s));
-  loss_merge_kernel<<<(unsigned)ceil_div(nb, 256), 256, 0, s>>>(loss_cfg_dev(cfg), (int)nb, (int)b, parts_local_used + parts, w.partial,
+  // (64-thread blocks: one thread per anchor walks its partial records; 256-thread blocks would put a 4096-anchor batch on 16 SMs)
+  loss_merge_kernel<<<(unsigned)ceil_div(nb, 64), 64, 0, s>>>(loss_cfg_dev(cfg), (int)nb, (int)b, parts_local_used + parts, w.partial,
                                                                 w.rowstat + row0 * 4, w.acc, w.acc_max);
   CU_TRY(cudaGetLastError());
   return WEALY_OK;

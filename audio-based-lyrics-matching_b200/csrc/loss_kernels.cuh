@@ -420,9 +420,16 @@ __global__ void __launch_bounds__(256) loss_finish_kernel(LossCfgDev cfg, int b,
   }
   if (writer) {
     const double n = B * (double)d;
-    o[1] = (double)__uint_as_float(zs->maxabs_bits);
-    o[2] = zs->sum / n;
-    const double var = n > 1.0 ? (zs->sumsq - zs->sum * zs->sum / n) / (n - 1.0) : 0.0;
+    double zsum = 0.0, zsq = 0.0;
+    unsigned int zmax = 0u;
+    for (int k = 0; k < kZSlots; ++k) {
+      zsum += zs->sum[k];
+      zsq += zs->sumsq[k];
+      zmax = max(zmax, zs->maxabs_bits[k]);
+    }
+    o[1] = (double)__uint_as_float(zmax);
+    o[2] = zsum / n;
+    const double var = n > 1.0 ? (zsq - zsum * zsum / n) / (n - 1.0) : 0.0;
     o[3] = sqrt(var > 0.0 ? var : 0.0);
     // labels / ids that do not fit in 32 bits were truncated by pack_ids_kernel: positives would be wrong, so the
     // loss is poisoned (NaN) and the count reported -- no host sync on the training path

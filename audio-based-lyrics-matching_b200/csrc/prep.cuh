@@ -21,11 +21,13 @@ enum PrepMode : int {
   kPrepRawPow2 = 2,   // x * 2^-e, e = exponent of max|x|; epilogue multiplies by 2^e
 };
 
+// Statistics of z for the losses' logdict.  Every warp adds its row's share with atomics; 32 slots (picked by block
+// index) keep thousands of same-address atomics from serialising on one L2 line -- the reader sums the slots.
+constexpr int kZSlots = 32;
 struct ZStats {
-  double sum;
-  double sumsq;
-  unsigned int maxabs_bits;  // float bits of max |z| (non-negative floats order like uints)
-  unsigned int pad;
+  double sum[kZSlots];
+  double sumsq[kZSlots];
+  unsigned int maxabs_bits[kZSlots];  // float bits of max |z| (non-negative floats order like uints)
 };
 
 template <typename T>
@@ -203,9 +205,10 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ x,
     s2 = warp_sum_d(s2);
     smx = warp_max(smx);
     if (lane == 0) {
-      atomicAdd(&stats->sum, s1);
-      atomicAdd(&stats->sumsq, s2);
-      atomicMax(&stats->maxabs_bits, __float_as_uint(smx));
+      const int slot = (int)((blockIdx.x * 8u + (threadIdx.x >> 5)) % kZSlots);
+      atomicAdd(&stats->sum[slot], s1);
+      atomicAdd(&stats->sumsq[slot], s2);
+      atomicMax(&stats->maxabs_bits[slot], __float_as_uint(smx));
     }
   }
 }
