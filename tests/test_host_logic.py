@@ -97,3 +97,31 @@ def test_merge_over_gloo_world2(n):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, n, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def test_redux_string_dispatch_follows_the_reference_order():
+    """lib/tensor_ops.py:291-368 tests the redux string in a fixed order ("best" swallows "bestmin", the "s" prefix comes
+    last); the plan for the fused kernel must make the same choices, and leave the random / nested forms alone."""
+    from wealy_b200.tensor_ops import _redux_plan
+    assert _redux_plan("min") == (0, 0, 0) and _redux_plan("meanmin") == (4, 0, 0)
+    assert _redux_plan("best") == (5, 1, 0) and _redux_plan("best-3") == (5, 3, 0)
+    assert _redux_plan("bestmin-2") == (5, 2, 0)                  # shadowed by "best", like upstream
+    assert _redux_plan("worst-2") == (6, 2, 0)
+    assert _redux_plan("bpwr") == (7, 0, 0) and _redux_plan("bpwr-3") == (7, 3, 0)
+    assert _redux_plan("smin") == (0, 0, 1) and _redux_plan("sbpwr-3") == (7, 3, 1) and _redux_plan("sbest-4") == (5, 4, 1)
+    assert _redux_plan("randmin") is None and _redux_plan("srandmin") is None
+    assert _redux_plan("ssmin") is None and _redux_plan("nope") is None and _redux_plan("s") is None
+
+
+def test_bench_arms_share_one_config():
+    """bench.py's GPU arm and its reference arm must describe the same workload with the same `config` dictionary."""
+    import importlib.util
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for n, world, tracks in ((100000, 1, 0), (282843, 8, 0), (500000, 8, 500000)):
+        a, b = bench.workload_config(n, world, tracks), bench.workload_config(n, world, tracks)
+        assert a == b and a["tracks"] == n and a["n_gpus"] == world and "workload" in a
+    synth = bench.load_synth()
+    assert hasattr(synth, "make_eval_set")
