@@ -878,7 +878,10 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   cudaStream_t s = (cudaStream_t)stream;
   if (!p) return fail(WEALY_ERR_BAD_ARG, "null plan");
   if (stage != 2 && (!queries_z || !candidates_z)) return fail(WEALY_ERR_BAD_ARG, "null pointer");
-  if (stage == 2) queries_z = candidates_z = p;  // (not dereferenced: the planes are in the plan)
+  if (stage == 2) {
+    if (!p->planes_buf || !p->lvl_thr_buf) return fail(WEALY_ERR_BAD_ARG, "wealy_eval_shard_sweep needs wealy_eval_shard_prepare first");
+    queries_z = candidates_z = p;  // (not dereferenced: the planes are in the plan)
+  }
   if (finish && (!aps || !r1s || !sums)) return fail(WEALY_ERR_BAD_ARG, "null pointer");
   if (shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) return fail(WEALY_ERR_BAD_ARG, "bad shard %d/%d", shard_rank, shard_world);
   if (d <= 0) return fail(WEALY_ERR_BAD_ARG, "bad embedding size %lld", (long long)d);

@@ -113,6 +113,8 @@ class EvalPlan:
 
     def shard_sweep(self, shard_rank, shard_world):
         """Stage 2: this rank's row blocks of the symmetric sweep on the planes / thresholds stage 1 left in the plan."""
+        if not hasattr(self, "_shard_dim"):
+            raise AssertionError("shard_sweep() needs shard_prepare() first")
         with torch.cuda.device(self.device):
             N.check(N.lib.wealy_eval_shard_sweep(self._handle, self._shard_dim, self._shard_passes, int(shard_rank),
                                                  int(shard_world), N.stream_ptr(self.device)))
