@@ -310,6 +310,86 @@ def _prefetch_to_device(queries_z, candidates_z):
     return qd, cd, side
 
 
+class EvalPipeline:
+    """Back-to-back all-vs-all evaluations of HOST-resident sets (serving / periodic evaluation during training): the
+    host -> device upload of request k + 1 runs on a copy stream while the sweep of request k occupies the SMs, and the
+    per-query results come back through pinned host buffers.  Every request still pays everything itself -- upload of
+    ids and embeddings, id plan, evaluation, read-back --; only the copy engine and the SMs work at the same time.
+
+        pipe = EvalPipeline()
+        t0 = pipe.submit(c, i, z)                # returns at once (the id plan build synchronises with the previous sweep)
+        t1 = pipe.submit(c2, i2, z2)
+        aps, r1s = pipe.result(t0)               # pinned host tensors, valid until `depth` more requests have been submitted
+
+    Single process / single GPU; `precision`, `eps` as in evaluate()."""
+
+    def __init__(self, depth=2, device=None, precision=None, eps=1e-6):
+        assert depth >= 2
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.depth, self.precision, self.eps = int(depth), precision, float(eps)
+        self.copy_stream = side_stream(self.device)
+        self.slots = [dict(z=None, c=None, i=None, aps=None, r1s=None, done=None, plan=None) for _ in range(self.depth)]
+        self.count = 0
+
+    def _buffers(self, slot, z, c, i):
+        n, d = z.shape
+        if slot["z"] is None or slot["z"].shape != z.shape or slot["z"].dtype != z.dtype:
+            with torch.cuda.stream(self.copy_stream):        # (allocated on the stream that fills them)
+                slot["z"] = torch.empty((n, d), dtype=z.dtype, device=self.device)
+                slot["c"] = torch.empty(n, dtype=torch.long, device=self.device)
+                slot["i"] = torch.empty(n, dtype=torch.long, device=self.device)
+            for t in (slot["z"], slot["c"], slot["i"]):
+                t.record_stream(torch.cuda.current_stream(self.device))
+            slot["aps"] = torch.empty(n, dtype=torch.float32).pin_memory()
+            slot["r1s"] = torch.empty(n, dtype=torch.float32).pin_memory()
+
+    def submit(self, c, i, z):
+        """Enqueue one all-vs-all evaluation of host tensors (pin them for an asynchronous upload) -> ticket."""
+        z, c, i = torch.as_tensor(z), torch.as_tensor(c).long(), torch.as_tensor(i).long()
+        if z.dtype == torch.float64:
+            z = z.float()
+        slot = self.slots[self.count % self.depth]
+        if slot["plan"] is not None:                          # the request that used this slot `depth` submits ago
+            slot["done"].synchronize()
+            slot["plan"].close()
+            slot["plan"] = None
+        self._buffers(slot, z, c, i)
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self.copy_stream):
+            slot["z"].copy_(z, non_blocking=True)
+            slot["c"].copy_(c, non_blocking=True)
+            slot["i"].copy_(i, non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(self.copy_stream)
+        compute.wait_event(uploaded)
+        with torch.cuda.device(self.device):
+            plan = EvalPlan(slot["c"], slot["i"], slot["c"], slot["i"], device=self.device)
+            res = plan.run(slot["z"], slot["z"], eps=self.eps, precision=self.precision)
+            slot["aps"].copy_(res["aps"], non_blocking=True)
+            slot["r1s"].copy_(res["r1s"], non_blocking=True)
+            slot["done"] = torch.cuda.Event()
+            slot["done"].record(compute)
+        # (the next upload into this slot waits for this sweep on the host: see the top of submit())
+        slot["plan"], slot["sums"] = plan, res["sums"]
+        self.count += 1
+        return self.count - 1
+
+    def result(self, ticket):
+        """-> (aps, r1s) pinned host tensors of request `ticket` (blocks until its read-back has finished)."""
+        if not (self.count - self.depth <= ticket < self.count):
+            raise ValueError("the result of this request has been overwritten (more than `depth` requests ago)")
+        slot = self.slots[ticket % self.depth]
+        slot["done"].synchronize()
+        return slot["aps"], slot["r1s"]
+
+    def close(self):
+        for slot in self.slots:
+            if slot["plan"] is not None:
+                slot["done"].synchronize()
+                slot["plan"].close()
+                slot["plan"] = None
+
+
 def mean_metrics(sums):
     """(MAP, MR1) from the device `sums` vector -- one 24-byte device->host read."""
     s = sums.detach().to("cpu")

@@ -555,22 +555,55 @@ def run_gpu_arm(args):
         if world > 1:
             out["plan"].close()
 
+    def timed_e2e(run_steps):
+        sync_all()
+        t0 = time.perf_counter()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        run_steps()
+        e3.record()
+        sync_all()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([max(e2.elapsed_time(e3), wall_ms)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     e2e_steps = max(2, min(args.steps, 5))
     step_e2e()
     step_e2e()
-    sync_all()
-    t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for _ in range(e2e_steps):
-        step_e2e()
-    e3.record()
-    sync_all()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([max(e2.elapsed_time(e3), wall_ms)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps
+    single_ms = timed_e2e(lambda: [step_e2e() for _ in range(e2e_steps)]) / e2e_steps
+    # `e2e` is the synchronous call at every N (comparable along the scaling series); the double-buffered serving form of the
+    # same public API is reported next to it at N = 1 (`e2e.pipelined`)
+    e2e_ms, e2e_api = single_ms, ("wealy_b200.evaluation.evaluate" if world == 1 else "wealy_b200.dist.evaluate_all_vs_all") + \
+        " (host pinned tensors in, host out; one synchronous call per step: upload, id plan, evaluation, read-back)"
+    if world == 1:
+        # the serving form: requests submitted back to back, the upload of request k + 1 on the copy engine while the
+        # sweep of request k runs.  Every request still uploads its ids and embeddings, builds its id plan, evaluates and
+        # reads its per-query results back -- all inside the timed region.
+        pipe = we.EvalPipeline(precision=args.precision)
+        pipe.result(pipe.submit(c_h, i_h, z_h))
+        last = {}
+
+        def run_pipelined():
+            prev = None
+            for _ in range(e2e_steps):
+                t = pipe.submit(c_h, i_h, z_h)
+                if prev is not None:
+                    pipe.result(prev)
+                prev = t
+            a, r = pipe.result(prev)
+            last["aps"] = a.clone()
+        pipe_ms = timed_e2e(run_pipelined) / e2e_steps
+        pipe_dmap = abs(float(last["aps"].double().mean()) - float(aps_h.double().mean()))
+        pipe.close()
+        pipelined = {"ms_per_step": pipe_ms, "value": pairs_total / (pipe_ms * 1e-3) / 1e9, "unit": UNIT,
+                     "abs_dMAP_vs_single_call": pipe_dmap,
+                     "api": "wealy_b200.evaluation.EvalPipeline.submit / .result: requests back to back, every request pays its own "
+                            "upload (ids + embeddings), id plan, evaluation and read-back inside the timed region; the upload of "
+                            "request k+1 runs on the copy engine while the sweep of request k runs"}
+    else:
+        pipelined = None
     e2e_value = pairs_total / (e2e_ms * 1e-3) / 1e9
     e2e_parity = None
     if rank == 0 and parity is not None:
@@ -657,8 +690,8 @@ def run_gpu_arm(args):
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms, "api": ("wealy_b200.evaluation.evaluate" if world == 1 else "wealy_b200.dist.evaluate_all_vs_all")
-                       + " (host pinned tensors in, host out)"},
+                "ms_per_step": e2e_ms, "api": e2e_api,
+                "pipelined": pipelined},
         "gpu_launches": 5 * args.steps,   # prep, pos_pairs, pos_sort, fused sweep, ap_reduce per step
         "roofline": roofline,
     }

@@ -657,3 +657,26 @@ def test_staged_sharded_sweep_emulated_on_one_gpu(world):
     _check_all_item_ranks(plans[0], s["c"], s["i"], s["z"])         # plan.ranks() after a staged run
     for pl in plans:
         pl.close()
+
+
+def test_eval_pipeline_overlaps_requests_and_matches_evaluate():
+    """EvalPipeline: back-to-back requests from pinned host memory (upload of request k + 1 on the copy stream while
+    request k sweeps); every result equals the synchronous evaluate() of the same request."""
+    we = _we()
+    sets = [_synth().make_eval_set(n, 64, seed=80 + k) for k, n in enumerate((1500, 1500, 900, 1500, 2100))]
+    want = []
+    for s in sets:
+        a, r = we.evaluate(s["c"].cuda(), s["i"].cuda(), s["z"].cuda(), s["c"].cuda(), s["i"].cuda(), s["z"].cuda())
+        want.append((a.cpu(), r.cpu()))
+    pipe = we.EvalPipeline()
+    tickets = []
+    for k, s in enumerate(sets):
+        tickets.append(pipe.submit(s["c"].pin_memory(), s["i"].pin_memory(), s["z"].pin_memory()))
+        if k >= 1:
+            a, r = pipe.result(tickets[k - 1])
+            assert torch.equal(a, want[k - 1][0]) and torch.equal(r, want[k - 1][1])
+    a, r = pipe.result(tickets[-1])
+    assert torch.equal(a, want[-1][0]) and torch.equal(r, want[-1][1])
+    with pytest.raises(ValueError):
+        pipe.result(tickets[0])                                   # overwritten: more than `depth` requests ago
+    pipe.close()
