@@ -863,8 +863,20 @@ static int topk_capacity(int k) {
 // chunks > 1 (row f1): every track has `chunks` embeddings (rows t * chunks .. of the matrices), the kS x kS chunk
 // similarities are reduced to one per track pair inside the epilogue (redux: WEALY_REDUX_*), all ids / outputs per track.
 template <int kS>
-static int launch_eval_tracks(int passes, const Planes& a, const Planes& b, GemmShape& sh, const EvalParams& ep, cudaStream_t s) {
-  return launch_gemm_rect<EvalTracksEpi<kS>>(passes, a, b, sh, ep, s);
+static int launch_eval_tracks(int passes, const Planes& a, const Planes& b, GemmShape& sh, const EvalParams& ep, cudaStream_t s,
+                              bool sym) {
+  if (!sym) return launch_gemm_rect<EvalTracksEpi<kS>>(passes, a, b, sh, ep, s);
+  // chunked all-vs-all: only the tiles that reach above the diagonal, on the CTA-pair core (super row block S = rows
+  // [256 S, 256 S + 256) needs column tiles >= S); every track pair scores both its row and its column query
+  GemmShape shp = sh;
+  shp.n_row_blocks = (sh.n_row_blocks + 1) / 2;
+  shp.group_rows = (sh.group_rows + 1) / 2;
+  shp.sym = 1;
+  if (passes == 3) {
+    shp.k_blocks = (int)(a.d_pad / 32);
+    return launch_gemm_pair<EvalTracksSymEpi<kS>, 3, 32, 8, false>(a, shp, ep, s);
+  }
+  return launch_gemm_pair<EvalTracksSymEpi<kS>, 1, 64, 8, false>(a, shp, ep, s);
 }
 
 static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,
@@ -918,6 +930,9 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
                         nq >= 192ll * topk && finish &&
                         shard_world == 1 && allow_sym_topk && env_int("WEALY_SYM_TOPK", 1) != 0;
   const bool sym = can_sym && (topk == 0 ? (shard_world > 1 || env_int("WEALY_SYM", 1) != 0) : sym_topk);
+  // chunked tracks, all-vs-all: the same halving for reductions that give d(q, c) == d(c, q) (min / max / mean)
+  const bool sym_tracks = same && p->same_ids && chunks > 1 && topk == 0 && red_inner == red_outer && shard_world == 1 &&
+                          nq * chunks > 2 * kTileM && env_int("WEALY_SYM_TRACKS", 1) != 0;
   if (shard_world > 1 && !sym)
     return fail(WEALY_ERR_BAD_ARG, "a sharded sweep needs queries == candidates (ids and embeddings) and no top-k");
 
@@ -1192,13 +1207,13 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       W_TRY((launch_gemm_t<EvalSymEpi<3>, 1, 64, 8, 3>(pq, pc, sh, sp, s)));
     }
   } else if (chunks == 2) {
-    W_TRY(launch_eval_tracks<2>(passes, pq, pc, sh, ep, s));
+    W_TRY(launch_eval_tracks<2>(passes, pq, pc, sh, ep, s, sym_tracks));
   } else if (chunks == 4) {
-    W_TRY(launch_eval_tracks<4>(passes, pq, pc, sh, ep, s));
+    W_TRY(launch_eval_tracks<4>(passes, pq, pc, sh, ep, s, sym_tracks));
   } else if (chunks == 8) {
-    W_TRY(launch_eval_tracks<8>(passes, pq, pc, sh, ep, s));
+    W_TRY(launch_eval_tracks<8>(passes, pq, pc, sh, ep, s, sym_tracks));
   } else if (chunks == 16) {
-    W_TRY(launch_eval_tracks<16>(passes, pq, pc, sh, ep, s));
+    W_TRY(launch_eval_tracks<16>(passes, pq, pc, sh, ep, s, sym_tracks));
   } else {
     W_TRY(launch_gemm_rect<EvalEpi>(passes, pq, pc, sh, ep, s));
   }

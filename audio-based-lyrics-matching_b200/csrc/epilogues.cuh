@@ -300,7 +300,13 @@ __device__ __forceinline__ float red_neutral(int op) {
   return op == kRedMax ? __int_as_float(0xff800000) : (op == kRedMin ? __int_as_float(0x7f800000) : 0.f);
 }
 
-template <int kQueueCapT, int kCachePairsT, int kS = 1>
+// kSym (chunked all-vs-all, queries == candidates, no top-k, a reduction that is the same in both directions): the
+// sweep visits only the tiles that reach above the diagonal (GemmShape::sym on the CTA-pair core) and every track pair
+// (q, c) with c > q is scored twice -- as candidate c of query q (the row direction: everything below, unchanged) and as
+// candidate q of query c (the column direction: the lowest threshold of the chunk's 32 / kS column tracks is prefetched
+// with their ids, the few elements that pass are queued with a direction bit and binned against the global CSR
+// thresholds of their column query).
+template <int kQueueCapT, int kCachePairsT, int kS = 1, bool kSym = false>
 struct EvalEpiT {
   static_assert(kS == 1 || kS == 2 || kS == 4 || kS == 8 || kS == 16, "chunks per track: a power of two <= 16");
   static constexpr int kGroups = 32 / kS;  // tracks per 32-row / 32-column chunk
@@ -332,6 +338,9 @@ struct EvalEpiT {
     int so;         // offset of the row's thresholds inside the shared cache, -1 if not cached
     int n_cached;   // cached pairs of the unit (all threads hold the same value)
     int cc_next, ci_next, next_col;  // ids of this lane's column in the NEXT chunk (prefetched)
+    float clim_next;                 // kSym: lowest threshold of that column's query
+    float clim_q[4];                 // kSym: per queued chunk, like cc_q
+    int own;                         // kSym: this lane carries a valid track
     long long off;
     long long base; // off[] of the unit's first row
     long long cbase;
@@ -356,6 +365,7 @@ struct EvalEpiT {
     const bool ok = lane < kGroups && col < sh.n_cols / kS;
     st.cc_next = ok ? __ldg(p.c_c + col) : 0;
     st.ci_next = ok ? __ldg(p.c_i + col) : 0;
+    if constexpr (kSym) st.clim_next = ok ? __ldg(p.lim + col) : __int_as_float(0x7f800000);
   }
 
   __device__ static __forceinline__ void row_begin(const Params& p, RowState& st, int row, int part,
@@ -368,6 +378,7 @@ struct EvalEpiT {
     const int q = row / kS;                                    // query (track) of this row
     const bool own = row < sh.m_rows && (lane % kS) == 0;      // one lane per track carries its state
     st.cbase = ((long long)part * p.nq_total + q) * p.cap;
+    st.own = own;
     if (own) {
       st.tlim = p.lim[q];
       st.qc = p.q_c[q];
@@ -428,7 +439,8 @@ struct EvalEpiT {
   // Process the queue range [begin, end): 32 elements per round, every lane busy.  cc / ci / colok are the
   // ids and validity of this lane's column in the chunk the range came from; col0 its first column.
   __device__ static __forceinline__ void process_range(const Params& p, RowState& st, const EpiCtx& ctx, int begin,
-                                                       int end, int cc, int ci, int colok, int col0, int lane) {
+                                                       int end, int cc, int ci, int colok, int col0, int lane,
+                                                       float clim = 0.f) {
     constexpr unsigned kFull = 0xffffffffu;
     const float* qv = q_val(ctx);
     const uint16_t* qt = q_tag(ctx);
@@ -441,6 +453,7 @@ struct EvalEpiT {
       const float s = active ? qv[r] : 0.f;
       const int tag = active ? (int)qt[r] : 0;
       const int L = (tag >> 5) & 31, e = tag & 31;  // row lane and column of the element
+      const bool coldir = kSym && (tag >> 10) != 0;  // the element scores its COLUMN's query (candidate: the row's track)
       const int rqc = __shfl_sync(kFull, st.qc, L);
       const int rqi = __shfl_sync(kFull, st.qi, L);
       const int rpc = __shfl_sync(kFull, st.cnt, L);
@@ -452,8 +465,15 @@ struct EvalEpiT {
       const int ok = __shfl_sync(kFull, colok, e);
       // i_j == i_q: self (or a version-id collision), never a candidate -- the test is symmetric
       const bool cand = active && ok && cicol != rqi;
-      const int pc = rpc, so = rso;
-      const float tl = rtl;
+      int pc = rpc, so = rso;
+      float tl = rtl;
+      if constexpr (kSym) {
+        const float cl = __shfl_sync(kFull, clim, e);
+        if (coldir) {
+          tl = cl;
+          so = -1;  // binned against the column query's thresholds in the global CSR
+        }
+      }
       if (cand && p.topk > 0 && s > tau) {
         const int slot = atomicAdd(&ncand[L], 1);
         const long long cb = st.cbase + (long long)(L / kS - lane / kS) * p.cap + slot;  // tracks of a warp are consecutive
@@ -488,8 +508,14 @@ struct EvalEpiT {
         }
       }
       const long long offL = __shfl_sync(kFull, st.off, L);
-      if (neg && so < 0) {  // thresholds not cached (giant clique): global CSR arrays
-        const long long o = offL;
+      if (neg && so < 0) {  // thresholds not cached (giant clique; column direction): global CSR arrays
+        long long o = offL;
+        if constexpr (kSym) {
+          if (coldir) {
+            o = __ldg(p.off + col0 + e);
+            pc = __ldg(p.cnt + col0 + e);
+          }
+        }
         k = count_below(p.thr + o, pc, s);
         if (k > 0) atomicAdd(p.hist + o + (k - 1), 1u);
       }
@@ -529,7 +555,8 @@ struct EvalEpiT {
 #pragma unroll
     for (int sl = 0; sl < kSlots; ++sl) {
       if (sl < st.nslot) {
-        process_range(p, st, ctx, begin, st.q_end[sl], st.cc_q[sl], st.ci_q[sl], st.ok_q[sl], st.col0_q[sl], lane);
+        process_range(p, st, ctx, begin, st.q_end[sl], st.cc_q[sl], st.ci_q[sl], st.ok_q[sl], st.col0_q[sl], lane,
+                      kSym ? st.clim_q[sl] : 0.f);
         begin = st.q_end[sl];
       }
     }
@@ -541,7 +568,7 @@ struct EvalEpiT {
 
   // scatter the elements selected by `mb` into the queue starting at `base`; returns their number
   __device__ static __forceinline__ int push(const EpiCtx& ctx, const uint32_t (&acc)[32], unsigned mb, int base,
-                                             int lane) {
+                                             int lane, int dir = 0) {
     float* qv = q_val(ctx);
     uint16_t* qt = q_tag(ctx);
     const int mine = __popc(mb);
@@ -555,7 +582,7 @@ struct EvalEpiT {
         for (int e = 8 * g; e < 8 * g + 8; ++e) {
           if (mb & (1u << e)) {
             qv[pos] = __uint_as_float(acc[e]);
-            qt[pos] = (uint16_t)((lane << 5) | e);
+            qt[pos] = (uint16_t)((dir << 10) | (lane << 5) | e);
             ++pos;
           }
         }
@@ -625,22 +652,37 @@ struct EvalEpiT {
     // ids of the 32 candidates of this chunk, one per lane, were prefetched during the previous
     // chunk; start the loads for the next one now so their L2 latency is off the critical path
     const int cc = st.cc_next, ci = st.ci_next;
+    const float clim = kSym ? st.clim_next : 0.f;
     const int colok = lane < kGroups && (col0 + lane) < sh.n_cols / kS;
     st.next_col = col0 * kS + ctx.col_step;
     prefetch_ids(p, st, sh, lane);
 
     // ---- fast path: one compare per element, nothing else when no lane of the warp passes
-    unsigned m = 0;
+    unsigned m = 0, mc = 0;
 #pragma unroll
     for (int e = 0; e < 32; ++e) m |= (__uint_as_float(acc[e]) > st.lim) ? (1u << e) : 0u;
-    if (!__any_sync(kFull, m != 0)) return;
+    if constexpr (kSym) {
+      // column direction: the element against the lowest threshold of its column's query; a pair is scored (both
+      // ways) where it is met above the diagonal, c > q
+#pragma unroll
+      for (int e = 0; e < kGroups; ++e) {
+        const float cl = __shfl_sync(kFull, clim, e);
+        mc |= (__uint_as_float(acc[e]) > cl) ? (1u << e) : 0u;
+      }
+      const int d = row / kS - col0;
+      const unsigned above = d < 0 ? 0xffffffffu : (d >= 31 ? 0u : (0xffffffffu << (d + 1)));
+      m &= above;
+      mc = st.own ? (mc & above) : 0u;
+    }
+    if (!__any_sync(kFull, (m | mc) != 0)) return;
 
     // ---- collect: the passing elements go to the warp queue; they are binned in drain(), after the
     // accumulator has been released, so the MMA warp never waits for a slow chunk
-    const int total = __reduce_add_sync(kFull, __popc(m));
+    const int total = __reduce_add_sync(kFull, __popc(m) + __popc(mc));
     if (st.nslot == kSlots || st.qn + total > kQueueCap) drain(p, st, ctx);
     if (total <= kQueueCap) {
-      push(ctx, acc, m, st.qn, lane);
+      const int n_row = push(ctx, acc, m, st.qn, lane);
+      if constexpr (kSym) push(ctx, acc, mc, st.qn + n_row, lane, 1);
       st.qn += total;
       const int sl = st.nslot++;
 #pragma unroll
@@ -651,18 +693,22 @@ struct EvalEpiT {
           st.cc_q[k] = cc;
           st.ci_q[k] = ci;
           st.ok_q[k] = colok;
+          if constexpr (kSym) st.clim_q[k] = clim;
         }
       }
     } else {
       // a chunk denser than the whole queue: bin it now, kBatchCols columns at a time
       constexpr int kCols = kBatchCols;
 #pragma unroll 1
-      for (int bi = 0; bi < 32 / kCols; ++bi) {
-        const unsigned sel = ((1u << kCols) - 1u) << (kCols * bi);
-        const int n = push(ctx, acc, m & sel, 0, lane);
-        __syncwarp();
-        process_range(p, st, ctx, 0, n, cc, ci, colok, col0, lane);
-        __syncwarp();
+      for (int dir = 0; dir < (kSym ? 2 : 1); ++dir) {
+#pragma unroll 1
+        for (int bi = 0; bi < 32 / kCols; ++bi) {
+          const unsigned sel = ((1u << kCols) - 1u) << (kCols * bi);
+          const int n = push(ctx, acc, (dir ? mc : m) & sel, 0, lane, dir);
+          __syncwarp();
+          process_range(p, st, ctx, 0, n, cc, ci, colok, col0, lane, clim);
+          __syncwarp();
+        }
       }
       if (p.topk > 0) compact_topk(p, st, ctx, lane);
     }
@@ -692,5 +738,7 @@ struct EvalEpiT {
 using EvalEpi = EvalEpiT<256, 3456>;           // 8 epilogue warps
 template <int kS>
 using EvalTracksEpi = EvalEpiT<256, 3456, kS>;  // kS chunk embeddings per track, reduced in the epilogue
+template <int kS>
+using EvalTracksSymEpi = EvalEpiT<256, 3456, kS, true>;  // ... chunked all-vs-all: tiles above the diagonal, both directions
 
 }  // namespace wealy

@@ -295,9 +295,9 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
       ctx.cta_scratch = scratch_base + kEpiWarps * Epi::kWarpScratchBytes;
       ctx.tid = ew * 32 + lane;
       ctx.nthreads = kEpiWarps * 32;
-      // symmetric sweeps: the pair's 256-row super block (the CTAs' rows interleave); otherwise this CTA's own 128 rows
-      ctx.row_base = shape.sym ? rb * 2 * kTileM : rb * 2 * kTileM + (int)cta_rank * kTileM;
-      ctx.row_span = shape.sym ? 2 * kTileM : kTileM;
+      // interleaved rows: the pair's 256-row super block (the CTAs' rows alternate); otherwise this CTA's own 128 rows
+      ctx.row_base = (shape.sym & 2) ? rb * 2 * kTileM : rb * 2 * kTileM + (int)cta_rank * kTileM;
+      ctx.row_span = (shape.sym & 2) ? 2 * kTileM : kTileM;
       ctx.first_col = t0 * kTileN + half * kChunkCols;
       ctx.col_step = kHalves * kChunkCols;
       ctx.col_slot = nullptr;

@@ -666,7 +666,8 @@ def test_eval_pipeline_overlaps_requests_and_matches_evaluate():
     sets = [_synth().make_eval_set(n, 64, seed=80 + k) for k, n in enumerate((1500, 1500, 900, 1500, 2100))]
     want = []
     for s in sets:
-        a, r = we.evaluate(s["c"].cuda(), s["i"].cuda(), s["z"].cuda(), s["c"].cuda(), s["i"].cuda(), s["z"].cuda())
+        c, i, z = s["c"].cuda(), s["i"].cuda(), s["z"].cuda()    # the SAME tensors on both sides: the symmetric sweep
+        a, r = we.evaluate(c, i, z, c, i, z)
         want.append((a.cpu(), r.cpu()))
     pipe = we.EvalPipeline()
     tickets = []

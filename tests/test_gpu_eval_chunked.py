@@ -146,3 +146,57 @@ def test_ragged_tracks_topk_similarities_against_reference_outputs(redux):
     got = torch.empty_like(want)
     got.scatter_(1, idx.cpu(), sim.cpu())
     assert (got - want).abs().max() <= 4e-6
+
+
+def _all_item_ranks_chunked(plan, c, i, z, redux, lens=None, gap=1e-5, sim_tol=4e-6):
+    """Every relevant item's rank (plan.ranks() of the run that just finished) inside the band its `gap` neighbours allow,
+    exact where the band is a single rank -- the contract of tests/test_gpu_eval.py::_check_all_item_ranks on tracks."""
+    off_g, ranks_g, sims_g = (t.cpu() for t in plan.ranks())
+    off_o, sims_o, exact, lo, hi = oev.rank_bands(c, i, z, c, i, z, gap=gap, redux=redux, q_len=lens, c_len=lens)
+    assert torch.equal(off_g, off_o)
+    r, sg = ranks_g.long(), sims_g.double()
+    assert float((sg - sims_o).abs().max()) <= sim_tol
+    assert bool(((r >= lo) & (r <= hi)).all()), "a relevant item's rank left the band its 1e-5 neighbours allow"
+    single = lo == hi
+    assert torch.equal(r[single], exact[single])
+    return int(single.sum()), int(single.numel())
+
+
+@pytest.mark.parametrize("redux", ["min", "mean", "max"])
+@pytest.mark.parametrize("n,s,d", [(2500, 4, 64), (1100, 8, 96), (3001, 2, 64), (130, 16, 32)])
+def test_chunked_all_vs_all_symmetric_sweep_all_item_ranks(n, s, d, redux):
+    """Chunked all-vs-all with a reduction that is the same in both directions runs the half sweep (tiles above the
+    diagonal on the CTA-pair core, every track pair scored for its row AND its column query): the rank of EVERY relevant
+    item against the oracle, at sizes that span several super row blocks / column chunks and end in ragged tiles."""
+    from wealy_b200 import evaluation as we
+    c, i, z = _chunked_set(n, s, d, seed=3 * n + s)
+    cq, iq, zq = c.cuda(), i.cuda(), z.cuda()
+    plan = we.EvalPlan(cq, iq, cq, iq)
+    res = plan.run(zq, zq, redux=redux)
+    torch.cuda.synchronize()
+    n_exact, n_all = _all_item_ranks_chunked(plan, c, i, z, redux)
+    assert n_exact > 0.5 * n_all
+    aps_o, r1_o = oev.evaluate_argsort(c, i, z, c, i, z, redux=redux)
+    assert abs(float(res["aps"].double().mean().cpu()) - float(aps_o.mean())) <= 1e-4
+    plan.close()
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+@pytest.mark.parametrize("redux", ["min", "max", "mean"])
+def test_chunked_symmetric_sweep_equals_rectangle_sweep(redux, ragged, monkeypatch):
+    """The half sweep against the full rectangle (WEALY_SYM_TRACKS=0) on the same data: min / max reduce the same 64
+    numbers either way (identical results); the mean's summation order differs between the directions (ranks may move
+    inside their 1e-5 band: MAP within 1e-6)."""
+    from wealy_b200 import evaluation as we
+    n, s, d = 1800, 8, 64
+    c, i, z, lens = _ragged(n, s, d, seed=21) if ragged else (*_chunked_set(n, s, d, seed=21), None)
+    cq, iq, zq = c.cuda(), i.cuda(), z.cuda()
+    kw = dict(q_chunks=lens, c_chunks=lens) if ragged else {}
+    a1, r1 = we.evaluate(cq, iq, zq, cq, iq, zq, redux=redux, **kw)
+    monkeypatch.setenv("WEALY_SYM_TRACKS", "0")
+    a0, r0 = we.evaluate(cq, iq, zq, cq, iq, zq, redux=redux, **kw)
+    if redux != "mean":
+        assert torch.equal(a1, a0) and torch.equal(r1, r0)
+    else:
+        assert abs(float(a1.double().mean()) - float(a0.double().mean())) <= 1e-6
+        assert float((r1 != r0).float().mean()) <= 0.01

@@ -44,10 +44,25 @@ def main():
     ids = synth.make_eval_set(n, 8, seed=2, device="cuda", md5_ids=False)
     z = s["z"].view(n, ch, 1024)
     plan = we.EvalPlan(ids["c"], ids["i"], ids["c"], ids["i"])
-    ms, r = timed(lambda: plan.run(z, z, redux="min", allow_empty=True))
-    out["chunked_tracks"] = {"tracks": n, "chunks": ch, "ms": ms, "g_chunk_pairs_per_s": (n * ch) ** 2 / (ms * 1e-3) / 1e9,
-                             "sweep_ms": plan.last_sweep_ms()}
+    for label, env in (("chunked_tracks", "1"), ("chunked_tracks_rectangle", "0")):   # half sweep (default) / full rectangle
+        os.environ["WEALY_SYM_TRACKS"] = env
+        ms, r = timed(lambda: plan.run(z, z, redux="min", allow_empty=True))
+        out[label] = {"tracks": n, "chunks": ch, "ms": ms, "g_chunk_pairs_per_s": (n * ch) ** 2 / (ms * 1e-3) / 1e9,
+                      "sweep_ms": plan.last_sweep_ms(), "map": float(r["sums"][0] / r["sums"][2])}
     plan.close()
+    # 2 chunks per track: a quarter of the elements survive the reduction (the column direction's worst case)
+    n2 = 50_000
+    ids2 = synth.make_eval_set(n2, 8, seed=3, device="cuda", md5_ids=False)
+    z2 = s["z"].view(n2, 2, 1024)
+    plan = we.EvalPlan(ids2["c"], ids2["i"], ids2["c"], ids2["i"])
+    for label, env in (("chunked_2", "1"), ("chunked_2_rectangle", "0")):
+        os.environ["WEALY_SYM_TRACKS"] = env
+        ms, r = timed(lambda: plan.run(z2, z2, redux="mean", allow_empty=True))
+        out[label] = {"tracks": n2, "chunks": 2, "redux": "mean", "ms": ms, "sweep_ms": plan.last_sweep_ms(),
+                      "map": float(r["sums"][0] / r["sums"][2])}
+    os.environ.pop("WEALY_SYM_TRACKS")
+    plan.close()
+    del z2
     del s, plan, z
     torch.cuda.empty_cache()
     os.environ["WEALY_SYM_TOPK"] = "0"
