@@ -16,6 +16,8 @@ print('parity', {k:v for k,v in d['parity'].items() if k!='note'})
 for k in ('c1_shs100k','c3_500k','c5_topk100'):
     c=d[k]; p=(c.get('parity') or c.get('parity_all_queries')); print(k, round(c['ms_per_step'],3), c.get('gpairs_per_s'), c.get('roofline_frac'), c.get('topk_path'), p['item_ranks_out_of_band'], p['item_ranks_exact_mismatches'], p.get('topk_idx_mismatches'))
 print('c4', {k:(round(v['fwd_ms'],4),round(v['fwd_bwd_eager_ms'],4),round(v['fwd_bwd_graph_ms'],4),v['loss_rel_err_vs_cpu_fp32']) for k,v in d['c4_loss'].items() if isinstance(v,dict)})
+f=d['f1_chunked']; print('f1', round(f['ms_per_step'],2), round(f['full_rectangle_ms_per_step'],2), f['rectangle_vs_half_identical'], f['stages_ms'], f['parity'])
+print('pipelined', d['e2e'].get('pipelined'))
 print('cpu', d['cpu_baseline'])
 PY
 ( time timeout 900 python bench.py --impl reference --steps 3 --warmup 3 ) > gpurun_out/r02z_bench_ref.json 2> gpurun_out/r02z_bench_ref.err
