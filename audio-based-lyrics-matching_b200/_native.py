@@ -34,6 +34,8 @@ class LossCfg(ctypes.Structure):
 SIGNATURES = {
     "wealy_last_error": (ctypes.c_char_p, []),
     "wealy_version": (c_int, []),
+    "wealy_pool_release": (c_int, []),
+    "wealy_pool_stats": (c_int, [ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "wealy_sim_matrix_workspace_bytes": (c_sz, [c_i64, c_i64, c_i64, c_int]),
     "wealy_sim_matrix": (c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_int, c_int, c_f32, c_f32, c_int,
                                  c_vp, c_i64, c_int, c_vp, c_sz, c_vp]),

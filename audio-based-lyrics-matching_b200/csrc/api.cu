@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -110,12 +112,135 @@ static cudaError_t dev_alloc(void** ptr, size_t bytes, cudaStream_t s) {
 static void dev_free(void* ptr, cudaStream_t s) {
   if (ptr) cudaFreeAsync(ptr, s);
 }
+// The large buffers of a plan (operand planes, top-k candidate lists) additionally go through a small free list of whole
+// blocks.  A serving loop destroys and creates a plan per request; handing the freed 0.4 GB block of one plan straight
+// to the next keeps the driver's pool out of that rhythm -- its stream-ordered sub-allocator was measured to stall
+// cudaMallocFromPoolAsync for 20-400 ms now and then when a block of that size had to be found while other work was
+// in flight (profiles/r02_summary.md, "EvalPipeline").  A block is reused on any stream: the new owner's stream waits
+// for the event recorded where the old owner released it.
+struct BigBlock {
+  void* ptr;
+  size_t bytes;
+  int dev;
+  cudaStream_t stream;
+  cudaEvent_t released;
+};
+static std::mutex g_big_mu;
+static std::vector<BigBlock> g_big;
+static const size_t kBigMin = (size_t)32 << 20;
+
+static cudaError_t big_alloc(void** ptr, size_t* cap, size_t bytes, cudaStream_t s) {
+  *ptr = nullptr;
+  *cap = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (bytes >= kBigMin) {
+    std::lock_guard<std::mutex> lock(g_big_mu);
+    int best = -1;
+    for (int k = 0; k < (int)g_big.size(); ++k) {
+      const BigBlock& b = g_big[k];
+      // (a block up to 1.5x the request: the next request of the same workload fits exactly, a much smaller one
+      //  should not pin a large block)
+      if (b.dev == dev && b.bytes >= bytes && b.bytes <= bytes + bytes / 2 && (best < 0 || b.bytes < g_big[best].bytes)) best = k;
+    }
+    if (best >= 0) {
+      BigBlock b = g_big[best];
+      g_big.erase(g_big.begin() + best);
+      if (b.stream != s) cudaStreamWaitEvent(s, b.released, 0);
+      cudaEventDestroy(b.released);
+      *ptr = b.ptr;
+      *cap = b.bytes;
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = dev_alloc(ptr, bytes, s);
+  if (e == cudaSuccess) *cap = bytes;
+  return e;
+}
+static void big_free(void* ptr, size_t bytes, cudaStream_t s) {
+  if (!ptr) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t keep = (size_t)env_int("WEALY_POOL_KEEP_MB", 4096) << 20;
+  BigBlock b{ptr, bytes, dev, s, nullptr};
+  bool cache = bytes >= kBigMin && bytes <= keep;
+  if (cache && (cudaEventCreateWithFlags(&b.released, cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventRecord(b.released, s) != cudaSuccess)) {
+    cudaGetLastError();
+    if (b.released) cudaEventDestroy(b.released);
+    cache = false;
+  }
+  if (!cache) dev_free(ptr, s);
+  std::lock_guard<std::mutex> lock(g_big_mu);
+  if (cache) g_big.push_back(b);
+  // oldest blocks go back to the pool once the list holds more than the limit
+  size_t total = 0;
+  for (const BigBlock& x : g_big) total += x.dev == dev ? x.bytes : 0;
+  for (size_t k = 0; k < g_big.size() && total > keep;) {
+    if (g_big[k].dev != dev) { ++k; continue; }
+    total -= g_big[k].bytes;
+    cudaFreeAsync(g_big[k].ptr, g_big[k].stream);
+    cudaEventDestroy(g_big[k].released);
+    g_big.erase(g_big.begin() + k);
+  }
+}
+
+// Called when a plan is destroyed.  Only memory that is cached AND unused counts against the limit: a trim releases
+// physical memory back to the driver (and the next plan pays for mapping it again, ~100 ms per GB), so it must not
+// fire while plans are being created and destroyed in a steady rhythm -- only when a process that evaluated something
+// big sits on more than WEALY_POOL_KEEP_MB of idle scratch.
 static void pool_trim() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !g_pools[dev]) return;
   const size_t keep = (size_t)env_int("WEALY_POOL_KEEP_MB", 4096) << 20;
-  cudaMemPoolTrimTo(g_pools[dev], keep);
+  cuuint64_t reserved = 0, used = 0;
+  if (cudaMemPoolGetAttribute(g_pools[dev], cudaMemPoolAttrReservedMemCurrent, &reserved) != cudaSuccess ||
+      cudaMemPoolGetAttribute(g_pools[dev], cudaMemPoolAttrUsedMemCurrent, &used) != cudaSuccess) {
+    cudaGetLastError();
+    return;
+  }
+  if (reserved > used && (size_t)(reserved - used) > keep) cudaMemPoolTrimTo(g_pools[dev], (size_t)used + keep);
+}
+
+extern "C" int wealy_pool_release(void) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lock(g_big_mu);
+    for (size_t k = 0; k < g_big.size();) {
+      if (g_big[k].dev != dev) { ++k; continue; }
+      cudaFreeAsync(g_big[k].ptr, g_big[k].stream);
+      cudaEventDestroy(g_big[k].released);
+      g_big.erase(g_big.begin() + k);
+    }
+  }
+  CU_TRY(cudaDeviceSynchronize());  // every stream-ordered free has happened
+  if (dev >= 0 && dev < 64 && g_pools[dev]) CU_TRY(cudaMemPoolTrimTo(g_pools[dev], 0));
+  return WEALY_OK;
+}
+
+extern "C" int wealy_pool_stats(int64_t* reserved_bytes, int64_t* used_bytes, int64_t* reserved_high, int64_t* used_high) {
+  int dev = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  cuuint64_t v[4] = {0, 0, 0, 0};
+  if (dev >= 0 && dev < 64 && g_pools[dev]) {
+    CU_TRY(cudaMemPoolGetAttribute(g_pools[dev], cudaMemPoolAttrReservedMemCurrent, &v[0]));
+    CU_TRY(cudaMemPoolGetAttribute(g_pools[dev], cudaMemPoolAttrUsedMemCurrent, &v[1]));
+    CU_TRY(cudaMemPoolGetAttribute(g_pools[dev], cudaMemPoolAttrReservedMemHigh, &v[2]));
+    CU_TRY(cudaMemPoolGetAttribute(g_pools[dev], cudaMemPoolAttrUsedMemHigh, &v[3]));
+  }
+  {
+    // blocks parked in the library's free list are idle scratch, not memory in use
+    std::lock_guard<std::mutex> lock(g_big_mu);
+    for (const BigBlock& x : g_big)
+      if (x.dev == dev && v[1] >= x.bytes) v[1] -= x.bytes;
+  }
+  if (reserved_bytes) *reserved_bytes = (int64_t)v[0];
+  if (used_bytes) *used_bytes = (int64_t)v[1];
+  if (reserved_high) *reserved_high = (int64_t)v[2];
+  if (used_high) *used_high = (int64_t)v[3];
+  return WEALY_OK;
 }
 
 // temporaries of one host function: freed (stream-ordered) on every return path
@@ -660,12 +785,15 @@ struct wealy_eval_plan {
 extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
   if (!p) return;
   void* ptrs[] = {p->q_c, p->q_i, p->sorted_c, p->sorted_idx, p->seg_lo, p->seg_len, p->npos, p->off,
-                  p->raw, p->lvl_thr_buf ? nullptr : (void*)p->thr, p->lim, p->cnt, p->hist, p->planes_buf, p->topk_buf, p->tks_buf,
+                  p->raw, p->lvl_thr_buf ? nullptr : (void*)p->thr, p->lim, p->cnt, p->hist,
                   p->s_i, p->s_seg_lo, p->s_seg_len, p->s_npos, p->s_off, p->lvl_thr_buf ? p->lvl_thr_buf : (void*)p->s_lvl,
                   p->s_cinfo, p->s_dirty};
   // frees are ordered behind the last work that touched the buffers: the stream of the last run
   cudaStream_t fs = p->timed ? p->last_stream : p->stream;
   for (void* q : ptrs) dev_free(q, fs);
+  big_free(p->planes_buf, p->planes_cap, fs);
+  big_free(p->topk_buf, p->topk_cap, fs);
+  big_free(p->tks_buf, p->tks_cap, fs);
   if (!p->same_ids) {
     dev_free(p->c_c, fs);
     dev_free(p->c_i, fs);
@@ -942,11 +1070,10 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   const int64_t rows_q = sym ? ceil_div(nq, kTileM) * kTileM : rq;
   const size_t need = planes_bytes(rows_q, d, passes) + (same ? 0 : planes_bytes(rc, d, passes)) + 2048;
   if (need > p->planes_cap) {
-    dev_free(p->planes_buf, s);
+    big_free(p->planes_buf, p->planes_cap, s);
     p->planes_buf = nullptr;
     p->planes_cap = 0;
-    CU_TRY(dev_alloc((void**)&p->planes_buf, need, s));
-    p->planes_cap = need;
+    CU_TRY(big_alloc((void**)&p->planes_buf, &p->planes_cap, need, s));
   }
   uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)p->planes_buf, 1024));
   Planes pq, pc;
@@ -1046,12 +1173,11 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     const size_t o_ti = reserve((size_t)rows * tk_cap2 * 4);
     const size_t o_tc = reserve((size_t)rows * 4);
     const size_t o_fail = reserve(256);
-    if (need_tk > p->tks_cap) {
-      dev_free(p->tks_buf, s);
+    if (need_tk + 1024 > p->tks_cap) {
+      big_free(p->tks_buf, p->tks_cap, s);
       p->tks_buf = nullptr;
       p->tks_cap = 0;
-      CU_TRY(dev_alloc(&p->tks_buf, need_tk + 1024, s));
-      p->tks_cap = need_tk;
+      CU_TRY(big_alloc(&p->tks_buf, &p->tks_cap, need_tk + 1024, s));
     }
     uint8_t* tb = reinterpret_cast<uint8_t*>(align_up((size_t)p->tks_buf, 1024));
     __half* samp = reinterpret_cast<__half*>(tb + o_samp);
@@ -1116,11 +1242,10 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     const size_t slots = (size_t)parts * nq * cap;
     const size_t tneed = slots * 16 + (size_t)parts * nq * 4 + 1024;  // candidate lists + finalize staging
     if (tneed > p->topk_cap) {
-      dev_free(p->topk_buf, s);
+      big_free(p->topk_buf, p->topk_cap, s);
       p->topk_buf = nullptr;
       p->topk_cap = 0;
-      CU_TRY(dev_alloc((void**)&p->topk_buf, tneed, s));
-      p->topk_cap = tneed;
+      CU_TRY(big_alloc((void**)&p->topk_buf, &p->topk_cap, tneed, s));
     }
     ep.cand_val = reinterpret_cast<float*>(p->topk_buf);
     ep.cand_idx = reinterpret_cast<int*>(ep.cand_val + slots);

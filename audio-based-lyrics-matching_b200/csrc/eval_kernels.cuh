@@ -144,9 +144,11 @@ __device__ __forceinline__ void mma_16x8x16(float (&c)[4], const unsigned (&a)[4
 // K_pos for chunked tracks (row f1).  One CTA (8 warps) per query track: for every relevant candidate track the kS x kS chunk
 // similarities (same planes, same three products as the sweep) are reduced exactly like the sweep's epilogue does
 // (red_inner over the candidate's chunks, red_outer over the query's), then rank-sorted ascending.
-// The kS x kS block of a (query track, candidate track) pair is one (kS <= 8) or two
-// (kS = 16) warp-level tensor-core tiles m16n8k16 (rows = the query's chunks, columns = the candidate's), read
-// straight from the planes: 16x less L2 traffic than kS^2 separate dot products.
+// The kS x kS blocks come from warp-level tensor-core tiles m16n8k16 read straight from the planes: the 16 tile ROWS
+// are candidate chunks -- 16 / kS whole candidates per tile for kS <= 8 (eight two-chunk tracks, two eight-chunk
+// tracks), one for kS = 16 -- and the 8 tile COLUMNS the query's chunks (two tiles for kS = 16), so a warp reads the
+// query's rows once for all the candidates of its tile.  Two accumulators take alternate k windows (the dependent MMA
+// chain is what bounds a warp).
 __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
     const __half* __restrict__ q_hi, const __half* __restrict__ q_lo, const __half* __restrict__ c_hi,
     const __half* __restrict__ c_lo, int d_pad, int ks, int red_inner, int red_outer, float red_scale,
@@ -154,8 +156,8 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
     const int* __restrict__ seg_lo, const int* __restrict__ seg_len, const long long* __restrict__ off,
     float* __restrict__ raw, float* __restrict__ thr, float* __restrict__ lim, int* __restrict__ cnt,
     const int* __restrict__ q_len, const int* __restrict__ c_len) {
-  // one CTA per query track, its 8 warps take the relevant candidates round-robin (a clique of 160 versions is 20
-  // sequential contractions per warp, not 160); slots of the query's CSR row are handed out by a shared counter
+  // its 8 warps take the relevant candidates tile by tile, round-robin (a clique of 160 versions is a handful of
+  // sequential contractions per warp); slots of the query's CSR row are handed out by a shared counter
   const int q = (int)blockIdx.x;
   const int lane = (int)(threadIdx.x & 31), warp = (int)(threadIdx.x >> 5);
   __shared__ int n_sh;
@@ -167,71 +169,89 @@ __global__ void __launch_bounds__(256) pos_thresholds_tracks_kernel(
   const bool ragged = c_len != nullptr;
   const int lq = ragged ? min(max(q_len[q], 1), ks) : ks;
   const long long o = off[q];
-  // A rows: the query's chunks g and g + 8 (clamped: rows >= ks are masked out of the reduction)
-  const long long ra0 = ((long long)q * ks + min(g, ks - 1)) * d_pad, ra1 = ((long long)q * ks + min(g + 8, ks - 1)) * d_pad;
-  const int ntile = ks > 8 ? 2 : 1;
-  for (int m = warp; m < len; m += 8) {
-    const int j = sorted_idx[first + m];
-    if (c_i[j] == qi) continue;  // self / id collision
-    const int lc = ragged ? min(max(c_len[j], 1), ks) : ks;
-    float v0 = red_neutral(red_inner), v1 = red_neutral(red_inner);  // inner reductions of rows g and g + 8
+  const bool wide = ks > 8;                      // 16 chunks: one candidate fills the tile's rows, the query two tiles
+  const int per = wide ? 1 : 16 / ks;            // candidates per tile
+  const int kr = wide ? 8 : ks;                  // rows of one candidate inside an 8-row half of the tile
+  // tile rows g and g + 8 of this lane: which candidate of the tile, which of its chunks
+  const int sA = wide ? 0 : g / ks, cA = wide ? g : g % ks;
+  const int sB = wide ? 0 : (g + 8) / ks, cB = wide ? g + 8 : (g + 8) % ks;
+  const int ntile = wide ? 2 : 1;
+  const float n_in = red_neutral(red_inner), n_out = red_neutral(red_outer);
+  for (int m0 = warp * per; m0 < len; m0 += 8 * per) {
+    const int mA = m0 + sA, mB = m0 + sB;
+    const int jA = mA < len ? sorted_idx[first + mA] : -1;
+    const int jB = mB < len ? sorted_idx[first + mB] : -1;
+    const bool okA = jA >= 0 && c_i[jA] != qi, okB = jB >= 0 && c_i[jB] != qi;  // (self / id collision: not a candidate)
+    const int lcA = (ragged && okA) ? min(max(c_len[jA], 1), ks) : ks;
+    const int lcB = (ragged && okB) ? min(max(c_len[jB], 1), ks) : ks;
+    const long long rA = ((long long)max(jA, 0) * ks + cA) * d_pad, rB = ((long long)max(jB, 0) * ks + cB) * d_pad;
+    float wA = n_out, wB = n_out;   // outer reductions (over the query's chunks) of this lane's two rows' candidates
     for (int t = 0; t < ntile; ++t) {
-      const long long rb = ((long long)j * ks + min(t * 8 + g, ks - 1)) * d_pad;  // B column g = candidate chunk t * 8 + g
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
-      // (8 consecutive halves per lane, row and 32-wide k window: see pos_pairs_sorted_kernel)
-#pragma unroll 2
-      for (int k = 0; k < d_pad; k += 32) {
-        const int ko = k + tig * 8;
-        // (tile rows 8 .. 15 exist only for 16 chunks per track: zero, not loaded, otherwise)
-        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-        const uint4 ah0 = __ldg(reinterpret_cast<const uint4*>(q_hi + ra0 + ko));
-        const uint4 ah1 = ks > 8 ? __ldg(reinterpret_cast<const uint4*>(q_hi + ra1 + ko)) : zero4;
-        const uint4 bh = __ldg(reinterpret_cast<const uint4*>(c_hi + rb + ko));
-        const unsigned a1[4] = {ah0.x, ah1.x, ah0.y, ah1.y}, a2[4] = {ah0.z, ah1.z, ah0.w, ah1.w};
-        const unsigned b1[2] = {bh.x, bh.y}, b2[2] = {bh.z, bh.w};
-        mma_16x8x16(c, a1, b1);
-        mma_16x8x16(c, a2, b2);
-        if (q_lo) {
-          const uint4 al0 = __ldg(reinterpret_cast<const uint4*>(q_lo + ra0 + ko));
-          const uint4 al1 = ks > 8 ? __ldg(reinterpret_cast<const uint4*>(q_lo + ra1 + ko)) : zero4;
-          const uint4 bl = __ldg(reinterpret_cast<const uint4*>(c_lo + rb + ko));
-          const unsigned l1[4] = {al0.x, al1.x, al0.y, al1.y}, l2[4] = {al0.z, al1.z, al0.w, al1.w};
-          const unsigned m1[2] = {bl.x, bl.y}, m2[2] = {bl.z, bl.w};
-          mma_16x8x16(c, a1, m1);
-          mma_16x8x16(c, a2, m2);
-          mma_16x8x16(c, l1, b1);
-          mma_16x8x16(c, l2, b2);
+      const long long rq = ((long long)q * ks + min(t * 8 + g, ks - 1)) * d_pad;  // B column g = query chunk t * 8 + g
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+      // (8 consecutive halves per lane, row and 32-wide k window: see pos_pairs_sorted_kernel; d_pad is a multiple of 64)
+      for (int k = 0; k < d_pad; k += 64) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float (&c)[4] = u ? c1 : c0;
+          const int ko = k + u * 32 + tig * 8;
+          const uint4 ah0 = __ldg(reinterpret_cast<const uint4*>(c_hi + rA + ko));
+          const uint4 ah1 = __ldg(reinterpret_cast<const uint4*>(c_hi + rB + ko));
+          const uint4 bh = __ldg(reinterpret_cast<const uint4*>(q_hi + rq + ko));
+          const unsigned a1[4] = {ah0.x, ah1.x, ah0.y, ah1.y}, a2[4] = {ah0.z, ah1.z, ah0.w, ah1.w};
+          const unsigned b1[2] = {bh.x, bh.y}, b2[2] = {bh.z, bh.w};
+          mma_16x8x16(c, a1, b1);
+          mma_16x8x16(c, a2, b2);
+          if (q_lo) {
+            const uint4 al0 = __ldg(reinterpret_cast<const uint4*>(c_lo + rA + ko));
+            const uint4 al1 = __ldg(reinterpret_cast<const uint4*>(c_lo + rB + ko));
+            const uint4 bl = __ldg(reinterpret_cast<const uint4*>(q_lo + rq + ko));
+            const unsigned l1[4] = {al0.x, al1.x, al0.y, al1.y}, l2[4] = {al0.z, al1.z, al0.w, al1.w};
+            const unsigned m1[2] = {bl.x, bl.y}, m2[2] = {bl.z, bl.w};
+            mma_16x8x16(c, a1, m1);
+            mma_16x8x16(c, a2, m2);
+            mma_16x8x16(c, l1, b1);
+            mma_16x8x16(c, l2, b2);
+          }
         }
       }
-      // c[0], c[1]: row g, candidate chunks t*8 + 2 tig, + 1;  c[2], c[3]: row g + 8, same columns
+      // c[0], c[1]: tile row g, query chunks t*8 + 2 tig, + 1;  c[2], c[3]: tile row g + 8, same columns
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        if (t * 8 + tig * 2 + e < lc) {
-          v0 = red_op(v0, c[e], red_inner);
-          v1 = red_op(v1, c[2 + e], red_inner);
+        // inner: over the candidate's chunks = the rows of its slot (lanes that differ in the low bits of g; kS = 16: + the other half)
+        float iA = cA < lcA ? c0[e] + c1[e] : n_in;
+        float iB = cB < lcB ? c0[2 + e] + c1[2 + e] : n_in;
+        if (wide) iA = red_op(iA, iB, red_inner);
+        for (int x = 4; x < 4 * kr; x <<= 1) {
+          iA = red_op(iA, __shfl_xor_sync(0xffffffffu, iA, x), red_inner);
+          iB = red_op(iB, __shfl_xor_sync(0xffffffffu, iB, x), red_inner);
+        }
+        if (ragged) {
+          if (red_inner == kRedSum) { iA *= 1.f / (float)lcA; iB *= 1.f / (float)lcB; }
+        } else if (red_inner == kRedSum && red_outer != kRedSum) {
+          iA *= red_scale;
+          iB *= red_scale;
+        }
+        // outer: over the query's chunks = the tile's columns
+        if (t * 8 + 2 * tig + e < lq) {
+          wA = red_op(wA, iA, red_outer);
+          wB = red_op(wB, iB, red_outer);
         }
       }
     }
-    // inner: across the four lanes of a row group (the candidate's chunks)
 #pragma unroll
     for (int x = 1; x < 4; x <<= 1) {
-      v0 = red_op(v0, __shfl_xor_sync(0xffffffffu, v0, x), red_inner);
-      v1 = red_op(v1, __shfl_xor_sync(0xffffffffu, v1, x), red_inner);
+      wA = red_op(wA, __shfl_xor_sync(0xffffffffu, wA, x), red_outer);
+      wB = red_op(wB, __shfl_xor_sync(0xffffffffu, wB, x), red_outer);
     }
-    if (ragged) {
-      if (red_inner == kRedSum) { v0 *= 1.f / (float)lc; v1 *= 1.f / (float)lc; }
-    } else if (red_inner == kRedSum && red_outer != kRedSum) {
-      v0 *= red_scale;
-      v1 *= red_scale;
+    if (red_outer == kRedSum) {
+      const float sc = ragged ? 1.f / (float)lq : red_scale;
+      wA *= sc;
+      wB *= sc;
     }
-    // outer: across the query's chunks = rows g (v0) and g + 8 (v1) of all row groups
-    float w = red_neutral(red_outer);
-    if (g < lq) w = red_op(w, v0, red_outer);
-    if (g + 8 < lq) w = red_op(w, v1, red_outer);
-#pragma unroll
-    for (int x = 4; x < 32; x <<= 1) w = red_op(w, __shfl_xor_sync(0xffffffffu, w, x), red_outer);
-    if (red_outer == kRedSum) w *= ragged ? 1.f / (float)lq : red_scale;
-    if (lane == 0) raw[o + atomicAdd(&n_sh, 1)] = w;
+    // one writer per candidate: the lane of its first chunk's row (kS = 16: both halves belong to candidate A)
+    if (tig == 0 && cA == 0 && okA) raw[o + atomicAdd(&n_sh, 1)] = wA;
+    if (!wide && tig == 0 && cB == 0 && okB) raw[o + atomicAdd(&n_sh, 1)] = wB;
   }
   __syncthreads();
   const int n = n_sh;

@@ -323,7 +323,7 @@ class EvalPipeline:
 
     Single process / single GPU; `precision`, `eps` as in evaluate().  The first requests of a pipeline allocate its slot
     buffers and grow the library's device pool to `depth` plans alive at once (tens to hundreds of ms each, once); after
-    that a request costs what its upload / sweep cost (C2: 26.4 ms per request against 29.3 ms for evaluate())."""
+    that a request costs what its upload / sweep cost (C2: 25 ms per request against 29.3 ms for evaluate())."""
 
     def __init__(self, depth=2, device=None, precision=None, eps=1e-6):
         assert depth >= 2
@@ -390,6 +390,21 @@ class EvalPipeline:
                 slot["done"].synchronize()
                 slot["plan"].close()
                 slot["plan"] = None
+
+
+def pool_stats(device=None):
+    """Device scratch of the library on `device` (its private stream-ordered pool; torch's allocator is not involved):
+    dict(reserved, used, reserved_high, used_high) in bytes."""
+    v = [ctypes.c_int64() for _ in range(4)]
+    with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+        N.check(N.lib.wealy_pool_stats(*[ctypes.byref(x) for x in v]))
+    return dict(zip(("reserved", "used", "reserved_high", "used_high"), (x.value for x in v)))
+
+
+def release_scratch(device=None):
+    """Give all idle device scratch of the library back to the driver (synchronises the device); live plans keep theirs."""
+    with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+        N.check(N.lib.wealy_pool_release())
 
 
 def mean_metrics(sums):

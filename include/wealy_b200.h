@@ -51,6 +51,13 @@ extern "C" {
 
 const char* wealy_last_error(void);
 int wealy_version(void);
+/* Device scratch of the library on the CURRENT device: plans and temporaries come from a private stream-ordered pool
+ * (nothing is taken from, or returned to, the caller's allocator -- the reference's functions allocate through torch;
+ * this is the C ABI's equivalent).  Bytes reserved from the driver / in use now, and their high-water marks.  Destroying
+ * a plan releases idle scratch above WEALY_POOL_KEEP_MB (default 4096) back to the driver. */
+int wealy_pool_stats(int64_t* reserved_bytes, int64_t* used_bytes, int64_t* reserved_high, int64_t* used_high);
+/* Give ALL idle scratch of the current device back to the driver now (synchronises the device). */
+int wealy_pool_release(void);
 
 /* ---- a1/a2: materialised similarity / distance matrix ------------------------------------
  * Replaces lib/tensor_ops.py:152-176 `pairwise_distance_matrix(x, y, mode, p, eps)` (modes

@@ -681,3 +681,41 @@ def test_eval_pipeline_overlaps_requests_and_matches_evaluate():
     with pytest.raises(ValueError):
         pipe.result(tickets[0])                                   # overwritten: more than `depth` requests ago
     pipe.close()
+
+
+def test_library_scratch_is_reused_and_returned(monkeypatch):  # noqa: C901
+    """Plans come and go (evaluate() builds one per call): the library's device scratch must reach a steady state
+    (no growth from call to call: the operand planes of one plan are handed to the next) and be given back to the driver
+    when the caller asks for it (WEALY_POOL_KEEP_MB=0)."""
+    we = _we()
+    s = _synth().make_eval_set(20000, 512, seed=90)                 # planes: 20k x 512 x 2 B x 2 = 41 MB
+    c, i, z = s["c"].cuda(), s["i"].cuda(), s["z"].cuda()
+    import gc
+    gc.collect()                                                    # plans other tests left to the garbage collector
+    torch.cuda.synchronize()
+    base = we.pool_stats()["used"]
+    slack = 32 << 20                                                # the driver reserves in whole 2 MB pages
+    stats = []
+    for _ in range(6):
+        we.evaluate(c, i, z, c, i, z)
+        torch.cuda.synchronize()
+        stats.append(we.pool_stats())
+    assert all(st["used"] == base for st in stats)                  # nothing is held once the plan is gone
+    assert all(st["reserved"] == stats[1]["reserved"] for st in stats[2:])
+    assert stats[-1]["reserved_high"] == stats[1]["reserved_high"]
+    a, r = we.evaluate(c, i, z, c, i, z)
+    we.release_scratch()
+    after = we.pool_stats()
+    assert after["used"] == base and after["reserved"] <= base + slack   # idle scratch released
+    plan = we.EvalPlan(c, i, c, i)
+    plan.run(z, z)
+    we.release_scratch()                                            # a live plan keeps what it holds
+    assert we.pool_stats()["used"] >= base + (40 << 20)
+    res = plan.run(z, z)
+    assert torch.equal(res["aps"], a) and torch.equal(res["r1s"], r)
+    plan.close()
+    monkeypatch.setenv("WEALY_POOL_KEEP_MB", "0")                   # no caching at all: every destroy returns its memory
+    a2, r2 = we.evaluate(c, i, z, c, i, z)
+    assert torch.equal(a, a2) and torch.equal(r, r2)
+    we.release_scratch()
+    assert we.pool_stats()["reserved"] <= base + slack
