@@ -325,10 +325,10 @@ class EvalPipeline:
     buffers and grow the library's device pool to `depth` plans alive at once (tens to hundreds of ms each, once); after
     that a request costs what its upload / sweep cost (C2: 25 ms per request against 29.3 ms for evaluate())."""
 
-    def __init__(self, depth=2, device=None, precision=None, eps=1e-6):
+    def __init__(self, depth=2, device=None, precision=None, eps=1e-6, allow_empty=False):
         assert depth >= 2
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.depth, self.precision, self.eps = int(depth), precision, float(eps)
+        self.depth, self.precision, self.eps, self.allow_empty = int(depth), precision, float(eps), bool(allow_empty)
         self.copy_stream = side_stream(self.device)
         self.slots = [dict(z=None, c=None, i=None, aps=None, r1s=None, done=None, plan=None) for _ in range(self.depth)]
         self.count = 0
@@ -366,7 +366,11 @@ class EvalPipeline:
         compute.wait_event(uploaded)
         with torch.cuda.device(self.device):
             plan = EvalPlan(slot["c"], slot["i"], slot["c"], slot["i"], device=self.device)
-            res = plan.run(slot["z"], slot["z"], eps=self.eps, precision=self.precision)
+            try:
+                res = plan.run(slot["z"], slot["z"], eps=self.eps, precision=self.precision, allow_empty=self.allow_empty)
+            except Exception:
+                plan.close()                                      # (e.g. queries without a relevant candidate: the slot stays free)
+                raise
             slot["aps"].copy_(res["aps"], non_blocking=True)
             slot["r1s"].copy_(res["r1s"], non_blocking=True)
             slot["done"] = torch.cuda.Event()

@@ -680,7 +680,21 @@ def test_eval_pipeline_overlaps_requests_and_matches_evaluate():
     assert torch.equal(a, want[-1][0]) and torch.equal(r, want[-1][1])
     with pytest.raises(ValueError):
         pipe.result(tickets[0])                                   # overwritten: more than `depth` requests ago
+    # a set with a singleton clique is refused like evaluate() refuses it, and the pipeline stays usable
+    bad = sets[0]
+    c_bad = bad["c"].clone()
+    c_bad[0] = int(c_bad.max()) + 1
+    with pytest.raises(ValueError):
+        pipe.submit(c_bad.pin_memory(), bad["i"].pin_memory(), bad["z"].pin_memory())
+    a, r = pipe.result(pipe.submit(sets[1]["c"].pin_memory(), sets[1]["i"].pin_memory(), sets[1]["z"].pin_memory()))
+    assert torch.equal(a, want[1][0]) and torch.equal(r, want[1][1])
     pipe.close()
+    lax = we.EvalPipeline(allow_empty=True)                      # ... or scored without that query when asked to
+    a, r = lax.result(lax.submit(c_bad.pin_memory(), bad["i"].pin_memory(), bad["z"].pin_memory()))
+    cb, ib, zb = c_bad.cuda(), bad["i"].cuda(), bad["z"].cuda()
+    ae, re_ = we.evaluate(cb, ib, zb, cb, ib, zb, allow_empty=True)
+    assert torch.allclose(a, ae.cpu(), rtol=0, atol=0, equal_nan=True) and torch.allclose(r, re_.cpu(), rtol=0, atol=0, equal_nan=True)
+    lax.close()
 
 
 def test_library_scratch_is_reused_and_returned(monkeypatch):  # noqa: C901
