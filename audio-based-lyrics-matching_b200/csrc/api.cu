@@ -1313,7 +1313,12 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
       const bool dyn = env_int("WEALY_PAIR_DYN", 1) != 0;
       if (passes == 3) {
         sh.k_blocks = (int)(pq.d_pad / 32);
-        if (dyn && w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12, true>(pq, sh, sp, s)));
+        // dense threshold levels on the pair core: 4 (C2: 23.45 ms per step against 23.2-23.4 with 3 -- the same --, MAP-0.1
+        // data: 43.7 against 49.1 ms; 2 levels: 24.0-24.2 / 56.9 ms)
+        const int lvp = env_int("WEALY_SYM_LEVELS", 4);
+        if (dyn && w12 && lvp == 2) W_TRY((launch_gemm_pair<EvalSymEpi<2>, 3, 32, 12, true>(pq, sh, sp, s)));
+        else if (dyn && w12 && lvp == 4) W_TRY((launch_gemm_pair<EvalSymEpi<4>, 3, 32, 12, true>(pq, sh, sp, s)));
+        else if (dyn && w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12, true>(pq, sh, sp, s)));
         else if (dyn) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 8, true>(pq, sh, sp, s)));
         else if (w12) W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32, 12>(pq, sh, sp, s)));
         else W_TRY((launch_gemm_pair<EvalSymEpi<3>, 3, 32>(pq, sh, sp, s)));

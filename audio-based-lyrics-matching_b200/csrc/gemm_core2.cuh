@@ -46,6 +46,11 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
   using CS = ColSlotTraits<Epi>;
   constexpr int kHalves = kEpiWarps / 4;
   constexpr int kColSlots = CS::kSlots;
+#ifdef WEALY_LATE_RELEASE
+  constexpr bool kEarlyRelease = false;  // (A/B builds: release the accumulator after the chunk has been scored)
+#else
+  constexpr bool kEarlyRelease = true;
+#endif
   static_assert(kEpiWarps == 8 || kEpiWarps == 12, "8 or 12 epilogue warps (2 or 3 per TMEM lane quadrant)");
   static_assert(kColSlots > 0 || !kDynChunks, "dynamic chunk claiming belongs to the symmetric evaluation epilogue");
 
@@ -331,11 +336,15 @@ gemm_pair_kernel(const __grid_constant__ GemmTmaps tmaps, const GemmShape shape,
           uint32_t v[32];
           ptx::tmem_ld_32x32(taddr + (uint32_t)(c * kChunkCols), v);
           ptx::tmem_ld_wait();
-          Epi::chunk32(ep, rs, row, (t0 + tile) * kTileN + c * kChunkCols, v, shape, ctx);
+          // the chunk now lives in registers: hand its part of the accumulator back BEFORE scoring it, so that a slow
+          // chunk (queue drain, dirty tile) never holds up the tensor pipe; only the column slot stays in use
           ptx::tc_fence_before_sync();
           __syncwarp();
+          if (kEarlyRelease && lane == 0) ptx::mbar_arrive_cluster_relaxed(leader_tmem_empty0 + 8u * a_cur);
+          Epi::chunk32(ep, rs, row, (t0 + tile) * kTileN + c * kChunkCols, v, shape, ctx);
+          __syncwarp();
           if (lane == 0) {
-            ptx::mbar_arrive_cluster_relaxed(leader_tmem_empty0 + 8u * a_cur);
+            if (!kEarlyRelease) ptx::mbar_arrive_cluster_relaxed(leader_tmem_empty0 + 8u * a_cur);
             ptx::mbar_arrive(&col_empty[c_cur]);
           }
         }

@@ -704,11 +704,13 @@ def run_gpu_arm(args):
     executed = 2.0 * 128 * 256 * DIM * tiles * passes / (last_sweep_ms * 1e-3) / 1e12
     peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
     variant = "pair" if os.environ.get("WEALY_SYM_PAIR", "1") != "0" else "single"
+    # (the capture must be of exactly this kernel: the pair kernel's template carries its number of dense threshold levels)
+    variant_key = f"pair_lv{os.environ.get('WEALY_SYM_LEVELS', '4')}" if variant == "pair" else "single"
     traffic, traffic_note = None, "no ncu capture of this exact configuration is committed"
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tpath) and world == 1 and not args.tracks:
         try:
-            rec = json.load(open(tpath)).get(f"{n_total}x{DIM}_{args.precision}_{variant}_1gpu")
+            rec = json.load(open(tpath)).get(f"{n_total}x{DIM}_{args.precision}_{variant_key}_1gpu")
             if rec:
                 traffic, traffic_note = rec["dram_bytes_per_launch"], f"dram__bytes_read.sum + dram__bytes_write.sum, {rec['source']}"
         except Exception:
