@@ -325,19 +325,20 @@ class EvalPipeline:
     buffers and grow the library's device pool to `depth` plans alive at once (tens to hundreds of ms each, once); after
     that a request costs what its upload / sweep cost (C2: 25 ms per request against 29.3 ms for evaluate())."""
 
-    def __init__(self, depth=2, device=None, precision=None, eps=1e-6, allow_empty=False):
+    def __init__(self, depth=2, device=None, precision=None, eps=1e-6, allow_empty=False, redux="min"):
         assert depth >= 2
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.depth, self.precision, self.eps, self.allow_empty = int(depth), precision, float(eps), bool(allow_empty)
+        self.redux = redux                                        # chunked tracks (z [N, s, D]): see EvalPlan.run
         self.copy_stream = side_stream(self.device)
         self.slots = [dict(z=None, c=None, i=None, aps=None, r1s=None, done=None, plan=None) for _ in range(self.depth)]
         self.count = 0
 
     def _buffers(self, slot, z, c, i):
-        n, d = z.shape
+        n = z.shape[0]
         if slot["z"] is None or slot["z"].shape != z.shape or slot["z"].dtype != z.dtype:
             with torch.cuda.stream(self.copy_stream):        # (allocated on the stream that fills them)
-                slot["z"] = torch.empty((n, d), dtype=z.dtype, device=self.device)
+                slot["z"] = torch.empty(tuple(z.shape), dtype=z.dtype, device=self.device)
                 slot["c"] = torch.empty(n, dtype=torch.long, device=self.device)
                 slot["i"] = torch.empty(n, dtype=torch.long, device=self.device)
             for t in (slot["z"], slot["c"], slot["i"]):
@@ -346,8 +347,11 @@ class EvalPipeline:
             slot["r1s"] = torch.empty(n, dtype=torch.float32).pin_memory()
 
     def submit(self, c, i, z):
-        """Enqueue one all-vs-all evaluation of host tensors (pin them for an asynchronous upload) -> ticket."""
+        """Enqueue one all-vs-all evaluation of host tensors (pin them for an asynchronous upload) -> ticket.
+        z: [N, D] embeddings, or [N, s, D] chunked tracks (reduced with the pipeline's `redux`)."""
         z, c, i = torch.as_tensor(z), torch.as_tensor(c).long(), torch.as_tensor(i).long()
+        assert z.ndim in (2, 3) and z.shape[0] == c.numel() == i.numel()
+        z = z.contiguous()
         if z.dtype == torch.float64:
             z = z.float()
         slot = self.slots[self.count % self.depth]
@@ -367,7 +371,8 @@ class EvalPipeline:
         with torch.cuda.device(self.device):
             plan = EvalPlan(slot["c"], slot["i"], slot["c"], slot["i"], device=self.device)
             try:
-                res = plan.run(slot["z"], slot["z"], eps=self.eps, precision=self.precision, allow_empty=self.allow_empty)
+                res = plan.run(slot["z"], slot["z"], eps=self.eps, precision=self.precision, allow_empty=self.allow_empty,
+                               redux=self.redux)
             except Exception:
                 plan.close()                                      # (e.g. queries without a relevant candidate: the slot stays free)
                 raise

@@ -695,6 +695,16 @@ def test_eval_pipeline_overlaps_requests_and_matches_evaluate():
     ae, re_ = we.evaluate(cb, ib, zb, cb, ib, zb, allow_empty=True)
     assert torch.allclose(a, ae.cpu(), rtol=0, atol=0, equal_nan=True) and torch.allclose(r, re_.cpu(), rtol=0, atol=0, equal_nan=True)
     lax.close()
+    # chunked tracks go through the same pipeline ([N, s, D] embeddings, the redux of the constructor)
+    g = torch.Generator().manual_seed(5)
+    zt = (sets[0]["z"][:, None, :] + 0.05 * torch.randn(1500, 4, 64, generator=g)).contiguous()
+    ct, it = sets[0]["c"].cuda(), sets[0]["i"].cuda()
+    ztc = zt.cuda()
+    at, rt = we.evaluate(ct, it, ztc, ct, it, ztc, redux="mean")
+    chunked = we.EvalPipeline(redux="mean")
+    a, r = chunked.result(chunked.submit(sets[0]["c"].pin_memory(), sets[0]["i"].pin_memory(), zt.pin_memory()))
+    assert torch.equal(a, at.cpu()) and torch.equal(r, rt.cpu())
+    chunked.close()
 
 
 def test_library_scratch_is_reused_and_returned(monkeypatch):  # noqa: C901
