@@ -725,8 +725,9 @@ def test_library_scratch_is_reused_and_returned(monkeypatch):  # noqa: C901
         torch.cuda.synchronize()
         stats.append(we.pool_stats())
     assert all(st["used"] == base for st in stats)                  # nothing is held once the plan is gone
-    assert all(st["reserved"] == stats[1]["reserved"] for st in stats[2:])
-    assert stats[-1]["reserved_high"] == stats[1]["reserved_high"]
+    # steady state after the second call (a few MB of slack: the driver's pool reserves in whole pages)
+    assert all(st["reserved"] <= stats[1]["reserved"] + (16 << 20) for st in stats[2:])
+    assert stats[-1]["reserved_high"] <= stats[1]["reserved_high"] + (16 << 20)
     a, r = we.evaluate(c, i, z, c, i, z)
     we.release_scratch()
     after = we.pool_stats()
