@@ -89,6 +89,67 @@ __global__ void __launch_bounds__(128) topk_beta_kernel(const float* __restrict_
   }
 }
 
+// k best of a list of n <= 32 * kPerLane entries, moved to its front (warp_select_topk's contract, epilogues.cuh); the
+// bisection over the order keys ends as soon as EXACTLY k entries lie at or above the prefix -- further bits could only
+// raise the threshold inside the gap below the k-th best, the selected set is already final (16-22 of the 32 steps on
+// similarity data).
+template <int kPerLane>
+__device__ __noinline__ void select_topk_exact(float* val, int* idx, int n, int k, int lane) {
+  constexpr unsigned kFull = 0xffffffffu;
+  __syncwarp();
+  unsigned key[kPerLane];
+  int id[kPerLane];
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const int e = j * 32 + lane;
+    const bool ok = e < n;
+    key[j] = ok ? float_order_key(val[e]) : 0u;  // 0 is below the key of every float
+    id[j] = ok ? idx[e] : -1;
+  }
+  unsigned T = 0;
+  for (int b = 31; b >= 0; --b) {
+    const unsigned cand = T | (1u << b);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kPerLane; ++j) c += key[j] >= cand;
+    c = __reduce_add_sync(kFull, c);
+    if (c >= k) T = cand;  // warp-uniform
+    if (c == k) break;
+  }
+  int g = 0, q = 0;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    g += key[j] > T;
+    q += key[j] == T;
+  }
+  int gi = g, qi = q;  // inclusive scans over lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int tg = __shfl_up_sync(kFull, gi, o);
+    const int tq = __shfl_up_sync(kFull, qi, o);
+    if (lane >= o) { gi += tg; qi += tq; }
+  }
+  const int G = __shfl_sync(kFull, gi, 31);
+  int pg = gi - g;          // first slot of this lane's "greater" entries
+  int pq = G + (qi - q);    // first slot of this lane's "equal" entries (kept while < k)
+  __syncwarp();             // every lane holds its entries in registers before anything is overwritten
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    if (key[j] > T) {
+      val[pg] = float_from_order_key(key[j]);
+      idx[pg] = id[j];
+      ++pg;
+    } else if (key[j] == T && key[j] != 0u) {
+      if (pq < k) {
+        val[pq] = float_from_order_key(key[j]);
+        idx[pq] = id[j];
+      }
+      ++pq;
+    }
+  }
+  __syncwarp();
+}
+
 // finalize: one warp per plane row (query).  Its list holds every candidate above beta (plane rows); select the k best,
 // order them (descending similarity, ties -> lower caller index, like a stable ascending-distance argsort) and write
 // them at the caller's row.  Lists that overflowed or hold fewer than k entries are reported in `fail`.
@@ -112,7 +173,14 @@ __global__ void __launch_bounds__(128) topk_sym_finalize_kernel(float* __restric
   int* si = tk_idx + (long long)p * cap;
   // plane row -> caller index first, so that ties are broken like the rectangle path does
   for (int e = lane; e < m; e += 32) si[e] = perm[spread_sorted_of(si[e])];
-  if (m > k) warp_select_topk<32>(sv, si, m, k, lane);
+  // (lists are sized mean + 8 sigma: most hold far fewer entries than `cap`, so the selection is instantiated for the
+  //  list's length, and its bisection stops at the first prefix that exactly k entries reach)
+  if (m > k) {
+    if (m <= 256) select_topk_exact<8>(sv, si, m, k, lane);
+    else if (m <= 512) select_topk_exact<16>(sv, si, m, k, lane);
+    else if (m <= 768) select_topk_exact<24>(sv, si, m, k, lane);
+    else select_topk_exact<32>(sv, si, m, k, lane);
+  }
   __syncwarp();
   for (int e = lane; e < k; e += 32) {
     const float ve = sv[e];
