@@ -1,5 +1,6 @@
 #!/bin/bash
 # round-2 GPU call 33: A/B of the early accumulator release in the pair kernel's dynamic-chunk epilogue
+# (the "late" library: nvcc ... -DWEALY_LATE_RELEASE -o audio-based-lyrics-matching_b200/lib/libwealy_b200_late.so audio-based-lyrics-matching_b200/csrc/api.cu, same flags as build.py; not kept)
 mkdir -p gpurun_out
 L=$PWD/audio-based-lyrics-matching_b200/lib
 run() {  # label, extra env, extra args
