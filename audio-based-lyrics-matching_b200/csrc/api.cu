@@ -154,6 +154,21 @@ static cudaError_t big_alloc(void** ptr, size_t* cap, size_t bytes, cudaStream_t
     }
   }
   cudaError_t e = dev_alloc(ptr, bytes, s);
+  if (e == cudaErrorMemoryAllocation) {
+    // out of memory with blocks parked: give them back to the pool (and the pool's idle pages to the driver), retry once
+    cudaGetLastError();
+    {
+      std::lock_guard<std::mutex> lock(g_big_mu);
+      for (size_t k = 0; k < g_big.size();) {
+        if (g_big[k].dev != dev) { ++k; continue; }
+        cudaFreeAsync(g_big[k].ptr, g_big[k].stream);
+        cudaEventDestroy(g_big[k].released);
+        g_big.erase(g_big.begin() + k);
+      }
+    }
+    cudaDeviceSynchronize();
+    e = dev_alloc(ptr, bytes, s);
+  }
   if (e == cudaSuccess) *cap = bytes;
   return e;
 }
