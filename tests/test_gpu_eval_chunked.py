@@ -200,3 +200,33 @@ def test_chunked_symmetric_sweep_equals_rectangle_sweep(redux, ragged, monkeypat
     else:
         assert abs(float(a1.double().mean()) - float(a0.double().mean())) <= 1e-6
         assert float((r1 != r0).float().mean()) <= 0.01
+
+
+def test_chunked_symmetric_sweep_id_collisions_and_singletons():
+    """Half sweep, both directions of a pair: a version-id collision between two tracks of DIFFERENT cliques removes the
+    pair for both of them (lib/losses.py:40-42: self is decided by the version id), and a track without any relevant
+    candidate (singleton clique, allow_empty) is still a candidate of every other query."""
+    from wealy_b200 import evaluation as we
+    n, s, d = 700, 4, 48
+    c, i, z = _chunked_set(n, s, d, seed=31)
+    c, i = c.clone(), i.clone()
+    a, b = 5, 400
+    assert c[a] != c[b]
+    i[b] = i[a]                                                    # collision across cliques, far apart in the sweep
+    c[650] = int(c.max()) + 1                                      # singleton clique
+    cq, iq, zq = c.cuda(), i.cuda(), z.cuda()
+    plan = we.EvalPlan(cq, iq, cq, iq)
+    with pytest.raises(ValueError):
+        plan.run(zq, zq, redux="min")
+    res = plan.run(zq, zq, redux="min", allow_empty=True)
+    torch.cuda.synchronize()
+    keep = ((c[:, None] == c[None, :]) & (i[:, None] != i[None, :])).any(dim=1)     # queries with a relevant candidate
+    assert not bool(keep[650])
+    off_g, ranks_g, sims_g = (t.cpu() for t in plan.ranks())
+    off_o, sims_o, exact, lo, hi = oev.rank_bands(c[keep], i[keep], z[keep], c, i, z, gap=1e-5, redux="min")
+    sel = torch.cat([torch.arange(int(off_g[q]), int(off_g[q + 1])) for q in torch.nonzero(keep).view(-1).tolist()])
+    r = ranks_g[sel].long()
+    assert r.numel() == exact.numel() == ranks_g.numel() and int(off_g[651] - off_g[650]) == 0
+    assert bool(((r >= lo) & (r <= hi)).all())
+    assert torch.equal(r[lo == hi], exact[lo == hi])
+    plan.close()
