@@ -1215,7 +1215,7 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     GroupMaxParams gp;
     gp.gmax = gmax;
     gp.n_groups = n_groups;
-    W_TRY(launch_gemm<GroupMaxEpi>(1, pa, pb, shp, gp, s));
+    W_TRY(launch_gemm<GroupMaxEpi>(1, pa, pb, shp, gp, s));  // (the CTA-pair core was measured no faster here: 1.385 vs 1.387 ms for K_pos + pre-pass)
     topk_beta_kernel<<<(unsigned)ceil_div(p->s_padded * 32, 128), 128, 0, s>>>(gmax, n_groups, rows, r + 1, n, tk_beta, p->s_lvl,
                                                                               (int)p->s_padded, tk_cnt);
     CU_TRY(cudaGetLastError());
