@@ -81,7 +81,12 @@ __global__ void __launch_bounds__(128) topk_beta_kernel(const float* __restrict_
       si[e] = e;
     }
     __syncwarp();
-    b = n_groups > m ? warp_select_topk<32>(sv, si, n_groups, m, lane) : __int_as_float(0xff800000);
+    // (instantiated for the number of groups: 128 at the minimum sample of 4096 rows -- 4 keys per lane, not 32)
+    if (n_groups <= m) b = __int_as_float(0xff800000);
+    else if (n_groups <= 128) b = warp_select_topk<4>(sv, si, n_groups, m, lane);
+    else if (n_groups <= 256) b = warp_select_topk<8>(sv, si, n_groups, m, lane);
+    else if (n_groups <= 512) b = warp_select_topk<16>(sv, si, n_groups, m, lane);
+    else b = warp_select_topk<32>(sv, si, n_groups, m, lane);
   }
   if (lane == 0) {
     if (p < n_rows) beta[p] = b;
