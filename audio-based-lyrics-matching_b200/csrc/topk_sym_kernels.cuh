@@ -176,8 +176,6 @@ __global__ void __launch_bounds__(128) topk_sym_finalize_kernel(float* __restric
   }
   float* sv = tk_val + (long long)p * cap;
   int* si = tk_idx + (long long)p * cap;
-  // plane row -> caller index first, so that ties are broken like the rectangle path does
-  for (int e = lane; e < m; e += 32) si[e] = perm[spread_sorted_of(si[e])];
   // (lists are sized mean + 8 sigma: most hold far fewer entries than `cap`, so the selection is instantiated for the
   //  list's length, and its bisection stops at the first prefix that exactly k entries reach)
   if (m > k) {
@@ -186,6 +184,10 @@ __global__ void __launch_bounds__(128) topk_sym_finalize_kernel(float* __restric
     else if (m <= 768) select_topk_exact<24>(sv, si, m, k, lane);
     else select_topk_exact<32>(sv, si, m, k, lane);
   }
+  __syncwarp();
+  // plane row -> caller index for the k survivors (the selection itself never looks at indices), so that equal
+  // similarities are ordered like the rectangle path orders them
+  for (int e = lane; e < k; e += 32) si[e] = perm[spread_sorted_of(si[e])];
   __syncwarp();
   for (int e = lane; e < k; e += 32) {
     const float ve = sv[e];
