@@ -1276,6 +1276,13 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
     // the pair kernel works on super row blocks (two adjacent row blocks per CTA pair)
     sh.n_row_blocks = (total_rb + 1) / 2;
     sh.group_rows = (sh.group_rows + 1) / 2;
+    // the plain (no top-k) sweep measured best with about half as many super row blocks per scheduling group as there
+    // are CTA pairs -- 37 instead of 19 on 148 SMs: 431-443 against 422-436 Gpairs/s at C2 on two boxes (56 .. 74 row
+    // blocks the same within the noise, 18 and 296 clearly worse)
+    if (!sym_topk && env_int("WEALY_GROUP_ROWS", 0) <= 0) {
+      sh.group_rows = std::max(1, num_sms() / 4);
+      if (sh.group_rows > sh.n_row_blocks) sh.group_rows = std::max(1, sh.n_row_blocks);
+    }
   }
   if (shard_world > 1) {
     const int total_owned = sh.n_row_blocks;
