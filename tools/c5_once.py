@@ -1,4 +1,4 @@
-"""BASELINE configs[4] once (50 000 x 2048, top-100): a few evaluations for `ncu` to attach to (tools/r02_run16.sh)."""
+"""BASELINE configs[4] once (50 000 x 2048, top-100): a few evaluations for `ncu` to attach to (tools/runs/r02_run16.sh)."""
 import os
 import sys
 
