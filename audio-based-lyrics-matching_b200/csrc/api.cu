@@ -454,7 +454,7 @@ static int launch_gemm_t(const Planes& a, const Planes& b, const GemmShape& sh, 
 // CTA-pair kernel (gemm_core2.cuh): sh.n_row_blocks / group_rows / rb_stride / rb_offset are in SUPER row blocks
 template <class Epi, int kPasses, int kBlockK, int kEpiWarps = 8, bool kDyn = false>
 static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename Epi::Params& ep, cudaStream_t s,
-                            const Planes* b_planes = nullptr) {
+                            const Planes* b_planes = nullptr, int max_pairs = 0) {
   constexpr int kStages = 4;
   const Planes& b = b_planes ? *b_planes : a;  // (the symmetric sweep contracts one set of planes with itself)
   const int il = (sh.sym & 2) ? 2 : 1;  // row stride of the A boxes
@@ -478,7 +478,8 @@ static int launch_gemm_pair(const Planes& a, const GemmShape& sh, const typename
   CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   const int n_units = sh.n_row_blocks * sh.n_col_chunks;
   if (n_units == 0) return WEALY_OK;
-  const int pairs = num_sms() / 2;
+  int pairs = num_sms() / 2;
+  if (max_pairs > 0 && max_pairs < pairs) pairs = max_pairs;  // (SMs left to another resident kernel)
   const int grid = 2 * (n_units < pairs ? n_units : pairs);
   GemmShape shl = sh;
   W_TRY(next_unit_counter(&shl.unit_counter, s));
@@ -767,6 +768,7 @@ struct wealy_eval_plan {
   int *seg_lo = nullptr, *seg_len = nullptr, *npos = nullptr;
   long long* off = nullptr;  // [nq + 1]
   int64_t total_pairs = 0, no_relevant = 0, max_relevant = 0;
+  int64_t max_clique = 0;  // longest run of one clique id among the candidates
   // scratch that depends on ids only
   float *raw = nullptr, *thr = nullptr, *lim = nullptr;
   int* cnt = nullptr;
@@ -795,6 +797,8 @@ struct wealy_eval_plan {
   bool timed = false;
   bool finished = false;  // the last run included ap_reduce (+ top-k finalize)
   bool last_sym = false;  // the last sweep ran in the clique-sorted view (its counters are in that CSR order)
+  // wealy_eval_run_host: [0] "planes allocated" on the run's stream, [1 + k] "rows of part k have arrived" on the upload stream
+  cudaEvent_t host_ev[1 + 8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
@@ -817,6 +821,8 @@ extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
   if (p->ev0) cudaEventDestroy(p->ev0);
   if (p->ev1) cudaEventDestroy(p->ev1);
   for (cudaEvent_t e : p->evs)
+    if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->host_ev)
     if (e) cudaEventDestroy(e);
   delete p;
 }
@@ -930,7 +936,7 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   }
 
   int bad_h[16];
-  unsigned long long totals_h[2];
+  unsigned long long totals_h[5];
   long long total = 0;
   CU_TRY(cudaMemcpyAsync(bad_h, bad, sizeof(int), cudaMemcpyDeviceToHost, s));
   CU_TRY(cudaMemcpyAsync(totals_h, totals, sizeof(totals_h), cudaMemcpyDeviceToHost, s));
@@ -940,6 +946,7 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   p->total_pairs = total;
   p->no_relevant = (int64_t)totals_h[0];
   p->max_relevant = (int64_t)totals_h[1];
+  p->max_clique = (int64_t)totals_h[4];
   const size_t pairs = (size_t)(total > 0 ? total : 1);
   CU_TRY(dev_alloc((void**)&p->raw, pairs * 4, s));
   if (p->same_ids) {
@@ -1444,6 +1451,246 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
                               float* r1s, double* sums, int64_t* topk_idx, float* topk_sim, void* stream) {
   return eval_run_impl(p, queries_z, ld_q, candidates_z, ld_c, d, dtype, eps, passes, topk, aps, r1s, sums, topk_idx,
                        topk_sim, 0, 1, true, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// All-vs-all evaluation of embeddings that still live in PINNED HOST memory: upload, normalisation and the symmetric
+// sweep as one pipeline.  The sweep runs in the plan's clique-sorted row order and a super row block only needs the
+// rows BEHIND it (tiles above the diagonal), so the rows are fetched from the end: part by part a small persistent
+// kernel (prep_rows_stream_kernel, on its own stream, resident next to the sweep's CTAs) reads the caller's rows over
+// PCIe in sorted order -- a gather no copy engine can do --, and as soon as a part has arrived its relevant
+// similarities (K_pos) and its row blocks of the sweep run on the caller's stream while the next part is in flight.
+// Parts grow towards the front: the work of a part grows with the square of the rows behind it.
+// ------------------------------------------------------------------------------------------
+static cudaStream_t upload_stream() {
+  static cudaStream_t streams[64] = {nullptr};
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) streams[dev] = nullptr;
+  return streams[dev];
+}
+
+template <int kLevels, int kPasses, int kBlockK>
+static int launch_sym_part(const Planes& pq, const GemmShape& sh, const EvalSymParams& sp, cudaStream_t s, int max_pairs) {
+  return launch_gemm_pair<EvalSymEpi<kLevels>, kPasses, kBlockK, 12, true>(pq, sh, sp, s, nullptr, max_pairs);
+}
+
+extern "C" int wealy_eval_run_host(wealy_eval_plan* p, const void* host_z, int64_t ld, int64_t d, int dtype, float eps,
+                                   int passes, float* aps, float* r1s, double* sums, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!p || !host_z || !aps || !r1s || !sums) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (passes != 1 && passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
+  if (dtype != WEALY_F32 && dtype != WEALY_F16 && dtype != WEALY_BF16) return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
+  const int64_t n = p->nq;
+  if (!(p->same_ids && p->nq == p->nc && p->total_pairs < (1ll << 31) - 8))
+    return fail(WEALY_ERR_UNSUPPORTED, "wealy_eval_run_host evaluates all-vs-all plans (queries == candidates)");
+  if (d <= 0 || d > 128 * kRowVecs || d % 4 != 0 || ld % 4 != 0 || ld < d)
+    return fail(WEALY_ERR_UNSUPPORTED, "wealy_eval_run_host needs rows of 4 k <= %d elements (d=%lld, ld=%lld)", 128 * kRowVecs,
+                (long long)d, (long long)ld);
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host_z) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(WEALY_ERR_UNSUPPORTED, "cannot classify the embeddings' pointer");
+  }
+  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)  // already on the device: the plain run
+    return eval_run_impl(p, host_z, ld, host_z, ld, d, dtype, eps, passes, 0, aps, r1s, sums, nullptr, nullptr, 0, 1, true, stream);
+  if (attr.type != cudaMemoryTypeHost || !attr.devicePointer)
+    return fail(WEALY_ERR_UNSUPPORTED, "host embeddings must be pinned (page-locked and mapped) to be read by the device");
+  const void* z = attr.devicePointer;
+  if ((reinterpret_cast<uintptr_t>(z) & 15) != 0) return fail(WEALY_ERR_UNSUPPORTED, "host embeddings must be 16-byte aligned");
+  cudaStream_t up = upload_stream();
+  if (!up) return fail(WEALY_ERR_CUDA, "no upload stream");
+  // The upload kernel uses no shared memory, and an SM whose L1 / shared-memory split was chosen for such a kernel cannot
+  // take a CTA of the sweep (225 KB) until it has drained: ask for the largest shared-memory carve-out, so that a sweep
+  // CTA fits next to an upload CTA whichever of the two arrived first.  (Per device, like the sweep's own attribute.)
+  // The upload kernel runs on U SMs of its own (WEALY_HOST_UP_SMS, default 8): CTAs of 512 threads whose shared-memory
+  // request keeps the sweep off their SM, while the parts of the sweep that can overlap with the upload run on the
+  // remaining SMs.  Measured at 100 000 x 1024 (profiles/r02_host_pipeline.md): 8 SMs already saturate PCIe (51 GB/s);
+  // upload CTAs NEXT to the sweep's CTAs (U = 0: two warps per SM, which fit beside a resident sweep CTA) slowed the
+  // sweep and K_pos 2-3x while rows were in flight -- the SM's memory pipeline queues behind the microsecond-long
+  // host reads --, and K_pos also slows down with the number of SMs that read host memory (U = 4: none, U = 16: 4x).
+  const int up_sms = std::min(std::max(env_int("WEALY_HOST_UP_SMS", 8), 0), num_sms() / 2);
+  const size_t up_smem = up_sms > 0 ? 120 * 1024 : 0;
+  const void* up_kernel =
+      up_sms > 0 ? (dtype == WEALY_F32 ? (const void*)prep_rows_stream_kernel<float, 512>
+                    : dtype == WEALY_F16 ? (const void*)prep_rows_stream_kernel<__half, 512>
+                                         : (const void*)prep_rows_stream_kernel<__nv_bfloat16, 512>)
+                 : (dtype == WEALY_F32 ? (const void*)prep_rows_stream_kernel<float, 64>
+                    : dtype == WEALY_F16 ? (const void*)prep_rows_stream_kernel<__half, 64>
+                                         : (const void*)prep_rows_stream_kernel<__nv_bfloat16, 64>);
+  CU_TRY(cudaFuncSetAttribute(up_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (up_smem) CU_TRY(cudaFuncSetAttribute(up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)up_smem));
+  // ... and the same for the K_pos kernels that run between the parts of the sweep: an upload CTA that joined an SM while
+  // a small-shared-memory kernel had it configured would pin that configuration for the rest of its part and keep the
+  // sweep off the SM.  (The attribute is read at launch: it is put back to the default behind the launches.)
+  const void* kpos_kernels[2] = {(const void*)pos_pairs_sorted_kernel<false>, (const void*)pos_sort_sorted_kernel};
+  struct RestoreCarveout {
+    const void* const* k;
+    bool on;
+    ~RestoreCarveout() {
+      for (int i = 0; on && i < 2; ++i) cudaFuncSetAttribute(k[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
+    }
+  } restore{kpos_kernels, up_sms == 0};
+  if (up_sms == 0)  // (upload CTAs on SMs of their own never share an SM with these kernels)
+    for (const void* k : kpos_kernels)
+      CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+
+  // operand planes in the sweep's spread order over whole 128-row blocks
+  const int64_t rows_q = ceil_div(n, kTileM) * kTileM;
+  const size_t need = planes_bytes(rows_q, d, passes) + 2048;
+  if (need > p->planes_cap) {
+    big_free(p->planes_buf, p->planes_cap, s);
+    p->planes_buf = nullptr;
+    p->planes_cap = 0;
+    CU_TRY(big_alloc((void**)&p->planes_buf, &p->planes_cap, need, s));
+  }
+  uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)p->planes_buf, 1024));
+  Planes pq;
+  carve_planes(pq, cur, rows_q, d, passes);
+  if (!p->ev0) {
+    CU_TRY(cudaEventCreate(&p->ev0));
+    CU_TRY(cudaEventCreate(&p->ev1));
+    for (cudaEvent_t& e : p->evs) CU_TRY(cudaEventCreate(&e));
+  }
+  for (cudaEvent_t& e : p->host_ev)
+    if (!e) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+  // parts, in super row blocks (256 rows) counted from the END: cumulative fractions of the rows
+  static const float kCum[4][8] = {{1.f}, {0.30f, 1.f}, {0.10f, 0.20f, 0.35f, 0.55f, 1.f}, {0.06f, 0.14f, 0.24f, 0.36f, 0.5f, 0.7f, 1.f}};
+  static const int kCount[4] = {1, 2, 5, 7};
+  const int nsb = (int)ceil_div(n, 2 * kTileM);
+  int preset = nsb >= 96 ? 2 : (nsb >= 24 ? 1 : 0);  // (24 k / 6 k rows)
+  const int forced = env_int("WEALY_HOST_PARTS", 0);
+  if (forced > 0) preset = forced >= 7 ? 3 : (forced >= 5 ? 2 : (forced >= 2 ? 1 : 0));
+  const int n_parts = kCount[preset];
+  const int64_t reach = p->max_clique > 1 ? p->max_clique : 1;  // K_pos of a query reads the rows of its whole clique
+
+  GemmShape sh0;
+  fill_shape(sh0, n, n, pq.d_pad, 64, 1 << 20, env_int("WEALY_TILES_PER_UNIT", 8));
+  const int total_rb = sh0.n_row_blocks;
+  sh0.sym = 1 | (env_int("WEALY_PAIR_INTERLEAVE", 1) != 0 ? 2 : 0);
+  if (passes == 3) sh0.k_blocks = (int)(pq.d_pad / 32);
+  EvalSymParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.lvl = p->s_lvl;
+  sp.cinfo = p->s_cinfo;
+  sp.s_c = p->sorted_c;
+  sp.s_i = p->s_i;
+  sp.thr = p->thr;
+  sp.hist = p->hist;
+  sp.dirty = p->s_dirty;
+  sp.n_col_tiles = sh0.n_col_tiles;
+  sp.n_row_blocks = total_rb;
+  sp.total_pairs = (unsigned)p->total_pairs;
+
+  CU_TRY(cudaEventRecord(p->evs[0], s));
+  CU_TRY(cudaEventRecord(p->evs[1], s));
+  CU_TRY(cudaMemsetAsync(p->hist, 0, (size_t)(p->total_pairs > 0 ? p->total_pairs : 1) * 4, s));
+  CU_TRY(cudaMemsetAsync(p->cnt, 0, (size_t)n * 4, s));
+  CU_TRY(cudaMemsetAsync(sums, 0, 3 * sizeof(double), s));
+  CU_TRY(cudaEventRecord(p->host_ev[0], s));           // the upload may touch the planes from here on
+  CU_TRY(cudaStreamWaitEvent(up, p->host_ev[0], 0));
+  CU_TRY(cudaEventRecord(p->ev0, s));
+
+  const int up_grid = up_sms > 0 ? up_sms : num_sms() * std::max(1, env_int("WEALY_HOST_UP_GRID", 1));
+  const int up_threads = up_sms > 0 ? 512 : (env_int("WEALY_HOST_UP_THREADS", 64) <= 32 ? 32 : 64);
+  // WEALY_HOST_TRACE=1 (diagnostics): time stamps of every part on both streams, printed to stderr after a synchronize
+  const bool trace = env_int("WEALY_HOST_TRACE", 0) != 0;
+  std::vector<cudaEvent_t> tev;
+  auto stamp = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tev.push_back(e);
+  };
+  stamp(s);
+  int sb_hi = nsb;
+  int64_t prep_hi = rows_q;
+  for (int k = 0; k < n_parts; ++k) {
+    int sb_lo = k + 1 == n_parts ? 0 : nsb - (int)lroundf(kCum[preset][k] * (float)nsb);
+    if (sb_lo > sb_hi) sb_lo = sb_hi;
+    // ---- upload stream: the rows this part's sweep AND its K_pos need (its cliques may start `reach` rows earlier)
+    int64_t prep_lo = k + 1 == n_parts ? 0 : ((int64_t)sb_lo * 2 * kTileM - reach) / kTileM * kTileM;
+    if (prep_lo < 0) prep_lo = 0;
+    if (prep_lo > prep_hi) prep_lo = prep_hi;
+    stamp(up);
+    if (prep_hi > prep_lo) {
+#define STREAM_ARGS (long long)ld, (int)prep_lo, (int)prep_hi, (int)d, (int)pq.d_pad, eps, pq.hi, pq.lo, pq.norm, pq.scale, pq.sq, \
+                    p->sorted_idx, (int)n
+#define STREAM_LAUNCH(T)                                                                                              \
+  do {                                                                                                                \
+    if (up_sms > 0) prep_rows_stream_kernel<T, 512><<<up_grid, up_threads, up_smem, up>>>((const T*)z, STREAM_ARGS);   \
+    else prep_rows_stream_kernel<T, 64><<<up_grid, up_threads, 0, up>>>((const T*)z, STREAM_ARGS);                     \
+  } while (0)
+      switch (dtype) {
+        case WEALY_F32: STREAM_LAUNCH(float); break;
+        case WEALY_F16: STREAM_LAUNCH(__half); break;
+        default: STREAM_LAUNCH(__nv_bfloat16); break;
+      }
+#undef STREAM_LAUNCH
+#undef STREAM_ARGS
+      CU_TRY(cudaGetLastError());
+    }
+    if (trace) fprintf(stderr, "[wealy host run] part %d: rows [%lld, %lld) arrive, super row blocks [%d, %d) swept\n", k,
+                       (long long)prep_lo, (long long)prep_hi, sb_lo, sb_hi);
+    prep_hi = prep_lo;
+    stamp(up);
+    CU_TRY(cudaEventRecord(p->host_ev[1 + k], up));
+    CU_TRY(cudaStreamWaitEvent(s, p->host_ev[1 + k], 0));
+    stamp(s);
+    // ---- caller's stream: K_pos of the part's queries, then its row blocks of the sweep
+    const int q_lo = sb_lo * 2 * kTileM;
+    const int q_hi = (int)std::min<int64_t>((int64_t)sb_hi * 2 * kTileM, n);
+    if (q_hi > q_lo) {
+      const int threads = 256;
+      pos_pairs_sorted_kernel<false><<<(unsigned)ceil_div(q_hi - q_lo, 16), threads, 0, s>>>(
+          pq.hi, pq.lo, (int)pq.d_pad, p->sorted_c, p->s_i, (int)n, p->s_seg_lo, p->s_seg_len, p->s_off, p->raw, p->cnt, nullptr,
+          q_lo, q_hi);
+      const int64_t sort_end = k == 0 ? p->s_padded : q_hi;  // (the first part reaches n: it owns the padding rows)
+      pos_sort_sorted_kernel<<<(unsigned)ceil_div((sort_end - q_lo) * 32, threads), threads, 0, s>>>(
+          p->s_npos, (int)n, (int)p->s_padded, p->s_off, p->raw, p->thr, p->cnt, p->s_lvl, p->s_cinfo, q_lo, q_hi, 1);
+      CU_TRY(cudaGetLastError());
+      stamp(s);
+      GemmShape sh = sh0;
+      sh.n_row_blocks = sb_hi - sb_lo;
+      sh.rb_offset = sb_lo;
+      sh.rb_stride = 1;
+      sh.group_rows = std::max(1, std::min(num_sms() / 4, sh.n_row_blocks));
+      const int max_pairs = (up_sms > 0 && k + 1 < n_parts) ? (num_sms() - up_sms) / 2 : 0;
+      if (passes == 3) W_TRY((launch_sym_part<4, 3, 32>(pq, sh, sp, s, max_pairs)));
+      else W_TRY((launch_sym_part<3, 1, 64>(pq, sh, sp, s, max_pairs)));
+    }
+    else stamp(s);
+    stamp(s);
+    sb_hi = sb_lo;
+  }
+  CU_TRY(cudaEventRecord(p->ev1, s));
+  if (trace) {
+    cudaStreamSynchronize(s);
+    cudaStreamSynchronize(up);
+    // per part: {upload begin, upload end} on the upload stream, {wait over, K_pos done, sweep done} on the run's stream
+    for (int k = 0; k < n_parts && (size_t)(1 + 5 * k + 4) < tev.size(); ++k) {
+      float t[5];
+      for (int j = 0; j < 5; ++j) cudaEventElapsedTime(&t[j], tev[0], tev[1 + 5 * k + j]);
+      fprintf(stderr, "[wealy host run] part %d: upload %.3f -> %.3f ms | ready %.3f, K_pos done %.3f, sweep done %.3f ms\n", k, t[0],
+              t[1], t[2], t[3], t[4]);
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+  }
+  p->timed = true;
+  p->finished = true;
+  p->last_sym = true;
+  p->last_stream = s;
+  p->last_topk_path = 0;
+  ap_reduce_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, s>>>(p->hist, p->s_off, p->cnt, (int)n, aps, r1s, sums, p->sorted_idx);
+  CU_TRY(cudaGetLastError());
+  CU_TRY(cudaEventRecord(p->evs[2], s));
+  CU_TRY(cudaEventRecord(p->evs[3], s));
+  return WEALY_OK;
 }
 
 extern "C" int wealy_eval_run_chunked(wealy_eval_plan* p, const void* queries_z, int64_t ld_q, const void* candidates_z,

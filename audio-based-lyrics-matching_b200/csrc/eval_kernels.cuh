@@ -39,7 +39,7 @@ __global__ void segment_lookup_kernel(const int* __restrict__ q_c, const int* __
                                       const int* __restrict__ sorted_c, const int* __restrict__ sorted_idx,
                                       const int* __restrict__ c_i, int nc, int* __restrict__ seg_lo,
                                       int* __restrict__ seg_len, int* __restrict__ npos,
-                                      unsigned long long* __restrict__ totals /*[0]=queries w/o positives,[1]=max P*/) {
+                                      unsigned long long* __restrict__ totals /*[0]=queries w/o positives,[1]=max P,[4]=max len*/) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nq) return;
   const int key = q_c[q];
@@ -63,6 +63,7 @@ __global__ void segment_lookup_kernel(const int* __restrict__ q_c, const int* __
   npos[q] = np;
   if (np == 0) atomicAdd(&totals[0], 1ull);
   atomicMax(&totals[1], (unsigned long long)np);
+  atomicMax(&totals[4], (unsigned long long)len);  // [4] = longest clique run
 }
 
 // K_pos.  One warp per query.  Similarities are computed from the SAME fp16 planes the tensor-core
@@ -420,10 +421,15 @@ __global__ void __launch_bounds__(256) pos_sort_sorted_kernel(const int* __restr
                                                               const long long* __restrict__ off,
                                                               const float* __restrict__ raw, float* __restrict__ thr,
                                                               int* __restrict__ cnt, float4* __restrict__ lvl,
-                                                              uint2* __restrict__ cinfo, int q_lo = 0, int q_hi = 0x7fffffff) {
-  const int q = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+                                                              uint2* __restrict__ cinfo, int q_lo = 0, int q_hi = 0x7fffffff,
+                                                              int partial = 0) {
+  // partial (wealy_eval_run_host: the queries arrive range by range): the grid covers [q_lo, n_padded) and touches
+  // nothing outside [q_lo, q_hi) -- the other ranges are written by their own launches; the padding rows belong to the
+  // range that reaches n
+  const int q = (partial ? q_lo : 0) + (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
   const int lane = (int)(threadIdx.x & 31);
   if (q >= n_padded) return;
+  if (partial && (q < n ? q >= q_hi : q_hi < n)) return;
   const float inf = __int_as_float(0x7f800000);
   const int pq = spread_plane_of(q);  // lvl / cinfo are read by plane row (per-tile bulk copies of the sweep)
   if (q < n && (q < q_lo || q >= q_hi)) {

@@ -213,4 +213,81 @@ __global__ void __launch_bounds__(256) prep_rows_kernel(const T* __restrict__ x,
   }
 }
 
+// K0 for embeddings that still live in PINNED HOST memory (wealy_eval_run_host): the same arithmetic as
+// prep_rows_kernel (identical summation order, IEEE division -> bit-identical planes), but every input row is read
+// exactly ONCE -- it crosses PCIe -- and kept in registers between the norm and the split.  A small persistent grid
+// (one CTA of two warps per SM, rows dealt warp by warp) that fits NEXT TO a resident CTA of the evaluation sweep
+// (<= 64 registers per thread, no shared memory): the upload of the next rows runs while the tensor cores sweep the
+// rows that have arrived.  Plane rows [row_lo, row_hi), whole 128-row blocks of the spread order; d <= 128 kRowVecs.
+constexpr int kRowVecs = 8;  // float4 per lane: rows of up to 1024 elements
+template <typename T, int kThreads>
+__global__ void __launch_bounds__(kThreads) prep_rows_stream_kernel(const T* __restrict__ x, long long ld, int row_lo, int row_hi,
+                                                              int d, int d_pad, float eps, __half* __restrict__ hi,
+                                                              __half* __restrict__ lo, float* __restrict__ norm_out,
+                                                              float* __restrict__ scale_out, float* __restrict__ sq_out,
+                                                              const int* __restrict__ gather, int spread_n) {
+  const int lane = (int)(threadIdx.x & 31);
+  const int n_warps = (int)(gridDim.x * (blockDim.x >> 5));
+  for (int r = row_lo + (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)); r < row_hi; r += n_warps) {
+    const int src = (r & ~127) + (((r & 127) & 31) << 2) + ((r & 127) >> 5);  // sorted row of plane row r
+    __half* hrow = hi + (long long)r * d_pad;
+    __half* lrow = lo ? lo + (long long)r * d_pad : nullptr;
+    if (src >= spread_n) {  // padding up to the whole block: zero rows
+      for (int k = lane * 4; k < d_pad; k += 128) {
+        *reinterpret_cast<uint2*>(hrow + k) = make_uint2(0u, 0u);
+        if (lrow) *reinterpret_cast<uint2*>(lrow + k) = make_uint2(0u, 0u);
+      }
+      if (lane == 0) {
+        if (norm_out) norm_out[r] = 0.f;
+        if (scale_out) scale_out[r] = 1.f;
+        if (sq_out) sq_out[r] = 0.f;
+      }
+      continue;
+    }
+    const T* row = x + (long long)__ldg(gather + src) * ld;
+    float4 v[kRowVecs];
+#pragma unroll
+    for (int i = 0; i < kRowVecs; ++i) {  // all of the row's loads in flight together
+      const int k = lane * 4 + i * 128;
+      v[i] = k < d ? load4<T>(row + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRowVecs; ++i) {
+      if (lane * 4 + i * 128 < d) {
+        ss = fmaf(v[i].x, v[i].x, ss); ss = fmaf(v[i].y, v[i].y, ss); ss = fmaf(v[i].z, v[i].z, ss); ss = fmaf(v[i].w, v[i].w, ss);
+      }
+    }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    const float div = nrm + eps;
+#pragma unroll
+    for (int i = 0; i < kRowVecs; ++i) {
+      const int k = lane * 4 + i * 128;
+      if (k < d_pad) {
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < d) q = make_float4(v[i].x / div, v[i].y / div, v[i].z / div, v[i].w / div);  // IEEE division, as torch does
+        const __half2 h0 = __floats2half2_rn(q.x, q.y), h1 = __floats2half2_rn(q.z, q.w);
+        uint2 oh;
+        oh.x = *reinterpret_cast<const unsigned*>(&h0);
+        oh.y = *reinterpret_cast<const unsigned*>(&h1);
+        *reinterpret_cast<uint2*>(hrow + k) = oh;
+        if (lrow) {
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+          const __half2 l0 = __floats2half2_rn(q.x - f0.x, q.y - f0.y), l1 = __floats2half2_rn(q.z - f1.x, q.w - f1.y);
+          uint2 ol;
+          ol.x = *reinterpret_cast<const unsigned*>(&l0);
+          ol.y = *reinterpret_cast<const unsigned*>(&l1);
+          *reinterpret_cast<uint2*>(lrow + k) = ol;
+        }
+      }
+    }
+    if (lane == 0) {
+      if (norm_out) norm_out[r] = nrm;
+      if (scale_out) scale_out[r] = 1.f;
+      if (sq_out) sq_out[r] = ss;
+    }
+  }
+}
+
 }  // namespace wealy

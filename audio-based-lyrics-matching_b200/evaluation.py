@@ -170,6 +170,28 @@ class EvalPlan:
         N.check(N.lib.wealy_eval_plan_stage_ms(self._handle, ms))
         return dict(zip(("prep", "kpos", "sweep", "ap_reduce", "topk_finalize"), (float(v) for v in ms)))
 
+    def run_host(self, z, *, eps=1e-6, precision=None, allow_empty=False):
+        """All-vs-all evaluation of PINNED HOST embeddings `z[N, D]` -> dict(aps, r1s, sums) on the device: the device
+        reads the rows itself, in the plan's sorted order and from the end, while the symmetric sweep already runs over
+        what has arrived (wealy_eval_run_host) -- no separate upload.  Raises NotImplementedError where that pipeline
+        does not apply (then upload and call run()); `z` must stay alive until the current stream has drained (the plan
+        keeps a reference until its next run)."""
+        if self.queries_without_relevant and not allow_empty:
+            raise ValueError(f"{self.queries_without_relevant} queries have no relevant candidate "
+                             "(every clique needs >= 2 versions; pass allow_empty=True to score the rest)")
+        assert z.ndim == 2 and z.shape[0] == self.nq == self.nc
+        if z.stride(1) != 1:
+            raise NotImplementedError("run_host needs contiguous rows")
+        aps = torch.empty(self.nq, dtype=torch.float32, device=self.device)
+        r1s = torch.empty(self.nq, dtype=torch.float32, device=self.device)
+        sums = torch.empty(3, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.wealy_eval_run_host(
+                self._handle, z.data_ptr(), z.stride(0), z.shape[1], N.dtype_code(z.dtype), float(eps),
+                passes_of(precision), aps.data_ptr(), r1s.data_ptr(), sums.data_ptr(), N.stream_ptr(self.device)))
+        self._keepalive = z
+        return {"aps": aps, "r1s": r1s, "sums": sums}
+
     def run(self, queries_z, candidates_z, *, topk=None, eps=1e-6, precision=None, allow_empty=False, chunks=None,
             redux="min", q_chunks=None, c_chunks=None):
         """-> dict(aps, r1s, sums[, topk_idx, topk_sim]); `sums` = device doubles {sum AP, sum R1, #scored}.
@@ -260,18 +282,31 @@ def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candid
     if mode not in ("cos", "cossim"):
         raise NotImplementedError("wealy_b200.evaluate ranks by cosine distance (mode='cos')")
     own = plan is None
+    # all-vs-all over pinned host embeddings: upload, normalisation and sweep run as one pipeline (EvalPlan.run_host)
+    host = (topk is None and chunks is None and q_chunks is None and c_chunks is None
+            and _host_streamable(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z))
     if own:
-        # host embeddings: start their upload on a side stream FIRST, so that the copy engine moves them while the id
-        # plan is built (a handful of small kernels and two host read-backs on the current stream)
-        queries_z, candidates_z, side = _prefetch_to_device(queries_z, candidates_z)
+        side = None
+        if not host:
+            # host embeddings: start their upload on a side stream FIRST, so that the copy engine moves them while the id
+            # plan is built (a handful of small kernels and two host read-backs on the current stream)
+            queries_z, candidates_z, side = _prefetch_to_device(queries_z, candidates_z)
         plan = EvalPlan(queries_c, queries_i, candidates_c, candidates_i)
         if side is not None:
             torch.cuda.current_stream(plan.device).wait_stream(side)
             for t in {id(queries_z): queries_z, id(candidates_z): candidates_z}.values():
                 t.record_stream(torch.cuda.current_stream(plan.device))
     try:
-        res = plan.run(queries_z, candidates_z, topk=topk, eps=eps, precision=precision, allow_empty=allow_empty,
-                       chunks=chunks, redux=redux, q_chunks=q_chunks, c_chunks=c_chunks)
+        res = None
+        if host:
+            try:
+                res = plan.run_host(queries_z, eps=eps, precision=precision, allow_empty=allow_empty)
+            except NotImplementedError:     # (e.g. equal shapes but different ids on the two sides): upload and run
+                res = None
+        _last_path[0] = "host_stream" if res is not None else "device"
+        if res is None:
+            res = plan.run(queries_z, candidates_z, topk=topk, eps=eps, precision=precision, allow_empty=allow_empty,
+                           chunks=chunks, redux=redux, q_chunks=q_chunks, c_chunks=c_chunks)
     finally:
         if own:
             torch.cuda.current_stream(plan.device).synchronize()
@@ -279,6 +314,32 @@ def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candid
     if topk is None:
         return res["aps"], res["r1s"]
     return res["aps"], res["r1s"], res["topk_idx"], res["topk_sim"]
+
+
+def _host_streamable(queries_c, queries_i, queries_z, candidates_c, candidates_i, candidates_z):
+    """True when evaluate() hands the embeddings to wealy_eval_run_host: one pinned host matrix on both sides, rows of
+    4 k <= 1024 contiguous elements, and enough of them for the pipeline to pay (below ~24 k rows the sweep is shorter
+    than the upload and the copy engine, which overlaps with the id plan, is the faster way in).
+    WEALY_HOST_STREAM=0 keeps the copy-then-compute path, WEALY_HOST_STREAM_MIN_ROWS moves the threshold."""
+    import os
+    z = queries_z
+    if os.environ.get("WEALY_HOST_STREAM", "1") == "0" or not isinstance(z, torch.Tensor):
+        return False
+    if not (z is candidates_z and queries_c is candidates_c and queries_i is candidates_i):
+        return False
+    if z.ndim != 2 or z.shape[0] < int(os.environ.get("WEALY_HOST_STREAM_MIN_ROWS", "24576")):
+        return False
+    return (not z.is_cuda and z.is_pinned() and z.ndim == 2 and z.dtype in (torch.float32, torch.float16, torch.bfloat16)
+            and z.stride(1) == 1 and z.stride(0) % 4 == 0 and z.shape[1] % 4 == 0 and 0 < z.shape[1] <= 1024
+            and z.data_ptr() % 16 == 0)
+
+
+_last_path = ["device"]
+
+
+def last_path():
+    """Which route the last evaluate() of this process took: "host_stream" (wealy_eval_run_host) or "device"."""
+    return _last_path[0]
 
 
 _side_streams = {}

@@ -630,6 +630,20 @@ def run_gpu_arm(args):
     # same public API is reported next to it at N = 1 (`e2e.pipelined`)
     e2e_ms, e2e_api = single_ms, ("wealy_b200.evaluation.evaluate" if world == 1 else "wealy_b200.dist.evaluate_all_vs_all") + \
         " (host pinned tensors in, host out; one synchronous call per step: upload, id plan, evaluation, read-back)"
+    e2e_route, copy_ms = None, None
+    if world == 1:
+        # which way the embeddings went in: "host_stream" = wealy_eval_run_host (the device reads the pinned rows itself, in
+        # sorted order, while the sweep runs over the rows that have arrived; the same bytes cross PCIe inside the call);
+        # the copy-then-compute route (copy engine, then the resident path) is timed beside it
+        e2e_route = we.last_path()
+        if e2e_route == "host_stream":
+            os.environ["WEALY_HOST_STREAM"] = "0"
+            try:
+                step_e2e()
+                copy_ms = timed_e2e(lambda: [step_e2e() for _ in range(e2e_steps)]) / e2e_steps
+            finally:
+                del os.environ["WEALY_HOST_STREAM"]
+            step_e2e()     # (leave the host buffers holding the default route's output)
     if world == 1:
         # the serving form: requests submitted back to back, the upload of request k + 1 on the copy engine while the
         # sweep of request k runs.  Every request still uploads its ids and embeddings, builds its id plan, evaluates and
@@ -751,7 +765,10 @@ def run_gpu_arm(args):
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_ms, "api": e2e_api,
+                "ms_per_step": e2e_ms, "api": e2e_api, "route": e2e_route,
+                "copy_then_compute": None if copy_ms is None else {
+                    "ms_per_step": copy_ms, "value": pairs_total / (copy_ms * 1e-3) / 1e9, "unit": UNIT,
+                    "note": "the same call with WEALY_HOST_STREAM=0: cudaMemcpyAsync of the embeddings on a side stream, then the resident path"},
                 "pipelined": pipelined},
         "gpu_launches": 5 * args.steps,   # prep, pos_pairs, pos_sort, fused sweep, ap_reduce per step
         "roofline": roofline,

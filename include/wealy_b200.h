@@ -124,6 +124,20 @@ int wealy_eval_plan_info(const wealy_eval_plan* plan, int64_t* total_pairs, int6
 int wealy_eval_run(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, const void* candidates_z, int64_t ld_c,
                    int64_t d, int dtype, float eps, int passes, int topk, float* aps, float* r1s, double* sums,
                    int64_t* topk_idx, float* topk_sim, void* stream);
+/* The all-vs-all case (plan built with queries == candidates, no top-k) for embeddings that are still in PINNED HOST
+ * memory: host_z [n, d] (row stride ld; d = 4 k <= 1024, 16-byte aligned) is read by the device itself -- a small
+ * persistent kernel on a few SMs of its own gathers the caller's rows over PCIe in the plan's clique-sorted order, from
+ * the last rows backwards -- while the symmetric sweep already runs over the rows that have arrived: upload,
+ * normalisation and sweep as one pipeline instead of copy-then-compute (the caller of the reference would `.cuda()` the
+ * embeddings first: lib/losses.py:45 / lib/tensor_ops.py:167-173 take device tensors).  Results are bit-identical to
+ * wealy_eval_run on a device copy of host_z.  Work is enqueued on `stream` and on an internal upload stream ordered
+ * with it; host_z must stay valid until `stream` has drained.  A device pointer is accepted and takes the plain path;
+ * WEALY_ERR_UNSUPPORTED for pageable memory, other shapes or plans (callers then upload and use wealy_eval_run).
+ * Environment: WEALY_HOST_UP_SMS (SMs of the upload kernel, default 8; 0 = next to the sweep's CTAs),
+ * WEALY_HOST_PARTS (1 / 2 / 5 / 7 parts instead of the size-based choice), WEALY_HOST_TRACE=1 (per-part time stamps
+ * on stderr; synchronises).                                                                                    */
+int wealy_eval_run_host(wealy_eval_plan* plan, const void* host_z, int64_t ld, int64_t d, int dtype, float eps, int passes,
+                        float* aps, float* r1s, double* sums, void* stream);
 
 /* f1: evaluation of CHUNKED tracks -- every track has `chunks` (1, 2, 4, 8 or 16) embeddings,
  * queries_z [nq * chunks, d] / candidates_z [nc * chunks, d] (the chunks of a track are consecutive rows), the plan's ids
