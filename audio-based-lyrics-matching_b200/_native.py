@@ -52,6 +52,8 @@ SIGNATURES = {
     "wealy_eval_plan_info": (c_int, [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "wealy_eval_run": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_int, c_vp, c_vp, c_vp,
                                c_vp, c_vp, c_vp]),
+    "wealy_eval_plan_create_host": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_vp,
+                                            ctypes.POINTER(c_vp)]),
     "wealy_eval_run_host": (c_int, [c_vp, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_vp, c_vp, c_vp, c_vp]),
     "wealy_eval_run_chunked": (c_int, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i64, c_int, c_f32, c_int, c_int, c_int, c_int, c_vp,
                                        c_vp, c_vp, c_vp, c_vp, c_vp]),

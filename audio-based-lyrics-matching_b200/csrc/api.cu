@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <vector>
 
@@ -799,10 +800,22 @@ struct wealy_eval_plan {
   bool last_sym = false;  // the last sweep ran in the clique-sorted view (its counters are in that CSR order)
   // wealy_eval_run_host: [0] "planes allocated" on the run's stream, [1 + k] "rows of part k have arrived" on the upload stream
   cudaEvent_t host_ev[1 + 8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // wealy_eval_plan_create_host: plane rows [early_lo, end) of this matrix are already in flight on the upload stream
+  // (issued while the rest of the plan was being built); -1 = none / consumed by the run
+  int64_t early_lo = -1, early_ld = 0, early_d = 0;
+  const void* early_z = nullptr;
+  int early_dtype = 0, early_passes = 0;
+  float early_eps = 0.f;
 };
+
+static cudaStream_t upload_stream();
 
 extern "C" void wealy_eval_plan_destroy(wealy_eval_plan* p) {
   if (!p) return;
+  if (p->early_lo >= 0) {  // (a plan created with an early upload and never run: the upload still writes the planes)
+    cudaStream_t up = upload_stream();
+    if (up) cudaStreamSynchronize(up);
+  }
   void* ptrs[] = {p->q_c, p->q_i, p->sorted_c, p->sorted_idx, p->seg_lo, p->seg_len, p->npos, p->off,
                   p->raw, p->lvl_thr_buf ? nullptr : (void*)p->thr, p->lim, p->cnt, p->hist,
                   p->s_i, p->s_seg_lo, p->s_seg_len, p->s_npos, p->s_off, p->lvl_thr_buf ? p->lvl_thr_buf : (void*)p->s_lvl,
@@ -835,7 +848,8 @@ struct WidenI32 {
 using WideCounts = cub::TransformInputIterator<long long, WidenI32, const int*>;
 
 static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_t* queries_i,
-                      const int64_t* candidates_c, const int64_t* candidates_i, cudaStream_t s) {
+                      const int64_t* candidates_c, const int64_t* candidates_i, cudaStream_t s,
+                      const std::function<int()>& after_sort = nullptr) {
   const int nq = (int)p->nq, nc = (int)p->nc;
   const int T = 256;
   TempAllocs tmps(s);
@@ -880,6 +894,9 @@ static int plan_build(wealy_eval_plan* p, const int64_t* queries_c, const int64_
   void* tmp = nullptr;
   CU_TRY(tmps.alloc((void**)&tmp, tmp_bytes + 16));
   CU_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, p->c_c, p->sorted_c, iota, p->sorted_idx, nc, 0, 32, s));
+  // (wealy_eval_plan_create_host: the sorted order is all the upload of the first rows needs -- it starts here, under
+  // the rest of the plan)
+  if (after_sort && p->same_ids) W_TRY(after_sort());
 
   CU_TRY(dev_alloc((void**)&p->seg_lo, (size_t)nq * 4 + 4, s));
   CU_TRY(dev_alloc((void**)&p->seg_len, (size_t)nq * 4 + 4, s));
@@ -1039,6 +1056,16 @@ static int eval_run_impl(wealy_eval_plan* p, const void* queries_z, int64_t ld_q
   // on the planes and thresholds stage 1 left in the plan
   cudaStream_t s = (cudaStream_t)stream;
   if (!p) return fail(WEALY_ERR_BAD_ARG, "null plan");
+  if (p->early_lo >= 0) {
+    // a plan created by wealy_eval_plan_create_host that is run on device embeddings after all: its early upload may
+    // still be writing the planes this run is about to fill -- order the run behind it
+    cudaStream_t up = upload_stream();
+    if (up && p->host_ev[1]) {
+      CU_TRY(cudaEventRecord(p->host_ev[1], up));
+      CU_TRY(cudaStreamWaitEvent(s, p->host_ev[1], 0));
+    }
+    p->early_lo = -1;
+  }
   if (stage != 2 && (!queries_z || !candidates_z)) return fail(WEALY_ERR_BAD_ARG, "null pointer");
   if (stage == 2) {
     if (!p->planes_buf || !p->lvl_thr_buf) return fail(WEALY_ERR_BAD_ARG, "wealy_eval_shard_sweep needs wealy_eval_shard_prepare first");
@@ -1478,68 +1505,90 @@ static int launch_sym_part(const Planes& pq, const GemmShape& sh, const EvalSymP
   return launch_gemm_pair<EvalSymEpi<kLevels>, kPasses, kBlockK, 12, true>(pq, sh, sp, s, nullptr, max_pairs);
 }
 
-extern "C" int wealy_eval_run_host(wealy_eval_plan* p, const void* host_z, int64_t ld, int64_t d, int dtype, float eps,
-                                   int passes, float* aps, float* r1s, double* sums, void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  if (!p || !host_z || !aps || !r1s || !sums) return fail(WEALY_ERR_BAD_ARG, "null pointer");
-  if (passes != 1 && passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
+// The upload kernel and where it runs.  By default on U = 8 SMs of its own (WEALY_HOST_UP_SMS): CTAs of 512 threads whose
+// shared-memory request keeps the sweep off their SM, while the parts of the sweep that can overlap with the upload run
+// on the remaining SMs.  Measured at 100 000 x 1024 (profiles/r02_host_pipeline.md): 8 SMs already saturate PCIe
+// (51 GB/s).  U = 0 puts two upload warps per SM NEXT to the sweep's CTAs (they fit beside a resident sweep CTA; the
+// largest shared-memory carve-out is requested for them and for the K_pos kernels between the parts, because an SM whose
+// L1 / shared-memory split was chosen for a kernel without shared memory cannot take a sweep CTA until it has drained):
+// that slowed the sweep and K_pos 2-3x while rows were in flight -- the SM's memory pipeline queues behind the
+// microsecond-long host reads.  K_pos also slows down with the number of SMs that read host memory (U = 4: not at all,
+// U = 16: 4x).
+struct HostUpload {
+  const void* z = nullptr;  // device-side address of the pinned host matrix
+  int64_t ld = 0, d = 0;
+  int dtype = 0;
+  float eps = 0.f;
+  int up_sms = 0, grid = 0, threads = 0;
+  size_t smem = 0;
+  cudaStream_t up = nullptr;
+};
+
+// status: WEALY_OK, or why the device cannot read these embeddings (*on_device: a device pointer, take the plain path)
+static int host_upload_setup(HostUpload& h, const void* host_z, int64_t ld, int64_t d, int dtype, float eps, bool* on_device) {
+  *on_device = false;
   if (dtype != WEALY_F32 && dtype != WEALY_F16 && dtype != WEALY_BF16) return fail(WEALY_ERR_BAD_ARG, "unknown element type %d", dtype);
-  const int64_t n = p->nq;
-  if (!(p->same_ids && p->nq == p->nc && p->total_pairs < (1ll << 31) - 8))
-    return fail(WEALY_ERR_UNSUPPORTED, "wealy_eval_run_host evaluates all-vs-all plans (queries == candidates)");
-  if (d <= 0 || d > 128 * kRowVecs || d % 4 != 0 || ld % 4 != 0 || ld < d)
-    return fail(WEALY_ERR_UNSUPPORTED, "wealy_eval_run_host needs rows of 4 k <= %d elements (d=%lld, ld=%lld)", 128 * kRowVecs,
-                (long long)d, (long long)ld);
   cudaPointerAttributes attr;
   if (cudaPointerGetAttributes(&attr, host_z) != cudaSuccess) {
     cudaGetLastError();
     return fail(WEALY_ERR_UNSUPPORTED, "cannot classify the embeddings' pointer");
   }
-  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)  // already on the device: the plain run
-    return eval_run_impl(p, host_z, ld, host_z, ld, d, dtype, eps, passes, 0, aps, r1s, sums, nullptr, nullptr, 0, 1, true, stream);
+  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
+    *on_device = true;
+    return WEALY_OK;
+  }
+  if (d <= 0 || d > 128 * kRowVecs || d % 4 != 0 || ld % 4 != 0 || ld < d)
+    return fail(WEALY_ERR_UNSUPPORTED, "wealy_eval_run_host needs rows of 4 k <= %d elements (d=%lld, ld=%lld)", 128 * kRowVecs,
+                (long long)d, (long long)ld);
   if (attr.type != cudaMemoryTypeHost || !attr.devicePointer)
     return fail(WEALY_ERR_UNSUPPORTED, "host embeddings must be pinned (page-locked and mapped) to be read by the device");
-  const void* z = attr.devicePointer;
-  if ((reinterpret_cast<uintptr_t>(z) & 15) != 0) return fail(WEALY_ERR_UNSUPPORTED, "host embeddings must be 16-byte aligned");
-  cudaStream_t up = upload_stream();
-  if (!up) return fail(WEALY_ERR_CUDA, "no upload stream");
-  // The upload kernel uses no shared memory, and an SM whose L1 / shared-memory split was chosen for such a kernel cannot
-  // take a CTA of the sweep (225 KB) until it has drained: ask for the largest shared-memory carve-out, so that a sweep
-  // CTA fits next to an upload CTA whichever of the two arrived first.  (Per device, like the sweep's own attribute.)
-  // The upload kernel runs on U SMs of its own (WEALY_HOST_UP_SMS, default 8): CTAs of 512 threads whose shared-memory
-  // request keeps the sweep off their SM, while the parts of the sweep that can overlap with the upload run on the
-  // remaining SMs.  Measured at 100 000 x 1024 (profiles/r02_host_pipeline.md): 8 SMs already saturate PCIe (51 GB/s);
-  // upload CTAs NEXT to the sweep's CTAs (U = 0: two warps per SM, which fit beside a resident sweep CTA) slowed the
-  // sweep and K_pos 2-3x while rows were in flight -- the SM's memory pipeline queues behind the microsecond-long
-  // host reads --, and K_pos also slows down with the number of SMs that read host memory (U = 4: none, U = 16: 4x).
-  const int up_sms = std::min(std::max(env_int("WEALY_HOST_UP_SMS", 8), 0), num_sms() / 2);
-  const size_t up_smem = up_sms > 0 ? 120 * 1024 : 0;
+  h.z = attr.devicePointer;
+  if ((reinterpret_cast<uintptr_t>(h.z) & 15) != 0) return fail(WEALY_ERR_UNSUPPORTED, "host embeddings must be 16-byte aligned");
+  h.ld = ld;
+  h.d = d;
+  h.dtype = dtype;
+  h.eps = eps;
+  h.up = upload_stream();
+  if (!h.up) return fail(WEALY_ERR_CUDA, "no upload stream");
+  h.up_sms = std::min(std::max(env_int("WEALY_HOST_UP_SMS", 8), 0), num_sms() / 2);
+  h.smem = h.up_sms > 0 ? 120 * 1024 : 0;
+  h.grid = h.up_sms > 0 ? h.up_sms : num_sms() * std::max(1, env_int("WEALY_HOST_UP_GRID", 1));
+  h.threads = h.up_sms > 0 ? 512 : (env_int("WEALY_HOST_UP_THREADS", 64) <= 32 ? 32 : 64);
   const void* up_kernel =
-      up_sms > 0 ? (dtype == WEALY_F32 ? (const void*)prep_rows_stream_kernel<float, 512>
-                    : dtype == WEALY_F16 ? (const void*)prep_rows_stream_kernel<__half, 512>
-                                         : (const void*)prep_rows_stream_kernel<__nv_bfloat16, 512>)
-                 : (dtype == WEALY_F32 ? (const void*)prep_rows_stream_kernel<float, 64>
-                    : dtype == WEALY_F16 ? (const void*)prep_rows_stream_kernel<__half, 64>
-                                         : (const void*)prep_rows_stream_kernel<__nv_bfloat16, 64>);
+      h.up_sms > 0 ? (dtype == WEALY_F32 ? (const void*)prep_rows_stream_kernel<float, 512>
+                      : dtype == WEALY_F16 ? (const void*)prep_rows_stream_kernel<__half, 512>
+                                           : (const void*)prep_rows_stream_kernel<__nv_bfloat16, 512>)
+                   : (dtype == WEALY_F32 ? (const void*)prep_rows_stream_kernel<float, 64>
+                      : dtype == WEALY_F16 ? (const void*)prep_rows_stream_kernel<__half, 64>
+                                           : (const void*)prep_rows_stream_kernel<__nv_bfloat16, 64>);
   CU_TRY(cudaFuncSetAttribute(up_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  if (up_smem) CU_TRY(cudaFuncSetAttribute(up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)up_smem));
-  // ... and the same for the K_pos kernels that run between the parts of the sweep: an upload CTA that joined an SM while
-  // a small-shared-memory kernel had it configured would pin that configuration for the rest of its part and keep the
-  // sweep off the SM.  (The attribute is read at launch: it is put back to the default behind the launches.)
-  const void* kpos_kernels[2] = {(const void*)pos_pairs_sorted_kernel<false>, (const void*)pos_sort_sorted_kernel};
-  struct RestoreCarveout {
-    const void* const* k;
-    bool on;
-    ~RestoreCarveout() {
-      for (int i = 0; on && i < 2; ++i) cudaFuncSetAttribute(k[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
-    }
-  } restore{kpos_kernels, up_sms == 0};
-  if (up_sms == 0)  // (upload CTAs on SMs of their own never share an SM with these kernels)
-    for (const void* k : kpos_kernels)
-      CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (h.smem) CU_TRY(cudaFuncSetAttribute(up_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h.smem));
+  return WEALY_OK;
+}
 
-  // operand planes in the sweep's spread order over whole 128-row blocks
-  const int64_t rows_q = ceil_div(n, kTileM) * kTileM;
+// plane rows [lo, hi) (whole 128-row blocks of the spread order) <- the caller's rows, on the upload stream
+static int host_upload_rows(const HostUpload& h, const Planes& pq, const int* sorted_idx, int64_t n, int64_t lo, int64_t hi) {
+  if (hi <= lo) return WEALY_OK;
+#define STREAM_ARGS (long long)h.ld, (int)lo, (int)hi, (int)h.d, (int)pq.d_pad, h.eps, pq.hi, pq.lo, pq.norm, pq.scale, pq.sq, sorted_idx, (int)n
+#define STREAM_LAUNCH(T)                                                                                                     \
+  do {                                                                                                                       \
+    if (h.up_sms > 0) prep_rows_stream_kernel<T, 512><<<h.grid, h.threads, h.smem, h.up>>>((const T*)h.z, STREAM_ARGS);       \
+    else prep_rows_stream_kernel<T, 64><<<h.grid, h.threads, 0, h.up>>>((const T*)h.z, STREAM_ARGS);                          \
+  } while (0)
+  switch (h.dtype) {
+    case WEALY_F32: STREAM_LAUNCH(float); break;
+    case WEALY_F16: STREAM_LAUNCH(__half); break;
+    default: STREAM_LAUNCH(__nv_bfloat16); break;
+  }
+#undef STREAM_LAUNCH
+#undef STREAM_ARGS
+  CU_TRY(cudaGetLastError());
+  return WEALY_OK;
+}
+
+// operand planes of an all-vs-all plan in the sweep's spread order over whole 128-row blocks, and the events of a host run
+static int host_planes(wealy_eval_plan* p, int64_t d, int passes, cudaStream_t s, Planes& pq) {
+  const int64_t rows_q = ceil_div(p->nq, kTileM) * kTileM;
   const size_t need = planes_bytes(rows_q, d, passes) + 2048;
   if (need > p->planes_cap) {
     big_free(p->planes_buf, p->planes_cap, s);
@@ -1548,7 +1597,6 @@ extern "C" int wealy_eval_run_host(wealy_eval_plan* p, const void* host_z, int64
     CU_TRY(big_alloc((void**)&p->planes_buf, &p->planes_cap, need, s));
   }
   uint8_t* cur = reinterpret_cast<uint8_t*>(align_up((size_t)p->planes_buf, 1024));
-  Planes pq;
   carve_planes(pq, cur, rows_q, d, passes);
   if (!p->ev0) {
     CU_TRY(cudaEventCreate(&p->ev0));
@@ -1557,15 +1605,113 @@ extern "C" int wealy_eval_run_host(wealy_eval_plan* p, const void* host_z, int64
   }
   for (cudaEvent_t& e : p->host_ev)
     if (!e) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return WEALY_OK;
+}
 
-  // parts, in super row blocks (256 rows) counted from the END: cumulative fractions of the rows
-  static const float kCum[4][8] = {{1.f}, {0.30f, 1.f}, {0.10f, 0.20f, 0.35f, 0.55f, 1.f}, {0.06f, 0.14f, 0.24f, 0.36f, 0.5f, 0.7f, 1.f}};
-  static const int kCount[4] = {1, 2, 5, 7};
+// parts of a host run, in super row blocks (256 rows) counted from the END: cumulative fractions of the rows
+static const float kHostCum[4][8] = {{1.f}, {0.30f, 1.f}, {0.10f, 0.20f, 0.35f, 0.55f, 1.f}, {0.06f, 0.14f, 0.24f, 0.36f, 0.5f, 0.7f, 1.f}};
+static const int kHostCount[4] = {1, 2, 5, 7};
+static int host_preset(int64_t n) {
   const int nsb = (int)ceil_div(n, 2 * kTileM);
   int preset = nsb >= 96 ? 2 : (nsb >= 24 ? 1 : 0);  // (24 k / 6 k rows)
   const int forced = env_int("WEALY_HOST_PARTS", 0);
   if (forced > 0) preset = forced >= 7 ? 3 : (forced >= 5 ? 2 : (forced >= 2 ? 1 : 0));
-  const int n_parts = kCount[preset];
+  return preset;
+}
+// first super row block of part k
+static int host_part_begin(int64_t n, int preset, int k) {
+  const int nsb = (int)ceil_div(n, 2 * kTileM);
+  if (k + 1 >= kHostCount[preset]) return 0;
+  const int sb = nsb - (int)lroundf(kHostCum[preset][k] * (float)nsb);
+  return sb < 0 ? 0 : sb;
+}
+
+// As wealy_eval_plan_create for an all-vs-all evaluation of pinned host embeddings (to be run with wealy_eval_run_host on
+// the same matrix): the upload of the first part starts as soon as the sorted order exists, under the rest of the plan.
+extern "C" int wealy_eval_plan_create_host(const int64_t* queries_c, const int64_t* queries_i, int64_t nq,
+                                           const int64_t* candidates_c, const int64_t* candidates_i, int64_t nc,
+                                           const void* host_z, int64_t ld, int64_t d, int dtype, float eps, int passes,
+                                           void* stream, wealy_eval_plan** plan) {
+  if (!plan) return fail(WEALY_ERR_BAD_ARG, "plan output pointer is null");
+  *plan = nullptr;
+  if (nq <= 0 || nc <= 0) return fail(WEALY_ERR_BAD_ARG, "empty query or candidate set (nq=%lld nc=%lld)", (long long)nq, (long long)nc);
+  if (!queries_c || !queries_i || !candidates_c || !candidates_i) return fail(WEALY_ERR_BAD_ARG, "null id pointer");
+  if (nq >= (1ll << 31) - 256 || nc >= (1ll << 31) - 256) return fail(WEALY_ERR_UNSUPPORTED, "more than 2^31 rows");
+  cudaStream_t s = (cudaStream_t)stream;
+  wealy_eval_plan* p = new wealy_eval_plan();
+  p->nq = nq;
+  p->nc = nc;
+  p->stream = s;
+  auto early = [&]() -> int {
+    HostUpload h;
+    bool on_device = false;
+    if (!host_z || (passes != 1 && passes != 3) || env_int("WEALY_HOST_EARLY", 1) == 0) return WEALY_OK;
+    if (host_upload_setup(h, host_z, ld, d, dtype, eps, &on_device) != WEALY_OK || on_device) return WEALY_OK;  // nothing to start early
+    Planes pq;
+    W_TRY(host_planes(p, d, passes, s, pq));
+    const int64_t lo = (int64_t)host_part_begin(nq, host_preset(nq), 0) * 2 * kTileM;
+    CU_TRY(cudaEventRecord(p->host_ev[0], s));
+    CU_TRY(cudaStreamWaitEvent(h.up, p->host_ev[0], 0));
+    W_TRY(host_upload_rows(h, pq, p->sorted_idx, nq, lo, pq.rows));
+    p->early_lo = lo;
+    p->early_z = h.z;
+    p->early_ld = ld;
+    p->early_d = d;
+    p->early_dtype = dtype;
+    p->early_passes = passes;
+    p->early_eps = eps;
+    return WEALY_OK;
+  };
+  int st = plan_build(p, queries_c, queries_i, candidates_c, candidates_i, s, early);
+  if (st != WEALY_OK) {
+    wealy_eval_plan_destroy(p);
+    return st;
+  }
+  *plan = p;
+  return WEALY_OK;
+}
+
+extern "C" int wealy_eval_run_host(wealy_eval_plan* p, const void* host_z, int64_t ld, int64_t d, int dtype, float eps,
+                                   int passes, float* aps, float* r1s, double* sums, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!p || !host_z || !aps || !r1s || !sums) return fail(WEALY_ERR_BAD_ARG, "null pointer");
+  if (passes != 1 && passes != 3) return fail(WEALY_ERR_BAD_ARG, "passes must be 1 or 3");
+  const int64_t n = p->nq;
+  if (!(p->same_ids && p->nq == p->nc && p->total_pairs < (1ll << 31) - 8))
+    return fail(WEALY_ERR_UNSUPPORTED, "wealy_eval_run_host evaluates all-vs-all plans (queries == candidates)");
+  HostUpload h;
+  bool on_device = false;
+  W_TRY(host_upload_setup(h, host_z, ld, d, dtype, eps, &on_device));
+  if (on_device)  // already on the device: the plain run
+    return eval_run_impl(p, host_z, ld, host_z, ld, d, dtype, eps, passes, 0, aps, r1s, sums, nullptr, nullptr, 0, 1, true, stream);
+  const void* z = h.z;
+  cudaStream_t up = h.up;
+  const int up_sms = h.up_sms;
+  const void* kpos_kernels[2] = {(const void*)pos_pairs_sorted_kernel<false>, (const void*)pos_sort_sorted_kernel};
+  struct RestoreCarveout {
+    const void* const* k;
+    bool on;
+    ~RestoreCarveout() {
+      for (int i = 0; on && i < 2; ++i) cudaFuncSetAttribute(k[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutDefault);
+    }
+  } restore{kpos_kernels, up_sms == 0};
+  if (up_sms == 0)  // (upload CTAs on SMs of their own never share an SM with these kernels; the attribute is read at launch)
+    for (const void* k : kpos_kernels)
+      CU_TRY(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+
+  Planes pq;
+  W_TRY(host_planes(p, d, passes, s, pq));
+  const int64_t rows_q = pq.rows;
+  // rows an early upload (wealy_eval_plan_create_host) of exactly this matrix has already put in flight
+  int64_t early_lo = -1;
+  if (p->early_lo >= 0 && p->early_z == z && p->early_ld == ld && p->early_d == d && p->early_dtype == dtype &&
+      p->early_passes == passes && p->early_eps == eps)
+    early_lo = p->early_lo;
+  p->early_lo = -1;
+
+  const int nsb = (int)ceil_div(n, 2 * kTileM);
+  const int preset = host_preset(n);
+  const int n_parts = kHostCount[preset];
   const int64_t reach = p->max_clique > 1 ? p->max_clique : 1;  // K_pos of a query reads the rows of its whole clique
 
   GemmShape sh0;
@@ -1595,8 +1741,6 @@ extern "C" int wealy_eval_run_host(wealy_eval_plan* p, const void* host_z, int64
   CU_TRY(cudaStreamWaitEvent(up, p->host_ev[0], 0));
   CU_TRY(cudaEventRecord(p->ev0, s));
 
-  const int up_grid = up_sms > 0 ? up_sms : num_sms() * std::max(1, env_int("WEALY_HOST_UP_GRID", 1));
-  const int up_threads = up_sms > 0 ? 512 : (env_int("WEALY_HOST_UP_THREADS", 64) <= 32 ? 32 : 64);
   // WEALY_HOST_TRACE=1 (diagnostics): time stamps of every part on both streams, printed to stderr after a synchronize
   const bool trace = env_int("WEALY_HOST_TRACE", 0) != 0;
   std::vector<cudaEvent_t> tev;
@@ -1611,30 +1755,15 @@ extern "C" int wealy_eval_run_host(wealy_eval_plan* p, const void* host_z, int64
   int sb_hi = nsb;
   int64_t prep_hi = rows_q;
   for (int k = 0; k < n_parts; ++k) {
-    int sb_lo = k + 1 == n_parts ? 0 : nsb - (int)lroundf(kCum[preset][k] * (float)nsb);
+    int sb_lo = host_part_begin(n, preset, k);
     if (sb_lo > sb_hi) sb_lo = sb_hi;
     // ---- upload stream: the rows this part's sweep AND its K_pos need (its cliques may start `reach` rows earlier)
     int64_t prep_lo = k + 1 == n_parts ? 0 : ((int64_t)sb_lo * 2 * kTileM - reach) / kTileM * kTileM;
     if (prep_lo < 0) prep_lo = 0;
     if (prep_lo > prep_hi) prep_lo = prep_hi;
     stamp(up);
-    if (prep_hi > prep_lo) {
-#define STREAM_ARGS (long long)ld, (int)prep_lo, (int)prep_hi, (int)d, (int)pq.d_pad, eps, pq.hi, pq.lo, pq.norm, pq.scale, pq.sq, \
-                    p->sorted_idx, (int)n
-#define STREAM_LAUNCH(T)                                                                                              \
-  do {                                                                                                                \
-    if (up_sms > 0) prep_rows_stream_kernel<T, 512><<<up_grid, up_threads, up_smem, up>>>((const T*)z, STREAM_ARGS);   \
-    else prep_rows_stream_kernel<T, 64><<<up_grid, up_threads, 0, up>>>((const T*)z, STREAM_ARGS);                     \
-  } while (0)
-      switch (dtype) {
-        case WEALY_F32: STREAM_LAUNCH(float); break;
-        case WEALY_F16: STREAM_LAUNCH(__half); break;
-        default: STREAM_LAUNCH(__nv_bfloat16); break;
-      }
-#undef STREAM_LAUNCH
-#undef STREAM_ARGS
-      CU_TRY(cudaGetLastError());
-    }
+    // (what an early upload already has in flight is not fetched again)
+    W_TRY(host_upload_rows(h, pq, p->sorted_idx, n, prep_lo, early_lo >= 0 ? std::min(prep_hi, early_lo) : prep_hi));
     if (trace) fprintf(stderr, "[wealy host run] part %d: rows [%lld, %lld) arrive, super row blocks [%d, %d) swept\n", k,
                        (long long)prep_lo, (long long)prep_hi, sb_lo, sb_hi);
     prep_hi = prep_lo;

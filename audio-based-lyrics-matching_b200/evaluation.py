@@ -35,7 +35,9 @@ class EvalPlan:
     """Everything that depends on ids only (clique-sorted candidate order, per-query relevant
     segments, CSR offsets) -- build once per (queries, candidates) id set, run for any embeddings."""
 
-    def __init__(self, queries_c, queries_i, candidates_c, candidates_i, device=None):
+    def __init__(self, queries_c, queries_i, candidates_c, candidates_i, device=None, host_z=None, eps=1e-6, precision=None):
+        """host_z (optional): the pinned host embeddings run_host() will be called with (same eps / precision) -- their
+        upload then starts inside the plan build, as soon as the sorted order exists (wealy_eval_plan_create_host)."""
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.device = torch.device(device)
@@ -51,9 +53,16 @@ class EvalPlan:
         self.nq, self.nc = self.q_c.numel(), self.c_c.numel()
         self._handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
-            N.check(N.lib.wealy_eval_plan_create(
-                self.q_c.data_ptr(), self.q_i.data_ptr(), self.nq, self.c_c.data_ptr(), self.c_i.data_ptr(), self.nc,
-                N.stream_ptr(self.device), ctypes.byref(self._handle)))
+            if host_z is not None and host_z.ndim == 2 and host_z.stride(1) == 1:
+                N.check(N.lib.wealy_eval_plan_create_host(
+                    self.q_c.data_ptr(), self.q_i.data_ptr(), self.nq, self.c_c.data_ptr(), self.c_i.data_ptr(), self.nc,
+                    host_z.data_ptr(), host_z.stride(0), host_z.shape[1], N.dtype_code(host_z.dtype), float(eps),
+                    passes_of(precision), N.stream_ptr(self.device), ctypes.byref(self._handle)))
+                self._keepalive = host_z
+            else:
+                N.check(N.lib.wealy_eval_plan_create(
+                    self.q_c.data_ptr(), self.q_i.data_ptr(), self.nq, self.c_c.data_ptr(), self.c_i.data_ptr(), self.nc,
+                    N.stream_ptr(self.device), ctypes.byref(self._handle)))
         tp, nr, mr = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
         N.check(N.lib.wealy_eval_plan_info(self._handle, ctypes.byref(tp), ctypes.byref(nr), ctypes.byref(mr)))
         self.total_pairs, self.queries_without_relevant, self.max_relevant = tp.value, nr.value, mr.value
@@ -291,7 +300,8 @@ def evaluate(queries_c, queries_i, queries_z, candidates_c, candidates_i, candid
             # host embeddings: start their upload on a side stream FIRST, so that the copy engine moves them while the id
             # plan is built (a handful of small kernels and two host read-backs on the current stream)
             queries_z, candidates_z, side = _prefetch_to_device(queries_z, candidates_z)
-        plan = EvalPlan(queries_c, queries_i, candidates_c, candidates_i)
+        plan = EvalPlan(queries_c, queries_i, candidates_c, candidates_i, host_z=queries_z if host else None, eps=eps,
+                        precision=precision)
         if side is not None:
             torch.cuda.current_stream(plan.device).wait_stream(side)
             for t in {id(queries_z): queries_z, id(candidates_z): candidates_z}.values():

@@ -138,6 +138,15 @@ int wealy_eval_run(wealy_eval_plan* plan, const void* queries_z, int64_t ld_q, c
  * on stderr; synchronises).                                                                                    */
 int wealy_eval_run_host(wealy_eval_plan* plan, const void* host_z, int64_t ld, int64_t d, int dtype, float eps, int passes,
                         float* aps, float* r1s, double* sums, void* stream);
+/* wealy_eval_plan_create for a plan that wealy_eval_run_host will run on host_z (same ld / d / dtype / eps / passes): the
+ * upload of the first rows starts as soon as the clique-sorted order exists and proceeds under the rest of the plan
+ * build (CSR offsets, collision maps, host read-backs) instead of behind it.  Anything wealy_eval_run_host would refuse
+ * (pageable memory, other shapes, queries != candidates) simply creates the plan without the early upload; a run on
+ * other embeddings ignores it.                                                                                  */
+int wealy_eval_plan_create_host(const int64_t* queries_c, const int64_t* queries_i, int64_t nq,
+                                const int64_t* candidates_c, const int64_t* candidates_i, int64_t nc, const void* host_z,
+                                int64_t ld, int64_t d, int dtype, float eps, int passes, void* stream,
+                                wealy_eval_plan** plan);
 
 /* f1: evaluation of CHUNKED tracks -- every track has `chunks` (1, 2, 4, 8 or 16) embeddings,
  * queries_z [nq * chunks, d] / candidates_z [nc * chunks, d] (the chunks of a track are consecutive rows), the plan's ids

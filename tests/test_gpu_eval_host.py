@@ -156,3 +156,32 @@ def test_default_threshold_keeps_small_sets_on_the_copy_engine():
     zp = s["z"].pin_memory()
     we.evaluate(s["c"], s["i"], zp, s["c"], s["i"], zp)
     assert we.last_path() == "device"
+
+
+@pytest.mark.parametrize("n,parts", [(3000, 1), (7000, 2), (6000, 5)])
+def test_early_upload_inside_the_plan_build(n, parts, monkeypatch):
+    # wealy_eval_plan_create_host starts the upload of the first part under the plan build; the run fetches the rest
+    monkeypatch.setenv("WEALY_HOST_PARTS", str(parts))
+    we = _we()
+    s = _synth().make_eval_set(n, 128, seed=n)
+    cd, idd, zd = s["c"].cuda(), s["i"].cuda(), s["z"].cuda()
+    zp = s["z"].pin_memory()
+    ref_plan = we.EvalPlan(cd, idd, cd, idd)
+    ref = ref_plan.run(zd, zd)
+    plan = we.EvalPlan(cd, idd, cd, idd, host_z=zp)
+    got = plan.run_host(zp)
+    assert torch.equal(ref["aps"], got["aps"]) and torch.equal(ref["r1s"], got["r1s"])
+    # a run on OTHER embeddings ignores the early upload ...
+    z2 = (s["z"] * 0.5 + 0.1).pin_memory()
+    plan2 = we.EvalPlan(cd, idd, cd, idd, host_z=zp)
+    got2 = plan2.run_host(z2)
+    z2d = z2.cuda()
+    ref2 = ref_plan.run(z2d, z2d)
+    assert torch.equal(ref2["aps"], got2["aps"])
+    # ... and so does the device route; a plan that is never run is torn down cleanly
+    got3 = we.EvalPlan(cd, idd, cd, idd, host_z=zp).run(zd, zd)
+    assert torch.equal(ref["aps"], got3["aps"])
+    we.EvalPlan(cd, idd, cd, idd, host_z=zp).close()
+    torch.cuda.synchronize()
+    for pl in (ref_plan, plan, plan2):
+        pl.close()
