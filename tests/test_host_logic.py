@@ -125,3 +125,21 @@ def test_bench_arms_share_one_config():
         assert a == b and a["tracks"] == n and a["n_gpus"] == world and "workload" in a
     synth = bench.load_synth()
     assert hasattr(synth, "make_eval_set")
+
+
+def test_host_route_is_only_offered_for_one_pinned_matrix(monkeypatch):
+    """evaluate() hands embeddings to wealy_eval_run_host only when the device can read them itself: ONE pinned host
+    matrix on both sides, big enough for the pipeline to pay; everything else keeps copy-then-compute.  (No GPU here:
+    pageable tensors cover the refusals; the accepting side runs in tests/test_gpu_eval_host.py.)"""
+    import torch
+    from wealy_b200.evaluation import _host_streamable
+    monkeypatch.setenv("WEALY_HOST_STREAM_MIN_ROWS", "8")
+    c, i = torch.arange(16) // 2, torch.arange(16)
+    z = torch.randn(16, 32)
+    assert not _host_streamable(c, i, z, c, i, z)                       # pageable memory
+    assert not _host_streamable(c, i, z, c, i, z.clone())               # two matrices
+    assert not _host_streamable(c, i, z, c.clone(), i, z)               # two id sets
+    assert not _host_streamable(c, i, z.numpy(), c, i, z.numpy())       # not a tensor
+    assert not _host_streamable(c, i, z[:, :30], c, i, z[:, :30])       # rows of 30 elements
+    monkeypatch.setenv("WEALY_HOST_STREAM", "0")
+    assert not _host_streamable(c, i, z, c, i, z)
