@@ -1553,7 +1553,11 @@ static int host_upload_setup(HostUpload& h, const void* host_z, int64_t ld, int6
   h.up_sms = std::min(std::max(env_int("WEALY_HOST_UP_SMS", 8), 0), num_sms() / 2);
   h.smem = h.up_sms > 0 ? 120 * 1024 : 0;
   h.grid = h.up_sms > 0 ? h.up_sms : num_sms() * std::max(1, env_int("WEALY_HOST_UP_GRID", 1));
-  h.threads = h.up_sms > 0 ? 512 : (env_int("WEALY_HOST_UP_THREADS", 64) <= 32 ? 32 : 64);
+  if (h.up_sms > 0) {
+    h.threads = std::min(512, std::max(32, env_int("WEALY_HOST_UP_THREADS", 512) / 32 * 32));  // (bytes in flight per upload SM)
+  } else {
+    h.threads = env_int("WEALY_HOST_UP_THREADS", 64) <= 32 ? 32 : 64;
+  }
   const void* up_kernel =
       h.up_sms > 0 ? (dtype == WEALY_F32 ? (const void*)prep_rows_stream_kernel<float, 512>
                       : dtype == WEALY_F16 ? (const void*)prep_rows_stream_kernel<__half, 512>
@@ -1609,13 +1613,31 @@ static int host_planes(wealy_eval_plan* p, int64_t d, int passes, cudaStream_t s
 }
 
 // parts of a host run, in super row blocks (256 rows) counted from the END: cumulative fractions of the rows
-static const float kHostCum[4][8] = {{1.f}, {0.30f, 1.f}, {0.10f, 0.20f, 0.35f, 0.55f, 1.f}, {0.06f, 0.14f, 0.24f, 0.36f, 0.5f, 0.7f, 1.f}};
-static const int kHostCount[4] = {1, 2, 5, 7};
+static float kHostCum[5][8] = {{1.f}, {0.30f, 1.f}, {0.10f, 0.20f, 0.35f, 0.55f, 1.f}, {0.06f, 0.14f, 0.24f, 0.36f, 0.5f, 0.7f, 1.f}, {1.f}};
+static int kHostCount[5] = {1, 2, 5, 7, 1};
 static int host_preset(int64_t n) {
   const int nsb = (int)ceil_div(n, 2 * kTileM);
   int preset = nsb >= 96 ? 2 : (nsb >= 24 ? 1 : 0);  // (24 k / 6 k rows)
   const int forced = env_int("WEALY_HOST_PARTS", 0);
   if (forced > 0) preset = forced >= 7 ? 3 : (forced >= 5 ? 2 : (forced >= 2 ? 1 : 0));
+  // WEALY_HOST_CUM="0.1,0.25,0.5" (tuning): a schedule of its own, up to 7 increasing fractions; 1.0 is appended
+  if (const char* cum = getenv("WEALY_HOST_CUM")) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    int cnt = 0;
+    float last = 0.f;
+    for (const char* q = cum; *q && cnt < 7;) {
+      char* end = nullptr;
+      const float v = strtof(q, &end);
+      if (end == q) break;
+      if (v > last && v < 1.f) kHostCum[4][cnt++] = last = v;
+      q = *end == ',' ? end + 1 : end;
+      if (*end != ',' && *end != 0) break;
+    }
+    kHostCum[4][cnt++] = 1.f;
+    kHostCount[4] = cnt;
+    preset = 4;
+  }
   return preset;
 }
 // first super row block of part k

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--parts", default="0,1,2,5,7")
     ap.add_argument("--only-host", action="store_true", help="skip the copy-then-compute runs (for a profiler to attach to)")
+    ap.add_argument("--sweep", default="", help='";"-separated settings, each "VAR=value&VAR=value" (WEALY_HOST_* knobs), timed in turn')
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     s = synth.make_eval_set(args.tracks, args.dim, seed=0, device=dev, md5_ids=False)
@@ -64,6 +65,24 @@ def main():
         out["runs"].append({"mode": mode, "route": we.last_path(), "ms_per_step": ms,
                             "gpairs_per_s": args.tracks * args.tracks / ms / 1e6,
                             "identical_to_copy_path": bool(torch.equal(a, ref)), "map": float(a.double().mean())})
+    if args.sweep:
+        os.environ["WEALY_HOST_STREAM"] = "1"
+        os.environ.pop("WEALY_HOST_PARTS", None)
+        out["sweep"] = []
+        for rep in range(2):
+            for setting in args.sweep.split(";"):
+                kv = dict(t.split("=", 1) for t in setting.split("&") if t)
+                for k_, v_ in kv.items():
+                    os.environ[k_] = v_
+                step()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    step()
+                ms = (time.perf_counter() - t0) * 1e3 / args.steps
+                out["sweep"].append({"setting": setting, "rep": rep, "ms_per_step": ms, "identical": bool(torch.equal(aps_h, ref))})
+                for k_ in kv:
+                    os.environ.pop(k_, None)
     print(json.dumps(out))
 
 
