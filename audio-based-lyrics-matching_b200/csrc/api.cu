@@ -1484,7 +1484,7 @@ extern "C" int wealy_eval_run(wealy_eval_plan* p, const void* queries_z, int64_t
 // All-vs-all evaluation of embeddings that still live in PINNED HOST memory: upload, normalisation and the symmetric
 // sweep as one pipeline.  The sweep runs in the plan's clique-sorted row order and a super row block only needs the
 // rows BEHIND it (tiles above the diagonal), so the rows are fetched from the end: part by part a small persistent
-// kernel (prep_rows_stream_kernel, on its own stream, resident next to the sweep's CTAs) reads the caller's rows over
+// kernel (prep_rows_stream_kernel, on its own stream and on a few SMs of its own) reads the caller's rows over
 // PCIe in sorted order -- a gather no copy engine can do --, and as soon as a part has arrived its relevant
 // similarities (K_pos) and its row blocks of the sweep run on the caller's stream while the next part is in flight.
 // Parts grow towards the front: the work of a part grows with the square of the rows behind it.
