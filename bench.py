@@ -766,6 +766,10 @@ def run_gpu_arm(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_ms, "api": e2e_api, "route": e2e_route,
+                "route_note": None if e2e_route != "host_stream" else (
+                    "wealy_eval_run_host: the h2d bytes are read from the pinned buffers by an upload kernel on 8 SMs (rows gathered "
+                    "in the plan's sorted order, from the end) INSIDE the timed call, while the symmetric sweep runs over the rows "
+                    "that have arrived; results bit-identical to the copy-then-compute route timed beside it"),
                 "copy_then_compute": None if copy_ms is None else {
                     "ms_per_step": copy_ms, "value": pairs_total / (copy_ms * 1e-3) / 1e9, "unit": UNIT,
                     "note": "the same call with WEALY_HOST_STREAM=0: cudaMemcpyAsync of the embeddings on a side stream, then the resident path"},
